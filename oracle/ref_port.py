@@ -1,0 +1,359 @@
+"""ORACLE — test infrastructure, NOT product code.
+
+CPU restatement (numpy / torch-CPU) of the reference's cross-modal correspondence
+path, op for op, so that every float->int decision rounds exactly as the reference's
+numpy does.  Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s CPU-baseline /
+`--impl reference` legs may import this module; the product package
+(`xmask3d_b200`) never does.
+
+Parity status: the reference ships no golden vectors for this path, so
+this port is pinned against outputs of the reference's own functions executed in the
+build container — `tests/golden/make_golden.py` imports them from /root/reference and
+writes `tests/golden/*.npz`; `tests/test_oracle_golden.py` replays them.
+
+Each function cites the reference lines it follows (paths relative to /root/reference).
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+FNV_OFFSET = np.uint64(14695981039346656037)
+FNV_PRIME = np.uint64(1099511628211)
+
+
+# --------------------------------------------------------------------------- stage 1
+def fnv_hash_vec(arr: np.ndarray) -> np.ndarray:
+    """dataset/voxelization_utils.py:6-18 — FNV-1 over whole uint64 words per row."""
+    assert arr.ndim == 2
+    words = arr.astype(np.uint64)
+    h = np.full(words.shape[0], FNV_OFFSET, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        for j in range(words.shape[1]):
+            h = h * FNV_PRIME
+            h = h ^ words[:, j]
+    return h
+
+
+def ravel_hash_vec(arr: np.ndarray) -> np.ndarray:
+    """dataset/voxelization_utils.py:21-35 — mixed-radix ravel after min-subtract."""
+    assert arr.ndim == 2
+    shifted = (arr - arr.min(0)).astype(np.uint64)
+    radix = shifted.max(0).astype(np.uint64) + np.uint64(1)
+    key = np.zeros(shifted.shape[0], dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        for j in range(shifted.shape[1] - 1):
+            key = (key + shifted[:, j]) * radix[j + 1]
+        key = key + shifted[:, -1]
+    return key
+
+
+def sparse_quantize(coords, feats=None, labels=None, ignore_label=255,
+                    set_ignore_label_when_collision=False, return_index=False,
+                    hash_type="fnv", quantization_size=1):
+    """dataset/voxelization_utils.py:38-102."""
+    has_lab, has_feat = labels is not None, feats is not None
+    if not has_lab and not has_feat:
+        return_index = True
+    assert hash_type in ("ravel", "fnv"), \
+        "Invalid hash_type. Either ravel, or fnv allowed. You put hash_type=" + hash_type
+    assert coords.ndim == 2, \
+        "The coordinates must be a 2D matrix. The shape of the input is " + str(coords.shape)
+    if has_feat:
+        assert feats.ndim == 2 and coords.shape[0] == feats.shape[0]
+    if has_lab:
+        assert coords.shape[0] == len(labels)
+    dim = coords.shape[1]
+    if np.isscalar(quantization_size):
+        q = [quantization_size] * dim
+    elif isinstance(quantization_size, (list, tuple, np.ndarray)) or hasattr(quantization_size, "__len__"):
+        assert len(quantization_size) == dim, "Quantization size and coordinates size mismatch."
+        q = [v for v in quantization_size]
+    else:
+        raise ValueError("Not supported type for quantization_size.")
+    cells = np.floor(coords / np.array(q))
+    key = ravel_hash_vec(cells) if hash_type == "ravel" else fnv_hash_vec(cells)
+    if has_lab:
+        _, first, cnt = np.unique(key, return_index=True, return_counts=True)
+        lab = labels[first]
+        if set_ignore_label_when_collision:
+            lab[cnt > 1] = ignore_label
+        if return_index:
+            return first, lab
+        return cells[first], feats[first], lab
+    _, first, inverse = np.unique(key, return_index=True, return_inverse=True)
+    if return_index:
+        return first, inverse
+    if has_feat:
+        return cells[first], feats[first]
+    return cells[first]
+
+
+def axis_rotation(axis: np.ndarray, theta: float) -> np.ndarray:
+    """dataset/voxelizer.py:7-8 — expm of the skew matrix of the scaled axis."""
+    from scipy.linalg import expm, norm
+    return expm(np.cross(np.eye(3), axis / norm(axis) * theta))
+
+
+class Voxelizer:
+    """dataset/voxelizer.py:11-132 (ctor :12-30)."""
+
+    def __init__(self, voxel_size=1, clip_bound=None, use_augmentation=False,
+                 scale_augmentation_bound=None, rotation_augmentation_bound=None,
+                 translation_augmentation_ratio_bound=None, ignore_label=255):
+        self.voxel_size = voxel_size
+        self.clip_bound = clip_bound
+        self.ignore_label = ignore_label
+        self.use_augmentation = use_augmentation
+        self.scale_augmentation_bound = scale_augmentation_bound
+        self.rotation_augmentation_bound = rotation_augmentation_bound
+        self.translation_augmentation_ratio_bound = translation_augmentation_ratio_bound
+
+    def get_transformation_matrix(self):
+        """:32-58 — same np.random draw order: 3x uniform, shuffle, 1x uniform."""
+        m_vox, m_rot = np.eye(4), np.eye(4)
+        rot = np.eye(3)
+        if self.use_augmentation and self.rotation_augmentation_bound is not None:
+            if not hasattr(self.rotation_augmentation_bound, "__iter__"):
+                raise ValueError()
+            mats = []
+            for ax, bound in enumerate(self.rotation_augmentation_bound):
+                theta = 0
+                axis = np.zeros(3)
+                axis[ax] = 1
+                if bound is not None:
+                    theta = np.random.uniform(*bound)
+                mats.append(axis_rotation(axis, theta))
+            np.random.shuffle(mats)
+            rot = mats[0] @ mats[1] @ mats[2]
+        m_rot[:3, :3] = rot
+        scale = 1 / self.voxel_size
+        if self.use_augmentation and self.scale_augmentation_bound is not None:
+            scale *= np.random.uniform(*self.scale_augmentation_bound)
+        np.fill_diagonal(m_vox[:3, :3], scale)
+        return m_vox, m_rot
+
+    def clip(self, coords, center=None, trans_aug_ratio=None):
+        """:60-79."""
+        lo = np.min(coords, 0).astype(float)
+        hi = np.max(coords, 0).astype(float)
+        size = hi - lo
+        if center is None:
+            center = lo + size * 0.5
+        if trans_aug_ratio is not None:
+            center += np.multiply(trans_aug_ratio, size)
+        lim = self.clip_bound
+        keep = np.ones(coords.shape[0], dtype=bool)
+        for a in range(3):
+            keep &= (coords[:, a] >= (lim[a][0] + center[a])) & (coords[:, a] < (lim[a][1] + center[a]))
+        return keep
+
+    def rigid_transformation(self):
+        m_vox, m_rot = self.get_transformation_matrix()
+        rt = m_vox
+        if self.use_augmentation:
+            rt = m_rot @ rt
+        return rt, m_rot
+
+    def voxelize(self, coords, feats, labels, center=None, link=None, return_ind=False, _rt=None):
+        """:81-132.  `_rt=(RT, M_r)` injects the matrices instead of drawing them."""
+        assert coords.shape[1] == 3 and coords.shape[0] == feats.shape[0] and coords.shape[0]
+        if self.clip_bound is not None:
+            ratio = np.zeros(3)
+            if self.use_augmentation and self.translation_augmentation_ratio_bound is not None:
+                for ax, b in enumerate(self.translation_augmentation_ratio_bound):
+                    ratio[ax] = np.random.uniform(*b)
+            keep = self.clip(coords, center, ratio)
+            if keep.sum():
+                coords, feats = coords[keep], feats[keep]
+                if labels is not None:
+                    labels = labels[keep]
+        rt, m_rot = self.rigid_transformation() if _rt is None else _rt
+        homo = np.hstack((coords, np.ones((coords.shape[0], 1), dtype=coords.dtype)))
+        grid = np.floor(homo @ rt.T[:, :3])
+        grid = np.floor(grid - grid.min(0))
+        first, inverse = sparse_quantize(grid, return_index=True)
+        grid, feats, labels = grid[first], feats[first], labels[first]
+        if feats.shape[1] > 6:
+            feats[:, 3:6] = feats[:, 3:6] @ (m_rot[:3, :3].T)
+        if return_ind:
+            return grid, feats, labels, np.array(inverse), first
+        if link is not None:
+            return grid, feats, labels, np.array(inverse), link[first]
+        return grid, feats, labels, np.array(inverse)
+
+
+# --------------------------------------------------------------------------- stage 2
+def make_intrinsic(fx, fy, mx, my):
+    """models/utils/fusion_util.py:7-15."""
+    k = np.eye(4)
+    k[0][0], k[1][1], k[0][2], k[1][2] = fx, fy, mx, my
+    return k
+
+
+def adjust_intrinsic(intrinsic, intrinsic_image_dim, image_dim):
+    """models/utils/fusion_util.py:18-33."""
+    if intrinsic_image_dim == image_dim:
+        return intrinsic
+    rw = int(math.floor(image_dim[1] * float(intrinsic_image_dim[0]) / float(intrinsic_image_dim[1])))
+    intrinsic[0, 0] *= float(rw) / float(intrinsic_image_dim[0])
+    intrinsic[1, 1] *= float(image_dim[1]) / float(intrinsic_image_dim[1])
+    intrinsic[0, 2] *= float(image_dim[0] - 1) / float(intrinsic_image_dim[0] - 1)
+    intrinsic[1, 2] *= float(image_dim[1] - 1) / float(intrinsic_image_dim[1] - 1)
+    return intrinsic
+
+
+class PointCloudToImageMapper:
+    """models/utils/fusion_util.py:36-142."""
+
+    def __init__(self, image_dim, visibility_threshold=0.25, cut_bound=0, intrinsics=None):
+        self.image_dim = image_dim
+        self.vis_thres = visibility_threshold
+        self.cut_bound = cut_bound
+        self.intrinsics = intrinsics
+
+    def compute_mapping(self, camera_to_world, coords, depth=None, intrinsic=None):
+        """:46-142 — returns int64 [N,3] rows (pixel row, pixel col, visible)."""
+        if self.intrinsics is not None:
+            intrinsic = self.intrinsics
+        n = coords.shape[0]
+        out = np.zeros((3, n), dtype=int)
+        homo = np.concatenate([coords, np.ones([n, 1])], axis=1).T
+        assert homo.shape[0] == 4, "[!] Shape error"
+        w2c = np.linalg.inv(camera_to_world)
+        p = np.matmul(w2c, homo)
+        zdiv = p[2].copy()
+        zdiv[np.abs(zdiv) < 1e-8] = 1.0
+        px = (p[0] * intrinsic[0][0]) / zdiv + intrinsic[0][2]
+        py = (p[1] * intrinsic[1][1]) / zdiv + intrinsic[1][2]
+        ix = np.round(px).astype(int)
+        iy = np.round(py).astype(int)
+        cut = self.cut_bound
+        keep = (p[2] > 0) & (ix >= cut) & (iy >= cut) & \
+               (ix < self.image_dim[0] - cut) & (iy < self.image_dim[1] - cut)
+        if depth is not None and np.any(keep):
+            ky, kx, kz = iy[keep], ix[keep], p[2][keep]
+            in_depth = (ky >= 0) & (ky < depth.shape[0]) & (kx >= 0) & (kx < depth.shape[1])
+            if np.any(in_depth):
+                d = depth[ky[in_depth], kx[in_depth]]
+                ok = np.abs(d - kz[in_depth]) <= self.vis_thres * d
+                survivors = np.where(keep)[0][in_depth][ok]
+                keep = np.zeros_like(keep)
+                keep[survivors] = True
+        out[0, keep] = iy[keep]
+        out[1, keep] = ix[keep]
+        out[2, keep] = 1
+        return out.T
+
+
+def getMapping():
+    """models/utils/mapping_util.py:10-39 (without the RNG reseeding side effect)."""
+    k = adjust_intrinsic(make_intrinsic(577.870605, 577.870605, 319.5, 239.5), [640, 480], (320, 240))
+    return PointCloudToImageMapper(image_dim=(320, 240), intrinsics=k,
+                                   visibility_threshold=0.25, cut_bound=10)
+
+
+def compact_mapping(mapping: np.ndarray):
+    """Caller-side compaction, dataset/data_loader_infer.py:176-182, 263-268:
+    visible mask, rows whose three entries are all non-zero, row/col lists."""
+    vis = mapping[:, 2]
+    nz = np.all(mapping != 0, axis=1)
+    kept = mapping[nz]
+    x_label = kept[:, 0][kept[:, 0] != 0]
+    y_label = kept[:, 1][kept[:, 1] != 0]
+    return vis == 1, x_label, y_label
+
+
+# --------------------------------------------------------------------------- stage 3
+def gather_masks(mask, x_label, y_label, mode: str):
+    """Mask-at-point gather + threshold.
+      mode "ge0.5"          models/utils/fuser.py:16-17       (mask >= 0.5)
+      mode "sigmoid_ge0.5"  models/utils/criterion.py:83-85   (sigmoid(mask) >= 0.5)
+      mode "sigmoid_gt0.5"  models/xmask3d.py:356-357         (sigmoid(mask) >  0.5)
+    mask: torch [K,H,W]; x_label = pixel row, y_label = pixel col (int64). -> bool [K,n]."""
+    m = mask[:, x_label, y_label].clone()
+    if mode == "ge0.5":
+        return m >= 0.5
+    if mode == "sigmoid_ge0.5":
+        return m.sigmoid() >= 0.5
+    if mode == "sigmoid_gt0.5":
+        return m.sigmoid() > 0.5
+    raise ValueError(mode)
+
+
+def scatter_mask_embed(member, mask_embed, n_rows_like):
+    """models/utils/fuser.py:22-34 (twin: models/xmask3d.py:441-455): mask -> point
+    scatter-mean.  member bool [K,n], mask_embed [K,C], returns (feat2d [n,C], counter [n,1])
+    where counter already has the 0 -> 1e-5 replacement applied."""
+    import torch
+    member = member.clone()
+    if len(member[torch.sum(member, dim=1) != 0]) == 0:
+        member[0][0] = True                                    # fuser.py:19-20
+    counter = torch.zeros((n_rows_like.shape[0], 1))
+    acc = torch.zeros_like(n_rows_like)
+    for row, emb in zip(member, mask_embed):
+        if torch.sum(row) == 0:
+            continue
+        acc[row] += emb
+        counter[row] += 1
+    counter[counter == 0] = 1e-5
+    return acc / counter, counter
+
+
+def masked_mean_pool(feat, member):
+    """models/utils/criterion.py:152-157: per mask `feat[member_k].mean(0)`.
+    feat torch [n,C] f32, member bool [K,n] -> (mean [K,C] f32, cnt [K] int64).
+    Empty masks give NaN rows in torch; we return zeros for them and cnt 0."""
+    import torch
+    k, c = member.shape[0], feat.shape[1]
+    out = torch.zeros(k, c, dtype=feat.dtype)
+    cnt = member.sum(1)
+    for i in range(k):
+        if cnt[i] > 0:
+            out[i] = torch.mean(feat[member[i]], dim=0)
+    return out, cnt
+
+
+def masked_score_pool(scores, member):
+    """models/xmask3d.py:362-367: sum(score*mask)/(sum(mask)+1e-10) per mask."""
+    import torch
+    s = scores.view(1, -1) * member
+    return torch.sum(s, dim=1) / (torch.sum(member, dim=1) + 1e-10)
+
+
+def masked_sum_f64(feat: np.ndarray, member: np.ndarray):
+    """High-precision truth for the tolerance tests: fp64 sums per mask."""
+    m = member.astype(np.float64)
+    return m @ feat.astype(np.float64), member.sum(1).astype(np.int64)
+
+
+# --------------------------------------------------------------------------- stage 4
+def ensemble_logits_with_labels(logits, labels: List[List[str]], ensemble_method: str = "max"):
+    """models/modeling/meta_arch/helper.py:72-97."""
+    import torch
+    sizes = [len(g) for g in labels]
+    assert logits.shape[-1] == sum(sizes), f"{logits.shape[-1]} != {sum(sizes)}"
+    assert ensemble_method in ["mean", "max"]
+    out = torch.zeros(*logits.shape[:-1], len(labels), dtype=logits.dtype)
+    start = 0
+    for i, s in enumerate(sizes):
+        chunk = logits[..., start:start + s]
+        out[..., i] = chunk.max(dim=-1).values if ensemble_method == "max" else chunk.mean(dim=-1)
+        start += s
+    return out
+
+
+def cal_pred_logits(outputs: dict):
+    """models/xmask3d.py:129-143."""
+    import torch
+    import torch.nn.functional as F
+    me = F.normalize(outputs["mask_embed"], dim=-1)
+    te = F.normalize(outputs["text_embed"], dim=-1)
+    scale = outputs["logit_scale"]
+    pred = scale * (me @ te.t())
+    pred = ensemble_logits_with_labels(pred, outputs["labels"], ensemble_method="max")
+    ne = F.normalize(outputs["null_embed"], dim=-1)
+    null = scale * (me @ ne.t())
+    return torch.cat([pred, null], dim=-1)
