@@ -1,0 +1,203 @@
+/* xm3d.h — C ABI of libxm3d.so: the B200-native (sm_100a) cross-modal correspondence path
+ * of XMask3D (voxelize -> project+occlusion -> mask gather/pool/scatter -> text logits).
+ *
+ * The reference (Zifeng-Zhang/XMask3D) has no FFI layer on this path: its boundary is a set
+ * of Python call signatures.  Every entry point below names the reference call it replaces
+ * (paths relative to the reference tree); the Python shims in xmask3d_b200/ keep those
+ * signatures and call this ABI through ctypes.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless its name ends
+ *     in `_host`.  The caller owns all buffers (allocate them with torch / cudaMalloc).
+ *   - all work is enqueued on `stream` (a cudaStream_t); no call synchronises the device.
+ *     Data-dependent sizes (visible counts, voxel counts) are written to device memory.
+ *   - return value: XM3D_OK or a negative xm3d_status; xm3d_last_error() has the text.
+ *   - `status` (device int32, may be NULL): kernels OR XM3D_FLAG_* bits into it when a
+ *     caller-provided capacity was too small; outputs are then truncated, never overrun.
+ *   - batched layout: a batch is a list of `segments` (one per (scene, view)); per-point
+ *     arrays of all segments are concatenated and addressed through offset arrays.
+ *   - no CPU fallback exists: without a CUDA device every compute call fails.
+ */
+#ifndef XM3D_H_
+#define XM3D_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XM3D_VERSION 100
+
+#if defined(__GNUC__)
+#define XM3D_API __attribute__((visibility("default")))
+#else
+#define XM3D_API
+#endif
+
+typedef void *xm3d_stream_t; /* cudaStream_t */
+
+typedef enum {
+    XM3D_OK = 0,
+    XM3D_ERR_BAD_ARG = -1,
+    XM3D_ERR_WORKSPACE = -2, /* workspace smaller than the matching *_ws_bytes() */
+    XM3D_ERR_CUDA = -3,
+    XM3D_ERR_UNSUPPORTED = -4
+} xm3d_status;
+
+#define XM3D_FLAG_VIS_OVERFLOW 1   /* more visible points than cap_vis          */
+#define XM3D_FLAG_PAIR_OVERFLOW 2  /* more (point,mask) pairs than cap_pairs    */
+#define XM3D_FLAG_GRID_RANGE 4     /* voxel coordinate outside +-2^30           */
+#define XM3D_FLAG_KEY_SENTINEL 8   /* a key equal to 2^64-1 was remapped        */
+
+/* depth image element type */
+#define XM3D_DEPTH_NONE 0
+#define XM3D_DEPTH_U16 1 /* raw PNG units; metres = value / depth_scale (float64 division)  */
+#define XM3D_DEPTH_F64 2 /* metres, what the reference loader hands to compute_mapping      */
+
+/* mask threshold modes of the three reference call sites */
+#define XM3D_THR_GE_HALF 0         /* m >= 0.5            models/utils/fuser.py:16-17       */
+#define XM3D_THR_SIGMOID_GE_HALF 1 /* sigmoid(m) >= 0.5   models/utils/criterion.py:83-85   */
+#define XM3D_THR_SIGMOID_GT_HALF 2 /* sigmoid(m) >  0.5   models/xmask3d.py:356-357         */
+#define XM3D_MASK_U8 0             /* bool / uint8 masks  */
+#define XM3D_MASK_F32 1            /* float32 masks / logits */
+
+XM3D_API int xm3d_version(void);
+XM3D_API const char *xm3d_last_error(void);
+/* SM count, compute capability of the current device (XM3D_ERR_CUDA without a GPU). */
+XM3D_API int xm3d_device_info(int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor);
+
+/* ------------------------------------------------------------------ stage 2: projection
+ * Replaces PointCloudToImageMapper.compute_mapping (models/utils/fusion_util.py:46-142) and
+ * the caller-side compaction (dataset/data_loader_infer.py:174-182, 263-268), batched over
+ * views.  One record per view, 192 bytes, 16-byte aligned (staged into shared memory with a
+ * bulk async copy). */
+typedef struct xm3d_view {
+    double w2c[12];    /* rows 0..2 of world_to_camera = np.linalg.inv(pose), row-major 3x4  */
+    double fx, fy, cx, cy;
+    int64_t pt_off;    /* first point of this view's scene in `xyz` (points, not floats)      */
+    int64_t out_off;   /* first element of this view in the per-(view,point) outputs          */
+    int64_t depth_off; /* element offset of this view's depth image in `depth`, <0 = no depth */
+    int32_t n_pts;     /* points of the scene                                                 */
+    int32_t depth_h, depth_w;
+    int32_t reserved0;
+    int64_t reserved1[3];
+} xm3d_view_t;
+
+XM3D_API size_t xm3d_project_ws_bytes(int32_t n_views, int64_t total_pts, int32_t max_pts_per_view);
+
+/* views_host: HOST array of n_views records (the library uploads it on `stream`).
+ * For every view v and scene point i (i < views[v].n_pts):
+ *   vis[out_off+i]        1 if the point projects inside the cut image and passes the depth test
+ *   mapping[(out_off+i)*3 + {0,1,2}] = (pixel row, pixel col, vis)   (optional, the drop-in
+ *                          int64 [N,3] array of compute_mapping; zero rows when invisible)
+ * and the order-preserving compaction of the visible points of each view:
+ *   n_vis[v], vis_off[0..V]   counts and their exclusive prefix (vis_off[V] = total)
+ *   vis_idx[vis_off[v]+j]     index (within the scene) of the j-th visible point
+ *   rowcol[(vis_off[v]+j)*2]  pixel row (x_label), pixel col (y_label)
+ *   xyz_vis[(vis_off[v]+j)*3] its coordinates (locals_3d)
+ * Compacted outputs hold at most cap_vis points in total (XM3D_FLAG_VIS_OVERFLOW otherwise).
+ * vis_idx / rowcol / xyz_vis / mapping may be NULL.  total_pts = sum of n_pts over views
+ * (size of vis).  depth: uint16 raw units (metres = value / depth_scale, float64 division — the
+ * loader's imread(png)/1000, dataset/data_loader_infer.py:168-171) or float64 metres. */
+XM3D_API int xm3d_project_batch(const float *xyz, const xm3d_view_t *views_host, int32_t n_views,
+                       int64_t total_pts, const void *depth, int32_t depth_kind, double depth_scale,
+                       int32_t img_w, int32_t img_h, int32_t cut_bound, double vis_thres,
+                       uint8_t *vis, int64_t *mapping, int32_t *n_vis, int64_t *vis_off,
+                       int64_t cap_vis, int32_t *vis_idx, int32_t *rowcol, float *xyz_vis,
+                       void *ws, size_t ws_bytes, int32_t *status, xm3d_stream_t stream);
+
+/* ------------------------------------------------------------------ stage 1: voxelization
+ * xm3d_unique_batch replaces np.unique(key, return_index, return_inverse, return_counts) as
+ * used by sparse_quantize (dataset/voxelization_utils.py:86, :95): per segment, unique keys in
+ * ascending order, index of the first occurrence, rank of every element, multiplicity.
+ * Segment s owns elements [seg_off[s], seg_off[s+1]) of `keys`; seg_off is a DEVICE int64
+ * [n_seg+1] array (seg_off[0] = 0) so a projection can feed it without a host round trip;
+ * `cap` is the host-known bound on seg_off[n_seg] (all per-element buffers hold cap entries;
+ * if the bound is exceeded XM3D_FLAG_VIS_OVERFLOW is raised and nothing is processed).
+ *   m[s], uniq_off[0..n_seg]  unique count per segment and exclusive prefix
+ *   first[uniq_off[s]+r]      index within the segment of the first occurrence of rank r
+ *   counts[uniq_off[s]+r]     multiplicity (optional)
+ *   inverse[seg_off[s]+i]     rank of element i (+ uniq_off[s] if collate != 0, the
+ *                             cumulative offset collation_fn adds, dataset/data_loader.py:341-342) */
+XM3D_API size_t xm3d_unique_ws_bytes(int32_t n_seg, int64_t cap);
+XM3D_API int xm3d_unique_batch(const uint64_t *keys, const int64_t *seg_off, int32_t n_seg, int64_t cap,
+                      int32_t *m, int64_t *uniq_off, int32_t *first, int32_t *counts,
+                      int32_t *inverse, int32_t collate, void *ws, size_t ws_bytes,
+                      int32_t *status, xm3d_stream_t stream);
+
+/* FNV-1 over whole 64-bit words per row (fnv_hash_vec, dataset/voxelization_utils.py:6-18)
+ * and the mixed-radix ravel key (ravel_hash_vec, :21-35) of float64 rows (dim <= 8 for ravel). */
+XM3D_API int xm3d_fnv_hash_f64(const double *coords, int64_t n, int32_t dim, uint64_t *keys, xm3d_stream_t stream);
+XM3D_API int xm3d_ravel_hash_f64(const double *coords, int64_t n, int32_t dim, uint64_t *keys, void *ws,
+                        size_t ws_bytes, xm3d_stream_t stream);
+XM3D_API size_t xm3d_ravel_ws_bytes(int32_t dim);
+
+/* Voxelizer.voxelize after the matrix is drawn (dataset/voxelizer.py:110-122) fused with
+ * sparse_quantize: grid = floor([x y z 1] @ RT.T[:, :3]); grid -= min; FNV key; unique.
+ *   xyz           [cap,3] float32, segments as above (e.g. xyz_vis / vis_off of the projection)
+ *   rt            [n_seg,12] float64: rows 0..2 of rigid_transformation per segment
+ *   grid_min      [n_seg,3] int32   column minima that were subtracted (optional)
+ *   voxel_xyz     [uniq_off[s]+r, 3] int32 voxel coordinates in unique order (grid[inds])
+ * other outputs as xm3d_unique_batch. */
+XM3D_API size_t xm3d_voxelize_ws_bytes(int32_t n_seg, int64_t cap);
+XM3D_API int xm3d_voxelize_batch(const float *xyz, const int64_t *seg_off, int32_t n_seg, int64_t cap,
+                        const double *rt, int32_t *m, int64_t *uniq_off, int32_t *first,
+                        int32_t *inverse, int32_t collate, int32_t *voxel_xyz, int32_t *grid_min,
+                        void *ws, size_t ws_bytes, int32_t *status, xm3d_stream_t stream);
+
+/* ------------------------------------------------------------------ stage 3: masks at points
+ * Mask-at-point gather + threshold (models/utils/fuser.py:16-17, models/utils/criterion.py:83-85,
+ * models/xmask3d.py:356-358).  masks: [n_seg, k, h, w] (uint8 or float32); rowcol as produced by
+ * xm3d_project_batch (row = x_label, col = y_label); seg_off / cap as in stage 1.
+ * member: per point xm3d_mask_words(k) = ceil(k/32) uint32 words, bit m%32 of word m/32 set iff
+ * the point is in mask m.  counts (optional): [n_seg,k] int32 points per mask.  k <= 256. */
+XM3D_API int32_t xm3d_mask_words(int32_t k);
+XM3D_API size_t xm3d_gather_ws_bytes(int32_t n_seg, int32_t k, int32_t h, int32_t w);
+XM3D_API int xm3d_gather_masks_batch(const void *masks, int32_t mask_kind, int32_t thr_mode, int32_t n_seg,
+                            int32_t k, int32_t h, int32_t w, const int32_t *rowcol,
+                            const int64_t *seg_off, int64_t cap, uint32_t *member, int32_t *counts,
+                            void *ws, size_t ws_bytes, xm3d_stream_t stream);
+
+/* Segmented mean pooling of per-point features under each mask (models/utils/criterion.py:148-157;
+ * scalar form models/xmask3d.py:362-367 with c = 1).
+ *   feat      [rows, c] float32;  row_index (optional int32 [cap]) maps point -> feature row
+ *             (e.g. inds_reconstruct, fusing pred_3d[inds_reconstruct], models/xmask3d.py:152)
+ *   member    as produced by xm3d_gather_masks_batch (general, overlapping masks) OR
+ *   label     int32 [cap], values outside [0,k) = in no mask (partition masks); exactly one of the two
+ *   sum [n_seg,k,c] float32, cnt [n_seg,k] int32 (optional), mean (optional) [n_seg,k,c] = sum/cnt
+ *   (0 where cnt = 0).  Deterministic: partial sums are combined in a fixed order. */
+XM3D_API size_t xm3d_pool_ws_bytes(int32_t n_seg, int32_t k, int32_t c);
+XM3D_API int xm3d_pool_batch(const float *feat, int32_t c, const int32_t *row_index, const uint32_t *member,
+                    const int32_t *label, int32_t n_seg, int32_t k, const int64_t *seg_off, int64_t cap,
+                    float *sum, int32_t *cnt, float *mean, void *ws, size_t ws_bytes, int32_t *status,
+                    xm3d_stream_t stream);
+
+/* Mask -> point scatter-mean (mask_mapper, models/utils/fuser.py:22-34; twin
+ * models/xmask3d.py:441-455): out[i,:] = (sum of emb[m,:] over masks m containing i, ascending m)
+ * / counter_i, counter 0 -> 1e-5; bit-exact with the reference's float32 op order.
+ *   emb [n_seg,k,c], out [cap,c], counter (optional) [cap] float32 */
+XM3D_API int xm3d_scatter_batch(const uint32_t *member, const int32_t *label, int32_t n_seg, int32_t k,
+                       const int64_t *seg_off, int64_t cap, const float *emb, int32_t c, float *out,
+                       float *counter, xm3d_stream_t stream);
+
+/* ------------------------------------------------------------------ stage 4: text logits
+ * XMASK3d.cal_pred_logits (models/xmask3d.py:129-143) + ensemble_logits_with_labels
+ * (models/modeling/meta_arch/helper.py:72-97, "max" or "mean"):
+ *   out[r, g] = reduce_{t in group g} scale * <mask_embed[r]/|.|, text_embed[t]/|.|>,
+ *   out[r, n_groups] = scale * <mask_embed[r]/|.|, null_embed/|.|>
+ * rows = B*K mask embeddings [rows,c]; text_embed [n_text,c]; group_off_host: HOST [n_groups+1]
+ * column offsets of the synonym groups; out [rows, n_groups+1]; argmax (optional) int32 [rows].
+ * n_text + 1 <= 256, c % 4 == 0, every group non-empty.
+ * The contraction runs on the tensor cores (tcgen05, 3xTF32 split, fp32 accumulate in TMEM). */
+XM3D_API size_t xm3d_logits_ws_bytes(int64_t rows, int32_t n_text, int32_t c, int32_t n_groups);
+XM3D_API int xm3d_logits(const float *mask_embed, int64_t rows, int32_t c, const float *text_embed,
+                int32_t n_text, const float *null_embed, const int32_t *group_off_host,
+                int32_t n_groups, int32_t ensemble_mean, float logit_scale, float *out,
+                int32_t *argmax, void *ws, size_t ws_bytes, xm3d_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XM3D_H_ */

@@ -1,0 +1,360 @@
+"""Parity of the CUDA path (through the C ABI) against (a) the golden fixtures produced by the
+reference's own functions and (b) the CPU oracle on seeded synthetic inputs.
+
+Bars: bit-exact for every integer / index / visibility output and for the float32 scatter-mean;
+pooled features within 1e-5 (vector-wise max|a-b| / max|b| per mask, float32); identical logits
+argmax.  Needs a B200: run with `pytest -m gpu`.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from xmask3d_b200 import synthetic as syn
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda", 0)
+
+
+def _intr(k):
+    return (k[0, 0], k[1, 1], k[0, 2], k[1, 2])
+
+
+# ----------------------------------------------------------------------------- stage 2
+def test_project_golden(golden, dev):
+    from xmask3d_b200.fusion_util import PointCloudToImageMapper
+    from xmask3d_b200.mapping_util import getMapping
+    g = golden("project")
+    m = getMapping()
+    assert np.array_equal(m.intrinsics, g["intrinsics"])
+    poses, dmm = g["poses"], g["depth_mm"]
+    # float64 metres exactly as the loader hands them over (imread(png) / 1000)
+    got = m.compute_mapping_batch(list(poses), g["xyz"], [d / 1000 for d in dmm])
+    for v in range(poses.shape[0]):
+        assert got[v].dtype == np.int64 and np.array_equal(got[v], g["mapping"][v])
+    # raw uint16 millimetres (the fast path: depth image staged in shared memory)
+    got = m.compute_mapping_batch(list(poses), g["xyz"], list(dmm))
+    for v in range(poses.shape[0]):
+        assert np.array_equal(got[v], g["mapping"][v])
+    for v in range(poses.shape[0]):
+        assert np.array_equal(m.compute_mapping(poses[v], g["xyz"], None), g["mapping_nodepth"][v])
+    # depth image smaller than the camera image, cut_bound = 0 (fusion_util.py:105-135)
+    m0 = PointCloudToImageMapper((320, 240), 0.25, 0, g["intrinsics"])
+    sd = g["small_depth_mm"]
+    assert np.array_equal(m0.compute_mapping(poses[0], g["xyz"], sd / 1000), g["mapping_small_cut0"])
+    assert np.array_equal(m0.compute_mapping(poses[0], g["xyz"], sd), g["mapping_small_cut0"])
+
+
+def _scene_views(seed, n_points, n_views):
+    sc = syn.make_scene(seed, n_points)
+    return sc, [syn.make_view(sc, v) for v in range(n_views)]
+
+
+def test_project_vs_oracle_and_compaction(cport, dev):
+    from xmask3d_b200 import ops
+    intr = syn.scannet_intrinsics()
+    scenes = [_scene_views(77, 150_000, 3), _scene_views(78, 41_237, 2)]      # ragged sizes, unaligned tail
+    xyz = np.concatenate([s.xyz for s, _ in scenes])
+    pt_off, n_pts, w2c, depth = [], [], [], []
+    o = 0
+    for sc, views in scenes:
+        for vw in views:
+            pt_off.append(o)
+            n_pts.append(sc.xyz.shape[0])
+            w2c.append(np.linalg.inv(vw.pose))
+            depth.append(vw.depth_mm)
+        o += sc.xyz.shape[0]
+    views, out_off = ops.make_views(np.stack(w2c), intr, pt_off, n_pts, depth[0].shape)
+    dten = torch.from_numpy(np.stack(depth).view(np.int16)).to(dev)
+    pr = ops.project_batch(torch.from_numpy(xyz).to(dev), views, out_off, dten, want_mapping=True)
+    assert int(pr.status.item()) == 0
+    mapping = pr.mapping.cpu().numpy()
+    vis = pr.vis.cpu().numpy()
+    n_vis = pr.n_vis.cpu().numpy()
+    vis_off = pr.vis_off.cpu().numpy()
+    vis_idx, rowcol, xyz_vis = pr.vis_idx.cpu().numpy(), pr.rowcol.cpu().numpy(), pr.xyz_vis.cpu().numpy()
+    i = 0
+    for sc, vws in scenes:
+        for vw in vws:
+            ref = cport.project(sc.xyz, np.linalg.inv(vw.pose), intr, vw.depth_mm)
+            a, b = out_off[i], out_off[i + 1]
+            assert np.array_equal(mapping[a:b], ref), f"view {i}"
+            assert np.array_equal(vis[a:b], ref[:, 2].astype(np.uint8))
+            idx = np.nonzero(ref[:, 2])[0]
+            assert n_vis[i] == len(idx) and vis_off[i + 1] - vis_off[i] == len(idx)
+            s = slice(vis_off[i], vis_off[i + 1])
+            assert np.array_equal(vis_idx[s], idx)                      # point order preserved
+            assert np.array_equal(rowcol[s], ref[idx][:, :2])           # x_label (row), y_label (col)
+            assert np.array_equal(xyz_vis[s], sc.xyz[idx])
+            assert len(idx) > 400
+            i += 1
+    # capacity too small: flagged, never overrun
+    pr2 = ops.project_batch(torch.from_numpy(xyz).to(dev), views, out_off, dten, cap_vis=1000)
+    assert int(pr2.status.item()) & 1
+    assert np.array_equal(pr2.vis_idx.cpu().numpy()[:1000], vis_idx[:1000])
+
+
+def test_project_edge_cases(cport, dev):
+    from xmask3d_b200 import ops
+    intr = syn.scannet_intrinsics()
+    rng = np.random.default_rng(5)
+    # points behind the camera, at z ~ 0, NaN / inf coordinates, far outside the image
+    xyz = rng.uniform(-3, 3, (5000, 3)).astype(np.float32)
+    xyz[:50, 2] = 0.0
+    xyz[50:60] = np.nan
+    xyz[60:70] = np.inf
+    xyz[70:80] = -np.inf
+    xyz[80:90] = 1e30
+    pose = np.eye(4)
+    depth = np.full((240, 320), 2000, np.uint16)
+    views, out_off = ops.make_views(np.linalg.inv(pose)[None], intr, [0], [5000], depth.shape)
+    pr = ops.project_batch(torch.from_numpy(xyz).to(dev), views, out_off,
+                           torch.from_numpy(depth.view(np.int16)).to(dev), want_mapping=True)
+    with np.errstate(all="ignore"):
+        ref = cport.project(xyz, np.linalg.inv(pose), intr, depth)
+    assert np.array_equal(pr.mapping.cpu().numpy(), ref)
+    # a view that sees nothing and an empty scene
+    pose2 = np.eye(4)
+    pose2[2, 3] = 100.0
+    views, out_off = ops.make_views(np.stack([np.linalg.inv(pose2)]), intr, [0], [5000], depth.shape)
+    pr = ops.project_batch(torch.from_numpy(xyz).to(dev), views, out_off,
+                           torch.from_numpy(depth.view(np.int16)).to(dev))
+    assert int(pr.n_vis[0].item()) == 0 and int(pr.vis_off[1].item()) == 0
+    views, out_off = ops.make_views(np.stack([np.linalg.inv(pose)]), intr, [0], [0], depth.shape)
+    pr = ops.project_batch(torch.from_numpy(xyz).to(dev), views, out_off,
+                           torch.from_numpy(depth.view(np.int16)).to(dev))
+    assert int(pr.vis_off[1].item()) == 0
+
+
+# ----------------------------------------------------------------------------- stage 1
+def test_voxelize_golden(golden, dev):
+    from tests.golden.make_golden_params import vox_kwargs
+    from xmask3d_b200.voxelizer import Voxelizer, voxelize_views
+    g = golden("voxelize")
+    for tag in "abc":
+        grid, inds, inv = voxelize_views([g["xyz"]], [g[f"rt_{tag}"]])[0]
+        assert grid.dtype == np.float64 and np.array_equal(grid, g[f"grid_{tag}"])
+        assert np.array_equal(inds, g[f"inds_{tag}"]) and np.array_equal(inv, g[f"inv_{tag}"])
+        # the full reference signature, drawing the matrix from the same np.random state
+        np.random.seed(int(g[f"seed_{tag}"]))
+        vox = Voxelizer(**vox_kwargs(float(g[f"vs_{tag}"])))
+        grid, feats, labels, inv, inds = vox.voxelize(g["xyz"], g["colors"].copy(), g["labels"].copy(),
+                                                      return_ind=True)
+        assert np.array_equal(grid, g[f"grid_{tag}"]) and np.array_equal(inv, g[f"inv_{tag}"])
+        assert np.array_equal(inds, g[f"inds_{tag}"]) and inv.dtype == np.int64
+        assert np.array_equal(feats, g[f"feats_{tag}"]) and np.array_equal(labels, g[f"labels_{tag}"])
+    grid, _, _, inv = Voxelizer(voxel_size=0.04).voxelize(g["xyz"], g["colors"].copy(), g["labels"].copy())
+    assert np.array_equal(grid, g["grid_plain"]) and np.array_equal(inv, g["inv_plain"])
+    link = np.arange(g["xyz"].shape[0]) * 3
+    out = Voxelizer(voxel_size=0.04).voxelize(g["xyz"], g["colors"].copy(), g["labels"].copy(), link=link)
+    assert np.array_equal(out[4], link[g["inds_plain"]])
+    with pytest.raises(AssertionError):
+        Voxelizer().voxelize(g["xyz"][:, :2], g["colors"], g["labels"])
+
+
+def _random_rt(rng, voxel_size):
+    from xmask3d_b200.voxelizer import M
+    rot = M(np.array([0, 0, 1.0]), rng.uniform(-np.pi, np.pi)) @ M(np.array([1.0, 0, 0]), rng.uniform(-0.05, 0.05))
+    rt = np.eye(4)
+    rt[:3, :3] = rot * (rng.uniform(0.9, 1.1) / voxel_size)
+    return rt
+
+
+def test_voxelize_vs_oracle_batched(cport, dev):
+    """Ragged batch through every sort path: tiny (bitonic), ~35k (2048-bucket sample sort),
+    >65k unique keys (4096 buckets), a 1-point and an all-duplicates segment."""
+    from xmask3d_b200 import ops
+    rng = np.random.default_rng(11)
+    sc = syn.make_scene(5, 150_000)
+    big = syn.make_scene(6, 400_000, room=(12.0, 10.0, 3.0))
+    segs = [(sc.xyz[:37_000], _random_rt(rng, 0.02)),
+            (sc.xyz[:900], _random_rt(rng, 0.02)),
+            (big.xyz, _random_rt(rng, 0.01)),
+            (sc.xyz[:1], _random_rt(rng, 0.02)),
+            (np.repeat(sc.xyz[:3], 2000, 0), _random_rt(rng, 0.02)),
+            (sc.xyz[50_000:50_000 + 4097], _random_rt(rng, 0.005)),
+            (sc.xyz, _random_rt(rng, 0.05))]
+    n = [s.shape[0] for s, _ in segs]
+    off = np.concatenate([[0], np.cumsum(n)]).astype(np.int64)
+    xyz = torch.from_numpy(np.concatenate([s for s, _ in segs])).to(dev)
+    rt = torch.from_numpy(np.stack([r[:3, :4] for _, r in segs])).to(dev)
+    for collate in (False, True):
+        u = ops.voxelize_batch(xyz, torch.from_numpy(off).to(dev), rt, collate=collate)
+        assert int(u.status.item()) == 0
+        m, uoff = u.m.cpu().numpy(), u.uniq_off.cpu().numpy()
+        first, inv, vox = u.first.cpu().numpy(), u.inverse.cpu().numpy(), u.voxel_xyz.cpu().numpy()
+        for i, (pts, r) in enumerate(segs):
+            rgrid, rfirst, rinv = cport.voxelize(pts, r)
+            assert m[i] == len(rfirst), f"segment {i}"
+            a = int(uoff[i])
+            assert np.array_equal(first[a:a + m[i]], rfirst), f"segment {i}"
+            assert np.array_equal(vox[a:a + m[i]].astype(np.float64), rgrid), f"segment {i}"
+            shift = a if collate else 0
+            assert np.array_equal(inv[off[i]:off[i + 1]] - shift, rinv), f"segment {i}"
+        assert uoff[-1] == m.sum()
+    assert m[2] > 65536 and 4096 < m[0] < 65536 and m[3] == 1 and m[4] == 3
+
+
+def test_sparse_quantize_and_hashes_golden(golden, cport, dev):
+    from xmask3d_b200.voxelization_utils import fnv_hash_vec, ravel_hash_vec, sparse_quantize
+    g = golden("hash")
+    assert np.array_equal(fnv_hash_vec(g["kat"]), g["kat_fnv"])
+    assert np.array_equal(fnv_hash_vec(g["rnd"]), g["rnd_fnv"])
+    assert np.array_equal(ravel_hash_vec(g["rnd"] - 100.0), g["rnd_ravel"])
+    inds, inv = sparse_quantize(g["ex"], return_index=True)
+    assert inds.tolist() == [3, 0, 1] and inv.tolist() == [1, 2, 1, 0, 2]
+    li, ll = sparse_quantize(g["dup"], labels=g["dup_labels"].copy(), return_index=True,
+                             set_ignore_label_when_collision=True)
+    assert np.array_equal(li, g["dup_lab_inds"]) and np.array_equal(ll, g["dup_lab_out"])
+    ri, rinv = sparse_quantize(g["dup"] - 5.0, return_index=True, hash_type="ravel")
+    assert np.array_equal(ri, g["dup_ravel_inds"]) and np.array_equal(rinv, g["dup_ravel_inv"])
+    q = golden("quant")
+    qi, qinv = sparse_quantize(q["coords"], return_index=True, quantization_size=0.05)       # negative cells
+    assert np.array_equal(qi, q["inds"]) and np.array_equal(qinv, q["inv"])
+    with pytest.raises(AssertionError):
+        sparse_quantize(g["ex"], hash_type="md5")
+    with pytest.raises(AssertionError):
+        sparse_quantize(g["ex"][:, 0])
+    # forced 64-bit collisions and adversarial (sorted / constant) keys through unique_batch
+    from xmask3d_b200 import ops
+    rng = np.random.default_rng(2)
+    segs = [np.sort(rng.integers(0, 2 ** 63, 70_000, dtype=np.int64)).astype(np.uint64) * np.uint64(2),
+            np.full(5000, 12345, np.uint64),
+            rng.integers(0, 40, 10_000).astype(np.uint64),
+            np.array([2 ** 64 - 2, 0, 2 ** 63, 0], np.uint64)]
+    off = np.concatenate([[0], np.cumsum([len(s) for s in segs])]).astype(np.int64)
+    keys = torch.from_numpy(np.concatenate(segs).view(np.int64)).to(dev)
+    u = ops.unique_batch(keys, torch.from_numpy(off).to(dev), want_counts=True)
+    m, uoff = u.m.cpu().numpy(), u.uniq_off.cpu().numpy()
+    for i, s in enumerate(segs):
+        rf, ri_, rc = cport.unique_u64(s)
+        a = int(uoff[i])
+        assert m[i] == len(rf)
+        assert np.array_equal(u.first.cpu().numpy()[a:a + m[i]], rf)
+        assert np.array_equal(u.counts.cpu().numpy()[a:a + m[i]], rc)
+        assert np.array_equal(u.inverse.cpu().numpy()[off[i]:off[i + 1]], ri_)
+
+
+# ----------------------------------------------------------------------------- stage 3
+def test_gather_pool_scatter_golden(golden, cport, dev):
+    from xmask3d_b200 import ops
+    from xmask3d_b200.fuser import mask_mapper
+    g = golden("pool")
+    xl, yl = torch.from_numpy(g["x_label"]), torch.from_numpy(g["y_label"])
+    emb, pred3d = torch.from_numpy(g["emb"]).to(dev), torch.from_numpy(g["pred3d"]).to(dev)
+
+    class Cfg:
+        caption_contra_2d_pre = True
+    for tag, masks in (("part", torch.from_numpy(g["part"]).float()), ("over", torch.from_numpy(g["over"]))):
+        fused, f2d, f3d, pre = mask_mapper([xl], [yl], [masks.to(dev)], [emb], [pred3d],
+                                           lambda a, b: a + 2.0 * b, lambda a: a, lambda a: a, Cfg)
+        assert np.array_equal(f2d[0].cpu().numpy(), g[f"feat2d_{tag}"])          # bit-exact float32
+        assert np.array_equal(fused[0].cpu().numpy(), g[f"fused_{tag}"])
+        assert np.array_equal(pre[0].cpu().numpy(), g[f"pre_{tag}"])
+        assert np.array_equal(f3d[0].cpu().numpy(), g["pred3d"])
+        seg = torch.tensor([0, len(xl)], dtype=torch.int64, device=dev)
+        rowcol = torch.stack([xl, yl], 1).to(dev, torch.int32)
+        for mode, key in (("ge0.5", "ge"), ("sigmoid_ge0.5", "sig")):
+            member, counts = ops.gather_masks(masks.to(dev)[None], rowcol, seg, mode=mode, want_counts=True)
+            s, cnt, mean = ops.pool(pred3d, seg, masks.shape[0], member=member)
+            assert np.array_equal(cnt[0].cpu().numpy(), g[f"cnt_{tag}_{key}"])
+            assert np.array_equal(counts[0].cpu().numpy(), g[f"cnt_{tag}_{key}"])
+            ref = g[f"mean_{tag}_{key}"]
+            err = np.abs(mean[0].cpu().numpy() - ref).max(1) / np.maximum(np.abs(ref).max(1), 1e-30)
+            assert err.max() < 1e-5, err.max()
+    from xmask3d_b200.pooling import masked_score_pool
+    sp, keep = masked_score_pool(torch.from_numpy(g["score"]).to(dev), [xl], [yl],
+                                 torch.from_numpy(g["over"]).to(dev)[None])
+    assert np.array_equal(keep[0].cpu().numpy(), g["score_keep"])
+    np.testing.assert_allclose(sp[0].cpu().numpy(), g["score_pool"], rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("k,c", [(50, 768), (100, 768), (7, 64), (130, 256), (3, 1)])
+def test_pool_scatter_vs_oracle(cport, dev, k, c):
+    """Ragged batch (incl. an empty segment), overlapping members and partition labels."""
+    from xmask3d_b200 import ops
+    rng = np.random.default_rng(k * 1000 + c)
+    n = [3000, 0, 1777, 1, 5200]
+    off = np.concatenate([[0], np.cumsum(n)]).astype(np.int64)
+    total = int(off[-1])
+    feat = rng.standard_normal((total, c), dtype=np.float32)
+    member_b = rng.random((len(n), k, max(n))) < 0.12
+    label = rng.integers(-1, k, total).astype(np.int32)
+    words = (k + 31) // 32
+    packed = np.zeros((total, words), np.uint32)
+    for s in range(len(n)):
+        mb = member_b[s][:, :n[s]]
+        for m in range(k):
+            packed[off[s]:off[s + 1], m // 32] |= (mb[m].astype(np.uint32) << np.uint32(m % 32))
+    seg = torch.from_numpy(off).to(dev)
+    f = torch.from_numpy(feat).to(dev)
+    mem = torch.from_numpy(packed.view(np.int32)).to(dev)
+    s_sum, cnt, mean = ops.pool(f, seg, k, member=mem)
+    l_sum, l_cnt, l_mean = ops.pool(f, seg, k, label=torch.from_numpy(label).to(dev))
+    emb = rng.standard_normal((len(n), k, c), dtype=np.float32)
+    out, counter = ops.scatter(torch.from_numpy(emb).to(dev), seg, total, member=mem)
+    lout, lcounter = ops.scatter(torch.from_numpy(emb).to(dev), seg, total, label=torch.from_numpy(label).to(dev))
+    for s in range(len(n)):
+        a, b = off[s], off[s + 1]
+        mb = member_b[s][:, :n[s]]
+        r_sum, r_cnt = cport.pool_member_f64(feat[a:b], mb) if n[s] else (np.zeros((k, c)), np.zeros(k, np.int64))
+        assert np.array_equal(cnt[s].cpu().numpy(), r_cnt)
+        scale = np.maximum(np.abs(r_sum).max(1), 1e-30)
+        assert (np.abs(s_sum[s].cpu().numpy() - r_sum).max(1) / scale).max() < 1e-5
+        r_mean = r_sum / np.maximum(r_cnt, 1)[:, None]
+        assert (np.abs(mean[s].cpu().numpy() - r_mean).max(1) / np.maximum(np.abs(r_mean).max(1), 1e-30)).max() < 1e-5
+        rl_sum, rl_cnt = cport.pool_label_f64(feat[a:b], label[a:b], k) if n[s] else (np.zeros((k, c)), np.zeros(k, np.int64))
+        assert np.array_equal(l_cnt[s].cpu().numpy(), rl_cnt)
+        assert (np.abs(l_sum[s].cpu().numpy() - rl_sum).max(1) / np.maximum(np.abs(rl_sum).max(1), 1e-30)).max() < 1e-5
+        if n[s]:
+            r_out, r_counter = cport.scatter_member_f32(mb, emb[s])
+            assert np.array_equal(out[a:b].cpu().numpy(), r_out)                    # bit-exact
+            assert np.array_equal(counter[a:b].cpu().numpy(), r_counter)
+            onehot = (label[a:b][None, :] == np.arange(k)[:, None])
+            rl_out, _ = cport.scatter_member_f32(onehot, emb[s])
+            assert np.array_equal(lout[a:b].cpu().numpy(), rl_out)
+    # determinism: same bits on a second run
+    s2, _, _ = ops.pool(f, seg, k, member=mem)
+    assert torch.equal(s2, s_sum)
+    # row_index indirection (pred_3d[inds_reconstruct], models/xmask3d.py:152)
+    perm = torch.randperm(total, device=dev).to(torch.int32)
+    inv = torch.empty_like(perm)
+    inv[perm.long()] = torch.arange(total, device=dev, dtype=torch.int32)
+    s3, _, _ = ops.pool(f[perm.long()], seg, k, member=mem, row_index=inv)
+    assert torch.equal(s3, s_sum)
+
+
+# ----------------------------------------------------------------------------- stage 4
+def test_logits_golden(golden, dev):
+    from xmask3d_b200.logits import cal_pred_logits, ensemble_logits_with_labels
+    g = golden("logits")
+    for tag, t in (("b15", 20), ("sn200", 201)):
+        o = {"mask_embed": torch.from_numpy(g[f"me_{tag}"]).to(dev), "text_embed": torch.from_numpy(g[f"te_{tag}"]).to(dev),
+             "null_embed": torch.from_numpy(g[f"ne_{tag}"]).to(dev), "labels": [[str(i)] for i in range(t - 1)],
+             "logit_scale": torch.tensor(1 / 0.07)}
+        got, amax = cal_pred_logits(o, want_argmax=True)
+        ref = g[f"logits_{tag}"]
+        got = got.cpu().numpy()
+        assert got.shape == ref.shape
+        assert np.array_equal(got.argmax(-1), ref.argmax(-1))                      # identical argmax
+        assert np.array_equal(amax.cpu().numpy(), ref.argmax(-1))
+        assert np.abs(got - ref).max() < 2e-5 * max(1.0, np.abs(ref).max()), np.abs(got - ref).max()
+    sizes = g["sizes_grp"].tolist()
+    labels, s = [], 0
+    for n in sizes:
+        labels.append([str(s + j) for j in range(n)])
+        s += n
+    o = {"mask_embed": torch.from_numpy(g["me_grp"]).to(dev), "text_embed": torch.from_numpy(g["te_grp"]).to(dev),
+         "null_embed": torch.from_numpy(g["ne_grp"]).to(dev), "labels": labels, "logit_scale": torch.tensor(100.0)}
+    got = cal_pred_logits(o).cpu().numpy()
+    assert np.array_equal(got.argmax(-1), g["logits_grp"].argmax(-1))
+    assert np.abs(got - g["logits_grp"]).max() < 2e-5 * np.abs(g["logits_grp"]).max()
+    raw = torch.from_numpy(g["ens_in"]).to(dev)
+    assert np.array_equal(ensemble_logits_with_labels(raw, labels, "max").cpu().numpy(), g["ens_max"])
+    np.testing.assert_allclose(ensemble_logits_with_labels(raw, labels, "mean").cpu().numpy(), g["ens_mean"], rtol=1e-6)
+    with pytest.raises(AssertionError):
+        ensemble_logits_with_labels(raw, labels[:-1], "max")

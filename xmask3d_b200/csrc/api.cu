@@ -1,0 +1,56 @@
+// libxm3d — error reporting, version and device queries of the C ABI (include/xm3d.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace xm3d {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_launch(const char *what) {
+    const cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) return XM3D_OK;
+    set_error("%s: CUDA error %d (%s)", what, (int)e, cudaGetErrorString(e));
+    return XM3D_ERR_CUDA;
+}
+
+int sm_count() {
+    static int cached = 0;
+    if (cached) return cached;
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return 148;          // B200; used only to size workspaces when no device is visible
+    }
+    cached = n;
+    return n;
+}
+
+}  // namespace xm3d
+
+extern "C" int xm3d_version(void) { return XM3D_VERSION; }
+
+extern "C" const char *xm3d_last_error(void) { return xm3d::g_err; }
+
+extern "C" int xm3d_device_info(int32_t *sm, int32_t *cc_major, int32_t *cc_minor) {
+    int dev = 0;
+    cudaDeviceProp prop;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+        cudaGetLastError();
+        xm3d::set_error("xm3d_device_info: no CUDA device");
+        return XM3D_ERR_CUDA;
+    }
+    if (sm) *sm = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    return XM3D_OK;
+}

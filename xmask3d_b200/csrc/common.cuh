@@ -1,0 +1,97 @@
+// Shared helpers of libxm3d (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/xm3d.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libxm3d is written for sm_100a (B200) only"
+#endif
+
+namespace xm3d {
+
+void set_error(const char *fmt, ...);
+int check_launch(const char *what);  // cudaGetLastError -> XM3D_OK / XM3D_ERR_CUDA
+int sm_count();
+
+#define XM3D_REQUIRE(cond, msg)                      \
+    do {                                             \
+        if (!(cond)) {                               \
+            xm3d::set_error("%s: %s", __func__, msg); \
+            return XM3D_ERR_BAD_ARG;                 \
+        }                                            \
+    } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Bump allocator over the caller's workspace; every block is 256-byte aligned.
+struct Carver {
+    char *base;
+    size_t off;
+    explicit Carver(void *p) : base(static_cast<char *>(p)), off(0) {}
+    template <typename T>
+    T *take(size_t count) {
+        T *p = base ? reinterpret_cast<T *>(base + off) : nullptr;
+        off += align_up(count * sizeof(T), 256);
+        return p;
+    }
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// Largest s with off[s] <= i  (off is an ascending int64 [n+1] array, off[0] == 0).
+__device__ __forceinline__ int seg_of(const int64_t *__restrict__ off, int n, int64_t i) {
+    int lo = 0, hi = n;  // invariant: off[lo] <= i < off[hi]
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (off[mid] <= i) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ float4 ldg_stream4(const float *p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+
+// ---- mbarrier + 1-D bulk async copy (TMA engine, SASS: UBLKCP) ----------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t phase) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a wrong transaction count must trap, never hang the GPU box.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
+    for (uint32_t spin = 0; !mbar_try_wait(bar, phase); ++spin)
+        if (spin > (1u << 26)) __trap();
+}
+// global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned.
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+#endif  // __CUDACC__
+
+}  // namespace xm3d

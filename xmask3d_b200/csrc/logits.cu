@@ -1,0 +1,351 @@
+// Stage 4 — cosine-similarity logits of mask embeddings against text embeddings.
+//
+// Replaces XMASK3d.cal_pred_logits (reference models/xmask3d.py:129-143; twin
+// models/modeling/meta_arch/odise.py:170-194) and ensemble_logits_with_labels
+// (models/modeling/meta_arch/helper.py:72-97):
+//   out[r, g]        = reduce_{t in group g} scale * <me_r/|me_r|, te_t/|te_t|>
+//   out[r, n_groups] = scale * <me_r/|me_r|, null/|null|>
+//
+// The (rows x C) . (C x T) contraction is the only tensor-core work on the path.  fp32 inputs
+// are split into two TF32-exact planes (hi = top 19 bits, lo = tf32(x - hi)) by a prep kernel
+// that also produces the inverse L2 norms; the GEMM kernel then issues three tcgen05.mma
+// kind::tf32 products per k-step (hi*hi + hi*lo + lo*hi, "3xTF32") into one fp32 accumulator in
+// tensor memory, which reproduces fp32 dot products to ~1e-6 relative so that argmax matches the
+// reference's fp32 matmul.  Operands are staged by TMA (cp.async.bulk.tensor, 128-byte swizzle)
+// through an mbarrier ring: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA
+// issuer, warps 2-5 = epilogue (tcgen05.ld -> normalise, scale, synonym-group max/mean, argmax).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace xm3d {
+
+constexpr int LG_BM = 128;          // rows of mask embeddings per CTA  (UMMA M)
+constexpr int LG_BK = 32;           // fp32 elements per k-block = one 128-byte swizzle row
+constexpr int LG_UMMA_K = 8;        // tf32: 32 bytes per MMA k-step
+constexpr int LG_MAX_N = 256;
+constexpr int LG_THREADS = 192;
+
+// ---- prep: inverse norms + hi/lo TF32 planes ------------------------------------------------
+__global__ void __launch_bounds__(256)
+logits_prep_kernel(const float *__restrict__ a, const float *__restrict__ b, int64_t rows_a, int64_t rows_b,
+                   int c, float *__restrict__ hi, float *__restrict__ lo, float *__restrict__ inv_norm) {
+    // one warp per row; rows [0, rows_a) come from a, [rows_a, rows_a + rows_b) from b
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows_a + rows_b) return;
+    const float *src = row < rows_a ? a + row * c : b + (row - rows_a) * c;
+    const int lane = threadIdx.x & 31;
+    float ss = 0.f;
+    for (int j = lane; j < c; j += 32) {
+        const float x = __ldg(src + j);
+        ss = fmaf(x, x, ss);
+        const float h = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+        const float l = __uint_as_float(__float_as_uint(__fsub_rn(x, h)) & 0xffffe000u);
+        hi[row * c + j] = h;
+        lo[row * c + j] = l;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    // F.normalize: x / max(||x||_2, 1e-12)
+    if (lane == 0) inv_norm[row] = __fdiv_rn(1.0f, fmaxf(sqrtf(ss), 1e-12f));
+}
+
+// ---- tcgen05 / TMA wrappers -----------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int x, int y, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ uint64_t make_sw128_desc(const void *smem_ptr) {
+    // K-major, 128-byte swizzle: 8-row atoms of 128 B, stride between atoms 1024 B, version 1 (sm_100)
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_u32(smem_ptr) & 0x3ffff) >> 4);        // start address, bits [0,14)
+    d |= (uint64_t)0 << 16;                                       // leading byte offset (unused: 1 atom in K)
+    d |= (uint64_t)(1024 >> 4) << 32;                             // stride byte offset, bits [32,46)
+    d |= (uint64_t)1 << 46;                                       // descriptor version
+    d |= (uint64_t)2 << 61;                                       // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                 ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct LogitsParams {
+    int64_t rows;
+    int c, n_cols, n_text, n_groups, bn, stages, tmem_cols;
+    int ensemble_mean;
+    float scale;
+    const float *inv_norm;      // [rows + n_cols]
+    const int *group_off;       // device [n_groups + 1]
+    float *out;                 // [rows, n_groups + 1]
+    int *argmax;                // [rows] or null
+};
+
+__global__ void __launch_bounds__(LG_THREADS, 1)
+logits_mma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                  const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                  const LogitsParams P) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ uint64_t s_full[4], s_empty[4], s_done;
+    __shared__ uint32_t s_tmem;
+    __shared__ float s_invb[LG_MAX_N];
+    __shared__ short s_gid[LG_MAX_N];           // output column of each GEMM column
+    __shared__ short s_glen[LG_MAX_N];          // >0 on the last column of a group: the group's length
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.x * LG_BM;
+    const int nkb = (P.c + LG_BK - 1) / LG_BK;
+    const uint32_t a_bytes = LG_BM * LG_BK * 4, b_bytes = (uint32_t)P.bn * LG_BK * 4;
+    const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+    // 128-byte swizzle atoms need 1024-byte aligned tiles: re-align defensively (the launch adds
+    // 1 KB of slack); every tile size is a multiple of 1024 B
+    unsigned char *tiles = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
+
+    for (int j = tid; j < LG_MAX_N; j += LG_THREADS) {
+        s_invb[j] = j < P.n_cols ? P.inv_norm[P.rows + j] : 0.f;
+        s_gid[j] = 0;
+        s_glen[j] = 0;
+    }
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < P.stages; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 1); }
+        mbar_init(&s_done, 1);
+        mbar_fence_init();
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_hi));
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_lo));
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_hi));
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_lo));
+    }
+    if (warp == 1) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(&s_tmem)), "r"((uint32_t)P.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    __syncthreads();
+    // group bookkeeping (after the zero fill above)
+    for (int g = tid; g <= P.n_groups; g += LG_THREADS) {
+        const int lo = g < P.n_groups ? P.group_off[g] : P.n_text;
+        const int hi = g < P.n_groups ? P.group_off[g + 1] : P.n_text + 1;
+        for (int j = lo; j < hi && j < LG_MAX_N; ++j) s_gid[j] = (short)g;
+        if (hi - 1 < LG_MAX_N && hi > lo) s_glen[hi - 1] = (short)(hi - lo);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = s_tmem;
+
+    if (warp == 0) {
+        // ===== TMA producer (one lane) =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(&s_empty[stage], phase ^ 1);
+                unsigned char *st = tiles + (size_t)stage * stage_bytes;
+                mbar_expect_tx(&s_full[stage], stage_bytes);
+                tma_load_2d(st, &map_a_hi, kb * LG_BK, m0, &s_full[stage]);
+                tma_load_2d(st + a_bytes, &map_a_lo, kb * LG_BK, m0, &s_full[stage]);
+                tma_load_2d(st + 2 * a_bytes, &map_b_hi, kb * LG_BK, 0, &s_full[stage]);
+                tma_load_2d(st + 2 * a_bytes + b_bytes, &map_b_lo, kb * LG_BK, 0, &s_full[stage]);
+                if (++stage == P.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one lane) =====
+        if (lane == 0) {
+            // instruction descriptor: D=f32, A=B=tf32, K-major both, N = bn, M = 128
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(P.bn >> 3) << 17) |
+                                   ((uint32_t)(LG_BM >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(&s_full[stage], phase);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                unsigned char *st = tiles + (size_t)stage * stage_bytes;
+                const uint64_t a_hi = make_sw128_desc(st), a_lo = make_sw128_desc(st + a_bytes);
+                const uint64_t b_hi = make_sw128_desc(st + 2 * a_bytes), b_lo = make_sw128_desc(st + 2 * a_bytes + b_bytes);
+#pragma unroll
+                for (int k = 0; k < LG_BK / LG_UMMA_K; ++k) {
+                    const uint64_t adv = (uint64_t)((k * LG_UMMA_K * 4) >> 4);   // bytes >> 4 inside the swizzle row
+                    umma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, (kb | k) ? 1u : 0u);
+                    umma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
+                    umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, 1u);
+                }
+                umma_commit(&s_empty[stage]);          // frees the smem slot when these MMAs retire
+                if (++stage == P.stages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(&s_done);                       // accumulator complete
+        }
+    } else {
+        // ===== epilogue: warps 2..5 own TMEM lane groups (warp % 4) =====
+        mbar_wait(&s_done, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int lg = warp & 3;
+        const int64_t r = (int64_t)m0 + lg * 32 + lane;
+        const bool row_ok = r < P.rows;
+        const float inv_a = row_ok ? P.inv_norm[r] : 0.f;
+        const int out_w = P.n_groups + 1;
+        float gacc = P.ensemble_mean ? 0.f : -INFINITY;
+        float best = -INFINITY;
+        int best_i = 0;
+        for (int c0 = 0; c0 < P.bn; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int col = c0 + j;
+                if (col < P.n_cols) {
+                    // (me/|me|).(te/|te|) * scale, normalisation applied to the fp32 dot product
+                    const float val = P.scale * ((__uint_as_float(v[j]) * inv_a) * s_invb[col]);
+                    gacc = P.ensemble_mean ? gacc + val : fmaxf(gacc, val);
+                    const int glen = s_glen[col];
+                    if (glen > 0) {
+                        const float o = P.ensemble_mean ? __fdiv_rn(gacc, (float)glen) : gacc;
+                        const int g = s_gid[col];
+                        if (row_ok) P.out[r * out_w + g] = o;
+                        if (o > best) { best = o; best_i = g; }
+                        gacc = P.ensemble_mean ? 0.f : -INFINITY;
+                    }
+                }
+            }
+        }
+        if (row_ok && P.argmax) P.argmax[r] = best_i;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        __syncwarp();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)P.tmem_cols)
+                     : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+    return fn;
+}
+
+static bool make_map(CUtensorMap *m, const float *base, int64_t rows, int c, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)c, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)c * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)LG_BK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+struct LogitsWs {
+    float *hi, *lo, *inv_norm;
+    int *group_off;
+};
+static LogitsWs carve_logits(void *ws, int64_t rows, int n_cols, int c, int n_groups, size_t *bytes) {
+    Carver cv(ws);
+    LogitsWs w;
+    w.hi = cv.take<float>((size_t)(rows + n_cols) * c);
+    w.lo = cv.take<float>((size_t)(rows + n_cols) * c);
+    w.inv_norm = cv.take<float>((size_t)(rows + n_cols));
+    w.group_off = cv.take<int>((size_t)n_groups + 1);
+    *bytes = cv.off + 256;
+    return w;
+}
+
+}  // namespace xm3d
+
+using namespace xm3d;
+
+extern "C" size_t xm3d_logits_ws_bytes(int64_t rows, int32_t n_text, int32_t c, int32_t n_groups) {
+    size_t b = 0;
+    carve_logits(nullptr, rows, n_text + 1, c, n_groups, &b);
+    return b;
+}
+
+extern "C" int xm3d_logits(const float *mask_embed, int64_t rows, int32_t c, const float *text_embed,
+                           int32_t n_text, const float *null_embed, const int32_t *group_off_host,
+                           int32_t n_groups, int32_t ensemble_mean, float logit_scale, float *out,
+                           int32_t *argmax, void *ws, size_t ws_bytes, xm3d_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    XM3D_REQUIRE(rows >= 0 && c > 0 && n_text > 0 && n_groups > 0, "bad sizes");
+    XM3D_REQUIRE(c % 4 == 0, "embedding width must be a multiple of 4");
+    XM3D_REQUIRE(n_text + 1 <= LG_MAX_N, "at most 255 text embeddings");
+    XM3D_REQUIRE(mask_embed && text_embed && null_embed && group_off_host && out && ws, "null pointer");
+    XM3D_REQUIRE(group_off_host[0] == 0 && group_off_host[n_groups] == n_text, "group offsets must span [0, n_text]");
+    for (int g = 0; g < n_groups; ++g)
+        XM3D_REQUIRE(group_off_host[g + 1] > group_off_host[g], "empty label group");
+    if (rows == 0) return XM3D_OK;
+    const int n_cols = n_text + 1;
+    size_t need = 0;
+    LogitsWs w = carve_logits(ws, rows, n_cols, c, n_groups, &need);
+    if (ws_bytes < need) {
+        set_error("xm3d_logits: workspace too small");
+        return XM3D_ERR_WORKSPACE;
+    }
+    cudaMemcpyAsync(w.group_off, group_off_host, sizeof(int) * (n_groups + 1), cudaMemcpyHostToDevice, stream);
+    // rows of A first, then text rows, then the null row (two launches keep the kernel simple)
+    const int wpb = 8;
+    logits_prep_kernel<<<(unsigned)((rows + wpb - 1) / wpb), 256, 0, stream>>>(mask_embed, nullptr, rows, 0, c, w.hi,
+                                                                               w.lo, w.inv_norm);
+    logits_prep_kernel<<<(unsigned)((n_cols + wpb - 1) / wpb), 256, 0, stream>>>(
+        text_embed, null_embed, n_text, 1, c, w.hi + (size_t)rows * c, w.lo + (size_t)rows * c, w.inv_norm + rows);
+
+    LogitsParams P;
+    P.rows = rows; P.c = c; P.n_cols = n_cols; P.n_text = n_text; P.n_groups = n_groups;
+    P.bn = (n_cols + 15) / 16 * 16;
+    P.ensemble_mean = ensemble_mean; P.scale = logit_scale; P.inv_norm = w.inv_norm; P.group_off = w.group_off;
+    P.out = out; P.argmax = argmax;
+    int tc = 32;
+    while (tc < P.bn) tc <<= 1;
+    P.tmem_cols = tc;
+    const size_t stage_bytes = 2 * (size_t)LG_BM * LG_BK * 4 + 2 * (size_t)P.bn * LG_BK * 4;
+    int stages = (int)((220 * 1024) / stage_bytes);
+    if (stages > 4) stages = 4;
+    if (stages < 1) { set_error("xm3d_logits: tile does not fit shared memory"); return XM3D_ERR_UNSUPPORTED; }
+    P.stages = stages;
+
+    CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+    if (!make_map(&ma_hi, w.hi, rows, c, LG_BM) || !make_map(&ma_lo, w.lo, rows, c, LG_BM) ||
+        !make_map(&mb_hi, w.hi + (size_t)rows * c, n_cols, c, P.bn) ||
+        !make_map(&mb_lo, w.lo + (size_t)rows * c, n_cols, c, P.bn)) {
+        set_error("xm3d_logits: cuTensorMapEncodeTiled failed");
+        return XM3D_ERR_CUDA;
+    }
+    const size_t smem = stage_bytes * stages + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(logits_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+        attr_set = true;
+    }
+    logits_mma_kernel<<<(unsigned)((rows + LG_BM - 1) / LG_BM), LG_THREADS, smem, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, P);
+    return check_launch("xm3d_logits");
+}

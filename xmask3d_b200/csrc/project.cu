@@ -1,0 +1,442 @@
+// Stage 2 — point-to-pixel projection with the depth-occlusion test, batched over views.
+//
+// Replaces PointCloudToImageMapper.compute_mapping (reference models/utils/fusion_util.py:46-142)
+// and the loaders' compaction of the visible points (dataset/data_loader_infer.py:174-182,
+// 263-268).  One CTA owns PART consecutive points of one view:
+//   * the 192-byte view record (world->camera rows, intrinsics) and, when it is a uint16
+//     image that fits, the whole depth image are staged into shared memory with 1-D bulk
+//     async copies (TMA engine) signalled through mbarriers; the camera-space transform of
+//     all the CTA's points runs while the depth image is still in flight;
+//   * xyz is streamed with 16-byte loads (4 points = 3 x float4 per thread);
+//   * every float->int decision is the exact IEEE operation sequence numpy performs
+//     (fp64 FMA chain for the dgemm dot products, individually rounded mul/div/add after
+//     it, rint = half-to-even), see oracle/xm3d_oracle.c for the scalar restatement;
+//   * visible points are compacted in point order inside the CTA (warp-shuffle scan) into a
+//     part-local staging run; a one-CTA scan over the (view, part) counts then gives every
+//     run its final offset and a relocation kernel writes vis_idx / rowcol / xyz_vis.
+#include "common.cuh"
+
+namespace xm3d {
+
+constexpr int PROJ_THREADS = 1024;
+constexpr int PROJ_GROUP = 4;                       // consecutive points per thread per group
+constexpr int PROJ_GROUPS = 2;                      // groups per thread
+constexpr int PROJ_GROUP_PTS = PROJ_THREADS * PROJ_GROUP;     // 4096
+constexpr int PROJ_PART = PROJ_GROUP_PTS * PROJ_GROUPS;       // 8192 points per CTA
+constexpr int PROJ_MAX_SMEM_DEPTH = 176 * 1024;     // bytes of depth image we are willing to stage
+
+struct ProjParams {
+    const float *xyz;
+    const xm3d_view_t *views;   // device copy
+    const void *depth;
+    int depth_kind;
+    double depth_scale;
+    double img_w, img_h, cut;   // as doubles: bounds are tested on the rounded double
+    double vis_thres;
+    uint8_t *vis;
+    int64_t *mapping;
+    unsigned long long *stage;  // [total_pts] part-local compacted (idx<<32 | row<<16 | col)
+    int *part_cnt;              // [n_views * parts]
+    int *view_flag;             // [n_views] any inside point within the depth image (exact mode)
+    int parts;
+    int smem_depth_bytes;
+    int use_flag;               // 1: vis = flag ? inside&&ok : inside   (depth smaller than image)
+};
+
+__device__ __forceinline__ double dot_row(const double *a, double x, double y, double z) {
+    // numpy float64 matmul == one accumulator per output, FMA in k order (OpenBLAS dgemm kernel)
+    double s = __dmul_rn(a[0], x);
+    s = __fma_rn(a[1], y, s);
+    s = __fma_rn(a[2], z, s);
+    s = __fma_rn(a[3], 1.0, s);
+    return s;
+}
+
+struct PointState {
+    double z;        // camera-space depth
+    int ix, iy;      // pixel column / row (valid when inside)
+    bool inside;
+};
+
+__device__ __forceinline__ PointState project_point(const double *vw, float fx_, float fy_, float fz_,
+                                                    const ProjParams &P) {
+    PointState s;
+    const double x = (double)fx_, y = (double)fy_, z = (double)fz_;
+    const double p0 = dot_row(vw + 0, x, y, z);                 // fusion_util.py:71
+    const double p1 = dot_row(vw + 4, x, y, z);
+    const double p2 = dot_row(vw + 8, x, y, z);
+    const double zdiv = (fabs(p2) < 1e-8) ? 1.0 : p2;           // :75-76
+    const double px = __dadd_rn(__ddiv_rn(__dmul_rn(p0, vw[12]), zdiv), vw[14]);   // :78
+    const double py = __dadd_rn(__ddiv_rn(__dmul_rn(p1, vw[13]), zdiv), vw[15]);   // :79
+    const double rx = rint(px), ry = rint(py);                  // :82-83 (half to even)
+    // :86-95 — tested on the integer-valued doubles (NaN / out-of-int64 values fail like the
+    // INT64_MIN numpy's astype(int) produces for them)
+    s.inside = (p2 > 0.0) && (rx >= P.cut) && (ry >= P.cut) && (rx < P.img_w - P.cut) && (ry < P.img_h - P.cut);
+    s.ix = s.inside ? (int)rx : 0;
+    s.iy = s.inside ? (int)ry : 0;
+    s.z = p2;
+    return s;
+}
+
+template <bool FLAG_ONLY>
+__global__ void __launch_bounds__(PROJ_THREADS, 1) project_kernel(const ProjParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(16) double s_view[24];      // the 192-byte record
+    __shared__ uint64_t s_bar[2];
+    __shared__ int s_warp_tot[PROJ_THREADS / 32];
+    __shared__ int s_any;
+
+    const int v = blockIdx.y, part = blockIdx.x, tid = threadIdx.x;
+    const xm3d_view_t *gv = P.views + v;
+    // n_pts sits at byte 152 of the record; read it directly so empty CTAs leave at once
+    const int n_pts = gv->n_pts;
+    const int64_t part_start = (int64_t)part * PROJ_PART;
+    if (part_start >= n_pts) {
+        if (!FLAG_ONLY && tid == 0) P.part_cnt[v * P.parts + part] = 0;
+        return;
+    }
+    const int64_t depth_off = gv->depth_off;
+    const int dh = gv->depth_h, dw = gv->depth_w;
+    const bool has_depth = P.depth_kind != XM3D_DEPTH_NONE && depth_off >= 0;
+    const size_t depth_bytes = (size_t)dh * dw * 2;
+    const bool stage_depth = has_depth && P.depth_kind == XM3D_DEPTH_U16 && depth_bytes <= (size_t)P.smem_depth_bytes &&
+                             (depth_bytes % 16 == 0) &&
+                             ((reinterpret_cast<uintptr_t>(P.depth) + (size_t)depth_off * 2) % 16 == 0);
+
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        mbar_fence_init();
+        s_any = 0;
+        mbar_expect_tx(&s_bar[0], (uint32_t)sizeof(xm3d_view_t));
+        bulk_g2s(s_view, gv, (uint32_t)sizeof(xm3d_view_t), &s_bar[0]);
+        if (stage_depth) {
+            mbar_expect_tx(&s_bar[1], (uint32_t)depth_bytes);
+            const char *src = reinterpret_cast<const char *>(P.depth) + (size_t)depth_off * 2;
+            for (size_t o = 0; o < depth_bytes; o += 32768) {
+                const uint32_t chunk = (uint32_t)((depth_bytes - o < 32768) ? depth_bytes - o : 32768);
+                bulk_g2s(smem_raw + o, src + o, chunk, &s_bar[1]);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- stream this thread's points (16-byte loads when the scene's xyz block is aligned)
+    const float *xyz = P.xyz + gv->pt_off * 3;
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(xyz) % 16 == 0);
+    float c[PROJ_GROUPS][PROJ_GROUP * 3];
+#pragma unroll
+    for (int g = 0; g < PROJ_GROUPS; ++g) {
+        const int64_t i0 = part_start + (int64_t)g * PROJ_GROUP_PTS + (int64_t)tid * PROJ_GROUP;
+        if (vec_ok && i0 + PROJ_GROUP <= n_pts) {
+            const float4 *q = reinterpret_cast<const float4 *>(xyz + i0 * 3);
+            const float4 a = __ldg(q), b = __ldg(q + 1), d = __ldg(q + 2);
+            c[g][0] = a.x; c[g][1] = a.y; c[g][2] = a.z; c[g][3] = a.w;
+            c[g][4] = b.x; c[g][5] = b.y; c[g][6] = b.z; c[g][7] = b.w;
+            c[g][8] = d.x; c[g][9] = d.y; c[g][10] = d.z; c[g][11] = d.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < PROJ_GROUP * 3; ++j) {
+                const int64_t e = i0 * 3 + j;
+                c[g][j] = (e < (int64_t)n_pts * 3) ? __ldg(xyz + e) : 0.f;
+            }
+        }
+    }
+
+    mbar_wait(&s_bar[0], 0);
+    // packed per-point state: bit31 inside, row<<16 | col ; z kept for the occlusion test
+    uint32_t code[PROJ_GROUPS][PROJ_GROUP];
+    double zc[PROJ_GROUPS][PROJ_GROUP];
+#pragma unroll
+    for (int g = 0; g < PROJ_GROUPS; ++g)
+#pragma unroll
+        for (int j = 0; j < PROJ_GROUP; ++j) {
+            const int64_t i = part_start + (int64_t)g * PROJ_GROUP_PTS + (int64_t)tid * PROJ_GROUP + j;
+            PointState s = project_point(s_view, c[g][3 * j], c[g][3 * j + 1], c[g][3 * j + 2], P);
+            if (i >= n_pts) s.inside = false;
+            code[g][j] = s.inside ? (0x80000000u | ((uint32_t)s.iy << 16) | (uint32_t)s.ix) : 0u;
+            zc[g][j] = s.z;
+        }
+
+    // ---- occlusion test (fusion_util.py:98-135)
+    if (has_depth) {
+        if (stage_depth) mbar_wait(&s_bar[1], 0);
+        const unsigned short *sd = reinterpret_cast<const unsigned short *>(smem_raw);
+        bool any_in_depth = false;
+#pragma unroll
+        for (int g = 0; g < PROJ_GROUPS; ++g)
+#pragma unroll
+            for (int j = 0; j < PROJ_GROUP; ++j) {
+                if (!(code[g][j] >> 31)) continue;
+                const int iy = (code[g][j] >> 16) & 0x7fff, ix = code[g][j] & 0xffff;
+                const bool in_depth = iy < dh && ix < dw;            // both are >= 0 here (cut >= 0)
+                bool ok = false;
+                if (in_depth) {
+                    any_in_depth = true;
+                    double d;
+                    const size_t e = (size_t)iy * dw + ix;
+                    if (P.depth_kind == XM3D_DEPTH_U16) {
+                        const unsigned short raw = stage_depth
+                            ? sd[e] : __ldg(reinterpret_cast<const unsigned short *>(P.depth) + depth_off + e);
+                        d = __ddiv_rn((double)raw, P.depth_scale);   // imread(png) / 1000
+                    } else {
+                        d = __ldg(reinterpret_cast<const double *>(P.depth) + depth_off + e);
+                    }
+                    ok = fabs(__dsub_rn(d, zc[g][j])) <= __dmul_rn(P.vis_thres, d);     // :125
+                }
+                if (FLAG_ONLY) continue;
+                // exact mode: keep `inside` when no inside point of the view hits the depth image
+                const bool keep = P.use_flag ? (P.view_flag[v] ? ok : true) : ok;
+                if (!keep) code[g][j] = 0u;
+            }
+        if (FLAG_ONLY) {
+            if (any_in_depth) s_any = 1;
+            __syncthreads();
+            if (tid == 0 && s_any) atomicOr(&P.view_flag[v], 1);
+            return;
+        }
+    } else if (FLAG_ONLY) {
+        return;
+    }
+
+    // ---- outputs: visibility bytes, optional int64 [N,3] mapping, part-local compaction
+    const int64_t out0 = gv->out_off;
+    int running = 0;
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int g = 0; g < PROJ_GROUPS; ++g) {
+        const int64_t i0 = part_start + (int64_t)g * PROJ_GROUP_PTS + (int64_t)tid * PROJ_GROUP;
+        int cnt = 0;
+#pragma unroll
+        for (int j = 0; j < PROJ_GROUP; ++j) cnt += code[g][j] >> 31;
+        if (i0 < n_pts) {
+            uint8_t *vp = P.vis + out0 + i0;
+            if (i0 + PROJ_GROUP <= n_pts && (reinterpret_cast<uintptr_t>(vp) % 4 == 0)) {
+                *reinterpret_cast<uint32_t *>(vp) = (code[g][0] >> 31) | ((code[g][1] >> 31) << 8) |
+                                                    ((code[g][2] >> 31) << 16) | ((code[g][3] >> 31) << 24);
+            } else {
+#pragma unroll
+                for (int j = 0; j < PROJ_GROUP; ++j)
+                    if (i0 + j < n_pts) vp[j] = (uint8_t)(code[g][j] >> 31);
+            }
+            if (P.mapping) {
+                int64_t *mp = P.mapping + (out0 + i0) * 3;
+#pragma unroll
+                for (int j = 0; j < PROJ_GROUP; ++j)
+                    if (i0 + j < n_pts) {
+                        const bool vis = code[g][j] >> 31;
+                        mp[3 * j + 0] = vis ? (int64_t)((code[g][j] >> 16) & 0x7fff) : 0;   // row (y)
+                        mp[3 * j + 1] = vis ? (int64_t)(code[g][j] & 0xffff) : 0;           // col (x)
+                        mp[3 * j + 2] = vis ? 1 : 0;
+                    }
+            }
+        }
+        // block-exclusive scan of cnt (order = thread order = point order)
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_warp_tot[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_warp_tot[lane];
+            int wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            s_warp_tot[lane] = wi - w;          // exclusive warp offsets
+            if (lane == 31) s_any = wi;          // group total (s_any is free in this mode)
+        }
+        __syncthreads();
+        int pos = running + s_warp_tot[warp] + incl - cnt;
+        unsigned long long *st = P.stage + out0 + part_start;
+#pragma unroll
+        for (int j = 0; j < PROJ_GROUP; ++j)
+            if (code[g][j] >> 31) {
+                const unsigned long long idx = (unsigned long long)(i0 + j);
+                st[pos++] = (idx << 32) | (unsigned long long)(code[g][j] & 0x7fffffffu);
+            }
+        running += s_any;
+        __syncthreads();
+    }
+    if (tid == 0) P.part_cnt[v * P.parts + part] = running;
+}
+
+// Exclusive scan over the (view-major) part counts: one CTA, chunks of 1024 with a carry.
+__global__ void __launch_bounds__(1024, 1)
+project_scan_kernel(const int *__restrict__ part_cnt, int n_views, int parts, int64_t *__restrict__ part_off,
+                    int *__restrict__ n_vis, int64_t *__restrict__ vis_off, int64_t cap_vis, int *status) {
+    __shared__ int64_t s_warp[32];
+    __shared__ int64_t s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int total = n_views * parts;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < total; base += 1024) {
+        const int e = base + tid;
+        const int64_t val = (e < total) ? part_cnt[e] : 0;
+        int64_t incl = val;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int64_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const int64_t w = s_warp[lane];
+            int64_t wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int64_t t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            s_warp[lane] = wi - w;
+        }
+        __syncthreads();
+        const int64_t excl = s_carry + s_warp[warp] + incl - val;
+        if (e < total) {
+            part_off[e] = excl;
+            if (e % parts == 0) vis_off[e / parts] = excl;
+        }
+        __syncthreads();
+        if (tid == 1023) s_carry = excl + val;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        vis_off[n_views] = s_carry;
+        if (s_carry > cap_vis && status) atomicOr(status, XM3D_FLAG_VIS_OVERFLOW);
+    }
+    __syncthreads();
+    for (int v = tid; v < n_views; v += 1024) {
+        const int64_t a = vis_off[v];
+        const int64_t b = (v + 1 < n_views) ? part_off[(v + 1) * parts] : s_carry;
+        n_vis[v] = (int)(b - a);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+project_emit_kernel(const float *__restrict__ xyz, const xm3d_view_t *__restrict__ views,
+                    const unsigned long long *__restrict__ stage, const int *__restrict__ part_cnt,
+                    const int64_t *__restrict__ part_off, int parts, int64_t cap_vis,
+                    int32_t *__restrict__ vis_idx, int32_t *__restrict__ rowcol, float *__restrict__ xyz_vis) {
+    const int v = blockIdx.y, part = blockIdx.x;
+    const int cnt = part_cnt[v * parts + part];
+    if (cnt == 0) return;
+    const xm3d_view_t *gv = views + v;
+    const int64_t dst0 = part_off[v * parts + part];
+    const unsigned long long *st = stage + gv->out_off + (int64_t)part * PROJ_PART;
+    const float *src = xyz + gv->pt_off * 3;
+    for (int j = threadIdx.x; j < cnt; j += blockDim.x) {
+        const int64_t d = dst0 + j;
+        if (d >= cap_vis) break;
+        const unsigned long long e = st[j];
+        const uint32_t idx = (uint32_t)(e >> 32), rc = (uint32_t)e;
+        if (vis_idx) vis_idx[d] = (int32_t)idx;
+        if (rowcol) *reinterpret_cast<int2 *>(rowcol + 2 * d) = make_int2((int)(rc >> 16), (int)(rc & 0xffff));
+        if (xyz_vis) {
+            const float *p = src + (size_t)idx * 3;
+            xyz_vis[3 * d + 0] = __ldg(p);
+            xyz_vis[3 * d + 1] = __ldg(p + 1);
+            xyz_vis[3 * d + 2] = __ldg(p + 2);
+        }
+    }
+}
+
+static int parts_for(int max_pts) {
+    const int p = (max_pts + PROJ_PART - 1) / PROJ_PART;
+    return p < 1 ? 1 : p;
+}
+
+}  // namespace xm3d
+
+using namespace xm3d;
+
+extern "C" size_t xm3d_project_ws_bytes(int32_t n_views, int64_t total_pts, int32_t max_pts_per_view) {
+    Carver c(nullptr);
+    const int parts = parts_for(max_pts_per_view);
+    c.take<xm3d_view_t>(n_views);
+    c.take<unsigned long long>(total_pts + PROJ_PART);
+    c.take<int>((size_t)n_views * parts);
+    c.take<int64_t>((size_t)n_views * parts);
+    c.take<int>(n_views);
+    return c.off + 256;
+}
+
+extern "C" int xm3d_project_batch(const float *xyz, const xm3d_view_t *views_host, int32_t n_views,
+                                  int64_t total_pts, const void *depth, int32_t depth_kind, double depth_scale,
+                                  int32_t img_w, int32_t img_h, int32_t cut_bound, double vis_thres,
+                                  uint8_t *vis, int64_t *mapping, int32_t *n_vis, int64_t *vis_off,
+                                  int64_t cap_vis, int32_t *vis_idx, int32_t *rowcol, float *xyz_vis,
+                                  void *ws, size_t ws_bytes, int32_t *status, xm3d_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    XM3D_REQUIRE(n_views >= 0 && total_pts >= 0, "negative size");
+    XM3D_REQUIRE(n_views == 0 || (xyz && views_host && vis && n_vis && vis_off && ws), "null pointer");
+    XM3D_REQUIRE(depth_kind == XM3D_DEPTH_NONE || depth_kind == XM3D_DEPTH_U16 || depth_kind == XM3D_DEPTH_F64,
+                 "bad depth_kind");
+    XM3D_REQUIRE(depth_kind == XM3D_DEPTH_NONE || depth != nullptr, "depth_kind set but depth is null");
+    XM3D_REQUIRE(img_w > 0 && img_h > 0 && img_w <= 65535 && img_h <= 32767, "image size out of range");
+    XM3D_REQUIRE(cut_bound >= 0, "cut_bound must be >= 0");
+    if (n_views == 0) return XM3D_OK;
+
+    int max_pts = 0;
+    int64_t sum_pts = 0;
+    bool covers = true, any_depth = false;
+    size_t stage_bytes = 0;
+    for (int v = 0; v < n_views; ++v) {
+        const xm3d_view_t &w = views_host[v];
+        XM3D_REQUIRE(w.n_pts >= 0 && w.pt_off >= 0 && w.out_off >= 0, "bad view record");
+        XM3D_REQUIRE(w.out_off + w.n_pts <= total_pts, "view outputs exceed total_pts");
+        max_pts = w.n_pts > max_pts ? w.n_pts : max_pts;
+        sum_pts += w.n_pts;
+        if (depth_kind != XM3D_DEPTH_NONE && w.depth_off >= 0) {
+            XM3D_REQUIRE(w.depth_h > 0 && w.depth_w > 0, "bad depth size");
+            any_depth = true;
+            // every inside pixel lies in the depth image -> "any inside" implies "any in depth"
+            if (w.depth_h < img_h - cut_bound || w.depth_w < img_w - cut_bound) covers = false;
+            const size_t b = (size_t)w.depth_h * w.depth_w * 2;
+            if (depth_kind == XM3D_DEPTH_U16 && b <= (size_t)PROJ_MAX_SMEM_DEPTH && b > stage_bytes) stage_bytes = b;
+        }
+    }
+    const int parts = parts_for(max_pts);
+    if (ws_bytes < xm3d_project_ws_bytes(n_views, total_pts, max_pts)) {
+        set_error("xm3d_project_batch: workspace too small");
+        return XM3D_ERR_WORKSPACE;
+    }
+    Carver c(ws);
+    xm3d_view_t *d_views = c.take<xm3d_view_t>(n_views);
+    unsigned long long *stage = c.take<unsigned long long>(total_pts + PROJ_PART);
+    int *part_cnt = c.take<int>((size_t)n_views * parts);
+    int64_t *part_off = c.take<int64_t>((size_t)n_views * parts);
+    int *view_flag = c.take<int>(n_views);
+
+    cudaMemcpyAsync(d_views, views_host, sizeof(xm3d_view_t) * n_views, cudaMemcpyHostToDevice, stream);
+
+    ProjParams P;
+    P.xyz = xyz; P.views = d_views; P.depth = depth; P.depth_kind = depth_kind; P.depth_scale = depth_scale;
+    P.img_w = img_w; P.img_h = img_h; P.cut = cut_bound; P.vis_thres = vis_thres;
+    P.vis = vis; P.mapping = mapping; P.stage = stage; P.part_cnt = part_cnt; P.view_flag = view_flag;
+    P.parts = parts; P.smem_depth_bytes = (int)stage_bytes; P.use_flag = (any_depth && !covers) ? 1 : 0;
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(project_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PROJ_MAX_SMEM_DEPTH);
+        cudaFuncSetAttribute(project_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PROJ_MAX_SMEM_DEPTH);
+        attr_set = true;
+    }
+    dim3 grid(parts, n_views);
+    if (P.use_flag) {
+        cudaMemsetAsync(view_flag, 0, sizeof(int) * n_views, stream);
+        project_kernel<true><<<grid, PROJ_THREADS, stage_bytes, stream>>>(P);
+    }
+    project_kernel<false><<<grid, PROJ_THREADS, stage_bytes, stream>>>(P);
+    project_scan_kernel<<<1, 1024, 0, stream>>>(part_cnt, n_views, parts, part_off, n_vis, vis_off, cap_vis, status);
+    if (vis_idx || rowcol || xyz_vis)
+        project_emit_kernel<<<grid, 256, 0, stream>>>(xyz, d_views, stage, part_cnt, part_off, parts, cap_vis,
+                                                      vis_idx, rowcol, xyz_vis);
+    return check_launch("xm3d_project_batch");
+}

@@ -1,0 +1,636 @@
+// Stage 1 — voxelization: grid quantisation, FNV-1 keys, unique / first-index / inverse maps.
+//
+// Replaces Voxelizer.voxelize after the matrix draw (reference dataset/voxelizer.py:110-122),
+// fnv_hash_vec / ravel_hash_vec (dataset/voxelization_utils.py:6-35) and the np.unique call of
+// sparse_quantize (:86, :95), batched over segments (one segment = one (scene, view)).
+//
+//   min pass      grid = floor(FMA-chain transform) per point; per-segment column minima
+//                 (warp-shuffle min, one atomicMin per warp and column)
+//   insert pass   key = FNV-1(grid - min); warp-cooperative open-addressing insert: lanes holding
+//                 the same key elect the lowest lane (= lowest point index) with match.any, only
+//                 that lane probes the segment's table (linear probing, 16-byte slots
+//                 {key, first index, rank}); winners of an empty slot append it to the segment's
+//                 unique list with one warp-aggregated atomicAdd
+//   sort pass     one CTA per segment orders the M unique keys ascending (np.unique's order):
+//                 bitonic sort in shared memory when M <= 4096, else a sample sort (4096 sorted
+//                 samples -> splitters -> buckets -> rank inside each bucket), writes the rank
+//                 into the table slot, `first`, and the voxel coordinates
+//   inverse pass  inverse[i] = rank stored in the slot point i resolved to
+//
+// Everything that decides an integer is exact: the transform is the fp64 FMA chain numpy's
+// dgemm performs, floor() is exact, keys are 64-bit so FNV collisions merge voxels exactly as
+// the reference's np.unique does.
+#include "common.cuh"
+
+namespace xm3d {
+
+constexpr unsigned long long KEY_EMPTY = 0xFFFFFFFFFFFFFFFFull;
+constexpr unsigned long long FNV_OFFSET = 14695981039346656037ull;
+constexpr unsigned long long FNV_PRIME = 1099511628211ull;
+constexpr int VOX_THREADS = 256;
+constexpr int SORT_THREADS = 1024;
+constexpr int SORT_SMALL = 4096;          // <= this many unique keys: whole-segment bitonic sort
+constexpr int SORT_SAMPLES = 4096;
+constexpr int GRID_LIMIT = 1 << 30;
+
+struct __align__(16) Slot {
+    unsigned long long key;
+    unsigned int first;   // lowest point index (within the segment) holding this key
+    unsigned int rank;    // rank of the key among the segment's unique keys
+};
+
+__host__ __device__ inline int64_t table_size(int64_t n) { return n + n / 2 + 32; }
+
+__device__ __forceinline__ unsigned long long mix64(unsigned long long h) {
+    h ^= h >> 33; h *= 0xff51afd7ed558ccdull;
+    h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ull;
+    h ^= h >> 33;
+    return h;
+}
+
+__device__ __forceinline__ unsigned long long fnv3(unsigned long long a, unsigned long long b,
+                                                   unsigned long long c) {
+    unsigned long long h = FNV_OFFSET;      // voxelization_utils.py:13-17: multiply, then xor the word
+    h *= FNV_PRIME; h ^= a;
+    h *= FNV_PRIME; h ^= b;
+    h *= FNV_PRIME; h ^= c;
+    return h;
+}
+
+// numpy's float64 -> uint64 cast on x86-64 (cvttsd2si below 2^63, wraps negatives)
+__device__ __forceinline__ unsigned long long f64_to_u64_numpy(double d) {
+    if (d < 9223372036854775808.0) return (unsigned long long)(long long)d;
+    return (unsigned long long)d;
+}
+
+// floor([x y z 1] @ RT.T[:, :3]) for one point: voxelizer.py:110-113
+__device__ __forceinline__ void grid_of(const float *__restrict__ p, const double *__restrict__ rt,
+                                        double out[3]) {
+    const double x = (double)p[0], y = (double)p[1], z = (double)p[2];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const double *r = rt + 4 * j;
+        double s = __dmul_rn(x, r[0]);
+        s = __fma_rn(y, r[1], s);
+        s = __fma_rn(z, r[2], s);
+        s = __fma_rn(1.0, r[3], s);
+        out[j] = floor(s);
+    }
+}
+
+// ---- plan: per-segment table offsets, zeroed counters -------------------------------------
+__global__ void __launch_bounds__(1024, 1)
+vox_plan_kernel(const int64_t *__restrict__ seg_off, int n_seg, int64_t cap, int64_t *__restrict__ tbl_off,
+                int64_t *__restrict__ total_eff, int *__restrict__ m, int *__restrict__ grid_min, int *status) {
+    __shared__ int64_t s_warp[32];
+    __shared__ int64_t s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // more elements than the caller's capacity: flag it and process nothing (never overrun)
+    const bool over = seg_off[n_seg] > cap;
+    if (tid == 0) {
+        s_carry = 0;
+        *total_eff = over ? 0 : seg_off[n_seg];
+        if (over && status) atomicOr(status, XM3D_FLAG_VIS_OVERFLOW);
+    }
+    __syncthreads();
+    for (int base = 0; base < n_seg; base += 1024) {
+        const int s = base + tid;
+        int64_t val = 0;
+        if (s < n_seg) {
+            val = table_size(over ? 0 : seg_off[s + 1] - seg_off[s]);
+            m[s] = 0;
+            if (grid_min) grid_min[3 * s] = grid_min[3 * s + 1] = grid_min[3 * s + 2] = 0x7fffffff;
+        }
+        int64_t incl = val;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int64_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const int64_t w = s_warp[lane];
+            int64_t wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int64_t t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            s_warp[lane] = wi - w;
+        }
+        __syncthreads();
+        const int64_t excl = s_carry + s_warp[warp] + incl - val;
+        if (s < n_seg) tbl_off[s] = excl;
+        __syncthreads();
+        if (tid == 1023) s_carry = excl + val;
+        __syncthreads();
+    }
+    if (tid == 0) tbl_off[n_seg] = s_carry;
+}
+
+__global__ void __launch_bounds__(256)
+vox_clear_kernel(Slot *__restrict__ tbl, const int64_t *__restrict__ tbl_off, int n_seg) {
+    const int64_t used = tbl_off[n_seg];
+    const uint4 e = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    uint4 *t = reinterpret_cast<uint4 *>(tbl);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < used; i += (int64_t)gridDim.x * blockDim.x)
+        t[i] = e;
+}
+
+// ---- min pass -----------------------------------------------------------------------------
+__global__ void __launch_bounds__(VOX_THREADS)
+vox_min_kernel(const float *__restrict__ xyz, const int64_t *__restrict__ seg_off, int n_seg,
+               const int64_t *__restrict__ total_eff, const double *__restrict__ rt, int *__restrict__ grid_min,
+               int *status) {
+    const int64_t total = *total_eff;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < total;
+    int s = 0;
+    int g[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff};
+    if (valid) {
+        s = seg_of(seg_off, n_seg, i);
+        double f[3];
+        grid_of(xyz + i * 3, rt + 12 * s, f);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            if (!(f[j] > -(double)GRID_LIMIT && f[j] < (double)GRID_LIMIT)) {
+                if (status) atomicOr(status, XM3D_FLAG_GRID_RANGE);
+                f[j] = 0.0;
+            }
+            g[j] = (int)f[j];
+        }
+    }
+    const unsigned act = __ballot_sync(0xffffffffu, valid);
+    if (!valid) return;
+    const unsigned same = __match_any_sync(act, s);
+    if (same == act) {                 // whole warp in one segment: shuffle-reduce, 3 atomics
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            int v = g[j];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const int t = __shfl_xor_sync(act, v, o);
+                // lanes outside `act` return garbage only if act is not the full mask; guard below
+                if ((act >> ((lane_id() ^ o) & 31)) & 1u) v = min(v, t);
+            }
+            g[j] = v;
+        }
+        if (lane_id() == (__ffs(act) - 1)) {
+            atomicMin(&grid_min[3 * s + 0], g[0]);
+            atomicMin(&grid_min[3 * s + 1], g[1]);
+            atomicMin(&grid_min[3 * s + 2], g[2]);
+        }
+    } else {
+        atomicMin(&grid_min[3 * s + 0], g[0]);
+        atomicMin(&grid_min[3 * s + 1], g[1]);
+        atomicMin(&grid_min[3 * s + 2], g[2]);
+    }
+}
+
+// ---- insert pass --------------------------------------------------------------------------
+// KEY_SRC 0: keys from xyz through the transform (voxelize); 1: keys given (unique_batch)
+template <int KEY_SRC>
+__global__ void __launch_bounds__(VOX_THREADS)
+vox_insert_kernel(const float *__restrict__ xyz, const unsigned long long *__restrict__ keys_in,
+                  const int64_t *__restrict__ seg_off, int n_seg, const int64_t *__restrict__ total_eff,
+                  const double *__restrict__ rt, const int *__restrict__ grid_min, Slot *__restrict__ tbl,
+                  const int64_t *__restrict__ tbl_off, unsigned int *__restrict__ pslot,
+                  unsigned int *__restrict__ uniq, int *__restrict__ m, int *status) {
+    const int64_t total = *total_eff;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < total;
+    const unsigned act = __ballot_sync(0xffffffffu, valid);
+    if (!valid) return;
+    const int lane = lane_id();
+    const int s = seg_of(seg_off, n_seg, i);
+    const int64_t base = seg_off[s];
+    unsigned long long key;
+    if (KEY_SRC == 0) {
+        double f[3];
+        grid_of(xyz + i * 3, rt + 12 * s, f);
+        unsigned long long w[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            if (!(f[j] > -(double)GRID_LIMIT && f[j] < (double)GRID_LIMIT)) f[j] = 0.0;
+            // floor(grid - min) of two integers is their exact difference (voxelizer.py:115-119)
+            w[j] = (unsigned long long)(long long)((int)f[j] - grid_min[3 * s + j]);
+        }
+        key = fnv3(w[0], w[1], w[2]);
+    } else {
+        key = keys_in[i];
+    }
+    if (key == KEY_EMPTY) {              // 2^-64 event: the sentinel value cannot be stored
+        if (status) atomicOr(status, XM3D_FLAG_KEY_SENTINEL);
+        key = KEY_EMPTY - 1;
+    }
+    // warp-cooperative de-duplication: one prober per distinct (segment, key) in the warp
+    const unsigned peers = __match_any_sync(act, key) & __match_any_sync(act, s);
+    const int leader = __ffs(peers) - 1;
+    unsigned int slot = 0;
+    bool is_new = false;
+    if (lane == leader) {
+        Slot *tb = tbl + tbl_off[s];
+        const unsigned int size = (unsigned int)(tbl_off[s + 1] - tbl_off[s]);
+        slot = (unsigned int)(((mix64(key) >> 32) * (unsigned long long)size) >> 32);
+        for (unsigned int probe = 0; probe <= size; ++probe) {
+            unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(&tb[slot].key);
+            if (cur == KEY_EMPTY) {
+                cur = atomicCAS(&tb[slot].key, KEY_EMPTY, key);
+                if (cur == KEY_EMPTY) { is_new = true; break; }
+            }
+            if (cur == key) break;
+            slot = (slot + 1 == size) ? 0u : slot + 1;
+        }
+        atomicMin(&tb[slot].first, (unsigned int)(i - base));     // leader = lowest index of its peers
+    }
+    slot = __shfl_sync(act, slot, leader);
+    pslot[i] = slot;
+    // append new unique slots: one atomicAdd per warp when the warp sits in one segment
+    const unsigned newm = __ballot_sync(act, is_new);
+    const unsigned sameseg = __match_any_sync(act, s);
+    if (sameseg == act) {
+        if (newm) {
+            int start = 0;
+            const int first_lane = __ffs(act) - 1;
+            if (lane == first_lane) start = atomicAdd(&m[s], __popc(newm));
+            start = __shfl_sync(act, start, first_lane);
+            if (is_new) uniq[base + start + __popc(newm & ((1u << lane) - 1u))] = slot;
+        }
+    } else if (is_new) {
+        uniq[base + atomicAdd(&m[s], 1)] = slot;
+    }
+}
+
+// ---- sort pass ----------------------------------------------------------------------------
+template <typename K, typename V, bool HAS_V>
+__device__ __forceinline__ void bitonic_smem(K *k, V *v, int n /*pow2*/) {
+    for (int size = 2; size <= n; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = threadIdx.x; t < (n >> 1); t += blockDim.x) {
+                const int lo = 2 * t - (t & (stride - 1));     // insert a 0 at bit log2(stride)
+                const int hi = lo + stride;
+                const bool up = (lo & size) == 0;
+                const K a = k[lo], b = k[hi];
+                if ((a > b) == up) {
+                    k[lo] = b; k[hi] = a;
+                    if (HAS_V) { const V x = v[lo]; v[lo] = v[hi]; v[hi] = x; }
+                }
+            }
+            __syncthreads();
+        }
+}
+
+struct SortOut {
+    int *first;            // [cap] first-occurrence index, unique order
+    int *voxel_xyz;        // [cap,3] or null
+    const float *xyz;      // for voxel_xyz
+    const double *rt;
+    const int *grid_min;
+};
+
+__device__ __forceinline__ void emit_rank(Slot *tb, unsigned int slot, int rank, int64_t base, int64_t ubase,
+                                          int s, const SortOut &O) {
+    tb[slot].rank = (unsigned int)rank;
+    const unsigned int f = tb[slot].first;
+    O.first[ubase + rank] = (int)f;
+    if (O.voxel_xyz) {
+        double g[3];
+        grid_of(O.xyz + (base + f) * 3, O.rt + 12 * s, g);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            if (!(g[j] > -(double)GRID_LIMIT && g[j] < (double)GRID_LIMIT)) g[j] = 0.0;
+            O.voxel_xyz[(ubase + rank) * 3 + j] = (int)g[j] - O.grid_min[3 * s + j];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(SORT_THREADS, 1)
+vox_sort_kernel(const int64_t *__restrict__ seg_off, int n_seg, Slot *__restrict__ tbl,
+                const int64_t *__restrict__ tbl_off, const unsigned int *__restrict__ uniq,
+                const int *__restrict__ m, int64_t *__restrict__ uniq_off,
+                unsigned long long *__restrict__ bk_key, unsigned int *__restrict__ bk_slot, SortOut O) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    unsigned long long *s_key = reinterpret_cast<unsigned long long *>(smem);             // 4096 x 8
+    unsigned int *s_aux = reinterpret_cast<unsigned int *>(smem + SORT_SAMPLES * 8);      // 4096 x 4
+    __shared__ int64_t s_red[32];
+    __shared__ int s_wsum[32];
+    const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int M = m[s];
+    const int64_t base = seg_off[s];
+    Slot *tb = tbl + tbl_off[s];
+    const unsigned int *U = uniq + base;
+
+    // exclusive prefix of the unique counts of the segments before this one
+    int64_t part = 0;
+    for (int t = tid; t < s; t += SORT_THREADS) part += m[t];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) s_red[warp] = part;
+    __syncthreads();
+    int64_t ubase = 0;
+    for (int w = 0; w < 32; ++w) ubase += s_red[w];
+    if (tid == 0) {
+        uniq_off[s] = ubase;
+        if (s == n_seg - 1) uniq_off[n_seg] = ubase + M;
+    }
+    if (M == 0) return;
+
+    if (M <= SORT_SMALL) {
+        int np = 2;
+        while (np < M) np <<= 1;
+        for (int t = tid; t < np; t += SORT_THREADS) {
+            const unsigned int sl = (t < M) ? U[t] : 0u;
+            s_key[t] = (t < M) ? tb[sl].key : KEY_EMPTY;
+            s_aux[t] = sl;
+        }
+        __syncthreads();
+        bitonic_smem<unsigned long long, unsigned int, true>(s_key, s_aux, np);
+        for (int t = tid; t < M; t += SORT_THREADS) emit_rank(tb, s_aux[t], t, base, ubase, s, O);
+        return;
+    }
+
+    // ---- sample sort
+    const int S = (M < 65536) ? 2048 : 4096;             // buckets
+    const int step = SORT_SAMPLES / S;
+    for (int t = tid; t < SORT_SAMPLES; t += SORT_THREADS)
+        s_key[t] = tb[U[(int)(((int64_t)t * M) / SORT_SAMPLES)]].key;
+    __syncthreads();
+    bitonic_smem<unsigned long long, unsigned int, false>(s_key, nullptr, SORT_SAMPLES);
+    // splitter j (0..S-2) = sorted sample (j+1)*step - 1; bucket = #splitters < key
+    auto bucket_of = [&](unsigned long long key) {
+        int lo = 0, hi = S - 1;                            // count of splitters < key in [0, S-1]
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (s_key[(mid + 1) * step - 1] < key) lo = mid + 1; else hi = mid;
+        }
+        return lo;
+    };
+    int *hist = reinterpret_cast<int *>(s_aux);
+    for (int t = tid; t < S; t += SORT_THREADS) hist[t] = 0;
+    __syncthreads();
+    for (int t = tid; t < M; t += SORT_THREADS) atomicAdd(&hist[bucket_of(tb[U[t]].key)], 1);
+    __syncthreads();
+    // exclusive scan of hist[S] in place (S / 1024 entries per thread)
+    {
+        const int per = S / SORT_THREADS;
+        int loc[4], sum = 0;
+        for (int j = 0; j < per; ++j) { loc[j] = hist[tid * per + j]; sum += loc[j]; }
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const int w = s_wsum[lane];
+            int wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            s_wsum[lane] = wi - w;
+        }
+        __syncthreads();
+        int run = s_wsum[warp] + incl - sum;
+        for (int j = 0; j < per; ++j) { hist[tid * per + j] = run; run += loc[j]; }
+    }
+    __syncthreads();
+    // scatter into buckets; afterwards hist[b] = end of bucket b
+    unsigned long long *bk = bk_key + base;
+    unsigned int *bs = bk_slot + base;
+    for (int t = tid; t < M; t += SORT_THREADS) {
+        const unsigned int sl = U[t];
+        const unsigned long long key = tb[sl].key;
+        const int d = atomicAdd(&hist[bucket_of(key)], 1);
+        bk[d] = key;
+        bs[d] = sl;
+    }
+    __syncthreads();
+    // rank inside each bucket: one warp per bucket, each lane counts the smaller keys
+    for (int b = warp; b < S; b += SORT_THREADS / 32) {
+        const int lo = (b == 0) ? 0 : hist[b - 1], hi = hist[b];
+        for (int e = lo + lane; e < hi; e += 32) {
+            const unsigned long long key = bk[e];
+            int smaller = 0;
+            for (int q = lo; q < hi; ++q) smaller += (bk[q] < key) ? 1 : 0;
+            emit_rank(tb, bs[e], lo + smaller, base, ubase, s, O);
+        }
+    }
+}
+
+// ---- inverse pass -------------------------------------------------------------------------
+__global__ void __launch_bounds__(VOX_THREADS)
+vox_inverse_kernel(const int64_t *__restrict__ seg_off, int n_seg, const int64_t *__restrict__ total_eff,
+                   const Slot *__restrict__ tbl, const int64_t *__restrict__ tbl_off,
+                   const unsigned int *__restrict__ pslot, const int64_t *__restrict__ uniq_off, int collate,
+                   int *__restrict__ inverse, int *__restrict__ counts) {
+    const int64_t total = *total_eff;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int s = seg_of(seg_off, n_seg, i);
+    const int rank = (int)tbl[tbl_off[s] + pslot[i]].rank;
+    inverse[i] = rank + (collate ? (int)uniq_off[s] : 0);
+    if (counts) atomicAdd(&counts[uniq_off[s] + rank], 1);
+}
+
+// ---- elementwise hashes (drop-ins for fnv_hash_vec / ravel_hash_vec on float64 rows) --------
+__global__ void __launch_bounds__(256)
+fnv_f64_kernel(const double *__restrict__ coords, int64_t n, int dim, unsigned long long *__restrict__ keys) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long h = FNV_OFFSET;
+    for (int j = 0; j < dim; ++j) {
+        h *= FNV_PRIME;
+        h ^= f64_to_u64_numpy(coords[i * dim + j]);
+    }
+    keys[i] = h;
+}
+
+// column min / max of a float64 [n, dim] matrix (dim <= 8) into ws[0..dim) / ws[8..8+dim)
+__global__ void __launch_bounds__(256)
+colminmax_f64_kernel(const double *__restrict__ coords, int64_t n, int dim, double *__restrict__ ws) {
+    // ordered-int trick is unnecessary: values are compared as doubles through atomicCAS loops
+    __shared__ double s_min[8][8], s_max[8][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double mn[8], mx[8];
+    for (int j = 0; j < 8; ++j) { mn[j] = INFINITY; mx[j] = -INFINITY; }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        for (int j = 0; j < dim; ++j) {
+            const double v = coords[i * dim + j];
+            mn[j] = fmin(mn[j], v); mx[j] = fmax(mx[j], v);
+        }
+    for (int j = 0; j < dim; ++j) {
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[j] = fmin(mn[j], __shfl_xor_sync(0xffffffffu, mn[j], o));
+            mx[j] = fmax(mx[j], __shfl_xor_sync(0xffffffffu, mx[j], o));
+        }
+        if (lane == 0) { s_min[warp][j] = mn[j]; s_max[warp][j] = mx[j]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < dim) {
+        const int j = threadIdx.x;
+        double a = INFINITY, b = -INFINITY;
+        for (int w = 0; w < 8; ++w) { a = fmin(a, s_min[w][j]); b = fmax(b, s_max[w][j]); }
+        // atomic min/max on doubles via CAS
+        unsigned long long *pa = reinterpret_cast<unsigned long long *>(ws + j);
+        unsigned long long old = *pa, assumed;
+        do { assumed = old; if (__longlong_as_double(assumed) <= a) break;
+             old = atomicCAS(pa, assumed, (unsigned long long)__double_as_longlong(a)); } while (old != assumed);
+        unsigned long long *pb = reinterpret_cast<unsigned long long *>(ws + 8 + j);
+        old = *pb;
+        do { assumed = old; if (__longlong_as_double(assumed) >= b) break;
+             old = atomicCAS(pb, assumed, (unsigned long long)__double_as_longlong(b)); } while (old != assumed);
+    }
+}
+
+__global__ void init_minmax_kernel(double *ws) {
+    if (threadIdx.x < 8) { ws[threadIdx.x] = INFINITY; ws[8 + threadIdx.x] = -INFINITY; }
+}
+
+// ravel_hash_vec (voxelization_utils.py:21-35): arr -= min; arr = uint64(arr); radix = max + 1;
+// key = ((k + a_0) * radix_1 + a_1) * radix_2 + ... + a_last
+__global__ void __launch_bounds__(256)
+ravel_f64_kernel(const double *__restrict__ coords, int64_t n, int dim, const double *__restrict__ ws,
+                 unsigned long long *__restrict__ keys) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long key = 0;
+    for (int j = 0; j < dim - 1; ++j) {
+        key += f64_to_u64_numpy(__dsub_rn(coords[i * dim + j], ws[j]));
+        key *= f64_to_u64_numpy(__dsub_rn(ws[8 + j + 1], ws[j + 1])) + 1ull;
+    }
+    key += f64_to_u64_numpy(__dsub_rn(coords[i * dim + dim - 1], ws[dim - 1]));
+    keys[i] = key;
+}
+
+struct VoxWs {
+    Slot *tbl;
+    int64_t *tbl_off, *total_eff;
+    unsigned int *pslot, *uniq, *bk_slot;
+    unsigned long long *bk_key;
+    int *grid_min;
+};
+
+static VoxWs carve_vox(void *ws, int n_seg, int64_t cap, size_t *bytes) {
+    Carver c(ws);
+    VoxWs w;
+    w.tbl = c.take<Slot>((size_t)(table_size(cap) + 32 * (int64_t)n_seg));
+    w.tbl_off = c.take<int64_t>(n_seg + 1);
+    w.total_eff = c.take<int64_t>(1);
+    w.pslot = c.take<unsigned int>(cap);
+    w.uniq = c.take<unsigned int>(cap);
+    w.bk_slot = c.take<unsigned int>(cap);
+    w.bk_key = c.take<unsigned long long>(cap);
+    w.grid_min = c.take<int>(3 * (size_t)n_seg);
+    *bytes = c.off + 256;
+    return w;
+}
+
+static int run_unique(const float *xyz, const unsigned long long *keys, const int64_t *seg_off, int n_seg,
+                      int64_t cap, const double *rt, int *m, int64_t *uniq_off, int *first, int *counts,
+                      int *inverse, int collate, int *voxel_xyz, int *grid_min_out, void *ws, size_t ws_bytes,
+                      int *status, cudaStream_t stream, const char *who) {
+    size_t need = 0;
+    VoxWs w = carve_vox(ws, n_seg, cap, &need);
+    if (ws_bytes < need) {
+        set_error("%s: workspace too small (%zu < %zu)", who, ws_bytes, need);
+        return XM3D_ERR_WORKSPACE;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(vox_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SAMPLES * 12);
+        attr_set = true;
+    }
+    int *gmin = grid_min_out ? grid_min_out : w.grid_min;
+    const unsigned blocks = (unsigned)((cap + VOX_THREADS - 1) / VOX_THREADS);
+    vox_plan_kernel<<<1, 1024, 0, stream>>>(seg_off, n_seg, cap, w.tbl_off, w.total_eff, m, xyz ? gmin : nullptr,
+                                            status);
+    vox_clear_kernel<<<(unsigned)(sm_count() * 8), 256, 0, stream>>>(w.tbl, w.tbl_off, n_seg);
+    if (counts) cudaMemsetAsync(counts, 0, sizeof(int) * cap, stream);
+    if (blocks) {
+        if (xyz) {
+            vox_min_kernel<<<blocks, VOX_THREADS, 0, stream>>>(xyz, seg_off, n_seg, w.total_eff, rt, gmin, status);
+            vox_insert_kernel<0><<<blocks, VOX_THREADS, 0, stream>>>(xyz, nullptr, seg_off, n_seg, w.total_eff, rt, gmin,
+                                                                     w.tbl, w.tbl_off, w.pslot, w.uniq, m, status);
+        } else {
+            vox_insert_kernel<1><<<blocks, VOX_THREADS, 0, stream>>>(nullptr, keys, seg_off, n_seg, w.total_eff, nullptr,
+                                                                     nullptr, w.tbl, w.tbl_off, w.pslot, w.uniq, m,
+                                                                     status);
+        }
+    }
+    SortOut O;
+    O.first = first; O.voxel_xyz = xyz ? voxel_xyz : nullptr; O.xyz = xyz; O.rt = rt; O.grid_min = gmin;
+    vox_sort_kernel<<<n_seg, SORT_THREADS, SORT_SAMPLES * 12, stream>>>(seg_off, n_seg, w.tbl, w.tbl_off, w.uniq, m,
+                                                                        uniq_off, w.bk_key, w.bk_slot, O);
+    if (blocks && inverse)
+        vox_inverse_kernel<<<blocks, VOX_THREADS, 0, stream>>>(seg_off, n_seg, w.total_eff, w.tbl, w.tbl_off, w.pslot,
+                                                               uniq_off, collate, inverse, counts);
+    return check_launch(who);
+}
+
+}  // namespace xm3d
+
+using namespace xm3d;
+
+extern "C" size_t xm3d_unique_ws_bytes(int32_t n_seg, int64_t cap) {
+    size_t b = 0;
+    carve_vox(nullptr, n_seg, cap, &b);
+    return b;
+}
+extern "C" size_t xm3d_voxelize_ws_bytes(int32_t n_seg, int64_t cap) { return xm3d_unique_ws_bytes(n_seg, cap); }
+
+extern "C" int xm3d_unique_batch(const uint64_t *keys, const int64_t *seg_off, int32_t n_seg, int64_t cap,
+                                 int32_t *m, int64_t *uniq_off, int32_t *first, int32_t *counts,
+                                 int32_t *inverse, int32_t collate, void *ws, size_t ws_bytes, int32_t *status,
+                                 xm3d_stream_t stream) {
+    XM3D_REQUIRE(n_seg > 0 && cap >= 0, "bad sizes");
+    XM3D_REQUIRE(keys && seg_off && m && uniq_off && first && ws, "null pointer");
+    XM3D_REQUIRE(cap < (int64_t)1 << 31, "cap must fit int32");
+    return run_unique(nullptr, reinterpret_cast<const unsigned long long *>(keys), seg_off, n_seg, cap, nullptr, m,
+                      uniq_off, first, counts, inverse, collate, nullptr, nullptr, ws, ws_bytes, status,
+                      static_cast<cudaStream_t>(stream), "xm3d_unique_batch");
+}
+
+extern "C" int xm3d_voxelize_batch(const float *xyz, const int64_t *seg_off, int32_t n_seg, int64_t cap,
+                                   const double *rt, int32_t *m, int64_t *uniq_off, int32_t *first,
+                                   int32_t *inverse, int32_t collate, int32_t *voxel_xyz, int32_t *grid_min,
+                                   void *ws, size_t ws_bytes, int32_t *status, xm3d_stream_t stream) {
+    XM3D_REQUIRE(n_seg > 0 && cap >= 0, "bad sizes");
+    XM3D_REQUIRE(xyz && seg_off && rt && m && uniq_off && first && ws, "null pointer");
+    XM3D_REQUIRE(cap < (int64_t)1 << 31, "cap must fit int32");
+    return run_unique(xyz, nullptr, seg_off, n_seg, cap, rt, m, uniq_off, first, nullptr, inverse, collate,
+                      voxel_xyz, grid_min, ws, ws_bytes, status, static_cast<cudaStream_t>(stream),
+                      "xm3d_voxelize_batch");
+}
+
+extern "C" int xm3d_fnv_hash_f64(const double *coords, int64_t n, int32_t dim, uint64_t *keys,
+                                 xm3d_stream_t stream) {
+    XM3D_REQUIRE(n >= 0 && dim > 0, "bad sizes");
+    if (n == 0) return XM3D_OK;
+    XM3D_REQUIRE(coords && keys, "null pointer");
+    fnv_f64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        coords, n, dim, reinterpret_cast<unsigned long long *>(keys));
+    return check_launch("xm3d_fnv_hash_f64");
+}
+
+extern "C" size_t xm3d_ravel_ws_bytes(int32_t dim) { (void)dim; return 256; }
+
+extern "C" int xm3d_ravel_hash_f64(const double *coords, int64_t n, int32_t dim, uint64_t *keys, void *ws,
+                                   size_t ws_bytes, xm3d_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    XM3D_REQUIRE(n >= 0 && dim > 0 && dim <= 8, "dim must be in 1..8");
+    if (n == 0) return XM3D_OK;
+    XM3D_REQUIRE(coords && keys && ws && ws_bytes >= 128, "null pointer / workspace");
+    double *mm = static_cast<double *>(ws);
+    init_minmax_kernel<<<1, 32, 0, stream>>>(mm);
+    unsigned blocks = (unsigned)((n + 255) / 256);
+    if (blocks > (unsigned)sm_count() * 8) blocks = sm_count() * 8;
+    colminmax_f64_kernel<<<blocks, 256, 0, stream>>>(coords, n, dim, mm);
+    ravel_f64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(coords, n, dim, mm,
+                                                                       reinterpret_cast<unsigned long long *>(keys));
+    return check_launch("xm3d_ravel_hash_f64");
+}

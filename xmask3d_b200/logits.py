@@ -1,0 +1,37 @@
+"""Drop-in for `XMASK3d.cal_pred_logits` (reference models/xmask3d.py:129-143; twin
+models/modeling/meta_arch/odise.py:170-194) and `ensemble_logits_with_labels`
+(models/modeling/meta_arch/helper.py:72-97) on libxm3d's tcgen05 kernel.
+"""
+from __future__ import annotations
+
+from typing import List
+
+import torch
+
+from . import ops
+
+
+def ensemble_logits_with_labels(logits: torch.Tensor, labels: List[List[str]], ensemble_method: str = "max"):
+    """helper.py:72-97 — kept in torch: it is a column regrouping of an existing logits tensor.
+    (`cal_pred_logits` below fuses the same reduction into the GEMM epilogue.)"""
+    len_list = [len(l) for l in labels]
+    assert logits.shape[-1] == sum(len_list), f"{logits.shape[-1]} != {sum(len_list)}"
+    assert ensemble_method in ["mean", "max"]
+    ensemble_logits = torch.zeros(*logits.shape[:-1], len(labels), dtype=logits.dtype, device=logits.device)
+    if ensemble_method == "max":
+        for i in range(len(labels)):
+            ensemble_logits[..., i] = logits[..., sum(len_list[:i]):sum(len_list[:i + 1])].max(dim=-1).values
+    else:
+        for i in range(len(labels)):
+            ensemble_logits[..., i] = logits[..., sum(len_list[:i]):sum(len_list[:i + 1])].mean(dim=-1)
+    return ensemble_logits
+
+
+def cal_pred_logits(outputs, ensemble_method: str = "max", want_argmax: bool = False):
+    """outputs: dict with mask_embed [B,K,C], text_embed [T-1,C], null_embed [1,C], labels
+    (list of synonym lists), logit_scale (tensor or float).  Returns [B,K,T] float32."""
+    scale = outputs["logit_scale"]
+    scale = float(scale.item()) if torch.is_tensor(scale) else float(scale)
+    sizes = [len(l) for l in outputs["labels"]]
+    return ops.logits(outputs["mask_embed"], outputs["text_embed"], outputs["null_embed"], sizes, scale,
+                      ensemble=ensemble_method, want_argmax=want_argmax)

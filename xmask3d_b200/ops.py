@@ -1,0 +1,328 @@
+"""Torch-tensor front end of the C ABI: allocates outputs / workspaces with torch, passes raw
+device pointers and the current CUDA stream to libxm3d.  Everything here is batched over
+segments (one segment = one (scene, view)); the reference-shaped single-call shims live in
+voxelizer.py / voxelization_utils.py / fusion_util.py / fuser.py / logits.py.
+
+No CPU fallback: every function requires CUDA tensors (or moves numpy input to `device`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise L.Xm3dError("xmask3d_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def _dev_contig(t: torch.Tensor, dtype) -> torch.Tensor:
+    assert t.is_cuda, "expected a CUDA tensor"
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+# ----------------------------------------------------------------------------- stage 2
+@dataclass
+class Projection:
+    vis: torch.Tensor                 # uint8 [total_pts]   (views concatenated, see out_off)
+    n_vis: torch.Tensor               # int32 [V]
+    vis_off: torch.Tensor             # int64 [V+1]
+    vis_idx: torch.Tensor             # int32 [cap_vis]
+    rowcol: torch.Tensor              # int32 [cap_vis,2]   (x_label, y_label)
+    xyz_vis: torch.Tensor             # float32 [cap_vis,3]
+    status: torch.Tensor              # int32 [1]
+    out_off: np.ndarray               # int64 [V+1] host: start of every view in `vis` / `mapping`
+    mapping: Optional[torch.Tensor] = None   # int64 [total_pts,3]
+
+
+def make_views(w2c: np.ndarray, intr: Sequence[float], pt_off: Sequence[int], n_pts: Sequence[int],
+               depth_shape=None, depth_off: Optional[Sequence[int]] = None):
+    """Build the host array of xm3d_view_t records.  w2c: [V,4,4] float64 world->camera
+    (np.linalg.inv(pose), reference models/utils/fusion_util.py:70); intr = (fx,fy,cx,cy)."""
+    v = len(n_pts)
+    arr = (L.View * v)()
+    out_off = np.zeros(v + 1, np.int64)
+    for i in range(v):
+        r = arr[i]
+        m = np.ascontiguousarray(w2c[i], np.float64)
+        for j in range(12):
+            r.w2c[j] = m[j // 4, j % 4]
+        r.fx, r.fy, r.cx, r.cy = (float(x) for x in intr)
+        r.pt_off, r.n_pts, r.out_off = int(pt_off[i]), int(n_pts[i]), int(out_off[i])
+        out_off[i + 1] = out_off[i] + int(n_pts[i])
+        if depth_shape is not None:
+            r.depth_h, r.depth_w = int(depth_shape[0]), int(depth_shape[1])
+            r.depth_off = int(depth_off[i]) if depth_off is not None else i * int(depth_shape[0]) * int(depth_shape[1])
+        else:
+            r.depth_off = -1
+    return arr, out_off
+
+
+def project_batch(xyz: torch.Tensor, views, out_off: np.ndarray, depth: Optional[torch.Tensor],
+                  depth_scale: float = 1000.0, image_dim=(320, 240), cut_bound: int = 10,
+                  vis_thres: float = 0.25, cap_vis: Optional[int] = None, want_mapping: bool = False,
+                  want_compact: bool = True, ws: Optional[torch.Tensor] = None) -> Projection:
+    """xyz: float32 [sum N_scene,3] (all scenes concatenated); views: (View * V) host records;
+    depth: uint16 / int16-viewed / float64 CUDA tensor holding every view's image, or None."""
+    _require_cuda()
+    dev = xyz.device
+    xyz = _dev_contig(xyz, torch.float32)
+    n_views = len(views)
+    total = int(out_off[-1])
+    cap = total if cap_vis is None else int(cap_vis)
+    if depth is None:
+        kind = L.DEPTH_NONE
+    elif depth.dtype == torch.float64:
+        kind = L.DEPTH_F64
+    elif depth.dtype in (torch.uint16, torch.int16):
+        kind = L.DEPTH_U16
+    else:
+        raise TypeError(f"depth dtype {depth.dtype}: expected uint16 (raw) or float64 (metres)")
+    if depth is not None:
+        assert depth.is_cuda and depth.is_contiguous()
+    vis = torch.empty(max(total, 1), dtype=torch.uint8, device=dev)
+    mapping = torch.empty((max(total, 1), 3), dtype=torch.int64, device=dev) if want_mapping else None
+    n_vis = torch.zeros(max(n_views, 1), dtype=torch.int32, device=dev)
+    vis_off = torch.zeros(n_views + 1, dtype=torch.int64, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    vis_idx = rowcol = xyz_vis = None
+    if want_compact:
+        vis_idx = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
+        rowcol = torch.empty((max(cap, 1), 2), dtype=torch.int32, device=dev)
+        xyz_vis = torch.empty((max(cap, 1), 3), dtype=torch.float32, device=dev)
+    max_pts = max((int(v.n_pts) for v in views), default=0)
+    need = L.lib().xm3d_project_ws_bytes(n_views, total, max_pts)
+    if ws is None or ws.numel() < need:
+        ws = _ws(need, dev)
+    L.check(L.lib().xm3d_project_batch(
+        _ptr(xyz), C.cast(views, C.c_void_p), n_views, total, _ptr(depth), kind, float(depth_scale),
+        int(image_dim[0]), int(image_dim[1]), int(cut_bound), float(vis_thres),
+        _ptr(vis), _ptr(mapping), _ptr(n_vis), _ptr(vis_off), cap, _ptr(vis_idx), _ptr(rowcol), _ptr(xyz_vis),
+        _ptr(ws), ws.numel(), _ptr(status), _stream()))
+    return Projection(vis, n_vis, vis_off, vis_idx, rowcol, xyz_vis, status, out_off, mapping)
+
+
+# ----------------------------------------------------------------------------- stage 1
+@dataclass
+class Unique:
+    m: torch.Tensor          # int32 [n_seg] unique count
+    uniq_off: torch.Tensor   # int64 [n_seg+1]
+    first: torch.Tensor      # int32 [cap] first-occurrence index (within segment), unique order
+    inverse: torch.Tensor    # int32 [cap]
+    counts: Optional[torch.Tensor]
+    status: torch.Tensor
+    voxel_xyz: Optional[torch.Tensor] = None   # int32 [cap,3]
+    grid_min: Optional[torch.Tensor] = None    # int32 [n_seg,3]
+
+
+def unique_batch(keys: torch.Tensor, seg_off: torch.Tensor, cap: Optional[int] = None, collate: bool = False,
+                 want_counts: bool = False) -> Unique:
+    """np.unique(keys, return_index, return_inverse[, return_counts]) per segment.
+    keys: int64/uint64-viewed CUDA tensor; seg_off int64 [n_seg+1] CUDA."""
+    _require_cuda()
+    dev = keys.device
+    keys = keys.contiguous()
+    assert keys.element_size() == 8
+    seg_off = _dev_contig(seg_off, torch.int64)
+    n_seg = seg_off.numel() - 1
+    cap = int(keys.numel()) if cap is None else int(cap)
+    m = torch.zeros(n_seg, dtype=torch.int32, device=dev)
+    uniq_off = torch.zeros(n_seg + 1, dtype=torch.int64, device=dev)
+    first = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
+    inverse = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
+    counts = torch.zeros(max(cap, 1), dtype=torch.int32, device=dev) if want_counts else None
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws = _ws(L.lib().xm3d_unique_ws_bytes(n_seg, cap), dev)
+    L.check(L.lib().xm3d_unique_batch(_ptr(keys), _ptr(seg_off), n_seg, cap, _ptr(m), _ptr(uniq_off), _ptr(first),
+                                      _ptr(counts), _ptr(inverse), int(collate), _ptr(ws), ws.numel(),
+                                      _ptr(status), _stream()))
+    return Unique(m, uniq_off, first, inverse, counts, status)
+
+
+def voxelize_batch(xyz: torch.Tensor, seg_off: torch.Tensor, rt: torch.Tensor, cap: Optional[int] = None,
+                   collate: bool = False, ws: Optional[torch.Tensor] = None) -> Unique:
+    """xyz float32 [cap,3] CUDA (segments concatenated); rt float64 [n_seg,3,4] (rows 0..2 of the
+    rigid transformation, reference dataset/voxelizer.py:104-108)."""
+    _require_cuda()
+    dev = xyz.device
+    xyz = _dev_contig(xyz, torch.float32)
+    seg_off = _dev_contig(seg_off, torch.int64)
+    rt = _dev_contig(rt, torch.float64)
+    n_seg = seg_off.numel() - 1
+    assert rt.numel() == n_seg * 12
+    cap = int(xyz.shape[0]) if cap is None else int(cap)
+    m = torch.zeros(n_seg, dtype=torch.int32, device=dev)
+    uniq_off = torch.zeros(n_seg + 1, dtype=torch.int64, device=dev)
+    first = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
+    inverse = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
+    voxel = torch.empty((max(cap, 1), 3), dtype=torch.int32, device=dev)
+    gmin = torch.empty((n_seg, 3), dtype=torch.int32, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    need = L.lib().xm3d_voxelize_ws_bytes(n_seg, cap)
+    if ws is None or ws.numel() < need:
+        ws = _ws(need, dev)
+    L.check(L.lib().xm3d_voxelize_batch(_ptr(xyz), _ptr(seg_off), n_seg, cap, _ptr(rt), _ptr(m), _ptr(uniq_off),
+                                        _ptr(first), _ptr(inverse), int(collate), _ptr(voxel), _ptr(gmin),
+                                        _ptr(ws), ws.numel(), _ptr(status), _stream()))
+    return Unique(m, uniq_off, first, inverse, None, status, voxel, gmin)
+
+
+def fnv_hash(coords: torch.Tensor) -> torch.Tensor:
+    """fnv_hash_vec on a float64 [n,dim] CUDA tensor -> int64 tensor holding the uint64 bits."""
+    _require_cuda()
+    coords = _dev_contig(coords, torch.float64)
+    n, dim = coords.shape
+    keys = torch.empty(n, dtype=torch.int64, device=coords.device)
+    L.check(L.lib().xm3d_fnv_hash_f64(_ptr(coords), n, dim, _ptr(keys), _stream()))
+    return keys
+
+
+def ravel_hash(coords: torch.Tensor) -> torch.Tensor:
+    _require_cuda()
+    coords = _dev_contig(coords, torch.float64)
+    n, dim = coords.shape
+    keys = torch.empty(n, dtype=torch.int64, device=coords.device)
+    ws = _ws(L.lib().xm3d_ravel_ws_bytes(dim), coords.device)
+    L.check(L.lib().xm3d_ravel_hash_f64(_ptr(coords), n, dim, _ptr(keys), _ptr(ws), ws.numel(), _stream()))
+    return keys
+
+
+# ----------------------------------------------------------------------------- stage 3
+THR = {"ge0.5": L.THR_GE_HALF, "sigmoid_ge0.5": L.THR_SIGMOID_GE_HALF, "sigmoid_gt0.5": L.THR_SIGMOID_GT_HALF}
+
+
+def mask_words(k: int) -> int:
+    return (int(k) + 31) // 32
+
+
+def gather_masks(masks: torch.Tensor, rowcol: torch.Tensor, seg_off: torch.Tensor, mode: str = "ge0.5",
+                 cap: Optional[int] = None, want_counts: bool = False, ws: Optional[torch.Tensor] = None):
+    """masks [n_seg,k,h,w] bool/uint8/float32 CUDA; rowcol int32 [cap,2].
+    Returns (member uint32-as-int32 [cap,words], counts int32 [n_seg,k] or None)."""
+    _require_cuda()
+    dev = masks.device
+    assert masks.dim() == 4
+    n_seg, k, h, w = masks.shape
+    if masks.dtype == torch.bool:
+        masks = masks.view(torch.uint8)
+    if masks.dtype == torch.uint8:
+        kind = L.MASK_U8
+    else:
+        masks, kind = masks.to(torch.float32), L.MASK_F32
+    masks = masks.contiguous()
+    rowcol = _dev_contig(rowcol, torch.int32)
+    seg_off = _dev_contig(seg_off, torch.int64)
+    assert seg_off.numel() == n_seg + 1
+    cap = int(rowcol.shape[0]) if cap is None else int(cap)
+    words = mask_words(k)
+    member = torch.empty((max(cap, 1), words), dtype=torch.int32, device=dev)
+    counts = torch.zeros((n_seg, k), dtype=torch.int32, device=dev) if want_counts else None
+    need = L.lib().xm3d_gather_ws_bytes(n_seg, k, h, w)
+    if ws is None or ws.numel() < need:
+        ws = _ws(need, dev)
+    L.check(L.lib().xm3d_gather_masks_batch(_ptr(masks), kind, THR[mode], n_seg, k, h, w, _ptr(rowcol),
+                                            _ptr(seg_off), cap, _ptr(member), _ptr(counts), _ptr(ws), ws.numel(),
+                                            _stream()))
+    return member, counts
+
+
+def pool(feat: torch.Tensor, seg_off: torch.Tensor, k: int, member: Optional[torch.Tensor] = None,
+         label: Optional[torch.Tensor] = None, row_index: Optional[torch.Tensor] = None,
+         cap: Optional[int] = None, want_mean: bool = True, ws: Optional[torch.Tensor] = None):
+    """Segmented mean pooling.  feat float32 [rows,c]; member int32 [cap,words] or label int32 [cap].
+    Returns (sum [n_seg,k,c], cnt int32 [n_seg,k], mean [n_seg,k,c] or None)."""
+    _require_cuda()
+    dev = feat.device
+    feat = _dev_contig(feat, torch.float32)
+    assert feat.dim() == 2
+    c = feat.shape[1]
+    seg_off = _dev_contig(seg_off, torch.int64)
+    n_seg = seg_off.numel() - 1
+    if member is not None:
+        member = _dev_contig(member, torch.int32)
+        n_pts = member.shape[0]
+    else:
+        label = _dev_contig(label, torch.int32)
+        n_pts = label.shape[0]
+    if row_index is not None:
+        row_index = _dev_contig(row_index, torch.int32)
+    cap = int(n_pts) if cap is None else int(cap)
+    s = torch.empty((n_seg, k, c), dtype=torch.float32, device=dev)
+    cnt = torch.empty((n_seg, k), dtype=torch.int32, device=dev)
+    mean = torch.empty((n_seg, k, c), dtype=torch.float32, device=dev) if want_mean else None
+    need = L.lib().xm3d_pool_ws_bytes(n_seg, k, c)
+    if ws is None or ws.numel() < need:
+        ws = _ws(need, dev)
+    L.check(L.lib().xm3d_pool_batch(_ptr(feat), c, _ptr(row_index), _ptr(member), _ptr(label), n_seg, int(k),
+                                    _ptr(seg_off), cap, _ptr(s), _ptr(cnt), _ptr(mean), _ptr(ws), ws.numel(),
+                                    None, _stream()))
+    return s, cnt, mean
+
+
+def scatter(emb: torch.Tensor, seg_off: torch.Tensor, n_pts: int, member: Optional[torch.Tensor] = None,
+            label: Optional[torch.Tensor] = None, want_counter: bool = True):
+    """Mask -> point scatter-mean.  emb float32 [n_seg,k,c].  Returns (out [n_pts,c], counter [n_pts])."""
+    _require_cuda()
+    dev = emb.device
+    emb = _dev_contig(emb, torch.float32)
+    n_seg, k, c = emb.shape
+    seg_off = _dev_contig(seg_off, torch.int64)
+    if member is not None:
+        member = _dev_contig(member, torch.int32)
+    else:
+        label = _dev_contig(label, torch.int32)
+    out = torch.empty((max(n_pts, 1), c), dtype=torch.float32, device=dev)
+    counter = torch.empty(max(n_pts, 1), dtype=torch.float32, device=dev) if want_counter else None
+    L.check(L.lib().xm3d_scatter_batch(_ptr(member), _ptr(label), n_seg, k, _ptr(seg_off), int(n_pts), _ptr(emb), c,
+                                       _ptr(out), _ptr(counter), _stream()))
+    return out[:n_pts], (counter[:n_pts] if counter is not None else None)
+
+
+# ----------------------------------------------------------------------------- stage 4
+def logits(mask_embed: torch.Tensor, text_embed: torch.Tensor, null_embed: torch.Tensor,
+           group_sizes: Sequence[int], logit_scale: float, ensemble: str = "max", want_argmax: bool = False,
+           ws: Optional[torch.Tensor] = None):
+    """mask_embed [...,c]; text_embed [n_text,c]; null_embed [1,c] -> [..., n_groups+1] float32."""
+    _require_cuda()
+    dev = mask_embed.device
+    lead = mask_embed.shape[:-1]
+    c = mask_embed.shape[-1]
+    me = _dev_contig(mask_embed.reshape(-1, c), torch.float32)
+    te = _dev_contig(text_embed, torch.float32)
+    ne = _dev_contig(null_embed.reshape(1, c), torch.float32)
+    rows, n_text, n_groups = me.shape[0], te.shape[0], len(group_sizes)
+    assert ensemble in ("max", "mean")
+    assert sum(group_sizes) == n_text, f"{n_text} != {sum(group_sizes)}"
+    goff = (C.c_int32 * (n_groups + 1))(*np.concatenate([[0], np.cumsum(group_sizes)]).astype(np.int32).tolist())
+    out = torch.empty((rows, n_groups + 1), dtype=torch.float32, device=dev)
+    amax = torch.empty(max(rows, 1), dtype=torch.int32, device=dev) if want_argmax else None
+    need = L.lib().xm3d_logits_ws_bytes(rows, n_text, c, n_groups)
+    if ws is None or ws.numel() < need:
+        ws = _ws(need, dev)
+    L.check(L.lib().xm3d_logits(_ptr(me), rows, c, _ptr(te), n_text, _ptr(ne), C.cast(goff, C.c_void_p), n_groups,
+                                int(ensemble == "mean"), float(logit_scale), _ptr(out), _ptr(amax), _ptr(ws),
+                                ws.numel(), _stream()))
+    out = out.reshape(*lead, n_groups + 1)
+    if want_argmax:
+        return out, amax[:rows].reshape(lead)
+    return out

@@ -1,0 +1,142 @@
+"""Drop-in for the reference's `dataset/voxelizer.py` (numpy in, numpy out) on libxm3d.
+
+Reference: Voxelizer ctor dataset/voxelizer.py:12-30, get_transformation_matrix :32-58, clip
+:60-79, voxelize :81-132.  The rigid transformation (a 4x4 float64, a handful of np.random
+draws and three scipy expm calls) stays on the host and consumes np.random in the reference's
+order — 3x uniform, 1x shuffle, 1x uniform — so a seeded run draws the same matrices; the
+per-point work (transform, floor, min, FNV key, unique / inverse) runs on the GPU.
+
+`voxelize_views` is the batched entry point used by the data loaders' per-view loop
+(dataset/data_loader_infer.py:161-270): one call for all views of a scene / batch.
+"""
+from __future__ import annotations
+
+from collections.abc import Iterable
+
+import numpy as np
+import torch
+from scipy.linalg import expm, norm
+
+from . import ops
+
+
+def M(axis, theta):
+    """Rotation about `axis` by `theta` (reference :7-8)."""
+    return expm(np.cross(np.eye(3), axis / norm(axis) * theta))
+
+
+class Voxelizer:
+    def __init__(self, voxel_size=1, clip_bound=None, use_augmentation=False,
+                 scale_augmentation_bound=None, rotation_augmentation_bound=None,
+                 translation_augmentation_ratio_bound=None, ignore_label=255):
+        self.voxel_size = voxel_size
+        self.clip_bound = clip_bound
+        self.ignore_label = ignore_label
+        self.use_augmentation = use_augmentation
+        self.scale_augmentation_bound = scale_augmentation_bound
+        self.rotation_augmentation_bound = rotation_augmentation_bound
+        self.translation_augmentation_ratio_bound = translation_augmentation_ratio_bound
+
+    # -- host side -------------------------------------------------------------------------
+    def get_transformation_matrix(self):
+        voxelization_matrix, rotation_matrix = np.eye(4), np.eye(4)
+        rot_mat = np.eye(3)
+        if self.use_augmentation and self.rotation_augmentation_bound is not None:
+            if not isinstance(self.rotation_augmentation_bound, Iterable):
+                raise ValueError()
+            rot_mats = []
+            for axis_ind, rot_bound in enumerate(self.rotation_augmentation_bound):
+                theta = 0
+                axis = np.zeros(3)
+                axis[axis_ind] = 1
+                if rot_bound is not None:
+                    theta = np.random.uniform(*rot_bound)
+                rot_mats.append(M(axis, theta))
+            np.random.shuffle(rot_mats)
+            rot_mat = rot_mats[0] @ rot_mats[1] @ rot_mats[2]
+        rotation_matrix[:3, :3] = rot_mat
+        scale = 1 / self.voxel_size
+        if self.use_augmentation and self.scale_augmentation_bound is not None:
+            scale *= np.random.uniform(*self.scale_augmentation_bound)
+        np.fill_diagonal(voxelization_matrix[:3, :3], scale)
+        return voxelization_matrix, rotation_matrix
+
+    def clip(self, coords, center=None, trans_aug_ratio=None):
+        bound_min = np.min(coords, 0).astype(float)
+        bound_max = np.max(coords, 0).astype(float)
+        bound_size = bound_max - bound_min
+        if center is None:
+            center = bound_min + bound_size * 0.5
+        if trans_aug_ratio is not None:
+            trans = np.multiply(trans_aug_ratio, bound_size)
+            center += trans
+        lim = self.clip_bound
+        clip_inds = ((coords[:, 0] >= (lim[0][0] + center[0])) & (coords[:, 0] < (lim[0][1] + center[0])) &
+                     (coords[:, 1] >= (lim[1][0] + center[1])) & (coords[:, 1] < (lim[1][1] + center[1])) &
+                     (coords[:, 2] >= (lim[2][0] + center[2])) & (coords[:, 2] < (lim[2][1] + center[2])))
+        return clip_inds
+
+    def draw_rigid_transformation(self):
+        """(rigid_transformation 4x4, M_r 4x4) exactly as voxelize draws them (:104-108)."""
+        M_v, M_r = self.get_transformation_matrix()
+        rigid_transformation = M_v
+        if self.use_augmentation:
+            rigid_transformation = M_r @ rigid_transformation
+        return rigid_transformation, M_r
+
+    # -- reference signature ---------------------------------------------------------------
+    def voxelize(self, coords, feats, labels, center=None, link=None, return_ind=False):
+        assert coords.shape[1] == 3 and coords.shape[0] == feats.shape[0] and coords.shape[0]
+        if self.clip_bound is not None:
+            trans_aug_ratio = np.zeros(3)
+            if self.use_augmentation and self.translation_augmentation_ratio_bound is not None:
+                for axis_ind, trans_ratio_bound in enumerate(self.translation_augmentation_ratio_bound):
+                    trans_aug_ratio[axis_ind] = np.random.uniform(*trans_ratio_bound)
+            clip_inds = self.clip(coords, center, trans_aug_ratio)
+            if clip_inds.sum():
+                coords, feats = coords[clip_inds], feats[clip_inds]
+                if labels is not None:
+                    labels = labels[clip_inds]
+        rigid_transformation, M_r = self.draw_rigid_transformation()
+        res = voxelize_views([coords], [rigid_transformation])
+        coords_aug, inds, inds_reconstruct = res[0]
+        feats, labels = feats[inds], labels[inds]
+        if feats.shape[1] > 6:
+            feats[:, 3:6] = feats[:, 3:6] @ (M_r[:3, :3].T)
+        if return_ind:
+            return coords_aug, feats, labels, np.array(inds_reconstruct), inds
+        if link is not None:
+            return coords_aug, feats, labels, np.array(inds_reconstruct), link[inds]
+        return coords_aug, feats, labels, np.array(inds_reconstruct)
+
+
+def voxelize_views(coords_list, rigid_transformations, device=None):
+    """Batched core of Voxelizer.voxelize: for every (points [n_i,3] float32, 4x4 float64 matrix)
+    returns (coords_aug float64 [M_i,3], inds int64 [M_i], inds_reconstruct int64 [n_i]) —
+    the values the reference computes at dataset/voxelizer.py:110-122."""
+    ops._require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+    n = [int(c.shape[0]) for c in coords_list]
+    off = np.concatenate([[0], np.cumsum(n)]).astype(np.int64)
+    for c in coords_list:
+        if c.dtype != np.float32:
+            raise TypeError("voxelize_views expects float32 coordinates (ScanNet .pth coords are float32; "
+                            "the reference widens them to float64 inside the matmul)")
+    xyz = torch.from_numpy(np.ascontiguousarray(np.concatenate(coords_list, 0))).to(dev)
+    rt = torch.from_numpy(np.ascontiguousarray(np.stack([np.asarray(r, np.float64)[:3, :4]
+                                                         for r in rigid_transformations]))).to(dev)
+    u = ops.voxelize_batch(xyz, torch.from_numpy(off).to(dev), rt)
+    status = int(u.status.item())
+    if status:
+        raise RuntimeError(f"voxelize: device status flags {status:#x} (grid range / sentinel / capacity)")
+    m = u.m.cpu().numpy()
+    uoff = u.uniq_off.cpu().numpy()
+    first = u.first.cpu().numpy()
+    inverse = u.inverse.cpu().numpy()
+    voxel = u.voxel_xyz.cpu().numpy()
+    out = []
+    for i in range(len(n)):
+        a, b = int(uoff[i]), int(uoff[i]) + int(m[i])
+        out.append((voxel[a:b].astype(np.float64), first[a:b].astype(np.int64),
+                    inverse[off[i]:off[i + 1]].astype(np.int64)))
+    return out
