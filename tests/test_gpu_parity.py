@@ -355,6 +355,6 @@ def test_logits_golden(golden, dev):
     assert np.abs(got - g["logits_grp"]).max() < 2e-5 * np.abs(g["logits_grp"]).max()
     raw = torch.from_numpy(g["ens_in"]).to(dev)
     assert np.array_equal(ensemble_logits_with_labels(raw, labels, "max").cpu().numpy(), g["ens_max"])
-    np.testing.assert_allclose(ensemble_logits_with_labels(raw, labels, "mean").cpu().numpy(), g["ens_mean"], rtol=1e-6)
+    np.testing.assert_allclose(ensemble_logits_with_labels(raw, labels, "mean").cpu().numpy(), g["ens_mean"], rtol=1e-5, atol=1e-7)
     with pytest.raises(AssertionError):
         ensemble_logits_with_labels(raw, labels[:-1], "max")

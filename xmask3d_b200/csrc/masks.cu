@@ -192,7 +192,8 @@ __global__ void __launch_bounds__(POOL_MAX_THREADS, 1) pool_kernel(const PoolPar
                             bits[j][0] = (uint32_t)__ldg(P.label + i);
                         } else {
 #pragma unroll
-                            for (int w = 0; w < WORDS; ++w) bits[j][w] = __ldg(P.member + i * WORDS + w);
+                            for (int w = 0; w < WORDS; ++w)
+                                bits[j][w] = (w < P.words) ? __ldg(P.member + i * P.words + w) : 0u;
                         }
                         const int64_t row = P.row_index ? (int64_t)__ldg(P.row_index + i) : i;
                         if (active) buf[j] = ld_feat<VEC>(P.feat + row * P.c + ch);
