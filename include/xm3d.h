@@ -67,6 +67,8 @@ XM3D_API int xm3d_version(void);
 XM3D_API const char *xm3d_last_error(void);
 /* SM count, compute capability of the current device (XM3D_ERR_CUDA without a GPU). */
 XM3D_API int xm3d_device_info(int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor);
+/* Number of CUDA kernels this library has launched in this process (monotonic; for benchmarks). */
+XM3D_API int64_t xm3d_launch_count(void);
 
 /* ------------------------------------------------------------------ stage 2: projection
  * Replaces PointCloudToImageMapper.compute_mapping (models/utils/fusion_util.py:46-142) and

@@ -1,5 +1,6 @@
 // libxm3d — error reporting, version and device queries of the C ABI (include/xm3d.h).
 #include <stdarg.h>
+#include <atomic>
 #include <string.h>
 
 #include "common.cuh"
@@ -7,6 +8,9 @@
 namespace xm3d {
 
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 void set_error(const char *fmt, ...) {
     va_list ap;
@@ -40,6 +44,8 @@ int sm_count() {
 extern "C" int xm3d_version(void) { return XM3D_VERSION; }
 
 extern "C" const char *xm3d_last_error(void) { return xm3d::g_err; }
+
+extern "C" int64_t xm3d_launch_count(void) { return xm3d::g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int xm3d_device_info(int32_t *sm, int32_t *cc_major, int32_t *cc_minor) {
     int dev = 0;

@@ -14,6 +14,7 @@ namespace xm3d {
 
 void set_error(const char *fmt, ...);
 int check_launch(const char *what);  // cudaGetLastError -> XM3D_OK / XM3D_ERR_CUDA
+void count_launches(int n);          // bookkeeping for xm3d_launch_count()
 int sm_count();
 
 #define XM3D_REQUIRE(cond, msg)                      \

@@ -315,9 +315,9 @@ extern "C" int xm3d_logits(const float *mask_embed, int64_t rows, int32_t c, con
     // rows of A first, then text rows, then the null row (two launches keep the kernel simple)
     const int wpb = 8;
     logits_prep_kernel<<<(unsigned)((rows + wpb - 1) / wpb), 256, 0, stream>>>(mask_embed, nullptr, rows, 0, c, w.hi,
-                                                                               w.lo, w.inv_norm);
+                                                                               w.lo, w.inv_norm); count_launches(1);
     logits_prep_kernel<<<(unsigned)((n_cols + wpb - 1) / wpb), 256, 0, stream>>>(
-        text_embed, null_embed, n_text, 1, c, w.hi + (size_t)rows * c, w.lo + (size_t)rows * c, w.inv_norm + rows);
+        text_embed, null_embed, n_text, 1, c, w.hi + (size_t)rows * c, w.lo + (size_t)rows * c, w.inv_norm + rows); count_launches(1);
 
     LogitsParams P;
     P.rows = rows; P.c = c; P.n_cols = n_cols; P.n_text = n_text; P.n_groups = n_groups;
@@ -346,6 +346,6 @@ extern "C" int xm3d_logits(const float *mask_embed, int64_t rows, int32_t c, con
         cudaFuncSetAttribute(logits_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
         attr_set = true;
     }
-    logits_mma_kernel<<<(unsigned)((rows + LG_BM - 1) / LG_BM), LG_THREADS, smem, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, P);
+    logits_mma_kernel<<<(unsigned)((rows + LG_BM - 1) / LG_BM), LG_THREADS, smem, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, P); count_launches(1);
     return check_launch("xm3d_logits");
 }

@@ -387,7 +387,7 @@ static void launch_pool(const PoolParams &P, const PoolPlan &pl, cudaStream_t st
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, POOL_SMEM_MAX);
         attr_set = true;
     }
-    kern<<<dim3(pl.G, pl.slices), pl.threads, pl.smem, stream>>>(P);
+    kern<<<dim3(pl.G, pl.slices), pl.threads, pl.smem, stream>>>(P); count_launches(1);
 }
 
 template <int VEC>
@@ -433,16 +433,16 @@ extern "C" int xm3d_gather_masks_batch(const void *masks, int32_t mask_kind, int
     const int esz = mask_kind == XM3D_MASK_U8 ? 1 : 4;
     const int vec_ok = (hw % 4 == 0) && (reinterpret_cast<uintptr_t>(masks) % (4 * esz) == 0);
     dim3 grid((hw / 4 + 256) / 256, n_seg);
-    if (mask_kind == XM3D_MASK_U8)
+    if (mask_kind == XM3D_MASK_U8) {
         pixel_bits_kernel<unsigned char><<<grid, 256, 0, stream>>>(static_cast<const unsigned char *>(masks), thr_mode,
-                                                                    k, hw, words, vec_ok, pixbits);
-    else
+                                                                    k, hw, words, vec_ok, pixbits); count_launches(1); }
+    else {
         pixel_bits_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float *>(masks), thr_mode, k, hw, words,
-                                                           vec_ok, pixbits);
+                                                           vec_ok, pixbits); count_launches(1); }
     if (counts) cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)n_seg * k, stream);
-    if (cap > 0)
+    if (cap > 0) {
         point_bits_kernel<<<(unsigned)((cap + 255) / 256), 256, 0, stream>>>(pixbits, rowcol, seg_off, n_seg, cap, k, h,
-                                                                             w, words, member, counts);
+                                                                             w, words, member, counts); count_launches(1); }
     return check_launch("xm3d_gather_masks_batch");
 }
 
@@ -486,7 +486,7 @@ extern "C" int xm3d_pool_batch(const float *feat, int32_t c, const int32_t *row_
     else rc = dispatch_pool<1>(P, pl, stream);
     if (rc != XM3D_OK) { set_error("xm3d_pool_batch: unsupported mask count"); return rc; }
     dim3 cgrid((unsigned)(((size_t)k * c + 255) / 256), n_seg);
-    pool_combine_kernel<<<cgrid, 256, 0, stream>>>(part_sum, part_cnt, seg_off, n_seg, cap, k, c, pl.G, sum, cnt, mean);
+    pool_combine_kernel<<<cgrid, 256, 0, stream>>>(part_sum, part_cnt, seg_off, n_seg, cap, k, c, pl.G, sum, cnt, mean); count_launches(1);
     return check_launch("xm3d_pool_batch");
 }
 
@@ -507,11 +507,11 @@ extern "C" int xm3d_scatter_batch(const uint32_t *member, const int32_t *label, 
     if (v4) {
         const int threads = (c / 4 + 31) / 32 * 32;
         scatter_kernel<4><<<blocks, threads, 0, stream>>>(member, label, seg_off, n_seg, cap, k, words_for(k), emb, c,
-                                                          out, counter, pts);
+                                                          out, counter, pts); count_launches(1);
     } else {
         const int threads = (c + 31) / 32 * 32;
         scatter_kernel<1><<<blocks, threads, 0, stream>>>(member, label, seg_off, n_seg, cap, k, words_for(k), emb, c,
-                                                          out, counter, pts);
+                                                          out, counter, pts); count_launches(1);
     }
     return check_launch("xm3d_scatter_batch");
 }

@@ -431,12 +431,12 @@ extern "C" int xm3d_project_batch(const float *xyz, const xm3d_view_t *views_hos
     dim3 grid(parts, n_views);
     if (P.use_flag) {
         cudaMemsetAsync(view_flag, 0, sizeof(int) * n_views, stream);
-        project_kernel<true><<<grid, PROJ_THREADS, stage_bytes, stream>>>(P);
+        project_kernel<true><<<grid, PROJ_THREADS, stage_bytes, stream>>>(P); count_launches(1);
     }
-    project_kernel<false><<<grid, PROJ_THREADS, stage_bytes, stream>>>(P);
-    project_scan_kernel<<<1, 1024, 0, stream>>>(part_cnt, n_views, parts, part_off, n_vis, vis_off, cap_vis, status);
-    if (vis_idx || rowcol || xyz_vis)
+    project_kernel<false><<<grid, PROJ_THREADS, stage_bytes, stream>>>(P); count_launches(1);
+    project_scan_kernel<<<1, 1024, 0, stream>>>(part_cnt, n_views, parts, part_off, n_vis, vis_off, cap_vis, status); count_launches(1);
+    if (vis_idx || rowcol || xyz_vis) {
         project_emit_kernel<<<grid, 256, 0, stream>>>(xyz, d_views, stage, part_cnt, part_off, parts, cap_vis,
-                                                      vis_idx, rowcol, xyz_vis);
+                                                      vis_idx, rowcol, xyz_vis); count_launches(1); }
     return check_launch("xm3d_project_batch");
 }

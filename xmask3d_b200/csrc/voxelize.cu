@@ -548,27 +548,27 @@ static int run_unique(const float *xyz, const unsigned long long *keys, const in
     int *gmin = grid_min_out ? grid_min_out : w.grid_min;
     const unsigned blocks = (unsigned)((cap + VOX_THREADS - 1) / VOX_THREADS);
     vox_plan_kernel<<<1, 1024, 0, stream>>>(seg_off, n_seg, cap, w.tbl_off, w.total_eff, m, xyz ? gmin : nullptr,
-                                            status);
-    vox_clear_kernel<<<(unsigned)(sm_count() * 8), 256, 0, stream>>>(w.tbl, w.tbl_off, n_seg);
+                                            status); count_launches(1);
+    vox_clear_kernel<<<(unsigned)(sm_count() * 8), 256, 0, stream>>>(w.tbl, w.tbl_off, n_seg); count_launches(1);
     if (counts) cudaMemsetAsync(counts, 0, sizeof(int) * cap, stream);
     if (blocks) {
         if (xyz) {
-            vox_min_kernel<<<blocks, VOX_THREADS, 0, stream>>>(xyz, seg_off, n_seg, w.total_eff, rt, gmin, status);
+            vox_min_kernel<<<blocks, VOX_THREADS, 0, stream>>>(xyz, seg_off, n_seg, w.total_eff, rt, gmin, status); count_launches(1);
             vox_insert_kernel<0><<<blocks, VOX_THREADS, 0, stream>>>(xyz, nullptr, seg_off, n_seg, w.total_eff, rt, gmin,
-                                                                     w.tbl, w.tbl_off, w.pslot, w.uniq, m, status);
+                                                                     w.tbl, w.tbl_off, w.pslot, w.uniq, m, status); count_launches(1);
         } else {
             vox_insert_kernel<1><<<blocks, VOX_THREADS, 0, stream>>>(nullptr, keys, seg_off, n_seg, w.total_eff, nullptr,
                                                                      nullptr, w.tbl, w.tbl_off, w.pslot, w.uniq, m,
-                                                                     status);
+                                                                     status); count_launches(1);
         }
     }
     SortOut O;
     O.first = first; O.voxel_xyz = xyz ? voxel_xyz : nullptr; O.xyz = xyz; O.rt = rt; O.grid_min = gmin;
     vox_sort_kernel<<<n_seg, SORT_THREADS, SORT_SAMPLES * 12, stream>>>(seg_off, n_seg, w.tbl, w.tbl_off, w.uniq, m,
-                                                                        uniq_off, w.bk_key, w.bk_slot, O);
-    if (blocks && inverse)
+                                                                        uniq_off, w.bk_key, w.bk_slot, O); count_launches(1);
+    if (blocks && inverse) {
         vox_inverse_kernel<<<blocks, VOX_THREADS, 0, stream>>>(seg_off, n_seg, w.total_eff, w.tbl, w.tbl_off, w.pslot,
-                                                               uniq_off, collate, inverse, counts);
+                                                               uniq_off, collate, inverse, counts); count_launches(1); }
     return check_launch(who);
 }
 
@@ -613,7 +613,7 @@ extern "C" int xm3d_fnv_hash_f64(const double *coords, int64_t n, int32_t dim, u
     if (n == 0) return XM3D_OK;
     XM3D_REQUIRE(coords && keys, "null pointer");
     fnv_f64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        coords, n, dim, reinterpret_cast<unsigned long long *>(keys));
+        coords, n, dim, reinterpret_cast<unsigned long long *>(keys)); count_launches(1);
     return check_launch("xm3d_fnv_hash_f64");
 }
 
@@ -626,11 +626,11 @@ extern "C" int xm3d_ravel_hash_f64(const double *coords, int64_t n, int32_t dim,
     if (n == 0) return XM3D_OK;
     XM3D_REQUIRE(coords && keys && ws && ws_bytes >= 128, "null pointer / workspace");
     double *mm = static_cast<double *>(ws);
-    init_minmax_kernel<<<1, 32, 0, stream>>>(mm);
+    init_minmax_kernel<<<1, 32, 0, stream>>>(mm); count_launches(1);
     unsigned blocks = (unsigned)((n + 255) / 256);
     if (blocks > (unsigned)sm_count() * 8) blocks = sm_count() * 8;
-    colminmax_f64_kernel<<<blocks, 256, 0, stream>>>(coords, n, dim, mm);
+    colminmax_f64_kernel<<<blocks, 256, 0, stream>>>(coords, n, dim, mm); count_launches(1);
     ravel_f64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(coords, n, dim, mm,
-                                                                       reinterpret_cast<unsigned long long *>(keys));
+                                                                       reinterpret_cast<unsigned long long *>(keys)); count_launches(1);
     return check_launch("xm3d_ravel_hash_f64");
 }
