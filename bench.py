@@ -243,6 +243,12 @@ def run_native(args, rank: int, world: int, local_rank: int):
     total_vis = int(n_vis.sum())
     pipe.set_cap(total_vis)
     masks, mode, mask_bytes = make_masks(args, batch.n_views, dev, 4242 + rank)
+    from xmask3d_b200 import ops
+    member0, _ = ops.gather_masks(masks, pr.rowcol, pr.vis_off, mode=mode, cap=total_vis)
+    total_pairs = int(ops._popcount32(member0[:total_vis]).sum().item())
+    del member0
+    pipe.pairs_per_point = total_pairs / max(total_vis, 1)
+    pipe._size_pool_ws()
     feat = torch.empty((total_vis, args.c), dtype=torch.float32, device=dev)
     g = torch.Generator(device=dev).manual_seed(7 + rank)
     for a in range(0, total_vis, 1 << 20):
@@ -281,12 +287,19 @@ def run_native(args, rank: int, world: int, local_rank: int):
         ms = e0.elapsed_time(e1)
         # per-stage durations inside the same region: a second timed pass with events between stages
         stage_acc = {}
+        ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev_a.record(); ev_b.record()                       # materialise the cudaEvent_t handles
+        torch.cuda.synchronize()
+        import ctypes
+        L.lib().xm3d_set_pool_events(ctypes.c_void_p(ev_a.cuda_event), ctypes.c_void_p(ev_b.cuda_event))
         for _ in range(min(args.steps, 20)):
             st = StageTimes()
             pipe.run(masks, feat, mode, times=st)
             torch.cuda.synchronize()
             for kk, vv in st.result().items():
                 stage_acc.setdefault(kk, []).append(vv)
+            stage_acc.setdefault("pool_sum_kernel", []).append(ev_a.elapsed_time(ev_b))
+        L.lib().xm3d_set_pool_events(None, None)
     launches = L.lib().xm3d_launch_count() - launches0
     launches_per_step = launches / (args.steps + min(args.steps, 20))
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -390,11 +403,13 @@ def run_native(args, rank: int, world: int, local_rank: int):
     n_pts_view = np.diff(batch.scene_off)[batch.view_scene]
     alg = algorithmic_bytes(n_pts_view, n_vis, m_vox, args.k, args.c, mask_bytes)
     words = (args.k + 31) // 32
-    pool_bytes = int((4 * args.c + 4 * words) * total_vis + batch.n_views * (4 * args.k * args.c + 4 * args.k))
-    pool_ms = stage_ms.get("pool", float("nan"))
+    # algorithmic bytes of the dominant kernel: every visible point's C-float row read once + its
+    # 4-byte row index, plus the [K,C] sums it produces per view
+    pool_bytes = int((4 * args.c + 4) * total_vis + batch.n_views * 4 * args.k * args.c)
+    pool_ms = stage_ms.get("pool_sum_kernel", float("nan"))
     achieved = pool_bytes / (pool_ms * 1e-3) / 1e9
     step_ms = ms / args.steps
-    roof = {"bound": "hbm", "kernel": "pool_kernel<4,2,false> (+ pool_combine_kernel, <1% of it)",
+    roof = {"bound": "hbm", "kernel": "pool_sum_kernel<4> (events recorded around this launch alone)",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
             "bytes_per_launch": pool_bytes, "ms_per_launch": pool_ms, "peak_source": peak_src}
     pipe_gbs = alg["total"] / (step_ms * 1e-3) / 1e9
@@ -402,7 +417,7 @@ def run_native(args, rank: int, world: int, local_rank: int):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64/u64/f32",
         "data": "synthetic",
-        "config": {"workload": workload_name(args), "point_views_per_gpu_step": pv_rank, "visible_pairs_per_gpu": total_vis,
+        "config": {"workload": workload_name(args), "point_views_per_gpu_step": pv_rank, "visible_pairs_per_gpu": total_vis, "mask_memberships_per_gpu": total_pairs,
                    "voxels_per_gpu": int(m_vox.sum()), "cache": "inputs larger than L2 (features %.1f GB per GPU)" % (feat.numel() * 4 / 1e9),
                    "parallelism": f"scenes sharded over {world} rank(s), no data-path collective", "setup_s": round(t_setup, 1)},
         "roofline": roof,

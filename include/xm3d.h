@@ -69,6 +69,10 @@ XM3D_API const char *xm3d_last_error(void);
 XM3D_API int xm3d_device_info(int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor);
 /* Number of CUDA kernels this library has launched in this process (monotonic; for benchmarks). */
 XM3D_API int64_t xm3d_launch_count(void);
+/* Benchmark hook: two cudaEvent_t handles (or NULLs to clear) that the calling thread's next
+ * xm3d_pool_batch calls record immediately before / after the dominant kernel (pool_sum_kernel)
+ * on the call's stream, so its duration can be read with cudaEventElapsedTime. */
+XM3D_API void xm3d_set_pool_events(void *ev_before, void *ev_after);
 
 /* ------------------------------------------------------------------ stage 2: projection
  * Replaces PointCloudToImageMapper.compute_mapping (models/utils/fusion_util.py:46-142) and
@@ -168,13 +172,15 @@ XM3D_API int xm3d_gather_masks_batch(const void *masks, int32_t mask_kind, int32
  *             (e.g. inds_reconstruct, fusing pred_3d[inds_reconstruct], models/xmask3d.py:152)
  *   member    as produced by xm3d_gather_masks_batch (general, overlapping masks) OR
  *   label     int32 [cap], values outside [0,k) = in no mask (partition masks); exactly one of the two
+ *   cap_pairs bounds the total number of (point, mask) memberships (= cap for labels / partition
+ *   masks); beyond it XM3D_FLAG_PAIR_OVERFLOW is raised and the sums are zero.
  *   sum [n_seg,k,c] float32, cnt [n_seg,k] int32 (optional), mean (optional) [n_seg,k,c] = sum/cnt
- *   (0 where cnt = 0).  Deterministic: partial sums are combined in a fixed order. */
-XM3D_API size_t xm3d_pool_ws_bytes(int32_t n_seg, int32_t k, int32_t c);
+ *   (0 where cnt = 0).  Deterministic: every summation order is fixed by the point order. */
+XM3D_API size_t xm3d_pool_ws_bytes(int32_t n_seg, int32_t k, int32_t c, int64_t cap_pairs);
 XM3D_API int xm3d_pool_batch(const float *feat, int32_t c, const int32_t *row_index, const uint32_t *member,
                     const int32_t *label, int32_t n_seg, int32_t k, const int64_t *seg_off, int64_t cap,
-                    float *sum, int32_t *cnt, float *mean, void *ws, size_t ws_bytes, int32_t *status,
-                    xm3d_stream_t stream);
+                    int64_t cap_pairs, float *sum, int32_t *cnt, float *mean, void *ws, size_t ws_bytes,
+                    int32_t *status, xm3d_stream_t stream);
 
 /* Mask -> point scatter-mean (mask_mapper, models/utils/fuser.py:22-34; twin
  * models/xmask3d.py:441-455): out[i,:] = (sum of emb[m,:] over masks m containing i, ascending m)

@@ -39,6 +39,7 @@ PROTOTYPES = {
     "xm3d_last_error": (C.c_char_p, []),
     "xm3d_device_info": (C.c_int, [_P, _P, _P]),
     "xm3d_launch_count": (_I64, []),
+    "xm3d_set_pool_events": (None, [_P, _P]),
     "xm3d_project_ws_bytes": (_SZ, [_I32, _I64, _I32]),
     "xm3d_project_batch": (C.c_int, [_P, _P, _I32, _I64, _P, _I32, _F64, _I32, _I32, _I32, _F64,
                                      _P, _P, _P, _P, _I64, _P, _P, _P, _P, _SZ, _P, _P]),
@@ -52,8 +53,8 @@ PROTOTYPES = {
     "xm3d_mask_words": (_I32, [_I32]),
     "xm3d_gather_ws_bytes": (_SZ, [_I32, _I32, _I32, _I32]),
     "xm3d_gather_masks_batch": (C.c_int, [_P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _I64, _P, _P, _P, _SZ, _P]),
-    "xm3d_pool_ws_bytes": (_SZ, [_I32, _I32, _I32]),
-    "xm3d_pool_batch": (C.c_int, [_P, _I32, _P, _P, _P, _I32, _I32, _P, _I64, _P, _P, _P, _P, _SZ, _P, _P]),
+    "xm3d_pool_ws_bytes": (_SZ, [_I32, _I32, _I32, _I64]),
+    "xm3d_pool_batch": (C.c_int, [_P, _I32, _P, _P, _P, _I32, _I32, _P, _I64, _I64, _P, _P, _P, _P, _SZ, _P, _P]),
     "xm3d_scatter_batch": (C.c_int, [_P, _P, _I32, _I32, _P, _I64, _P, _I32, _P, _P, _P]),
     "xm3d_logits_ws_bytes": (_SZ, [_I64, _I32, _I32, _I32]),
     "xm3d_logits": (C.c_int, [_P, _I64, _I32, _P, _I32, _P, _P, _I32, _I32, _F32, _P, _P, _P, _SZ, _P]),

@@ -10,6 +10,8 @@ namespace xm3d {
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
 
+thread_local cudaEvent_t g_pool_ev[2] = {nullptr, nullptr};
+
 void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 void set_error(const char *fmt, ...) {
@@ -59,4 +61,9 @@ extern "C" int xm3d_device_info(int32_t *sm, int32_t *cc_major, int32_t *cc_mino
     if (cc_major) *cc_major = prop.major;
     if (cc_minor) *cc_minor = prop.minor;
     return XM3D_OK;
+}
+
+extern "C" void xm3d_set_pool_events(void *before, void *after) {
+    xm3d::g_pool_ev[0] = static_cast<cudaEvent_t>(before);
+    xm3d::g_pool_ev[1] = static_cast<cudaEvent_t>(after);
 }

@@ -16,6 +16,7 @@ void set_error(const char *fmt, ...);
 int check_launch(const char *what);  // cudaGetLastError -> XM3D_OK / XM3D_ERR_CUDA
 void count_launches(int n);          // bookkeeping for xm3d_launch_count()
 int sm_count();
+extern thread_local cudaEvent_t g_pool_ev[2];   // optional timing hook (xm3d_set_pool_events)
 
 #define XM3D_REQUIRE(cond, msg)                      \
     do {                                             \

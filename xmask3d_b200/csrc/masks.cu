@@ -16,13 +16,10 @@
 //   scatter  out[i,:] = (sum over masks m containing i, ascending m, of emb[m,:]) / count_i
 //            (fuser.py:22-34; xmask3d.py:441-455) — float32 op order of the reference, bit-exact.
 #include "common.cuh"
+#include "vec.cuh"
 
 namespace xm3d {
 
-constexpr int MAX_WORDS = 8;                  // k <= 256 masks per segment
-constexpr int POOL_SMEM_MAX = 224 * 1024;     // accumulator bytes per CTA
-constexpr int POOL_HALF = 8;                  // rows per half of the register ring
-constexpr int POOL_MAX_THREADS = 256;         // <= 256 threads per CTA keeps 255 registers per thread
 
 __device__ __forceinline__ bool mask_hit(float x, int thr_mode) {
     if (thr_mode == XM3D_THR_GE_HALF) return x >= 0.5f;
@@ -105,191 +102,6 @@ point_bits_kernel(const uint32_t *__restrict__ pixbits, const int32_t *__restric
     }
 }
 
-// ---- pooling ------------------------------------------------------------------------------
-template <int VEC> struct VecT;
-template <> struct VecT<4> { using type = float4; };
-template <> struct VecT<2> { using type = float2; };
-template <> struct VecT<1> { using type = float; };
-
-template <int VEC>
-__device__ __forceinline__ typename VecT<VEC>::type ld_feat(const float *p);
-template <>
-__device__ __forceinline__ float4 ld_feat<4>(const float *p) { return ldg_stream4(p); }
-template <>
-__device__ __forceinline__ float2 ld_feat<2>(const float *p) {
-    float2 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
-    return r;
-}
-template <>
-__device__ __forceinline__ float ld_feat<1>(const float *p) {
-    float r;
-    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
-    return r;
-}
-__device__ __forceinline__ void vadd(float4 &a, const float4 &b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
-__device__ __forceinline__ void vadd(float2 &a, const float2 &b) { a.x += b.x; a.y += b.y; }
-__device__ __forceinline__ void vadd(float &a, const float &b) { a += b; }
-__device__ __forceinline__ void vzero(float4 &a) { a = make_float4(0.f, 0.f, 0.f, 0.f); }
-__device__ __forceinline__ void vzero(float2 &a) { a = make_float2(0.f, 0.f); }
-__device__ __forceinline__ void vzero(float &a) { a = 0.f; }
-
-__host__ __device__ inline int64_t pool_chunk_start(int64_t total, int g, int G) {
-    return total * (int64_t)g / G;      // total < 2^31, G < 2^12
-}
-
-struct PoolParams {
-    const float *feat;
-    int c;
-    const int32_t *row_index;
-    const uint32_t *member;      // [total, words] or null
-    const int32_t *label;        // [total] or null
-    const int64_t *seg_off;
-    int n_seg, k, words;
-    int64_t cap;
-    float *part_sum;             // [n_seg + G, k, c]
-    int32_t *part_cnt;           // [n_seg + G, k]
-    int wc;                      // channels per CTA slice
-};
-
-template <int VEC, int WORDS, bool LABEL>
-__global__ void __launch_bounds__(POOL_MAX_THREADS, 1) pool_kernel(const PoolParams P) {
-    using V = typename VecT<VEC>::type;
-    extern __shared__ __align__(16) unsigned char smem_acc[];
-    V *acc = reinterpret_cast<V *>(smem_acc);           // [k][blockDim.x]
-    const int tid = threadIdx.x, T = blockDim.x;
-    const int G = gridDim.x, g = blockIdx.x;
-    const int ch = blockIdx.y * P.wc + tid * VEC;        // first channel of this thread
-    const bool active = ch < P.c && tid * VEC < P.wc;
-    int64_t total = P.seg_off[P.n_seg];
-    if (total > P.cap) total = 0;
-    int64_t p = pool_chunk_start(total, g, G);
-    const int64_t p_end = pool_chunk_start(total, g + 1, G);
-    if (p >= p_end) return;
-    int s = seg_of(P.seg_off, P.n_seg, p);
-    const bool count_warp = (blockIdx.y == 0) && (tid < 32);
-    const int k = P.k;
-
-    while (p < p_end) {
-        const int64_t s_end = P.seg_off[s + 1];
-        const int64_t e = s_end < p_end ? s_end : p_end;
-        if (e > p) {
-            // ---- one (CTA, segment) piece: zero own accumulator columns
-            for (int m = 0; m < k; ++m) vzero(acc[m * T + tid]);
-            int cnt_reg[MAX_WORDS];
-#pragma unroll
-            for (int j = 0; j < MAX_WORDS; ++j) cnt_reg[j] = 0;
-
-            V bufA[POOL_HALF], bufB[POOL_HALF];
-            uint32_t bitA[POOL_HALF][WORDS], bitB[POOL_HALF][WORDS];
-
-            auto load_half = [&](V (&buf)[POOL_HALF], uint32_t (&bits)[POOL_HALF][WORDS], int64_t base) {
-#pragma unroll
-                for (int j = 0; j < POOL_HALF; ++j) {
-                    const int64_t i = base + j;
-                    if (i < e) {
-                        if (LABEL) {
-                            bits[j][0] = (uint32_t)__ldg(P.label + i);
-                        } else {
-#pragma unroll
-                            for (int w = 0; w < WORDS; ++w)
-                                bits[j][w] = (w < P.words) ? __ldg(P.member + i * P.words + w) : 0u;
-                        }
-                        const int64_t row = P.row_index ? (int64_t)__ldg(P.row_index + i) : i;
-                        if (active) buf[j] = ld_feat<VEC>(P.feat + row * P.c + ch);
-                    }
-                }
-            };
-            auto consume_half = [&](V (&buf)[POOL_HALF], uint32_t (&bits)[POOL_HALF][WORDS], int64_t base) {
-#pragma unroll
-                for (int j = 0; j < POOL_HALF; ++j) {
-                    if (base + j < e) {
-                        if (LABEL) {
-                            const int m = (int)bits[j][0];
-                            if (m >= 0 && m < k) {
-                                if (active) { V a = acc[m * T + tid]; vadd(a, buf[j]); acc[m * T + tid] = a; }
-                                if (count_warp && (m & 31) == tid) {
-#pragma unroll
-                                    for (int w = 0; w < MAX_WORDS; ++w) cnt_reg[w] += ((m >> 5) == w) ? 1 : 0;
-                                }
-                            }
-                        } else {
-#pragma unroll
-                            for (int w = 0; w < WORDS; ++w) {
-                                uint32_t b = bits[j][w];
-                                if (count_warp) cnt_reg[w] += (b >> tid) & 1u;
-                                while (b) {
-                                    const int m = w * 32 + __ffs(b) - 1;
-                                    b &= b - 1;
-                                    if (active) { V a = acc[m * T + tid]; vadd(a, buf[j]); acc[m * T + tid] = a; }
-                                }
-                            }
-                        }
-                    }
-                }
-            };
-
-            load_half(bufA, bitA, p);
-            for (int64_t base = p; base < e; base += 2 * POOL_HALF) {
-                load_half(bufB, bitB, base + POOL_HALF);
-                consume_half(bufA, bitA, base);
-                load_half(bufA, bitA, base + 2 * POOL_HALF);
-                consume_half(bufB, bitB, base + POOL_HALF);
-            }
-
-            // ---- flush this piece
-            const size_t slot = (size_t)s + g;
-            if (active) {
-                float *dst = P.part_sum + (slot * k) * P.c + ch;
-                for (int m = 0; m < k; ++m)
-                    *reinterpret_cast<V *>(dst + (size_t)m * P.c) = acc[m * T + tid];
-            }
-            if (count_warp) {
-#pragma unroll
-                for (int w = 0; w < MAX_WORDS; ++w) {
-                    const int m = w * 32 + tid;
-                    if (m < k) P.part_cnt[slot * k + m] = cnt_reg[w];
-                }
-            }
-        }
-        p = e;
-        ++s;
-    }
-}
-
-__global__ void __launch_bounds__(256)
-pool_combine_kernel(const float *__restrict__ part_sum, const int32_t *__restrict__ part_cnt,
-                    const int64_t *__restrict__ seg_off, int n_seg, int64_t cap, int k, int c, int G,
-                    float *__restrict__ sum, int32_t *__restrict__ cnt, float *__restrict__ mean) {
-    const int s = blockIdx.y;
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;      // element of [k, c]
-    if (e >= k * c) return;
-    int64_t total = seg_off[n_seg];
-    if (total > cap) total = 0;
-    const int64_t a = seg_off[s], b = total ? seg_off[s + 1] : a;
-    float acc = 0.f;
-    int n = 0;
-    const int m = e / c;
-    if (b > a) {
-        // CTAs whose chunk intersects [a, b): chunk g = [total*g/G, total*(g+1)/G)
-        int g_lo = (int)(a * (int64_t)G / total);
-        while (g_lo > 0 && pool_chunk_start(total, g_lo, G) > a) --g_lo;
-        while (g_lo + 1 < G && pool_chunk_start(total, g_lo + 1, G) <= a) ++g_lo;
-        for (int g = g_lo; g < G; ++g) {
-            const int64_t cs = pool_chunk_start(total, g, G), ce = pool_chunk_start(total, g + 1, G);
-            if (cs >= b) break;
-            const int64_t lo = cs > a ? cs : a, hi = ce < b ? ce : b;
-            if (hi <= lo) continue;
-            const size_t slot = (size_t)s + g;
-            acc += part_sum[slot * k * c + e];                  // fixed ascending-g order
-            n += part_cnt[slot * k + m];
-        }
-    }
-    sum[(size_t)s * k * c + e] = acc;
-    if (mean) mean[(size_t)s * k * c + e] = n > 0 ? __fdiv_rn(acc, (float)n) : 0.f;
-    if (cnt && (e % c) == 0) cnt[(size_t)s * k + m] = n;
-}
-
 // ---- scatter ------------------------------------------------------------------------------
 template <int VEC>
 __global__ void __launch_bounds__(1024)
@@ -340,69 +152,6 @@ scatter_kernel(const uint32_t *__restrict__ member, const int32_t *__restrict__ 
     }
 }
 
-static int words_for(int k) { return (k + 31) / 32; }
-
-struct PoolPlan {
-    int vec, wc, threads, slices, G;
-    size_t smem;
-};
-
-static bool plan_pool(int c, int k, bool aligned16, PoolPlan *pl) {
-    // channels per CTA slice: the whole row when the k accumulator rows fit in shared memory and
-    // one thread per VEC channels stays within POOL_MAX_THREADS, else even slices of whole warps
-    int vec = (c % 4 == 0 && aligned16) ? 4 : 1;
-    const int gran = 32 * vec;
-    int wc = c < POOL_MAX_THREADS * vec ? c : POOL_MAX_THREADS * vec;
-    while ((size_t)k * ((wc + vec - 1) / vec * vec) * 4 > (size_t)POOL_SMEM_MAX) {
-        const int next = ((wc - 1) / gran) * gran;
-        if (next <= 0) return false;
-        wc = next;
-    }
-    if (wc < c) {
-        const int slices = (c + wc - 1) / wc;
-        const int even = ((c + slices - 1) / slices + gran - 1) / gran * gran;
-        if (even <= wc) wc = even;
-    }
-    // few threads per CTA starve the memory pipeline: narrow the per-thread vector instead
-    if (vec == 4 && wc / 4 < 128 && wc % 2 == 0) vec = 2;
-    if (vec == 2 && wc / 2 < 128) vec = 1;
-    const int threads = ((wc + vec - 1) / vec + 31) / 32 * 32;
-    if (threads > POOL_MAX_THREADS) return false;
-    pl->vec = vec; pl->wc = wc; pl->threads = threads;
-    pl->slices = (c + wc - 1) / wc;
-    pl->smem = (size_t)k * threads * vec * 4;
-    if (pl->smem > (size_t)POOL_SMEM_MAX) return false;
-    const int per_sm = (int)(POOL_SMEM_MAX / (pl->smem ? pl->smem : 1));
-    const int ctas = sm_count() * (per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm));
-    pl->G = ctas / pl->slices;
-    if (pl->G < 1) pl->G = 1;
-    return true;
-}
-
-template <int VEC, int WORDS, bool LABEL>
-static void launch_pool(const PoolParams &P, const PoolPlan &pl, cudaStream_t stream) {
-    auto kern = pool_kernel<VEC, WORDS, LABEL>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, POOL_SMEM_MAX);
-        attr_set = true;
-    }
-    kern<<<dim3(pl.G, pl.slices), pl.threads, pl.smem, stream>>>(P); count_launches(1);
-}
-
-template <int VEC>
-static int dispatch_pool(const PoolParams &P, const PoolPlan &pl, cudaStream_t stream) {
-    if (P.label) { launch_pool<VEC, 1, true>(P, pl, stream); return XM3D_OK; }
-    switch (P.words) {
-        case 1: launch_pool<VEC, 1, false>(P, pl, stream); break;
-        case 2: launch_pool<VEC, 2, false>(P, pl, stream); break;
-        case 3: launch_pool<VEC, 3, false>(P, pl, stream); break;
-        case 4: launch_pool<VEC, 4, false>(P, pl, stream); break;
-        case 5: case 6: case 7: case 8: launch_pool<VEC, 8, false>(P, pl, stream); break;
-        default: return XM3D_ERR_UNSUPPORTED;
-    }
-    return XM3D_OK;
-}
 
 }  // namespace xm3d
 
@@ -444,50 +193,6 @@ extern "C" int xm3d_gather_masks_batch(const void *masks, int32_t mask_kind, int
         point_bits_kernel<<<(unsigned)((cap + 255) / 256), 256, 0, stream>>>(pixbits, rowcol, seg_off, n_seg, cap, k, h,
                                                                              w, words, member, counts); count_launches(1); }
     return check_launch("xm3d_gather_masks_batch");
-}
-
-extern "C" size_t xm3d_pool_ws_bytes(int32_t n_seg, int32_t k, int32_t c) {
-    const size_t slots = (size_t)n_seg + (size_t)sm_count() * 4 + 1;
-    return align_up(slots * k * c * 4, 256) + align_up(slots * k * 4, 256) + 256;
-}
-
-extern "C" int xm3d_pool_batch(const float *feat, int32_t c, const int32_t *row_index, const uint32_t *member,
-                               const int32_t *label, int32_t n_seg, int32_t k, const int64_t *seg_off, int64_t cap,
-                               float *sum, int32_t *cnt, float *mean, void *ws, size_t ws_bytes, int32_t *status,
-                               xm3d_stream_t stream_) {
-    (void)status;
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    XM3D_REQUIRE(n_seg > 0 && k > 0 && c > 0 && cap >= 0, "bad sizes");
-    XM3D_REQUIRE(k <= 32 * MAX_WORDS, "at most 256 masks per segment");
-    XM3D_REQUIRE(feat && seg_off && sum && ws, "null pointer");
-    XM3D_REQUIRE((member != nullptr) != (label != nullptr), "exactly one of member / label");
-    if (ws_bytes < xm3d_pool_ws_bytes(n_seg, k, c)) {
-        set_error("xm3d_pool_batch: workspace too small");
-        return XM3D_ERR_WORKSPACE;
-    }
-    PoolPlan pl;
-    const bool aligned16 = reinterpret_cast<uintptr_t>(feat) % 16 == 0;
-    if (!plan_pool(c, k, aligned16, &pl)) {
-        set_error("xm3d_pool_batch: k=%d accumulator rows do not fit in shared memory", k);
-        return XM3D_ERR_UNSUPPORTED;
-    }
-    const size_t slots = (size_t)n_seg + (size_t)sm_count() * 4 + 1;
-    Carver cv(ws);
-    float *part_sum = cv.take<float>(slots * k * c);
-    int32_t *part_cnt = cv.take<int32_t>(slots * k);
-
-    PoolParams P;
-    P.feat = feat; P.c = c; P.row_index = row_index; P.member = member; P.label = label; P.seg_off = seg_off;
-    P.n_seg = n_seg; P.k = k; P.words = words_for(k); P.cap = cap; P.part_sum = part_sum; P.part_cnt = part_cnt;
-    P.wc = pl.wc;
-    int rc = XM3D_OK;
-    if (pl.vec == 4) rc = dispatch_pool<4>(P, pl, stream);
-    else if (pl.vec == 2) rc = dispatch_pool<2>(P, pl, stream);
-    else rc = dispatch_pool<1>(P, pl, stream);
-    if (rc != XM3D_OK) { set_error("xm3d_pool_batch: unsupported mask count"); return rc; }
-    dim3 cgrid((unsigned)(((size_t)k * c + 255) / 256), n_seg);
-    pool_combine_kernel<<<cgrid, 256, 0, stream>>>(part_sum, part_cnt, seg_off, n_seg, cap, k, c, pl.G, sum, cnt, mean); count_launches(1);
-    return check_launch("xm3d_pool_batch");
 }
 
 extern "C" int xm3d_scatter_batch(const uint32_t *member, const int32_t *label, int32_t n_seg, int32_t k,

@@ -246,10 +246,21 @@ def gather_masks(masks: torch.Tensor, rowcol: torch.Tensor, seg_off: torch.Tenso
     return member, counts
 
 
+def _popcount32(x: torch.Tensor) -> torch.Tensor:
+    x = x.to(torch.int64) & 0xFFFFFFFF
+    x = x - ((x >> 1) & 0x55555555)
+    x = (x & 0x33333333) + ((x >> 2) & 0x33333333)
+    x = (x + (x >> 4)) & 0x0F0F0F0F
+    return (x * 0x01010101 >> 24) & 0xFF
+
+
 def pool(feat: torch.Tensor, seg_off: torch.Tensor, k: int, member: Optional[torch.Tensor] = None,
          label: Optional[torch.Tensor] = None, row_index: Optional[torch.Tensor] = None,
-         cap: Optional[int] = None, want_mean: bool = True, ws: Optional[torch.Tensor] = None):
+         cap: Optional[int] = None, cap_pairs: Optional[int] = None, want_mean: bool = True,
+         ws: Optional[torch.Tensor] = None, status: Optional[torch.Tensor] = None):
     """Segmented mean pooling.  feat float32 [rows,c]; member int32 [cap,words] or label int32 [cap].
+    cap_pairs: bound on the number of (point, mask) memberships (None: labels -> cap, members ->
+    counted on the device, which costs one host sync).
     Returns (sum [n_seg,k,c], cnt int32 [n_seg,k], mean [n_seg,k,c] or None)."""
     _require_cuda()
     dev = feat.device
@@ -267,15 +278,18 @@ def pool(feat: torch.Tensor, seg_off: torch.Tensor, k: int, member: Optional[tor
     if row_index is not None:
         row_index = _dev_contig(row_index, torch.int32)
     cap = int(n_pts) if cap is None else int(cap)
+    if cap_pairs is None:
+        cap_pairs = cap if member is None else int(_popcount32(member[:cap]).sum().item())
+    cap_pairs = int(cap_pairs)
     s = torch.empty((n_seg, k, c), dtype=torch.float32, device=dev)
     cnt = torch.empty((n_seg, k), dtype=torch.int32, device=dev)
     mean = torch.empty((n_seg, k, c), dtype=torch.float32, device=dev) if want_mean else None
-    need = L.lib().xm3d_pool_ws_bytes(n_seg, k, c)
+    need = L.lib().xm3d_pool_ws_bytes(n_seg, k, c, cap_pairs)
     if ws is None or ws.numel() < need:
         ws = _ws(need, dev)
     L.check(L.lib().xm3d_pool_batch(_ptr(feat), c, _ptr(row_index), _ptr(member), _ptr(label), n_seg, int(k),
-                                    _ptr(seg_off), cap, _ptr(s), _ptr(cnt), _ptr(mean), _ptr(ws), ws.numel(),
-                                    None, _stream()))
+                                    _ptr(seg_off), cap, cap_pairs, _ptr(s), _ptr(cnt), _ptr(mean), _ptr(ws),
+                                    ws.numel(), _ptr(status), _stream()))
     return s, cnt, mean
 
 

@@ -65,7 +65,8 @@ class CorrespondencePipeline:
     """Owns the device-resident inputs of a batch and the workspaces; `run` enqueues one pass."""
 
     def __init__(self, batch: Batch, k: int, c: int, device, cap_vis: Optional[int] = None,
-                 cut_bound: int = 10, vis_thres: float = 0.25, depth_scale: float = 1000.0):
+                 cut_bound: int = 10, vis_thres: float = 0.25, depth_scale: float = 1000.0,
+                 pairs_per_point: float = 1.0):
         ops._require_cuda()
         self.batch, self.k, self.c, self.dev = batch, int(k), int(c), device
         self.cut_bound, self.vis_thres, self.depth_scale = cut_bound, vis_thres, depth_scale
@@ -82,7 +83,12 @@ class CorrespondencePipeline:
         self.ws_proj = ops._ws(lib.xm3d_project_ws_bytes(self.n_views, self.total_pv, int(n_pts.max())), device)
         self.ws_vox = ops._ws(lib.xm3d_voxelize_ws_bytes(self.n_views, self.cap_vis), device)
         self.ws_gather = ops._ws(lib.xm3d_gather_ws_bytes(self.n_views, self.k, IMG_H, IMG_W), device)
-        self.ws_pool = ops._ws(lib.xm3d_pool_ws_bytes(self.n_views, self.k, self.c), device)
+        self.pairs_per_point = float(pairs_per_point)     # bound on masks per visible point (1 = partition)
+        self._size_pool_ws()
+
+    def _size_pool_ws(self):
+        self.cap_pairs = int(self.cap_vis * self.pairs_per_point) + 1
+        self.ws_pool = ops._ws(L.lib().xm3d_pool_ws_bytes(self.n_views, self.k, self.c, self.cap_pairs), self.dev)
 
     def upload(self, xyz_host: torch.Tensor, depth_host: torch.Tensor):
         """H2D of the loader-side inputs (pinned host tensors -> device), on the current stream."""
@@ -92,6 +98,7 @@ class CorrespondencePipeline:
     def set_cap(self, cap_vis: int):
         self.cap_vis = int(cap_vis)
         self.ws_vox = ops._ws(L.lib().xm3d_voxelize_ws_bytes(self.n_views, self.cap_vis), self.dev)
+        self._size_pool_ws()
 
     def project(self):
         return ops.project_batch(self.xyz, self.views, self.out_off, self.depth, depth_scale=self.depth_scale,
@@ -113,7 +120,8 @@ class CorrespondencePipeline:
         member, _ = ops.gather_masks(masks, pr.rowcol, pr.vis_off, mode=mode, cap=self.cap_vis, ws=self.ws_gather)
         if times is not None:
             times.mark("gather")
-        s, cnt, mean = ops.pool(feat, pr.vis_off, self.k, member=member, cap=self.cap_vis, ws=self.ws_pool)
+        s, cnt, mean = ops.pool(feat, pr.vis_off, self.k, member=member, cap=self.cap_vis, cap_pairs=self.cap_pairs,
+                                ws=self.ws_pool, status=pr.status)
         if times is not None:
             times.mark("pool")
         return {"proj": pr, "vox": vox, "member": member, "sum": s, "cnt": cnt, "mean": mean}
