@@ -176,7 +176,7 @@ XM3D_API int xm3d_gather_masks_batch(const void *masks, int32_t mask_kind, int32
  *   masks); beyond it XM3D_FLAG_PAIR_OVERFLOW is raised and the sums are zero.
  *   sum [n_seg,k,c] float32, cnt [n_seg,k] int32 (optional), mean (optional) [n_seg,k,c] = sum/cnt
  *   (0 where cnt = 0).  Deterministic: every summation order is fixed by the point order. */
-XM3D_API size_t xm3d_pool_ws_bytes(int32_t n_seg, int32_t k, int32_t c, int64_t cap_pairs);
+XM3D_API size_t xm3d_pool_ws_bytes(int32_t n_seg, int32_t k, int32_t c, int64_t cap, int64_t cap_pairs);
 XM3D_API int xm3d_pool_batch(const float *feat, int32_t c, const int32_t *row_index, const uint32_t *member,
                     const int32_t *label, int32_t n_seg, int32_t k, const int64_t *seg_off, int64_t cap,
                     int64_t cap_pairs, float *sum, int32_t *cnt, float *mean, void *ws, size_t ws_bytes,

@@ -28,39 +28,61 @@ __device__ __forceinline__ bool mask_hit(float x, int thr_mode) {
 }
 
 // ---- gather, step 1: [k,h,w] masks -> per-pixel membership words ---------------------------
+// One thread owns PIX = 16 / sizeof(T) consecutive pixels and walks the k mask planes with
+// 16-byte loads (four planes in flight), so every plane is read exactly once, coalesced.
+template <typename T>
+__device__ __forceinline__ bool pix_hit(T v, int thr_mode) {
+    if (sizeof(T) == 1 && thr_mode == XM3D_THR_GE_HALF) return v != 0;      // bool / uint8 masks: 1 >= 0.5
+    return mask_hit((float)v, thr_mode);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 pixel_bits_kernel(const T *__restrict__ masks, int thr_mode, int k, int hw, int words, int vec_ok,
                   uint32_t *__restrict__ pixbits) {
+    constexpr int PIX = 16 / sizeof(T);
     const int s = blockIdx.y;
-    const int p0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int p0 = (blockIdx.x * blockDim.x + threadIdx.x) * PIX;
     if (p0 >= hw) return;
-    const T *base = masks + (size_t)s * k * hw;
-    uint32_t *out = pixbits + ((size_t)s * hw + p0) * words;
-    const int np = min(4, hw - p0);
+    const T *base = masks + (size_t)s * k * hw + p0;
+    uint32_t *out = pixbits + (size_t)s * words * hw + p0;      // layout [segment][word][pixel]
+    const int np = min(PIX, hw - p0);
+    const bool vec = vec_ok && np == PIX;
     for (int wd = 0; wd < words; ++wd) {
-        uint32_t acc[4] = {0u, 0u, 0u, 0u};
-        const int m_end = min(k, (wd + 1) * 32);
-        for (int m = wd * 32; m < m_end; ++m) {
-            const T *pl = base + (size_t)m * hw + p0;
-            float x[4];
-            if (vec_ok && np == 4) {
-                if (sizeof(T) == 1) {
-                    const uchar4 v = __ldg(reinterpret_cast<const uchar4 *>(pl));
-                    x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
-                } else {
-                    const float4 v = __ldg(reinterpret_cast<const float4 *>(pl));
-                    x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
-                }
-            } else {
+        uint32_t acc[PIX];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) x[j] = (j < np) ? (float)__ldg(pl + j) : 0.f;
+        for (int j = 0; j < PIX; ++j) acc[j] = 0u;
+        const int m_end = min(k, (wd + 1) * 32);
+        for (int m0 = wd * 32; m0 < m_end; m0 += 4) {
+            union { uint4 q; T e[PIX]; } v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (m0 + u < m_end) {
+                    const T *pl = base + (size_t)(m0 + u) * hw;
+                    if (vec) {
+                        v[u].q = __ldg(reinterpret_cast<const uint4 *>(pl));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < PIX; ++j) v[u].e[j] = (j < np) ? __ldg(pl + j) : T(0);
+                    }
+                }
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (mask_hit(x[j], thr_mode)) acc[j] |= 1u << (m & 31);
+            for (int u = 0; u < 4; ++u)
+                if (m0 + u < m_end) {
+#pragma unroll
+                    for (int j = 0; j < PIX; ++j)
+                        if (pix_hit<T>(v[u].e[j], thr_mode)) acc[j] |= 1u << ((m0 + u) & 31);
+                }
         }
-        for (int j = 0; j < np; ++j) out[(size_t)j * words + wd] = acc[j];
+        uint32_t *o = out + (size_t)wd * hw;
+        if (vec) {
+#pragma unroll
+            for (int j = 0; j < PIX; j += 4)
+                *reinterpret_cast<uint4 *>(o + j) = make_uint4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+        } else {
+            for (int j = 0; j < np; ++j) o[j] = acc[j];
+        }
     }
 }
 
@@ -78,10 +100,11 @@ point_bits_kernel(const uint32_t *__restrict__ pixbits, const int32_t *__restric
     const int s = seg_of(seg_off, n_seg, i);
     const int2 rc = __ldg(reinterpret_cast<const int2 *>(rowcol) + i);
     const bool inb = rc.x >= 0 && rc.x < h && rc.y >= 0 && rc.y < w;
-    const uint32_t *src = pixbits + ((size_t)s * h * w + (size_t)rc.x * w + rc.y) * words;
+    const size_t hw = (size_t)h * w;
+    const uint32_t *src = pixbits + (size_t)s * words * hw + (size_t)rc.x * w + rc.y;
     const unsigned sameseg = __match_any_sync(act, s);
     for (int wd = 0; wd < words; ++wd) {
-        const uint32_t b = inb ? __ldg(src + wd) : 0u;
+        const uint32_t b = inb ? __ldg(src + (size_t)wd * hw) : 0u;
         member[i * words + wd] = b;
         if (counts) {
             if (sameseg == act) {          // warp inside one segment: one atomic per mask per warp
@@ -180,8 +203,9 @@ extern "C" int xm3d_gather_masks_batch(const void *masks, int32_t mask_kind, int
     const int words = words_for(k), hw = h * w;
     uint32_t *pixbits = static_cast<uint32_t *>(ws);
     const int esz = mask_kind == XM3D_MASK_U8 ? 1 : 4;
-    const int vec_ok = (hw % 4 == 0) && (reinterpret_cast<uintptr_t>(masks) % (4 * esz) == 0);
-    dim3 grid((hw / 4 + 256) / 256, n_seg);
+    const int pix = 16 / esz;
+    const int vec_ok = (hw % pix == 0) && (reinterpret_cast<uintptr_t>(masks) % 16 == 0);
+    dim3 grid(((hw + pix - 1) / pix + 255) / 256, n_seg);
     if (mask_kind == XM3D_MASK_U8) {
         pixel_bits_kernel<unsigned char><<<grid, 256, 0, stream>>>(static_cast<const unsigned char *>(masks), thr_mode,
                                                                     k, hw, words, vec_ok, pixbits); count_launches(1); }

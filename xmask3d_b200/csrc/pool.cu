@@ -7,11 +7,12 @@
 //   sum[s,m,:] = sum of feat[row(i),:] over points i of segment s inside mask m ;  cnt[s,m]
 //
 // This is the dominant HBM stream of the whole path (n x C float32, read once).  Design:
-//   count   one CTA per segment: points per (segment, mask)                    (shared-mem atomics)
+//   count   one CTA per tile of 1024 points: members of every mask in the tile (warp ballots)
+//   prefix  per (segment, mask): exclusive prefix of the tile counts, unit totals cnt[s][m]
 //   scan    one CTA: exclusive prefixes -> pair offsets and chunk offsets of every (segment, mask)
-//   fill    one CTA per segment: STABLE partition of the segment's points by mask (ballot ranks
-//           inside a warp, byte counters across warps) -> perm[] = feature row of every
-//           (point, mask) pair, masks ascending, points ascending inside a mask
+//   fill    one CTA per tile: STABLE placement (ballot ranks inside a warp, byte counters across
+//           warps, tile prefixes across tiles) -> perm[] = feature row of every (point, mask)
+//           pair, masks ascending, points ascending inside a mask
 //   sum     one CTA per chunk of <= 256 pairs of one (segment, mask): each thread owns VEC channels
 //           and accumulates the chunk's rows in REGISTERS — no atomics, no shared-memory traffic;
 //           rows are fetched 8 at a time with 16-byte L1-bypassing loads and many CTAs are
@@ -63,33 +64,112 @@ __device__ __forceinline__ void load_bits(const PoolIdx &P, int64_t i, bool vali
     }
 }
 
-__global__ void __launch_bounds__(FILL_THREADS, 1)
-pool_count_kernel(const PoolIdx P, int32_t *__restrict__ cnt /*[n_seg*k]*/) {
-    __shared__ int s_cnt[32 * MAX_WORDS];
-    const int s = blockIdx.x, tid = threadIdx.x;
-    int64_t total = P.seg_off[P.n_seg];
-    const bool over = total > P.cap;
-    const int64_t a = over ? 0 : P.seg_off[s], e = over ? 0 : P.seg_off[s + 1];
-    for (int m = tid; m < 32 * MAX_WORDS; m += FILL_THREADS) s_cnt[m] = 0;
+// tiles: every segment is cut into tiles of FILL_THREADS points; tile_off[s] = first tile of segment s
+__global__ void __launch_bounds__(1024, 1)
+pool_tileplan_kernel(const int64_t *__restrict__ seg_off, int n_seg, int64_t cap, int32_t *__restrict__ tile_off) {
+    __shared__ int s_w[32];
+    __shared__ int s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool over = seg_off[n_seg] > cap;
+    if (tid == 0) s_carry = 0;
     __syncthreads();
-    for (int64_t base = a; base < e; base += FILL_THREADS) {
-        const int64_t i = base + tid;
-        uint32_t b[MAX_WORDS];
-        load_bits(P, i, i < e, b);
+    for (int base = 0; base < n_seg; base += 1024) {
+        const int s = base + tid;
+        const int val = (s < n_seg && !over) ? (int)((seg_off[s + 1] - seg_off[s] + FILL_THREADS - 1) / FILL_THREADS) : 0;
+        int incl = val;
 #pragma unroll
-        for (int w = 0; w < MAX_WORDS; ++w) {
-            // one shared atomic per (warp, mask): ballot over the warp's union of set bits
-            uint32_t u = __reduce_or_sync(0xffffffffu, b[w]);
-            while (u) {
-                const int bit = __ffs(u) - 1;
-                u &= u - 1;
-                const unsigned vote = __ballot_sync(0xffffffffu, (b[w] >> bit) & 1u);
-                if ((tid & 31) == 0) atomicAdd(&s_cnt[w * 32 + bit], __popc(vote));
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const int w = s_w[lane];
+            int wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
             }
+            s_w[lane] = wi - w;
+        }
+        __syncthreads();
+        const int excl = s_carry + s_w[warp] + incl - val;
+        if (s < n_seg) tile_off[s] = excl;
+        __syncthreads();
+        if (tid == 1023) s_carry = excl + val;
+        __syncthreads();
+    }
+    if (tid == 0) tile_off[n_seg] = s_carry;
+}
+
+// Per-warp member counts of one tile: s_wtot[warp][mask] (bytes, <= 32 each).  All threads call it.
+__device__ __forceinline__ void tile_warp_counts(const uint32_t (&b)[MAX_WORDS], uint32_t (&uni)[MAX_WORDS],
+                                                 unsigned char (*s_wtot)[32 * MAX_WORDS], int warp, int lane) {
+#pragma unroll
+    for (int w = 0; w < MAX_WORDS; ++w) {
+        uni[w] = __reduce_or_sync(0xffffffffu, b[w]);
+        uint32_t u = uni[w];
+        while (u) {
+            const int bit = __ffs(u) - 1;
+            u &= u - 1;
+            const unsigned vote = __ballot_sync(0xffffffffu, (b[w] >> bit) & 1u);
+            if (lane == 0) s_wtot[warp][w * 32 + bit] = (unsigned char)__popc(vote);
         }
     }
+}
+
+__device__ __forceinline__ int tile_segment(const int32_t *__restrict__ tile_off, int n_seg, int tile) {
+    int lo = 0, hi = n_seg;        // largest s with tile_off[s] <= tile
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (tile_off[mid] <= tile) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// one CTA per tile: members of every mask inside the tile -> tile_cnt[tile][k]
+__global__ void __launch_bounds__(FILL_THREADS, 1)
+pool_tilecount_kernel(const PoolIdx P, const int32_t *__restrict__ tile_off, int32_t *__restrict__ tile_cnt) {
+    __shared__ unsigned char s_wtot[32][32 * MAX_WORDS];
+    __shared__ int s_seg;
+    const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tile >= tile_off[P.n_seg]) return;
+    if (tid == 0) s_seg = tile_segment(tile_off, P.n_seg, tile);
+    for (int j = tid; j < 32 * 32 * MAX_WORDS / 4; j += FILL_THREADS) reinterpret_cast<uint32_t *>(&s_wtot[0][0])[j] = 0u;
     __syncthreads();
-    for (int m = tid; m < P.k; m += FILL_THREADS) cnt[(size_t)s * P.k + m] = s_cnt[m];
+    const int s = s_seg;
+    const int64_t e = P.seg_off[s + 1];
+    const int64_t i = P.seg_off[s] + (int64_t)(tile - tile_off[s]) * FILL_THREADS + tid;
+    uint32_t b[MAX_WORDS], uni[MAX_WORDS];
+    load_bits(P, i, i < e, b);
+    tile_warp_counts(b, uni, s_wtot, warp, lane);
+    __syncthreads();
+    if (tid < P.k) {
+        int run = 0;
+#pragma unroll 8
+        for (int w = 0; w < 32; ++w) run += s_wtot[w][tid];
+        tile_cnt[(size_t)tile * P.k + tid] = run;
+    }
+}
+
+// one CTA per segment, one thread per mask: exclusive prefix of the tile counts along the
+// segment's tiles (tile_cnt is overwritten with it) and the unit totals cnt[s][m]
+__global__ void __launch_bounds__(256)
+pool_unitprefix_kernel(const int32_t *__restrict__ tile_off, int k, int32_t *__restrict__ tile_cnt,
+                       int32_t *__restrict__ cnt) {
+    const int s = blockIdx.x;
+    const int t0 = tile_off[s], t1 = tile_off[s + 1];
+    for (int m = threadIdx.x; m < k; m += blockDim.x) {
+        int run = 0;
+        for (int t = t0; t < t1; ++t) {
+            const int v = tile_cnt[(size_t)t * k + m];
+            tile_cnt[(size_t)t * k + m] = run;
+            run += v;
+        }
+        cnt[(size_t)s * k + m] = run;
+    }
 }
 
 // exclusive prefixes over the (segment, mask) units: pair offsets and chunk offsets
@@ -146,65 +226,51 @@ pool_scan_kernel(const int32_t *__restrict__ cnt, int n_units, int64_t cap_pairs
     }
 }
 
-// stable partition of each segment's points by mask -> perm[pair] = feature row
+// one CTA per tile: STABLE placement of the tile's (point, mask) pairs:
+// perm[pair_off[s][m] + (members of m in earlier tiles) + (members in earlier warps / lanes)] = row
 __global__ void __launch_bounds__(FILL_THREADS, 1)
-pool_fill_kernel(const PoolIdx P, const int64_t *__restrict__ pair_off, int64_t cap_pairs,
-                 int32_t *__restrict__ perm) {
+pool_fill_kernel(const PoolIdx P, const int32_t *__restrict__ tile_off, const int32_t *__restrict__ tile_pre,
+                 const int64_t *__restrict__ pair_off, int64_t cap_pairs, int32_t *__restrict__ perm) {
     __shared__ unsigned char s_wtot[32][32 * MAX_WORDS];     // per warp, per mask: members in this tile
     __shared__ unsigned short s_wpre[32][32 * MAX_WORDS];    // exclusive prefix over warps
-    __shared__ int64_t s_base[32 * MAX_WORDS];               // next free pair slot of every mask
-    const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ int64_t s_base[32 * MAX_WORDS];               // first pair slot of this tile, per mask
+    __shared__ int s_seg;
+    const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int k = P.k;
-    int64_t total = P.seg_off[P.n_seg];
-    if (total > P.cap || pair_off[(size_t)P.n_seg * k] > cap_pairs) return;     // flagged by the scan
-    const int64_t a = P.seg_off[s], e = P.seg_off[s + 1];
-    for (int m = tid; m < k; m += FILL_THREADS) s_base[m] = pair_off[(size_t)s * k + m];
-    for (int64_t base = a; base < e; base += FILL_THREADS) {
-        for (int j = tid; j < 32 * 32 * MAX_WORDS / 4; j += FILL_THREADS)
-            reinterpret_cast<uint32_t *>(&s_wtot[0][0])[j] = 0u;
-        __syncthreads();
-        const int64_t i = base + tid;
-        uint32_t b[MAX_WORDS], uni[MAX_WORDS];
-        load_bits(P, i, i < e, b);
-#pragma unroll
-        for (int w = 0; w < MAX_WORDS; ++w) {
-            uni[w] = __reduce_or_sync(0xffffffffu, b[w]);
-            uint32_t u = uni[w];
-            while (u) {
-                const int bit = __ffs(u) - 1;
-                u &= u - 1;
-                const unsigned vote = __ballot_sync(0xffffffffu, (b[w] >> bit) & 1u);
-                if (lane == 0) s_wtot[warp][w * 32 + bit] = (unsigned char)__popc(vote);
-            }
-        }
-        __syncthreads();
-        int64_t tile_tot = 0;
-        if (tid < k) {
-            int run = 0;
+    if (tile >= tile_off[P.n_seg] || pair_off[(size_t)P.n_seg * k] > cap_pairs) return;     // overflow: flagged by the scan
+    if (tid == 0) s_seg = tile_segment(tile_off, P.n_seg, tile);
+    for (int j = tid; j < 32 * 32 * MAX_WORDS / 4; j += FILL_THREADS) reinterpret_cast<uint32_t *>(&s_wtot[0][0])[j] = 0u;
+    __syncthreads();
+    const int s = s_seg;
+    const int64_t e = P.seg_off[s + 1];
+    const int64_t i = P.seg_off[s] + (int64_t)(tile - tile_off[s]) * FILL_THREADS + tid;
+    uint32_t b[MAX_WORDS], uni[MAX_WORDS];
+    load_bits(P, i, i < e, b);
+    tile_warp_counts(b, uni, s_wtot, warp, lane);
+    __syncthreads();
+    if (tid < k) {
+        int run = 0;
 #pragma unroll 8
-            for (int w = 0; w < 32; ++w) {
-                s_wpre[w][tid] = (unsigned short)run;
-                run += s_wtot[w][tid];
-            }
-            tile_tot = run;
+        for (int w = 0; w < 32; ++w) {
+            s_wpre[w][tid] = (unsigned short)run;
+            run += s_wtot[w][tid];
         }
-        __syncthreads();
-        const int row = (i < e) ? (P.row_index ? __ldg(P.row_index + i) : (int)i) : 0;
+        s_base[tid] = pair_off[(size_t)s * k + tid] + tile_pre[(size_t)tile * k + tid];
+    }
+    __syncthreads();
+    const int row = (i < e) ? (P.row_index ? __ldg(P.row_index + i) : (int)i) : 0;
 #pragma unroll
-        for (int w = 0; w < MAX_WORDS; ++w) {
-            uint32_t u = uni[w];
-            while (u) {
-                const int bit = __ffs(u) - 1;
-                u &= u - 1;
-                const unsigned vote = __ballot_sync(0xffffffffu, (b[w] >> bit) & 1u);
-                if ((b[w] >> bit) & 1u) {
-                    const int m = w * 32 + bit;
-                    perm[s_base[m] + s_wpre[warp][m] + __popc(vote & ((1u << lane) - 1u))] = row;
-                }
+    for (int w = 0; w < MAX_WORDS; ++w) {
+        uint32_t u = uni[w];
+        while (u) {
+            const int bit = __ffs(u) - 1;
+            u &= u - 1;
+            const unsigned vote = __ballot_sync(0xffffffffu, (b[w] >> bit) & 1u);
+            if ((b[w] >> bit) & 1u) {
+                const int m = w * 32 + bit;
+                perm[s_base[m] + s_wpre[warp][m] + __popc(vote & ((1u << lane) - 1u))] = row;
             }
         }
-        __syncthreads();
-        if (tid < k) s_base[tid] += tile_tot;
     }
 }
 
@@ -281,13 +347,14 @@ pool_combine_kernel(const float *__restrict__ partial, const int32_t *__restrict
 }
 
 struct PoolWs {
-    int32_t *cnt, *chunk_off, *perm;
+    int32_t *cnt, *chunk_off, *perm, *tile_off, *tile_cnt;
+    int64_t max_tiles;
     int64_t *pair_off;
     float *partial;
     int64_t max_chunks;
 };
 
-static PoolWs carve_pool(void *ws, int n_seg, int k, int c, int64_t cap_pairs, size_t *bytes) {
+static PoolWs carve_pool(void *ws, int n_seg, int k, int c, int64_t cap, int64_t cap_pairs, size_t *bytes) {
     Carver cv(ws);
     PoolWs w;
     const size_t units = (size_t)n_seg * k;
@@ -297,6 +364,9 @@ static PoolWs carve_pool(void *ws, int n_seg, int k, int c, int64_t cap_pairs, s
     w.pair_off = cv.take<int64_t>(units + 1);
     w.perm = cv.take<int32_t>((size_t)cap_pairs + 32);
     w.partial = cv.take<float>((size_t)w.max_chunks * c);
+    w.max_tiles = cap / FILL_THREADS + n_seg + 1;
+    w.tile_off = cv.take<int32_t>((size_t)n_seg + 1);
+    w.tile_cnt = cv.take<int32_t>((size_t)w.max_tiles * k);
     *bytes = cv.off + 256;
     return w;
 }
@@ -305,9 +375,9 @@ static PoolWs carve_pool(void *ws, int n_seg, int k, int c, int64_t cap_pairs, s
 
 using namespace xm3d;
 
-extern "C" size_t xm3d_pool_ws_bytes(int32_t n_seg, int32_t k, int32_t c, int64_t cap_pairs) {
+extern "C" size_t xm3d_pool_ws_bytes(int32_t n_seg, int32_t k, int32_t c, int64_t cap, int64_t cap_pairs) {
     size_t b = 0;
-    carve_pool(nullptr, n_seg, k, c, cap_pairs, &b);
+    carve_pool(nullptr, n_seg, k, c, cap, cap_pairs, &b);
     return b;
 }
 
@@ -322,7 +392,7 @@ extern "C" int xm3d_pool_batch(const float *feat, int32_t c, const int32_t *row_
     XM3D_REQUIRE((member != nullptr) != (label != nullptr), "exactly one of member / label");
     XM3D_REQUIRE(cap_pairs < ((int64_t)1 << 31) && (int64_t)n_seg * k < ((int64_t)1 << 30), "sizes exceed int32");
     size_t need = 0;
-    PoolWs w = carve_pool(ws, n_seg, k, c, cap_pairs, &need);
+    PoolWs w = carve_pool(ws, n_seg, k, c, cap, cap_pairs, &need);
     if (ws_bytes < need) {
         set_error("xm3d_pool_batch: workspace too small (%zu < %zu)", ws_bytes, need);
         return XM3D_ERR_WORKSPACE;
@@ -333,9 +403,12 @@ extern "C" int xm3d_pool_batch(const float *feat, int32_t c, const int32_t *row_
     I.member = member; I.label = label; I.row_index = row_index; I.seg_off = seg_off; I.n_seg = n_seg; I.k = k;
     I.words = words_for(k); I.cap = cap;
     const int n_units = n_seg * k;
-    pool_count_kernel<<<n_seg, FILL_THREADS, 0, stream>>>(I, w.cnt); count_launches(1);
+    pool_tileplan_kernel<<<1, 1024, 0, stream>>>(seg_off, n_seg, cap, w.tile_off); count_launches(1);
+    pool_tilecount_kernel<<<(unsigned)w.max_tiles, FILL_THREADS, 0, stream>>>(I, w.tile_off, w.tile_cnt); count_launches(1);
+    pool_unitprefix_kernel<<<n_seg, 256, 0, stream>>>(w.tile_off, k, w.tile_cnt, w.cnt); count_launches(1);
     pool_scan_kernel<<<1, 1024, 0, stream>>>(w.cnt, n_units, cap_pairs, w.pair_off, w.chunk_off, status); count_launches(1);
-    pool_fill_kernel<<<n_seg, FILL_THREADS, 0, stream>>>(I, w.pair_off, cap_pairs, w.perm); count_launches(1);
+    pool_fill_kernel<<<(unsigned)w.max_tiles, FILL_THREADS, 0, stream>>>(I, w.tile_off, w.tile_cnt, w.pair_off, cap_pairs,
+                                                                      w.perm); count_launches(1);
     SumParams S;
     S.feat = feat; S.c = c; S.perm = w.perm; S.pair_off = w.pair_off; S.chunk_off = w.chunk_off; S.n_units = n_units;
     S.cap_pairs = cap_pairs; S.partial = w.partial;

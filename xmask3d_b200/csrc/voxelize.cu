@@ -3,23 +3,29 @@
 // Replaces Voxelizer.voxelize after the matrix draw (reference dataset/voxelizer.py:110-122),
 // fnv_hash_vec / ravel_hash_vec (dataset/voxelization_utils.py:6-35) and the np.unique call of
 // sparse_quantize (:86, :95), batched over segments (one segment = one (scene, view)).
+// np.unique orders its output by ascending KEY (the 64-bit FNV value), returns the index of the
+// first occurrence and the rank of every element; all three are reproduced bit-exactly.
 //
-//   min pass      grid = floor(FMA-chain transform) per point; per-segment column minima
-//                 (warp-shuffle min, one atomicMin per warp and column)
-//   insert pass   key = FNV-1(grid - min); warp-cooperative open-addressing insert: lanes holding
-//                 the same key elect the lowest lane (= lowest point index) with match.any, only
-//                 that lane probes the segment's table (linear probing, 16-byte slots
-//                 {key, first index, rank}); winners of an empty slot append it to the segment's
-//                 unique list with one warp-aggregated atomicAdd
-//   sort pass     one CTA per segment orders the M unique keys ascending (np.unique's order):
-//                 bitonic sort in shared memory when M <= 4096, else a sample sort (4096 sorted
-//                 samples -> splitters -> buckets -> rank inside each bucket), writes the rank
-//                 into the table slot, `first`, and the voxel coordinates
-//   inverse pass  inverse[i] = rank stored in the slot point i resolved to
+//   plan      per-segment table / splitter offsets, counters zeroed                      (1 CTA)
+//   clear     hash-table slots <- empty
+//   min       grid = floor(FMA-chain transform); per-segment column minima
+//   sample    one CTA per segment: S sample keys, bitonic-sorted in shared memory -> splitters
+//   insert    key = FNV-1(grid - min).  Warp-cooperative open addressing: lanes holding the same
+//             key elect the lowest lane (= lowest point index) with match.any; only that lane
+//             probes the segment's table (linear probing, 16-byte slots {key, first, rank}).  The
+//             winner of an empty slot appends (slot, key) to the segment's unique list (one
+//             warp-aggregated atomicAdd), finds the key's splitter bucket and takes a ticket in it
+//   bscan     one CTA per segment: exclusive scan of the bucket counts; prefix of unique counts
+//   scatter   unique keys -> bucket order
+//   rank      one thread per unique key: rank = bucket start + #smaller keys inside its bucket
+//             (~10 keys, L1-resident); writes the rank into the table slot and emits `first` and the
+//             voxel coordinates in unique order
+//   inverse   inverse[i] = rank stored in the slot point i resolved to
 //
-// Everything that decides an integer is exact: the transform is the fp64 FMA chain numpy's
-// dgemm performs, floor() is exact, keys are 64-bit so FNV collisions merge voxels exactly as
-// the reference's np.unique does.
+// Everything that decides an integer is exact: the transform is the fp64 FMA chain numpy's dgemm
+// performs, floor() is exact, keys are 64-bit so FNV collisions merge voxels exactly as the
+// reference's np.unique does.  The sample sort is comparison based, so the skewed high bits of
+// FNV-1 over small integers (only ~50 distinct top-12-bit patterns per scene) cost nothing.
 #include "common.cuh"
 
 namespace xm3d {
@@ -28,9 +34,8 @@ constexpr unsigned long long KEY_EMPTY = 0xFFFFFFFFFFFFFFFFull;
 constexpr unsigned long long FNV_OFFSET = 14695981039346656037ull;
 constexpr unsigned long long FNV_PRIME = 1099511628211ull;
 constexpr int VOX_THREADS = 256;
-constexpr int SORT_THREADS = 1024;
-constexpr int SORT_SMALL = 4096;          // <= this many unique keys: whole-segment bitonic sort
-constexpr int SORT_SAMPLES = 4096;
+constexpr int SPL_MAX = 4096;             // splitters (= buckets) per segment, at most
+constexpr int SPL_MIN = 32;
 constexpr int GRID_LIMIT = 1 << 30;
 
 struct __align__(16) Slot {
@@ -40,6 +45,12 @@ struct __align__(16) Slot {
 };
 
 __host__ __device__ inline int64_t table_size(int64_t n) { return n + n / 2 + 32; }
+// buckets of a segment of n elements: power of two, about one per 8..16 elements
+__host__ __device__ inline int bucket_count(int64_t n) {
+    int s = SPL_MIN;
+    while (s < SPL_MAX && (int64_t)s * 16 < n) s <<= 1;
+    return s;
+}
 
 __device__ __forceinline__ unsigned long long mix64(unsigned long long h) {
     h ^= h >> 33; h *= 0xff51afd7ed558ccdull;
@@ -78,55 +89,100 @@ __device__ __forceinline__ void grid_of(const float *__restrict__ p, const doubl
     }
 }
 
-// ---- plan: per-segment table offsets, zeroed counters -------------------------------------
+// FNV key of point i of segment s (voxelizer.py:115-121: floor(grid - min) -> uint64 -> FNV-1)
+__device__ __forceinline__ unsigned long long point_key(const float *__restrict__ xyz, int64_t i, int s,
+                                                        const double *__restrict__ rt,
+                                                        const int *__restrict__ grid_min) {
+    double f[3];
+    grid_of(xyz + i * 3, rt + 12 * s, f);
+    unsigned long long w[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        if (!(f[j] > -(double)GRID_LIMIT && f[j] < (double)GRID_LIMIT)) f[j] = 0.0;
+        // floor(grid - min) of two integers is their exact difference
+        w[j] = (unsigned long long)(long long)((int)f[j] - grid_min[3 * s + j]);
+    }
+    return fnv3(w[0], w[1], w[2]);
+}
+
+__device__ __forceinline__ unsigned long long clean_key(unsigned long long key, int *status) {
+    if (key == KEY_EMPTY) {              // 2^-64 event: the sentinel value cannot be stored
+        if (status) atomicOr(status, XM3D_FLAG_KEY_SENTINEL);
+        return KEY_EMPTY - 1;
+    }
+    return key;
+}
+
+// bucket of a key: number of splitters < key, splitter j (0..S-2) = spl[j+1]
+__device__ __forceinline__ int bucket_of(const unsigned long long *__restrict__ spl, int S, unsigned long long key) {
+    int lo = 0, hi = S - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (spl[mid + 1] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// exclusive prefix of `val` over a 1024-thread block, carried across calls through *s_carry
+__device__ __forceinline__ int64_t block_excl_scan_1024(int64_t val, int64_t *s_warp, int64_t *s_carry) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int64_t incl = val;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int64_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const int64_t w = s_warp[lane];
+        int64_t wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int64_t t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
+        }
+        s_warp[lane] = wi - w;
+    }
+    __syncthreads();
+    const int64_t excl = *s_carry + s_warp[warp] + incl - val;
+    __syncthreads();
+    if (tid == 1023) *s_carry = excl + val;
+    __syncthreads();
+    return excl;
+}
+
+// ---- plan ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024, 1)
 vox_plan_kernel(const int64_t *__restrict__ seg_off, int n_seg, int64_t cap, int64_t *__restrict__ tbl_off,
-                int64_t *__restrict__ total_eff, int *__restrict__ m, int *__restrict__ grid_min, int *status) {
+                int64_t *__restrict__ spl_off, int64_t *__restrict__ total_eff, int *__restrict__ m,
+                int *__restrict__ grid_min, int *status) {
     __shared__ int64_t s_warp[32];
-    __shared__ int64_t s_carry;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ int64_t s_carry[2];
+    const int tid = threadIdx.x;
     // more elements than the caller's capacity: flag it and process nothing (never overrun)
     const bool over = seg_off[n_seg] > cap;
     if (tid == 0) {
-        s_carry = 0;
+        s_carry[0] = s_carry[1] = 0;
         *total_eff = over ? 0 : seg_off[n_seg];
         if (over && status) atomicOr(status, XM3D_FLAG_VIS_OVERFLOW);
     }
     __syncthreads();
     for (int base = 0; base < n_seg; base += 1024) {
         const int s = base + tid;
-        int64_t val = 0;
+        int64_t vt = 0, vs = 0;
         if (s < n_seg) {
-            val = table_size(over ? 0 : seg_off[s + 1] - seg_off[s]);
+            const int64_t n = over ? 0 : seg_off[s + 1] - seg_off[s];
+            vt = table_size(n);
+            vs = bucket_count(n);
             m[s] = 0;
             if (grid_min) grid_min[3 * s] = grid_min[3 * s + 1] = grid_min[3 * s + 2] = 0x7fffffff;
         }
-        int64_t incl = val;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int64_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        if (lane == 31) s_warp[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            const int64_t w = s_warp[lane];
-            int64_t wi = w;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int64_t t = __shfl_up_sync(0xffffffffu, wi, o);
-                if (lane >= o) wi += t;
-            }
-            s_warp[lane] = wi - w;
-        }
-        __syncthreads();
-        const int64_t excl = s_carry + s_warp[warp] + incl - val;
-        if (s < n_seg) tbl_off[s] = excl;
-        __syncthreads();
-        if (tid == 1023) s_carry = excl + val;
-        __syncthreads();
+        const int64_t et = block_excl_scan_1024(vt, s_warp, &s_carry[0]);
+        const int64_t es = block_excl_scan_1024(vs, s_warp, &s_carry[1]);
+        if (s < n_seg) { tbl_off[s] = et; spl_off[s] = es; }
     }
-    if (tid == 0) tbl_off[n_seg] = s_carry;
+    if (tid == 0) { tbl_off[n_seg] = s_carry[0]; spl_off[n_seg] = s_carry[1]; }
 }
 
 __global__ void __launch_bounds__(256)
@@ -143,13 +199,19 @@ __global__ void __launch_bounds__(VOX_THREADS)
 vox_min_kernel(const float *__restrict__ xyz, const int64_t *__restrict__ seg_off, int n_seg,
                const int64_t *__restrict__ total_eff, const double *__restrict__ rt, int *__restrict__ grid_min,
                int *status) {
+    __shared__ int s_min[VOX_THREADS / 32][3];
     const int64_t total = *total_eff;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t b0 = (int64_t)blockIdx.x * blockDim.x;
+    if (b0 >= total) return;
+    const int64_t i = b0 + threadIdx.x;
     const bool valid = i < total;
-    int s = 0;
+    // segment of the block's first and last point: equal for almost every block
+    const int64_t last = (b0 + blockDim.x - 1 < total) ? b0 + blockDim.x - 1 : total - 1;
+    const int s_first = seg_of(seg_off, n_seg, b0), s_last = seg_of(seg_off, n_seg, last);
+    int s = s_first;
     int g[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff};
     if (valid) {
-        s = seg_of(seg_off, n_seg, i);
+        if (s_first != s_last) s = seg_of(seg_off, n_seg, i);
         double f[3];
         grid_of(xyz + i * 3, rt + 12 * s, f);
 #pragma unroll
@@ -161,42 +223,81 @@ vox_min_kernel(const float *__restrict__ xyz, const int64_t *__restrict__ seg_of
             g[j] = (int)f[j];
         }
     }
-    const unsigned act = __ballot_sync(0xffffffffu, valid);
-    if (!valid) return;
-    const unsigned same = __match_any_sync(act, s);
-    if (same == act) {                 // whole warp in one segment: shuffle-reduce, 3 atomics
+    if (s_first == s_last) {           // warp-shuffle min, then one atomic per block and column
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            int v = g[j];
+        for (int j = 0; j < 3; ++j)
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const int t = __shfl_xor_sync(act, v, o);
-                // lanes outside `act` return garbage only if act is not the full mask; guard below
-                if ((act >> ((lane_id() ^ o) & 31)) & 1u) v = min(v, t);
-            }
-            g[j] = v;
+            for (int o = 16; o > 0; o >>= 1) g[j] = min(g[j], __shfl_xor_sync(0xffffffffu, g[j], o));
+        if (lane_id() == 0) {
+            s_min[threadIdx.x >> 5][0] = g[0]; s_min[threadIdx.x >> 5][1] = g[1]; s_min[threadIdx.x >> 5][2] = g[2];
         }
-        if (lane_id() == (__ffs(act) - 1)) {
-            atomicMin(&grid_min[3 * s + 0], g[0]);
-            atomicMin(&grid_min[3 * s + 1], g[1]);
-            atomicMin(&grid_min[3 * s + 2], g[2]);
+        __syncthreads();
+        if (threadIdx.x < 3) {
+            int v = 0x7fffffff;
+            for (int w = 0; w < VOX_THREADS / 32; ++w) v = min(v, s_min[w][threadIdx.x]);
+            atomicMin(&grid_min[3 * s + threadIdx.x], v);
         }
-    } else {
+    } else if (valid) {
         atomicMin(&grid_min[3 * s + 0], g[0]);
         atomicMin(&grid_min[3 * s + 1], g[1]);
         atomicMin(&grid_min[3 * s + 2], g[2]);
     }
 }
 
-// ---- insert pass --------------------------------------------------------------------------
+// ---- sample pass --------------------------------------------------------------------------
+template <typename K>
+__device__ __forceinline__ void bitonic_smem(K *k, int n /*pow2*/) {
+    for (int size = 2; size <= n; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = threadIdx.x; t < (n >> 1); t += blockDim.x) {
+                const int lo = 2 * t - (t & (stride - 1));     // insert a 0 at bit log2(stride)
+                const int hi = lo + stride;
+                const bool up = (lo & size) == 0;
+                const K a = k[lo], b = k[hi];
+                if ((a > b) == up) { k[lo] = b; k[hi] = a; }
+            }
+            __syncthreads();
+        }
+}
+
 // KEY_SRC 0: keys from xyz through the transform (voxelize); 1: keys given (unique_batch)
+template <int KEY_SRC>
+__global__ void __launch_bounds__(256)
+vox_sample_kernel(const float *__restrict__ xyz, const unsigned long long *__restrict__ keys_in,
+                  const int64_t *__restrict__ seg_off, const int64_t *__restrict__ total_eff,
+                  const double *__restrict__ rt, const int *__restrict__ grid_min,
+                  const int64_t *__restrict__ spl_off, unsigned long long *__restrict__ spl, int *__restrict__ hist) {
+    __shared__ unsigned long long s_key[SPL_MAX];
+    const int s = blockIdx.x, tid = threadIdx.x;
+    const int64_t a = seg_off[s];
+    const int64_t n = (*total_eff > 0) ? seg_off[s + 1] - a : 0;
+    const int S = (int)(spl_off[s + 1] - spl_off[s]);
+    for (int j = tid; j < S; j += 256) {
+        unsigned long long key = KEY_EMPTY;
+        if (n > 0) {
+            const int64_t i = a + (int64_t)j * n / S;          // j < 4096, n < 2^31
+            key = (KEY_SRC == 0) ? point_key(xyz, i, s, rt, grid_min) : keys_in[i];
+            if (key == KEY_EMPTY) key = KEY_EMPTY - 1;
+        }
+        s_key[j] = key;
+        hist[spl_off[s] + j] = 0;
+    }
+    __syncthreads();
+    bitonic_smem(s_key, S);
+    for (int j = tid; j < S; j += 256) spl[spl_off[s] + j] = s_key[j];
+}
+
+// ---- insert pass --------------------------------------------------------------------------
 template <int KEY_SRC>
 __global__ void __launch_bounds__(VOX_THREADS)
 vox_insert_kernel(const float *__restrict__ xyz, const unsigned long long *__restrict__ keys_in,
                   const int64_t *__restrict__ seg_off, int n_seg, const int64_t *__restrict__ total_eff,
                   const double *__restrict__ rt, const int *__restrict__ grid_min, Slot *__restrict__ tbl,
-                  const int64_t *__restrict__ tbl_off, unsigned int *__restrict__ pslot,
-                  unsigned int *__restrict__ uniq, int *__restrict__ m, int *status) {
+                  const int64_t *__restrict__ tbl_off, const int64_t *__restrict__ spl_off,
+                  const unsigned long long *__restrict__ spl, int *__restrict__ hist,
+                  unsigned int *__restrict__ pslot, unsigned int *__restrict__ uniq,
+                  unsigned long long *__restrict__ ukey, unsigned int *__restrict__ ubkt,
+                  unsigned int *__restrict__ upos, int *__restrict__ m, int *status) {
     const int64_t total = *total_eff;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < total;
@@ -205,25 +306,8 @@ vox_insert_kernel(const float *__restrict__ xyz, const unsigned long long *__res
     const int lane = lane_id();
     const int s = seg_of(seg_off, n_seg, i);
     const int64_t base = seg_off[s];
-    unsigned long long key;
-    if (KEY_SRC == 0) {
-        double f[3];
-        grid_of(xyz + i * 3, rt + 12 * s, f);
-        unsigned long long w[3];
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            if (!(f[j] > -(double)GRID_LIMIT && f[j] < (double)GRID_LIMIT)) f[j] = 0.0;
-            // floor(grid - min) of two integers is their exact difference (voxelizer.py:115-119)
-            w[j] = (unsigned long long)(long long)((int)f[j] - grid_min[3 * s + j]);
-        }
-        key = fnv3(w[0], w[1], w[2]);
-    } else {
-        key = keys_in[i];
-    }
-    if (key == KEY_EMPTY) {              // 2^-64 event: the sentinel value cannot be stored
-        if (status) atomicOr(status, XM3D_FLAG_KEY_SENTINEL);
-        key = KEY_EMPTY - 1;
-    }
+    unsigned long long key = (KEY_SRC == 0) ? point_key(xyz, i, s, rt, grid_min) : keys_in[i];
+    key = clean_key(key, status);
     // warp-cooperative de-duplication: one prober per distinct (segment, key) in the warp
     const unsigned peers = __match_any_sync(act, key) & __match_any_sync(act, s);
     const int leader = __ffs(peers) - 1;
@@ -246,178 +330,146 @@ vox_insert_kernel(const float *__restrict__ xyz, const unsigned long long *__res
     }
     slot = __shfl_sync(act, slot, leader);
     pslot[i] = slot;
-    // append new unique slots: one atomicAdd per warp when the warp sits in one segment
+    // new unique keys: bucket ticket + append to the unique list (one atomicAdd per warp when the
+    // warp sits inside one segment)
+    unsigned int bkt = 0, pos = 0;
+    if (is_new) {
+        const int64_t so = spl_off[s];
+        bkt = (unsigned int)bucket_of(spl + so, (int)(spl_off[s + 1] - so), key);
+        pos = (unsigned int)atomicAdd(&hist[so + bkt], 1);
+    }
     const unsigned newm = __ballot_sync(act, is_new);
     const unsigned sameseg = __match_any_sync(act, s);
+    int64_t up = -1;
     if (sameseg == act) {
         if (newm) {
             int start = 0;
             const int first_lane = __ffs(act) - 1;
             if (lane == first_lane) start = atomicAdd(&m[s], __popc(newm));
             start = __shfl_sync(act, start, first_lane);
-            if (is_new) uniq[base + start + __popc(newm & ((1u << lane) - 1u))] = slot;
+            if (is_new) up = base + start + __popc(newm & ((1u << lane) - 1u));
         }
     } else if (is_new) {
-        uniq[base + atomicAdd(&m[s], 1)] = slot;
+        up = base + atomicAdd(&m[s], 1);
+    }
+    if (up >= 0) {
+        uniq[up] = slot;
+        ukey[up] = key;
+        ubkt[up] = bkt;
+        upos[up] = pos;
     }
 }
 
-// ---- sort pass ----------------------------------------------------------------------------
-template <typename K, typename V, bool HAS_V>
-__device__ __forceinline__ void bitonic_smem(K *k, V *v, int n /*pow2*/) {
-    for (int size = 2; size <= n; size <<= 1)
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int t = threadIdx.x; t < (n >> 1); t += blockDim.x) {
-                const int lo = 2 * t - (t & (stride - 1));     // insert a 0 at bit log2(stride)
-                const int hi = lo + stride;
-                const bool up = (lo & size) == 0;
-                const K a = k[lo], b = k[hi];
-                if ((a > b) == up) {
-                    k[lo] = b; k[hi] = a;
-                    if (HAS_V) { const V x = v[lo]; v[lo] = v[hi]; v[hi] = x; }
-                }
-            }
-            __syncthreads();
-        }
-}
-
-struct SortOut {
-    int *first;            // [cap] first-occurrence index, unique order
-    int *voxel_xyz;        // [cap,3] or null
-    const float *xyz;      // for voxel_xyz
-    const double *rt;
-    const int *grid_min;
-};
-
-__device__ __forceinline__ void emit_rank(Slot *tb, unsigned int slot, int rank, int64_t base, int64_t ubase,
-                                          int s, const SortOut &O) {
-    tb[slot].rank = (unsigned int)rank;
-    const unsigned int f = tb[slot].first;
-    O.first[ubase + rank] = (int)f;
-    if (O.voxel_xyz) {
-        double g[3];
-        grid_of(O.xyz + (base + f) * 3, O.rt + 12 * s, g);
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            if (!(g[j] > -(double)GRID_LIMIT && g[j] < (double)GRID_LIMIT)) g[j] = 0.0;
-            O.voxel_xyz[(ubase + rank) * 3 + j] = (int)g[j] - O.grid_min[3 * s + j];
-        }
-    }
-}
-
-__global__ void __launch_bounds__(SORT_THREADS, 1)
-vox_sort_kernel(const int64_t *__restrict__ seg_off, int n_seg, Slot *__restrict__ tbl,
-                const int64_t *__restrict__ tbl_off, const unsigned int *__restrict__ uniq,
-                const int *__restrict__ m, int64_t *__restrict__ uniq_off,
-                unsigned long long *__restrict__ bk_key, unsigned int *__restrict__ bk_slot, SortOut O) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    unsigned long long *s_key = reinterpret_cast<unsigned long long *>(smem);             // 4096 x 8
-    unsigned int *s_aux = reinterpret_cast<unsigned int *>(smem + SORT_SAMPLES * 8);      // 4096 x 4
-    __shared__ int64_t s_red[32];
-    __shared__ int s_wsum[32];
+// ---- bucket scan: one CTA per segment -----------------------------------------------------
+__global__ void __launch_bounds__(256)
+vox_bscan_kernel(const int64_t *__restrict__ spl_off, int n_seg, int *__restrict__ hist, const int *__restrict__ m,
+                 int64_t *__restrict__ uniq_off) {
+    __shared__ int s_w[8];
+    __shared__ int64_t s_red[8];
+    __shared__ int s_carry;
     const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int M = m[s];
-    const int64_t base = seg_off[s];
-    Slot *tb = tbl + tbl_off[s];
-    const unsigned int *U = uniq + base;
-
     // exclusive prefix of the unique counts of the segments before this one
     int64_t part = 0;
-    for (int t = tid; t < s; t += SORT_THREADS) part += m[t];
+    for (int t = tid; t < s; t += 256) part += m[t];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
     if (lane == 0) s_red[warp] = part;
+    if (tid == 0) s_carry = 0;
     __syncthreads();
-    int64_t ubase = 0;
-    for (int w = 0; w < 32; ++w) ubase += s_red[w];
     if (tid == 0) {
-        uniq_off[s] = ubase;
-        if (s == n_seg - 1) uniq_off[n_seg] = ubase + M;
+        int64_t ub = 0;
+        for (int w = 0; w < 8; ++w) ub += s_red[w];
+        uniq_off[s] = ub;
+        if (s == n_seg - 1) uniq_off[n_seg] = ub + m[s];
     }
-    if (M == 0) return;
-
-    if (M <= SORT_SMALL) {
-        int np = 2;
-        while (np < M) np <<= 1;
-        for (int t = tid; t < np; t += SORT_THREADS) {
-            const unsigned int sl = (t < M) ? U[t] : 0u;
-            s_key[t] = (t < M) ? tb[sl].key : KEY_EMPTY;
-            s_aux[t] = sl;
-        }
-        __syncthreads();
-        bitonic_smem<unsigned long long, unsigned int, true>(s_key, s_aux, np);
-        for (int t = tid; t < M; t += SORT_THREADS) emit_rank(tb, s_aux[t], t, base, ubase, s, O);
-        return;
-    }
-
-    // ---- sample sort
-    const int S = (M < 65536) ? 2048 : 4096;             // buckets
-    const int step = SORT_SAMPLES / S;
-    for (int t = tid; t < SORT_SAMPLES; t += SORT_THREADS)
-        s_key[t] = tb[U[(int)(((int64_t)t * M) / SORT_SAMPLES)]].key;
-    __syncthreads();
-    bitonic_smem<unsigned long long, unsigned int, false>(s_key, nullptr, SORT_SAMPLES);
-    // splitter j (0..S-2) = sorted sample (j+1)*step - 1; bucket = #splitters < key
-    auto bucket_of = [&](unsigned long long key) {
-        int lo = 0, hi = S - 1;                            // count of splitters < key in [0, S-1]
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (s_key[(mid + 1) * step - 1] < key) lo = mid + 1; else hi = mid;
-        }
-        return lo;
-    };
-    int *hist = reinterpret_cast<int *>(s_aux);
-    for (int t = tid; t < S; t += SORT_THREADS) hist[t] = 0;
-    __syncthreads();
-    for (int t = tid; t < M; t += SORT_THREADS) atomicAdd(&hist[bucket_of(tb[U[t]].key)], 1);
-    __syncthreads();
-    // exclusive scan of hist[S] in place (S / 1024 entries per thread)
-    {
-        const int per = S / SORT_THREADS;
-        int loc[4], sum = 0;
-        for (int j = 0; j < per; ++j) { loc[j] = hist[tid * per + j]; sum += loc[j]; }
-        int incl = sum;
+    int *h = hist + spl_off[s];
+    const int S = (int)(spl_off[s + 1] - spl_off[s]);
+    for (int base = 0; base < S; base += 256) {
+        const int val = (base + tid < S) ? h[base + tid] : 0;
+        int incl = val;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int t = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += t;
         }
-        if (lane == 31) s_wsum[warp] = incl;
+        if (lane == 31) s_w[warp] = incl;
         __syncthreads();
         if (warp == 0) {
-            const int w = s_wsum[lane];
+            const int w = lane < 8 ? s_w[lane] : 0;
             int wi = w;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
+            for (int o = 1; o < 8; o <<= 1) {
                 const int t = __shfl_up_sync(0xffffffffu, wi, o);
                 if (lane >= o) wi += t;
             }
-            s_wsum[lane] = wi - w;
+            if (lane < 8) s_w[lane] = wi - w;
         }
         __syncthreads();
-        int run = s_wsum[warp] + incl - sum;
-        for (int j = 0; j < per; ++j) { hist[tid * per + j] = run; run += loc[j]; }
+        const int excl = s_carry + s_w[warp] + incl - val;
+        if (base + tid < S) h[base + tid] = excl;
+        __syncthreads();
+        if (tid == 255) s_carry = excl + val;
+        __syncthreads();
     }
-    __syncthreads();
-    // scatter into buckets; afterwards hist[b] = end of bucket b
-    unsigned long long *bk = bk_key + base;
-    unsigned int *bs = bk_slot + base;
-    for (int t = tid; t < M; t += SORT_THREADS) {
-        const unsigned int sl = U[t];
-        const unsigned long long key = tb[sl].key;
-        const int d = atomicAdd(&hist[bucket_of(key)], 1);
-        bk[d] = key;
-        bs[d] = sl;
-    }
-    __syncthreads();
-    // rank inside each bucket: one warp per bucket, each lane counts the smaller keys
-    for (int b = warp; b < S; b += SORT_THREADS / 32) {
-        const int lo = (b == 0) ? 0 : hist[b - 1], hi = hist[b];
-        for (int e = lo + lane; e < hi; e += 32) {
-            const unsigned long long key = bk[e];
-            int smaller = 0;
-            for (int q = lo; q < hi; ++q) smaller += (bk[q] < key) ? 1 : 0;
-            emit_rank(tb, bs[e], lo + smaller, base, ubase, s, O);
+}
+
+// ---- scatter unique keys into bucket order ------------------------------------------------
+__global__ void __launch_bounds__(VOX_THREADS)
+vox_scatter_kernel(const int64_t *__restrict__ seg_off, int n_seg, const int64_t *__restrict__ total_eff,
+                   const int *__restrict__ m, const int64_t *__restrict__ spl_off, const int *__restrict__ hist,
+                   const unsigned int *__restrict__ uniq, const unsigned long long *__restrict__ ukey,
+                   const unsigned int *__restrict__ ubkt, const unsigned int *__restrict__ upos,
+                   unsigned long long *__restrict__ bk_key, unsigned int *__restrict__ bk_slot,
+                   unsigned int *__restrict__ bk_bkt) {
+    const int64_t total = *total_eff;
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= total) return;
+    const int s = seg_of(seg_off, n_seg, p);
+    const int64_t base = seg_off[s];
+    if (p - base >= m[s]) return;                       // the unique list of a segment has m[s] entries
+    const unsigned int b = ubkt[p];
+    const int64_t d = base + hist[spl_off[s] + b] + upos[p];
+    bk_key[d] = ukey[p];
+    bk_slot[d] = uniq[p];
+    bk_bkt[d] = b;
+}
+
+// ---- rank + emit: one thread per unique key, in bucket order --------------------------------
+__global__ void __launch_bounds__(VOX_THREADS)
+vox_rank_kernel(const int64_t *__restrict__ seg_off, int n_seg, const int64_t *__restrict__ total_eff,
+                const int *__restrict__ m, const int64_t *__restrict__ spl_off, const int *__restrict__ hist,
+                const unsigned long long *__restrict__ bk_key, const unsigned int *__restrict__ bk_slot,
+                const unsigned int *__restrict__ bk_bkt, Slot *__restrict__ tbl,
+                const int64_t *__restrict__ tbl_off, const int64_t *__restrict__ uniq_off,
+                const float *__restrict__ xyz, const double *__restrict__ rt, const int *__restrict__ grid_min,
+                int *__restrict__ first, int *__restrict__ voxel_xyz) {
+    const int64_t total = *total_eff;
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= total) return;
+    const int s = seg_of(seg_off, n_seg, p);
+    const int64_t base = seg_off[s];
+    const int M = m[s];
+    if (p - base >= M) return;
+    const unsigned long long key = bk_key[p];
+    const int b = (int)bk_bkt[p];
+    const int S = (int)(spl_off[s + 1] - spl_off[s]);
+    const int *h = hist + spl_off[s];
+    const int lo = h[b], hi = (b + 1 < S) ? h[b + 1] : M;
+    int smaller = 0;
+    for (int q = lo; q < hi; ++q) smaller += (bk_key[base + q] < key) ? 1 : 0;
+    const int rank = lo + smaller;
+    Slot *sl = tbl + tbl_off[s] + bk_slot[p];
+    const unsigned int f = sl->first;
+    sl->rank = (unsigned int)rank;                     // read back by the inverse pass
+    const int64_t o = uniq_off[s] + rank;
+    first[o] = (int)f;
+    if (voxel_xyz) {
+        double g[3];
+        grid_of(xyz + (base + f) * 3, rt + 12 * s, g);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            if (!(g[j] > -(double)GRID_LIMIT && g[j] < (double)GRID_LIMIT)) g[j] = 0.0;
+            voxel_xyz[o * 3 + j] = (int)g[j] - grid_min[3 * s + j];
         }
     }
 }
@@ -453,7 +505,6 @@ fnv_f64_kernel(const double *__restrict__ coords, int64_t n, int dim, unsigned l
 // column min / max of a float64 [n, dim] matrix (dim <= 8) into ws[0..dim) / ws[8..8+dim)
 __global__ void __launch_bounds__(256)
 colminmax_f64_kernel(const double *__restrict__ coords, int64_t n, int dim, double *__restrict__ ws) {
-    // ordered-int trick is unnecessary: values are compared as doubles through atomicCAS loops
     __shared__ double s_min[8][8], s_max[8][8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double mn[8], mx[8];
@@ -475,7 +526,7 @@ colminmax_f64_kernel(const double *__restrict__ coords, int64_t n, int dim, doub
         const int j = threadIdx.x;
         double a = INFINITY, b = -INFINITY;
         for (int w = 0; w < 8; ++w) { a = fmin(a, s_min[w][j]); b = fmax(b, s_max[w][j]); }
-        // atomic min/max on doubles via CAS
+        // atomic min / max on doubles through compare-and-swap
         unsigned long long *pa = reinterpret_cast<unsigned long long *>(ws + j);
         unsigned long long old = *pa, assumed;
         do { assumed = old; if (__longlong_as_double(assumed) <= a) break;
@@ -509,22 +560,31 @@ ravel_f64_kernel(const double *__restrict__ coords, int64_t n, int dim, const do
 
 struct VoxWs {
     Slot *tbl;
-    int64_t *tbl_off, *total_eff;
-    unsigned int *pslot, *uniq, *bk_slot;
-    unsigned long long *bk_key;
-    int *grid_min;
+    int64_t *tbl_off, *spl_off, *total_eff;
+    unsigned int *pslot, *uniq, *ubkt, *upos, *bk_slot, *bk_bkt;
+    unsigned long long *ukey, *bk_key, *spl;
+    int *hist, *grid_min;
 };
 
 static VoxWs carve_vox(void *ws, int n_seg, int64_t cap, size_t *bytes) {
     Carver c(ws);
     VoxWs w;
+    // sum of bucket_count(n_s) <= sum max(32, n_s / 8) <= cap / 8 + 32 n_seg
+    const size_t nspl = (size_t)(cap / 8 + (int64_t)(SPL_MIN + 8) * n_seg + SPL_MAX);
     w.tbl = c.take<Slot>((size_t)(table_size(cap) + 32 * (int64_t)n_seg));
     w.tbl_off = c.take<int64_t>(n_seg + 1);
+    w.spl_off = c.take<int64_t>(n_seg + 1);
     w.total_eff = c.take<int64_t>(1);
     w.pslot = c.take<unsigned int>(cap);
     w.uniq = c.take<unsigned int>(cap);
+    w.ubkt = c.take<unsigned int>(cap);
+    w.upos = c.take<unsigned int>(cap);
     w.bk_slot = c.take<unsigned int>(cap);
+    w.bk_bkt = c.take<unsigned int>(cap);
+    w.ukey = c.take<unsigned long long>(cap);
     w.bk_key = c.take<unsigned long long>(cap);
+    w.spl = c.take<unsigned long long>(nspl);
+    w.hist = c.take<int>(nspl);
     w.grid_min = c.take<int>(3 * (size_t)n_seg);
     *bytes = c.off + 256;
     return w;
@@ -540,35 +600,55 @@ static int run_unique(const float *xyz, const unsigned long long *keys, const in
         set_error("%s: workspace too small (%zu < %zu)", who, ws_bytes, need);
         return XM3D_ERR_WORKSPACE;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(vox_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SAMPLES * 12);
-        attr_set = true;
-    }
     int *gmin = grid_min_out ? grid_min_out : w.grid_min;
     const unsigned blocks = (unsigned)((cap + VOX_THREADS - 1) / VOX_THREADS);
-    vox_plan_kernel<<<1, 1024, 0, stream>>>(seg_off, n_seg, cap, w.tbl_off, w.total_eff, m, xyz ? gmin : nullptr,
-                                            status); count_launches(1);
-    vox_clear_kernel<<<(unsigned)(sm_count() * 8), 256, 0, stream>>>(w.tbl, w.tbl_off, n_seg); count_launches(1);
+    vox_plan_kernel<<<1, 1024, 0, stream>>>(seg_off, n_seg, cap, w.tbl_off, w.spl_off, w.total_eff, m,
+                                            xyz ? gmin : nullptr, status);
+    count_launches(1);
+    vox_clear_kernel<<<(unsigned)(sm_count() * 8), 256, 0, stream>>>(w.tbl, w.tbl_off, n_seg);
+    count_launches(1);
     if (counts) cudaMemsetAsync(counts, 0, sizeof(int) * cap, stream);
-    if (blocks) {
-        if (xyz) {
-            vox_min_kernel<<<blocks, VOX_THREADS, 0, stream>>>(xyz, seg_off, n_seg, w.total_eff, rt, gmin, status); count_launches(1);
+    if (xyz) {
+        if (blocks) {
+            vox_min_kernel<<<blocks, VOX_THREADS, 0, stream>>>(xyz, seg_off, n_seg, w.total_eff, rt, gmin, status);
+            count_launches(1);
+        }
+        vox_sample_kernel<0><<<n_seg, 256, 0, stream>>>(xyz, nullptr, seg_off, w.total_eff, rt, gmin, w.spl_off, w.spl,
+                                                        w.hist);
+        count_launches(1);
+        if (blocks) {
             vox_insert_kernel<0><<<blocks, VOX_THREADS, 0, stream>>>(xyz, nullptr, seg_off, n_seg, w.total_eff, rt, gmin,
-                                                                     w.tbl, w.tbl_off, w.pslot, w.uniq, m, status); count_launches(1);
-        } else {
+                                                                     w.tbl, w.tbl_off, w.spl_off, w.spl, w.hist, w.pslot,
+                                                                     w.uniq, w.ukey, w.ubkt, w.upos, m, status);
+            count_launches(1);
+        }
+    } else {
+        vox_sample_kernel<1><<<n_seg, 256, 0, stream>>>(nullptr, keys, seg_off, w.total_eff, nullptr, nullptr, w.spl_off,
+                                                        w.spl, w.hist);
+        count_launches(1);
+        if (blocks) {
             vox_insert_kernel<1><<<blocks, VOX_THREADS, 0, stream>>>(nullptr, keys, seg_off, n_seg, w.total_eff, nullptr,
-                                                                     nullptr, w.tbl, w.tbl_off, w.pslot, w.uniq, m,
-                                                                     status); count_launches(1);
+                                                                     nullptr, w.tbl, w.tbl_off, w.spl_off, w.spl, w.hist,
+                                                                     w.pslot, w.uniq, w.ukey, w.ubkt, w.upos, m, status);
+            count_launches(1);
         }
     }
-    SortOut O;
-    O.first = first; O.voxel_xyz = xyz ? voxel_xyz : nullptr; O.xyz = xyz; O.rt = rt; O.grid_min = gmin;
-    vox_sort_kernel<<<n_seg, SORT_THREADS, SORT_SAMPLES * 12, stream>>>(seg_off, n_seg, w.tbl, w.tbl_off, w.uniq, m,
-                                                                        uniq_off, w.bk_key, w.bk_slot, O); count_launches(1);
-    if (blocks && inverse) {
-        vox_inverse_kernel<<<blocks, VOX_THREADS, 0, stream>>>(seg_off, n_seg, w.total_eff, w.tbl, w.tbl_off, w.pslot,
-                                                               uniq_off, collate, inverse, counts); count_launches(1); }
+    vox_bscan_kernel<<<n_seg, 256, 0, stream>>>(w.spl_off, n_seg, w.hist, m, uniq_off);
+    count_launches(1);
+    if (blocks) {
+        vox_scatter_kernel<<<blocks, VOX_THREADS, 0, stream>>>(seg_off, n_seg, w.total_eff, m, w.spl_off, w.hist, w.uniq,
+                                                               w.ukey, w.ubkt, w.upos, w.bk_key, w.bk_slot, w.bk_bkt);
+        count_launches(1);
+        vox_rank_kernel<<<blocks, VOX_THREADS, 0, stream>>>(seg_off, n_seg, w.total_eff, m, w.spl_off, w.hist, w.bk_key,
+                                                            w.bk_slot, w.bk_bkt, w.tbl, w.tbl_off, uniq_off, xyz, rt,
+                                                            gmin, first, xyz ? voxel_xyz : nullptr);
+        count_launches(1);
+        if (inverse) {
+            vox_inverse_kernel<<<blocks, VOX_THREADS, 0, stream>>>(seg_off, n_seg, w.total_eff, w.tbl, w.tbl_off, w.pslot,
+                                                                   uniq_off, collate, inverse, counts);
+            count_launches(1);
+        }
+    }
     return check_launch(who);
 }
 
@@ -613,7 +693,8 @@ extern "C" int xm3d_fnv_hash_f64(const double *coords, int64_t n, int32_t dim, u
     if (n == 0) return XM3D_OK;
     XM3D_REQUIRE(coords && keys, "null pointer");
     fnv_f64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        coords, n, dim, reinterpret_cast<unsigned long long *>(keys)); count_launches(1);
+        coords, n, dim, reinterpret_cast<unsigned long long *>(keys));
+    count_launches(1);
     return check_launch("xm3d_fnv_hash_f64");
 }
 
@@ -626,11 +707,14 @@ extern "C" int xm3d_ravel_hash_f64(const double *coords, int64_t n, int32_t dim,
     if (n == 0) return XM3D_OK;
     XM3D_REQUIRE(coords && keys && ws && ws_bytes >= 128, "null pointer / workspace");
     double *mm = static_cast<double *>(ws);
-    init_minmax_kernel<<<1, 32, 0, stream>>>(mm); count_launches(1);
+    init_minmax_kernel<<<1, 32, 0, stream>>>(mm);
+    count_launches(1);
     unsigned blocks = (unsigned)((n + 255) / 256);
     if (blocks > (unsigned)sm_count() * 8) blocks = sm_count() * 8;
-    colminmax_f64_kernel<<<blocks, 256, 0, stream>>>(coords, n, dim, mm); count_launches(1);
+    colminmax_f64_kernel<<<blocks, 256, 0, stream>>>(coords, n, dim, mm);
+    count_launches(1);
     ravel_f64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(coords, n, dim, mm,
-                                                                       reinterpret_cast<unsigned long long *>(keys)); count_launches(1);
+                                                                       reinterpret_cast<unsigned long long *>(keys));
+    count_launches(1);
     return check_launch("xm3d_ravel_hash_f64");
 }

@@ -284,7 +284,7 @@ def pool(feat: torch.Tensor, seg_off: torch.Tensor, k: int, member: Optional[tor
     s = torch.empty((n_seg, k, c), dtype=torch.float32, device=dev)
     cnt = torch.empty((n_seg, k), dtype=torch.int32, device=dev)
     mean = torch.empty((n_seg, k, c), dtype=torch.float32, device=dev) if want_mean else None
-    need = L.lib().xm3d_pool_ws_bytes(n_seg, k, c, cap_pairs)
+    need = L.lib().xm3d_pool_ws_bytes(n_seg, k, c, cap, cap_pairs)
     if ws is None or ws.numel() < need:
         ws = _ws(need, dev)
     L.check(L.lib().xm3d_pool_batch(_ptr(feat), c, _ptr(row_index), _ptr(member), _ptr(label), n_seg, int(k),

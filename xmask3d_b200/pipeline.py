@@ -88,7 +88,7 @@ class CorrespondencePipeline:
 
     def _size_pool_ws(self):
         self.cap_pairs = int(self.cap_vis * self.pairs_per_point) + 1
-        self.ws_pool = ops._ws(L.lib().xm3d_pool_ws_bytes(self.n_views, self.k, self.c, self.cap_pairs), self.dev)
+        self.ws_pool = ops._ws(L.lib().xm3d_pool_ws_bytes(self.n_views, self.k, self.c, self.cap_vis, self.cap_pairs), self.dev)
 
     def upload(self, xyz_host: torch.Tensor, depth_host: torch.Tensor):
         """H2D of the loader-side inputs (pinned host tensors -> device), on the current stream."""
