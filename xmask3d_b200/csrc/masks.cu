@@ -86,6 +86,59 @@ pixel_bits_kernel(const T *__restrict__ masks, int thr_mode, int k, int hw, int 
     }
 }
 
+// bool / uint8 masks thresholded at >= 0.5 (the partition masks of mask_mapper): byte-SIMD path.
+// One thread owns 16 consecutive pixels (4 quads of 4 bytes).  For mask m the four bytes of a quad
+// become 0xFF / 0x00 with one vcmpne4, are AND-ed with bit (m & 7) replicated in every byte and
+// OR-ed into the quad's accumulator of byte group (m & 31) >> 3 — three integer instructions per
+// four pixels and mask; the per-pixel words are assembled once per 32 masks.
+__global__ void __launch_bounds__(256)
+pixel_bits_u8_kernel(const unsigned char *__restrict__ masks, int k, int hw, int words,
+                     uint32_t *__restrict__ pixbits) {
+    const int s = blockIdx.y;
+    const int p0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (p0 >= hw) return;                                   // hw % 16 == 0 on this path
+    const unsigned char *base = masks + (size_t)s * k * hw + p0;
+    uint32_t *out = pixbits + (size_t)s * words * hw + p0;
+    for (int wd = 0; wd < words; ++wd) {
+        uint32_t acc[4][4];                                 // [byte group][quad]
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[g][q] = 0u;
+        const int m_beg = wd * 32, m_cnt = min(32, k - m_beg);
+#pragma unroll
+        for (int mm = 0; mm < 32; mm += 4) {
+            if (mm < m_cnt) {
+                uint4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    v[u] = (mm + u < m_cnt) ? __ldg(reinterpret_cast<const uint4 *>(base + (size_t)(m_beg + mm + u) * hw))
+                                            : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t sel = 0x01010101u << ((mm + u) & 7);
+                    const int g = (mm + u) >> 3;
+                    acc[g][0] |= __vcmpne4(v[u].x, 0u) & sel;
+                    acc[g][1] |= __vcmpne4(v[u].y, 0u) & sel;
+                    acc[g][2] |= __vcmpne4(v[u].z, 0u) & sel;
+                    acc[g][3] |= __vcmpne4(v[u].w, 0u) & sel;
+                }
+            }
+        }
+        uint32_t *o = out + (size_t)wd * hw;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            // transpose 4 byte groups x 4 pixels: word of pixel j = byte j of every group
+            const uint32_t a0 = acc[0][q], a1 = acc[1][q], a2 = acc[2][q], a3 = acc[3][q];
+            const uint32_t t01l = __byte_perm(a0, a1, 0x5140), t01h = __byte_perm(a0, a1, 0x7362);
+            const uint32_t t23l = __byte_perm(a2, a3, 0x5140), t23h = __byte_perm(a2, a3, 0x7362);
+            const uint4 w = make_uint4(__byte_perm(t01l, t23l, 0x5410), __byte_perm(t01l, t23l, 0x7632),
+                                       __byte_perm(t01h, t23h, 0x5410), __byte_perm(t01h, t23h, 0x7632));
+            *reinterpret_cast<uint4 *>(o + 4 * q) = w;
+        }
+    }
+}
+
 // ---- gather, step 2: per-point words (+ optional per-mask counts) --------------------------
 __global__ void __launch_bounds__(256)
 point_bits_kernel(const uint32_t *__restrict__ pixbits, const int32_t *__restrict__ rowcol,
@@ -206,7 +259,10 @@ extern "C" int xm3d_gather_masks_batch(const void *masks, int32_t mask_kind, int
     const int pix = 16 / esz;
     const int vec_ok = (hw % pix == 0) && (reinterpret_cast<uintptr_t>(masks) % 16 == 0);
     dim3 grid(((hw + pix - 1) / pix + 255) / 256, n_seg);
-    if (mask_kind == XM3D_MASK_U8) {
+    if (mask_kind == XM3D_MASK_U8 && thr_mode == XM3D_THR_GE_HALF && vec_ok) {
+        pixel_bits_u8_kernel<<<grid, 256, 0, stream>>>(static_cast<const unsigned char *>(masks), k, hw, words, pixbits);
+        count_launches(1);
+    } else if (mask_kind == XM3D_MASK_U8) {
         pixel_bits_kernel<unsigned char><<<grid, 256, 0, stream>>>(static_cast<const unsigned char *>(masks), thr_mode,
                                                                     k, hw, words, vec_ok, pixbits); count_launches(1); }
     else {

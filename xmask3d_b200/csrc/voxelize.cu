@@ -152,6 +152,24 @@ __device__ __forceinline__ int64_t block_excl_scan_1024(int64_t val, int64_t *s_
     return excl;
 }
 
+// Segment of every thread of a block that walks consecutive elements: almost every block lies inside
+// one segment, so thread 0 resolves the block's first and last element and the others reuse it.
+struct BlockSeg { int s; bool uniform; };
+__device__ __forceinline__ BlockSeg block_segment(const int64_t *__restrict__ seg_off, int n_seg, int64_t total,
+                                                  int64_t i, bool valid, int *s_pair /*[2] shared*/) {
+    if (threadIdx.x == 0) {
+        const int64_t b0 = (int64_t)blockIdx.x * blockDim.x;
+        const int64_t last = (b0 + blockDim.x - 1 < total) ? b0 + blockDim.x - 1 : total - 1;
+        s_pair[0] = seg_of(seg_off, n_seg, b0);
+        s_pair[1] = seg_of(seg_off, n_seg, last);
+    }
+    __syncthreads();
+    BlockSeg r;
+    r.uniform = s_pair[0] == s_pair[1];
+    r.s = r.uniform ? s_pair[0] : (valid ? seg_of(seg_off, n_seg, i) : s_pair[0]);
+    return r;
+}
+
 // ---- plan ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024, 1)
 vox_plan_kernel(const int64_t *__restrict__ seg_off, int n_seg, int64_t cap, int64_t *__restrict__ tbl_off,
@@ -298,13 +316,15 @@ vox_insert_kernel(const float *__restrict__ xyz, const unsigned long long *__res
                   unsigned int *__restrict__ pslot, unsigned int *__restrict__ uniq,
                   unsigned long long *__restrict__ ukey, unsigned int *__restrict__ ubkt,
                   unsigned int *__restrict__ upos, int *__restrict__ m, int *status) {
+    __shared__ int s_pair[2];
     const int64_t total = *total_eff;
+    if ((int64_t)blockIdx.x * blockDim.x >= total) return;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < total;
+    const int s = block_segment(seg_off, n_seg, total, i, valid, s_pair).s;
     const unsigned act = __ballot_sync(0xffffffffu, valid);
     if (!valid) return;
     const int lane = lane_id();
-    const int s = seg_of(seg_off, n_seg, i);
     const int64_t base = seg_off[s];
     unsigned long long key = (KEY_SRC == 0) ? point_key(xyz, i, s, rt, grid_min) : keys_in[i];
     key = clean_key(key, status);
@@ -419,46 +439,69 @@ vox_scatter_kernel(const int64_t *__restrict__ seg_off, int n_seg, const int64_t
                    const int *__restrict__ m, const int64_t *__restrict__ spl_off, const int *__restrict__ hist,
                    const unsigned int *__restrict__ uniq, const unsigned long long *__restrict__ ukey,
                    const unsigned int *__restrict__ ubkt, const unsigned int *__restrict__ upos,
-                   unsigned long long *__restrict__ bk_key, unsigned int *__restrict__ bk_slot,
-                   unsigned int *__restrict__ bk_bkt) {
+                   unsigned long long *__restrict__ bk_key, unsigned long long *__restrict__ bk_sb) {
+    __shared__ int s_pair[2];
     const int64_t total = *total_eff;
+    if ((int64_t)blockIdx.x * blockDim.x >= total) return;
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= total) return;
-    const int s = seg_of(seg_off, n_seg, p);
+    const bool valid = p < total;
+    const int s = block_segment(seg_off, n_seg, total, p, valid, s_pair).s;
+    if (!valid) return;
     const int64_t base = seg_off[s];
     if (p - base >= m[s]) return;                       // the unique list of a segment has m[s] entries
     const unsigned int b = ubkt[p];
     const int64_t d = base + hist[spl_off[s] + b] + upos[p];
     bk_key[d] = ukey[p];
-    bk_slot[d] = uniq[p];
-    bk_bkt[d] = b;
+    bk_sb[d] = ((unsigned long long)b << 32) | uniq[p];      // (bucket, table slot)
 }
 
 // ---- rank + emit: one thread per unique key, in bucket order --------------------------------
+// A block's 256 keys and their buckets sit in a contiguous window of bk_key, staged once in shared
+// memory, so the "count the smaller keys of my bucket" loop makes no global memory requests.
+constexpr int RANK_PAD = 192;
+constexpr int RANK_WIN = VOX_THREADS + 2 * RANK_PAD;
+
 __global__ void __launch_bounds__(VOX_THREADS)
 vox_rank_kernel(const int64_t *__restrict__ seg_off, int n_seg, const int64_t *__restrict__ total_eff,
                 const int *__restrict__ m, const int64_t *__restrict__ spl_off, const int *__restrict__ hist,
-                const unsigned long long *__restrict__ bk_key, const unsigned int *__restrict__ bk_slot,
-                const unsigned int *__restrict__ bk_bkt, Slot *__restrict__ tbl,
-                const int64_t *__restrict__ tbl_off, const int64_t *__restrict__ uniq_off,
+                const unsigned long long *__restrict__ bk_key, const unsigned long long *__restrict__ bk_sb,
+                Slot *__restrict__ tbl, const int64_t *__restrict__ tbl_off, const int64_t *__restrict__ uniq_off,
                 const float *__restrict__ xyz, const double *__restrict__ rt, const int *__restrict__ grid_min,
                 int *__restrict__ first, int *__restrict__ voxel_xyz) {
+    __shared__ int s_pair[2];
+    __shared__ unsigned long long s_win[RANK_WIN];
     const int64_t total = *total_eff;
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= total) return;
-    const int s = seg_of(seg_off, n_seg, p);
+    const int64_t p0 = (int64_t)blockIdx.x * blockDim.x;
+    if (p0 >= total) return;
+    const int64_t p = p0 + threadIdx.x;
+    const bool valid = p < total;
+    const BlockSeg bs = block_segment(seg_off, n_seg, total, p, valid, s_pair);
+    const int s = bs.s;
     const int64_t base = seg_off[s];
     const int M = m[s];
-    if (p - base >= M) return;
+    // window of bucket-ordered keys around the block (only when the block lies in one segment)
+    int64_t wlo = 0, whi = 0;
+    if (bs.uniform) {
+        wlo = (p0 - RANK_PAD > base) ? p0 - RANK_PAD : base;
+        whi = (p0 + VOX_THREADS + RANK_PAD < base + M) ? p0 + VOX_THREADS + RANK_PAD : base + M;
+        for (int64_t j = wlo + threadIdx.x; j < whi; j += VOX_THREADS) s_win[j - wlo] = bk_key[j];
+    }
+    __syncthreads();
+    if (!valid || p - base >= M) return;
     const unsigned long long key = bk_key[p];
-    const int b = (int)bk_bkt[p];
+    const unsigned long long sb = bk_sb[p];
+    const int b = (int)(sb >> 32);
     const int S = (int)(spl_off[s + 1] - spl_off[s]);
     const int *h = hist + spl_off[s];
     const int lo = h[b], hi = (b + 1 < S) ? h[b + 1] : M;
     int smaller = 0;
-    for (int q = lo; q < hi; ++q) smaller += (bk_key[base + q] < key) ? 1 : 0;
+    for (int q = lo; q < hi; ++q) {
+        const int64_t g = base + q;
+        const unsigned long long kq = (g >= wlo && g < whi) ? s_win[g - wlo] : bk_key[g];
+        smaller += (kq < key) ? 1 : 0;
+    }
     const int rank = lo + smaller;
-    Slot *sl = tbl + tbl_off[s] + bk_slot[p];
+    Slot *sl = tbl + tbl_off[s] + (unsigned int)sb;
     const unsigned int f = sl->first;
     sl->rank = (unsigned int)rank;                     // read back by the inverse pass
     const int64_t o = uniq_off[s] + rank;
@@ -480,10 +523,13 @@ vox_inverse_kernel(const int64_t *__restrict__ seg_off, int n_seg, const int64_t
                    const Slot *__restrict__ tbl, const int64_t *__restrict__ tbl_off,
                    const unsigned int *__restrict__ pslot, const int64_t *__restrict__ uniq_off, int collate,
                    int *__restrict__ inverse, int *__restrict__ counts) {
+    __shared__ int s_pair[2];
     const int64_t total = *total_eff;
+    if ((int64_t)blockIdx.x * blockDim.x >= total) return;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int s = seg_of(seg_off, n_seg, i);
+    const bool valid = i < total;
+    const int s = block_segment(seg_off, n_seg, total, i, valid, s_pair).s;
+    if (!valid) return;
     const int rank = (int)tbl[tbl_off[s] + pslot[i]].rank;
     inverse[i] = rank + (collate ? (int)uniq_off[s] : 0);
     if (counts) atomicAdd(&counts[uniq_off[s] + rank], 1);
@@ -561,8 +607,8 @@ ravel_f64_kernel(const double *__restrict__ coords, int64_t n, int dim, const do
 struct VoxWs {
     Slot *tbl;
     int64_t *tbl_off, *spl_off, *total_eff;
-    unsigned int *pslot, *uniq, *ubkt, *upos, *bk_slot, *bk_bkt;
-    unsigned long long *ukey, *bk_key, *spl;
+    unsigned int *pslot, *uniq, *ubkt, *upos;
+    unsigned long long *ukey, *bk_key, *bk_sb, *spl;
     int *hist, *grid_min;
 };
 
@@ -579,10 +625,9 @@ static VoxWs carve_vox(void *ws, int n_seg, int64_t cap, size_t *bytes) {
     w.uniq = c.take<unsigned int>(cap);
     w.ubkt = c.take<unsigned int>(cap);
     w.upos = c.take<unsigned int>(cap);
-    w.bk_slot = c.take<unsigned int>(cap);
-    w.bk_bkt = c.take<unsigned int>(cap);
     w.ukey = c.take<unsigned long long>(cap);
     w.bk_key = c.take<unsigned long long>(cap);
+    w.bk_sb = c.take<unsigned long long>(cap);
     w.spl = c.take<unsigned long long>(nspl);
     w.hist = c.take<int>(nspl);
     w.grid_min = c.take<int>(3 * (size_t)n_seg);
@@ -637,11 +682,11 @@ static int run_unique(const float *xyz, const unsigned long long *keys, const in
     count_launches(1);
     if (blocks) {
         vox_scatter_kernel<<<blocks, VOX_THREADS, 0, stream>>>(seg_off, n_seg, w.total_eff, m, w.spl_off, w.hist, w.uniq,
-                                                               w.ukey, w.ubkt, w.upos, w.bk_key, w.bk_slot, w.bk_bkt);
+                                                               w.ukey, w.ubkt, w.upos, w.bk_key, w.bk_sb);
         count_launches(1);
         vox_rank_kernel<<<blocks, VOX_THREADS, 0, stream>>>(seg_off, n_seg, w.total_eff, m, w.spl_off, w.hist, w.bk_key,
-                                                            w.bk_slot, w.bk_bkt, w.tbl, w.tbl_off, uniq_off, xyz, rt,
-                                                            gmin, first, xyz ? voxel_xyz : nullptr);
+                                                            w.bk_sb, w.tbl, w.tbl_off, uniq_off, xyz, rt, gmin, first,
+                                                            xyz ? voxel_xyz : nullptr);
         count_launches(1);
         if (inverse) {
             vox_inverse_kernel<<<blocks, VOX_THREADS, 0, stream>>>(seg_off, n_seg, w.total_eff, w.tbl, w.tbl_off, w.pslot,
