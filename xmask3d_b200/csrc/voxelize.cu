@@ -12,15 +12,15 @@
 //   sample    one CTA per segment: S sample keys, bitonic-sorted in shared memory -> splitters
 //   insert    key = FNV-1(grid - min).  Warp-cooperative open addressing: lanes holding the same
 //             key elect the lowest lane (= lowest point index) with match.any; only that lane
-//             probes the segment's table (linear probing, 16-byte slots {key, first, rank}).  The
+//             probes the segment's table (linear probing, 16-byte slots {key, -, rank}).  The
 //             winner of an empty slot appends (slot, key) to the segment's unique list (one
 //             warp-aggregated atomicAdd), finds the key's splitter bucket and takes a ticket in it
 //   bscan     one CTA per segment: exclusive scan of the bucket counts; prefix of unique counts
 //   scatter   unique keys -> bucket order
-//   rank      one thread per unique key: rank = bucket start + #smaller keys inside its bucket
-//             (~10 keys, L1-resident); writes the rank into the table slot and emits `first` and the
-//             voxel coordinates in unique order
-//   inverse   inverse[i] = rank stored in the slot point i resolved to
+//   rank      one thread per unique key: rank = bucket start + #smaller keys inside its bucket (~10
+//             keys, staged in shared memory); the rank is written into the key's table slot
+//   inverse   inverse[i] = rank stored in the slot point i resolved to; first[rank] = atomicMin(i)
+//   coords    voxel coordinates of every unique key from its first occurrence, in unique order
 //
 // Everything that decides an integer is exact: the transform is the fp64 FMA chain numpy's dgemm
 // performs, floor() is exact, keys are 64-bit so FNV collisions merge voxels exactly as the
@@ -40,7 +40,7 @@ constexpr int GRID_LIMIT = 1 << 30;
 
 struct __align__(16) Slot {
     unsigned long long key;
-    unsigned int first;   // lowest point index (within the segment) holding this key
+    unsigned int pad;
     unsigned int rank;    // rank of the key among the segment's unique keys
 };
 
@@ -204,12 +204,15 @@ vox_plan_kernel(const int64_t *__restrict__ seg_off, int n_seg, int64_t cap, int
 }
 
 __global__ void __launch_bounds__(256)
-vox_clear_kernel(Slot *__restrict__ tbl, const int64_t *__restrict__ tbl_off, int n_seg) {
+vox_clear_kernel(Slot *__restrict__ tbl, const int64_t *__restrict__ tbl_off, int n_seg,
+                 const int64_t *__restrict__ total_eff, int *__restrict__ first) {
     const int64_t used = tbl_off[n_seg];
     const uint4 e = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
     uint4 *t = reinterpret_cast<uint4 *>(tbl);
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < used; i += (int64_t)gridDim.x * blockDim.x)
-        t[i] = e;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < used; i += stride) t[i] = e;
+    const int64_t total = *total_eff;            // first[] receives atomicMin in the inverse pass
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) first[i] = 0x7fffffff;
 }
 
 // ---- min pass -----------------------------------------------------------------------------
@@ -346,7 +349,6 @@ vox_insert_kernel(const float *__restrict__ xyz, const unsigned long long *__res
             if (cur == key) break;
             slot = (slot + 1 == size) ? 0u : slot + 1;
         }
-        atomicMin(&tb[slot].first, (unsigned int)(i - base));     // leader = lowest index of its peers
     }
     slot = __shfl_sync(act, slot, leader);
     pslot[i] = slot;
@@ -465,9 +467,7 @@ __global__ void __launch_bounds__(VOX_THREADS)
 vox_rank_kernel(const int64_t *__restrict__ seg_off, int n_seg, const int64_t *__restrict__ total_eff,
                 const int *__restrict__ m, const int64_t *__restrict__ spl_off, const int *__restrict__ hist,
                 const unsigned long long *__restrict__ bk_key, const unsigned long long *__restrict__ bk_sb,
-                Slot *__restrict__ tbl, const int64_t *__restrict__ tbl_off, const int64_t *__restrict__ uniq_off,
-                const float *__restrict__ xyz, const double *__restrict__ rt, const int *__restrict__ grid_min,
-                int *__restrict__ first, int *__restrict__ voxel_xyz) {
+                Slot *__restrict__ tbl, const int64_t *__restrict__ tbl_off) {
     __shared__ int s_pair[2];
     __shared__ unsigned long long s_win[RANK_WIN];
     const int64_t total = *total_eff;
@@ -500,29 +500,18 @@ vox_rank_kernel(const int64_t *__restrict__ seg_off, int n_seg, const int64_t *_
         const unsigned long long kq = (g >= wlo && g < whi) ? s_win[g - wlo] : bk_key[g];
         smaller += (kq < key) ? 1 : 0;
     }
-    const int rank = lo + smaller;
-    Slot *sl = tbl + tbl_off[s] + (unsigned int)sb;
-    const unsigned int f = sl->first;
-    sl->rank = (unsigned int)rank;                     // read back by the inverse pass
-    const int64_t o = uniq_off[s] + rank;
-    first[o] = (int)f;
-    if (voxel_xyz) {
-        double g[3];
-        grid_of(xyz + (base + f) * 3, rt + 12 * s, g);
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            if (!(g[j] > -(double)GRID_LIMIT && g[j] < (double)GRID_LIMIT)) g[j] = 0.0;
-            voxel_xyz[o * 3 + j] = (int)g[j] - grid_min[3 * s + j];
-        }
-    }
+    // read back by the inverse pass, which also resolves the first-occurrence index
+    tbl[tbl_off[s] + (unsigned int)sb].rank = (unsigned int)(lo + smaller);
 }
 
 // ---- inverse pass -------------------------------------------------------------------------
+// inverse[i] = rank of point i's key; first[rank] = min over the points of that key of the index
+// inside the segment (np.unique's return_index), resolved here with one reduction per point.
 __global__ void __launch_bounds__(VOX_THREADS)
 vox_inverse_kernel(const int64_t *__restrict__ seg_off, int n_seg, const int64_t *__restrict__ total_eff,
                    const Slot *__restrict__ tbl, const int64_t *__restrict__ tbl_off,
                    const unsigned int *__restrict__ pslot, const int64_t *__restrict__ uniq_off, int collate,
-                   int *__restrict__ inverse, int *__restrict__ counts) {
+                   int *__restrict__ inverse, int *__restrict__ first, int *__restrict__ counts) {
     __shared__ int s_pair[2];
     const int64_t total = *total_eff;
     if ((int64_t)blockIdx.x * blockDim.x >= total) return;
@@ -531,8 +520,31 @@ vox_inverse_kernel(const int64_t *__restrict__ seg_off, int n_seg, const int64_t
     const int s = block_segment(seg_off, n_seg, total, i, valid, s_pair).s;
     if (!valid) return;
     const int rank = (int)tbl[tbl_off[s] + pslot[i]].rank;
-    inverse[i] = rank + (collate ? (int)uniq_off[s] : 0);
-    if (counts) atomicAdd(&counts[uniq_off[s] + rank], 1);
+    const int64_t o = uniq_off[s] + rank;
+    if (inverse) inverse[i] = rank + (collate ? (int)uniq_off[s] : 0);
+    atomicMin(&first[o], (int)(i - seg_off[s]));
+    if (counts) atomicAdd(&counts[o], 1);
+}
+
+// ---- voxel coordinates in unique order: grid(first occurrence) - min ------------------------
+__global__ void __launch_bounds__(VOX_THREADS)
+vox_coords_kernel(const int64_t *__restrict__ seg_off, int n_seg, const int64_t *__restrict__ uniq_off,
+                  const int *__restrict__ first, const float *__restrict__ xyz, const double *__restrict__ rt,
+                  const int *__restrict__ grid_min, int *__restrict__ voxel_xyz) {
+    __shared__ int s_pair[2];
+    const int64_t total = uniq_off[n_seg];
+    if ((int64_t)blockIdx.x * blockDim.x >= total) return;
+    const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = o < total;
+    const int s = block_segment(uniq_off, n_seg, total, o, valid, s_pair).s;
+    if (!valid) return;
+    double g[3];
+    grid_of(xyz + (seg_off[s] + first[o]) * 3, rt + 12 * s, g);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        if (!(g[j] > -(double)GRID_LIMIT && g[j] < (double)GRID_LIMIT)) g[j] = 0.0;
+        voxel_xyz[o * 3 + j] = (int)g[j] - grid_min[3 * s + j];
+    }
 }
 
 // ---- elementwise hashes (drop-ins for fnv_hash_vec / ravel_hash_vec on float64 rows) --------
@@ -650,7 +662,7 @@ static int run_unique(const float *xyz, const unsigned long long *keys, const in
     vox_plan_kernel<<<1, 1024, 0, stream>>>(seg_off, n_seg, cap, w.tbl_off, w.spl_off, w.total_eff, m,
                                             xyz ? gmin : nullptr, status);
     count_launches(1);
-    vox_clear_kernel<<<(unsigned)(sm_count() * 8), 256, 0, stream>>>(w.tbl, w.tbl_off, n_seg);
+    vox_clear_kernel<<<(unsigned)(sm_count() * 8), 256, 0, stream>>>(w.tbl, w.tbl_off, n_seg, w.total_eff, first);
     count_launches(1);
     if (counts) cudaMemsetAsync(counts, 0, sizeof(int) * cap, stream);
     if (xyz) {
@@ -685,12 +697,14 @@ static int run_unique(const float *xyz, const unsigned long long *keys, const in
                                                                w.ukey, w.ubkt, w.upos, w.bk_key, w.bk_sb);
         count_launches(1);
         vox_rank_kernel<<<blocks, VOX_THREADS, 0, stream>>>(seg_off, n_seg, w.total_eff, m, w.spl_off, w.hist, w.bk_key,
-                                                            w.bk_sb, w.tbl, w.tbl_off, uniq_off, xyz, rt, gmin, first,
-                                                            xyz ? voxel_xyz : nullptr);
+                                                            w.bk_sb, w.tbl, w.tbl_off);
         count_launches(1);
-        if (inverse) {
-            vox_inverse_kernel<<<blocks, VOX_THREADS, 0, stream>>>(seg_off, n_seg, w.total_eff, w.tbl, w.tbl_off, w.pslot,
-                                                                   uniq_off, collate, inverse, counts);
+        vox_inverse_kernel<<<blocks, VOX_THREADS, 0, stream>>>(seg_off, n_seg, w.total_eff, w.tbl, w.tbl_off, w.pslot,
+                                                               uniq_off, collate, inverse, first, counts);
+        count_launches(1);
+        if (xyz && voxel_xyz) {
+            vox_coords_kernel<<<blocks, VOX_THREADS, 0, stream>>>(seg_off, n_seg, uniq_off, first, xyz, rt, gmin,
+                                                                  voxel_xyz);
             count_launches(1);
         }
     }
