@@ -24,6 +24,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: NCCL's banner / debug output goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 METRIC = "points*views/sec (voxelize+project+mask-pool)"
 UNIT = "points*views/s"
@@ -49,6 +51,9 @@ def parse():
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--no-e2e-all", action="store_true")
     p.add_argument("--profile-steps", type=int, default=0, help="run only this many plain steps (for ncu)")
+    p.add_argument("--workload", default="batch", choices=["batch", "split_scene"],
+                   help="batch = configs[1] (default, weak scaling); split_scene = configs[3]: one 1M-point scene, "
+                        "100 views block-partitioned over the ranks, NCCL all-reduce of per-mask sums/counts")
     return p.parse_args()
 
 
@@ -449,6 +454,85 @@ def run_native(args, rank: int, world: int, local_rank: int):
         dist.destroy_process_group()
 
 
+def run_split_scene(args, rank: int, world: int, local_rank: int):
+    """configs[3]: one dense scene (1M points, 1 cm voxels), 100 views split over the ranks; every rank
+    pools its views under a scene-level set of K masks and one all-reduce(SUM) of the packed
+    [K, C+1] sums/counts yields the scene-level mask features on every rank.  Strong scaling."""
+    import torch
+    import torch.distributed as dist
+    from xmask3d_b200 import dist as xd, ops, synthetic as syn
+    from xmask3d_b200.pipeline import Batch, CorrespondencePipeline
+    from xmask3d_b200.voxelizer import Voxelizer
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_pts, n_views_total, voxel = 1_000_000, 100, 0.01
+    sc = syn.make_scene(2000, n_pts, room=(12.0, 10.0, 3.0))
+    mine = list(xd.shard_views(n_views_total, world, rank))
+    w2c, depth, rts = [], [], []
+    for v in mine:
+        vw = syn.make_view(sc, v)
+        w2c.append(np.linalg.inv(vw.pose))
+        depth.append(vw.depth_mm)
+        np.random.seed(5557 + v)
+        rt, _ = Voxelizer(voxel_size=voxel, **LOADER_VOX).draw_rigid_transformation()
+        rts.append(rt[:3, :4])
+    batch = Batch(sc.xyz, np.array([0, n_pts], np.int64), np.zeros(len(mine), np.int64), np.stack(w2c), np.stack(depth),
+                  np.stack(rts), syn.scannet_intrinsics())
+    pipe = CorrespondencePipeline(batch, args.k, args.c, dev)
+    pipe.upload(torch.from_numpy(batch.xyz).pin_memory(), torch.from_numpy(batch.depth_mm.view(np.int16)).pin_memory())
+    pr = pipe.project()
+    total_vis = int(pr.n_vis.sum().item())
+    pipe.set_cap(total_vis)
+    masks, mode, _ = make_masks(args, len(mine), dev, 777 + rank)
+    g = torch.Generator(device=dev).manual_seed(11)          # the scene's per-point features: same on every rank
+    feat = torch.empty((n_pts, args.c), dtype=torch.float32, device=dev)
+    for a in range(0, n_pts, 1 << 18):
+        feat[a:a + (1 << 18)].normal_(generator=g)
+
+    def step():
+        o = pipe.run(masks, feat, mode, feat_per_point=True)
+        tot, cnt = xd.allreduce_mask_sums(o["sum"], o["cnt"])
+        return o, xd.finalize_mean(tot, cnt), cnt
+
+    for _ in range(max(args.warmup, 3)):
+        o, mean, cnt = step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        o, mean, cnt = step()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / args.steps
+    # cross-rank consistency: every rank must hold the same scene-level result
+    chk = torch.stack([mean.double().sum(), cnt.double().sum()])
+    lo, hi = chk.clone(), chk.clone()
+    if world > 1:
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        line = {"metric": METRIC, "value": n_pts * n_views_total / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64/u64/f32", "data": "synthetic",
+                "config": {"workload": f"configs[3]: 1 scene x {n_pts} pts, 1 cm voxels, {n_views_total} views split over "
+                                       f"{world} rank(s), K={args.k} scene-level masks, C={args.c}, one all-reduce of "
+                                       f"[K,C+1] float64 per step", "visible_pairs_rank0": total_vis,
+                           "pooled_pairs_all_ranks": int(cnt.sum().item()),
+                           "ranks_agree": bool(torch.equal(lo, hi))}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -456,6 +540,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.workload == "split_scene":
+        run_split_scene(args, rank, world, local_rank)
         return
     run_native(args, rank, world, local_rank)
 

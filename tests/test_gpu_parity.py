@@ -358,3 +358,52 @@ def test_logits_golden(golden, dev):
     np.testing.assert_allclose(ensemble_logits_with_labels(raw, labels, "mean").cpu().numpy(), g["ens_mean"], rtol=1e-5, atol=1e-7)
     with pytest.raises(AssertionError):
         ensemble_logits_with_labels(raw, labels[:-1], "max")
+
+
+# ----------------------------------------------------------------------------- whole path
+def test_pipeline_end_to_end_vs_oracle(cport, dev):
+    """project -> voxelize -> masks at points -> pool, chained on the device with no host round
+    trip, against the oracle run stage by stage; per-point features gathered through vis_idx, and
+    the scene-level all-reduce helper in its single-process form."""
+    from oracle import ref_port as P
+    from xmask3d_b200 import dist as xd
+    from xmask3d_b200.pipeline import Batch, CorrespondencePipeline
+    k, c, n_views = 9, 32, 3
+    sc = syn.make_scene(91, 60_000)
+    views = [syn.make_view(sc, v) for v in range(n_views)]
+    rng = np.random.default_rng(3)
+    rts = [_random_rt(rng, 0.02) for _ in views]
+    batch = Batch(sc.xyz, np.array([0, 60_000], np.int64), np.zeros(n_views, np.int64),
+                  np.stack([np.linalg.inv(v.pose) for v in views]), np.stack([v.depth_mm for v in views]),
+                  np.stack([r[:3, :4] for r in rts]), syn.scannet_intrinsics())
+    pipe = CorrespondencePipeline(batch, k, c, dev, pairs_per_point=1.0)
+    pipe.upload(torch.from_numpy(batch.xyz), torch.from_numpy(batch.depth_mm.view(np.int16)))
+    masks_np = np.stack([syn.make_partition_masks(40 + v, k) for v in range(n_views)])
+    feat = rng.standard_normal((60_000, c), dtype=np.float32)
+    out = pipe.run(torch.from_numpy(masks_np).to(dev), torch.from_numpy(feat).to(dev), feat_per_point=True)
+    assert int(out["proj"].status.item()) == 0 and int(out["vox"].status.item()) == 0
+    voff = out["proj"].vis_off.cpu().numpy()
+    uoff = out["vox"].uniq_off.cpu().numpy()
+    m = P.getMapping()
+    tot_ref, cnt_ref = np.zeros((k, c)), np.zeros(k, np.int64)
+    for v, vw in enumerate(views):
+        mapping = m.compute_mapping(vw.pose, sc.xyz, vw.depth_m)
+        vis, xl, yl = P.compact_mapping(mapping)
+        a, b = voff[v], voff[v + 1]
+        assert np.array_equal(out["proj"].vis_idx.cpu().numpy()[a:b], np.nonzero(vis)[0])
+        assert np.array_equal(out["proj"].rowcol.cpu().numpy()[a:b], np.stack([xl, yl], 1))
+        g, first, inv = cport.voxelize(sc.xyz[vis], rts[v])
+        assert np.array_equal(out["vox"].first.cpu().numpy()[uoff[v]:uoff[v + 1]], first)
+        assert np.array_equal(out["vox"].inverse.cpu().numpy()[a:b] - uoff[v], inv)          # collated offsets
+        assert np.array_equal(out["vox"].voxel_xyz.cpu().numpy()[uoff[v]:uoff[v + 1]].astype(np.float64), g)
+        member = masks_np[v][:, xl, yl]
+        s64, c64 = cport.pool_member_f64(feat[vis], member)
+        assert np.array_equal(out["cnt"][v].cpu().numpy(), c64)
+        assert (np.abs(out["sum"][v].cpu().numpy() - s64).max(1) / np.maximum(np.abs(s64).max(1), 1e-30)).max() < 1e-5
+        tot_ref += s64
+        cnt_ref += c64
+    tot, cnt = xd.allreduce_mask_sums(out["sum"], out["cnt"])
+    assert np.array_equal(cnt.cpu().numpy(), cnt_ref)
+    mean = xd.finalize_mean(tot, cnt).cpu().numpy()
+    ref_mean = tot_ref / np.maximum(cnt_ref, 1)[:, None]
+    assert (np.abs(mean - ref_mean).max(1) / np.maximum(np.abs(ref_mean).max(1), 1e-30)).max() < 1e-5

@@ -106,9 +106,12 @@ class CorrespondencePipeline:
                                  cap_vis=self.cap_vis, ws=self.ws_proj)
 
     def run(self, masks: torch.Tensor, feat: torch.Tensor, mode: str = "ge0.5",
-            times: Optional[StageTimes] = None):
-        """masks [V,k,240,320] bool/uint8/float32, feat [cap_vis, c] float32 (row j = j-th visible
-        (view, point) pair in view-major, point-ascending order).  Returns a dict of device tensors."""
+            times: Optional[StageTimes] = None, feat_per_point: bool = False):
+        """masks [V,k,240,320] bool/uint8/float32.  feat: [cap_vis, c] float32 with row j = j-th
+        visible (view, point) pair in view-major, point-ascending order — or, with
+        feat_per_point=True, the per-point features [N, c] of a single-scene batch, gathered through
+        the visible-point indices (the pred_3d[inds_reconstruct] pattern of models/xmask3d.py:152).
+        Returns a dict of device tensors."""
         if times is not None:
             times.mark("start")
         pr = self.project()
@@ -121,7 +124,7 @@ class CorrespondencePipeline:
         if times is not None:
             times.mark("gather")
         s, cnt, mean = ops.pool(feat, pr.vis_off, self.k, member=member, cap=self.cap_vis, cap_pairs=self.cap_pairs,
-                                ws=self.ws_pool, status=pr.status)
+                                row_index=(pr.vis_idx if feat_per_point else None), ws=self.ws_pool, status=pr.status)
         if times is not None:
             times.mark("pool")
         return {"proj": pr, "vox": vox, "member": member, "sum": s, "cnt": cnt, "mean": mean}
