@@ -41,25 +41,26 @@ struct PoolIdx {
 };
 
 // membership words of point i (label mode: a single bit, or none)
-__device__ __forceinline__ void load_bits(const PoolIdx &P, int64_t i, bool valid, uint32_t (&b)[MAX_WORDS]) {
+template <int W>
+__device__ __forceinline__ void load_bits(const PoolIdx &P, int64_t i, bool valid, uint32_t (&b)[W]) {
 #pragma unroll
-    for (int w = 0; w < MAX_WORDS; ++w) b[w] = 0u;
+    for (int w = 0; w < W; ++w) b[w] = 0u;
     if (!valid) return;
     if (P.label) {
         const int m = __ldg(P.label + i);
         if (m >= 0 && m < P.k) {
 #pragma unroll
-            for (int w = 0; w < MAX_WORDS; ++w)
+            for (int w = 0; w < W; ++w)
                 if ((m >> 5) == w) b[w] = 1u << (m & 31);
         }
     } else {
 #pragma unroll
-        for (int w = 0; w < MAX_WORDS; ++w)
+        for (int w = 0; w < W; ++w)
             if (w < P.words) b[w] = __ldg(P.member + i * P.words + w);
         // ignore bits of masks >= k
         const int tail = P.k & 31;
 #pragma unroll
-        for (int w = 0; w < MAX_WORDS; ++w)
+        for (int w = 0; w < W; ++w)
             if (tail && w == P.words - 1) b[w] &= (1u << tail) - 1u;
     }
 }
@@ -105,10 +106,11 @@ pool_tileplan_kernel(const int64_t *__restrict__ seg_off, int n_seg, int64_t cap
 }
 
 // Per-warp member counts of one tile: s_wtot[warp][mask] (bytes, <= 32 each).  All threads call it.
-__device__ __forceinline__ void tile_warp_counts(const uint32_t (&b)[MAX_WORDS], uint32_t (&uni)[MAX_WORDS],
-                                                 unsigned char (*s_wtot)[32 * MAX_WORDS], int warp, int lane) {
+template <int W>
+__device__ __forceinline__ void tile_warp_counts(const uint32_t (&b)[W], uint32_t (&uni)[W],
+                                                 unsigned char (*s_wtot)[32 * W], int warp, int lane) {
 #pragma unroll
-    for (int w = 0; w < MAX_WORDS; ++w) {
+    for (int w = 0; w < W; ++w) {
         uni[w] = __reduce_or_sync(0xffffffffu, b[w]);
         uint32_t u = uni[w];
         while (u) {
@@ -130,21 +132,22 @@ __device__ __forceinline__ int tile_segment(const int32_t *__restrict__ tile_off
 }
 
 // one CTA per tile: members of every mask inside the tile -> tile_cnt[tile][k]
+template <int W>
 __global__ void __launch_bounds__(FILL_THREADS, 1)
 pool_tilecount_kernel(const PoolIdx P, const int32_t *__restrict__ tile_off, int32_t *__restrict__ tile_cnt) {
-    __shared__ unsigned char s_wtot[32][32 * MAX_WORDS];
+    __shared__ unsigned char s_wtot[32][32 * W];
     __shared__ int s_seg;
     const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tile >= tile_off[P.n_seg]) return;
     if (tid == 0) s_seg = tile_segment(tile_off, P.n_seg, tile);
-    for (int j = tid; j < 32 * 32 * MAX_WORDS / 4; j += FILL_THREADS) reinterpret_cast<uint32_t *>(&s_wtot[0][0])[j] = 0u;
+    for (int j = tid; j < 32 * 32 * W / 4; j += FILL_THREADS) reinterpret_cast<uint32_t *>(&s_wtot[0][0])[j] = 0u;
     __syncthreads();
     const int s = s_seg;
     const int64_t e = P.seg_off[s + 1];
     const int64_t i = P.seg_off[s] + (int64_t)(tile - tile_off[s]) * FILL_THREADS + tid;
-    uint32_t b[MAX_WORDS], uni[MAX_WORDS];
-    load_bits(P, i, i < e, b);
-    tile_warp_counts(b, uni, s_wtot, warp, lane);
+    uint32_t b[W], uni[W];
+    load_bits<W>(P, i, i < e, b);
+    tile_warp_counts<W>(b, uni, s_wtot, warp, lane);
     __syncthreads();
     if (tid < P.k) {
         int run = 0;
@@ -228,25 +231,26 @@ pool_scan_kernel(const int32_t *__restrict__ cnt, int n_units, int64_t cap_pairs
 
 // one CTA per tile: STABLE placement of the tile's (point, mask) pairs:
 // perm[pair_off[s][m] + (members of m in earlier tiles) + (members in earlier warps / lanes)] = row
+template <int W>
 __global__ void __launch_bounds__(FILL_THREADS, 1)
 pool_fill_kernel(const PoolIdx P, const int32_t *__restrict__ tile_off, const int32_t *__restrict__ tile_pre,
                  const int64_t *__restrict__ pair_off, int64_t cap_pairs, int32_t *__restrict__ perm) {
-    __shared__ unsigned char s_wtot[32][32 * MAX_WORDS];     // per warp, per mask: members in this tile
-    __shared__ unsigned short s_wpre[32][32 * MAX_WORDS];    // exclusive prefix over warps
-    __shared__ int64_t s_base[32 * MAX_WORDS];               // first pair slot of this tile, per mask
+    __shared__ unsigned char s_wtot[32][32 * W];     // per warp, per mask: members in this tile
+    __shared__ unsigned short s_wpre[32][32 * W];    // exclusive prefix over warps
+    __shared__ int64_t s_base[32 * W];               // first pair slot of this tile, per mask
     __shared__ int s_seg;
     const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int k = P.k;
     if (tile >= tile_off[P.n_seg] || pair_off[(size_t)P.n_seg * k] > cap_pairs) return;     // overflow: flagged by the scan
     if (tid == 0) s_seg = tile_segment(tile_off, P.n_seg, tile);
-    for (int j = tid; j < 32 * 32 * MAX_WORDS / 4; j += FILL_THREADS) reinterpret_cast<uint32_t *>(&s_wtot[0][0])[j] = 0u;
+    for (int j = tid; j < 32 * 32 * W / 4; j += FILL_THREADS) reinterpret_cast<uint32_t *>(&s_wtot[0][0])[j] = 0u;
     __syncthreads();
     const int s = s_seg;
     const int64_t e = P.seg_off[s + 1];
     const int64_t i = P.seg_off[s] + (int64_t)(tile - tile_off[s]) * FILL_THREADS + tid;
-    uint32_t b[MAX_WORDS], uni[MAX_WORDS];
-    load_bits(P, i, i < e, b);
-    tile_warp_counts(b, uni, s_wtot, warp, lane);
+    uint32_t b[W], uni[W];
+    load_bits<W>(P, i, i < e, b);
+    tile_warp_counts<W>(b, uni, s_wtot, warp, lane);
     __syncthreads();
     if (tid < k) {
         int run = 0;
@@ -260,7 +264,7 @@ pool_fill_kernel(const PoolIdx P, const int32_t *__restrict__ tile_off, const in
     __syncthreads();
     const int row = (i < e) ? (P.row_index ? __ldg(P.row_index + i) : (int)i) : 0;
 #pragma unroll
-    for (int w = 0; w < MAX_WORDS; ++w) {
+    for (int w = 0; w < W; ++w) {
         uint32_t u = uni[w];
         while (u) {
             const int bit = __ffs(u) - 1;
@@ -404,11 +408,24 @@ extern "C" int xm3d_pool_batch(const float *feat, int32_t c, const int32_t *row_
     I.words = words_for(k); I.cap = cap;
     const int n_units = n_seg * k;
     pool_tileplan_kernel<<<1, 1024, 0, stream>>>(seg_off, n_seg, cap, w.tile_off); count_launches(1);
-    pool_tilecount_kernel<<<(unsigned)w.max_tiles, FILL_THREADS, 0, stream>>>(I, w.tile_off, w.tile_cnt); count_launches(1);
+    const int wt = I.words <= 1 ? 1 : (I.words <= 2 ? 2 : (I.words <= 4 ? 4 : 8));
+    const unsigned tgrid = (unsigned)w.max_tiles;
+    switch (wt) {
+        case 1: pool_tilecount_kernel<1><<<tgrid, FILL_THREADS, 0, stream>>>(I, w.tile_off, w.tile_cnt); break;
+        case 2: pool_tilecount_kernel<2><<<tgrid, FILL_THREADS, 0, stream>>>(I, w.tile_off, w.tile_cnt); break;
+        case 4: pool_tilecount_kernel<4><<<tgrid, FILL_THREADS, 0, stream>>>(I, w.tile_off, w.tile_cnt); break;
+        default: pool_tilecount_kernel<8><<<tgrid, FILL_THREADS, 0, stream>>>(I, w.tile_off, w.tile_cnt); break;
+    }
+    count_launches(1);
     pool_unitprefix_kernel<<<n_seg, 256, 0, stream>>>(w.tile_off, k, w.tile_cnt, w.cnt); count_launches(1);
     pool_scan_kernel<<<1, 1024, 0, stream>>>(w.cnt, n_units, cap_pairs, w.pair_off, w.chunk_off, status); count_launches(1);
-    pool_fill_kernel<<<(unsigned)w.max_tiles, FILL_THREADS, 0, stream>>>(I, w.tile_off, w.tile_cnt, w.pair_off, cap_pairs,
-                                                                      w.perm); count_launches(1);
+    switch (wt) {
+        case 1: pool_fill_kernel<1><<<tgrid, FILL_THREADS, 0, stream>>>(I, w.tile_off, w.tile_cnt, w.pair_off, cap_pairs, w.perm); break;
+        case 2: pool_fill_kernel<2><<<tgrid, FILL_THREADS, 0, stream>>>(I, w.tile_off, w.tile_cnt, w.pair_off, cap_pairs, w.perm); break;
+        case 4: pool_fill_kernel<4><<<tgrid, FILL_THREADS, 0, stream>>>(I, w.tile_off, w.tile_cnt, w.pair_off, cap_pairs, w.perm); break;
+        default: pool_fill_kernel<8><<<tgrid, FILL_THREADS, 0, stream>>>(I, w.tile_off, w.tile_cnt, w.pair_off, cap_pairs, w.perm); break;
+    }
+    count_launches(1);
     SumParams S;
     S.feat = feat; S.c = c; S.perm = w.perm; S.pair_off = w.pair_off; S.chunk_off = w.chunk_off; S.n_units = n_units;
     S.cap_pairs = cap_pairs; S.partial = w.partial;

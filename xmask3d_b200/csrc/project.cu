@@ -23,7 +23,8 @@ constexpr int PROJ_GROUP = 4;                       // consecutive points per th
 constexpr int PROJ_GROUPS = 2;                      // groups per thread
 constexpr int PROJ_GROUP_PTS = PROJ_THREADS * PROJ_GROUP;     // 4096
 constexpr int PROJ_PART = PROJ_GROUP_PTS * PROJ_GROUPS;       // 8192 points per CTA
-constexpr int PROJ_MAX_SMEM_DEPTH = 176 * 1024;     // bytes of depth image we are willing to stage
+constexpr int PROJ_MAX_SMEM_DEPTH = 160 * 1024;     // bytes of depth image we are willing to stage
+constexpr int PROJ_SMEM_EXTRA = PROJ_PART * 4 + PROJ_PART * 2;   // candidate codes + queue
 
 struct ProjParams {
     const float *xyz;
@@ -52,17 +53,12 @@ __device__ __forceinline__ double dot_row(const double *a, double x, double y, d
     return s;
 }
 
-struct PointState {
-    double z;        // camera-space depth
-    int ix, iy;      // pixel column / row (valid when inside)
-    bool inside;
-};
-
-__device__ __forceinline__ PointState project_point(const double *vw, float fx_, float fy_, float fz_,
-                                                    const ProjParams &P) {
-    PointState s;
+// Exact per-point arithmetic of compute_mapping (fusion_util.py:71-95): returns the packed code
+// (bit31 inside, row<<16 | col) and the camera-space depth.
+__device__ __forceinline__ uint32_t project_exact(const double *vw, float fx_, float fy_, float fz_,
+                                                  const ProjParams &P, double *z_out) {
     const double x = (double)fx_, y = (double)fy_, z = (double)fz_;
-    const double p0 = dot_row(vw + 0, x, y, z);                 // fusion_util.py:71
+    const double p0 = dot_row(vw + 0, x, y, z);                 // :71
     const double p1 = dot_row(vw + 4, x, y, z);
     const double p2 = dot_row(vw + 8, x, y, z);
     const double zdiv = (fabs(p2) < 1e-8) ? 1.0 : p2;           // :75-76
@@ -71,24 +67,62 @@ __device__ __forceinline__ PointState project_point(const double *vw, float fx_,
     const double rx = rint(px), ry = rint(py);                  // :82-83 (half to even)
     // :86-95 — tested on the integer-valued doubles (NaN / out-of-int64 values fail like the
     // INT64_MIN numpy's astype(int) produces for them)
-    s.inside = (p2 > 0.0) && (rx >= P.cut) && (ry >= P.cut) && (rx < P.img_w - P.cut) && (ry < P.img_h - P.cut);
-    s.ix = s.inside ? (int)rx : 0;
-    s.iy = s.inside ? (int)ry : 0;
-    s.z = p2;
-    return s;
+    const bool inside = (p2 > 0.0) && (rx >= P.cut) && (ry >= P.cut) && (rx < P.img_w - P.cut) && (ry < P.img_h - P.cut);
+    *z_out = p2;
+    return inside ? (0x80000000u | ((uint32_t)(int)ry << 16) | (uint32_t)(int)rx) : 0u;
+}
+
+// Conservative float32 reject filter: true only when the exact arithmetic above is guaranteed to
+// give inside == false (behind the camera, or outside the cut image by more than 0.49 px beyond
+// every rounding error).  Everything else — including NaN / inf — goes to the exact path.
+struct FilterConst {
+    float a[12], aa[12];     // world->camera rows and their absolute values
+    float fx, fy;
+    float lx, hx, ly, hy;    // (cut - 0.51 - cx), (W - cut - 0.49 - cx), same for y
+};
+__device__ __forceinline__ bool surely_outside(const FilterConst &F, float x, float y, float z) {
+    const float GAM = 1.0e-6f;      // >= 8 ulp: coefficient rounding + three fused multiply-adds
+    const float ax = fabsf(x), ay = fabsf(y), az = fabsf(z);
+    const float p2 = fmaf(F.a[8], x, fmaf(F.a[9], y, fmaf(F.a[10], z, F.a[11])));
+    const float e2 = GAM * fmaf(F.aa[8], ax, fmaf(F.aa[9], ay, fmaf(F.aa[10], az, F.aa[11])));
+    if (p2 + e2 <= 0.f) return true;                       // exact p2 <= 0: not in front
+    if (!(p2 - e2 > 1.0e-3f)) return false;                // too close to the z singularity: exact path
+    const float p0 = fmaf(F.a[0], x, fmaf(F.a[1], y, fmaf(F.a[2], z, F.a[3])));
+    const float e0 = GAM * fmaf(F.aa[0], ax, fmaf(F.aa[1], ay, fmaf(F.aa[2], az, F.aa[3])));
+    const float t = p0 * F.fx;
+    {   // px < lo  <=>  p0*fx < (lo - cx) * z   (z > 0)
+        const float u = F.lx * p2, v = F.hx * p2;
+        const float el = 2.f * (F.fx * e0 + fabsf(F.lx) * e2 + 4e-7f * (fabsf(t) + fabsf(u)));
+        const float eh = 2.f * (F.fx * e0 + fabsf(F.hx) * e2 + 4e-7f * (fabsf(t) + fabsf(v)));
+        if (t - u < -el) return true;
+        if (t - v > eh) return true;
+    }
+    const float p1 = fmaf(F.a[4], x, fmaf(F.a[5], y, fmaf(F.a[6], z, F.a[7])));
+    const float e1 = GAM * fmaf(F.aa[4], ax, fmaf(F.aa[5], ay, fmaf(F.aa[6], az, F.aa[7])));
+    const float s = p1 * F.fy;
+    {
+        const float u = F.ly * p2, v = F.hy * p2;
+        const float el = 2.f * (F.fy * e1 + fabsf(F.ly) * e2 + 4e-7f * (fabsf(s) + fabsf(u)));
+        const float eh = 2.f * (F.fy * e1 + fabsf(F.hy) * e2 + 4e-7f * (fabsf(s) + fabsf(v)));
+        if (s - u < -el) return true;
+        if (s - v > eh) return true;
+    }
+    return false;
 }
 
 template <bool FLAG_ONLY>
 __global__ void __launch_bounds__(PROJ_THREADS, 1) project_kernel(const ProjParams P) {
+    // dynamic shared memory: [depth image (P.smem_depth_bytes)] [codes u32 x PART] [queue u16 x PART]
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(16) double s_view[24];      // the 192-byte record
     __shared__ uint64_t s_bar[2];
     __shared__ int s_warp_tot[PROJ_THREADS / 32];
     __shared__ int s_any;
+    uint32_t *s_code = reinterpret_cast<uint32_t *>(smem_raw + P.smem_depth_bytes);
+    unsigned short *s_queue = reinterpret_cast<unsigned short *>(smem_raw + P.smem_depth_bytes + PROJ_PART * 4);
 
-    const int v = blockIdx.y, part = blockIdx.x, tid = threadIdx.x;
+    const int v = blockIdx.y, part = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const xm3d_view_t *gv = P.views + v;
-    // n_pts sits at byte 152 of the record; read it directly so empty CTAs leave at once
     const int n_pts = gv->n_pts;
     const int64_t part_start = (int64_t)part * PROJ_PART;
     if (part_start >= n_pts) {
@@ -121,7 +155,7 @@ __global__ void __launch_bounds__(PROJ_THREADS, 1) project_kernel(const ProjPara
     }
     __syncthreads();
 
-    // ---- stream this thread's points (16-byte loads when the scene's xyz block is aligned)
+    // ---- phase 1: stream the points (16-byte loads), float32 reject filter, queue the candidates
     const float *xyz = P.xyz + gv->pt_off * 3;
     const bool vec_ok = (reinterpret_cast<uintptr_t>(xyz) % 16 == 0);
     float c[PROJ_GROUPS][PROJ_GROUP * 3];
@@ -142,91 +176,102 @@ __global__ void __launch_bounds__(PROJ_THREADS, 1) project_kernel(const ProjPara
             }
         }
     }
-
     mbar_wait(&s_bar[0], 0);
-    // packed per-point state: bit31 inside, row<<16 | col ; z kept for the occlusion test
-    uint32_t code[PROJ_GROUPS][PROJ_GROUP];
-    double zc[PROJ_GROUPS][PROJ_GROUP];
+    FilterConst F;
+#pragma unroll
+    for (int j = 0; j < 12; ++j) { F.a[j] = (float)s_view[j]; F.aa[j] = fabsf(F.a[j]); }
+    F.fx = fabsf((float)s_view[12]); F.fy = fabsf((float)s_view[13]);
+    const bool filter_ok = s_view[12] > 0.0 && s_view[13] > 0.0;          // the inequalities assume fx, fy > 0
+    F.lx = (float)(P.cut - 0.51 - s_view[14]); F.hx = (float)(P.img_w - P.cut - 0.49 - s_view[14]);
+    F.ly = (float)(P.cut - 0.51 - s_view[15]); F.hy = (float)(P.img_h - P.cut - 0.49 - s_view[15]);
+    // every warp owns its 256 points end to end: no block barrier until the ordered compaction
+    unsigned short *wq = s_queue + warp * (PROJ_GROUPS * PROJ_GROUP * 32);
+    int wcount = 0;
 #pragma unroll
     for (int g = 0; g < PROJ_GROUPS; ++g)
 #pragma unroll
         for (int j = 0; j < PROJ_GROUP; ++j) {
-            const int64_t i = part_start + (int64_t)g * PROJ_GROUP_PTS + (int64_t)tid * PROJ_GROUP + j;
-            PointState s = project_point(s_view, c[g][3 * j], c[g][3 * j + 1], c[g][3 * j + 2], P);
-            if (i >= n_pts) s.inside = false;
-            code[g][j] = s.inside ? (0x80000000u | ((uint32_t)s.iy << 16) | (uint32_t)s.ix) : 0u;
-            zc[g][j] = s.z;
+            const int local = g * PROJ_GROUP_PTS + tid * PROJ_GROUP + j;
+            const bool live = part_start + local < n_pts;
+            const bool cand = live && !(filter_ok && surely_outside(F, c[g][3 * j], c[g][3 * j + 1], c[g][3 * j + 2]));
+            s_code[local] = 0u;
+            const unsigned vote = __ballot_sync(0xffffffffu, cand);
+            if (cand) wq[wcount + __popc(vote & ((1u << lane) - 1u))] = (unsigned short)local;
+            wcount += __popc(vote);
         }
+    __syncwarp();
 
-    // ---- occlusion test (fusion_util.py:98-135)
-    if (has_depth) {
-        if (stage_depth) mbar_wait(&s_bar[1], 0);
-        const unsigned short *sd = reinterpret_cast<const unsigned short *>(smem_raw);
-        bool any_in_depth = false;
-#pragma unroll
-        for (int g = 0; g < PROJ_GROUPS; ++g)
-#pragma unroll
-            for (int j = 0; j < PROJ_GROUP; ++j) {
-                if (!(code[g][j] >> 31)) continue;
-                const int iy = (code[g][j] >> 16) & 0x7fff, ix = code[g][j] & 0xffff;
-                const bool in_depth = iy < dh && ix < dw;            // both are >= 0 here (cut >= 0)
-                bool ok = false;
-                if (in_depth) {
-                    any_in_depth = true;
-                    double d;
-                    const size_t e = (size_t)iy * dw + ix;
-                    if (P.depth_kind == XM3D_DEPTH_U16) {
-                        const unsigned short raw = stage_depth
-                            ? sd[e] : __ldg(reinterpret_cast<const unsigned short *>(P.depth) + depth_off + e);
-                        d = __ddiv_rn((double)raw, P.depth_scale);   // imread(png) / 1000
-                    } else {
-                        d = __ldg(reinterpret_cast<const double *>(P.depth) + depth_off + e);
-                    }
-                    ok = fabs(__dsub_rn(d, zc[g][j])) <= __dmul_rn(P.vis_thres, d);     // :125
+    // ---- phase 2: exact arithmetic + occlusion test, one candidate per lane (dense within the warp)
+    if (has_depth && stage_depth) mbar_wait(&s_bar[1], 0);
+    const unsigned short *sd = reinterpret_cast<const unsigned short *>(smem_raw);
+    bool any_in_depth = false;
+    for (int q = lane; q < wcount; q += 32) {
+        const int local = wq[q];
+        const float *pt = xyz + (part_start + local) * 3;
+        double zc;
+        uint32_t code = project_exact(s_view, __ldg(pt), __ldg(pt + 1), __ldg(pt + 2), P, &zc);
+        if (has_depth && (code >> 31)) {                         // fusion_util.py:98-135
+            const int iy = (code >> 16) & 0x7fff, ix = code & 0xffff;
+            const bool in_depth = iy < dh && ix < dw;            // both are >= 0 here (cut >= 0)
+            bool ok = false;
+            if (in_depth) {
+                any_in_depth = true;
+                double d;
+                const size_t e = (size_t)iy * dw + ix;
+                if (P.depth_kind == XM3D_DEPTH_U16) {
+                    const unsigned short raw = stage_depth
+                        ? sd[e] : __ldg(reinterpret_cast<const unsigned short *>(P.depth) + depth_off + e);
+                    d = __ddiv_rn((double)raw, P.depth_scale);   // imread(png) / 1000
+                } else {
+                    d = __ldg(reinterpret_cast<const double *>(P.depth) + depth_off + e);
                 }
-                if (FLAG_ONLY) continue;
+                ok = fabs(__dsub_rn(d, zc)) <= __dmul_rn(P.vis_thres, d);     // :125
+            }
+            if (!FLAG_ONLY) {
                 // exact mode: keep `inside` when no inside point of the view hits the depth image
                 const bool keep = P.use_flag ? (P.view_flag[v] ? ok : true) : ok;
-                if (!keep) code[g][j] = 0u;
+                if (!keep) code = 0u;
             }
-        if (FLAG_ONLY) {
-            if (any_in_depth) s_any = 1;
-            __syncthreads();
-            if (tid == 0 && s_any) atomicOr(&P.view_flag[v], 1);
-            return;
         }
-    } else if (FLAG_ONLY) {
+        if (!FLAG_ONLY) s_code[local] = code;
+    }
+    if (FLAG_ONLY) {
+        if (any_in_depth) s_any = 1;
+        __syncthreads();
+        if (tid == 0 && s_any) atomicOr(&P.view_flag[v], 1);
         return;
     }
+    __syncthreads();
 
-    // ---- outputs: visibility bytes, optional int64 [N,3] mapping, part-local compaction
+    // ---- phase 3: visibility bytes, optional int64 [N,3] mapping, part-local compaction (point order)
     const int64_t out0 = gv->out_off;
     int running = 0;
-    const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
     for (int g = 0; g < PROJ_GROUPS; ++g) {
         const int64_t i0 = part_start + (int64_t)g * PROJ_GROUP_PTS + (int64_t)tid * PROJ_GROUP;
+        const uint4 cd = *reinterpret_cast<const uint4 *>(s_code + g * PROJ_GROUP_PTS + tid * PROJ_GROUP);
+        const uint32_t code[PROJ_GROUP] = {cd.x, cd.y, cd.z, cd.w};
         int cnt = 0;
 #pragma unroll
-        for (int j = 0; j < PROJ_GROUP; ++j) cnt += code[g][j] >> 31;
+        for (int j = 0; j < PROJ_GROUP; ++j) cnt += code[j] >> 31;
         if (i0 < n_pts) {
             uint8_t *vp = P.vis + out0 + i0;
             if (i0 + PROJ_GROUP <= n_pts && (reinterpret_cast<uintptr_t>(vp) % 4 == 0)) {
-                *reinterpret_cast<uint32_t *>(vp) = (code[g][0] >> 31) | ((code[g][1] >> 31) << 8) |
-                                                    ((code[g][2] >> 31) << 16) | ((code[g][3] >> 31) << 24);
+                *reinterpret_cast<uint32_t *>(vp) = (code[0] >> 31) | ((code[1] >> 31) << 8) |
+                                                    ((code[2] >> 31) << 16) | ((code[3] >> 31) << 24);
             } else {
 #pragma unroll
                 for (int j = 0; j < PROJ_GROUP; ++j)
-                    if (i0 + j < n_pts) vp[j] = (uint8_t)(code[g][j] >> 31);
+                    if (i0 + j < n_pts) vp[j] = (uint8_t)(code[j] >> 31);
             }
             if (P.mapping) {
                 int64_t *mp = P.mapping + (out0 + i0) * 3;
 #pragma unroll
                 for (int j = 0; j < PROJ_GROUP; ++j)
                     if (i0 + j < n_pts) {
-                        const bool vis = code[g][j] >> 31;
-                        mp[3 * j + 0] = vis ? (int64_t)((code[g][j] >> 16) & 0x7fff) : 0;   // row (y)
-                        mp[3 * j + 1] = vis ? (int64_t)(code[g][j] & 0xffff) : 0;           // col (x)
+                        const bool vis = code[j] >> 31;
+                        mp[3 * j + 0] = vis ? (int64_t)((code[j] >> 16) & 0x7fff) : 0;   // row (y)
+                        mp[3 * j + 1] = vis ? (int64_t)(code[j] & 0xffff) : 0;           // col (x)
                         mp[3 * j + 2] = vis ? 1 : 0;
                     }
             }
@@ -249,16 +294,16 @@ __global__ void __launch_bounds__(PROJ_THREADS, 1) project_kernel(const ProjPara
                 if (lane >= o) wi += t;
             }
             s_warp_tot[lane] = wi - w;          // exclusive warp offsets
-            if (lane == 31) s_any = wi;          // group total (s_any is free in this mode)
+            if (lane == 31) s_any = wi;          // group total
         }
         __syncthreads();
         int pos = running + s_warp_tot[warp] + incl - cnt;
         unsigned long long *st = P.stage + out0 + part_start;
 #pragma unroll
         for (int j = 0; j < PROJ_GROUP; ++j)
-            if (code[g][j] >> 31) {
+            if (code[j] >> 31) {
                 const unsigned long long idx = (unsigned long long)(i0 + j);
-                st[pos++] = (idx << 32) | (unsigned long long)(code[g][j] & 0x7fffffffu);
+                st[pos++] = (idx << 32) | (unsigned long long)(code[j] & 0x7fffffffu);
             }
         running += s_any;
         __syncthreads();
@@ -420,20 +465,21 @@ extern "C" int xm3d_project_batch(const float *xyz, const xm3d_view_t *views_hos
     P.xyz = xyz; P.views = d_views; P.depth = depth; P.depth_kind = depth_kind; P.depth_scale = depth_scale;
     P.img_w = img_w; P.img_h = img_h; P.cut = cut_bound; P.vis_thres = vis_thres;
     P.vis = vis; P.mapping = mapping; P.stage = stage; P.part_cnt = part_cnt; P.view_flag = view_flag;
+    stage_bytes = (stage_bytes + 127) / 128 * 128;
     P.parts = parts; P.smem_depth_bytes = (int)stage_bytes; P.use_flag = (any_depth && !covers) ? 1 : 0;
 
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(project_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PROJ_MAX_SMEM_DEPTH);
-        cudaFuncSetAttribute(project_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PROJ_MAX_SMEM_DEPTH);
+        cudaFuncSetAttribute(project_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PROJ_MAX_SMEM_DEPTH + PROJ_SMEM_EXTRA);
+        cudaFuncSetAttribute(project_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PROJ_MAX_SMEM_DEPTH + PROJ_SMEM_EXTRA);
         attr_set = true;
     }
     dim3 grid(parts, n_views);
     if (P.use_flag) {
         cudaMemsetAsync(view_flag, 0, sizeof(int) * n_views, stream);
-        project_kernel<true><<<grid, PROJ_THREADS, stage_bytes, stream>>>(P); count_launches(1);
+        project_kernel<true><<<grid, PROJ_THREADS, stage_bytes + PROJ_SMEM_EXTRA, stream>>>(P); count_launches(1);
     }
-    project_kernel<false><<<grid, PROJ_THREADS, stage_bytes, stream>>>(P); count_launches(1);
+    project_kernel<false><<<grid, PROJ_THREADS, stage_bytes + PROJ_SMEM_EXTRA, stream>>>(P); count_launches(1);
     project_scan_kernel<<<1, 1024, 0, stream>>>(part_cnt, n_views, parts, part_off, n_vis, vis_off, cap_vis, status); count_launches(1);
     if (vis_idx || rowcol || xyz_vis) {
         project_emit_kernel<<<grid, 256, 0, stream>>>(xyz, d_views, stage, part_cnt, part_off, parts, cap_vis,

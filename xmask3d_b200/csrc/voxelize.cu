@@ -221,18 +221,17 @@ vox_min_kernel(const float *__restrict__ xyz, const int64_t *__restrict__ seg_of
                const int64_t *__restrict__ total_eff, const double *__restrict__ rt, int *__restrict__ grid_min,
                int *status) {
     __shared__ int s_min[VOX_THREADS / 32][3];
+    __shared__ int s_pair[2];
     const int64_t total = *total_eff;
     const int64_t b0 = (int64_t)blockIdx.x * blockDim.x;
     if (b0 >= total) return;
     const int64_t i = b0 + threadIdx.x;
     const bool valid = i < total;
-    // segment of the block's first and last point: equal for almost every block
-    const int64_t last = (b0 + blockDim.x - 1 < total) ? b0 + blockDim.x - 1 : total - 1;
-    const int s_first = seg_of(seg_off, n_seg, b0), s_last = seg_of(seg_off, n_seg, last);
-    int s = s_first;
+    const BlockSeg bs = block_segment(seg_off, n_seg, total, i, valid, s_pair);
+    const int s = bs.s;
+    const int s_first = s_pair[0], s_last = s_pair[1];
     int g[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff};
     if (valid) {
-        if (s_first != s_last) s = seg_of(seg_off, n_seg, i);
         double f[3];
         grid_of(xyz + i * 3, rt + 12 * s, f);
 #pragma unroll
