@@ -51,6 +51,7 @@ def parse():
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--no-e2e-all", action="store_true")
     p.add_argument("--profile-steps", type=int, default=0, help="run only this many plain steps (for ncu)")
+    p.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")
     p.add_argument("--workload", default="batch", choices=["batch", "split_scene"],
                    help="batch = configs[1] (default, weak scaling); split_scene = configs[3]: one 1M-point scene, "
                         "100 views block-partitioned over the ranks, NCCL all-reduce of per-mask sums/counts")
@@ -279,14 +280,25 @@ def run_native(args, rank: int, world: int, local_rank: int):
     assert int(out["proj"].status.item()) == 0 and int(out["vox"].status.item()) == 0
     m_vox = out["vox"].m.cpu().numpy().astype(np.int64)
 
+    # the whole step (~30 launches) is captured once and replayed as one CUDA graph
+    use_graph = not args.no_graph
+    l0 = L.lib().xm3d_launch_count()
+    if use_graph:
+        pipe.capture(masks, feat, mode)
+    else:
+        pipe.run(masks, feat, mode)
+    launches_per_step = L.lib().xm3d_launch_count() - l0
+
+    def do_step():
+        return pipe.replay() if use_graph else pipe.run(masks, feat, mode)
+
     # ---- device-resident throughput (`value`): K steps between barriers, CUDA events, max over ranks
     barrier()
-    launches0 = L.lib().xm3d_launch_count()
     with ClockSampler(local_rank) as clk:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.steps):
-            pipe.run(masks, feat, mode)
+            do_step()
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -305,8 +317,6 @@ def run_native(args, rank: int, world: int, local_rank: int):
                 stage_acc.setdefault(kk, []).append(vv)
             stage_acc.setdefault("pool_sum_kernel", []).append(ev_a.elapsed_time(ev_b))
         L.lib().xm3d_set_pool_events(None, None)
-    launches = L.lib().xm3d_launch_count() - launches0
-    launches_per_step = launches / (args.steps + min(args.steps, 20))
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     lt = torch.tensor([float(launches_per_step * args.steps)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -336,7 +346,7 @@ def run_native(args, rank: int, world: int, local_rank: int):
             masks_d2.copy_(all_host[0], non_blocking=True)
             feat.copy_(all_host[1], non_blocking=True)
             mk, ft = masks_d2, feat
-        o = pipe.run(mk, ft, mode)
+        o = do_step() if all_host is None else pipe.run(mk, ft, mode)
         res_h["rowcol"].copy_(o["proj"].rowcol[:total_vis], non_blocking=True)
         res_h["vis_off"].copy_(o["proj"].vis_off, non_blocking=True)
         res_h["inverse"].copy_(o["vox"].inverse[:total_vis], non_blocking=True)
@@ -424,7 +434,9 @@ def run_native(args, rank: int, world: int, local_rank: int):
         "data": "synthetic",
         "config": {"workload": workload_name(args), "point_views_per_gpu_step": pv_rank, "visible_pairs_per_gpu": total_vis, "mask_memberships_per_gpu": total_pairs,
                    "voxels_per_gpu": int(m_vox.sum()), "cache": "inputs larger than L2 (features %.1f GB per GPU)" % (feat.numel() * 4 / 1e9),
-                   "parallelism": f"scenes sharded over {world} rank(s), no data-path collective", "setup_s": round(t_setup, 1)},
+                   "parallelism": f"scenes sharded over {world} rank(s), no data-path collective",
+                   "launch": ("one CUDA graph replay per step" if use_graph else "eager launches"),
+                   "kernels_per_step": int(launches_per_step), "setup_s": round(t_setup, 1)},
         "roofline": roof,
         "pipeline_roofline": {"algorithmic_bytes_per_step": alg, "achieved": pipe_gbs, "peak": peak, "unit": "GB/s",
                               "frac": pipe_gbs / peak},

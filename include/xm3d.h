@@ -93,7 +93,9 @@ typedef struct xm3d_view {
 
 XM3D_API size_t xm3d_project_ws_bytes(int32_t n_views, int64_t total_pts, int32_t max_pts_per_view);
 
-/* views_host: HOST array of n_views records (the library uploads it on `stream`).
+/* views_host: HOST array of n_views records, read for launch planning.  views_dev: the same
+ * records already in device memory, or NULL — then the library uploads views_host on `stream`
+ * (a pageable-memory copy: pass views_dev when the call is captured into a CUDA graph).
  * For every view v and scene point i (i < views[v].n_pts):
  *   vis[out_off+i]        1 if the point projects inside the cut image and passes the depth test
  *   mapping[(out_off+i)*3 + {0,1,2}] = (pixel row, pixel col, vis)   (optional, the drop-in
@@ -107,8 +109,8 @@ XM3D_API size_t xm3d_project_ws_bytes(int32_t n_views, int64_t total_pts, int32_
  * vis_idx / rowcol / xyz_vis / mapping may be NULL.  total_pts = sum of n_pts over views
  * (size of vis).  depth: uint16 raw units (metres = value / depth_scale, float64 division — the
  * loader's imread(png)/1000, dataset/data_loader_infer.py:168-171) or float64 metres. */
-XM3D_API int xm3d_project_batch(const float *xyz, const xm3d_view_t *views_host, int32_t n_views,
-                       int64_t total_pts, const void *depth, int32_t depth_kind, double depth_scale,
+XM3D_API int xm3d_project_batch(const float *xyz, const xm3d_view_t *views_host, const xm3d_view_t *views_dev,
+                       int32_t n_views, int64_t total_pts, const void *depth, int32_t depth_kind, double depth_scale,
                        int32_t img_w, int32_t img_h, int32_t cut_bound, double vis_thres,
                        uint8_t *vis, int64_t *mapping, int32_t *n_vis, int64_t *vis_off,
                        int64_t cap_vis, int32_t *vis_idx, int32_t *rowcol, float *xyz_vis,

@@ -41,7 +41,7 @@ PROTOTYPES = {
     "xm3d_launch_count": (_I64, []),
     "xm3d_set_pool_events": (None, [_P, _P]),
     "xm3d_project_ws_bytes": (_SZ, [_I32, _I64, _I32]),
-    "xm3d_project_batch": (C.c_int, [_P, _P, _I32, _I64, _P, _I32, _F64, _I32, _I32, _I32, _F64,
+    "xm3d_project_batch": (C.c_int, [_P, _P, _P, _I32, _I64, _P, _I32, _F64, _I32, _I32, _I32, _F64,
                                      _P, _P, _P, _P, _I64, _P, _P, _P, _P, _SZ, _P, _P]),
     "xm3d_unique_ws_bytes": (_SZ, [_I32, _I64]),
     "xm3d_unique_batch": (C.c_int, [_P, _P, _I32, _I64, _P, _P, _P, _P, _P, _I32, _P, _SZ, _P, _P]),

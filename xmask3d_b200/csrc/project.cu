@@ -412,8 +412,8 @@ extern "C" size_t xm3d_project_ws_bytes(int32_t n_views, int64_t total_pts, int3
     return c.off + 256;
 }
 
-extern "C" int xm3d_project_batch(const float *xyz, const xm3d_view_t *views_host, int32_t n_views,
-                                  int64_t total_pts, const void *depth, int32_t depth_kind, double depth_scale,
+extern "C" int xm3d_project_batch(const float *xyz, const xm3d_view_t *views_host, const xm3d_view_t *views_dev,
+                                  int32_t n_views, int64_t total_pts, const void *depth, int32_t depth_kind, double depth_scale,
                                   int32_t img_w, int32_t img_h, int32_t cut_bound, double vis_thres,
                                   uint8_t *vis, int64_t *mapping, int32_t *n_vis, int64_t *vis_off,
                                   int64_t cap_vis, int32_t *vis_idx, int32_t *rowcol, float *xyz_vis,
@@ -459,7 +459,8 @@ extern "C" int xm3d_project_batch(const float *xyz, const xm3d_view_t *views_hos
     int64_t *part_off = c.take<int64_t>((size_t)n_views * parts);
     int *view_flag = c.take<int>(n_views);
 
-    cudaMemcpyAsync(d_views, views_host, sizeof(xm3d_view_t) * n_views, cudaMemcpyHostToDevice, stream);
+    if (views_dev) d_views = const_cast<xm3d_view_t *>(views_dev);
+    else cudaMemcpyAsync(d_views, views_host, sizeof(xm3d_view_t) * n_views, cudaMemcpyHostToDevice, stream);
 
     ProjParams P;
     P.xyz = xyz; P.views = d_views; P.depth = depth; P.depth_kind = depth_kind; P.depth_scale = depth_scale;

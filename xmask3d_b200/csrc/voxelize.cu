@@ -282,7 +282,7 @@ __device__ __forceinline__ void bitonic_smem(K *k, int n /*pow2*/) {
 
 // KEY_SRC 0: keys from xyz through the transform (voxelize); 1: keys given (unique_batch)
 template <int KEY_SRC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 vox_sample_kernel(const float *__restrict__ xyz, const unsigned long long *__restrict__ keys_in,
                   const int64_t *__restrict__ seg_off, const int64_t *__restrict__ total_eff,
                   const double *__restrict__ rt, const int *__restrict__ grid_min,
@@ -292,7 +292,7 @@ vox_sample_kernel(const float *__restrict__ xyz, const unsigned long long *__res
     const int64_t a = seg_off[s];
     const int64_t n = (*total_eff > 0) ? seg_off[s + 1] - a : 0;
     const int S = (int)(spl_off[s + 1] - spl_off[s]);
-    for (int j = tid; j < S; j += 256) {
+    for (int j = tid; j < S; j += blockDim.x) {
         unsigned long long key = KEY_EMPTY;
         if (n > 0) {
             const int64_t i = a + (int64_t)j * n / S;          // j < 4096, n < 2^31
@@ -304,7 +304,7 @@ vox_sample_kernel(const float *__restrict__ xyz, const unsigned long long *__res
     }
     __syncthreads();
     bitonic_smem(s_key, S);
-    for (int j = tid; j < S; j += 256) spl[spl_off[s] + j] = s_key[j];
+    for (int j = tid; j < S; j += blockDim.x) spl[spl_off[s] + j] = s_key[j];
 }
 
 // ---- insert pass --------------------------------------------------------------------------
@@ -669,7 +669,7 @@ static int run_unique(const float *xyz, const unsigned long long *keys, const in
             vox_min_kernel<<<blocks, VOX_THREADS, 0, stream>>>(xyz, seg_off, n_seg, w.total_eff, rt, gmin, status);
             count_launches(1);
         }
-        vox_sample_kernel<0><<<n_seg, 256, 0, stream>>>(xyz, nullptr, seg_off, w.total_eff, rt, gmin, w.spl_off, w.spl,
+        vox_sample_kernel<0><<<n_seg, 1024, 0, stream>>>(xyz, nullptr, seg_off, w.total_eff, rt, gmin, w.spl_off, w.spl,
                                                         w.hist);
         count_launches(1);
         if (blocks) {
@@ -679,7 +679,7 @@ static int run_unique(const float *xyz, const unsigned long long *keys, const in
             count_launches(1);
         }
     } else {
-        vox_sample_kernel<1><<<n_seg, 256, 0, stream>>>(nullptr, keys, seg_off, w.total_eff, nullptr, nullptr, w.spl_off,
+        vox_sample_kernel<1><<<n_seg, 1024, 0, stream>>>(nullptr, keys, seg_off, w.total_eff, nullptr, nullptr, w.spl_off,
                                                         w.spl, w.hist);
         count_launches(1);
         if (blocks) {

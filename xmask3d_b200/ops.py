@@ -78,10 +78,17 @@ def make_views(w2c: np.ndarray, intr: Sequence[float], pt_off: Sequence[int], n_
     return arr, out_off
 
 
+def views_to_device(views, device) -> torch.Tensor:
+    """Device copy of the host view records (uint8 [V*192]) for graph-capturable projection calls."""
+    raw = np.frombuffer(bytes(views), dtype=np.uint8).copy()
+    return torch.from_numpy(raw).to(device)
+
+
 def project_batch(xyz: torch.Tensor, views, out_off: np.ndarray, depth: Optional[torch.Tensor],
                   depth_scale: float = 1000.0, image_dim=(320, 240), cut_bound: int = 10,
                   vis_thres: float = 0.25, cap_vis: Optional[int] = None, want_mapping: bool = False,
-                  want_compact: bool = True, ws: Optional[torch.Tensor] = None) -> Projection:
+                  want_compact: bool = True, ws: Optional[torch.Tensor] = None,
+                  views_dev: Optional[torch.Tensor] = None) -> Projection:
     """xyz: float32 [sum N_scene,3] (all scenes concatenated); views: (View * V) host records;
     depth: uint16 / int16-viewed / float64 CUDA tensor holding every view's image, or None."""
     _require_cuda()
@@ -115,7 +122,7 @@ def project_batch(xyz: torch.Tensor, views, out_off: np.ndarray, depth: Optional
     if ws is None or ws.numel() < need:
         ws = _ws(need, dev)
     L.check(L.lib().xm3d_project_batch(
-        _ptr(xyz), C.cast(views, C.c_void_p), n_views, total, _ptr(depth), kind, float(depth_scale),
+        _ptr(xyz), C.cast(views, C.c_void_p), _ptr(views_dev), n_views, total, _ptr(depth), kind, float(depth_scale),
         int(image_dim[0]), int(image_dim[1]), int(cut_bound), float(vis_thres),
         _ptr(vis), _ptr(mapping), _ptr(n_vis), _ptr(vis_off), cap, _ptr(vis_idx), _ptr(rowcol), _ptr(xyz_vis),
         _ptr(ws), ws.numel(), _ptr(status), _stream()))

@@ -74,6 +74,9 @@ class CorrespondencePipeline:
         self.views, self.out_off = ops.make_views(batch.w2c, batch.intr, batch.scene_off[batch.view_scene], n_pts,
                                                   batch.depth_mm.shape[1:])
         self.n_views = batch.n_views
+        self.views_dev = ops.views_to_device(self.views, device)      # keeps project() graph-capturable
+        self.graph = None
+        self._graph_out = None
         self.total_pv = int(self.out_off[-1])
         self.xyz = torch.empty((batch.xyz.shape[0], 3), dtype=torch.float32, device=device)
         self.depth = torch.empty(batch.depth_mm.shape, dtype=torch.int16, device=device)
@@ -103,7 +106,7 @@ class CorrespondencePipeline:
     def project(self):
         return ops.project_batch(self.xyz, self.views, self.out_off, self.depth, depth_scale=self.depth_scale,
                                  image_dim=(IMG_W, IMG_H), cut_bound=self.cut_bound, vis_thres=self.vis_thres,
-                                 cap_vis=self.cap_vis, ws=self.ws_proj)
+                                 cap_vis=self.cap_vis, ws=self.ws_proj, views_dev=self.views_dev)
 
     def run(self, masks: torch.Tensor, feat: torch.Tensor, mode: str = "ge0.5",
             times: Optional[StageTimes] = None, feat_per_point: bool = False):
@@ -128,6 +131,23 @@ class CorrespondencePipeline:
         if times is not None:
             times.mark("pool")
         return {"proj": pr, "vox": vox, "member": member, "sum": s, "cnt": cnt, "mean": mean}
+
+
+    # -- CUDA graph replay ------------------------------------------------------------------
+    def capture(self, masks: torch.Tensor, feat: torch.Tensor, mode: str = "ge0.5", feat_per_point: bool = False):
+        """Capture one pass (≈ 30 launches) into a CUDA graph.  Inputs are read from the tensors
+        given here (update them in place); the returned dict holds the graph's static outputs.
+        Run at least one eager pass first (kernel attributes are set lazily)."""
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = self.run(masks, feat, mode, feat_per_point=feat_per_point)
+        self.graph, self._graph_out = g, out
+        return out
+
+    def replay(self):
+        self.graph.replay()
+        return self._graph_out
 
 
 def algorithmic_bytes(n_pts_per_view: np.ndarray, n_vis: np.ndarray, m_vox: np.ndarray, k: int, c: int,
