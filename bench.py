@@ -51,6 +51,7 @@ def parse():
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--no-e2e-all", action="store_true")
     p.add_argument("--profile-steps", type=int, default=0, help="run only this many plain steps (for ncu)")
+    p.add_argument("--no-overlap", action="store_true", help="run the stages back to back on one stream")
     p.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")
     p.add_argument("--workload", default="batch", choices=["batch", "split_scene"],
                    help="batch = configs[1] (default, weak scaling); split_scene = configs[3]: one 1M-point scene, "
@@ -239,7 +240,7 @@ def run_native(args, rank: int, world: int, local_rank: int):
         dist.init_process_group("nccl", device_id=dev)
     t_setup = time.perf_counter()
     batch, scenes = build_batch(args, rank)
-    pipe = CorrespondencePipeline(batch, args.k, args.c, dev)
+    pipe = CorrespondencePipeline(batch, args.k, args.c, dev, overlap=not args.no_overlap)
     xyz_h = torch.from_numpy(batch.xyz).pin_memory()
     depth_h = torch.from_numpy(batch.depth_mm.view(np.int16)).pin_memory()
     pipe.upload(xyz_h, depth_h)
@@ -278,6 +279,7 @@ def run_native(args, rank: int, world: int, local_rank: int):
     for _ in range(max(args.warmup, 3)):
         out = pipe.run(masks, feat, mode)
     assert int(out["proj"].status.item()) == 0 and int(out["vox"].status.item()) == 0
+    assert int(out["pool_status"].item()) == 0
     m_vox = out["vox"].m.cpu().numpy().astype(np.int64)
 
     # the whole step (~30 launches) is captured once and replayed as one CUDA graph
@@ -435,7 +437,8 @@ def run_native(args, rank: int, world: int, local_rank: int):
         "config": {"workload": workload_name(args), "point_views_per_gpu_step": pv_rank, "visible_pairs_per_gpu": total_vis, "mask_memberships_per_gpu": total_pairs,
                    "voxels_per_gpu": int(m_vox.sum()), "cache": "inputs larger than L2 (features %.1f GB per GPU)" % (feat.numel() * 4 / 1e9),
                    "parallelism": f"scenes sharded over {world} rank(s), no data-path collective",
-                   "launch": ("one CUDA graph replay per step" if use_graph else "eager launches"),
+                   "launch": ("one CUDA graph replay per step" if use_graph else "eager launches") +
+                             ("; voxelize overlapped with gather+pool on a second stream" if pipe.overlap else ""),
                    "kernels_per_step": int(launches_per_step), "setup_s": round(t_setup, 1)},
         "roofline": roof,
         "pipeline_roofline": {"algorithmic_bytes_per_step": alg, "achieved": pipe_gbs, "peak": peak, "unit": "GB/s",

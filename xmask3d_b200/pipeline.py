@@ -66,7 +66,7 @@ class CorrespondencePipeline:
 
     def __init__(self, batch: Batch, k: int, c: int, device, cap_vis: Optional[int] = None,
                  cut_bound: int = 10, vis_thres: float = 0.25, depth_scale: float = 1000.0,
-                 pairs_per_point: float = 1.0):
+                 pairs_per_point: float = 1.0, overlap: bool = True):
         ops._require_cuda()
         self.batch, self.k, self.c, self.dev = batch, int(k), int(c), device
         self.cut_bound, self.vis_thres, self.depth_scale = cut_bound, vis_thres, depth_scale
@@ -77,6 +77,9 @@ class CorrespondencePipeline:
         self.views_dev = ops.views_to_device(self.views, device)      # keeps project() graph-capturable
         self.graph = None
         self._graph_out = None
+        self.overlap = bool(overlap)                       # voxelize || (gather + pool) on two streams
+        self._side = torch.cuda.Stream(device=device)
+        self._side_status = torch.zeros(1, dtype=torch.int32, device=device)
         self.total_pv = int(self.out_off[-1])
         self.xyz = torch.empty((batch.xyz.shape[0], 3), dtype=torch.float32, device=device)
         self.depth = torch.empty(batch.depth_mm.shape, dtype=torch.int16, device=device)
@@ -115,11 +118,31 @@ class CorrespondencePipeline:
         feat_per_point=True, the per-point features [N, c] of a single-scene batch, gathered through
         the visible-point indices (the pred_3d[inds_reconstruct] pattern of models/xmask3d.py:152).
         Returns a dict of device tensors."""
+        overlap = self.overlap and times is None
         if times is not None:
             times.mark("start")
         pr = self.project()
         if times is not None:
             times.mark("project")
+        if overlap:
+            # fork: masks-at-points + pooling (HBM-bandwidth bound) run on a side stream while the
+            # voxelization (latency bound, little bandwidth) runs on the caller's stream
+            main = torch.cuda.current_stream()
+            side = self._side
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                member, _ = ops.gather_masks(masks, pr.rowcol, pr.vis_off, mode=mode, cap=self.cap_vis,
+                                             ws=self.ws_gather)
+                s, cnt, mean = ops.pool(feat, pr.vis_off, self.k, member=member, cap=self.cap_vis,
+                                        cap_pairs=self.cap_pairs,
+                                        row_index=(pr.vis_idx if feat_per_point else None), ws=self.ws_pool,
+                                        status=self._side_status)
+            vox = ops.voxelize_batch(pr.xyz_vis, pr.vis_off, self.rt, cap=self.cap_vis, collate=True, ws=self.ws_vox)
+            main.wait_stream(side)                      # join
+            for t in (member, s, cnt, mean):
+                t.record_stream(main)
+            return {"proj": pr, "vox": vox, "member": member, "sum": s, "cnt": cnt, "mean": mean,
+                    "pool_status": self._side_status}
         vox = ops.voxelize_batch(pr.xyz_vis, pr.vis_off, self.rt, cap=self.cap_vis, collate=True, ws=self.ws_vox)
         if times is not None:
             times.mark("voxelize")
@@ -127,11 +150,12 @@ class CorrespondencePipeline:
         if times is not None:
             times.mark("gather")
         s, cnt, mean = ops.pool(feat, pr.vis_off, self.k, member=member, cap=self.cap_vis, cap_pairs=self.cap_pairs,
-                                row_index=(pr.vis_idx if feat_per_point else None), ws=self.ws_pool, status=pr.status)
+                                row_index=(pr.vis_idx if feat_per_point else None), ws=self.ws_pool,
+                                status=self._side_status)
         if times is not None:
             times.mark("pool")
-        return {"proj": pr, "vox": vox, "member": member, "sum": s, "cnt": cnt, "mean": mean}
-
+        return {"proj": pr, "vox": vox, "member": member, "sum": s, "cnt": cnt, "mean": mean,
+                "pool_status": self._side_status}
 
     # -- CUDA graph replay ------------------------------------------------------------------
     def capture(self, masks: torch.Tensor, feat: torch.Tensor, mode: str = "ge0.5", feat_per_point: bool = False):
