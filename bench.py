@@ -426,8 +426,15 @@ def run_native(args, rank: int, world: int, local_rank: int):
     pool_ms = stage_ms.get("pool_sum_kernel", float("nan"))
     achieved = pool_bytes / (pool_ms * 1e-3) / 1e9
     step_ms = ms / args.steps
+    # dram__bytes_read+write of this kernel from the committed `ncu --set full` capture of this same
+    # default workload (profiles/r01_pool_sum_kernel_ncu_full.json); null for any other workload
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_pool_sum_kernel_ncu_full.json")
+    default_wl = (args.scenes, args.views, args.points, args.k, args.c, args.masks, rank) == (8, 20, 150_000, 50, 768, "partition", 0)
+    if default_wl and os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("_summary", {}).get("traffic_bytes_per_launch")
     roof = {"bound": "hbm", "kernel": "pool_sum_kernel<4> (events recorded around this launch alone)",
-            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
             "bytes_per_launch": pool_bytes, "ms_per_launch": pool_ms, "peak_source": peak_src}
     pipe_gbs = alg["total"] / (step_ms * 1e-3) / 1e9
     line = {
