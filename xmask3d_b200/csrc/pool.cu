@@ -330,23 +330,35 @@ __global__ void __launch_bounds__(1024) pool_sum_kernel(const SumParams P) {
     if (active) *reinterpret_cast<V *>(P.partial + (size_t)chunk * P.c + ch) = acc;
 }
 
+// VEC consecutive channels per thread (16-byte loads / stores when c % 4 == 0)
+template <int VEC>
 __global__ void __launch_bounds__(256)
 pool_combine_kernel(const float *__restrict__ partial, const int32_t *__restrict__ cnt_in,
                     const int64_t *__restrict__ pair_off, const int32_t *__restrict__ chunk_off, int n_units,
                     int64_t cap_pairs, int k, int c, float *__restrict__ sum, int32_t *__restrict__ cnt,
                     float *__restrict__ mean) {
+    using V = typename VecT<VEC>::type;
     const int s = blockIdx.y;
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;       // element of [k, c]
-    if (e >= k * c) return;
-    const int m = e / c, ch = e - m * c;
+    const int cv = c / VEC;                                    // vectors per row
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;       // vector element of [k, c / VEC]
+    if (e >= k * cv) return;
+    const int m = e / cv, ch = (e - m * cv) * VEC;
     const int u = s * k + m;
     const bool ok = pair_off[n_units] <= cap_pairs;
     const int n = ok ? cnt_in[u] : 0;
-    float acc = 0.f;
+    V acc; vzero(acc);
     if (ok)
-        for (int q = chunk_off[u]; q < chunk_off[u + 1]; ++q) acc += partial[(size_t)q * c + ch];   // fixed order
-    sum[(size_t)s * k * c + e] = acc;
-    if (mean) mean[(size_t)s * k * c + e] = n > 0 ? __fdiv_rn(acc, (float)n) : 0.f;
+        for (int q = chunk_off[u]; q < chunk_off[u + 1]; ++q)      // fixed order
+            vadd(acc, *reinterpret_cast<const V *>(partial + (size_t)q * c + ch));
+    const size_t o = ((size_t)s * k + m) * c + ch;
+    *reinterpret_cast<V *>(sum + o) = acc;
+    if (mean) {
+        V mv = acc;
+        float *a = reinterpret_cast<float *>(&mv);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) a[j] = n > 0 ? __fdiv_rn(a[j], (float)n) : 0.f;
+        *reinterpret_cast<V *>(mean + o) = mv;
+    }
     if (cnt && ch == 0) cnt[u] = n;
 }
 
@@ -434,8 +446,16 @@ extern "C" int xm3d_pool_batch(const float *feat, int32_t c, const int32_t *row_
     if (vec == 4) { pool_sum_kernel<4><<<(unsigned)w.max_chunks, threads, 0, stream>>>(S); count_launches(1); }
     else { pool_sum_kernel<1><<<(unsigned)w.max_chunks, threads, 0, stream>>>(S); count_launches(1); }
     if (g_pool_ev[1]) cudaEventRecord(g_pool_ev[1], stream);
-    dim3 cgrid((unsigned)(((size_t)k * c + 255) / 256), n_seg);
-    pool_combine_kernel<<<cgrid, 256, 0, stream>>>(w.partial, w.cnt, w.pair_off, w.chunk_off, n_units, cap_pairs, k, c, sum,
-                                                   cnt, mean); count_launches(1);
+    const bool cv4 = vec == 4 && reinterpret_cast<uintptr_t>(sum) % 16 == 0 && (!mean || reinterpret_cast<uintptr_t>(mean) % 16 == 0);
+    if (cv4) {
+        dim3 cgrid((unsigned)(((size_t)k * (c / 4) + 255) / 256), n_seg);
+        pool_combine_kernel<4><<<cgrid, 256, 0, stream>>>(w.partial, w.cnt, w.pair_off, w.chunk_off, n_units, cap_pairs, k, c,
+                                                          sum, cnt, mean);
+    } else {
+        dim3 cgrid((unsigned)(((size_t)k * c + 255) / 256), n_seg);
+        pool_combine_kernel<1><<<cgrid, 256, 0, stream>>>(w.partial, w.cnt, w.pair_off, w.chunk_off, n_units, cap_pairs, k, c,
+                                                          sum, cnt, mean);
+    }
+    count_launches(1);
     return check_launch("xm3d_pool_batch");
 }

@@ -40,6 +40,8 @@ struct ProjParams {
     int *part_cnt;              // [n_views * parts]
     int *view_flag;             // [n_views] any inside point within the depth image (exact mode)
     int parts;
+    const int *item_off;        // [n_views + 1] exclusive prefix of the parts of every view (device)
+    int n_views;
     int smem_depth_bytes;
     int use_flag;               // 1: vis = flag ? inside&&ok : inside   (depth smaller than image)
 };
@@ -121,39 +123,71 @@ __global__ void __launch_bounds__(PROJ_THREADS, 1) project_kernel(const ProjPara
     uint32_t *s_code = reinterpret_cast<uint32_t *>(smem_raw + P.smem_depth_bytes);
     unsigned short *s_queue = reinterpret_cast<unsigned short *>(smem_raw + P.smem_depth_bytes + PROJ_PART * 4);
 
-    const int v = blockIdx.y, part = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const xm3d_view_t *gv = P.views + v;
-    const int n_pts = gv->n_pts;
-    const int64_t part_start = (int64_t)part * PROJ_PART;
-    if (part_start >= n_pts) {
-        if (!FLAG_ONLY && tid == 0) P.part_cnt[v * P.parts + part] = 0;
-        return;
-    }
-    const int64_t depth_off = gv->depth_off;
-    const int dh = gv->depth_h, dw = gv->depth_w;
-    const bool has_depth = P.depth_kind != XM3D_DEPTH_NONE && depth_off >= 0;
-    const size_t depth_bytes = (size_t)dh * dw * 2;
-    const bool stage_depth = has_depth && P.depth_kind == XM3D_DEPTH_U16 && depth_bytes <= (size_t)P.smem_depth_bytes &&
-                             (depth_bytes % 16 == 0) &&
-                             ((reinterpret_cast<uintptr_t>(P.depth) + (size_t)depth_off * 2) % 16 == 0);
-
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // persistent CTA: a contiguous run of (view, part) work items; the view record and the depth
+    // image stay in shared memory while consecutive items belong to the same view
+    const int n_items = P.item_off[P.n_views];
+    const int it0 = (int)((int64_t)n_items * blockIdx.x / gridDim.x);
+    const int it1 = (int)((int64_t)n_items * (blockIdx.x + 1) / gridDim.x);
+    if (it0 >= it1) return;
     if (tid == 0) {
         mbar_init(&s_bar[0], 1);
         mbar_init(&s_bar[1], 1);
         mbar_fence_init();
         s_any = 0;
-        mbar_expect_tx(&s_bar[0], (uint32_t)sizeof(xm3d_view_t));
-        bulk_g2s(s_view, gv, (uint32_t)sizeof(xm3d_view_t), &s_bar[0]);
-        if (stage_depth) {
-            mbar_expect_tx(&s_bar[1], (uint32_t)depth_bytes);
-            const char *src = reinterpret_cast<const char *>(P.depth) + (size_t)depth_off * 2;
-            for (size_t o = 0; o < depth_bytes; o += 32768) {
-                const uint32_t chunk = (uint32_t)((depth_bytes - o < 32768) ? depth_bytes - o : 32768);
-                bulk_g2s(smem_raw + o, src + o, chunk, &s_bar[1]);
+    }
+    int v = 0;
+    {   // view of the first item: largest v with item_off[v] <= it0
+        int lo = 0, hi = P.n_views;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (P.item_off[mid] <= it0) lo = mid; else hi = mid;
+        }
+        v = lo;
+    }
+    int cur_view = -1;
+    uint32_t ph = 0;                              // parity of both barriers (they complete together)
+    bool staged = false, has_depth = false;
+    int dh = 0, dw = 0, n_pts = 0;
+    int64_t depth_off = -1;
+    const xm3d_view_t *gv = nullptr;
+  for (int it = it0; it < it1; ++it) {
+    while (it >= P.item_off[v + 1]) ++v;
+    const int part = it - P.item_off[v];
+    const int64_t part_start = (int64_t)part * PROJ_PART;
+    __syncthreads();                               // previous item done with s_code / depth / s_any
+    bool stage_depth = staged;
+    if (v != cur_view) {
+        cur_view = v;
+        gv = P.views + v;
+        n_pts = gv->n_pts;
+        depth_off = gv->depth_off;
+        dh = gv->depth_h; dw = gv->depth_w;
+        has_depth = P.depth_kind != XM3D_DEPTH_NONE && depth_off >= 0;
+        const size_t depth_bytes = (size_t)dh * dw * 2;
+        stage_depth = has_depth && P.depth_kind == XM3D_DEPTH_U16 && depth_bytes <= (size_t)P.smem_depth_bytes &&
+                      (depth_bytes % 16 == 0) &&
+                      ((reinterpret_cast<uintptr_t>(P.depth) + (size_t)depth_off * 2) % 16 == 0);
+        staged = stage_depth;
+        if (tid == 0) {
+            mbar_expect_tx(&s_bar[0], (uint32_t)sizeof(xm3d_view_t));
+            bulk_g2s(s_view, gv, (uint32_t)sizeof(xm3d_view_t), &s_bar[0]);
+            if (stage_depth) {
+                mbar_expect_tx(&s_bar[1], (uint32_t)depth_bytes);
+                const char *src = reinterpret_cast<const char *>(P.depth) + (size_t)depth_off * 2;
+                for (size_t o = 0; o < depth_bytes; o += 32768) {
+                    const uint32_t chunk = (uint32_t)((depth_bytes - o < 32768) ? depth_bytes - o : 32768);
+                    bulk_g2s(smem_raw + o, src + o, chunk, &s_bar[1]);
+                }
+            } else {
+                mbar_expect_tx(&s_bar[1], 0);    // keep both barriers in the same phase
             }
         }
+        __syncthreads();
+        mbar_wait(&s_bar[0], ph);
+        if (!stage_depth) mbar_wait(&s_bar[1], ph);
+        // (a staged depth image is awaited right before its first use, after the float32 filter)
     }
-    __syncthreads();
 
     // ---- phase 1: stream the points (16-byte loads), float32 reject filter, queue the candidates
     const float *xyz = P.xyz + gv->pt_off * 3;
@@ -176,7 +210,6 @@ __global__ void __launch_bounds__(PROJ_THREADS, 1) project_kernel(const ProjPara
             }
         }
     }
-    mbar_wait(&s_bar[0], 0);
     FilterConst F;
 #pragma unroll
     for (int j = 0; j < 12; ++j) { F.a[j] = (float)s_view[j]; F.aa[j] = fabsf(F.a[j]); }
@@ -202,7 +235,7 @@ __global__ void __launch_bounds__(PROJ_THREADS, 1) project_kernel(const ProjPara
     __syncwarp();
 
     // ---- phase 2: exact arithmetic + occlusion test, one candidate per lane (dense within the warp)
-    if (has_depth && stage_depth) mbar_wait(&s_bar[1], 0);
+    if (stage_depth) mbar_wait(&s_bar[1], ph);     // no-op once the phase has completed
     const unsigned short *sd = reinterpret_cast<const unsigned short *>(smem_raw);
     bool any_in_depth = false;
     for (int q = lane; q < wcount; q += 32) {
@@ -238,8 +271,12 @@ __global__ void __launch_bounds__(PROJ_THREADS, 1) project_kernel(const ProjPara
     if (FLAG_ONLY) {
         if (any_in_depth) s_any = 1;
         __syncthreads();
-        if (tid == 0 && s_any) atomicOr(&P.view_flag[v], 1);
-        return;
+        if (tid == 0) {
+            if (s_any) atomicOr(&P.view_flag[v], 1);
+            s_any = 0;                               // ordered before the next item by its leading barrier
+        }
+        if (it + 1 < it1 && it + 1 >= P.item_off[v + 1]) ph ^= 1;      // next item starts a new view
+        continue;
     }
     __syncthreads();
 
@@ -309,6 +346,49 @@ __global__ void __launch_bounds__(PROJ_THREADS, 1) project_kernel(const ProjPara
         __syncthreads();
     }
     if (tid == 0) P.part_cnt[v * P.parts + part] = running;
+    if (it + 1 < it1 && it + 1 >= P.item_off[v + 1]) ph ^= 1;          // next item starts a new view
+  }
+}
+
+// parts of every view (exclusive prefix) for the persistent kernel; part counts zeroed
+__global__ void __launch_bounds__(1024, 1)
+project_plan_kernel(const xm3d_view_t *__restrict__ views, int n_views, int parts, int *__restrict__ item_off,
+                    int *__restrict__ part_cnt) {
+    __shared__ int s_w[32];
+    __shared__ int s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    for (int e = tid; e < n_views * parts; e += 1024) part_cnt[e] = 0;
+    __syncthreads();
+    for (int base = 0; base < n_views; base += 1024) {
+        const int v = base + tid;
+        const int val = v < n_views ? (views[v].n_pts + PROJ_PART - 1) / PROJ_PART : 0;
+        int incl = val;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const int w = s_w[lane];
+            int wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            s_w[lane] = wi - w;
+        }
+        __syncthreads();
+        const int excl = s_carry + s_w[warp] + incl - val;
+        if (v < n_views) item_off[v] = excl;
+        __syncthreads();
+        if (tid == 1023) s_carry = excl + val;
+        __syncthreads();
+    }
+    if (tid == 0) item_off[n_views] = s_carry;
 }
 
 // Exclusive scan over the (view-major) part counts: one CTA, chunks of 1024 with a carry.
@@ -409,6 +489,7 @@ extern "C" size_t xm3d_project_ws_bytes(int32_t n_views, int64_t total_pts, int3
     c.take<int>((size_t)n_views * parts);
     c.take<int64_t>((size_t)n_views * parts);
     c.take<int>(n_views);
+    c.take<int>(n_views + 1);
     return c.off + 256;
 }
 
@@ -458,6 +539,7 @@ extern "C" int xm3d_project_batch(const float *xyz, const xm3d_view_t *views_hos
     int *part_cnt = c.take<int>((size_t)n_views * parts);
     int64_t *part_off = c.take<int64_t>((size_t)n_views * parts);
     int *view_flag = c.take<int>(n_views);
+    int *item_off = c.take<int>(n_views + 1);
 
     if (views_dev) d_views = const_cast<xm3d_view_t *>(views_dev);
     else cudaMemcpyAsync(d_views, views_host, sizeof(xm3d_view_t) * n_views, cudaMemcpyHostToDevice, stream);
@@ -467,6 +549,7 @@ extern "C" int xm3d_project_batch(const float *xyz, const xm3d_view_t *views_hos
     P.img_w = img_w; P.img_h = img_h; P.cut = cut_bound; P.vis_thres = vis_thres;
     P.vis = vis; P.mapping = mapping; P.stage = stage; P.part_cnt = part_cnt; P.view_flag = view_flag;
     stage_bytes = (stage_bytes + 127) / 128 * 128;
+    P.item_off = item_off; P.n_views = n_views;
     P.parts = parts; P.smem_depth_bytes = (int)stage_bytes; P.use_flag = (any_depth && !covers) ? 1 : 0;
 
     static bool attr_set = false;
@@ -476,11 +559,13 @@ extern "C" int xm3d_project_batch(const float *xyz, const xm3d_view_t *views_hos
         attr_set = true;
     }
     dim3 grid(parts, n_views);
+    project_plan_kernel<<<1, 1024, 0, stream>>>(d_views, n_views, parts, item_off, part_cnt); count_launches(1);
+    const unsigned pgrid = (unsigned)sm_count();       // persistent: one CTA per SM
     if (P.use_flag) {
         cudaMemsetAsync(view_flag, 0, sizeof(int) * n_views, stream);
-        project_kernel<true><<<grid, PROJ_THREADS, stage_bytes + PROJ_SMEM_EXTRA, stream>>>(P); count_launches(1);
+        project_kernel<true><<<pgrid, PROJ_THREADS, stage_bytes + PROJ_SMEM_EXTRA, stream>>>(P); count_launches(1);
     }
-    project_kernel<false><<<grid, PROJ_THREADS, stage_bytes + PROJ_SMEM_EXTRA, stream>>>(P); count_launches(1);
+    project_kernel<false><<<pgrid, PROJ_THREADS, stage_bytes + PROJ_SMEM_EXTRA, stream>>>(P); count_launches(1);
     project_scan_kernel<<<1, 1024, 0, stream>>>(part_cnt, n_views, parts, part_off, n_vis, vis_off, cap_vis, status); count_launches(1);
     if (vis_idx || rowcol || xyz_vis) {
         project_emit_kernel<<<grid, 256, 0, stream>>>(xyz, d_views, stage, part_cnt, part_off, parts, cap_vis,
