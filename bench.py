@@ -411,6 +411,36 @@ def run_native(args, rank: int, world: int, local_rank: int):
             dist.destroy_process_group()
         return
 
+    # ---- stage 4 (text logits, the only tensor-core kernel): timed apart, it is not part of the metric
+    logits_info = {}
+    try:
+        from xmask3d_b200 import ops as _ops
+        peaks_tf = 1678.5
+        if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
+            peaks_tf = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops", peaks_tf))
+        gl = torch.Generator(device=dev).manual_seed(1)
+        for name, rows, t in (("configs[1] B15N4 160x50 masks x 20 classes", 160 * 50, 20),
+                              ("configs[2] B170N30 160x100 masks x 201 classes", 160 * 100, 201)):
+            me = torch.randn(rows, args.c, device=dev, generator=gl)
+            te = torch.randn(t - 1, args.c, device=dev, generator=gl)
+            ne = torch.randn(1, args.c, device=dev, generator=gl)
+            for _ in range(3):
+                _ops.logits(me, te, ne, [1] * (t - 1), 1 / 0.07)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(20):
+                _ops.logits(me, te, ne, [1] * (t - 1), 1 / 0.07)
+            e1.record()
+            torch.cuda.synchronize()
+            ms_l = e0.elapsed_time(e1) / 20
+            fl = 2.0 * rows * args.c * t
+            logits_info[name] = {"ms": ms_l, "useful_tflops": fl / (ms_l * 1e-3) / 1e12,
+                                 "mma_tflops_3xtf32": 3 * fl / (ms_l * 1e-3) / 1e12,
+                                 "frac_of_bf16_peak": 3 * fl / (ms_l * 1e-3) / 1e12 / peaks_tf,
+                                 "note": "prep + tcgen05 GEMM + epilogue; <= 5 GFLOP, launch/latency bound by construction"}
+    except Exception as e:                      # noqa: BLE001
+        logits_info = {"error": f"{type(e).__name__}: {e}"[:200]}
+
     # ---- roofline of the dominant kernel (pool) and of the whole step
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -451,6 +481,7 @@ def run_native(args, rank: int, world: int, local_rank: int):
         "pipeline_roofline": {"algorithmic_bytes_per_step": alg, "achieved": pipe_gbs, "peak": peak, "unit": "GB/s",
                               "frac": pipe_gbs / peak},
         "stage_ms": stage_ms,
+        "logits": logits_info,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "note": "host->device: scene xyz, depth PNG arrays, view records (the reference's loader-side numpy inputs); "
                         "device->host: x/y labels, inverse/first/voxel maps, pooled means and counts; per-point features "

@@ -407,3 +407,122 @@ def test_pipeline_end_to_end_vs_oracle(cport, dev):
     mean = xd.finalize_mean(tot, cnt).cpu().numpy()
     ref_mean = tot_ref / np.maximum(cnt_ref, 1)[:, None]
     assert (np.abs(mean - ref_mean).max(1) / np.maximum(np.abs(ref_mean).max(1), 1e-30)).max() < 1e-5
+
+
+# ----------------------------------------------------------------------------- full-size properties
+def _u64_order(t):
+    """int64 tensor holding uint64 bits -> int64 with the same ordering as the unsigned values."""
+    return t ^ torch.tensor(-2 ** 63, dtype=torch.int64, device=t.device)
+
+
+def test_full_size_properties(dev):
+    """BASELINE configs[1] sizes (150k-point scenes x 20 views, C=768, K=50): size-independent
+    invariants of every stage — no oracle, the CPU path would take minutes."""
+    from xmask3d_b200 import ops
+    from xmask3d_b200.pipeline import Batch, CorrespondencePipeline
+    from xmask3d_b200.voxelizer import Voxelizer
+    from bench import LOADER_VOX
+    n_scenes, n_views, n_pts, k, c = 2, 20, 150_000, 50, 768
+    xyz, off, vs, w2c, depth, rts = [], [0], [], [], [], []
+    for s in range(n_scenes):
+        sc = syn.make_scene(1000 + s, n_pts)
+        xyz.append(sc.xyz)
+        off.append(off[-1] + n_pts)
+        for v in range(n_views):
+            vw = syn.make_view(sc, v)
+            vs.append(s)
+            w2c.append(np.linalg.inv(vw.pose))
+            depth.append(vw.depth_mm)
+            np.random.seed(5557 + 1000 * s + v)
+            rts.append(Voxelizer(voxel_size=0.02, **LOADER_VOX).draw_rigid_transformation()[0][:3, :4])
+    batch = Batch(np.concatenate(xyz), np.array(off, np.int64), np.array(vs, np.int64), np.stack(w2c), np.stack(depth),
+                  np.stack(rts), syn.scannet_intrinsics())
+    pipe = CorrespondencePipeline(batch, k, c, dev)
+    pipe.upload(torch.from_numpy(batch.xyz), torch.from_numpy(batch.depth_mm.view(np.int16)))
+    pr = pipe.project()
+    total = int(pr.vis_off[-1].item())
+    pipe.set_cap(total)
+    V = batch.n_views
+    masks = torch.from_numpy(np.stack([syn.make_partition_masks(500 + v, k) for v in range(V)])).to(dev)
+    feat = torch.randn(total, c, device=dev, generator=torch.Generator(device=dev).manual_seed(3))
+    out = pipe.run(masks, feat)
+    pr, vox = out["proj"], out["vox"]
+    assert int(pr.status.item()) == 0 and int(vox.status.item()) == 0 and int(out["pool_status"].item()) == 0
+    voff, nv = pr.vis_off.cpu().numpy(), pr.n_vis.cpu().numpy()
+    assert voff[0] == 0 and np.all(np.diff(voff) == nv) and voff[-1] == total and nv.max() > 20_000
+    seg = torch.repeat_interleave(torch.arange(V, device=dev), torch.from_numpy(nv).to(dev))
+    # projection: visibility bytes agree with the compaction; pixels inside the cut image; order kept
+    assert int(pr.vis.sum().item()) == total
+    rc = pr.rowcol[:total]
+    assert int(rc[:, 0].min()) >= 10 and int(rc[:, 0].max()) < 230 and int(rc[:, 1].min()) >= 10 and int(rc[:, 1].max()) < 310
+    d = pr.vis_idx[1:total] - pr.vis_idx[:total - 1]
+    same = seg[1:] == seg[:-1]
+    assert bool((d[same] > 0).all())
+    scene_of_view = torch.from_numpy(batch.view_scene).to(dev)
+    src = pr.vis_idx[:total].long() + scene_of_view[seg] * n_pts
+    assert torch.equal(pr.xyz_vis[:total], pipe.xyz[src])
+    # voxelization: keys strictly ascending inside every segment; inverse / first consistent;
+    # every point's own grid coordinates equal its voxel's
+    m, uoff = vox.m.cpu().numpy(), vox.uniq_off.cpu().numpy()
+    M = int(uoff[-1])
+    assert np.all(np.diff(uoff) == m) and M == m.sum() and np.all(m <= nv) and np.all(m[nv > 0] >= 1) and M > 0.6 * total
+    useg = torch.repeat_interleave(torch.arange(V, device=dev), torch.from_numpy(m).to(dev))
+    keys = _u64_order(ops.fnv_hash(vox.voxel_xyz[:M].double()))
+    assert bool((keys[1:] > keys[:-1])[useg[1:] == useg[:-1]].all())
+    inv = vox.inverse[:total].long()                                     # collated (global unique index)
+    assert bool((useg[inv] == seg).all())
+    local = torch.arange(total, device=dev) - torch.from_numpy(voff).to(dev)[seg]
+    first = vox.first[:M].long()
+    assert bool((first[inv] <= local).all())
+    assert torch.equal(inv[first + torch.from_numpy(voff).to(dev)[useg]], torch.arange(M, device=dev))
+    rt = pipe.rt[seg]                                                    # [total,3,4] float64
+    grid = torch.floor((rt[:, :, :3] * pr.xyz_vis[:total].double().unsqueeze(1)).sum(-1) + rt[:, :, 3])
+    gmin = torch.stack([grid[voff[v]:voff[v + 1]].min(0).values for v in range(V)])
+    # (float64 sum order differs from the FMA chain only in the last bit; compare where it is safe)
+    frac_ok = ((rt[:, :, :3] * pr.xyz_vis[:total].double().unsqueeze(1)).sum(-1) + rt[:, :, 3])
+    safe = ((frac_ok - torch.floor(frac_ok)).abs() > 1e-9).all(1) & ((torch.ceil(frac_ok) - frac_ok).abs() > 1e-9).all(1)
+    assert float(safe.float().mean()) > 0.999
+    assert torch.equal((grid - gmin[seg])[safe].long(), vox.voxel_xyz[:M].long()[inv][safe])
+    # pooling: partition masks -> counts add up to the visible points, sums add up to the column sums
+    cnt, s = out["cnt"], out["sum"]
+    assert np.array_equal(cnt.sum(1).cpu().numpy(), nv)
+    colsum = torch.zeros(V, c, device=dev, dtype=torch.float64).index_add_(0, seg, feat.double())
+    err = (s.double().sum(1) - colsum).abs().max(1).values / colsum.abs().max(1).values
+    assert float(err.max()) < 1e-5
+    mean_chk = (out["mean"].double() * cnt.unsqueeze(-1)).sum(1)
+    assert float(((mean_chk - colsum).abs().max(1).values / colsum.abs().max(1).values).max()) < 1e-5
+    # idempotence: a second pass returns identical bits (deterministic reductions)
+    out2 = pipe.run(masks, feat)
+    assert torch.equal(out2["sum"], s) and torch.equal(out2["vox"].inverse[:total], vox.inverse[:total])
+
+
+def test_logits_full_size_vs_torch(dev):
+    """configs[2]: 160 x 100 mask embeddings vs 200 + null text embeddings (ScanNet200), against a
+    float32 torch matmul on the same device: identical argmax, |diff| at float32 rounding level."""
+    import torch.nn.functional as F
+    from xmask3d_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(5)
+    for rows, t in ((160 * 100, 201), (160 * 50, 20), (129, 33), (1, 2)):
+        me = torch.randn(rows, 768, device=dev, generator=g)
+        te = torch.randn(t - 1, 768, device=dev, generator=g)
+        ne = torch.randn(1, 768, device=dev, generator=g)
+        got, amax = ops.logits(me, te, ne, [1] * (t - 1), 1 / 0.07, want_argmax=True)
+        torch.backends.cuda.matmul.allow_tf32 = False
+        mn = F.normalize(me.double(), dim=-1)
+        ref = (1 / 0.07) * torch.cat([mn @ F.normalize(te.double(), dim=-1).t(), mn @ F.normalize(ne.double(), dim=-1).t()], -1)
+        assert got.shape == ref.shape
+        assert float((got.double() - ref).abs().max()) < 2e-5 * float(ref.abs().max())
+        top2 = ref.topk(2, -1).values
+        clear = (top2[:, 0] - top2[:, 1]) > 1e-4                     # ignore numerical ties of the reference itself
+        assert torch.equal(got.argmax(-1)[clear], ref.argmax(-1)[clear])
+        assert torch.equal(amax.long()[clear], ref.argmax(-1)[clear])
+    # embedding width that is not a multiple of the 32-float k-block, and mean ensembling
+    me = torch.randn(70, 100, device=dev, generator=g)
+    te = torch.randn(9, 100, device=dev, generator=g)
+    ne = torch.randn(1, 100, device=dev, generator=g)
+    got = ops.logits(me, te, ne, [2, 3, 4], 10.0, ensemble="mean")
+    mn = F.normalize(me.double(), dim=-1)
+    raw = 10.0 * (mn @ F.normalize(te.double(), dim=-1).t())
+    ref = torch.stack([raw[:, :2].mean(1), raw[:, 2:5].mean(1), raw[:, 5:].mean(1),
+                       10.0 * (mn @ F.normalize(ne.double(), dim=-1).t())[:, 0]], 1)
+    assert float((got.double() - ref).abs().max()) < 1e-4
