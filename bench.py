@@ -51,6 +51,8 @@ def parse():
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--no-e2e-all", action="store_true")
     p.add_argument("--profile-steps", type=int, default=0, help="run only this many plain steps (for ncu)")
+    p.add_argument("--distinct-scenes", action="store_true",
+                   help="rank r processes scenes 8r..8r+7 (data-dependent imbalance) instead of a copy of scenes 0..7")
     p.add_argument("--no-overlap", action="store_true", help="run the stages back to back on one stream")
     p.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")
     p.add_argument("--workload", default="batch", choices=["batch", "split_scene"],
@@ -66,7 +68,10 @@ def build_batch(args, rank: int):
     from xmask3d_b200.voxelizer import Voxelizer
     xyz, off, vs, w2c, depth, rts, scenes = [], [0], [], [], [], [], []
     for s in range(args.scenes):
-        gs = rank * args.scenes + s
+        # weak scaling: every rank owns the same amount of work, i.e. a copy of the same 8 synthetic
+        # scenes (--distinct-scenes gives rank-specific seeds; the visible fraction then varies by
+        # +-15 % between ranks and the slowest rank sets the time)
+        gs = (rank * args.scenes + s) if args.distinct_scenes else s
         sc = syn.make_scene(1000 + gs, args.points)
         scenes.append(sc)
         xyz.append(sc.xyz)
@@ -473,7 +478,8 @@ def run_native(args, rank: int, world: int, local_rank: int):
         "data": "synthetic",
         "config": {"workload": workload_name(args), "point_views_per_gpu_step": pv_rank, "visible_pairs_per_gpu": total_vis, "mask_memberships_per_gpu": total_pairs,
                    "voxels_per_gpu": int(m_vox.sum()), "cache": "inputs larger than L2 (features %.1f GB per GPU)" % (feat.numel() * 4 / 1e9),
-                   "parallelism": f"scenes sharded over {world} rank(s), no data-path collective",
+                   "parallelism": f"scenes sharded over {world} rank(s), no data-path collective; " +
+                                  ("rank-specific scenes" if args.distinct_scenes else "every rank processes a copy of the same 8 scenes"),
                    "launch": ("one CUDA graph replay per step" if use_graph else "eager launches") +
                              ("; voxelize overlapped with gather+pool on a second stream" if pipe.overlap else ""),
                    "kernels_per_step": int(launches_per_step), "setup_s": round(t_setup, 1)},
