@@ -526,3 +526,45 @@ def test_logits_full_size_vs_torch(dev):
     ref = torch.stack([raw[:, :2].mean(1), raw[:, 2:5].mean(1), raw[:, 5:].mean(1),
                        10.0 * (mn @ F.normalize(ne.double(), dim=-1).t())[:, 0]], 1)
     assert float((got.double() - ref).abs().max()) < 1e-4
+
+
+# ----------------------------------------------------------------------------- error behaviour
+def test_abi_error_reporting(dev):
+    """Bad arguments come back as negative status codes with a message, never as a crash; capacity
+    overflows are flagged in device memory and nothing is overrun."""
+    import ctypes as C
+    from xmask3d_b200 import _lib as L, ops
+    lib = L.lib()
+    sm, major = C.c_int32(0), C.c_int32(0)
+    assert lib.xm3d_device_info(C.byref(sm), C.byref(major), None) == 0 and sm.value >= 100 and major.value == 10
+    assert lib.xm3d_pool_batch(None, 768, None, None, None, 1, 50, None, 0, 0, None, None, None, None, 0, None, None) == -1
+    assert b"xm3d_pool_batch" in lib.xm3d_last_error()
+    with pytest.raises(L.Xm3dError):                      # workspace too small
+        feat = torch.zeros(8, 4, device=dev)
+        seg = torch.tensor([0, 8], dtype=torch.int64, device=dev)
+        lab = torch.zeros(8, dtype=torch.int32, device=dev)
+        out = torch.zeros(1, 2, 4, device=dev)
+        L.check(lib.xm3d_pool_batch(C.c_void_p(feat.data_ptr()), 4, None, None, C.c_void_p(lab.data_ptr()), 1, 2,
+                                    C.c_void_p(seg.data_ptr()), 8, 8, C.c_void_p(out.data_ptr()), None, None,
+                                    C.c_void_p(out.data_ptr()), 16, None, None))
+    with pytest.raises(L.Xm3dError):                      # more than 256 masks per segment
+        ops.pool(torch.zeros(8, 4, device=dev), torch.tensor([0, 8], device=dev), 300,
+                 label=torch.zeros(8, dtype=torch.int32, device=dev))
+    with pytest.raises(L.Xm3dError):                      # empty label group
+        lib_rc = ops.logits(torch.randn(4, 8, device=dev), torch.randn(3, 8, device=dev), torch.randn(1, 8, device=dev),
+                            [3, 0], 1.0) if False else None
+        L.check(lib.xm3d_logits(None, 4, 8, None, 3, None, None, 2, 0, 1.0, None, None, None, 0, None))
+    # pooling with more memberships than cap_pairs: flagged, sums zero, no overrun
+    n, k, c = 5000, 40, 64
+    member = torch.full((n, 2), -1, dtype=torch.int32, device=dev)            # every point in every mask
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    s, cnt, _ = ops.pool(torch.ones(n, c, device=dev), torch.tensor([0, n], device=dev), k, member=member,
+                         cap_pairs=1000, status=status)
+    assert int(status.item()) & L.FLAG_PAIR_OVERFLOW and float(s.abs().sum()) == 0.0
+    s, cnt, _ = ops.pool(torch.ones(n, c, device=dev), torch.tensor([0, n], device=dev), k, member=member)
+    assert torch.all(cnt == n) and torch.all(s == n)
+    # voxelize with more points than `cap`: flagged, nothing processed
+    xyz = torch.rand(1000, 3, device=dev)
+    rt = torch.eye(4, dtype=torch.float64, device=dev)[:3].reshape(1, 3, 4) * 50
+    u = ops.voxelize_batch(xyz, torch.tensor([0, 1000], device=dev), rt, cap=500)
+    assert int(u.status.item()) & L.FLAG_VIS_OVERFLOW and int(u.m.sum().item()) == 0
