@@ -12,19 +12,18 @@ from . import ops
 
 
 def ensemble_logits_with_labels(logits: torch.Tensor, labels: List[List[str]], ensemble_method: str = "max"):
-    """helper.py:72-97 — kept in torch: it is a column regrouping of an existing logits tensor.
-    (`cal_pred_logits` below fuses the same reduction into the GEMM epilogue.)"""
-    len_list = [len(l) for l in labels]
-    assert logits.shape[-1] == sum(len_list), f"{logits.shape[-1]} != {sum(len_list)}"
+    """helper.py:72-97 — reduce every synonym group (consecutive columns) to one column.  Kept in
+    torch: it only regroups an existing logits tensor (`cal_pred_logits` below fuses the same
+    reduction into the GEMM epilogue)."""
+    sizes = [len(group) for group in labels]
+    assert logits.shape[-1] == sum(sizes), f"{logits.shape[-1]} != {sum(sizes)}"
     assert ensemble_method in ["mean", "max"]
-    ensemble_logits = torch.zeros(*logits.shape[:-1], len(labels), dtype=logits.dtype, device=logits.device)
+    pieces = torch.split(logits, sizes, dim=-1)
     if ensemble_method == "max":
-        for i in range(len(labels)):
-            ensemble_logits[..., i] = logits[..., sum(len_list[:i]):sum(len_list[:i + 1])].max(dim=-1).values
+        cols = [p.max(dim=-1).values for p in pieces]
     else:
-        for i in range(len(labels)):
-            ensemble_logits[..., i] = logits[..., sum(len_list[:i]):sum(len_list[:i + 1])].mean(dim=-1)
-    return ensemble_logits
+        cols = [p.mean(dim=-1) for p in pieces]
+    return torch.stack(cols, dim=-1)
 
 
 def cal_pred_logits(outputs, ensemble_method: str = "max", want_argmax: bool = False):

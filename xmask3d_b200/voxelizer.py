@@ -39,42 +39,34 @@ class Voxelizer:
 
     # -- host side -------------------------------------------------------------------------
     def get_transformation_matrix(self):
-        voxelization_matrix, rotation_matrix = np.eye(4), np.eye(4)
-        rot_mat = np.eye(3)
-        if self.use_augmentation and self.rotation_augmentation_bound is not None:
-            if not isinstance(self.rotation_augmentation_bound, Iterable):
+        """(scale matrix, rotation matrix), both 4x4 float64.  np.random is consumed in the
+        reference's order (:32-58): one uniform per bounded axis, one shuffle, one uniform."""
+        scale_m, rot_m = np.eye(4), np.eye(4)
+        bounds = self.rotation_augmentation_bound
+        if self.use_augmentation and bounds is not None:
+            if not isinstance(bounds, Iterable):
                 raise ValueError()
-            rot_mats = []
-            for axis_ind, rot_bound in enumerate(self.rotation_augmentation_bound):
-                theta = 0
-                axis = np.zeros(3)
-                axis[axis_ind] = 1
-                if rot_bound is not None:
-                    theta = np.random.uniform(*rot_bound)
-                rot_mats.append(M(axis, theta))
-            np.random.shuffle(rot_mats)
-            rot_mat = rot_mats[0] @ rot_mats[1] @ rot_mats[2]
-        rotation_matrix[:3, :3] = rot_mat
-        scale = 1 / self.voxel_size
+            per_axis = [M(np.eye(3)[a], np.random.uniform(*b) if b is not None else 0)
+                        for a, b in enumerate(bounds)]
+            np.random.shuffle(per_axis)
+            rot_m[:3, :3] = per_axis[0] @ per_axis[1] @ per_axis[2]
+        s = 1 / self.voxel_size
         if self.use_augmentation and self.scale_augmentation_bound is not None:
-            scale *= np.random.uniform(*self.scale_augmentation_bound)
-        np.fill_diagonal(voxelization_matrix[:3, :3], scale)
-        return voxelization_matrix, rotation_matrix
+            s *= np.random.uniform(*self.scale_augmentation_bound)
+        scale_m[[0, 1, 2], [0, 1, 2]] = s
+        return scale_m, rot_m
 
     def clip(self, coords, center=None, trans_aug_ratio=None):
-        bound_min = np.min(coords, 0).astype(float)
-        bound_max = np.max(coords, 0).astype(float)
-        bound_size = bound_max - bound_min
+        """Axis-aligned crop predicate around the (optionally shifted) centre (:60-79)."""
+        lo, hi = coords.min(0).astype(float), coords.max(0).astype(float)
+        extent = hi - lo
         if center is None:
-            center = bound_min + bound_size * 0.5
+            center = lo + extent * 0.5
         if trans_aug_ratio is not None:
-            trans = np.multiply(trans_aug_ratio, bound_size)
-            center += trans
-        lim = self.clip_bound
-        clip_inds = ((coords[:, 0] >= (lim[0][0] + center[0])) & (coords[:, 0] < (lim[0][1] + center[0])) &
-                     (coords[:, 1] >= (lim[1][0] + center[1])) & (coords[:, 1] < (lim[1][1] + center[1])) &
-                     (coords[:, 2] >= (lim[2][0] + center[2])) & (coords[:, 2] < (lim[2][1] + center[2])))
-        return clip_inds
+            center += np.multiply(trans_aug_ratio, extent)
+        lim = np.asarray(self.clip_bound, dtype=float)               # [3, 2]: (low, high) per axis
+        inside = (coords >= lim[:, 0] + center) & (coords < lim[:, 1] + center)
+        return inside.all(axis=1)
 
     def draw_rigid_transformation(self):
         """(rigid_transformation 4x4, M_r 4x4) exactly as voxelize draws them (:104-108)."""
