@@ -207,6 +207,20 @@ XM3D_API int xm3d_logits(const float *mask_embed, int64_t rows, int32_t c, const
                 int32_t n_groups, int32_t ensemble_mean, float logit_scale, float *out,
                 int32_t *argmax, void *ws, size_t ws_bytes, xm3d_stream_t stream);
 
+/* ------------------------------------------------------------------ after the path: votes
+ * Cross-view vote accumulation of the inference loop (run/infer.py:642-647, :658), batched:
+ *   votes[p, cls[j]] += 1, counter[p] += 1   for every visible pair j, p = view_pt_off[seg(j)] + vis_idx[j]
+ * vis_idx / seg_off as produced by xm3d_project_batch; view_pt_off: DEVICE int64 [n_seg], first
+ * point of each view's scene in the scene-point arrays; cls: predicted class of every pair
+ * (values outside [0,n_classes) only count the visit).  votes int32 [n_scene_pts, n_classes] and
+ * counter int32 [n_scene_pts] are accumulated into (zero them once per scene).
+ * xm3d_vote_argmax: pred[p] = first maximum of votes[p,:] (torch.max semantics), -1 if counter[p] == 0. */
+XM3D_API int xm3d_vote_batch(const int32_t *vis_idx, const int64_t *seg_off, int32_t n_seg, int64_t cap,
+                    const int64_t *view_pt_off, const int32_t *cls, int32_t n_classes, int32_t *votes,
+                    int32_t *counter, xm3d_stream_t stream);
+XM3D_API int xm3d_vote_argmax(const int32_t *votes, const int32_t *counter, int64_t n_pts, int32_t n_classes,
+                     int32_t *pred, xm3d_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -357,3 +357,16 @@ def cal_pred_logits(outputs: dict):
     ne = F.normalize(outputs["null_embed"], dim=-1)
     null = scale * (me @ ne.t())
     return torch.cat([pred, null], dim=-1)
+
+
+# --------------------------------------------------------------------------- after the path
+def accumulate_votes(scene_pred, counter, mask_2d, logits_pred):
+    """run/infer.py:642-647 — one view's votes (numpy, in place)."""
+    idx = np.nonzero(mask_2d)[0]
+    scene_pred[idx, logits_pred] += 1
+    counter[idx] += 1
+
+
+def vote_argmax(scene_pred):
+    """run/infer.py:658 — torch.max(scene_pred, dim=1)[1]: first maximum."""
+    return scene_pred.argmax(1)

@@ -568,3 +568,43 @@ def test_abi_error_reporting(dev):
     rt = torch.eye(4, dtype=torch.float64, device=dev)[:3].reshape(1, 3, 4) * 50
     u = ops.voxelize_batch(xyz, torch.tensor([0, 1000], device=dev), rt, cap=500)
     assert int(u.status.item()) & L.FLAG_VIS_OVERFLOW and int(u.m.sum().item()) == 0
+
+
+def test_vote_accumulation(cport, dev):
+    """Cross-view votes (run/infer.py:642-647, :658) on the projection's compaction outputs."""
+    from oracle import ref_port as P
+    from xmask3d_b200 import ops
+    t, n_views = 19, 5
+    scenes = [syn.make_scene(61, 30_000), syn.make_scene(62, 17_001)]
+    intr = syn.scannet_intrinsics()
+    xyz = np.concatenate([s.xyz for s in scenes])
+    pt_off, n_pts, w2c, depth, view_scene = [], [], [], [], []
+    o = 0
+    for si, sc in enumerate(scenes):
+        for v in range(n_views):
+            vw = syn.make_view(sc, v)
+            pt_off.append(o); n_pts.append(sc.xyz.shape[0]); w2c.append(np.linalg.inv(vw.pose)); depth.append(vw.depth_mm)
+            view_scene.append(si)
+        o += sc.xyz.shape[0]
+    views, out_off = ops.make_views(np.stack(w2c), intr, pt_off, n_pts, depth[0].shape)
+    pr = ops.project_batch(torch.from_numpy(xyz).to(dev), views, out_off,
+                           torch.from_numpy(np.stack(depth).view(np.int16)).to(dev), want_mapping=True)
+    total = int(pr.vis_off[-1].item())
+    rng = np.random.default_rng(8)
+    cls = rng.integers(0, t, total).astype(np.int32)
+    votes = torch.zeros(xyz.shape[0], t, dtype=torch.int32, device=dev)
+    counter = torch.zeros(xyz.shape[0], dtype=torch.int32, device=dev)
+    ops.accumulate_votes(pr.vis_idx, pr.vis_off, torch.tensor(pt_off, dtype=torch.int64, device=dev),
+                         torch.from_numpy(cls).to(dev), votes, counter, cap=total)
+    pred = ops.vote_argmax(votes, counter).cpu().numpy()
+    ref_votes = np.zeros((xyz.shape[0], t), np.int64)
+    ref_cnt = np.zeros(xyz.shape[0], np.int64)
+    mapping, voff = pr.mapping.cpu().numpy(), pr.vis_off.cpu().numpy()
+    for v in range(len(views)):
+        m = mapping[out_off[v]:out_off[v + 1]][:, 2] == 1
+        sl = slice(pt_off[v], pt_off[v] + n_pts[v])
+        P.accumulate_votes(ref_votes[sl], ref_cnt[sl], m, cls[voff[v]:voff[v + 1]])
+    assert np.array_equal(votes.cpu().numpy(), ref_votes) and np.array_equal(counter.cpu().numpy(), ref_cnt)
+    seen = ref_cnt > 0
+    assert np.array_equal(pred[seen], P.vote_argmax(ref_votes)[seen]) and np.all(pred[~seen] == -1)
+    assert seen.sum() > 10_000 and ref_cnt.max() >= 3

@@ -347,3 +347,28 @@ def logits(mask_embed: torch.Tensor, text_embed: torch.Tensor, null_embed: torch
     if want_argmax:
         return out, amax[:rows].reshape(lead)
     return out
+
+
+# ----------------------------------------------------------------------------- after the path
+def accumulate_votes(vis_idx: torch.Tensor, seg_off: torch.Tensor, view_pt_off: torch.Tensor, cls: torch.Tensor,
+                     votes: torch.Tensor, counter: torch.Tensor, cap: Optional[int] = None):
+    """scene_pred[mask_2d, logits_pred] += 1; counter[mask_2d] += 1 (run/infer.py:642-647) for all
+    views of a batch at once.  votes int32 [n_scene_pts, T] and counter int32 [n_scene_pts] are
+    updated in place."""
+    _require_cuda()
+    assert votes.dtype == torch.int32 and counter.dtype == torch.int32 and votes.is_contiguous()
+    vis_idx = _dev_contig(vis_idx, torch.int32)
+    seg_off = _dev_contig(seg_off, torch.int64)
+    view_pt_off = _dev_contig(view_pt_off, torch.int64)
+    cls = _dev_contig(cls, torch.int32)
+    cap = int(cls.shape[0]) if cap is None else int(cap)
+    L.check(L.lib().xm3d_vote_batch(_ptr(vis_idx), _ptr(seg_off), seg_off.numel() - 1, cap, _ptr(view_pt_off),
+                                    _ptr(cls), votes.shape[1], _ptr(votes), _ptr(counter), _stream()))
+
+
+def vote_argmax(votes: torch.Tensor, counter: torch.Tensor) -> torch.Tensor:
+    """torch.max(scene_pred, dim=1)[1] (run/infer.py:658); -1 where no view saw the point."""
+    _require_cuda()
+    pred = torch.empty(votes.shape[0], dtype=torch.int32, device=votes.device)
+    L.check(L.lib().xm3d_vote_argmax(_ptr(votes), _ptr(counter), votes.shape[0], votes.shape[1], _ptr(pred), _stream()))
+    return pred
