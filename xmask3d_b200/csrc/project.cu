@@ -77,35 +77,35 @@ __device__ __forceinline__ uint32_t project_exact(const double *vw, float fx_, f
 // Conservative float32 reject filter: true only when the exact arithmetic above is guaranteed to
 // give inside == false (behind the camera, or outside the cut image by more than 0.49 px beyond
 // every rounding error).  Everything else — including NaN / inf — goes to the exact path.
+// Error bound of a float32 camera coordinate p_i = sum_j a_ij x_j: coefficient rounding plus three
+// fused multiply-adds stay below 1e-6 * sum_j |a_ij| |x_j| (>= 8 ulp); |x_j| is bounded per work
+// item by the largest |coordinate| of the CTA's points (one shared-memory max per axis), so the
+// per-point cost is the three dot products and a handful of compares.
 struct FilterConst {
-    float a[12], aa[12];     // world->camera rows and their absolute values
+    float a[12];             // world->camera rows
     float fx, fy;
     float lx, hx, ly, hy;    // (cut - 0.51 - cx), (W - cut - 0.49 - cx), same for y
+    float e0, e1, e2;        // error bounds of the float32 camera coordinates for this work item
 };
 __device__ __forceinline__ bool surely_outside(const FilterConst &F, float x, float y, float z) {
-    const float GAM = 1.0e-6f;      // >= 8 ulp: coefficient rounding + three fused multiply-adds
-    const float ax = fabsf(x), ay = fabsf(y), az = fabsf(z);
     const float p2 = fmaf(F.a[8], x, fmaf(F.a[9], y, fmaf(F.a[10], z, F.a[11])));
-    const float e2 = GAM * fmaf(F.aa[8], ax, fmaf(F.aa[9], ay, fmaf(F.aa[10], az, F.aa[11])));
-    if (p2 + e2 <= 0.f) return true;                       // exact p2 <= 0: not in front
-    if (!(p2 - e2 > 1.0e-3f)) return false;                // too close to the z singularity: exact path
+    if (p2 + F.e2 <= 0.f) return true;                     // exact p2 <= 0: not in front
+    if (!(p2 - F.e2 > 1.0e-3f)) return false;              // too close to the z singularity: exact path
     const float p0 = fmaf(F.a[0], x, fmaf(F.a[1], y, fmaf(F.a[2], z, F.a[3])));
-    const float e0 = GAM * fmaf(F.aa[0], ax, fmaf(F.aa[1], ay, fmaf(F.aa[2], az, F.aa[3])));
     const float t = p0 * F.fx;
     {   // px < lo  <=>  p0*fx < (lo - cx) * z   (z > 0)
         const float u = F.lx * p2, v = F.hx * p2;
-        const float el = 2.f * (F.fx * e0 + fabsf(F.lx) * e2 + 4e-7f * (fabsf(t) + fabsf(u)));
-        const float eh = 2.f * (F.fx * e0 + fabsf(F.hx) * e2 + 4e-7f * (fabsf(t) + fabsf(v)));
+        const float el = 2.f * (F.fx * F.e0 + fabsf(F.lx) * F.e2 + 4e-7f * (fabsf(t) + fabsf(u)));
+        const float eh = 2.f * (F.fx * F.e0 + fabsf(F.hx) * F.e2 + 4e-7f * (fabsf(t) + fabsf(v)));
         if (t - u < -el) return true;
         if (t - v > eh) return true;
     }
     const float p1 = fmaf(F.a[4], x, fmaf(F.a[5], y, fmaf(F.a[6], z, F.a[7])));
-    const float e1 = GAM * fmaf(F.aa[4], ax, fmaf(F.aa[5], ay, fmaf(F.aa[6], az, F.aa[7])));
     const float s = p1 * F.fy;
     {
         const float u = F.ly * p2, v = F.hy * p2;
-        const float el = 2.f * (F.fy * e1 + fabsf(F.ly) * e2 + 4e-7f * (fabsf(s) + fabsf(u)));
-        const float eh = 2.f * (F.fy * e1 + fabsf(F.hy) * e2 + 4e-7f * (fabsf(s) + fabsf(v)));
+        const float el = 2.f * (F.fy * F.e1 + fabsf(F.ly) * F.e2 + 4e-7f * (fabsf(s) + fabsf(u)));
+        const float eh = 2.f * (F.fy * F.e1 + fabsf(F.hy) * F.e2 + 4e-7f * (fabsf(s) + fabsf(v)));
         if (s - u < -el) return true;
         if (s - v > eh) return true;
     }
@@ -120,6 +120,7 @@ __global__ void __launch_bounds__(PROJ_THREADS, 1) project_kernel(const ProjPara
     __shared__ uint64_t s_bar[2];
     __shared__ int s_warp_tot[PROJ_THREADS / 32];
     __shared__ int s_any;
+    __shared__ int s_amax[3];                        // max |x|, |y|, |z| of the item's points (float bits)
     uint32_t *s_code = reinterpret_cast<uint32_t *>(smem_raw + P.smem_depth_bytes);
     unsigned short *s_queue = reinterpret_cast<unsigned short *>(smem_raw + P.smem_depth_bytes + PROJ_PART * 4);
 
@@ -135,6 +136,7 @@ __global__ void __launch_bounds__(PROJ_THREADS, 1) project_kernel(const ProjPara
         mbar_init(&s_bar[1], 1);
         mbar_fence_init();
         s_any = 0;
+        s_amax[0] = s_amax[1] = s_amax[2] = 0;
     }
     int v = 0;
     {   // view of the first item: largest v with item_off[v] <= it0
@@ -210,9 +212,38 @@ __global__ void __launch_bounds__(PROJ_THREADS, 1) project_kernel(const ProjPara
             }
         }
     }
+    // largest |coordinate| per axis over the item's points (non-negative floats order like ints)
+    {
+        float mx = 0.f, my = 0.f, mz = 0.f;
+#pragma unroll
+        for (int g = 0; g < PROJ_GROUPS; ++g)
+#pragma unroll
+            for (int j = 0; j < PROJ_GROUP; ++j) {
+                mx = fmaxf(mx, fabsf(c[g][3 * j])); my = fmaxf(my, fabsf(c[g][3 * j + 1])); mz = fmaxf(mz, fabsf(c[g][3 * j + 2]));
+                // fmaxf drops NaNs: keep them so that a NaN coordinate disables the filter
+                if (!(c[g][3 * j] == c[g][3 * j]) || !(c[g][3 * j + 1] == c[g][3 * j + 1]) || !(c[g][3 * j + 2] == c[g][3 * j + 2]))
+                    mx = __int_as_float(0x7fc00000);
+            }
+        int ix = __float_as_int(mx), iy = __float_as_int(my), iz = __float_as_int(mz);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ix = max(ix, __shfl_xor_sync(0xffffffffu, ix, o));
+            iy = max(iy, __shfl_xor_sync(0xffffffffu, iy, o));
+            iz = max(iz, __shfl_xor_sync(0xffffffffu, iz, o));
+        }
+        if (lane == 0) { atomicMax(&s_amax[0], ix); atomicMax(&s_amax[1], iy); atomicMax(&s_amax[2], iz); }
+    }
+    __syncthreads();
     FilterConst F;
 #pragma unroll
-    for (int j = 0; j < 12; ++j) { F.a[j] = (float)s_view[j]; F.aa[j] = fabsf(F.a[j]); }
+    for (int j = 0; j < 12; ++j) F.a[j] = (float)s_view[j];
+    {
+        const float GAM = 1.0e-6f;
+        const float X = __int_as_float(s_amax[0]), Y = __int_as_float(s_amax[1]), Z = __int_as_float(s_amax[2]);
+        F.e0 = GAM * fmaf(fabsf(F.a[0]), X, fmaf(fabsf(F.a[1]), Y, fmaf(fabsf(F.a[2]), Z, fabsf(F.a[3]))));
+        F.e1 = GAM * fmaf(fabsf(F.a[4]), X, fmaf(fabsf(F.a[5]), Y, fmaf(fabsf(F.a[6]), Z, fabsf(F.a[7]))));
+        F.e2 = GAM * fmaf(fabsf(F.a[8]), X, fmaf(fabsf(F.a[9]), Y, fmaf(fabsf(F.a[10]), Z, fabsf(F.a[11]))));
+    }
     F.fx = fabsf((float)s_view[12]); F.fy = fabsf((float)s_view[13]);
     const bool filter_ok = s_view[12] > 0.0 && s_view[13] > 0.0;          // the inequalities assume fx, fy > 0
     F.lx = (float)(P.cut - 0.51 - s_view[14]); F.hx = (float)(P.img_w - P.cut - 0.49 - s_view[14]);
@@ -274,6 +305,7 @@ __global__ void __launch_bounds__(PROJ_THREADS, 1) project_kernel(const ProjPara
         if (tid == 0) {
             if (s_any) atomicOr(&P.view_flag[v], 1);
             s_any = 0;                               // ordered before the next item by its leading barrier
+            s_amax[0] = s_amax[1] = s_amax[2] = 0;
         }
         if (it + 1 < it1 && it + 1 >= P.item_off[v + 1]) ph ^= 1;      // next item starts a new view
         continue;
@@ -345,7 +377,10 @@ __global__ void __launch_bounds__(PROJ_THREADS, 1) project_kernel(const ProjPara
         running += s_any;
         __syncthreads();
     }
-    if (tid == 0) P.part_cnt[v * P.parts + part] = running;
+    if (tid == 0) {
+        P.part_cnt[v * P.parts + part] = running;
+        s_amax[0] = s_amax[1] = s_amax[2] = 0;
+    }
     if (it + 1 < it1 && it + 1 >= P.item_off[v + 1]) ph ^= 1;          // next item starts a new view
   }
 }
