@@ -106,9 +106,35 @@ pool_tileplan_kernel(const int64_t *__restrict__ seg_off, int n_seg, int64_t cap
 }
 
 // Per-warp member counts of one tile: s_wtot[warp][mask] (bytes, <= 32 each).  All threads call it.
+// `single`: every lane of the warp is in at most one mask (partition masks / labels) — warp-uniform.
+// Then one match.any groups the lanes by mask and replaces the per-mask ballot loop.
+template <int W>
+__device__ __forceinline__ bool warp_single_membership(const uint32_t (&b)[W]) {
+    int pc = 0;
+#pragma unroll
+    for (int w = 0; w < W; ++w) pc += __popc(b[w]);
+    return __all_sync(0xffffffffu, pc <= 1);
+}
+template <int W>
+__device__ __forceinline__ int single_mask_id(const uint32_t (&b)[W]) {      // -1: in no mask
+    int m = -1;
+#pragma unroll
+    for (int w = 0; w < W; ++w)
+        if (b[w]) m = w * 32 + __ffs(b[w]) - 1;
+    return m;
+}
+
 template <int W>
 __device__ __forceinline__ void tile_warp_counts(const uint32_t (&b)[W], uint32_t (&uni)[W],
                                                  unsigned char (*s_wtot)[32 * W], int warp, int lane) {
+    if (warp_single_membership<W>(b)) {
+        const int m = single_mask_id<W>(b);
+        const unsigned grp = __match_any_sync(0xffffffffu, m);
+        if (m >= 0 && lane == __ffs(grp) - 1) s_wtot[warp][m] = (unsigned char)__popc(grp);
+#pragma unroll
+        for (int w = 0; w < W; ++w) uni[w] = 0u;            // unused on this path
+        return;
+    }
 #pragma unroll
     for (int w = 0; w < W; ++w) {
         uni[w] = __reduce_or_sync(0xffffffffu, b[w]);
@@ -263,6 +289,12 @@ pool_fill_kernel(const PoolIdx P, const int32_t *__restrict__ tile_off, const in
     }
     __syncthreads();
     const int row = (i < e) ? (P.row_index ? __ldg(P.row_index + i) : (int)i) : 0;
+    if (warp_single_membership<W>(b)) {
+        const int m = single_mask_id<W>(b);
+        const unsigned grp = __match_any_sync(0xffffffffu, m);
+        if (m >= 0) perm[s_base[m] + s_wpre[warp][m] + __popc(grp & ((1u << lane) - 1u))] = row;
+        return;
+    }
 #pragma unroll
     for (int w = 0; w < W; ++w) {
         uint32_t u = uni[w];
