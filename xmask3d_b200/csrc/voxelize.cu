@@ -44,7 +44,8 @@ struct __align__(16) Slot {
     unsigned int rank;    // rank of the key among the segment's unique keys
 };
 
-__host__ __device__ inline int64_t table_size(int64_t n) { return n + n / 2 + 32; }
+// slots per segment table: load factor <= 0.67, an even number (slots are probed in aligned pairs)
+__host__ __device__ inline int64_t table_size(int64_t n) { return (n + n / 2 + 32) & ~(int64_t)1; }
 // buckets of a segment of n elements: power of two, about one per 8..16 elements
 __host__ __device__ inline int bucket_count(int64_t n) {
     int s = SPL_MIN;
@@ -338,18 +339,29 @@ vox_insert_kernel(const float *__restrict__ xyz, const unsigned long long *__res
     bool is_new = false;
     if (lane == leader) {
         Slot *tb = tbl + tbl_off[s];
-        const unsigned int size = (unsigned int)(tbl_off[s + 1] - tbl_off[s]);
-        slot = (unsigned int)(((mix64(key) >> 32) * (unsigned long long)size) >> 32);
-        for (unsigned int probe = 0; probe <= size; ++probe) {
-            // plain load first: a CAS on an occupied slot costs an L2 atomic round trip and was
-            // measured slower (0.59 vs 0.45 ms for the stage) than load + CAS-on-empty
-            unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(&tb[slot].key);
-            if (cur == KEY_EMPTY) {
-                cur = atomicCAS(&tb[slot].key, KEY_EMPTY, key);
-                if (cur == KEY_EMPTY) { is_new = true; break; }
+        const unsigned int npairs = (unsigned int)((tbl_off[s + 1] - tbl_off[s]) >> 1);
+        // Probe aligned PAIRS of slots: both keys sit in one 32-byte sector, so one round trip
+        // examines two slots.  Invariant: a key goes into the second slot of a pair only while the
+        // first is occupied, and slots never empty again — an empty first slot ends the search.
+        unsigned int pair = (unsigned int)(((mix64(key) >> 32) * (unsigned long long)npairs) >> 32);
+        for (unsigned int probe = 0; probe <= npairs; ++probe) {
+            Slot *p0 = tb + 2 * pair;
+            unsigned long long k0 = *reinterpret_cast<volatile unsigned long long *>(&p0[0].key);
+            unsigned long long k1 = *reinterpret_cast<volatile unsigned long long *>(&p0[1].key);
+            if (k0 == key) { slot = 2 * pair; break; }
+            if (k0 == KEY_EMPTY) {
+                k0 = atomicCAS(&p0[0].key, KEY_EMPTY, key);
+                if (k0 == KEY_EMPTY) { is_new = true; slot = 2 * pair; break; }
+                if (k0 == key) { slot = 2 * pair; break; }
+                k1 = *reinterpret_cast<volatile unsigned long long *>(&p0[1].key);   // lost the race: look again
             }
-            if (cur == key) break;
-            slot = (slot + 1 == size) ? 0u : slot + 1;
+            if (k1 == key) { slot = 2 * pair + 1; break; }
+            if (k1 == KEY_EMPTY) {
+                k1 = atomicCAS(&p0[1].key, KEY_EMPTY, key);
+                if (k1 == KEY_EMPTY) { is_new = true; slot = 2 * pair + 1; break; }
+                if (k1 == key) { slot = 2 * pair + 1; break; }
+            }
+            pair = (pair + 1 == npairs) ? 0u : pair + 1;
         }
     }
     slot = __shfl_sync(act, slot, leader);
