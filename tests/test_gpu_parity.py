@@ -608,3 +608,61 @@ def test_vote_accumulation(cport, dev):
     seen = ref_cnt > 0
     assert np.array_equal(pred[seen], P.vote_argmax(ref_votes)[seen]) and np.all(pred[~seen] == -1)
     assert seen.sum() > 10_000 and ref_cnt.max() >= 3
+
+
+# ----------------------------------------------------------------------------- training drop-in
+def test_autograd_wrappers(dev):
+    """Gradients of cal_pred_logits and mask_mapper's scatter-mean against plain torch autograd of
+    the reference formulas (float32; tolerance 1e-4 relative to the gradient's largest entry)."""
+    import torch.nn.functional as F
+    from xmask3d_b200.fuser import mask_mapper
+    from xmask3d_b200.logits import cal_pred_logits
+    g = torch.Generator(device=dev).manual_seed(2)
+    me = torch.randn(2, 11, 64, device=dev, generator=g, requires_grad=True)
+    te = torch.randn(7, 64, device=dev, generator=g, requires_grad=True)
+    ne = torch.randn(1, 64, device=dev, generator=g, requires_grad=True)
+    ls = torch.tensor(14.2857, device=dev, requires_grad=True)
+    labels = [["a"], ["b", "c"], ["d"], ["e", "f", "g"]]
+    w = torch.randn(2, 11, 5, device=dev, generator=g)
+    out = cal_pred_logits({"mask_embed": me, "text_embed": te, "null_embed": ne, "labels": labels, "logit_scale": ls})
+    (out * w).sum().backward()
+    got = [t.grad.clone() for t in (me, te, ne, ls)]
+    for t in (me, te, ne, ls):
+        t.grad = None
+    m = F.normalize(me, dim=-1)
+    pred = ls * (m @ F.normalize(te, dim=-1).t())
+    ref = torch.cat([torch.stack([p.max(-1).values for p in torch.split(pred, [1, 2, 1, 3], -1)], -1),
+                     ls * (m @ F.normalize(ne, dim=-1).t())], -1)
+    assert float((out - ref).abs().max()) < 1e-4
+    (ref * w).sum().backward()
+    for a, t in zip(got, (me, te, ne, ls)):
+        assert float((a - t.grad).abs().max()) <= 1e-4 * max(1.0, float(t.grad.abs().max()))
+    # scatter-mean inside mask_mapper
+    k, h, wd, n, c = 6, 24, 32, 500, 16
+    rngs = np.random.default_rng(4)
+    xl, yl = torch.from_numpy(rngs.integers(0, h, n)), torch.from_numpy(rngs.integers(0, wd, n))
+    masks = (torch.rand(k, h, wd, device=dev, generator=g) > 0.7).float()
+    emb = torch.randn(k, c, device=dev, generator=g, requires_grad=True)
+    pred3d = torch.randn(n, c, device=dev, generator=g)
+
+    class Cfg:
+        caption_contra_2d_pre = False
+    wt = torch.randn(n, c, device=dev, generator=g)
+    fused, f2d, _, _ = mask_mapper([xl], [yl], [masks], [emb], [pred3d], lambda a, b: a * 2 + b, lambda a: a, lambda a: a, Cfg)
+    ((fused[0] + f2d[0]) * wt).sum().backward()
+    got = emb.grad.clone()
+    emb.grad = None
+    member = masks[:, xl.to(dev), yl.to(dev)] >= 0.5                           # reference loop, differentiable
+    feat = torch.zeros(n, c, device=dev)
+    cnt = torch.zeros(n, 1, device=dev)
+    for mk, e in zip(member, emb):
+        if mk.sum() == 0:
+            continue
+        feat = feat + mk.unsqueeze(1).float() * e
+        cnt = cnt + mk.unsqueeze(1).float()
+    cnt = torch.where(cnt == 0, torch.full_like(cnt, 1e-5), cnt)
+    feat = feat / cnt
+    cov = cnt.squeeze(1) >= 1
+    final = torch.where(cov.unsqueeze(1), feat * 2 + pred3d, pred3d)
+    ((final + feat) * wt).sum().backward()
+    assert float((got - emb.grad).abs().max()) <= 1e-4 * float(emb.grad.abs().max())

@@ -3,9 +3,9 @@ models/xmask3d.py:405-473): mask-at-point gather, threshold, mask -> point scatt
 
 The gather / threshold / scatter-mean run on libxm3d for all scenes of the batch in three
 launches; the learned layers (`fuser`, `fc1`, `fc2`) stay the caller's torch modules.  The
-scatter-mean output is bit-identical to the reference loop (same float32 op order).  The fused
-kernels do not record autograd history: this is the inference / no-grad path (the reference's
-training use needs grads w.r.t. mask_embed, out of scope here — see DESIGN.md).
+scatter-mean output is bit-identical to the reference loop (same float32 op order).  When
+mask_embed requires grad the scatter-mean goes through `autograd.scatter_mean`, whose backward is
+the segmented pooling kernel (gradients w.r.t. mask_embed as in the reference's training loop).
 """
 from __future__ import annotations
 
@@ -42,7 +42,11 @@ def mask_mapper(x_list, y_list, masks, mask_embeds, pred_3ds, fuser, fc1, fc2, c
             member[int(seg[s]), 0] |= 1
     emb = mask_embeds if torch.is_tensor(mask_embeds) else torch.stack(list(mask_embeds))
     total = int(seg[-1])
-    feat2d_all, counter_all = ops.scatter(emb.detach(), seg_d, total, member=member)
+    if torch.is_grad_enabled() and emb.requires_grad:
+        from .autograd import scatter_mean                  # training: gradients flow to mask_embed
+        feat2d_all, counter_all = scatter_mean(emb, seg_d, member, total)
+    else:
+        feat2d_all, counter_all = ops.scatter(emb, seg_d, total, member=member)
 
     output, output_2d, output_3d, output_2d_pre = [], [], [], []
     for s in range(b):

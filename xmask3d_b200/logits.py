@@ -30,7 +30,14 @@ def cal_pred_logits(outputs, ensemble_method: str = "max", want_argmax: bool = F
     """outputs: dict with mask_embed [B,K,C], text_embed [T-1,C], null_embed [1,C], labels
     (list of synonym lists), logit_scale (tensor or float).  Returns [B,K,T] float32."""
     scale = outputs["logit_scale"]
-    scale = float(scale.item()) if torch.is_tensor(scale) else float(scale)
     sizes = [len(l) for l in outputs["labels"]]
+    needs_grad = torch.is_grad_enabled() and any(
+        torch.is_tensor(t) and t.requires_grad
+        for t in (outputs["mask_embed"], outputs["text_embed"], outputs["null_embed"], scale))
+    if needs_grad and not want_argmax:
+        from .autograd import pred_logits
+        return pred_logits(outputs["mask_embed"], outputs["text_embed"], outputs["null_embed"], scale, sizes,
+                           ensemble_method)
+    scale = float(scale.item()) if torch.is_tensor(scale) else float(scale)
     return ops.logits(outputs["mask_embed"], outputs["text_embed"], outputs["null_embed"], sizes, scale,
                       ensemble=ensemble_method, want_argmax=want_argmax)
