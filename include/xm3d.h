@@ -207,6 +207,19 @@ XM3D_API int xm3d_logits(const float *mask_embed, int64_t rows, int32_t c, const
                 int32_t n_groups, int32_t ensemble_mean, float logit_scale, float *out,
                 int32_t *argmax, void *ws, size_t ws_bytes, xm3d_stream_t stream);
 
+/* ------------------------------------------------------------------ after the path: per-point logits
+ * logit_scale * (normalize(feat) @ normalize(text_embed).T) for every point, optional base / novel
+ * blending with the binary head and argmax (run/infer.py:557, 606-640; models/utils/criterion.py:184-207):
+ *   val[i,t] = scale * <feat_i/|feat_i|, text_t/|text_t|>
+ *   binary given:  val[i,t] = b_i * (is_base[t] ? val : -1e10) + (1 - b_i) * (is_base[t] ? -1e10 : val)
+ *   out [rows, n_text] float32 (optional), argmax int32 [rows] (optional, first maximum)
+ * feat [rows, c] float32 is read from HBM once (TMA -> in-place TF32 hi/lo split in shared memory ->
+ * tcgen05 3xTF32); n_text <= 256, c % 4 == 0, feat 16-byte aligned. */
+XM3D_API size_t xm3d_point_logits_ws_bytes(int32_t n_text, int32_t c);
+XM3D_API int xm3d_point_logits(const float *feat, int64_t rows, int32_t c, const float *text_embed, int32_t n_text,
+                      float logit_scale, const float *binary, const uint8_t *is_base, float *out,
+                      int32_t *argmax, void *ws, size_t ws_bytes, xm3d_stream_t stream);
+
 /* ------------------------------------------------------------------ after the path: votes
  * Cross-view vote accumulation of the inference loop (run/infer.py:642-647, :658), batched:
  *   votes[p, cls[j]] += 1, counter[p] += 1   for every visible pair j, p = view_pt_off[seg(j)] + vis_idx[j]

@@ -666,3 +666,38 @@ def test_autograd_wrappers(dev):
     final = torch.where(cov.unsqueeze(1), feat * 2 + pred3d, pred3d)
     ((final + feat) * wt).sum().backward()
     assert float((got - emb.grad).abs().max()) <= 1e-4 * float(emb.grad.abs().max())
+
+
+def test_point_logits_vs_torch(dev):
+    """Per-point logits / base-novel blend / argmax (run/infer.py:557, 606-640) against float64 torch."""
+    import torch.nn.functional as F
+    from xmask3d_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(9)
+    for n, t, c in ((40_000, 19, 768), (1000, 200, 768), (129, 7, 100), (1, 3, 64)):
+        feat = torch.randn(n, c, device=dev, generator=g) * 3
+        te = torch.randn(t, c, device=dev, generator=g)
+        ref = (1 / 0.07) * (F.normalize(feat.double(), dim=-1) @ F.normalize(te.double(), dim=-1).t())
+        out, amax = ops.point_logits(feat, te, 1 / 0.07)
+        assert out.shape == (n, t)
+        assert float((out.double() - ref).abs().max()) < 2e-5 * float(ref.abs().max())
+        top2 = ref.topk(min(2, t), -1).values
+        clear = (top2[:, 0] - top2[:, -1]) > 1e-4 if t > 1 else torch.ones(n, dtype=torch.bool, device=dev)
+        assert torch.equal(amax.long()[clear], ref.argmax(-1)[clear])
+        # base / novel blending with the binary head
+        binary = (torch.rand(n, device=dev, generator=g) > 0.5).float()
+        is_base = torch.rand(t, device=dev, generator=g) > 0.4
+        out_b, amax_b = ops.point_logits(feat, te, 1 / 0.07, binary=binary, is_base=is_base)
+        novel = ref.clone(); novel[:, is_base] = -1e10
+        base = ref.clone(); base[:, ~is_base] = -1e10
+        ref_b = binary.double().unsqueeze(1) * base + (1 - binary.double().unsqueeze(1)) * novel
+        live = ref_b > -1e9
+        assert float((out_b.double() - ref_b)[live].abs().max() if live.any() else 0.0) < 2e-5 * float(ref.abs().max())
+        assert bool(((out_b < -1e9) == ~live).all())
+        ok = live.any(1)
+        rb = ref_b.clone()
+        t2 = rb.topk(min(2, t), -1).values
+        clear_b = ok & (((t2[:, 0] - t2[:, -1]) > 1e-4) if t > 1 else ok)
+        assert torch.equal(amax_b.long()[clear_b], rb.argmax(-1)[clear_b])
+        # argmax-only call (no [n,T] write)
+        none, amax2 = ops.point_logits(feat, te, 1 / 0.07, want_logits=False)
+        assert none is None and torch.equal(amax2, amax)

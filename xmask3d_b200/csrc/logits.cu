@@ -281,6 +281,207 @@ static LogitsWs carve_logits(void *ws, int64_t rows, int n_cols, int c, int n_gr
     return w;
 }
 
+// ============================================================================================
+// Per-point logits: logit_scale * (normalize(feature) @ normalize(text).T) for
+// every visible point, base / novel blending with the binary head and argmax — the pattern of
+// run/infer.py:557, 606-640 (and loss_exact, models/utils/criterion.py:184-207).
+//
+// The [n, C] float32 features are read from HBM exactly once: TMA brings raw 128 x 32 tiles into
+// shared memory, four converter warps split every tile in place into its TF32-exact hi / lo tiles
+// (the split is elementwise, so the 128-byte swizzle written by TMA carries over unchanged) and
+// accumulate the row norms on the way; one thread issues the 3xTF32 tcgen05.mma chain into TMEM;
+// the converter warps then run the epilogue (normalise, scale, blend, argmax).
+constexpr int PL_THREADS = 192;
+
+struct PointLogitsParams {
+    int64_t rows;
+    int c, n_text, bn, stages, tmem_cols;
+    float scale;
+    const float *inv_norm_b;     // [n_text]
+    const float *binary;         // [rows] or null
+    const unsigned char *is_base;// [n_text] or null (required with binary)
+    float *out;                  // [rows, n_text] or null
+    int *argmax;                 // [rows] or null
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(PL_THREADS, 1)
+point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b_hi,
+                    const __grid_constant__ CUtensorMap map_b_lo, const PointLogitsParams P) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ uint64_t s_raw[4], s_conv[4], s_empty[4], s_done;
+    __shared__ uint32_t s_tmem;
+    __shared__ float s_invb[LG_MAX_N];
+    __shared__ unsigned char s_base[LG_MAX_N];
+    __shared__ float s_ss[LG_BM];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t m0 = (int64_t)blockIdx.x * LG_BM;
+    const int nkb = (P.c + LG_BK - 1) / LG_BK;
+    const uint32_t a_bytes = LG_BM * LG_BK * 4, b_bytes = (uint32_t)P.bn * LG_BK * 4;
+    const uint32_t stage_bytes = 3 * a_bytes + 2 * b_bytes;       // raw, hi, lo, B hi, B lo
+    unsigned char *tiles = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
+
+    for (int j = tid; j < LG_MAX_N; j += PL_THREADS) {
+        s_invb[j] = j < P.n_text ? P.inv_norm_b[j] : 0.f;
+        s_base[j] = (j < P.n_text && P.is_base) ? P.is_base[j] : 0;
+    }
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < P.stages; ++s) {
+            mbar_init(&s_raw[s], 1);
+            mbar_init(&s_conv[s], 128);
+            mbar_init(&s_empty[s], 1);
+        }
+        mbar_init(&s_done, 1);
+        mbar_fence_init();
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a));
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_hi));
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_lo));
+    }
+    if (warp == 1) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(&s_tmem)), "r"((uint32_t)P.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = s_tmem;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(&s_empty[stage], phase ^ 1);
+                unsigned char *st = tiles + (size_t)stage * stage_bytes;
+                mbar_expect_tx(&s_raw[stage], a_bytes + 2 * b_bytes);
+                tma_load_2d(st, &map_a, kb * LG_BK, (int)m0, &s_raw[stage]);
+                tma_load_2d(st + 3 * a_bytes, &map_b_hi, kb * LG_BK, 0, &s_raw[stage]);
+                tma_load_2d(st + 3 * a_bytes + b_bytes, &map_b_lo, kb * LG_BK, 0, &s_raw[stage]);
+                if (++stage == P.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(P.bn >> 3) << 17) |
+                                   ((uint32_t)(LG_BM >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(&s_raw[stage], phase);                 // B tiles landed (async proxy)
+                mbar_wait(&s_conv[stage], phase);                // hi / lo tiles written and fenced
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                unsigned char *st = tiles + (size_t)stage * stage_bytes;
+                const uint64_t a_hi = make_sw128_desc(st + a_bytes), a_lo = make_sw128_desc(st + 2 * a_bytes);
+                const uint64_t b_hi = make_sw128_desc(st + 3 * a_bytes), b_lo = make_sw128_desc(st + 3 * a_bytes + b_bytes);
+#pragma unroll
+                for (int k = 0; k < LG_BK / LG_UMMA_K; ++k) {
+                    const uint64_t adv = (uint64_t)((k * LG_UMMA_K * 4) >> 4);
+                    umma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, (kb | k) ? 1u : 0u);
+                    umma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
+                    umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, 1u);
+                }
+                umma_commit(&s_empty[stage]);
+                if (++stage == P.stages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(&s_done);
+        }
+    } else {
+        // ===== converter warps (then epilogue): 128 threads, thread t owns 16-byte chunks t + 128 j =====
+        const int t = tid - 64;
+        float ss[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ss[j] = 0.f;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(&s_raw[stage], phase);
+            unsigned char *st = tiles + (size_t)stage * stage_bytes;
+            const uint4 *raw = reinterpret_cast<const uint4 *>(st);
+            uint4 *hi = reinterpret_cast<uint4 *>(st + a_bytes), *lo = reinterpret_cast<uint4 *>(st + 2 * a_bytes);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int q = t + 128 * j;                        // chunk q lies in row q >> 3 (any swizzle)
+                const uint4 v = raw[q];
+                uint4 h, l;
+                const uint32_t in[4] = {v.x, v.y, v.z, v.w};
+                uint32_t ho[4], lw[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float x = __uint_as_float(in[e]);
+                    ho[e] = in[e] & 0xffffe000u;
+                    lw[e] = __float_as_uint(__fsub_rn(x, __uint_as_float(ho[e]))) & 0xffffe000u;
+                    ss[j] = fmaf(x, x, ss[j]);
+                }
+                h = make_uint4(ho[0], ho[1], ho[2], ho[3]);
+                l = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                hi[q] = h;
+                lo[q] = l;
+            }
+            // generic-proxy writes -> visible to the tensor core's async proxy, then signal
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(&s_conv[stage]);
+            if (++stage == P.stages) { stage = 0; phase ^= 1; }
+        }
+        // row sums of squares: the 8 chunks of a row sit in 8 consecutive threads
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float v = ss[j];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            if ((t & 7) == 0) s_ss[(t >> 3) + 16 * j] = v;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");            // converter warps only
+
+        mbar_wait(&s_done, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int lg = warp & 3;                                   // TMEM lane group of this warp
+        const int rloc = lg * 32 + lane;
+        const int64_t r = m0 + rloc;
+        const bool row_ok = r < P.rows;
+        const float inv_a = __fdiv_rn(1.0f, fmaxf(sqrtf(s_ss[rloc]), 1e-12f));      // F.normalize
+        const float b = (row_ok && P.binary) ? P.binary[r] : 0.f;
+        const bool blend = P.binary != nullptr;
+        float best = -INFINITY;
+        int best_i = 0;
+        for (int c0 = 0; c0 < P.bn; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int col = c0 + j;
+                if (col < P.n_text) {
+                    float val = P.scale * ((__uint_as_float(v[j]) * inv_a) * s_invb[col]);
+                    if (blend) {
+                        // binary * logits_base + (1 - binary) * logits_novel, masked entries = -1e10
+                        const float lb = s_base[col] ? val : -1e10f, ln = s_base[col] ? -1e10f : val;
+                        val = __fadd_rn(__fmul_rn(b, lb), __fmul_rn(__fsub_rn(1.0f, b), ln));
+                    }
+                    if (row_ok && P.out) P.out[r * P.n_text + col] = val;
+                    if (val > best) { best = val; best_i = col; }
+                }
+            }
+        }
+        if (row_ok && P.argmax) P.argmax[r] = best_i;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        __syncwarp();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)P.tmem_cols)
+                     : "memory");
+    }
+}
+
 }  // namespace xm3d
 
 using namespace xm3d;
@@ -348,4 +549,63 @@ extern "C" int xm3d_logits(const float *mask_embed, int64_t rows, int32_t c, con
     }
     logits_mma_kernel<<<(unsigned)((rows + LG_BM - 1) / LG_BM), LG_THREADS, smem, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, P); count_launches(1);
     return check_launch("xm3d_logits");
+}
+
+extern "C" size_t xm3d_point_logits_ws_bytes(int32_t n_text, int32_t c) {
+    Carver cv(nullptr);
+    cv.take<float>((size_t)n_text * c);
+    cv.take<float>((size_t)n_text * c);
+    cv.take<float>((size_t)n_text);
+    return cv.off + 256;
+}
+
+extern "C" int xm3d_point_logits(const float *feat, int64_t rows, int32_t c, const float *text_embed, int32_t n_text,
+                                 float logit_scale, const float *binary, const uint8_t *is_base, float *out,
+                                 int32_t *argmax, void *ws, size_t ws_bytes, xm3d_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    XM3D_REQUIRE(rows >= 0 && c > 0 && n_text > 0, "bad sizes");
+    XM3D_REQUIRE(c % 4 == 0, "feature width must be a multiple of 4");
+    XM3D_REQUIRE(n_text <= LG_MAX_N, "at most 256 classes");
+    XM3D_REQUIRE(feat && text_embed && ws && (out || argmax), "null pointer");
+    XM3D_REQUIRE(!binary || is_base, "is_base is required with binary");
+    XM3D_REQUIRE(rows < ((int64_t)1 << 31) - LG_BM, "rows exceed int32 tile coordinates");
+    XM3D_REQUIRE(reinterpret_cast<uintptr_t>(feat) % 16 == 0, "feat must be 16-byte aligned");
+    if (rows == 0) return XM3D_OK;
+    if (ws_bytes < xm3d_point_logits_ws_bytes(n_text, c)) {
+        set_error("xm3d_point_logits: workspace too small");
+        return XM3D_ERR_WORKSPACE;
+    }
+    Carver cv(ws);
+    float *b_hi = cv.take<float>((size_t)n_text * c);
+    float *b_lo = cv.take<float>((size_t)n_text * c);
+    float *inv_b = cv.take<float>((size_t)n_text);
+    logits_prep_kernel<<<(unsigned)((n_text + 7) / 8), 256, 0, stream>>>(text_embed, nullptr, n_text, 0, c, b_hi, b_lo, inv_b);
+    count_launches(1);
+
+    PointLogitsParams P;
+    P.rows = rows; P.c = c; P.n_text = n_text; P.bn = (n_text + 15) / 16 * 16; P.scale = logit_scale;
+    P.inv_norm_b = inv_b; P.binary = binary; P.is_base = is_base; P.out = out; P.argmax = argmax;
+    int tc = 32;
+    while (tc < P.bn) tc <<= 1;
+    P.tmem_cols = tc;
+    const size_t stage_bytes = 3 * (size_t)LG_BM * LG_BK * 4 + 2 * (size_t)P.bn * LG_BK * 4;
+    int stages = (int)((220 * 1024) / stage_bytes);
+    if (stages > 4) stages = 4;
+    if (stages < 1) { set_error("xm3d_point_logits: tile does not fit shared memory"); return XM3D_ERR_UNSUPPORTED; }
+    P.stages = stages;
+    CUtensorMap ma, mbh, mbl;
+    if (!make_map(&ma, feat, rows, c, LG_BM) || !make_map(&mbh, b_hi, n_text, c, P.bn) ||
+        !make_map(&mbl, b_lo, n_text, c, P.bn)) {
+        set_error("xm3d_point_logits: cuTensorMapEncodeTiled failed");
+        return XM3D_ERR_CUDA;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(point_logits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+        attr_set = true;
+    }
+    point_logits_kernel<<<(unsigned)((rows + LG_BM - 1) / LG_BM), PL_THREADS, stage_bytes * stages + 1024, stream>>>(ma, mbh,
+                                                                                                                 mbl, P);
+    count_launches(1);
+    return check_launch("xm3d_point_logits");
 }

@@ -350,6 +350,31 @@ def logits(mask_embed: torch.Tensor, text_embed: torch.Tensor, null_embed: torch
 
 
 # ----------------------------------------------------------------------------- after the path
+def point_logits(feat: torch.Tensor, text_embed: torch.Tensor, logit_scale: float,
+                 binary: Optional[torch.Tensor] = None, is_base: Optional[torch.Tensor] = None,
+                 want_logits: bool = True, want_argmax: bool = True):
+    """Per-point logits / argmax (run/infer.py:557, 606-640).  feat [n,c] float32 CUDA, text_embed
+    [T,c]; binary [n] float32 (the binary head's 0/1 prediction) with is_base [T] bool selects the
+    base / novel blending.  Returns (logits [n,T] or None, argmax int32 [n] or None)."""
+    _require_cuda()
+    dev = feat.device
+    feat = _dev_contig(feat, torch.float32)
+    te = _dev_contig(text_embed, torch.float32)
+    n, c = feat.shape
+    t = te.shape[0]
+    if binary is not None:
+        binary = _dev_contig(binary.reshape(-1), torch.float32)
+        is_base = _dev_contig(is_base.reshape(-1).to(torch.uint8), torch.uint8)
+        assert binary.numel() == n and is_base.numel() == t
+    out = torch.empty((n, t), dtype=torch.float32, device=dev) if want_logits else None
+    amax = torch.empty(max(n, 1), dtype=torch.int32, device=dev) if want_argmax else None
+    ws = _ws(L.lib().xm3d_point_logits_ws_bytes(t, c), dev)
+    L.check(L.lib().xm3d_point_logits(_ptr(feat), n, c, _ptr(te), t, float(logit_scale), _ptr(binary), _ptr(is_base),
+                                      _ptr(out), _ptr(amax), _ptr(ws), ws.numel(), _stream()))
+    return out, (amax[:n] if amax is not None else None)
+
+
+
 def accumulate_votes(vis_idx: torch.Tensor, seg_off: torch.Tensor, view_pt_off: torch.Tensor, cls: torch.Tensor,
                      votes: torch.Tensor, counter: torch.Tensor, cap: Optional[int] = None):
     """scene_pred[mask_2d, logits_pred] += 1; counter[mask_2d] += 1 (run/infer.py:642-647) for all
