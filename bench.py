@@ -492,9 +492,10 @@ def run_native(args, rank: int, world: int, local_rank: int):
     logits_info = {}
     try:
         from xmask3d_b200 import ops as _ops
-        peaks_tf = 1678.5
+        peaks_tf, peak_hbm = 1678.5, 6650.0
         if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
-            peaks_tf = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops", peaks_tf))
+            _pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            peaks_tf, peak_hbm = float(_pk.get("bf16_tflops", peaks_tf)), float(_pk.get("hbm_gbs", peak_hbm))
         gl = torch.Generator(device=dev).manual_seed(1)
         for name, rows, t in (("configs[1] B15N4 160x50 masks x 20 classes", 160 * 50, 20),
                               ("configs[2] B170N30 160x100 masks x 201 classes", 160 * 100, 201)):
@@ -515,6 +516,24 @@ def run_native(args, rank: int, world: int, local_rank: int):
                                  "mma_tflops_3xtf32": 3 * fl / (ms_l * 1e-3) / 1e12,
                                  "frac_of_bf16_peak": 3 * fl / (ms_l * 1e-3) / 1e12 / peaks_tf,
                                  "note": "prep + tcgen05 GEMM + epilogue; <= 5 GFLOP, launch/latency bound by construction"}
+        # per-point logits: the visible points' features (the pooling input) x text
+        # embeddings, argmax only — the [n, C] features are read from HBM once
+        for name, t in (("per-point argmax, 19 classes", 19), ("per-point argmax, 200 classes", 200)):
+            te = torch.randn(t, args.c, device=dev, generator=gl)
+            for _ in range(2):
+                _ops.point_logits(feat, te, 1 / 0.07, want_logits=False)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(5):
+                _ops.point_logits(feat, te, 1 / 0.07, want_logits=False)
+            e1.record()
+            torch.cuda.synchronize()
+            ms_l = e0.elapsed_time(e1) / 5
+            fl = 2.0 * total_vis * args.c * t
+            logits_info[name] = {"ms": ms_l, "rows": total_vis, "feature_gbs": 4.0 * args.c * total_vis / (ms_l * 1e-3) / 1e9,
+                                 "frac_of_hbm_peak": 4.0 * args.c * total_vis / (ms_l * 1e-3) / 1e9 / peak_hbm,
+                                 "useful_tflops": fl / (ms_l * 1e-3) / 1e12,
+                                 "mma_tflops_3xtf32": 3 * fl / (ms_l * 1e-3) / 1e12}
     except Exception as e:                      # noqa: BLE001
         logits_info = {"error": f"{type(e).__name__}: {e}"[:200]}
 

@@ -291,7 +291,10 @@ static LogitsWs carve_logits(void *ws, int64_t rows, int n_cols, int c, int n_gr
 // (the split is elementwise, so the 128-byte swizzle written by TMA carries over unchanged) and
 // accumulate the row norms on the way; one thread issues the 3xTF32 tcgen05.mma chain into TMEM;
 // the converter warps then run the epilogue (normalise, scale, blend, argmax).
-constexpr int PL_THREADS = 192;
+constexpr int PL_CONV_WARPS = 4;                 // converter warps (the first four also run the epilogue)
+constexpr int PL_CONV = PL_CONV_WARPS * 32;
+constexpr int PL_CHUNKS = LG_BM * LG_BK * 4 / 16 / PL_CONV;    // 16-byte chunks per converter thread and k-block
+constexpr int PL_THREADS = 64 + PL_CONV;
 
 struct PointLogitsParams {
     int64_t rows;
@@ -308,7 +311,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-__global__ void __launch_bounds__(PL_THREADS, 1)
+__global__ void __launch_bounds__(PL_THREADS, 2)
 point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b_hi,
                     const __grid_constant__ CUtensorMap map_b_lo, const PointLogitsParams P) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -322,7 +325,7 @@ point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const int64_t m0 = (int64_t)blockIdx.x * LG_BM;
     const int nkb = (P.c + LG_BK - 1) / LG_BK;
     const uint32_t a_bytes = LG_BM * LG_BK * 4, b_bytes = (uint32_t)P.bn * LG_BK * 4;
-    const uint32_t stage_bytes = 3 * a_bytes + 2 * b_bytes;       // raw, hi, lo, B hi, B lo
+    const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;       // A raw -> hi (in place), A lo, B hi, B lo
     unsigned char *tiles = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
 
     for (int j = tid; j < LG_MAX_N; j += PL_THREADS) {
@@ -332,7 +335,7 @@ point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < P.stages; ++s) {
             mbar_init(&s_raw[s], 1);
-            mbar_init(&s_conv[s], 128);
+            mbar_init(&s_conv[s], PL_CONV);
             mbar_init(&s_empty[s], 1);
         }
         mbar_init(&s_done, 1);
@@ -362,8 +365,8 @@ point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 unsigned char *st = tiles + (size_t)stage * stage_bytes;
                 mbar_expect_tx(&s_raw[stage], a_bytes + 2 * b_bytes);
                 tma_load_2d(st, &map_a, kb * LG_BK, (int)m0, &s_raw[stage]);
-                tma_load_2d(st + 3 * a_bytes, &map_b_hi, kb * LG_BK, 0, &s_raw[stage]);
-                tma_load_2d(st + 3 * a_bytes + b_bytes, &map_b_lo, kb * LG_BK, 0, &s_raw[stage]);
+                tma_load_2d(st + 2 * a_bytes, &map_b_hi, kb * LG_BK, 0, &s_raw[stage]);
+                tma_load_2d(st + 2 * a_bytes + b_bytes, &map_b_lo, kb * LG_BK, 0, &s_raw[stage]);
                 if (++stage == P.stages) { stage = 0; phase ^= 1; }
             }
         }
@@ -379,8 +382,8 @@ point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 mbar_wait(&s_conv[stage], phase);                // hi / lo tiles written and fenced
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 unsigned char *st = tiles + (size_t)stage * stage_bytes;
-                const uint64_t a_hi = make_sw128_desc(st + a_bytes), a_lo = make_sw128_desc(st + 2 * a_bytes);
-                const uint64_t b_hi = make_sw128_desc(st + 3 * a_bytes), b_lo = make_sw128_desc(st + 3 * a_bytes + b_bytes);
+                const uint64_t a_hi = make_sw128_desc(st), a_lo = make_sw128_desc(st + a_bytes);
+                const uint64_t b_hi = make_sw128_desc(st + 2 * a_bytes), b_lo = make_sw128_desc(st + 2 * a_bytes + b_bytes);
 #pragma unroll
                 for (int k = 0; k < LG_BK / LG_UMMA_K; ++k) {
                     const uint64_t adv = (uint64_t)((k * LG_UMMA_K * 4) >> 4);
@@ -394,21 +397,21 @@ point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             umma_commit(&s_done);
         }
     } else {
-        // ===== converter warps (then epilogue): 128 threads, thread t owns 16-byte chunks t + 128 j =====
+        // ===== converter warps (then epilogue): thread t owns the 16-byte chunks t + PL_CONV * j =====
         const int t = tid - 64;
-        float ss[8];
+        float ss[PL_CHUNKS];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) ss[j] = 0.f;
+        for (int j = 0; j < PL_CHUNKS; ++j) ss[j] = 0.f;
         int stage = 0;
         uint32_t phase = 0;
         for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait(&s_raw[stage], phase);
             unsigned char *st = tiles + (size_t)stage * stage_bytes;
-            const uint4 *raw = reinterpret_cast<const uint4 *>(st);
-            uint4 *hi = reinterpret_cast<uint4 *>(st + a_bytes), *lo = reinterpret_cast<uint4 *>(st + 2 * a_bytes);
+            uint4 *raw = reinterpret_cast<uint4 *>(st);             // overwritten in place by its hi part
+            uint4 *hi = raw, *lo = reinterpret_cast<uint4 *>(st + a_bytes);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int q = t + 128 * j;                        // chunk q lies in row q >> 3 (any swizzle)
+            for (int j = 0; j < PL_CHUNKS; ++j) {
+                const int q = t + PL_CONV * j;                    // chunk q lies in row q >> 3 (any swizzle)
                 const uint4 v = raw[q];
                 uint4 h, l;
                 const uint32_t in[4] = {v.x, v.y, v.z, v.w};
@@ -432,15 +435,15 @@ point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         }
         // row sums of squares: the 8 chunks of a row sit in 8 consecutive threads
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < PL_CHUNKS; ++j) {
             float v = ss[j];
             v += __shfl_xor_sync(0xffffffffu, v, 1);
             v += __shfl_xor_sync(0xffffffffu, v, 2);
             v += __shfl_xor_sync(0xffffffffu, v, 4);
-            if ((t & 7) == 0) s_ss[(t >> 3) + 16 * j] = v;
+            if ((t & 7) == 0) s_ss[(t >> 3) + (PL_CONV / 8) * j] = v;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");            // converter warps only
-
+        asm volatile("bar.sync 1, %0;" ::"n"(PL_CONV) : "memory");   // converter warps only
+      if (warp < 6) {                                              // four epilogue warps: TMEM lane groups 2,3,0,1
         mbar_wait(&s_done, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int lg = warp & 3;                                   // TMEM lane group of this warp
@@ -471,6 +474,7 @@ point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
         }
         if (row_ok && P.argmax) P.argmax[r] = best_i;
+      }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -588,8 +592,11 @@ extern "C" int xm3d_point_logits(const float *feat, int64_t rows, int32_t c, con
     int tc = 32;
     while (tc < P.bn) tc <<= 1;
     P.tmem_cols = tc;
-    const size_t stage_bytes = 3 * (size_t)LG_BM * LG_BK * 4 + 2 * (size_t)P.bn * LG_BK * 4;
-    int stages = (int)((220 * 1024) / stage_bytes);
+    const size_t stage_bytes = 2 * (size_t)LG_BM * LG_BK * 4 + 2 * (size_t)P.bn * LG_BK * 4;
+    // two CTAs per SM when two stages of each fit (the second CTA's TMA / MMA hides the first one's
+    // conversion pass), else one CTA with as many stages as fit
+    int stages = (int)((108 * 1024) / stage_bytes);
+    if (stages < 2) stages = (int)((220 * 1024) / stage_bytes);
     if (stages > 4) stages = 4;
     if (stages < 1) { set_error("xm3d_point_logits: tile does not fit shared memory"); return XM3D_ERR_UNSUPPORTED; }
     P.stages = stages;
