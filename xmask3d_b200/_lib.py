@@ -11,7 +11,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libxm3d.so")
+SO_PATH = os.environ.get("XM3D_SO") or os.path.join(_HERE, "libxm3d.so")   # XM3D_SO: A/B builds of the same ABI
 CSRC = os.path.join(_HERE, "csrc")
 
 XM3D_OK = 0

@@ -27,7 +27,10 @@
 
 namespace xm3d {
 
-constexpr int POOL_CH = 256;        // pairs per chunk (one partial row each)
+#ifndef XM3D_POOL_CH
+#define XM3D_POOL_CH 256
+#endif
+constexpr int POOL_CH = XM3D_POOL_CH;        // pairs per chunk (one partial row each)
 constexpr int POOL_UNROLL = 8;      // rows in flight per thread in the sum kernel
 constexpr int FILL_THREADS = 1024;
 

@@ -44,6 +44,10 @@ struct ProjParams {
     int n_views;
     int smem_depth_bytes;
     int use_flag;               // 1: vis = flag ? inside&&ok : inside   (depth smaller than image)
+    // float32 classifier constants (host-computed so that they are plain constant-bank operands)
+    float f_lx, f_hx, f_ly, f_hy;   // rounding boundaries of the cut image: cut - 0.5, W - cut - 0.5, same for y
+    float f_ecw, f_ech;             // 4e-7 (W + 1), 4e-7 (H + 1)
+    float f_inv_scale, f_vt;        // 1 / depth_scale, visibility threshold
 };
 
 __device__ __forceinline__ double dot_row(const double *a, double x, double y, double z) {
@@ -74,42 +78,96 @@ __device__ __forceinline__ uint32_t project_exact(const double *vw, float fx_, f
     return inside ? (0x80000000u | ((uint32_t)(int)ry << 16) | (uint32_t)(int)rx) : 0u;
 }
 
-// Conservative float32 reject filter: true only when the exact arithmetic above is guaranteed to
-// give inside == false (behind the camera, or outside the cut image by more than 0.49 px beyond
-// every rounding error).  Everything else — including NaN / inf — goes to the exact path.
+// Float32 classifier: decides a point WITHOUT the fp64 sequence whenever the float32 estimate is
+// farther from every decision boundary of the exact arithmetic than a bound on its own error —
+// behind the camera, outside the cut image, the rounded pixel (px, py more than `ex` away from a
+// half-integer), and the occlusion test (|d - z| vs thres * d with a margin).  Everything else —
+// borderline values, NaN / inf, anything near the z singularity — returns CLS_EXACT and is
+// evaluated by project_exact, so the result is the exact path's by construction.
 // Error bound of a float32 camera coordinate p_i = sum_j a_ij x_j: coefficient rounding plus three
 // fused multiply-adds stay below 1e-6 * sum_j |a_ij| |x_j| (>= 8 ulp); |x_j| is bounded per work
-// item by the largest |coordinate| of the CTA's points (one shared-memory max per axis), so the
-// per-point cost is the three dot products and a handful of compares.
+// item by the largest |coordinate| of the CTA's points (one shared-memory max per axis).
+// px32 = (p0 * fx) * (1 / p2) + cx:  |px32 - px| <= fx r e0 + |px - cx| (r e2 + RHO) + ecx, with
+// r = 1 / p2, RHO = 1e-6 (>= 16 ulp: fx conversion, two products, the approximate reciprocal) and
+// ecx = 4e-7 (|cx| + W + 1) for the conversion of cx and the final add.
+constexpr uint32_t CLS_EXACT = 0xffffffffu;        // not a valid code: rows are < 32767
 struct FilterConst {
     float a[12];             // world->camera rows
-    float fx, fy;
-    float lx, hx, ly, hy;    // (cut - 0.51 - cx), (W - cut - 0.49 - cx), same for y
-    float e0, e1, e2;        // error bounds of the float32 camera coordinates for this work item
+    float fx, fy, cx, cy;
+    float e2, zmin;          // error bound of the float32 camera z for this work item; 64 e2 + 1e-3
+    float e2r, fxe0, fye1, ecx, ecy;   // 1.05 e2 (1/(1-t) <= 1 + 1.04 t for t < 1/64), 1.02 fx e0, ...
+    float lxc, hxc, lyc, hyc;          // boundaries relative to the principal point (coarse test)
 };
-__device__ __forceinline__ bool surely_outside(const FilterConst &F, float x, float y, float z) {
+struct DepthSrc {
+    const unsigned short *sd;    // staged uint16 image or nullptr
+    const void *g;               // global image (uint16 or float64)
+    int64_t off;
+    int kind, dh, dw;
+    bool has;
+};
+// Coarse reject in multiplied form (no reciprocal): true only if the exact arithmetic is certain
+// to give inside == false.  With e2 / p2 < 1/64 the classifier's ex * p2 is below
+// fxe0 + 0.0166 |p0 fx| + ecx p2; the test doubles the last term for its own roundings.
+__device__ __forceinline__ bool coarse_reject(const FilterConst &F, float x, float y, float z) {
     const float p2 = fmaf(F.a[8], x, fmaf(F.a[9], y, fmaf(F.a[10], z, F.a[11])));
     if (p2 + F.e2 <= 0.f) return true;                     // exact p2 <= 0: not in front
-    if (!(p2 - F.e2 > 1.0e-3f)) return false;              // too close to the z singularity: exact path
+    if (!(p2 > F.zmin)) return false;                      // near the z singularity (or NaN): not decided here
+    const float t = fmaf(F.a[0], x, fmaf(F.a[1], y, fmaf(F.a[2], z, F.a[3]))) * F.fx;
+    const float s = fmaf(F.a[4], x, fmaf(F.a[5], y, fmaf(F.a[6], z, F.a[7]))) * F.fy;
+    const float mx = fmaf(0.0166f, fabsf(t), fmaf(2.f * F.ecx, p2, F.fxe0));
+    const float my = fmaf(0.0166f, fabsf(s), fmaf(2.f * F.ecy, p2, F.fye1));
+    return fmaf(-F.lxc, p2, t) < -mx || fmaf(-F.hxc, p2, t) > mx ||
+           fmaf(-F.lyc, p2, s) < -my || fmaf(-F.hyc, p2, s) > my;
+}
+
+template <bool FLAG_ONLY>
+__device__ __forceinline__ uint32_t classify_fast(const ProjParams &P, const FilterConst &F, const DepthSrc &D, float x, float y, float z,
+                                                  int use_flag, int vflag, bool *any_in_depth) {
+    const float p2 = fmaf(F.a[8], x, fmaf(F.a[9], y, fmaf(F.a[10], z, F.a[11])));
+    if (p2 + F.e2 <= 0.f) return 0u;                       // exact p2 <= 0: not in front
+    if (!(p2 > F.zmin)) return CLS_EXACT;   // near the z singularity (or NaN); e2 / p2 < 1/64 below
     const float p0 = fmaf(F.a[0], x, fmaf(F.a[1], y, fmaf(F.a[2], z, F.a[3])));
-    const float t = p0 * F.fx;
-    {   // px < lo  <=>  p0*fx < (lo - cx) * z   (z > 0)
-        const float u = F.lx * p2, v = F.hx * p2;
-        const float el = 2.f * (F.fx * F.e0 + fabsf(F.lx) * F.e2 + 4e-7f * (fabsf(t) + fabsf(u)));
-        const float eh = 2.f * (F.fx * F.e0 + fabsf(F.hx) * F.e2 + 4e-7f * (fabsf(t) + fabsf(v)));
-        if (t - u < -el) return true;
-        if (t - v > eh) return true;
-    }
     const float p1 = fmaf(F.a[4], x, fmaf(F.a[5], y, fmaf(F.a[6], z, F.a[7])));
-    const float s = p1 * F.fy;
-    {
-        const float u = F.ly * p2, v = F.hy * p2;
-        const float el = 2.f * (F.fy * F.e1 + fabsf(F.ly) * F.e2 + 4e-7f * (fabsf(s) + fabsf(u)));
-        const float eh = 2.f * (F.fy * F.e1 + fabsf(F.hy) * F.e2 + 4e-7f * (fabsf(s) + fabsf(v)));
-        if (s - u < -el) return true;
-        if (s - v > eh) return true;
+    const float r = __fdividef(1.f, p2);
+    const float u = (p0 * F.fx) * r, w = (p1 * F.fy) * r;
+    const float px = u + F.cx, py = w + F.cy;
+    const float rel = fmaf(F.e2r, r, 1.0e-6f);
+    const float ex = fmaf(fabsf(u), rel, fmaf(F.fxe0, r, F.ecx));
+    const float ey = fmaf(fabsf(w), rel, fmaf(F.fye1, r, F.ecy));
+    if (px < P.f_lx - ex || px > P.f_hx + ex || py < P.f_ly - ey || py > P.f_hy + ey) return 0u;   // outside for sure
+    const float nx = rintf(px), ny = rintf(py);
+    if (!(fabsf(px - nx) < 0.5f - ex) || !(fabsf(py - ny) < 0.5f - ey)) return CLS_EXACT;   // rounding not certain
+    // nx, ny are the exact path's rx, ry; the boundaries lx.. sit on half-integers
+    if (!(nx > P.f_lx && nx < P.f_hx && ny > P.f_ly && ny < P.f_hy)) return 0u;
+    const int ix = (int)nx, iy = (int)ny;
+    uint32_t code = 0x80000000u | ((uint32_t)iy << 16) | (uint32_t)ix;
+    if (D.has) {                                           // fusion_util.py:98-135
+        const bool in_depth = iy < D.dh && ix < D.dw;
+        bool ok = false;
+        if (in_depth) {
+            *any_in_depth = true;
+            if (!FLAG_ONLY) {
+                const size_t e = (size_t)iy * D.dw + ix;
+                float d;
+                if (D.kind == XM3D_DEPTH_U16) {
+                    const unsigned short raw = D.sd ? D.sd[e] : __ldg(reinterpret_cast<const unsigned short *>(D.g) + D.off + e);
+                    d = (float)raw * P.f_inv_scale;
+                } else {
+                    d = (float)__ldg(reinterpret_cast<const double *>(D.g) + D.off + e);
+                }
+                const float aa = fabsf(d - p2), bb = P.f_vt * d;
+                const float m = F.e2 + 2.0e-6f * (fabsf(d) + p2 + fabsf(bb));
+                if (aa <= bb - m) ok = true;
+                else if (aa > bb + m) ok = false;
+                else return CLS_EXACT;                     // occlusion test too close to call (or NaN / inf)
+            }
+        }
+        if (!FLAG_ONLY) {
+            const bool keep = use_flag ? (vflag ? ok : true) : ok;
+            if (!keep) code = 0u;
+        }
     }
-    return false;
+    return code;
 }
 
 template <bool FLAG_ONLY>
@@ -167,7 +225,7 @@ __global__ void __launch_bounds__(PROJ_THREADS, 1) project_kernel(const ProjPara
         dh = gv->depth_h; dw = gv->depth_w;
         has_depth = P.depth_kind != XM3D_DEPTH_NONE && depth_off >= 0;
         const size_t depth_bytes = (size_t)dh * dw * 2;
-        stage_depth = has_depth && P.depth_kind == XM3D_DEPTH_U16 && depth_bytes <= (size_t)P.smem_depth_bytes &&
+        stage_depth = !FLAG_ONLY && has_depth && P.depth_kind == XM3D_DEPTH_U16 && depth_bytes <= (size_t)P.smem_depth_bytes &&
                       (depth_bytes % 16 == 0) &&
                       ((reinterpret_cast<uintptr_t>(P.depth) + (size_t)depth_off * 2) % 16 == 0);
         staged = stage_depth;
@@ -188,7 +246,6 @@ __global__ void __launch_bounds__(PROJ_THREADS, 1) project_kernel(const ProjPara
         __syncthreads();
         mbar_wait(&s_bar[0], ph);
         if (!stage_depth) mbar_wait(&s_bar[1], ph);
-        // (a staged depth image is awaited right before its first use, after the float32 filter)
     }
 
     // ---- phase 1: stream the points (16-byte loads), float32 reject filter, queue the candidates
@@ -237,41 +294,80 @@ __global__ void __launch_bounds__(PROJ_THREADS, 1) project_kernel(const ProjPara
     FilterConst F;
 #pragma unroll
     for (int j = 0; j < 12; ++j) F.a[j] = (float)s_view[j];
+    F.fx = (float)s_view[12]; F.fy = (float)s_view[13]; F.cx = (float)s_view[14]; F.cy = (float)s_view[15];
     {
         const float GAM = 1.0e-6f;
         const float X = __int_as_float(s_amax[0]), Y = __int_as_float(s_amax[1]), Z = __int_as_float(s_amax[2]);
-        F.e0 = GAM * fmaf(fabsf(F.a[0]), X, fmaf(fabsf(F.a[1]), Y, fmaf(fabsf(F.a[2]), Z, fabsf(F.a[3]))));
-        F.e1 = GAM * fmaf(fabsf(F.a[4]), X, fmaf(fabsf(F.a[5]), Y, fmaf(fabsf(F.a[6]), Z, fabsf(F.a[7]))));
+        const float e0 = GAM * fmaf(fabsf(F.a[0]), X, fmaf(fabsf(F.a[1]), Y, fmaf(fabsf(F.a[2]), Z, fabsf(F.a[3]))));
+        const float e1 = GAM * fmaf(fabsf(F.a[4]), X, fmaf(fabsf(F.a[5]), Y, fmaf(fabsf(F.a[6]), Z, fabsf(F.a[7]))));
         F.e2 = GAM * fmaf(fabsf(F.a[8]), X, fmaf(fabsf(F.a[9]), Y, fmaf(fabsf(F.a[10]), Z, fabsf(F.a[11]))));
+        F.zmin = fmaf(64.f, F.e2, 1.0e-3f);
+        F.e2r = 1.05f * F.e2; F.fxe0 = 1.02f * F.fx * e0; F.fye1 = 1.02f * F.fy * e1;
     }
-    F.fx = fabsf((float)s_view[12]); F.fy = fabsf((float)s_view[13]);
-    const bool filter_ok = s_view[12] > 0.0 && s_view[13] > 0.0;          // the inequalities assume fx, fy > 0
-    F.lx = (float)(P.cut - 0.51 - s_view[14]); F.hx = (float)(P.img_w - P.cut - 0.49 - s_view[14]);
-    F.ly = (float)(P.cut - 0.51 - s_view[15]); F.hy = (float)(P.img_h - P.cut - 0.49 - s_view[15]);
-    // every warp owns its 256 points end to end: no block barrier until the ordered compaction
+    // the classifier's inequalities assume fx, fy > 0 and sane intrinsics
+    const bool filter_ok = s_view[12] > 0.0 && s_view[13] > 0.0 && s_view[12] < 1e6 && s_view[13] < 1e6 &&
+                           fabs(s_view[14]) < 1e6 && fabs(s_view[15]) < 1e6;
+    F.ecx = fmaf(4.0e-7f, fabsf(F.cx), P.f_ecw); F.ecy = fmaf(4.0e-7f, fabsf(F.cy), P.f_ech);
+    F.lxc = P.f_lx - F.cx; F.hxc = P.f_hx - F.cx; F.lyc = P.f_ly - F.cy; F.hyc = P.f_hy - F.cy;
+    DepthSrc D;
+    D.has = has_depth; D.kind = P.depth_kind; D.dh = dh; D.dw = dw; D.off = depth_off; D.g = P.depth;
+    D.sd = stage_depth ? reinterpret_cast<const unsigned short *>(smem_raw) : nullptr;
+    const int vflag = (!FLAG_ONLY && P.use_flag) ? P.view_flag[v] : 0;
+    if (stage_depth) mbar_wait(&s_bar[1], ph);     // no-op once the phase has completed
+
+    // ---- phase 1: coarse float32 reject of every point (points arrive in scene order, so almost
+    // every warp holds a few inside points: the full classifier would run for all of them); the
+    // survivors are queued per warp.  Every warp owns its 256 points end to end: no block barrier
+    // until the ordered compaction.
     unsigned short *wq = s_queue + warp * (PROJ_GROUPS * PROJ_GROUP * 32);
-    int wcount = 0;
+    int wcand = 0;
+    bool any_in_depth = false;
 #pragma unroll
     for (int g = 0; g < PROJ_GROUPS; ++g)
 #pragma unroll
         for (int j = 0; j < PROJ_GROUP; ++j) {
             const int local = g * PROJ_GROUP_PTS + tid * PROJ_GROUP + j;
             const bool live = part_start + local < n_pts;
-            const bool cand = live && !(filter_ok && surely_outside(F, c[g][3 * j], c[g][3 * j + 1], c[g][3 * j + 2]));
-            s_code[local] = 0u;
+            const bool cand = live && !(filter_ok && coarse_reject(F, c[g][3 * j], c[g][3 * j + 1], c[g][3 * j + 2]));
             const unsigned vote = __ballot_sync(0xffffffffu, cand);
-            if (cand) wq[wcount + __popc(vote & ((1u << lane) - 1u))] = (unsigned short)local;
-            wcount += __popc(vote);
+            if (cand) wq[wcand + __popc(vote & ((1u << lane) - 1u))] = (unsigned short)local;
+            wcand += __popc(vote);
         }
+    if (!FLAG_ONLY) {
+#pragma unroll
+        for (int g = 0; g < PROJ_GROUPS; ++g)
+            *reinterpret_cast<uint4 *>(s_code + g * PROJ_GROUP_PTS + tid * PROJ_GROUP) = make_uint4(0u, 0u, 0u, 0u);
+    }
     __syncwarp();
 
-    // ---- phase 2: exact arithmetic + occlusion test, one candidate per lane (dense within the warp)
-    if (stage_depth) mbar_wait(&s_bar[1], ph);     // no-op once the phase has completed
+    // ---- phase 1b: the float32 classifier on the survivors, one per lane; the undecided ones are
+    // queued again (the second queue overwrites entries that have already been consumed)
+    const float *xyz_item = xyz + part_start * 3;
+    int wcount = 0;
+    for (int q0 = 0; q0 < wcand; q0 += 32) {
+        const bool act = q0 + lane < wcand;
+        const int local = act ? wq[q0 + lane] : 0;
+        uint32_t code = 0u;
+        if (act) {
+            const float *pt = xyz_item + local * 3;
+            code = filter_ok ? classify_fast<FLAG_ONLY>(P, F, D, __ldg(pt), __ldg(pt + 1), __ldg(pt + 2),
+                                                        P.use_flag, vflag, &any_in_depth)
+                             : CLS_EXACT;
+        }
+        const bool und = code == CLS_EXACT;
+        if (!FLAG_ONLY && act && !und) s_code[local] = code;
+        __syncwarp();
+        const unsigned vote = __ballot_sync(0xffffffffu, und);
+        if (und) wq[wcount + __popc(vote & ((1u << lane) - 1u))] = (unsigned short)local;
+        wcount += __popc(vote);
+    }
+    __syncwarp();
+
+    // ---- phase 2: the exact fp64 sequence for the undecided points, one per lane
     const unsigned short *sd = reinterpret_cast<const unsigned short *>(smem_raw);
-    bool any_in_depth = false;
     for (int q = lane; q < wcount; q += 32) {
         const int local = wq[q];
-        const float *pt = xyz + (part_start + local) * 3;
+        const float *pt = xyz_item + local * 3;
         double zc;
         uint32_t code = project_exact(s_view, __ldg(pt), __ldg(pt + 1), __ldg(pt + 2), P, &zc);
         if (has_depth && (code >> 31)) {                         // fusion_util.py:98-135
@@ -293,7 +389,7 @@ __global__ void __launch_bounds__(PROJ_THREADS, 1) project_kernel(const ProjPara
             }
             if (!FLAG_ONLY) {
                 // exact mode: keep `inside` when no inside point of the view hits the depth image
-                const bool keep = P.use_flag ? (P.view_flag[v] ? ok : true) : ok;
+                const bool keep = P.use_flag ? (vflag ? ok : true) : ok;
                 if (!keep) code = 0u;
             }
         }
@@ -314,71 +410,79 @@ __global__ void __launch_bounds__(PROJ_THREADS, 1) project_kernel(const ProjPara
 
     // ---- phase 3: visibility bytes, optional int64 [N,3] mapping, part-local compaction (point order)
     const int64_t out0 = gv->out_off;
-    int running = 0;
+    uint32_t code[PROJ_GROUPS][PROJ_GROUP];
+    int packed = 0;                                  // visible count of group g in bits [16g, 16g+16)
 #pragma unroll
     for (int g = 0; g < PROJ_GROUPS; ++g) {
         const int64_t i0 = part_start + (int64_t)g * PROJ_GROUP_PTS + (int64_t)tid * PROJ_GROUP;
         const uint4 cd = *reinterpret_cast<const uint4 *>(s_code + g * PROJ_GROUP_PTS + tid * PROJ_GROUP);
-        const uint32_t code[PROJ_GROUP] = {cd.x, cd.y, cd.z, cd.w};
+        code[g][0] = cd.x; code[g][1] = cd.y; code[g][2] = cd.z; code[g][3] = cd.w;
         int cnt = 0;
 #pragma unroll
-        for (int j = 0; j < PROJ_GROUP; ++j) cnt += code[j] >> 31;
+        for (int j = 0; j < PROJ_GROUP; ++j) cnt += code[g][j] >> 31;
+        packed |= cnt << (16 * g);
         if (i0 < n_pts) {
             uint8_t *vp = P.vis + out0 + i0;
             if (i0 + PROJ_GROUP <= n_pts && (reinterpret_cast<uintptr_t>(vp) % 4 == 0)) {
-                *reinterpret_cast<uint32_t *>(vp) = (code[0] >> 31) | ((code[1] >> 31) << 8) |
-                                                    ((code[2] >> 31) << 16) | ((code[3] >> 31) << 24);
+                *reinterpret_cast<uint32_t *>(vp) = (code[g][0] >> 31) | ((code[g][1] >> 31) << 8) |
+                                                    ((code[g][2] >> 31) << 16) | ((code[g][3] >> 31) << 24);
             } else {
 #pragma unroll
                 for (int j = 0; j < PROJ_GROUP; ++j)
-                    if (i0 + j < n_pts) vp[j] = (uint8_t)(code[j] >> 31);
+                    if (i0 + j < n_pts) vp[j] = (uint8_t)(code[g][j] >> 31);
             }
             if (P.mapping) {
                 int64_t *mp = P.mapping + (out0 + i0) * 3;
 #pragma unroll
                 for (int j = 0; j < PROJ_GROUP; ++j)
                     if (i0 + j < n_pts) {
-                        const bool vis = code[j] >> 31;
-                        mp[3 * j + 0] = vis ? (int64_t)((code[j] >> 16) & 0x7fff) : 0;   // row (y)
-                        mp[3 * j + 1] = vis ? (int64_t)(code[j] & 0xffff) : 0;           // col (x)
+                        const bool vis = code[g][j] >> 31;
+                        mp[3 * j + 0] = vis ? (int64_t)((code[g][j] >> 16) & 0x7fff) : 0;   // row (y)
+                        mp[3 * j + 1] = vis ? (int64_t)(code[g][j] & 0xffff) : 0;           // col (x)
                         mp[3 * j + 2] = vis ? 1 : 0;
                     }
             }
         }
-        // block-exclusive scan of cnt (order = thread order = point order)
-        int incl = cnt;
+    }
+    // one block-exclusive scan serves both groups (order = thread order = point order inside a
+    // group; a group holds <= 4096 visible points, so the 16-bit fields never carry)
+    static_assert(PROJ_GROUPS == 2 && PROJ_GROUP_PTS <= 32768, "packed scan layout");
+    int incl = packed;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const int w = s_warp_tot[lane];
+        int wi = w;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
+            const int t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
         }
-        if (lane == 31) s_warp_tot[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            int w = s_warp_tot[lane];
-            int wi = w;
+        s_warp_tot[lane] = wi - w;               // exclusive warp offsets
+        if (lane == 31) s_any = wi;              // totals of both groups
+    }
+    __syncthreads();
+    const int excl = s_warp_tot[warp] + incl - packed;
+    const int tot0 = s_any & 0xffff, tot1 = s_any >> 16;
+    unsigned long long *st = P.stage + out0 + part_start;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, wi, o);
-                if (lane >= o) wi += t;
-            }
-            s_warp_tot[lane] = wi - w;          // exclusive warp offsets
-            if (lane == 31) s_any = wi;          // group total
-        }
-        __syncthreads();
-        int pos = running + s_warp_tot[warp] + incl - cnt;
-        unsigned long long *st = P.stage + out0 + part_start;
+    for (int g = 0; g < PROJ_GROUPS; ++g) {
+        const int64_t i0 = part_start + (int64_t)g * PROJ_GROUP_PTS + (int64_t)tid * PROJ_GROUP;
+        int pos = g == 0 ? (excl & 0xffff) : tot0 + (excl >> 16);
 #pragma unroll
         for (int j = 0; j < PROJ_GROUP; ++j)
-            if (code[j] >> 31) {
+            if (code[g][j] >> 31) {
                 const unsigned long long idx = (unsigned long long)(i0 + j);
-                st[pos++] = (idx << 32) | (unsigned long long)(code[j] & 0x7fffffffu);
+                st[pos++] = (idx << 32) | (unsigned long long)(code[g][j] & 0x7fffffffu);
             }
-        running += s_any;
-        __syncthreads();
     }
     if (tid == 0) {
-        P.part_cnt[v * P.parts + part] = running;
+        P.part_cnt[v * P.parts + part] = tot0 + tot1;
         s_amax[0] = s_amax[1] = s_amax[2] = 0;
     }
     if (it + 1 < it1 && it + 1 >= P.item_off[v + 1]) ph ^= 1;          // next item starts a new view
@@ -585,6 +689,10 @@ extern "C" int xm3d_project_batch(const float *xyz, const xm3d_view_t *views_hos
     P.vis = vis; P.mapping = mapping; P.stage = stage; P.part_cnt = part_cnt; P.view_flag = view_flag;
     stage_bytes = (stage_bytes + 127) / 128 * 128;
     P.item_off = item_off; P.n_views = n_views;
+    P.f_lx = (float)(cut_bound - 0.5); P.f_hx = (float)(img_w - cut_bound - 0.5);
+    P.f_ly = (float)(cut_bound - 0.5); P.f_hy = (float)(img_h - cut_bound - 0.5);
+    P.f_ecw = 4.0e-7f * (float)(img_w + 1); P.f_ech = 4.0e-7f * (float)(img_h + 1);
+    P.f_inv_scale = (float)(1.0 / depth_scale); P.f_vt = (float)vis_thres;
     P.parts = parts; P.smem_depth_bytes = (int)stage_bytes; P.use_flag = (any_depth && !covers) ? 1 : 0;
 
     static bool attr_set = false;
