@@ -73,13 +73,41 @@ def f_full(): pipe.run(masks, feat, mode)
 pipe2 = CorrespondencePipeline(batch, args.k, args.c, dev, overlap=False); pipe2.xyz = pipe.xyz; pipe2.depth = pipe.depth; pipe2.set_cap(total_vis)
 pipe2.pairs_per_point = pipe.pairs_per_point; pipe2._size_pool_ws()
 def f_serial(): pipe2.run(masks, feat, mode)
-timeit(f_proj, "project")
-timeit(f_vox, "voxelize")
-timeit(f_gather, "gather")
-timeit(f_pool, "pool")
-timeit(f_gp, "gather+pool")
-timeit(f_gp_vox, "gather+pool || voxelize")
-timeit(f_gp_vox_prio, "gather+pool || voxelize(high prio)")
-timeit(f_full_prio, "full, voxelize on high-prio stream")
-timeit(f_serial, "full serial")
-timeit(f_full, "full overlap")
+import os
+QUICK = os.environ.get("QUICK")
+if not QUICK: timeit(f_proj, "project")
+if not QUICK: timeit(f_vox, "voxelize")
+if not QUICK: timeit(f_gather, "gather")
+if not QUICK or QUICK == "2": timeit(f_pool, "pool")
+if not QUICK: timeit(f_gp, "gather+pool")
+if not QUICK: timeit(f_gp_vox, "gather+pool || voxelize")
+if not QUICK: timeit(f_gp_vox_prio, "gather+pool || voxelize(high prio)")
+if not QUICK: timeit(f_full_prio, "full, voxelize on high-prio stream")
+if not QUICK: timeit(f_serial, "full serial")
+if not QUICK or QUICK == "2": timeit(f_full, "full overlap")
+
+if QUICK == '2': sys.exit(0)
+# ---- does voxelize slow down next to an HBM-saturating copy that uses no SMs (copy engine)?
+import ctypes
+rt_ = ctypes.CDLL('libcudart.so.12')
+rt_.cudaMemcpyAsync.argtypes=[ctypes.c_void_p,ctypes.c_void_p,ctypes.c_size_t,ctypes.c_int,ctypes.c_void_p]
+big_a = torch.empty(3 << 30, dtype=torch.uint8, device=dev); big_b = torch.empty_like(big_a)
+cs = torch.cuda.Stream()
+def ev(): return torch.cuda.Event(enable_timing=True)
+for trial in range(3):
+    torch.cuda.synchronize()
+    a0, a1, b0, b1 = ev(), ev(), ev(), ev()
+    with torch.cuda.stream(cs):
+        b0.record()
+        assert rt_.cudaMemcpyAsync(big_b.data_ptr(), big_a.data_ptr(), big_a.numel(), 3, cs.cuda_stream) == 0
+        b1.record()
+    a0.record()
+    for _ in range(2): f_vox()
+    a1.record()
+    torch.cuda.synchronize()
+    print(f"vox x2 next to a CE copy: {a0.elapsed_time(a1)*500:.1f} us per vox;  copy {b0.elapsed_time(b1)*1000:.0f} us ({2*big_a.numel()/b0.elapsed_time(b1)/1e6:.0f} GB/s r+w)")
+torch.cuda.synchronize()
+a0, a1 = ev(), ev(); a0.record()
+for _ in range(2): f_vox()
+a1.record(); torch.cuda.synchronize()
+print(f"vox x2 alone (eager): {a0.elapsed_time(a1)*500:.1f} us per vox")

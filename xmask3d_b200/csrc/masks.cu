@@ -99,7 +99,8 @@ pixel_bits_u8_kernel(const unsigned char *__restrict__ masks, int k, int hw, int
     if (p0 >= hw) return;                                   // hw % 16 == 0 on this path
     const unsigned char *base = masks + (size_t)s * k * hw + p0;
     uint32_t *out = pixbits + (size_t)s * words * hw + p0;
-    for (int wd = 0; wd < words; ++wd) {
+    {
+        const int wd = blockIdx.z;                          // one word of 32 masks per CTA: short CTAs, short tail
         uint32_t acc[4][4];                                 // [byte group][quad]
 #pragma unroll
         for (int g = 0; g < 4; ++g)
@@ -260,7 +261,8 @@ extern "C" int xm3d_gather_masks_batch(const void *masks, int32_t mask_kind, int
     const int vec_ok = (hw % pix == 0) && (reinterpret_cast<uintptr_t>(masks) % 16 == 0);
     dim3 grid(((hw + pix - 1) / pix + 255) / 256, n_seg);
     if (mask_kind == XM3D_MASK_U8 && thr_mode == XM3D_THR_GE_HALF && vec_ok) {
-        pixel_bits_u8_kernel<<<grid, 256, 0, stream>>>(static_cast<const unsigned char *>(masks), k, hw, words, pixbits);
+        dim3 grid8(grid.x, n_seg, words);
+        pixel_bits_u8_kernel<<<grid8, 256, 0, stream>>>(static_cast<const unsigned char *>(masks), k, hw, words, pixbits);
         count_launches(1);
     } else if (mask_kind == XM3D_MASK_U8) {
         pixel_bits_kernel<unsigned char><<<grid, 256, 0, stream>>>(static_cast<const unsigned char *>(masks), thr_mode,

@@ -322,6 +322,11 @@ struct SumParams {
     int n_units;
     int64_t cap_pairs;
     float *partial;            // [chunks, c]
+    // units made of exactly one chunk are finished here (no partial row, no combine pass)
+    const int32_t *cnt_in;     // [n_units] pairs per unit
+    float *sum, *mean;         // [n_units, c]; mean may be null
+    int32_t *cnt;              // [n_units] or null
+    int direct;                // 1: sum / mean are 16-byte aligned for the vector store
 };
 
 template <int VEC>
@@ -362,6 +367,20 @@ __global__ void __launch_bounds__(1024) pool_sum_kernel(const SumParams P) {
                 if (active && j0 + j < nb) vadd(acc, buf[j]);          // fixed row order
         }
     }
+    if (P.direct && P.chunk_off[u + 1] - P.chunk_off[u] == 1) {
+        const size_t o = (size_t)u * P.c + ch;
+        if (active) {
+            *reinterpret_cast<V *>(P.sum + o) = acc;
+            if (P.mean) {
+                float *a = reinterpret_cast<float *>(&acc);
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) a[j] = __fdiv_rn(a[j], (float)n);      // n >= 1 here
+                *reinterpret_cast<V *>(P.mean + o) = acc;
+            }
+        }
+        if (P.cnt && tid == 0) P.cnt[u] = n;
+        return;
+    }
     if (active) *reinterpret_cast<V *>(P.partial + (size_t)chunk * P.c + ch) = acc;
 }
 
@@ -371,7 +390,7 @@ __global__ void __launch_bounds__(256)
 pool_combine_kernel(const float *__restrict__ partial, const int32_t *__restrict__ cnt_in,
                     const int64_t *__restrict__ pair_off, const int32_t *__restrict__ chunk_off, int n_units,
                     int64_t cap_pairs, int k, int c, float *__restrict__ sum, int32_t *__restrict__ cnt,
-                    float *__restrict__ mean) {
+                    float *__restrict__ mean, int direct) {
     using V = typename VecT<VEC>::type;
     const int s = blockIdx.y;
     const int cv = c / VEC;                                    // vectors per row
@@ -380,6 +399,7 @@ pool_combine_kernel(const float *__restrict__ partial, const int32_t *__restrict
     const int m = e / cv, ch = (e - m * cv) * VEC;
     const int u = s * k + m;
     const bool ok = pair_off[n_units] <= cap_pairs;
+    if (ok && direct && chunk_off[u + 1] - chunk_off[u] == 1) return;      // finished by the sum kernel
     const int n = ok ? cnt_in[u] : 0;
     V acc; vzero(acc);
     if (ok)
@@ -476,20 +496,21 @@ extern "C" int xm3d_pool_batch(const float *feat, int32_t c, const int32_t *row_
     SumParams S;
     S.feat = feat; S.c = c; S.perm = w.perm; S.pair_off = w.pair_off; S.chunk_off = w.chunk_off; S.n_units = n_units;
     S.cap_pairs = cap_pairs; S.partial = w.partial;
+    const bool cv4 = vec == 4 && reinterpret_cast<uintptr_t>(sum) % 16 == 0 && (!mean || reinterpret_cast<uintptr_t>(mean) % 16 == 0);
+    S.cnt_in = w.cnt; S.sum = sum; S.mean = mean; S.cnt = cnt; S.direct = (cv4 || vec == 1) ? 1 : 0;
     const int threads = ((c + vec - 1) / vec + 31) / 32 * 32;
     if (g_pool_ev[0]) cudaEventRecord(g_pool_ev[0], stream);
     if (vec == 4) { pool_sum_kernel<4><<<(unsigned)w.max_chunks, threads, 0, stream>>>(S); count_launches(1); }
     else { pool_sum_kernel<1><<<(unsigned)w.max_chunks, threads, 0, stream>>>(S); count_launches(1); }
     if (g_pool_ev[1]) cudaEventRecord(g_pool_ev[1], stream);
-    const bool cv4 = vec == 4 && reinterpret_cast<uintptr_t>(sum) % 16 == 0 && (!mean || reinterpret_cast<uintptr_t>(mean) % 16 == 0);
     if (cv4) {
         dim3 cgrid((unsigned)(((size_t)k * (c / 4) + 255) / 256), n_seg);
         pool_combine_kernel<4><<<cgrid, 256, 0, stream>>>(w.partial, w.cnt, w.pair_off, w.chunk_off, n_units, cap_pairs, k, c,
-                                                          sum, cnt, mean);
+                                                          sum, cnt, mean, S.direct);
     } else {
         dim3 cgrid((unsigned)(((size_t)k * c + 255) / 256), n_seg);
         pool_combine_kernel<1><<<cgrid, 256, 0, stream>>>(w.partial, w.cnt, w.pair_off, w.chunk_off, n_units, cap_pairs, k, c,
-                                                          sum, cnt, mean);
+                                                          sum, cnt, mean, S.direct);
     }
     count_launches(1);
     return check_launch("xm3d_pool_batch");

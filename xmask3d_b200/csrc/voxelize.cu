@@ -267,10 +267,16 @@ vox_min_kernel(const float *__restrict__ xyz, const int64_t *__restrict__ seg_of
 }
 
 // ---- sample pass --------------------------------------------------------------------------
+// Bitonic sort of n keys in shared memory (n a power of two >= 32, blockDim.x a multiple of 32).
+// Strides >= 32 are shared-memory steps with a block barrier each; all strides < 32 of a merge
+// size run in registers (element e sits in lane e & 31, partners are exchanged with shuffles), so
+// a 1024-key sort needs 21 barriers instead of 55.
 template <typename K>
 __device__ __forceinline__ void bitonic_smem(K *k, int n /*pow2*/) {
-    for (int size = 2; size <= n; size <<= 1)
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+    const int lane = threadIdx.x & 31;
+    for (int size = 2; size <= n; size <<= 1) {
+        int stride = size >> 1;
+        for (; stride >= 32; stride >>= 1) {
             for (int t = threadIdx.x; t < (n >> 1); t += blockDim.x) {
                 const int lo = 2 * t - (t & (stride - 1));     // insert a 0 at bit log2(stride)
                 const int hi = lo + stride;
@@ -280,6 +286,24 @@ __device__ __forceinline__ void bitonic_smem(K *k, int n /*pow2*/) {
             }
             __syncthreads();
         }
+        // register pass: merge sizes 2..32 in one go the first time, then strides 16..1 of `size`
+        const int top = size < 32 ? 32 : size;
+        for (int e = threadIdx.x; e < n; e += blockDim.x) {
+            K v = k[e];
+            for (int sz = size; sz <= top; sz <<= 1) {
+                const bool up = (e & sz) == 0;
+                for (int st = (sz < 32 ? sz : 32) >> 1; st > 0; st >>= 1) {
+                    const K o = __shfl_xor_sync(0xffffffffu, v, st);
+                    const bool lower = (lane & st) == 0;
+                    const bool take_min = lower == up;
+                    v = ((o < v) == take_min) ? o : v;
+                }
+            }
+            k[e] = v;
+        }
+        if (size < 32) size = 32;
+        __syncthreads();
+    }
 }
 
 // KEY_SRC 0: keys from xyz through the transform (voxelize); 1: keys given (unique_batch)
@@ -371,6 +395,8 @@ vox_insert_kernel(const float *__restrict__ xyz, const unsigned long long *__res
     unsigned int bkt = 0, pos = 0;
     if (is_new) {
         const int64_t so = spl_off[s];
+        // (the splitters of a segment stay hot in L1: staging them in shared memory was measured
+        // 90 us slower — the 32 KB per CTA shrink the L1 that serves the table and xyz reads)
         bkt = (unsigned int)bucket_of(spl + so, (int)(spl_off[s + 1] - so), key);
         pos = (unsigned int)atomicAdd(&hist[so + bkt], 1);
     }
