@@ -54,10 +54,18 @@ __device__ __forceinline__ int seg_of(const int64_t *__restrict__ off, int n, in
     return lo;
 }
 
+// Read-once stream: no L1 allocation and an L2 evict-first policy, so that a multi-GB stream does
+// not push the L2-resident working sets of concurrently running kernels (hash tables, depth
+// images, membership words) out to DRAM.
+__device__ __forceinline__ unsigned long long l2_evict_first_policy() {
+    unsigned long long pol;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
 __device__ __forceinline__ float4 ldg_stream4(const float *p) {
     float4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(l2_evict_first_policy()));
     return r;
 }
 
