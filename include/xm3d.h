@@ -234,6 +234,35 @@ XM3D_API int xm3d_vote_batch(const int32_t *vis_idx, const int64_t *seg_off, int
 XM3D_API int xm3d_vote_argmax(const int32_t *votes, const int32_t *counter, int64_t n_pts, int32_t n_classes,
                      int32_t *pred, xm3d_stream_t stream);
 
+/* ------------------------------------------------------------------ after the path: mask preparation
+ * The dense torch sequence that turns the mask head's low-resolution logits into the masks the path
+ * consumes (models/xmask3d.py:326-331, 356-358, 391-435; models/utils/criterion.py:239-244, 273-320),
+ * fused into one pass per output pixel:
+ *   up  = F.interpolate(logits [k,hs,ws] -> [k,h,w], "bilinear", align_corners=False)   (torch's CPU
+ *         arithmetic bit for bit)
+ *   pixbits (optional)  [n_seg, words, h*w] uint32: bit m set iff threshold(up[m]) per thr_mode
+ *                       (XM3D_THR_SIGMOID_GT_HALF = `.sigmoid() > 0.5`); feed xm3d_point_bits_batch
+ *   label   (optional)  [n_seg, h*w] int16: m = argmax over kept masks of scores[m] * sigmoid(up[m])
+ *                       (first maximum) if sigmoid(up[m]) >= 0.5, else -1 — the final partition masks
+ *                       (cur_mask_ids == m) & (cur_masks[m] >= 0.5); feed xm3d_gather_labels_batch
+ *   areas   (optional)  [n_seg, k, 3] int32: mask_area, original_area, intersection; the reference
+ *                       keeps mask m iff all three are > 0 (<=> intersection > 0)
+ *   upsampled (optional) [n_seg, k, h*w] float32 (tests / callers that want the dense tensor)
+ *   scores [n_seg,k] (null = 1), keep [n_seg,k] uint8 (null = all): `scores > thresh` of the caller. */
+XM3D_API int xm3d_mask_prep_batch(const float *logits, int32_t n_seg, int32_t k, int32_t hs, int32_t ws, int32_t h,
+                         int32_t w, const float *scores, const uint8_t *keep, int32_t thr_mode,
+                         uint32_t *pixbits, int16_t *label, int32_t *areas, float *upsampled,
+                         xm3d_stream_t stream);
+/* member words of every visible point from per-pixel words (second half of xm3d_gather_masks_batch) */
+XM3D_API int xm3d_point_bits_batch(const uint32_t *pixbits, int32_t n_seg, int32_t k, int32_t h, int32_t w,
+                          const int32_t *rowcol, const int64_t *seg_off, int64_t cap, uint32_t *member,
+                          int32_t *counts, xm3d_stream_t stream);
+/* point_label[i] = label image of the point's segment at (row, col); -1 outside the image.  The result
+ * is the `label` input of xm3d_pool_batch / xm3d_scatter_batch (mask_3d = mask[:, x_label, y_label]). */
+XM3D_API int xm3d_gather_labels_batch(const int16_t *label_img, int32_t n_seg, int32_t h, int32_t w,
+                             const int32_t *rowcol, const int64_t *seg_off, int64_t cap,
+                             int32_t *point_label, xm3d_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

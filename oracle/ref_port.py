@@ -370,3 +370,42 @@ def accumulate_votes(scene_pred, counter, mask_2d, logits_pred):
 def vote_argmax(scene_pred):
     """run/infer.py:658 — torch.max(scene_pred, dim=1)[1]: first maximum."""
     return scene_pred.argmax(1)
+
+
+# ----------------------------------------------------------------------------- mask preparation
+def mask_prep_ref(mask_pred_lowres, scores, mask_shape, score_thresh=0.0):
+    """Restatement of the reference's inline mask preparation for one view (torch CPU ops, same
+    order): models/xmask3d.py:326-331 (interpolate), :391-397 (sigmoid, keep), :415-435 (argmax
+    partition + area checks); twin models/utils/criterion.py:239-244, 273-320.
+    Returns dict(up, sig, keep, ids, final_keep (indices into the unfiltered masks), final_mask,
+    areas [K,3], prob)."""
+    import torch
+    import torch.nn.functional as F
+    x = torch.as_tensor(mask_pred_lowres, dtype=torch.float32)
+    sc = torch.as_tensor(scores, dtype=torch.float32)
+    up = F.interpolate(x[None], size=tuple(mask_shape), mode="bilinear", align_corners=False)[0]
+    mask_pred = up.sigmoid()
+    keep = sc > score_thresh
+    kept = torch.nonzero(keep).flatten()
+    cur_scores, cur_masks = sc[keep], mask_pred[keep]
+    K = x.shape[0]
+    areas = torch.zeros((K, 3), dtype=torch.int64)
+    final_keep, final_mask = [], []
+    ids = torch.full(tuple(mask_shape), -1, dtype=torch.int64)
+    prob = None
+    if cur_masks.shape[0] > 0:
+        prob = cur_scores.view(-1, 1, 1) * cur_masks
+        cur_mask_ids = prob.argmax(0)
+        ids = kept[cur_mask_ids]
+        for k in range(cur_masks.shape[0]):
+            mask_area = int((cur_mask_ids == k).sum().item())
+            original_area = int((cur_masks[k] >= 0.5).sum().item())
+            mask = (cur_mask_ids == k) & (cur_masks[k] >= 0.5)
+            areas[kept[k]] = torch.tensor([mask_area, original_area, int(mask.sum().item())])
+            if mask_area > 0 and original_area > 0 and mask.sum().item() > 0:
+                if mask_area / original_area <= 0:
+                    continue
+                final_keep.append(int(kept[k]))
+                final_mask.append(mask)
+    return {"up": up, "sig": mask_pred, "keep": keep, "ids": ids, "final_keep": final_keep,
+            "final_mask": final_mask, "areas": areas, "prob": prob, "kept": kept}

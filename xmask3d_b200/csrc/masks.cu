@@ -277,6 +277,20 @@ extern "C" int xm3d_gather_masks_batch(const void *masks, int32_t mask_kind, int
     return check_launch("xm3d_gather_masks_batch");
 }
 
+extern "C" int xm3d_point_bits_batch(const uint32_t *pixbits, int32_t n_seg, int32_t k, int32_t h, int32_t w,
+                                     const int32_t *rowcol, const int64_t *seg_off, int64_t cap, uint32_t *member,
+                                     int32_t *counts, xm3d_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    XM3D_REQUIRE(n_seg > 0 && k > 0 && h > 0 && w > 0 && cap >= 0, "bad sizes");
+    XM3D_REQUIRE(k <= 32 * MAX_WORDS, "at most 256 masks per segment");
+    XM3D_REQUIRE(pixbits && rowcol && seg_off && member, "null pointer");
+    if (counts) cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)n_seg * k, stream);
+    if (cap > 0) {
+        point_bits_kernel<<<(unsigned)((cap + 255) / 256), 256, 0, stream>>>(pixbits, rowcol, seg_off, n_seg, cap, k, h,
+                                                                             w, words_for(k), member, counts); count_launches(1); }
+    return check_launch("xm3d_point_bits_batch");
+}
+
 extern "C" int xm3d_scatter_batch(const uint32_t *member, const int32_t *label, int32_t n_seg, int32_t k,
                                   const int64_t *seg_off, int64_t cap, const float *emb, int32_t c, float *out,
                                   float *counter, xm3d_stream_t stream_) {

@@ -18,7 +18,14 @@
 
 namespace xm3d {
 
-constexpr int PROJ_THREADS = 1024;
+#ifndef XM3D_PROJ_THREADS
+#define XM3D_PROJ_THREADS 1024
+#endif
+#ifndef XM3D_PROJ_CTAS
+#define XM3D_PROJ_CTAS 1
+#endif
+constexpr int PROJ_THREADS = XM3D_PROJ_THREADS;
+constexpr int PROJ_CTAS = XM3D_PROJ_CTAS;            // persistent CTAs per SM (> 1: the depth image is not staged)
 constexpr int PROJ_GROUP = 4;                       // consecutive points per thread per group
 constexpr int PROJ_GROUPS = 2;                      // groups per thread
 constexpr int PROJ_GROUP_PTS = PROJ_THREADS * PROJ_GROUP;     // 4096
@@ -171,7 +178,7 @@ __device__ __forceinline__ uint32_t classify_fast(const ProjParams &P, const Fil
 }
 
 template <bool FLAG_ONLY>
-__global__ void __launch_bounds__(PROJ_THREADS, 1) project_kernel(const ProjParams P) {
+__global__ void __launch_bounds__(PROJ_THREADS, PROJ_CTAS) project_kernel(const ProjParams P) {
     // dynamic shared memory: [depth image (P.smem_depth_bytes)] [codes u32 x PART] [queue u16 x PART]
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(16) double s_view[24];      // the 192-byte record
@@ -456,14 +463,14 @@ __global__ void __launch_bounds__(PROJ_THREADS, 1) project_kernel(const ProjPara
     if (lane == 31) s_warp_tot[warp] = incl;
     __syncthreads();
     if (warp == 0) {
-        const int w = s_warp_tot[lane];
+        const int w = lane < PROJ_THREADS / 32 ? s_warp_tot[lane] : 0;
         int wi = w;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int t = __shfl_up_sync(0xffffffffu, wi, o);
             if (lane >= o) wi += t;
         }
-        s_warp_tot[lane] = wi - w;               // exclusive warp offsets
+        if (lane < PROJ_THREADS / 32) s_warp_tot[lane] = wi - w;               // exclusive warp offsets
         if (lane == 31) s_any = wi;              // totals of both groups
     }
     __syncthreads();
@@ -687,6 +694,7 @@ extern "C" int xm3d_project_batch(const float *xyz, const xm3d_view_t *views_hos
     P.xyz = xyz; P.views = d_views; P.depth = depth; P.depth_kind = depth_kind; P.depth_scale = depth_scale;
     P.img_w = img_w; P.img_h = img_h; P.cut = cut_bound; P.vis_thres = vis_thres;
     P.vis = vis; P.mapping = mapping; P.stage = stage; P.part_cnt = part_cnt; P.view_flag = view_flag;
+    if (PROJ_CTAS > 1) stage_bytes = 0;
     stage_bytes = (stage_bytes + 127) / 128 * 128;
     P.item_off = item_off; P.n_views = n_views;
     P.f_lx = (float)(cut_bound - 0.5); P.f_hx = (float)(img_w - cut_bound - 0.5);
@@ -703,7 +711,7 @@ extern "C" int xm3d_project_batch(const float *xyz, const xm3d_view_t *views_hos
     }
     dim3 grid(parts, n_views);
     project_plan_kernel<<<1, 1024, 0, stream>>>(d_views, n_views, parts, item_off, part_cnt); count_launches(1);
-    const unsigned pgrid = (unsigned)sm_count();       // persistent: one CTA per SM
+    const unsigned pgrid = (unsigned)sm_count() * PROJ_CTAS;       // persistent: PROJ_CTAS per SM
     if (P.use_flag) {
         cudaMemsetAsync(view_flag, 0, sizeof(int) * n_views, stream);
         project_kernel<true><<<pgrid, PROJ_THREADS, stage_bytes + PROJ_SMEM_EXTRA, stream>>>(P); count_launches(1);

@@ -397,3 +397,70 @@ def vote_argmax(votes: torch.Tensor, counter: torch.Tensor) -> torch.Tensor:
     pred = torch.empty(votes.shape[0], dtype=torch.int32, device=votes.device)
     L.check(L.lib().xm3d_vote_argmax(_ptr(votes), _ptr(counter), votes.shape[0], votes.shape[1], _ptr(pred), _stream()))
     return pred
+
+
+# ----------------------------------------------------------------------------- after the path: mask preparation
+@dataclass
+class PreparedMasks:
+    pixbits: Optional[torch.Tensor]    # int32 (uint32 bits) [n_seg, words, h*w]
+    label: Optional[torch.Tensor]      # int16 [n_seg, h, w]; -1 = in no final mask
+    areas: Optional[torch.Tensor]      # int32 [n_seg, k, 3]: mask_area, original_area, intersection
+    upsampled: Optional[torch.Tensor]  # float32 [n_seg, k, h, w]
+    k: int
+    h: int
+    w: int
+
+
+def mask_prep(logits_lowres: torch.Tensor, size, scores: Optional[torch.Tensor] = None,
+              keep: Optional[torch.Tensor] = None, mode: str = "sigmoid_gt0.5", want_bits: bool = True,
+              want_partition: bool = False, want_upsampled: bool = False) -> PreparedMasks:
+    """Bilinear upsample (align_corners=False) + sigmoid / threshold (+ score-weighted argmax partition
+    with its areas) of low-resolution mask logits [n_seg,k,hs,ws], one dense pass, nothing of size
+    k*h*w written unless want_upsampled (reference models/xmask3d.py:326-331, 356-358, 391-435)."""
+    _require_cuda()
+    dev = logits_lowres.device
+    lg = _dev_contig(logits_lowres, torch.float32)
+    assert lg.dim() == 4
+    n_seg, k, hs, ws_ = lg.shape
+    h, w = int(size[0]), int(size[1])
+    words = mask_words(k)
+    sc = _dev_contig(scores.reshape(n_seg, k), torch.float32) if scores is not None else None
+    kp = _dev_contig(keep.reshape(n_seg, k).to(torch.uint8), torch.uint8) if keep is not None else None
+    pixbits = torch.empty((n_seg, words, h * w), dtype=torch.int32, device=dev) if want_bits else None
+    label = torch.empty((n_seg, h, w), dtype=torch.int16, device=dev) if want_partition else None
+    areas = torch.empty((n_seg, k, 3), dtype=torch.int32, device=dev) if want_partition else None
+    up = torch.empty((n_seg, k, h, w), dtype=torch.float32, device=dev) if want_upsampled else None
+    L.check(L.lib().xm3d_mask_prep_batch(_ptr(lg), n_seg, k, hs, ws_, h, w, _ptr(sc), _ptr(kp), THR[mode], _ptr(pixbits),
+                                         _ptr(label), _ptr(areas), _ptr(up), _stream()))
+    return PreparedMasks(pixbits, label, areas, up, k, h, w)
+
+
+def point_bits(prep: PreparedMasks, rowcol: torch.Tensor, seg_off: torch.Tensor, cap: Optional[int] = None,
+               want_counts: bool = False):
+    """member words of every visible point from PreparedMasks.pixbits (mask[:, x_label, y_label] > thr)."""
+    _require_cuda()
+    dev = prep.pixbits.device
+    rowcol = _dev_contig(rowcol, torch.int32)
+    seg_off = _dev_contig(seg_off, torch.int64)
+    n_seg = prep.pixbits.shape[0]
+    cap = int(rowcol.shape[0]) if cap is None else int(cap)
+    member = torch.empty((max(cap, 1), mask_words(prep.k)), dtype=torch.int32, device=dev)
+    counts = torch.empty((n_seg, prep.k), dtype=torch.int32, device=dev) if want_counts else None
+    L.check(L.lib().xm3d_point_bits_batch(_ptr(prep.pixbits), n_seg, prep.k, prep.h, prep.w, _ptr(rowcol), _ptr(seg_off),
+                                          cap, _ptr(member), _ptr(counts), _stream()))
+    return member, counts
+
+
+def gather_labels(label_img: torch.Tensor, rowcol: torch.Tensor, seg_off: torch.Tensor,
+                  cap: Optional[int] = None) -> torch.Tensor:
+    """point_label[i] = label_img[seg(i), row_i, col_i] (int32; the `label` input of pool / scatter)."""
+    _require_cuda()
+    label_img = _dev_contig(label_img, torch.int16)
+    n_seg, h, w = label_img.shape
+    rowcol = _dev_contig(rowcol, torch.int32)
+    seg_off = _dev_contig(seg_off, torch.int64)
+    cap = int(rowcol.shape[0]) if cap is None else int(cap)
+    out = torch.full((max(cap, 1),), -1, dtype=torch.int32, device=label_img.device)
+    L.check(L.lib().xm3d_gather_labels_batch(_ptr(label_img), n_seg, h, w, _ptr(rowcol), _ptr(seg_off), cap, _ptr(out),
+                                             _stream()))
+    return out
