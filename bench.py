@@ -537,6 +537,45 @@ def run_native(args, rank: int, world: int, local_rank: int):
     except Exception as e:                      # noqa: BLE001
         logits_info = {"error": f"{type(e).__name__}: {e}"[:200]}
 
+    # ---- mask preparation: low-resolution logits of the mask head -> membership words /
+    # partition labels of every view of the batch, one fused pass (timed apart, not part of the metric)
+    mask_prep_info = {}
+    try:
+        from xmask3d_b200 import ops as _ops
+        import torch.nn.functional as _F
+        gm = torch.Generator(device=dev).manual_seed(2)
+        lg = torch.randn(batch.n_views, args.k, 16, 16, device=dev, generator=gm)
+        lg = _F.interpolate(lg, size=(128, 128), mode="bicubic", align_corners=False).contiguous() * 3.0
+        scm = torch.rand(batch.n_views, args.k, device=dev, generator=gm) + 0.05
+
+        def _time(fn, n):
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(n):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / n
+
+        def _torch_ops():
+            up = _F.interpolate(lg, size=(240, 320), mode="bilinear", align_corners=False)
+            sg = up.sigmoid()
+            return sg > 0.5, (scm.view(batch.n_views, args.k, 1, 1) * sg).argmax(1)
+        mask_prep_info = {
+            "shape": f"{batch.n_views} views x {args.k} masks, 128x128 -> 240x320",
+            "bits_ms": _time(lambda: _ops.mask_prep(lg, (240, 320), mode="sigmoid_gt0.5", want_bits=True), 10),
+            "partition_ms": _time(lambda: _ops.mask_prep(lg, (240, 320), scores=scm, want_bits=False,
+                                                         want_partition=True), 10),
+            "torch_cuda_ops_ms": _time(_torch_ops, 3),
+            "note": "fused bilinear upsample + sigmoid threshold (+ score-weighted argmax partition and areas); "
+                    "torch_cuda_ops = interpolate + sigmoid + mul + argmax + compare on the same GPU",
+        }
+        del lg
+    except Exception as e:                      # noqa: BLE001
+        mask_prep_info = {"error": f"{type(e).__name__}: {e}"[:200]}
+
     # ---- roofline of the dominant kernel (pool) and of the whole step
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -579,6 +618,7 @@ def run_native(args, rank: int, world: int, local_rank: int):
                               "frac": pipe_gbs / peak},
         "stage_ms": stage_ms,
         "logits": logits_info,
+        "mask_prep": mask_prep_info,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "unpipelined_value": e2e_serial,
                 "note": "double-buffered: copy-in / compute / copy-out streams overlap across steps; host->device: scene xyz, depth PNG arrays, view records (the reference's loader-side numpy inputs); "

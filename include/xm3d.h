@@ -263,6 +263,16 @@ XM3D_API int xm3d_gather_labels_batch(const int16_t *label_img, int32_t n_seg, i
                              const int32_t *rowcol, const int64_t *seg_off, int64_t cap,
                              int32_t *point_label, xm3d_stream_t stream);
 
+/* ------------------------------------------------------------------ after the path: batch layout
+ * collation_fn (dataset/data_loader.py:319-357) on the device, from the outputs of the stages above:
+ *   ori_coords (optional) [total visible, 4] float32: (batch item, x, y, z)   from xyz_vis / vis_off
+ *   coords     (optional) [total voxels, 4]  int32:   (batch item, vx, vy, vz) from voxel_xyz / uniq_off
+ * cap bounds both row counts; inds_reconstruct with the cumulative voxel offset is the `inverse`
+ * output of xm3d_voxelize_batch(collate = 1); x_label / y_label are the columns of rowcol. */
+XM3D_API int xm3d_collate_batch(const float *xyz_vis, const int64_t *vis_off, const int32_t *voxel_xyz,
+                       const int64_t *uniq_off, int32_t n_seg, int64_t cap, float *ori_coords,
+                       int32_t *coords, xm3d_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

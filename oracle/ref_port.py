@@ -409,3 +409,25 @@ def mask_prep_ref(mask_pred_lowres, scores, mask_shape, score_thresh=0.0):
                 final_mask.append(mask)
     return {"up": up, "sig": mask_pred, "keep": keep, "ids": ids, "final_keep": final_keep,
             "final_mask": final_mask, "areas": areas, "prob": prob, "kept": kept}
+
+
+# ----------------------------------------------------------------------------- batch layout
+def collation_ref(locals_3d, coords, inds_reconstruct):
+    """The index-carrying part of collation_fn (dataset/data_loader.py:337-342, 345-346, 355): every
+    sample arrives with a leading column of ones (data_loader.py:262-265, 283-285), which `[:, 0] *= i` turns
+    into the batch index; inds_reconstruct is shifted by the voxels of the samples before it."""
+    import torch
+    loc_out, crd_out, ind_out = [], [], []
+    acc = 0
+    for i in range(len(coords)):
+        l3 = torch.cat((torch.ones(len(locals_3d[i]), 1, dtype=torch.float32),
+                        torch.as_tensor(locals_3d[i], dtype=torch.float32)), dim=1)
+        cd = torch.cat((torch.ones(len(coords[i]), 1, dtype=torch.int32),
+                        torch.as_tensor(coords[i]).to(torch.int32)), dim=1)
+        cd[:, 0] *= i
+        l3[:, 0] *= i
+        ind_out.append(acc + torch.as_tensor(inds_reconstruct[i], dtype=torch.int64))
+        acc += cd.shape[0]
+        loc_out.append(l3)
+        crd_out.append(cd)
+    return torch.cat(loc_out), torch.cat(crd_out), torch.cat(ind_out)

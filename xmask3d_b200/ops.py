@@ -464,3 +464,19 @@ def gather_labels(label_img: torch.Tensor, rowcol: torch.Tensor, seg_off: torch.
     L.check(L.lib().xm3d_gather_labels_batch(_ptr(label_img), n_seg, h, w, _ptr(rowcol), _ptr(seg_off), cap, _ptr(out),
                                              _stream()))
     return out
+
+
+# ----------------------------------------------------------------------------- after the path: batch layout
+def collate(proj: Projection, vox: Unique, cap: Optional[int] = None):
+    """collation_fn (dataset/data_loader.py:319-357) on the device.  Returns (ori_coords float32 [cap,4],
+    coords int32 [cap,4]); rows beyond vis_off[-1] / uniq_off[-1] are unspecified.  inds_reconstruct is
+    `vox.inverse` of voxelize_batch(collate=True), x_label / y_label = proj.rowcol[:, 0] / [:, 1]."""
+    _require_cuda()
+    dev = proj.xyz_vis.device
+    n_seg = proj.vis_off.numel() - 1
+    cap = int(proj.xyz_vis.shape[0]) if cap is None else int(cap)
+    ori = torch.empty((max(cap, 1), 4), dtype=torch.float32, device=dev)
+    coords = torch.empty((max(cap, 1), 4), dtype=torch.int32, device=dev)
+    L.check(L.lib().xm3d_collate_batch(_ptr(proj.xyz_vis), _ptr(proj.vis_off), _ptr(vox.voxel_xyz), _ptr(vox.uniq_off),
+                                       n_seg, cap, _ptr(ori), _ptr(coords), _stream()))
+    return ori, coords
