@@ -150,6 +150,16 @@ XM3D_API size_t xm3d_ravel_ws_bytes(int32_t dim);
  *   voxel_xyz     [uniq_off[s]+r, 3] int32 voxel coordinates in unique order (grid[inds])
  * other outputs as xm3d_unique_batch. */
 XM3D_API size_t xm3d_voxelize_ws_bytes(int32_t n_seg, int64_t cap);
+/* Path selection of xm3d_unique_batch / xm3d_voxelize_batch (both paths are bit-identical; tests and
+ * A/B timings use it).  mode 0 (default): shared-memory units whenever every segment fits, the
+ * multi-kernel global-memory path otherwise; mode 1: multi-kernel path only.  unit_pts: points per
+ * unit the plan aims at (0 = default 7000; smaller values force several key-range units per segment). */
+XM3D_API void xm3d_set_voxel_path(int32_t mode, int32_t unit_pts);
+/* Which path the last call on this workspace took (synchronises the stream; diagnostics / tests):
+ * ctl_host[0] = 1 if the batch was not eligible for the shared-memory path, ctl_host[1] = 1 if a
+ * unit overflowed and the batch was recomputed by the multi-kernel path. */
+XM3D_API int xm3d_voxel_path_info(const void *ws, int32_t n_seg, int64_t cap, int32_t *ctl_host,
+                         xm3d_stream_t stream);
 XM3D_API int xm3d_voxelize_batch(const float *xyz, const int64_t *seg_off, int32_t n_seg, int64_t cap,
                         const double *rt, int32_t *m, int64_t *uniq_off, int32_t *first,
                         int32_t *inverse, int32_t collate, int32_t *voxel_xyz, int32_t *grid_min,

@@ -199,6 +199,103 @@ def test_voxelize_vs_oracle_batched(cport, dev):
     assert m[2] > 65536 and 4096 < m[0] < 65536 and m[3] == 1 and m[4] == 3
 
 
+@pytest.mark.parametrize("mode,unit_pts", [(0, 0), (0, 1200), (0, 64), (1, 0)])
+def test_voxelize_paths_vs_oracle(cport, dev, mode, unit_pts):
+    """The shared-memory unit path (default; several key-range units per segment when unit_pts is
+    small), the multi-kernel path (mode 1) and the overflow fallback all give the oracle's result:
+    ragged batch with an empty, a 1-point, an all-duplicates, a very fine and a coarse segment."""
+    from xmask3d_b200 import ops
+    rng = np.random.default_rng(12)
+    sc = syn.make_scene(7, 150_000)
+    if unit_pts == 64:          # 64-point units: keep every segment below 32 units
+        segs = [(sc.xyz[:2000], _random_rt(rng, 0.02)), (sc.xyz[:0], _random_rt(rng, 0.02)),
+                (sc.xyz[3000:3001], _random_rt(rng, 0.02)), (np.repeat(sc.xyz[:3], 600, 0), _random_rt(rng, 0.02)),
+                (sc.xyz[5000:5000 + 1025], _random_rt(rng, 0.005)), (sc.xyz[:64], _random_rt(rng, 0.02)),
+                (sc.xyz[:65], _random_rt(rng, 0.02))]
+    else:
+        segs = [(sc.xyz[:37_000], _random_rt(rng, 0.02)), (sc.xyz[:0], _random_rt(rng, 0.02)),
+                (sc.xyz[:900], _random_rt(rng, 0.02)), (sc.xyz[:1], _random_rt(rng, 0.02)),
+                (np.repeat(sc.xyz[:3], 2000, 0), _random_rt(rng, 0.02)),
+                (sc.xyz[50_000:50_000 + 8193], _random_rt(rng, 0.005)),
+                (sc.xyz[:14_000], _random_rt(rng, 0.02)), (sc.xyz[:0], _random_rt(rng, 0.02))]
+        if unit_pts == 0:
+            segs.append((sc.xyz, _random_rt(rng, 0.05)))
+    n = [s.shape[0] for s, _ in segs]
+    off = np.concatenate([[0], np.cumsum(n)]).astype(np.int64)
+    xyz = torch.from_numpy(np.concatenate([s for s, _ in segs])).to(dev)
+    rt = torch.from_numpy(np.stack([r[:3, :4] for _, r in segs])).to(dev)
+    ops.set_voxel_path(mode, unit_pts)
+    try:
+        for collate in (False, True):
+            u = ops.voxelize_batch(xyz, torch.from_numpy(off).to(dev), rt, collate=collate, cap=xyz.shape[0] + 777)
+            assert int(u.status.item()) == 0
+            assert ops.voxel_path_info(u) == ((1, 0) if mode == 1 else (0, 0))
+            m, uoff = u.m.cpu().numpy(), u.uniq_off.cpu().numpy()
+            first, inv, vox = u.first.cpu().numpy(), u.inverse.cpu().numpy(), u.voxel_xyz.cpu().numpy()
+            for i, (pts, r) in enumerate(segs):
+                if len(pts) == 0:
+                    assert m[i] == 0 and uoff[i + 1] == uoff[i]
+                    continue
+                rgrid, rfirst, rinv = cport.voxelize(pts, r)
+                assert m[i] == len(rfirst), f"segment {i}"
+                a = int(uoff[i])
+                assert np.array_equal(first[a:a + m[i]], rfirst), f"segment {i}"
+                assert np.array_equal(vox[a:a + m[i]].astype(np.float64), rgrid), f"segment {i}"
+                shift = a if collate else 0
+                assert np.array_equal(inv[off[i]:off[i + 1]] - shift, rinv), f"segment {i}"
+            assert uoff[-1] == m.sum()
+    finally:
+        ops.set_voxel_path(0, 0)
+
+
+def test_voxelize_unit_overflow_falls_back(cport, dev):
+    """A segment whose 1024 sample positions all hold the same voxel defeats the key-range split:
+    one unit receives ~20 k distinct keys, overflows its 8704-key table, and the batch is recomputed by
+    the multi-kernel path (same result, ctl = (0, 1)).  Keys-only variant through unique_batch too."""
+    from xmask3d_b200 import ops
+    rng = np.random.default_rng(13)
+    sc = syn.make_scene(8, 60_000)
+    n = 20 * 1024
+    pts = sc.xyz[:n].copy()
+    pts[np.arange(1024) * 20] = pts[0]
+    segs = [(sc.xyz[30_000:36_000], _random_rt(rng, 0.02)), (pts, _random_rt(rng, 0.004))]
+    off = np.concatenate([[0], np.cumsum([len(s) for s, _ in segs])]).astype(np.int64)
+    xyz = torch.from_numpy(np.concatenate([s for s, _ in segs])).to(dev)
+    rt = torch.from_numpy(np.stack([r[:3, :4] for _, r in segs])).to(dev)
+    u = ops.voxelize_batch(xyz, torch.from_numpy(off).to(dev), rt)
+    assert ops.voxel_path_info(u) == (0, 1)
+    m, uoff = u.m.cpu().numpy(), u.uniq_off.cpu().numpy()
+    for i, (p, r) in enumerate(segs):
+        rgrid, rfirst, rinv = cport.voxelize(p, r)
+        a = int(uoff[i])
+        assert m[i] == len(rfirst)
+        assert np.array_equal(u.first.cpu().numpy()[a:a + m[i]], rfirst)
+        assert np.array_equal(u.voxel_xyz.cpu().numpy()[a:a + m[i]].astype(np.float64), rgrid)
+        assert np.array_equal(u.inverse.cpu().numpy()[off[i]:off[i + 1]], rinv)
+    assert m[1] > 2 * 8704
+    # keys given (np.unique drop-in): fast path, several units per segment, adversarial keys
+    ksegs = [np.sort(rng.integers(0, 2 ** 63, 30_000, dtype=np.int64)).astype(np.uint64) * np.uint64(2),
+             np.full(5000, 12345, np.uint64), rng.integers(0, 40, 10_000).astype(np.uint64),
+             np.array([2 ** 64 - 2, 0, 2 ** 63, 0], np.uint64), np.zeros(0, np.uint64)]
+    koff = np.concatenate([[0], np.cumsum([len(s) for s in ksegs])]).astype(np.int64)
+    keys = torch.from_numpy(np.concatenate(ksegs).view(np.int64)).to(dev)
+    for unit_pts in (0, 300):
+        ops.set_voxel_path(0, unit_pts)
+        try:
+            ku = ops.unique_batch(keys, torch.from_numpy(koff).to(dev), collate=True)
+            if unit_pts == 0:
+                assert ops.voxel_path_info(ku) == (0, 0)
+        finally:
+            ops.set_voxel_path(0, 0)
+        km, kuoff = ku.m.cpu().numpy(), ku.uniq_off.cpu().numpy()
+        for i, ks in enumerate(ksegs):
+            rf, ri_, rc = cport.unique_u64(ks) if len(ks) else (np.zeros(0, np.int64),) * 3
+            a = int(kuoff[i])
+            assert km[i] == len(rf)
+            assert np.array_equal(ku.first.cpu().numpy()[a:a + km[i]], rf)
+            assert np.array_equal(ku.inverse.cpu().numpy()[koff[i]:koff[i + 1]] - a, ri_)
+
+
 def test_sparse_quantize_and_hashes_golden(golden, cport, dev):
     from xmask3d_b200.voxelization_utils import fnv_hash_vec, ravel_hash_vec, sparse_quantize
     g = golden("hash")

@@ -49,6 +49,8 @@ PROTOTYPES = {
     "xm3d_ravel_hash_f64": (C.c_int, [_P, _I64, _I32, _P, _P, _SZ, _P]),
     "xm3d_ravel_ws_bytes": (_SZ, [_I32]),
     "xm3d_voxelize_ws_bytes": (_SZ, [_I32, _I64]),
+    "xm3d_set_voxel_path": (None, [_I32, _I32]),
+    "xm3d_voxel_path_info": (C.c_int, [_P, _I32, _I64, _P, _P]),
     "xm3d_voxelize_batch": (C.c_int, [_P, _P, _I32, _I64, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _SZ, _P, _P]),
     "xm3d_mask_words": (_I32, [_I32]),
     "xm3d_gather_ws_bytes": (_SZ, [_I32, _I32, _I32, _I32]),

@@ -22,6 +22,16 @@
 //   inverse   inverse[i] = rank stored in the slot point i resolved to; first[rank] = atomicMin(i)
 //   coords    voxel coordinates of every unique key from its first occurrence, in unique order
 //
+// Fast path (vox_fast_kernel, taken whenever every segment fits): after `min` has written the grid
+// coordinates of every point, ONE persistent 1024-thread CTA per unit does insert / rank / inverse /
+// coords entirely in shared memory (16384-slot table of 64-bit keys, bucket ranking as above) — no
+// dependent global-memory round trips, so it does not starve next to the pooling stream.  A segment
+// of n points is split by KEY RANGE into ceil(n / unit_pts) units (splitters from a 1024-key
+// sample every unit of the segment computes identically); unique counts of the units are
+// exchanged through a decoupled look-back, which yields both the rank base inside the segment
+// and uniq_off.  A unit that overflows its table raises ctl[1] and the multi-kernel path below
+// (gated on ctl) recomputes the whole batch.
+//
 // Everything that decides an integer is exact: the transform is the fp64 FMA chain numpy's dgemm
 // performs, floor() is exact, keys are 64-bit so FNV collisions merge voxels exactly as the
 // reference's np.unique does.  The sample sort is comparison based, so the skewed high bits of
@@ -37,6 +47,19 @@ constexpr int VOX_THREADS = 256;
 constexpr int SPL_MAX = 4096;             // splitters (= buckets) per segment, at most
 constexpr int SPL_MIN = 32;
 constexpr int GRID_LIMIT = 1 << 30;
+// shared-memory fast path
+constexpr int FV_THREADS = 1024;
+constexpr int FV_TABLE = 16384;           // 64-bit key slots per unit (128 KB)
+constexpr int FV_MU = 8704;               // unique keys per unit, at most (load factor <= 0.53)
+constexpr int FV_UNIT_PTS = 7000;         // points per unit the plan aims at (24 % headroom to FV_MU)
+constexpr int FV_UNIT_PTS_MIN = 64;       // smallest value xm3d_set_voxel_path accepts (sizes the unit tables)
+constexpr int FV_PMAX = 32;               // units per segment, at most (224 k points)
+constexpr int FV_NS = 1024;               // sample keys for the key-range split / rank buckets
+constexpr size_t FV_SMEM = (size_t)FV_TABLE * 8 + (size_t)FV_MU * 4 + (size_t)FV_MU * 2 + (size_t)FV_MU * 4 +
+                           (size_t)FV_NS * 8 + (size_t)(FV_NS + 32) * 4;
+
+static int g_vox_mode = 0;                // 0: fast path when eligible, 1: multi-kernel path only
+static int g_vox_unit_pts = FV_UNIT_PTS;
 
 struct __align__(16) Slot {
     unsigned long long key;
@@ -173,41 +196,63 @@ __device__ __forceinline__ BlockSeg block_segment(const int64_t *__restrict__ se
 }
 
 // ---- plan ---------------------------------------------------------------------------------
+// ctl[0] = 1: the fast path is not eligible (decided here); ctl[1] = 1: a fast unit overflowed.
 __global__ void __launch_bounds__(1024, 1)
 vox_plan_kernel(const int64_t *__restrict__ seg_off, int n_seg, int64_t cap, int64_t *__restrict__ tbl_off,
                 int64_t *__restrict__ spl_off, int64_t *__restrict__ total_eff, int *__restrict__ m,
-                int *__restrict__ grid_min, int *status) {
+                int *__restrict__ grid_min, int *status, int unit_pts, int units_max, int force_slow,
+                int *__restrict__ unit_off, int *__restrict__ unit_seg, int *__restrict__ unit_m,
+                int *__restrict__ ctl) {
     __shared__ int64_t s_warp[32];
-    __shared__ int64_t s_carry[2];
+    __shared__ int64_t s_carry[3];
+    __shared__ int s_slow;
     const int tid = threadIdx.x;
     // more elements than the caller's capacity: flag it and process nothing (never overrun)
     const bool over = seg_off[n_seg] > cap;
     if (tid == 0) {
-        s_carry[0] = s_carry[1] = 0;
+        s_carry[0] = s_carry[1] = s_carry[2] = 0;
+        s_slow = force_slow;
         *total_eff = over ? 0 : seg_off[n_seg];
         if (over && status) atomicOr(status, XM3D_FLAG_VIS_OVERFLOW);
     }
+    for (int t = tid; t < units_max; t += 1024) unit_m[t] = -1;
     __syncthreads();
     for (int base = 0; base < n_seg; base += 1024) {
         const int s = base + tid;
-        int64_t vt = 0, vs = 0;
+        int64_t vt = 0, vs = 0, vu = 0;
         if (s < n_seg) {
             const int64_t n = over ? 0 : seg_off[s + 1] - seg_off[s];
             vt = table_size(n);
             vs = bucket_count(n);
+            vu = n <= unit_pts ? 1 : (n + unit_pts - 1) / unit_pts;
+            if (vu > FV_PMAX) { s_slow = 1; vu = 1; }
             m[s] = 0;
             if (grid_min) grid_min[3 * s] = grid_min[3 * s + 1] = grid_min[3 * s + 2] = 0x7fffffff;
         }
         const int64_t et = block_excl_scan_1024(vt, s_warp, &s_carry[0]);
         const int64_t es = block_excl_scan_1024(vs, s_warp, &s_carry[1]);
-        if (s < n_seg) { tbl_off[s] = et; spl_off[s] = es; }
+        const int64_t eu = block_excl_scan_1024(vu, s_warp, &s_carry[2]);
+        if (s < n_seg) {
+            tbl_off[s] = et; spl_off[s] = es; unit_off[s] = (int)eu;
+            if (eu + vu <= units_max)
+                for (int p = 0; p < (int)vu; ++p) unit_seg[eu + p] = s;
+        }
     }
-    if (tid == 0) { tbl_off[n_seg] = s_carry[0]; spl_off[n_seg] = s_carry[1]; }
+    __syncthreads();
+    if (tid == 0) {
+        tbl_off[n_seg] = s_carry[0]; spl_off[n_seg] = s_carry[1]; unit_off[n_seg] = (int)s_carry[2];
+        ctl[0] = (s_slow || s_carry[2] > units_max) ? 1 : 0;
+        ctl[1] = 0;
+    }
 }
 
 __global__ void __launch_bounds__(256)
 vox_clear_kernel(Slot *__restrict__ tbl, const int64_t *__restrict__ tbl_off, int n_seg,
-                 const int64_t *__restrict__ total_eff, int *__restrict__ first) {
+                 const int64_t *__restrict__ total_eff, int *__restrict__ first, int *__restrict__ m,
+                 const int *__restrict__ ctl) {
+    if (!(ctl[0] | ctl[1])) return;              // the fast path produced the result
+    // (a fast unit that overflowed may already have added its count)
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n_seg; s += gridDim.x * blockDim.x) m[s] = 0;
     const int64_t used = tbl_off[n_seg];
     const uint4 e = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
     uint4 *t = reinterpret_cast<uint4 *>(tbl);
@@ -222,7 +267,7 @@ vox_clear_kernel(Slot *__restrict__ tbl, const int64_t *__restrict__ tbl_off, in
 __global__ void __launch_bounds__(VOX_THREADS)
 vox_min_kernel(const float *__restrict__ xyz, const int64_t *__restrict__ seg_off, int n_seg,
                const int64_t *__restrict__ total_eff, const double *__restrict__ rt, int *__restrict__ grid_min,
-               int *status) {
+               int4 *__restrict__ pgrid, int *status) {
     __shared__ int s_min[VOX_THREADS / 32][3];
     __shared__ int s_pair[2];
     const int64_t total = *total_eff;
@@ -244,6 +289,7 @@ vox_min_kernel(const float *__restrict__ xyz, const int64_t *__restrict__ seg_of
             }
             g[j] = (int)f[j];
         }
+        if (pgrid) pgrid[i] = make_int4(g[0], g[1], g[2], 0);     // read by the fast path
     }
     if (bs.uniform) {                  // warp-shuffle min, then one atomic per block and column
 #pragma unroll
@@ -312,7 +358,8 @@ __global__ void __launch_bounds__(1024)
 vox_sample_kernel(const float *__restrict__ xyz, const unsigned long long *__restrict__ keys_in,
                   const int64_t *__restrict__ seg_off, const int64_t *__restrict__ total_eff,
                   const double *__restrict__ rt, const int *__restrict__ grid_min,
-                  const int64_t *__restrict__ spl_off, unsigned long long *__restrict__ spl, int *__restrict__ hist) {
+                  const int64_t *__restrict__ spl_off, unsigned long long *__restrict__ spl, int *__restrict__ hist, const int *__restrict__ ctl) {
+    if (!(ctl[0] | ctl[1])) return;              // the fast path produced the result
     __shared__ unsigned long long s_key[SPL_MAX];
     const int s = blockIdx.x, tid = threadIdx.x;
     const int64_t a = seg_off[s];
@@ -343,7 +390,8 @@ vox_insert_kernel(const float *__restrict__ xyz, const unsigned long long *__res
                   const unsigned long long *__restrict__ spl, int *__restrict__ hist,
                   unsigned int *__restrict__ pslot, unsigned int *__restrict__ uniq,
                   unsigned long long *__restrict__ ukey, unsigned int *__restrict__ ubkt,
-                  unsigned int *__restrict__ upos, int *__restrict__ m, int *status) {
+                  unsigned int *__restrict__ upos, int *__restrict__ m, int *status, const int *__restrict__ ctl) {
+    if (!(ctl[0] | ctl[1])) return;              // the fast path produced the result
     __shared__ int s_pair[2];
     const int64_t total = *total_eff;
     if ((int64_t)blockIdx.x * blockDim.x >= total) return;
@@ -425,7 +473,8 @@ vox_insert_kernel(const float *__restrict__ xyz, const unsigned long long *__res
 // ---- bucket scan: one CTA per segment -----------------------------------------------------
 __global__ void __launch_bounds__(256)
 vox_bscan_kernel(const int64_t *__restrict__ spl_off, int n_seg, int *__restrict__ hist, const int *__restrict__ m,
-                 int64_t *__restrict__ uniq_off) {
+                 int64_t *__restrict__ uniq_off, const int *__restrict__ ctl) {
+    if (!(ctl[0] | ctl[1])) return;              // the fast path produced the result
     __shared__ int s_w[8];
     __shared__ int64_t s_red[8];
     __shared__ int s_carry;
@@ -481,7 +530,8 @@ vox_scatter_kernel(const int64_t *__restrict__ seg_off, int n_seg, const int64_t
                    const int *__restrict__ m, const int64_t *__restrict__ spl_off, const int *__restrict__ hist,
                    const unsigned int *__restrict__ uniq, const unsigned long long *__restrict__ ukey,
                    const unsigned int *__restrict__ ubkt, const unsigned int *__restrict__ upos,
-                   unsigned long long *__restrict__ bk_key, unsigned long long *__restrict__ bk_sb) {
+                   unsigned long long *__restrict__ bk_key, unsigned long long *__restrict__ bk_sb, const int *__restrict__ ctl) {
+    if (!(ctl[0] | ctl[1])) return;              // the fast path produced the result
     __shared__ int s_pair[2];
     const int64_t total = *total_eff;
     if ((int64_t)blockIdx.x * blockDim.x >= total) return;
@@ -507,7 +557,8 @@ __global__ void __launch_bounds__(VOX_THREADS)
 vox_rank_kernel(const int64_t *__restrict__ seg_off, int n_seg, const int64_t *__restrict__ total_eff,
                 const int *__restrict__ m, const int64_t *__restrict__ spl_off, const int *__restrict__ hist,
                 const unsigned long long *__restrict__ bk_key, const unsigned long long *__restrict__ bk_sb,
-                Slot *__restrict__ tbl, const int64_t *__restrict__ tbl_off) {
+                Slot *__restrict__ tbl, const int64_t *__restrict__ tbl_off, const int *__restrict__ ctl) {
+    if (!(ctl[0] | ctl[1])) return;              // the fast path produced the result
     __shared__ int s_pair[2];
     __shared__ unsigned long long s_win[RANK_WIN];
     const int64_t total = *total_eff;
@@ -551,7 +602,8 @@ __global__ void __launch_bounds__(VOX_THREADS)
 vox_inverse_kernel(const int64_t *__restrict__ seg_off, int n_seg, const int64_t *__restrict__ total_eff,
                    const Slot *__restrict__ tbl, const int64_t *__restrict__ tbl_off,
                    const unsigned int *__restrict__ pslot, const int64_t *__restrict__ uniq_off, int collate,
-                   int *__restrict__ inverse, int *__restrict__ first, int *__restrict__ counts) {
+                   int *__restrict__ inverse, int *__restrict__ first, int *__restrict__ counts, const int *__restrict__ ctl) {
+    if (!(ctl[0] | ctl[1])) return;              // the fast path produced the result
     __shared__ int s_pair[2];
     const int64_t total = *total_eff;
     if ((int64_t)blockIdx.x * blockDim.x >= total) return;
@@ -570,7 +622,8 @@ vox_inverse_kernel(const int64_t *__restrict__ seg_off, int n_seg, const int64_t
 __global__ void __launch_bounds__(VOX_THREADS)
 vox_coords_kernel(const int64_t *__restrict__ seg_off, int n_seg, const int64_t *__restrict__ uniq_off,
                   const int *__restrict__ first, const float *__restrict__ xyz, const double *__restrict__ rt,
-                  const int *__restrict__ grid_min, int *__restrict__ voxel_xyz) {
+                  const int *__restrict__ grid_min, int *__restrict__ voxel_xyz, const int *__restrict__ ctl) {
+    if (!(ctl[0] | ctl[1])) return;              // the fast path produced the result
     __shared__ int s_pair[2];
     const int64_t total = uniq_off[n_seg];
     if ((int64_t)blockIdx.x * blockDim.x >= total) return;
@@ -584,6 +637,251 @@ vox_coords_kernel(const int64_t *__restrict__ seg_off, int n_seg, const int64_t 
     for (int j = 0; j < 3; ++j) {
         if (!(g[j] > -(double)GRID_LIMIT && g[j] < (double)GRID_LIMIT)) g[j] = 0.0;
         voxel_xyz[o * 3 + j] = (int)g[j] - grid_min[3 * s + j];
+    }
+}
+
+// ---- fast path: one persistent CTA per unit, everything in shared memory ----------------------
+static_assert(FV_TABLE == 1 << 14, "fv_hash yields 14 bits");
+__device__ __forceinline__ unsigned int fv_hash(unsigned long long key) {
+    const unsigned int x = (unsigned int)key ^ (unsigned int)(key >> 32);
+    return (x * 0x9E3779B1u) >> 18;
+}
+
+// key of element i: FNV-1 of (grid - min) from the grid coordinates the min pass stored, or the given key
+template <int KEY_SRC>
+__device__ __forceinline__ unsigned long long fv_key(const int4 *__restrict__ pgrid,
+                                                     const unsigned long long *__restrict__ keys_in, int64_t i,
+                                                     int g0, int g1, int g2, int *status) {
+    unsigned long long key;
+    if (KEY_SRC == 0) {
+        const int4 g = __ldg(pgrid + i);
+        key = fnv3((unsigned long long)(long long)(g.x - g0), (unsigned long long)(long long)(g.y - g1),
+                   (unsigned long long)(long long)(g.z - g2));
+    } else {
+        key = keys_in[i];
+    }
+    return clean_key(key, status);
+}
+
+template <int KEY_SRC>
+__global__ void __launch_bounds__(FV_THREADS, 1)
+vox_fast_kernel(const int4 *__restrict__ pgrid, const unsigned long long *__restrict__ keys_in,
+                const int64_t *__restrict__ seg_off, int n_seg, const int64_t *__restrict__ total_eff,
+                const int *__restrict__ unit_off, const int *__restrict__ unit_seg, int *unit_m, int *ctl,
+                const int *__restrict__ grid_min, unsigned int *__restrict__ pslot, int *__restrict__ m,
+                int64_t *__restrict__ uniq_off, int *__restrict__ first, int *__restrict__ inverse, int collate,
+                int *__restrict__ voxel_xyz, int *status) {
+    extern __shared__ __align__(16) unsigned char fv_smem[];
+    unsigned long long *s_tab = reinterpret_cast<unsigned long long *>(fv_smem);     // keys, later ranks
+    unsigned int *s_ub = reinterpret_cast<unsigned int *>(s_tab + FV_TABLE);          // bucket << 16 | ticket; later
+                                                                                      // ranks (u16), first index (int)
+    unsigned short *s_uslot = reinterpret_cast<unsigned short *>(s_ub + FV_MU);       // slot of unique u (insertion order)
+    unsigned int *s_bk = reinterpret_cast<unsigned int *>(s_uslot + FV_MU);           // bucket order: bucket << 16 | slot
+    unsigned long long *s_spl = reinterpret_cast<unsigned long long *>(s_bk + FV_MU); // sample keys / splitters
+    int *s_hist = reinterpret_cast<int *>(s_spl + FV_NS);                             // [S + 1]
+    __shared__ int s_cnt, s_ovf;
+    __shared__ long long s_red[2][32];
+    __shared__ int s_wsum[32];
+
+    if (ctl[0]) return;                           // not eligible: the multi-kernel path runs
+    const int u = blockIdx.x;
+    const int U = unit_off[n_seg];
+    if (u >= U) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int s = unit_seg[u];
+    const int u0 = unit_off[s];
+    const int p = u - u0, P = unit_off[s + 1] - u0;
+    const int64_t a = seg_off[s];
+    const int n = (*total_eff > 0) ? (int)(seg_off[s + 1] - a) : 0;
+    int g0 = 0, g1 = 0, g2 = 0;
+    if (KEY_SRC == 0) { g0 = grid_min[3 * s]; g1 = grid_min[3 * s + 1]; g2 = grid_min[3 * s + 2]; }
+
+    // key range of this unit: [klo, khi) between the P-quantiles of a 1024-key sample (every unit
+    // of the segment computes the same sample); KEY_EMPTY is never a key, so it closes the last range
+    unsigned long long klo = 0, khi = KEY_EMPTY;
+    if (P > 1) {
+        for (int j = tid; j < FV_NS; j += FV_THREADS)
+            s_spl[j] = fv_key<KEY_SRC>(pgrid, keys_in, a + (int64_t)j * n / FV_NS, g0, g1, g2, nullptr);
+        __syncthreads();
+        bitonic_smem(s_spl, FV_NS);
+        if (p > 0) klo = s_spl[(int)((int64_t)p * FV_NS / P)];
+        if (p < P - 1) khi = s_spl[(int)((int64_t)(p + 1) * FV_NS / P)];
+        __syncthreads();
+    }
+    for (int j = tid; j < FV_TABLE / 2; j += FV_THREADS)
+        reinterpret_cast<uint4 *>(s_tab)[j] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    if (tid == 0) { s_cnt = 0; s_ovf = 0; }
+    __syncthreads();
+
+    // ---- insert: open addressing in shared memory; the winner of an empty slot appends it to the unique list
+    volatile unsigned long long *vtab = s_tab;
+    for (int base = 0; base < n; base += FV_THREADS) {
+        int full = 0;
+        if (lane == 0) full = *reinterpret_cast<volatile int *>(&s_cnt) > FV_MU;
+        if (__shfl_sync(0xffffffffu, full, 0)) break;            // overflow: the batch is recomputed anyway
+        const int j = base + tid;
+        bool own = false;
+        unsigned long long key = 0;
+        if (j < n) {
+            key = fv_key<KEY_SRC>(pgrid, keys_in, a + j, g0, g1, g2, status);
+            own = key >= klo && key < khi;
+        }
+        unsigned int slot = 0;
+        bool is_new = false;
+        if (own) {
+            unsigned int h = fv_hash(key);
+            int probe = 0;
+            for (; probe < FV_TABLE; ++probe) {
+                unsigned long long cur = vtab[h];
+                if (cur == key) break;
+                if (cur == KEY_EMPTY) {
+                    cur = atomicCAS(&s_tab[h], KEY_EMPTY, key);
+                    if (cur == KEY_EMPTY) { is_new = true; break; }
+                    if (cur == key) break;
+                }
+                h = (h + 1) & (FV_TABLE - 1);
+            }
+            if (probe == FV_TABLE) s_ovf = 1;
+            slot = h;
+        }
+        __syncwarp();
+        const unsigned newm = __ballot_sync(0xffffffffu, is_new);
+        if (newm) {
+            int start = 0;
+            if (lane == 0) start = atomicAdd(&s_cnt, __popc(newm));
+            start = __shfl_sync(0xffffffffu, start, 0);
+            if (is_new) {
+                const int ui = start + __popc(newm & ((1u << lane) - 1u));
+                if (ui < FV_MU) s_uslot[ui] = (unsigned short)slot;
+            }
+        }
+        if (own) pslot[a + j] = slot;
+    }
+    __syncthreads();
+    const int M = s_cnt;
+    if (M > FV_MU || s_ovf) {                     // does not fit: publish (nobody may wait for ever) and fall back
+        if (tid == 0) { atomicExch(&ctl[1], 1); atomicExch(&unit_m[u], 0); }
+        return;
+    }
+    if (tid == 0) atomicExch(&unit_m[u], M);
+
+    // ---- rank of every unique key: sample -> splitters -> bucket tickets -> count inside the bucket
+    if (M > 0) {
+        int S = 32;
+        while (S < FV_NS && S * 8 < M) S <<= 1;
+        for (int j = tid; j < S; j += FV_THREADS) s_spl[j] = s_tab[s_uslot[(int)((int64_t)j * M / S)]];
+        for (int j = tid; j <= S; j += FV_THREADS) s_hist[j] = 0;
+        __syncthreads();
+        bitonic_smem(s_spl, S);
+        for (int q = tid; q < M; q += FV_THREADS) {
+            const unsigned long long key = s_tab[s_uslot[q]];
+            const int b = bucket_of(s_spl, S, key);
+            const int pos = atomicAdd(&s_hist[b], 1);
+            s_ub[q] = ((unsigned int)b << 16) | (unsigned int)pos;
+        }
+        __syncthreads();
+        {   // exclusive scan of the S <= 1024 bucket counts, one per thread
+            const int val = tid < S ? s_hist[tid] : 0;
+            int incl = val;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (lane == 31) s_wsum[warp] = incl;
+            __syncthreads();
+            if (warp == 0) {
+                const int w = s_wsum[lane];
+                int wi = w;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, wi, o);
+                    if (lane >= o) wi += t;
+                }
+                s_wsum[lane] = wi - w;
+            }
+            __syncthreads();
+            if (tid < S) s_hist[tid] = s_wsum[warp] + incl - val;
+            if (tid == 0) s_hist[S] = M;
+        }
+        __syncthreads();
+        for (int q = tid; q < M; q += FV_THREADS) {
+            const unsigned int ub = s_ub[q];
+            s_bk[s_hist[ub >> 16] + (int)(ub & 0xffffu)] = (ub & 0xffff0000u) | s_uslot[q];
+        }
+        __syncthreads();
+        unsigned short *s_rank = reinterpret_cast<unsigned short *>(s_ub);
+        for (int d = tid; d < M; d += FV_THREADS) {
+            const unsigned int sb = s_bk[d];
+            const int b = (int)(sb >> 16);
+            const unsigned long long key = s_tab[sb & 0xffffu];
+            const int lo = s_hist[b], hi = s_hist[b + 1];
+            int smaller = 0;
+            for (int q = lo; q < hi; ++q) smaller += (s_tab[s_bk[q] & 0xffffu] < key) ? 1 : 0;
+            s_rank[d] = (unsigned short)(lo + smaller);
+        }
+        __syncthreads();
+        for (int d = tid; d < M; d += FV_THREADS) s_tab[s_bk[d] & 0xffffu] = s_rank[d];   // keys are not needed any more
+        __syncthreads();
+    }
+
+    // ---- decoupled look-back: unique counts of all earlier units (blocks are dispatched in index order)
+    long long sum_all = 0, sum_seg = 0;
+    for (int t = tid; t < u; t += FV_THREADS) {
+        int v;
+        unsigned spin = 0;
+        while ((v = *reinterpret_cast<volatile int *>(&unit_m[t])) < 0) {
+            __nanosleep(64);
+            if (++spin > (1u << 24)) __trap();
+        }
+        sum_all += v;
+        if (t >= u0) sum_seg += v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum_all += __shfl_xor_sync(0xffffffffu, sum_all, o);
+        sum_seg += __shfl_xor_sync(0xffffffffu, sum_seg, o);
+    }
+    if (lane == 0) { s_red[0][warp] = sum_all; s_red[1][warp] = sum_seg; }
+    __syncthreads();
+    sum_all = 0; sum_seg = 0;
+    for (int w = 0; w < FV_THREADS / 32; ++w) { sum_all += s_red[0][w]; sum_seg += s_red[1][w]; }
+    const int64_t uo = sum_all - sum_seg;          // uniq_off[s]
+    const int rbase = (int)sum_seg;                // rank of this unit's smallest key inside the segment
+    if (tid == 0) {
+        if (p == 0) uniq_off[s] = uo;
+        if (u == U - 1) uniq_off[n_seg] = sum_all + M;
+        if (M > 0) atomicAdd(&m[s], M);
+    }
+    if (M == 0) return;
+
+    // ---- inverse map and first occurrence
+    int *s_first = reinterpret_cast<int *>(s_ub);
+    for (int r = tid; r < M; r += FV_THREADS) s_first[r] = 0x7fffffff;
+    __syncthreads();
+    const int add = rbase + (collate ? (int)uo : 0);
+    for (int base = 0; base < n; base += FV_THREADS) {
+        const int j = base + tid;
+        bool own = j < n;
+        if (own && P > 1) {
+            const unsigned long long key = fv_key<KEY_SRC>(pgrid, keys_in, a + j, g0, g1, g2, nullptr);
+            own = key >= klo && key < khi;
+        }
+        if (own) {
+            const int r = (int)s_tab[pslot[a + j]];
+            if (inverse) inverse[a + j] = add + r;
+            atomicMin(&s_first[r], j);
+        }
+    }
+    __syncthreads();
+    for (int r = tid; r < M; r += FV_THREADS) {
+        const int f = s_first[r];
+        const int64_t o = uo + rbase + r;
+        first[o] = f;
+        if (KEY_SRC == 0 && voxel_xyz) {
+            const int4 g = __ldg(pgrid + a + f);
+            voxel_xyz[o * 3 + 0] = g.x - g0; voxel_xyz[o * 3 + 1] = g.y - g1; voxel_xyz[o * 3 + 2] = g.z - g2;
+        }
     }
 }
 
@@ -662,6 +960,9 @@ struct VoxWs {
     unsigned int *pslot, *uniq, *ubkt, *upos;
     unsigned long long *ukey, *bk_key, *bk_sb, *spl;
     int *hist, *grid_min;
+    int4 *pgrid;                       // grid coordinates of every point (fast path, voxel coords)
+    int *unit_off, *unit_seg, *unit_m, *ctl;
+    int units_cap;
 };
 
 static VoxWs carve_vox(void *ws, int n_seg, int64_t cap, size_t *bytes) {
@@ -683,6 +984,12 @@ static VoxWs carve_vox(void *ws, int n_seg, int64_t cap, size_t *bytes) {
     w.spl = c.take<unsigned long long>(nspl);
     w.hist = c.take<int>(nspl);
     w.grid_min = c.take<int>(3 * (size_t)n_seg);
+    w.pgrid = c.take<int4>((size_t)cap);
+    w.units_cap = (int)(cap / FV_UNIT_PTS_MIN + n_seg);
+    w.unit_off = c.take<int>((size_t)n_seg + 1);
+    w.unit_seg = c.take<int>((size_t)w.units_cap);
+    w.unit_m = c.take<int>((size_t)w.units_cap);
+    w.ctl = c.take<int>(64);
     *bytes = c.off + 256;
     return w;
 }
@@ -699,52 +1006,76 @@ static int run_unique(const float *xyz, const unsigned long long *keys, const in
     }
     int *gmin = grid_min_out ? grid_min_out : w.grid_min;
     const unsigned blocks = (unsigned)((cap + VOX_THREADS - 1) / VOX_THREADS);
+    // fast path: one shared-memory CTA per unit; the multi-kernel path below is gated on w.ctl
+    const int unit_pts = g_vox_unit_pts;
+    int64_t units_max64 = cap / unit_pts + n_seg;
+    if (units_max64 > w.units_cap) units_max64 = w.units_cap;
+    const int units_max = (int)units_max64;
+    const int force_slow = (g_vox_mode == 1 || counts != nullptr) ? 1 : 0;
+    static bool smem_set = false;
+    if (!smem_set) {
+        cudaFuncSetAttribute(vox_fast_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FV_SMEM);
+        cudaFuncSetAttribute(vox_fast_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FV_SMEM);
+        smem_set = true;
+    }
     vox_plan_kernel<<<1, 1024, 0, stream>>>(seg_off, n_seg, cap, w.tbl_off, w.spl_off, w.total_eff, m,
-                                            xyz ? gmin : nullptr, status);
+                                            xyz ? gmin : nullptr, status, unit_pts, units_max, force_slow,
+                                            w.unit_off, w.unit_seg, w.unit_m, w.ctl);
     count_launches(1);
-    vox_clear_kernel<<<(unsigned)(sm_count() * 8), 256, 0, stream>>>(w.tbl, w.tbl_off, n_seg, w.total_eff, first);
+    if (xyz && blocks) {
+        vox_min_kernel<<<blocks, VOX_THREADS, 0, stream>>>(xyz, seg_off, n_seg, w.total_eff, rt, gmin, w.pgrid, status);
+        count_launches(1);
+    }
+    if (!force_slow) {
+        if (xyz)
+            vox_fast_kernel<0><<<units_max, FV_THREADS, FV_SMEM, stream>>>(
+                w.pgrid, nullptr, seg_off, n_seg, w.total_eff, w.unit_off, w.unit_seg, w.unit_m, w.ctl, gmin, w.pslot, m,
+                uniq_off, first, inverse, collate, voxel_xyz, status);
+        else
+            vox_fast_kernel<1><<<units_max, FV_THREADS, FV_SMEM, stream>>>(
+                nullptr, keys, seg_off, n_seg, w.total_eff, w.unit_off, w.unit_seg, w.unit_m, w.ctl, nullptr, w.pslot, m,
+                uniq_off, first, inverse, collate, nullptr, status);
+        count_launches(1);
+    }
+    vox_clear_kernel<<<(unsigned)(sm_count() * 8), 256, 0, stream>>>(w.tbl, w.tbl_off, n_seg, w.total_eff, first, m, w.ctl);
     count_launches(1);
     if (counts) cudaMemsetAsync(counts, 0, sizeof(int) * cap, stream);
     if (xyz) {
-        if (blocks) {
-            vox_min_kernel<<<blocks, VOX_THREADS, 0, stream>>>(xyz, seg_off, n_seg, w.total_eff, rt, gmin, status);
-            count_launches(1);
-        }
         vox_sample_kernel<0><<<n_seg, 1024, 0, stream>>>(xyz, nullptr, seg_off, w.total_eff, rt, gmin, w.spl_off, w.spl,
-                                                        w.hist);
+                                                        w.hist, w.ctl);
         count_launches(1);
         if (blocks) {
             vox_insert_kernel<0><<<blocks, VOX_THREADS, 0, stream>>>(xyz, nullptr, seg_off, n_seg, w.total_eff, rt, gmin,
                                                                      w.tbl, w.tbl_off, w.spl_off, w.spl, w.hist, w.pslot,
-                                                                     w.uniq, w.ukey, w.ubkt, w.upos, m, status);
+                                                                     w.uniq, w.ukey, w.ubkt, w.upos, m, status, w.ctl);
             count_launches(1);
         }
     } else {
         vox_sample_kernel<1><<<n_seg, 1024, 0, stream>>>(nullptr, keys, seg_off, w.total_eff, nullptr, nullptr, w.spl_off,
-                                                        w.spl, w.hist);
+                                                        w.spl, w.hist, w.ctl);
         count_launches(1);
         if (blocks) {
             vox_insert_kernel<1><<<blocks, VOX_THREADS, 0, stream>>>(nullptr, keys, seg_off, n_seg, w.total_eff, nullptr,
                                                                      nullptr, w.tbl, w.tbl_off, w.spl_off, w.spl, w.hist,
-                                                                     w.pslot, w.uniq, w.ukey, w.ubkt, w.upos, m, status);
+                                                                     w.pslot, w.uniq, w.ukey, w.ubkt, w.upos, m, status, w.ctl);
             count_launches(1);
         }
     }
-    vox_bscan_kernel<<<n_seg, 256, 0, stream>>>(w.spl_off, n_seg, w.hist, m, uniq_off);
+    vox_bscan_kernel<<<n_seg, 256, 0, stream>>>(w.spl_off, n_seg, w.hist, m, uniq_off, w.ctl);
     count_launches(1);
     if (blocks) {
         vox_scatter_kernel<<<blocks, VOX_THREADS, 0, stream>>>(seg_off, n_seg, w.total_eff, m, w.spl_off, w.hist, w.uniq,
-                                                               w.ukey, w.ubkt, w.upos, w.bk_key, w.bk_sb);
+                                                               w.ukey, w.ubkt, w.upos, w.bk_key, w.bk_sb, w.ctl);
         count_launches(1);
         vox_rank_kernel<<<blocks, VOX_THREADS, 0, stream>>>(seg_off, n_seg, w.total_eff, m, w.spl_off, w.hist, w.bk_key,
-                                                            w.bk_sb, w.tbl, w.tbl_off);
+                                                            w.bk_sb, w.tbl, w.tbl_off, w.ctl);
         count_launches(1);
         vox_inverse_kernel<<<blocks, VOX_THREADS, 0, stream>>>(seg_off, n_seg, w.total_eff, w.tbl, w.tbl_off, w.pslot,
-                                                               uniq_off, collate, inverse, first, counts);
+                                                               uniq_off, collate, inverse, first, counts, w.ctl);
         count_launches(1);
         if (xyz && voxel_xyz) {
             vox_coords_kernel<<<blocks, VOX_THREADS, 0, stream>>>(seg_off, n_seg, uniq_off, first, xyz, rt, gmin,
-                                                                  voxel_xyz);
+                                                                  voxel_xyz, w.ctl);
             count_launches(1);
         }
     }
@@ -754,6 +1085,24 @@ static int run_unique(const float *xyz, const unsigned long long *keys, const in
 }  // namespace xm3d
 
 using namespace xm3d;
+
+extern "C" void xm3d_set_voxel_path(int32_t mode, int32_t unit_pts) {
+    g_vox_mode = mode == 1 ? 1 : 0;
+    g_vox_unit_pts = unit_pts <= 0 ? FV_UNIT_PTS : (unit_pts < FV_UNIT_PTS_MIN ? FV_UNIT_PTS_MIN
+                                                    : (unit_pts > FV_UNIT_PTS ? FV_UNIT_PTS : unit_pts));
+}
+
+extern "C" int xm3d_voxel_path_info(const void *ws, int32_t n_seg, int64_t cap, int32_t *ctl_host,
+                                    xm3d_stream_t stream_) {
+    XM3D_REQUIRE(ws && ctl_host && n_seg > 0 && cap >= 0, "bad arguments");
+    size_t need = 0;
+    const VoxWs w = carve_vox(const_cast<void *>(ws), n_seg, cap, &need);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (cudaMemcpyAsync(ctl_host, w.ctl, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
+        cudaStreamSynchronize(stream) != cudaSuccess)
+        return check_launch("xm3d_voxel_path_info");
+    return XM3D_OK;
+}
 
 extern "C" size_t xm3d_unique_ws_bytes(int32_t n_seg, int64_t cap) {
     size_t b = 0;

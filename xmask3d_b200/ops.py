@@ -140,6 +140,23 @@ class Unique:
     status: torch.Tensor
     voxel_xyz: Optional[torch.Tensor] = None   # int32 [cap,3]
     grid_min: Optional[torch.Tensor] = None    # int32 [n_seg,3]
+    ws: Optional[torch.Tensor] = None          # workspace of the call (voxel_path_info reads it)
+    cap: Optional[int] = None
+
+
+def set_voxel_path(mode: int = 0, unit_pts: int = 0) -> None:
+    """0: shared-memory units when every segment fits (default), 1: multi-kernel path only;
+    unit_pts < 7000 forces several key-range units per segment (tests)."""
+    L.lib().xm3d_set_voxel_path(int(mode), int(unit_pts))
+
+
+def voxel_path_info(u: "Unique"):
+    """(not_eligible, overflowed) of the call that produced `u` (synchronises)."""
+    out = (C.c_int32 * 2)()
+    n_seg = u.m.numel()
+    L.check(L.lib().xm3d_voxel_path_info(_ptr(u.ws), n_seg, int(u.first.numel() if u.cap is None else u.cap),
+                                         C.cast(out, C.c_void_p), _stream()))
+    return int(out[0]), int(out[1])
 
 
 def unique_batch(keys: torch.Tensor, seg_off: torch.Tensor, cap: Optional[int] = None, collate: bool = False,
@@ -163,7 +180,7 @@ def unique_batch(keys: torch.Tensor, seg_off: torch.Tensor, cap: Optional[int] =
     L.check(L.lib().xm3d_unique_batch(_ptr(keys), _ptr(seg_off), n_seg, cap, _ptr(m), _ptr(uniq_off), _ptr(first),
                                       _ptr(counts), _ptr(inverse), int(collate), _ptr(ws), ws.numel(),
                                       _ptr(status), _stream()))
-    return Unique(m, uniq_off, first, inverse, counts, status)
+    return Unique(m, uniq_off, first, inverse, counts, status, ws=ws, cap=cap)
 
 
 def voxelize_batch(xyz: torch.Tensor, seg_off: torch.Tensor, rt: torch.Tensor, cap: Optional[int] = None,
@@ -191,7 +208,7 @@ def voxelize_batch(xyz: torch.Tensor, seg_off: torch.Tensor, rt: torch.Tensor, c
     L.check(L.lib().xm3d_voxelize_batch(_ptr(xyz), _ptr(seg_off), n_seg, cap, _ptr(rt), _ptr(m), _ptr(uniq_off),
                                         _ptr(first), _ptr(inverse), int(collate), _ptr(voxel), _ptr(gmin),
                                         _ptr(ws), ws.numel(), _ptr(status), _stream()))
-    return Unique(m, uniq_off, first, inverse, None, status, voxel, gmin)
+    return Unique(m, uniq_off, first, inverse, None, status, voxel, gmin, ws=ws, cap=cap)
 
 
 def fnv_hash(coords: torch.Tensor) -> torch.Tensor:
