@@ -48,12 +48,18 @@ constexpr int SPL_MAX = 4096;             // splitters (= buckets) per segment, 
 constexpr int SPL_MIN = 32;
 constexpr int GRID_LIMIT = 1 << 30;
 // shared-memory fast path
-constexpr int FV_THREADS = 1024;
+#ifndef XM3D_FV_THREADS
+#define XM3D_FV_THREADS 1024
+#endif
+// (measured: 512- / 256-thread units, which leave room for the pooling stream's CTAs on the same SM, make
+// the step slower — 1.82 / 1.95 ms against 1.80 ms — the SM time of the two streams simply adds up)
+constexpr int FV_THREADS = XM3D_FV_THREADS;
 constexpr int FV_TABLE = 16384;           // 64-bit key slots per unit (128 KB)
 constexpr int FV_MU = 8704;               // unique keys per unit, at most (load factor <= 0.53)
 constexpr int FV_UNIT_PTS = 7000;         // points per unit the plan aims at (24 % headroom to FV_MU)
 constexpr int FV_UNIT_PTS_MIN = 64;       // smallest value xm3d_set_voxel_path accepts (sizes the unit tables)
 constexpr int FV_PMAX = 32;               // units per segment, at most (224 k points)
+constexpr int FV_BATCH = 4;               // loads a thread keeps in flight in the point passes
 constexpr int FV_NS = 1024;               // sample keys for the key-range split / rank buckets
 constexpr size_t FV_SMEM = (size_t)FV_TABLE * 8 + (size_t)FV_MU * 4 + (size_t)FV_MU * 2 + (size_t)FV_MU * 4 +
                            (size_t)FV_NS * 8 + (size_t)(FV_NS + 32) * 4;
@@ -647,25 +653,36 @@ __device__ __forceinline__ unsigned int fv_hash(unsigned long long key) {
     return (x * 0x9E3779B1u) >> 18;
 }
 
-// key of element i: FNV-1 of (grid - min) from the grid coordinates the min pass stored, or the given key
+// key of an element: FNV-1 of (grid - min) from the grid coordinates the min pass stored, or the given key.
+// fv_load / fv_make are separate so that a thread can put several loads in flight before it hashes.
+// (pgrid is read with plain loads: the owning unit tags .w in place during the insert pass.)
+struct FvRaw { int4 g; unsigned long long k; };
 template <int KEY_SRC>
-__device__ __forceinline__ unsigned long long fv_key(const int4 *__restrict__ pgrid,
-                                                     const unsigned long long *__restrict__ keys_in, int64_t i,
-                                                     int g0, int g1, int g2, int *status) {
+__device__ __forceinline__ FvRaw fv_load(const int4 *pgrid, const unsigned long long *__restrict__ keys_in, int64_t i) {
+    FvRaw r;
+    if (KEY_SRC == 0) { r.g = pgrid[i]; r.k = 0; }
+    else { r.g = make_int4(0, 0, 0, 0); r.k = keys_in[i]; }
+    return r;
+}
+template <int KEY_SRC>
+__device__ __forceinline__ unsigned long long fv_make(const FvRaw &r, int g0, int g1, int g2, int *status) {
     unsigned long long key;
-    if (KEY_SRC == 0) {
-        const int4 g = __ldg(pgrid + i);
-        key = fnv3((unsigned long long)(long long)(g.x - g0), (unsigned long long)(long long)(g.y - g1),
-                   (unsigned long long)(long long)(g.z - g2));
-    } else {
-        key = keys_in[i];
-    }
+    if (KEY_SRC == 0)
+        key = fnv3((unsigned long long)(long long)(r.g.x - g0), (unsigned long long)(long long)(r.g.y - g1),
+                   (unsigned long long)(long long)(r.g.z - g2));
+    else
+        key = r.k;
     return clean_key(key, status);
+}
+template <int KEY_SRC>
+__device__ __forceinline__ unsigned long long fv_key(const int4 *pgrid, const unsigned long long *__restrict__ keys_in,
+                                                     int64_t i, int g0, int g1, int g2, int *status) {
+    return fv_make<KEY_SRC>(fv_load<KEY_SRC>(pgrid, keys_in, i), g0, g1, g2, status);
 }
 
 template <int KEY_SRC>
-__global__ void __launch_bounds__(FV_THREADS, 1)
-vox_fast_kernel(const int4 *__restrict__ pgrid, const unsigned long long *__restrict__ keys_in,
+__global__ void __launch_bounds__(FV_THREADS, 65536 / (FV_THREADS * 64))
+vox_fast_kernel(int4 *pgrid, const unsigned long long *__restrict__ keys_in,
                 const int64_t *__restrict__ seg_off, int n_seg, const int64_t *__restrict__ total_eff,
                 const int *__restrict__ unit_off, const int *__restrict__ unit_seg, int *unit_m, int *ctl,
                 const int *__restrict__ grid_min, unsigned int *__restrict__ pslot, int *__restrict__ m,
@@ -715,47 +732,60 @@ vox_fast_kernel(const int4 *__restrict__ pgrid, const unsigned long long *__rest
 
     // ---- insert: open addressing in shared memory; the winner of an empty slot appends it to the unique list
     volatile unsigned long long *vtab = s_tab;
-    for (int base = 0; base < n; base += FV_THREADS) {
+    const unsigned int tag = (unsigned int)(p + 1) << 16;          // owner mark in pgrid[i].w (slot in the low half)
+    for (int base = 0; base < n; base += FV_BATCH * FV_THREADS) {
         int full = 0;
         if (lane == 0) full = *reinterpret_cast<volatile int *>(&s_cnt) > FV_MU;
         if (__shfl_sync(0xffffffffu, full, 0)) break;            // overflow: the batch is recomputed anyway
-        const int j = base + tid;
-        bool own = false;
-        unsigned long long key = 0;
-        if (j < n) {
-            key = fv_key<KEY_SRC>(pgrid, keys_in, a + j, g0, g1, g2, status);
-            own = key >= klo && key < khi;
+        FvRaw raw[FV_BATCH];
+#pragma unroll
+        for (int k = 0; k < FV_BATCH; ++k) {
+            const int j = base + k * FV_THREADS + tid;
+            if (j < n) raw[k] = fv_load<KEY_SRC>(pgrid, keys_in, a + j);
         }
-        unsigned int slot = 0;
-        bool is_new = false;
-        if (own) {
-            unsigned int h = fv_hash(key);
-            int probe = 0;
-            for (; probe < FV_TABLE; ++probe) {
-                unsigned long long cur = vtab[h];
-                if (cur == key) break;
-                if (cur == KEY_EMPTY) {
-                    cur = atomicCAS(&s_tab[h], KEY_EMPTY, key);
-                    if (cur == KEY_EMPTY) { is_new = true; break; }
+#pragma unroll
+        for (int k = 0; k < FV_BATCH; ++k) {
+            const int j = base + k * FV_THREADS + tid;
+            bool own = false;
+            unsigned long long key = 0;
+            if (j < n) {
+                key = fv_make<KEY_SRC>(raw[k], g0, g1, g2, status);
+                own = key >= klo && key < khi;
+            }
+            unsigned int slot = 0;
+            bool is_new = false;
+            if (own) {
+                unsigned int h = fv_hash(key);
+                int probe = 0;
+                for (; probe < FV_TABLE; ++probe) {
+                    unsigned long long cur = vtab[h];
                     if (cur == key) break;
+                    if (cur == KEY_EMPTY) {
+                        cur = atomicCAS(&s_tab[h], KEY_EMPTY, key);
+                        if (cur == KEY_EMPTY) { is_new = true; break; }
+                        if (cur == key) break;
+                    }
+                    h = (h + 1) & (FV_TABLE - 1);
                 }
-                h = (h + 1) & (FV_TABLE - 1);
+                if (probe == FV_TABLE) s_ovf = 1;
+                slot = h;
             }
-            if (probe == FV_TABLE) s_ovf = 1;
-            slot = h;
-        }
-        __syncwarp();
-        const unsigned newm = __ballot_sync(0xffffffffu, is_new);
-        if (newm) {
-            int start = 0;
-            if (lane == 0) start = atomicAdd(&s_cnt, __popc(newm));
-            start = __shfl_sync(0xffffffffu, start, 0);
-            if (is_new) {
-                const int ui = start + __popc(newm & ((1u << lane) - 1u));
-                if (ui < FV_MU) s_uslot[ui] = (unsigned short)slot;
+            __syncwarp();
+            const unsigned newm = __ballot_sync(0xffffffffu, is_new);
+            if (newm) {
+                int start = 0;
+                if (lane == 0) start = atomicAdd(&s_cnt, __popc(newm));
+                start = __shfl_sync(0xffffffffu, start, 0);
+                if (is_new) {
+                    const int ui = start + __popc(newm & ((1u << lane) - 1u));
+                    if (ui < FV_MU) s_uslot[ui] = (unsigned short)slot;
+                }
+            }
+            if (own) {
+                if (KEY_SRC == 0) reinterpret_cast<unsigned int *>(pgrid + a + j)[3] = tag | slot;
+                else pslot[a + j] = slot;
             }
         }
-        if (own) pslot[a + j] = slot;
     }
     __syncthreads();
     const int M = s_cnt;
@@ -768,7 +798,7 @@ vox_fast_kernel(const int4 *__restrict__ pgrid, const unsigned long long *__rest
     // ---- rank of every unique key: sample -> splitters -> bucket tickets -> count inside the bucket
     if (M > 0) {
         int S = 32;
-        while (S < FV_NS && S * 8 < M) S <<= 1;
+        while (S < FV_NS && S < FV_THREADS && S * 8 < M) S <<= 1;
         for (int j = tid; j < S; j += FV_THREADS) s_spl[j] = s_tab[s_uslot[(int)((int64_t)j * M / S)]];
         for (int j = tid; j <= S; j += FV_THREADS) s_hist[j] = 0;
         __syncthreads();
@@ -791,7 +821,7 @@ vox_fast_kernel(const int4 *__restrict__ pgrid, const unsigned long long *__rest
             if (lane == 31) s_wsum[warp] = incl;
             __syncthreads();
             if (warp == 0) {
-                const int w = s_wsum[lane];
+                const int w = lane < FV_THREADS / 32 ? s_wsum[lane] : 0;
                 int wi = w;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
@@ -860,17 +890,33 @@ vox_fast_kernel(const int4 *__restrict__ pgrid, const unsigned long long *__rest
     for (int r = tid; r < M; r += FV_THREADS) s_first[r] = 0x7fffffff;
     __syncthreads();
     const int add = rbase + (collate ? (int)uo : 0);
-    for (int base = 0; base < n; base += FV_THREADS) {
-        const int j = base + tid;
-        bool own = j < n;
-        if (own && P > 1) {
-            const unsigned long long key = fv_key<KEY_SRC>(pgrid, keys_in, a + j, g0, g1, g2, nullptr);
-            own = key >= klo && key < khi;
+    for (int base = 0; base < n; base += FV_BATCH * FV_THREADS) {
+        unsigned int w[FV_BATCH];
+        unsigned long long kk[FV_BATCH];
+#pragma unroll
+        for (int k = 0; k < FV_BATCH; ++k) {
+            const int j = base + k * FV_THREADS + tid;
+            w[k] = 0; kk[k] = 0;
+            if (j < n) {
+                if (KEY_SRC == 0) w[k] = reinterpret_cast<const unsigned int *>(pgrid + a + j)[3];
+                else { w[k] = pslot[a + j]; if (P > 1) kk[k] = keys_in[a + j]; }
+            }
         }
-        if (own) {
-            const int r = (int)s_tab[pslot[a + j]];
-            if (inverse) inverse[a + j] = add + r;
-            atomicMin(&s_first[r], j);
+#pragma unroll
+        for (int k = 0; k < FV_BATCH; ++k) {
+            const int j = base + k * FV_THREADS + tid;
+            bool own = j < n;
+            if (KEY_SRC == 0) {
+                own = own && (w[k] & 0xffff0000u) == tag;      // tagged by this unit's insert pass (same thread)
+            } else if (own && P > 1) {
+                const unsigned long long key = clean_key(kk[k], nullptr);
+                own = key >= klo && key < khi;
+            }
+            if (own) {
+                const int r = (int)s_tab[w[k] & 0xffffu];
+                if (inverse) inverse[a + j] = add + r;
+                atomicMin(&s_first[r], j);
+            }
         }
     }
     __syncthreads();
@@ -879,7 +925,7 @@ vox_fast_kernel(const int4 *__restrict__ pgrid, const unsigned long long *__rest
         const int64_t o = uo + rbase + r;
         first[o] = f;
         if (KEY_SRC == 0 && voxel_xyz) {
-            const int4 g = __ldg(pgrid + a + f);
+            const int4 g = pgrid[a + f];
             voxel_xyz[o * 3 + 0] = g.x - g0; voxel_xyz[o * 3 + 1] = g.y - g1; voxel_xyz[o * 3 + 2] = g.z - g2;
         }
     }
