@@ -59,6 +59,7 @@ constexpr int FV_MU = 8704;               // unique keys per unit, at most (load
 constexpr int FV_UNIT_PTS = 7000;         // points per unit the plan aims at (24 % headroom to FV_MU)
 constexpr int FV_UNIT_PTS_MIN = 64;       // smallest value xm3d_set_voxel_path accepts (sizes the unit tables)
 constexpr int FV_PMAX = 32;               // units per segment, at most (224 k points)
+constexpr int FV_PROBE_MAX = 2048;        // a longer probe sequence means the table is (nearly) full: give up
 constexpr int FV_BATCH = 4;               // loads a thread keeps in flight in the point passes
 constexpr int FV_NS = 1024;               // sample keys for the key-range split / rank buckets
 constexpr size_t FV_SMEM = (size_t)FV_TABLE * 8 + (size_t)FV_MU * 4 + (size_t)FV_MU * 2 + (size_t)FV_MU * 4 +
@@ -648,6 +649,7 @@ vox_coords_kernel(const int64_t *__restrict__ seg_off, int n_seg, const int64_t 
 
 // ---- fast path: one persistent CTA per unit, everything in shared memory ----------------------
 static_assert(FV_TABLE == 1 << 14, "fv_hash yields 14 bits");
+static_assert(FV_TABLE / FV_THREADS <= 32 && FV_TABLE % FV_THREADS == 0, "table scan: one bit per slot");
 __device__ __forceinline__ unsigned int fv_hash(unsigned long long key) {
     const unsigned int x = (unsigned int)key ^ (unsigned int)(key >> 32);
     return (x * 0x9E3779B1u) >> 18;
@@ -680,6 +682,15 @@ __device__ __forceinline__ unsigned long long fv_key(const int4 *pgrid, const un
     return fv_make<KEY_SRC>(fv_load<KEY_SRC>(pgrid, keys_in, i), g0, g1, g2, status);
 }
 
+#ifdef XM3D_FV_TIMING
+__device__ long long *g_fv_dbg = nullptr;
+#define FV_T(i) do { if (threadIdx.x == 0 && g_fv_dbg) { g_fv_dbg[blockIdx.x * 32 + (i)] = clock64(); \
+    if ((i) == 0 || (i) == 8) { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); \
+                                g_fv_dbg[blockIdx.x * 32 + ((i) == 0 ? 28 : 29)] = (long long)gt; } } } while (0)
+#else
+#define FV_T(i) do { } while (0)
+#endif
+
 template <int KEY_SRC>
 __global__ void __launch_bounds__(FV_THREADS, 65536 / (FV_THREADS * 64))
 vox_fast_kernel(int4 *pgrid, const unsigned long long *__restrict__ keys_in,
@@ -710,6 +721,7 @@ vox_fast_kernel(int4 *pgrid, const unsigned long long *__restrict__ keys_in,
     const int p = u - u0, P = unit_off[s + 1] - u0;
     const int64_t a = seg_off[s];
     const int n = (*total_eff > 0) ? (int)(seg_off[s + 1] - a) : 0;
+    FV_T(0);
     int g0 = 0, g1 = 0, g2 = 0;
     if (KEY_SRC == 0) { g0 = grid_min[3 * s]; g1 = grid_min[3 * s + 1]; g2 = grid_min[3 * s + 2]; }
 
@@ -717,26 +729,27 @@ vox_fast_kernel(int4 *pgrid, const unsigned long long *__restrict__ keys_in,
     // of the segment computes the same sample); KEY_EMPTY is never a key, so it closes the last range
     unsigned long long klo = 0, khi = KEY_EMPTY;
     if (P > 1) {
-        for (int j = tid; j < FV_NS; j += FV_THREADS)
-            s_spl[j] = fv_key<KEY_SRC>(pgrid, keys_in, a + (int64_t)j * n / FV_NS, g0, g1, g2, nullptr);
+        const int ns = P <= 8 ? FV_NS / 4 : FV_NS;          // >= 32 sample keys per unit
+        for (int j = tid; j < ns; j += FV_THREADS)
+            s_spl[j] = fv_key<KEY_SRC>(pgrid, keys_in, a + (int64_t)j * n / ns, g0, g1, g2, nullptr);
         __syncthreads();
-        bitonic_smem(s_spl, FV_NS);
-        if (p > 0) klo = s_spl[(int)((int64_t)p * FV_NS / P)];
-        if (p < P - 1) khi = s_spl[(int)((int64_t)(p + 1) * FV_NS / P)];
+        bitonic_smem(s_spl, ns);
+        if (p > 0) klo = s_spl[(int)((int64_t)p * ns / P)];
+        if (p < P - 1) khi = s_spl[(int)((int64_t)(p + 1) * ns / P)];
         __syncthreads();
     }
+    FV_T(1);
     for (int j = tid; j < FV_TABLE / 2; j += FV_THREADS)
         reinterpret_cast<uint4 *>(s_tab)[j] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
     if (tid == 0) { s_cnt = 0; s_ovf = 0; }
     __syncthreads();
 
+    FV_T(2);
     // ---- insert: open addressing in shared memory; the winner of an empty slot appends it to the unique list
     volatile unsigned long long *vtab = s_tab;
     const unsigned int tag = (unsigned int)(p + 1) << 16;          // owner mark in pgrid[i].w (slot in the low half)
     for (int base = 0; base < n; base += FV_BATCH * FV_THREADS) {
-        int full = 0;
-        if (lane == 0) full = *reinterpret_cast<volatile int *>(&s_cnt) > FV_MU;
-        if (__shfl_sync(0xffffffffu, full, 0)) break;            // overflow: the batch is recomputed anyway
+        if (*reinterpret_cast<volatile int *>(&s_ovf)) break;      // overflow: the batch is recomputed anyway
         FvRaw raw[FV_BATCH];
 #pragma unroll
         for (int k = 0; k < FV_BATCH; ++k) {
@@ -746,48 +759,65 @@ vox_fast_kernel(int4 *pgrid, const unsigned long long *__restrict__ keys_in,
 #pragma unroll
         for (int k = 0; k < FV_BATCH; ++k) {
             const int j = base + k * FV_THREADS + tid;
-            bool own = false;
-            unsigned long long key = 0;
-            if (j < n) {
-                key = fv_make<KEY_SRC>(raw[k], g0, g1, g2, status);
-                own = key >= klo && key < khi;
-            }
-            unsigned int slot = 0;
-            bool is_new = false;
-            if (own) {
-                unsigned int h = fv_hash(key);
-                int probe = 0;
-                for (; probe < FV_TABLE; ++probe) {
-                    unsigned long long cur = vtab[h];
-                    if (cur == key) break;
-                    if (cur == KEY_EMPTY) {
-                        cur = atomicCAS(&s_tab[h], KEY_EMPTY, key);
-                        if (cur == KEY_EMPTY) { is_new = true; break; }
-                        if (cur == key) break;
-                    }
-                    h = (h + 1) & (FV_TABLE - 1);
+            if (j >= n) continue;
+            const unsigned long long key = fv_make<KEY_SRC>(raw[k], g0, g1, g2, status);
+            if (!(key >= klo && key < khi)) continue;
+            unsigned int h = fv_hash(key);
+            int probe = 0;
+            for (; probe < FV_PROBE_MAX; ++probe) {
+                unsigned long long cur = vtab[h];
+                if (cur == key) break;
+                if (cur == KEY_EMPTY) {
+                    cur = atomicCAS(&s_tab[h], KEY_EMPTY, key);
+                    if (cur == KEY_EMPTY || cur == key) break;
                 }
-                if (probe == FV_TABLE) s_ovf = 1;
-                slot = h;
+                h = (h + 1) & (FV_TABLE - 1);
             }
-            __syncwarp();
-            const unsigned newm = __ballot_sync(0xffffffffu, is_new);
-            if (newm) {
-                int start = 0;
-                if (lane == 0) start = atomicAdd(&s_cnt, __popc(newm));
-                start = __shfl_sync(0xffffffffu, start, 0);
-                if (is_new) {
-                    const int ui = start + __popc(newm & ((1u << lane) - 1u));
-                    if (ui < FV_MU) s_uslot[ui] = (unsigned short)slot;
-                }
+            if (probe == FV_PROBE_MAX) s_ovf = 1;
+            if (KEY_SRC == 0) reinterpret_cast<unsigned int *>(pgrid + a + j)[3] = tag | h;
+            else pslot[a + j] = h;
+        }
+    }
+    __syncthreads();
+    FV_T(3);
+    // ---- unique list: the occupied slots, found by scanning the table (no shared counter in the insert loop)
+    {
+        constexpr int SPT = FV_TABLE / FV_THREADS;                 // slots per thread
+        unsigned int occ = 0;
+#pragma unroll
+        for (int i = 0; i < SPT; ++i) occ |= (s_tab[i * FV_THREADS + tid] != KEY_EMPTY ? 1u : 0u) << i;   // conflict-free
+        const int val = __popc(occ);
+        int incl = val;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const int w = lane < FV_THREADS / 32 ? s_wsum[lane] : 0;
+            int wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
             }
-            if (own) {
-                if (KEY_SRC == 0) reinterpret_cast<unsigned int *>(pgrid + a + j)[3] = tag | slot;
-                else pslot[a + j] = slot;
+            s_wsum[lane] = wi - w;
+            if (lane == 31) s_cnt = wi;
+        }
+        __syncthreads();
+        int ui = s_wsum[warp] + incl - val;
+        if (s_cnt <= FV_MU) {
+            while (occ) {
+                const int i = __ffs(occ) - 1;
+                occ &= occ - 1;
+                s_uslot[ui++] = (unsigned short)(i * FV_THREADS + tid);
             }
         }
     }
     __syncthreads();
+    FV_T(9);
     const int M = s_cnt;
     if (M > FV_MU || s_ovf) {                     // does not fit: publish (nobody may wait for ever) and fall back
         if (tid == 0) { atomicExch(&ctl[1], 1); atomicExch(&unit_m[u], 0); }
@@ -803,13 +833,38 @@ vox_fast_kernel(int4 *pgrid, const unsigned long long *__restrict__ keys_in,
         for (int j = tid; j <= S; j += FV_THREADS) s_hist[j] = 0;
         __syncthreads();
         bitonic_smem(s_spl, S);
-        for (int q = tid; q < M; q += FV_THREADS) {
-            const unsigned long long key = s_tab[s_uslot[q]];
-            const int b = bucket_of(s_spl, S, key);
-            const int pos = atomicAdd(&s_hist[b], 1);
-            s_ub[q] = ((unsigned int)b << 16) | (unsigned int)pos;
+        FV_T(10);
+        int logS = 5;
+        while ((1 << logS) < S) ++logS;
+        // four independent binary searches per thread (the chain of dependent shared-memory loads is
+        // what bounds this phase); S is a power of two, so every search takes exactly log2 S steps
+        for (int q0 = tid; q0 < M; q0 += FV_BATCH * FV_THREADS) {
+            unsigned long long key[FV_BATCH];
+            int lo[FV_BATCH], hi[FV_BATCH];
+#pragma unroll
+            for (int k = 0; k < FV_BATCH; ++k) {
+                const int q = q0 + k * FV_THREADS;
+                key[k] = q < M ? s_tab[s_uslot[q]] : 0ull;
+                lo[k] = 0; hi[k] = S - 1;
+            }
+            for (int step = 0; step < logS; ++step) {
+#pragma unroll
+                for (int k = 0; k < FV_BATCH; ++k) {
+                    const int mid = (lo[k] + hi[k]) >> 1;
+                    if (s_spl[mid + 1] < key[k]) lo[k] = mid + 1; else hi[k] = mid;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < FV_BATCH; ++k) {
+                const int q = q0 + k * FV_THREADS;
+                if (q < M) {
+                    const int pos = atomicAdd(&s_hist[lo[k]], 1);
+                    s_ub[q] = ((unsigned int)lo[k] << 16) | (unsigned int)pos;
+                }
+            }
         }
         __syncthreads();
+        FV_T(11);
         {   // exclusive scan of the S <= 1024 bucket counts, one per thread
             const int val = tid < S ? s_hist[tid] : 0;
             int incl = val;
@@ -835,11 +890,13 @@ vox_fast_kernel(int4 *pgrid, const unsigned long long *__restrict__ keys_in,
             if (tid == 0) s_hist[S] = M;
         }
         __syncthreads();
+        FV_T(12);
         for (int q = tid; q < M; q += FV_THREADS) {
             const unsigned int ub = s_ub[q];
             s_bk[s_hist[ub >> 16] + (int)(ub & 0xffffu)] = (ub & 0xffff0000u) | s_uslot[q];
         }
         __syncthreads();
+        FV_T(13);
         unsigned short *s_rank = reinterpret_cast<unsigned short *>(s_ub);
         for (int d = tid; d < M; d += FV_THREADS) {
             const unsigned int sb = s_bk[d];
@@ -847,14 +904,23 @@ vox_fast_kernel(int4 *pgrid, const unsigned long long *__restrict__ keys_in,
             const unsigned long long key = s_tab[sb & 0xffffu];
             const int lo = s_hist[b], hi = s_hist[b + 1];
             int smaller = 0;
-            for (int q = lo; q < hi; ++q) smaller += (s_tab[s_bk[q] & 0xffffu] < key) ? 1 : 0;
+            int q = lo;
+            for (; q + 3 < hi; q += 4) {            // four mates in flight
+                const unsigned int b0 = s_bk[q], b1 = s_bk[q + 1], b2 = s_bk[q + 2], b3 = s_bk[q + 3];
+                const unsigned long long k0 = s_tab[b0 & 0xffffu], k1 = s_tab[b1 & 0xffffu];
+                const unsigned long long k2 = s_tab[b2 & 0xffffu], k3 = s_tab[b3 & 0xffffu];
+                smaller += (k0 < key) + (k1 < key) + (k2 < key) + (k3 < key);
+            }
+            for (; q < hi; ++q) smaller += (s_tab[s_bk[q] & 0xffffu] < key) ? 1 : 0;
             s_rank[d] = (unsigned short)(lo + smaller);
         }
         __syncthreads();
+        FV_T(14);
         for (int d = tid; d < M; d += FV_THREADS) s_tab[s_bk[d] & 0xffffu] = s_rank[d];   // keys are not needed any more
         __syncthreads();
     }
 
+    FV_T(4);
     // ---- decoupled look-back: unique counts of all earlier units (blocks are dispatched in index order)
     long long sum_all = 0, sum_seg = 0;
     for (int t = tid; t < u; t += FV_THREADS) {
@@ -876,6 +942,7 @@ vox_fast_kernel(int4 *pgrid, const unsigned long long *__restrict__ keys_in,
     __syncthreads();
     sum_all = 0; sum_seg = 0;
     for (int w = 0; w < FV_THREADS / 32; ++w) { sum_all += s_red[0][w]; sum_seg += s_red[1][w]; }
+    FV_T(5);
     const int64_t uo = sum_all - sum_seg;          // uniq_off[s]
     const int rbase = (int)sum_seg;                // rank of this unit's smallest key inside the segment
     if (tid == 0) {
@@ -889,6 +956,7 @@ vox_fast_kernel(int4 *pgrid, const unsigned long long *__restrict__ keys_in,
     int *s_first = reinterpret_cast<int *>(s_ub);
     for (int r = tid; r < M; r += FV_THREADS) s_first[r] = 0x7fffffff;
     __syncthreads();
+    FV_T(6);
     const int add = rbase + (collate ? (int)uo : 0);
     for (int base = 0; base < n; base += FV_BATCH * FV_THREADS) {
         unsigned int w[FV_BATCH];
@@ -920,15 +988,33 @@ vox_fast_kernel(int4 *pgrid, const unsigned long long *__restrict__ keys_in,
         }
     }
     __syncthreads();
-    for (int r = tid; r < M; r += FV_THREADS) {
-        const int f = s_first[r];
-        const int64_t o = uo + rbase + r;
-        first[o] = f;
-        if (KEY_SRC == 0 && voxel_xyz) {
-            const int4 g = pgrid[a + f];
-            voxel_xyz[o * 3 + 0] = g.x - g0; voxel_xyz[o * 3 + 1] = g.y - g1; voxel_xyz[o * 3 + 2] = g.z - g2;
+    FV_T(7);
+    for (int r0 = tid; r0 < M; r0 += FV_BATCH * FV_THREADS) {
+        int f[FV_BATCH];
+        int4 g[FV_BATCH];
+#pragma unroll
+        for (int k = 0; k < FV_BATCH; ++k) {
+            const int r = r0 + k * FV_THREADS;
+            f[k] = r < M ? s_first[r] : 0;
+            if (KEY_SRC == 0 && voxel_xyz && r < M) g[k] = pgrid[a + f[k]];     // four gathers in flight
+        }
+#pragma unroll
+        for (int k = 0; k < FV_BATCH; ++k) {
+            const int r = r0 + k * FV_THREADS;
+            if (r < M) {
+                const int64_t o = uo + rbase + r;
+                first[o] = f[k];
+                if (KEY_SRC == 0 && voxel_xyz) {
+                    voxel_xyz[o * 3 + 0] = g[k].x - g0; voxel_xyz[o * 3 + 1] = g[k].y - g1; voxel_xyz[o * 3 + 2] = g[k].z - g2;
+                }
+            }
         }
     }
+    FV_T(8);
+#ifdef XM3D_FV_TIMING
+    if (threadIdx.x == 0 && g_fv_dbg) { g_fv_dbg[blockIdx.x * 32 + 24] = n; g_fv_dbg[blockIdx.x * 32 + 25] = M; g_fv_dbg[blockIdx.x * 32 + 26] = P;
+        unsigned smid; asm("mov.u32 %0, %%smid;" : "=r"(smid)); g_fv_dbg[blockIdx.x * 32 + 27] = smid; }
+#endif
 }
 
 // ---- elementwise hashes (drop-ins for fnv_hash_vec / ravel_hash_vec on float64 rows) --------
@@ -1149,6 +1235,12 @@ extern "C" int xm3d_voxel_path_info(const void *ws, int32_t n_seg, int64_t cap, 
         return check_launch("xm3d_voxel_path_info");
     return XM3D_OK;
 }
+
+#ifdef XM3D_FV_TIMING
+extern "C" __attribute__((visibility("default"))) int xm3d_voxel_debug(void *dev_buf) {
+    return (int)cudaMemcpyToSymbol(g_fv_dbg, &dev_buf, sizeof(void *));
+}
+#endif
 
 extern "C" size_t xm3d_unique_ws_bytes(int32_t n_seg, int64_t cap) {
     size_t b = 0;
