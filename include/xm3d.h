@@ -244,6 +244,24 @@ XM3D_API int xm3d_vote_batch(const int32_t *vis_idx, const int64_t *seg_off, int
 XM3D_API int xm3d_vote_argmax(const int32_t *votes, const int32_t *counter, int64_t n_pts, int32_t n_classes,
                      int32_t *pred, xm3d_stream_t stream);
 
+/* Nearest SEEN neighbour of every point no view has seen (run/infer.py:651-656, 684-694: the reference
+ * builds sklearn KDTree(scene_coords[counter != 0]) and queries scene_coords[counter == 0] with k = 1,
+ * then copies the neighbour's prediction: scene_pred[false_idx] = scene_pred[true_idx[indices]]).
+ * Batched over scenes: seg_off DEVICE int64 [n_seg+1] point offsets, counter int32 [n_total] (seen iff != 0).
+ *   match[seg_off[s]+i] = index inside scene s of the nearest seen point (Euclidean, float64 arithmetic on
+ *   the float32 coordinates; ties -> lowest index); i itself for a seen point; -1 if the scene has no
+ *   seen point.  Filling is then pred[seg_off[s]+i] = pred[seg_off[s]+match[...]]. */
+XM3D_API size_t xm3d_nn_fill_ws_bytes(int32_t n_seg, int64_t n_total);
+XM3D_API int xm3d_nn_fill_batch(const float *xyz, const int32_t *counter, const int64_t *seg_off, int32_t n_seg,
+                       int64_t n_total, int32_t *match, void *ws, size_t ws_bytes, xm3d_stream_t stream);
+
+/* Per-scene maximum of the sparse bottleneck features (models/xmask3d.py:154-159:
+ * torch.max(imp_condition[_idx_ == scene_idx], dim=0)[0] for every scene): feat [rows, c] float32 with the
+ * rows of scene s at [seg_off[s], seg_off[s+1]) (collation order), out [n_seg, c].  NaN propagates like
+ * torch.max; an empty scene gives -inf. */
+XM3D_API int xm3d_segment_max(const float *feat, const int64_t *seg_off, int32_t n_seg, int32_t c, float *out,
+                     xm3d_stream_t stream);
+
 /* ------------------------------------------------------------------ after the path: mask preparation
  * The dense torch sequence that turns the mask head's low-resolution logits into the masks the path
  * consumes (models/xmask3d.py:326-331, 356-358, 391-435; models/utils/criterion.py:239-244, 273-320),

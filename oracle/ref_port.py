@@ -372,6 +372,26 @@ def vote_argmax(scene_pred):
     return scene_pred.argmax(1)
 
 
+def nn_fill_match(scene_coords: np.ndarray, counter: np.ndarray) -> np.ndarray:
+    """run/infer.py:651-656, 684-686 — index of the nearest seen point for every point (own index for a
+    seen point), restated as an exhaustive float64 search: the KD tree of the reference returns the exact
+    Euclidean nearest neighbour of the float32 coordinates promoted to float64; ties -> lowest index.
+    O(n_unseen x n_seen): small cases only."""
+    xyz = scene_coords.astype(np.float64)
+    seen = np.nonzero(counter != 0)[0]
+    out = np.arange(len(xyz), dtype=np.int64)
+    for i in np.nonzero(counter == 0)[0]:
+        d = xyz[seen] - xyz[i]
+        d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+        out[i] = seen[np.argmin(d2)] if len(seen) else -1
+    return out
+
+
+def segment_max(feat: np.ndarray, idx: np.ndarray) -> np.ndarray:
+    """models/xmask3d.py:154-159 — torch.max(imp_condition[_idx_ == scene_idx], dim=0)[0] per scene."""
+    return np.stack([feat[idx == s].max(0) for s in np.unique(idx)])
+
+
 # ----------------------------------------------------------------------------- mask preparation
 def mask_prep_ref(mask_pred_lowres, scores, mask_shape, score_thresh=0.0):
     """Restatement of the reference's inline mask preparation for one view (torch CPU ops, same

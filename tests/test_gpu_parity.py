@@ -798,3 +798,51 @@ def test_point_logits_vs_torch(dev):
         # argmax-only call (no [n,T] write)
         none, amax2 = ops.point_logits(feat, te, 1 / 0.07, want_logits=False)
         assert none is None and torch.equal(amax2, amax)
+
+
+def test_nn_fill_and_segment_max(golden, dev):
+    """Nearest-seen-neighbour fill (run/infer.py:651-656, 684-694) against the golden KDTree result and the
+    exhaustive oracle on a ragged multi-scene batch (a scene without seen points, one without unseen
+    points, duplicated points, an outlier far outside the seen bounding box); per-scene maxima."""
+    from oracle import ref_port
+    from xmask3d_b200 import ops
+    g = golden("nnfill")
+    xyz = torch.from_numpy(g["xyz"]).to(dev)
+    counter = torch.from_numpy(g["counter"]).to(dev)
+    match = ops.nn_fill_match(xyz, counter).cpu().numpy()
+    false_idx = g["false_idx"]
+    same = match[false_idx] == g["match"]
+    if not same.all():
+        x64 = g["xyz"].astype(np.float64)
+        bad = false_idx[~same]
+        assert np.array_equal(((x64[bad] - x64[match[bad]]) ** 2).sum(1), ((x64[bad] - x64[g["match"][~same]]) ** 2).sum(1))
+    filled = ops.nn_fill(torch.from_numpy(g["pred"]).to(dev), xyz, counter).cpu().numpy()
+    assert np.array_equal(filled, g["filled"])
+    # ragged batch against the exhaustive restatement
+    rng = np.random.default_rng(5)
+    sc = syn.make_scene(43, 6000)
+    a = sc.xyz[:2500].copy()
+    a[7] = [40.0, -35.0, 20.0]                                   # unseen outlier
+    ca = (rng.uniform(size=2500) < 0.4).astype(np.int32); ca[7] = 0
+    b = sc.xyz[2500:3000]; cb = np.zeros(500, np.int32)          # nothing seen
+    c = sc.xyz[3000:3700]; cc = np.ones(700, np.int32)           # everything seen
+    d = np.repeat(sc.xyz[3700:3900], 3, 0); cd = np.tile(np.array([1, 0, 0], np.int32), 200)   # exact duplicates
+    e = sc.xyz[4000:4001]; ce = np.zeros(1, np.int32)
+    f = sc.xyz[4100:6000]; cf = (rng.uniform(size=1900) < 0.02).astype(np.int32); cf[0] = 1  # sparse seen set
+    parts, cnts = [a, b, c, d, e, f], [ca, cb, cc, cd, ce, cf]
+    off = np.concatenate([[0], np.cumsum([len(p) for p in parts])]).astype(np.int64)
+    xyz_b = torch.from_numpy(np.concatenate(parts)).to(dev)
+    cnt_b = torch.from_numpy(np.concatenate(cnts)).to(dev)
+    got = ops.nn_fill_match(xyz_b, cnt_b, torch.from_numpy(off).to(dev)).cpu().numpy()
+    for i, (p, c_) in enumerate(zip(parts, cnts)):
+        ref = ref_port.nn_fill_match(p, c_)
+        mine = got[off[i]:off[i + 1]] - off[i]
+        if not (c_ != 0).any():
+            assert np.array_equal(mine, np.arange(len(p))), f"scene {i}: nothing seen -> unchanged"
+            continue
+        assert np.array_equal(mine, ref), f"scene {i}"
+    # per-scene maximum
+    idx = g["idx"]
+    soff = np.concatenate([[0], np.cumsum(np.bincount(idx))]).astype(np.int64)
+    sm = ops.segment_max(torch.from_numpy(g["feat"]).to(dev), torch.from_numpy(soff).to(dev)).cpu().numpy()
+    assert np.array_equal(sm, g["segmax"])

@@ -147,3 +147,24 @@ def test_logits(golden):
     assert np.array_equal(P.ensemble_logits_with_labels(raw, labels, "mean").numpy(), g["ens_mean"])
     with pytest.raises(AssertionError):
         P.ensemble_logits_with_labels(raw, labels[:-1], "max")
+
+
+def test_nn_fill_and_segment_max_oracle_vs_reference_statements(golden):
+    """The restated exhaustive search returns what the reference's KDTree(k=1) statements returned
+    (tests/golden/make_golden_nnfill.py), wherever the nearest neighbour is unique; segment maxima equal."""
+    from oracle import ref_port
+    g = golden("nnfill")
+    match = ref_port.nn_fill_match(g["xyz"], g["counter"])
+    false_idx = g["false_idx"]
+    assert np.array_equal(false_idx, np.nonzero(g["counter"] == 0)[0])
+    same = match[false_idx] == g["match"]
+    if not same.all():       # only exact distance ties may differ
+        xyz = g["xyz"].astype(np.float64)
+        bad = false_idx[~same]
+        d_mine = ((xyz[bad] - xyz[match[bad]]) ** 2).sum(1)
+        d_ref = ((xyz[bad] - xyz[g["match"][~same]]) ** 2).sum(1)
+        assert np.array_equal(d_mine, d_ref)
+    assert np.array_equal(g["pred"][match], g["filled"])
+    seen = np.nonzero(g["counter"] != 0)[0]
+    assert np.array_equal(match[seen], seen)
+    assert np.array_equal(ref_port.segment_max(g["feat"], g["idx"]), g["segmax"])

@@ -62,6 +62,9 @@ PROTOTYPES = {
     "xm3d_point_logits": (C.c_int, [_P, _I64, _I32, _P, _I32, _F32, _P, _P, _P, _P, _P, _SZ, _P]),
     "xm3d_vote_batch": (C.c_int, [_P, _P, _I32, _I64, _P, _P, _I32, _P, _P, _P]),
     "xm3d_vote_argmax": (C.c_int, [_P, _P, _I64, _I32, _P, _P]),
+    "xm3d_nn_fill_ws_bytes": (_SZ, [_I32, _I64]),
+    "xm3d_nn_fill_batch": (C.c_int, [_P, _P, _P, _I32, _I64, _P, _P, _SZ, _P]),
+    "xm3d_segment_max": (C.c_int, [_P, _P, _I32, _I32, _P, _P]),
     "xm3d_mask_prep_batch": (C.c_int, [_P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _I32, _P, _P, _P, _P, _P]),
     "xm3d_point_bits_batch": (C.c_int, [_P, _I32, _I32, _I32, _I32, _P, _P, _I64, _P, _P, _P]),
     "xm3d_gather_labels_batch": (C.c_int, [_P, _I32, _I32, _I32, _P, _P, _I64, _P, _P]),

@@ -416,6 +416,46 @@ def vote_argmax(votes: torch.Tensor, counter: torch.Tensor) -> torch.Tensor:
     return pred
 
 
+def nn_fill_match(xyz: torch.Tensor, counter: torch.Tensor, seg_off: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Nearest seen neighbour of every unseen point (run/infer.py:651-656, 684-694: KDTree over the seen
+    points, k = 1).  xyz float32 [N,3], counter int32 [N] (seen iff != 0), seg_off int64 [S+1] scene offsets
+    (one scene if None).  Returns int64 [N] GLOBAL indices: pred[match] is the filled prediction."""
+    _require_cuda()
+    dev = xyz.device
+    xyz = _dev_contig(xyz, torch.float32)
+    counter = _dev_contig(counter.to(torch.int32), torch.int32)
+    n = int(xyz.shape[0])
+    if seg_off is None:
+        seg_off = torch.tensor([0, n], dtype=torch.int64, device=dev)
+    seg_off = _dev_contig(seg_off, torch.int64)
+    n_seg = seg_off.numel() - 1
+    match = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    ws = _ws(L.lib().xm3d_nn_fill_ws_bytes(n_seg, n), dev)
+    L.check(L.lib().xm3d_nn_fill_batch(_ptr(xyz), _ptr(counter), _ptr(seg_off), n_seg, n, _ptr(match), _ptr(ws),
+                                       ws.numel(), _stream()))
+    match = match[:n].to(torch.int64)
+    seg = torch.bucketize(torch.arange(n, device=dev), seg_off[1:-1], right=True) if n_seg > 1 else None
+    base = seg_off[seg] if seg is not None else seg_off[0]
+    return torch.where(match >= 0, match + base, torch.arange(n, device=dev))
+
+
+def nn_fill(pred: torch.Tensor, xyz: torch.Tensor, counter: torch.Tensor,
+            seg_off: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """scene_pred[false_idx] = scene_pred[true_idx[nearest]] (run/infer.py:686-694); pred [N] or [N, ...]."""
+    return pred[nn_fill_match(xyz, counter, seg_off)]
+
+
+def segment_max(feat: torch.Tensor, seg_off: torch.Tensor) -> torch.Tensor:
+    """torch.stack([feat[seg_off[s]:seg_off[s+1]].max(0)[0] for s ...]) (models/xmask3d.py:154-159)."""
+    _require_cuda()
+    feat = _dev_contig(feat, torch.float32)
+    seg_off = _dev_contig(seg_off, torch.int64)
+    n_seg = seg_off.numel() - 1
+    out = torch.empty((n_seg, feat.shape[1]), dtype=torch.float32, device=feat.device)
+    L.check(L.lib().xm3d_segment_max(_ptr(feat), _ptr(seg_off), n_seg, int(feat.shape[1]), _ptr(out), _stream()))
+    return out
+
+
 # ----------------------------------------------------------------------------- after the path: mask preparation
 @dataclass
 class PreparedMasks:
