@@ -24,13 +24,14 @@
 //
 // Fast path (vox_fast_kernel, taken whenever every segment fits): after `min` has written the grid
 // coordinates of every point, ONE persistent 1024-thread CTA per unit does insert / rank / inverse /
-// coords entirely in shared memory (16384-slot table of 64-bit keys, bucket ranking as above) — no
-// dependent global-memory round trips, so it does not starve next to the pooling stream.  A segment
-// of n points is split by KEY RANGE into ceil(n / unit_pts) units (splitters from a 1024-key
-// sample every unit of the segment computes identically); unique counts of the units are
-// exchanged through a decoupled look-back, which yields both the rank base inside the segment
-// and uniq_off.  A unit that overflows its table raises ctl[1] and the multi-kernel path below
-// (gated on ctl) recomputes the whole batch.
+// coords entirely in shared memory (16384-slot table of 64-bit keys, unique list from a scan of the
+// table, bucket ranking as above) — no dependent global-memory round trips, so it does not starve next
+// to the pooling stream.  A segment of n points is split by KEY RANGE into ceil(n / unit_pts) units
+// (quantiles of a 256 / 1024-key sample every unit of the segment computes identically); the owner
+// of a point tags its stored grid record in place.  Unique counts of the units are exchanged through
+// a decoupled look-back, which yields both the rank base inside the segment and uniq_off.  A unit
+// that overflows its table raises ctl[1] and the multi-kernel path below (gated on ctl) recomputes
+// the whole batch.
 //
 // Everything that decides an integer is exact: the transform is the fp64 FMA chain numpy's dgemm
 // performs, floor() is exact, keys are 64-bit so FNV collisions merge voxels exactly as the
