@@ -50,6 +50,7 @@ def parse():
     p.add_argument("--cpu-views", type=int, default=12, help="views of scene 0 timed by the CPU baseline")
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--no-e2e-all", action="store_true")
+    p.add_argument("--e2e-slots", type=int, default=3, help="staging slots of the pipelined end-to-end loop")
     p.add_argument("--profile-steps", type=int, default=0, help="run only this many plain steps (for ncu)")
     p.add_argument("--distinct-scenes", action="store_true",
                    help="rank r processes scenes 8r..8r+7 (data-dependent imbalance) instead of a copy of scenes 0..7")
@@ -370,26 +371,28 @@ def run_native(args, rank: int, world: int, local_rank: int):
     # Pipelined end-to-end loop: the copy engines run beside the kernels.  Step i's inputs are copied
     # H2D on a copy-in stream into a staging slot, the compute stream moves them into the pipeline's
     # input tensors and replays the step, copies the results into an output staging slot, and a
-    # copy-out stream moves that slot to pinned host memory.  Two slots each way; the host waits for
-    # the results of step i-1 before it enqueues step i+1, so at most two steps are in flight.
+    # copy-out stream moves that slot to pinned host memory.  --e2e-slots slots each way; the host waits for
+    # the results of the oldest step in flight before it enqueues the next one.
     s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
     comp = torch.cuda.current_stream()
-    xyz_st = [torch.empty_like(pipe.xyz) for _ in range(2)]
-    dep_st = [torch.empty_like(pipe.depth) for _ in range(2)]
-    out_st = [{k2: torch.empty(v2.shape, dtype=v2.dtype, device=dev) for k2, v2 in res_h.items()} for _ in range(2)]
-    res_h2 = [res_h, {k2: torch.empty(v2.shape, dtype=v2.dtype).pin_memory() for k2, v2 in res_h.items()}]
-    ev_in_ready = [torch.cuda.Event() for _ in range(2)]
-    ev_consumed = [torch.cuda.Event() for _ in range(2)]
-    ev_out_ready = [torch.cuda.Event() for _ in range(2)]
-    ev_out_free = [torch.cuda.Event() for _ in range(2)]
-    ev_done = [torch.cuda.Event() for _ in range(2)]
-    for b in range(2):
+    NSLOT = args.e2e_slots
+    xyz_st = [torch.empty_like(pipe.xyz) for _ in range(NSLOT)]
+    dep_st = [torch.empty_like(pipe.depth) for _ in range(NSLOT)]
+    out_st = [{k2: torch.empty(v2.shape, dtype=v2.dtype, device=dev) for k2, v2 in res_h.items()} for _ in range(NSLOT)]
+    res_h2 = [res_h] + [{k2: torch.empty(v2.shape, dtype=v2.dtype).pin_memory() for k2, v2 in res_h.items()}
+                       for _ in range(NSLOT - 1)]
+    ev_in_ready = [torch.cuda.Event() for _ in range(NSLOT)]
+    ev_consumed = [torch.cuda.Event() for _ in range(NSLOT)]
+    ev_out_ready = [torch.cuda.Event() for _ in range(NSLOT)]
+    ev_out_free = [torch.cuda.Event() for _ in range(NSLOT)]
+    ev_done = [torch.cuda.Event() for _ in range(NSLOT)]
+    for b in range(NSLOT):
         ev_consumed[b].record(comp)
         ev_out_free[b].record(comp)
         ev_done[b].record(comp)
 
     def e2e_pipelined(i):
-        b = i & 1
+        b = i % NSLOT
         with torch.cuda.stream(s_in):
             s_in.wait_event(ev_consumed[b])
             xyz_st[b].copy_(xyz_h, non_blocking=True)
@@ -417,10 +420,10 @@ def run_native(args, rank: int, world: int, local_rank: int):
                 res_h2[b][k2].copy_(ost[k2], non_blocking=True)
             ev_out_free[b].record(s_out)
             ev_done[b].record(s_out)
-        if i > 0:
-            ev_done[(i - 1) & 1].synchronize()           # the caller consumes step i-1's results
+        if i >= NSLOT - 1:
+            ev_done[(i - NSLOT + 1) % NSLOT].synchronize()   # the caller consumes the oldest step in flight
 
-    for i in range(4):
+    for i in range(2 * NSLOT):
         e2e_pipelined(i)
     barrier()
     n_e2e = max(4, min(args.steps, 50))
@@ -433,7 +436,7 @@ def run_native(args, rank: int, world: int, local_rank: int):
     barrier()
     e2e_ms = e0.elapsed_time(e1)                      # device clock around H2D + kernels + D2H of all steps
     # sanity: what came back is what the device computed
-    assert torch.equal(res_h2[(n_e2e - 1) & 1]["cnt"], out["cnt"].cpu()) or use_graph is None
+    assert torch.equal(res_h2[(n_e2e - 1) % NSLOT]["cnt"], out["cnt"].cpu()) or use_graph is None
     te = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
