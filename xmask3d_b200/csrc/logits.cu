@@ -16,6 +16,8 @@
 // issuer, warps 2-5 = epilogue (tcgen05.ld -> normalise, scale, synonym-group max/mean, argmax).
 #include <cuda.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace xm3d {
@@ -291,14 +293,22 @@ static LogitsWs carve_logits(void *ws, int64_t rows, int n_cols, int c, int n_gr
 // (the split is elementwise, so the 128-byte swizzle written by TMA carries over unchanged) and
 // accumulate the row norms on the way; one thread issues the 3xTF32 tcgen05.mma chain into TMEM;
 // the converter warps then run the epilogue (normalise, scale, blend, argmax).
-constexpr int PL_CONV_WARPS = 4;                 // converter warps (the first four also run the epilogue)
+#ifndef XM3D_PL_RAW_HI
+#define XM3D_PL_RAW_HI 1
+#endif
+#ifndef XM3D_PL_CONV_WARPS
+#define XM3D_PL_CONV_WARPS 4
+#endif
+constexpr int PL_CONV_WARPS = XM3D_PL_CONV_WARPS;                 // converter warps (the first four also run the epilogue)
 constexpr int PL_CONV = PL_CONV_WARPS * 32;
 constexpr int PL_CHUNKS = LG_BM * LG_BK * 4 / 16 / PL_CONV;    // 16-byte chunks per converter thread and k-block
 constexpr int PL_THREADS = 64 + PL_CONV;
+constexpr int PL_MAX_STAGES = 8;
 
 struct PointLogitsParams {
     int64_t rows;
     int c, n_text, bn, stages, tmem_cols;
+    int fused;                   // 1: [B_hi; B_lo] is one N = 2 bn operand (A_hi is read once), needs 2 bn <= 256
     float scale;
     const float *inv_norm_b;     // [n_text]
     const float *binary;         // [rows] or null
@@ -315,7 +325,7 @@ __global__ void __launch_bounds__(PL_THREADS, 2)
 point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b_hi,
                     const __grid_constant__ CUtensorMap map_b_lo, const PointLogitsParams P) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ uint64_t s_raw[4], s_conv[4], s_empty[4], s_done;
+    __shared__ uint64_t s_raw[PL_MAX_STAGES], s_conv[PL_MAX_STAGES], s_empty[PL_MAX_STAGES], s_done;
     __shared__ uint32_t s_tmem;
     __shared__ float s_invb[LG_MAX_N];
     __shared__ unsigned char s_base[LG_MAX_N];
@@ -375,6 +385,8 @@ point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(P.bn >> 3) << 17) |
                                    ((uint32_t)(LG_BM >> 4) << 24);
+            const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * P.bn) >> 3) << 17) |
+                                    ((uint32_t)(LG_BM >> 4) << 24);
             int stage = 0;
             uint32_t phase = 0;
             for (int kb = 0; kb < nkb; ++kb) {
@@ -384,12 +396,23 @@ point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 unsigned char *st = tiles + (size_t)stage * stage_bytes;
                 const uint64_t a_hi = make_sw128_desc(st), a_lo = make_sw128_desc(st + a_bytes);
                 const uint64_t b_hi = make_sw128_desc(st + 2 * a_bytes), b_lo = make_sw128_desc(st + 2 * a_bytes + b_bytes);
+                if (P.fused) {
+                    // B_hi and B_lo are adjacent 8-row-group aligned tiles: one N = 2 bn operand.  Columns
+                    // [0, bn) accumulate hi*hi + lo*hi, columns [bn, 2 bn) hi*lo; the epilogue adds them.
 #pragma unroll
-                for (int k = 0; k < LG_BK / LG_UMMA_K; ++k) {
-                    const uint64_t adv = (uint64_t)((k * LG_UMMA_K * 4) >> 4);
-                    umma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, (kb | k) ? 1u : 0u);
-                    umma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
-                    umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, 1u);
+                    for (int k = 0; k < LG_BK / LG_UMMA_K; ++k) {
+                        const uint64_t adv = (uint64_t)((k * LG_UMMA_K * 4) >> 4);
+                        umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc2, (kb | k) ? 1u : 0u);
+                        umma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, 1u);
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < LG_BK / LG_UMMA_K; ++k) {
+                        const uint64_t adv = (uint64_t)((k * LG_UMMA_K * 4) >> 4);
+                        umma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, (kb | k) ? 1u : 0u);
+                        umma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
+                        umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, 1u);
+                    }
                 }
                 umma_commit(&s_empty[stage]);
                 if (++stage == P.stages) { stage = 0; phase ^= 1; }
@@ -425,7 +448,13 @@ point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 }
                 h = make_uint4(ho[0], ho[1], ho[2], ho[3]);
                 l = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+#if XM3D_PL_RAW_HI
+                // the tensor core ignores the 13 low mantissa bits of a tf32 operand: the raw tile IS its hi
+                // part, and not writing it back saves a third of the converter's shared-memory traffic
+                (void)h; (void)hi;
+#else
                 hi[q] = h;
+#endif
                 lo[q] = l;
             }
             // generic-proxy writes -> visible to the tensor core's async proxy, then signal
@@ -456,13 +485,15 @@ point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         float best = -INFINITY;
         int best_i = 0;
         for (int c0 = 0; c0 < P.bn; c0 += 16) {
-            uint32_t v[16];
+            uint32_t v[16], v2[16];
             tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0, v);
+            if (P.fused) tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(P.bn + c0), v2);
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const int col = c0 + j;
                 if (col < P.n_text) {
-                    float val = P.scale * ((__uint_as_float(v[j]) * inv_a) * s_invb[col]);
+                    const float dot = P.fused ? __uint_as_float(v[j]) + __uint_as_float(v2[j]) : __uint_as_float(v[j]);
+                    float val = P.scale * ((dot * inv_a) * s_invb[col]);
                     if (blend) {
                         // binary * logits_base + (1 - binary) * logits_novel, masked entries = -1e10
                         const float lb = s_base[col] ? val : -1e10f, ln = s_base[col] ? -1e10f : val;
@@ -589,8 +620,9 @@ extern "C" int xm3d_point_logits(const float *feat, int64_t rows, int32_t c, con
     PointLogitsParams P;
     P.rows = rows; P.c = c; P.n_text = n_text; P.bn = (n_text + 15) / 16 * 16; P.scale = logit_scale;
     P.inv_norm_b = inv_b; P.binary = binary; P.is_base = is_base; P.out = out; P.argmax = argmax;
+    P.fused = (2 * P.bn <= 256 && !getenv("XM3D_PL_NO_FUSE")) ? 1 : 0;
     int tc = 32;
-    while (tc < P.bn) tc <<= 1;
+    while (tc < (P.fused ? 2 * P.bn : P.bn)) tc <<= 1;
     P.tmem_cols = tc;
     const size_t stage_bytes = 2 * (size_t)LG_BM * LG_BK * 4 + 2 * (size_t)P.bn * LG_BK * 4;
     // two CTAs per SM when two stages of each fit (the second CTA's TMA / MMA hides the first one's
@@ -598,6 +630,10 @@ extern "C" int xm3d_point_logits(const float *feat, int64_t rows, int32_t c, con
     int stages = (int)((108 * 1024) / stage_bytes);
     if (stages < 2) stages = (int)((220 * 1024) / stage_bytes);
     if (stages > 4) stages = 4;
+    if (const char *e = getenv("XM3D_PL_STAGES")) {          // A/B experiments: force the ring depth
+        const int f = atoi(e);
+        if (f >= 1 && f <= PL_MAX_STAGES && (size_t)f * stage_bytes + 1024 <= 224 * 1024) stages = f;
+    }
     if (stages < 1) { set_error("xm3d_point_logits: tile does not fit shared memory"); return XM3D_ERR_UNSUPPORTED; }
     P.stages = stages;
     CUtensorMap ma, mbh, mbl;
