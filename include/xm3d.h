@@ -177,6 +177,11 @@ XM3D_API int xm3d_gather_masks_batch(const void *masks, int32_t mask_kind, int32
                             int32_t k, int32_t h, int32_t w, const int32_t *rowcol,
                             const int64_t *seg_off, int64_t cap, uint32_t *member, int32_t *counts,
                             void *ws, size_t ws_bytes, xm3d_stream_t stream);
+/* First half of xm3d_gather_masks_batch alone: masks -> per-pixel membership words
+ * pixbits [n_seg, xm3d_mask_words(k), h*w] (the input of xm3d_point_bits_batch).  It does not depend on
+ * the projection, so a pipeline can run it NEXT TO the projection (xmask3d_b200/pipeline.py). */
+XM3D_API int xm3d_pixel_bits_batch(const void *masks, int32_t mask_kind, int32_t thr_mode, int32_t n_seg, int32_t k,
+                          int32_t h, int32_t w, uint32_t *pixbits, xm3d_stream_t stream);
 
 /* Segmented mean pooling of per-point features under each mask (models/utils/criterion.py:148-157;
  * scalar form models/xmask3d.py:362-367 with c = 1).

@@ -55,6 +55,7 @@ PROTOTYPES = {
     "xm3d_mask_words": (_I32, [_I32]),
     "xm3d_gather_ws_bytes": (_SZ, [_I32, _I32, _I32, _I32]),
     "xm3d_gather_masks_batch": (C.c_int, [_P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _I64, _P, _P, _P, _SZ, _P]),
+    "xm3d_pixel_bits_batch": (C.c_int, [_P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P]),
     "xm3d_pool_ws_bytes": (_SZ, [_I32, _I32, _I32, _I64, _I64]),
     "xm3d_pool_batch": (C.c_int, [_P, _I32, _P, _P, _P, _I32, _I32, _P, _I64, _I64, _P, _P, _P, _P, _SZ, _P, _P]),
     "xm3d_scatter_batch": (C.c_int, [_P, _P, _I32, _I32, _P, _I64, _P, _I32, _P, _P, _P]),

@@ -240,6 +240,39 @@ extern "C" size_t xm3d_gather_ws_bytes(int32_t n_seg, int32_t k, int32_t h, int3
 
 extern "C" int32_t xm3d_mask_words(int32_t k) { return words_for(k); }
 
+// [n_seg, k, h, w] masks -> per-pixel membership words [n_seg, words, h*w]
+static int launch_pixel_bits(const void *masks, int mask_kind, int thr_mode, int n_seg, int k, int h, int w,
+                             uint32_t *pixbits, cudaStream_t stream) {
+    const int words = words_for(k), hw = h * w;
+    const int esz = mask_kind == XM3D_MASK_U8 ? 1 : 4;
+    const int pix = 16 / esz;
+    const int vec_ok = (hw % pix == 0) && (reinterpret_cast<uintptr_t>(masks) % 16 == 0);
+    dim3 grid(((hw + pix - 1) / pix + 255) / 256, n_seg);
+    if (mask_kind == XM3D_MASK_U8 && thr_mode == XM3D_THR_GE_HALF && vec_ok) {
+        dim3 grid8(grid.x, n_seg, words);
+        pixel_bits_u8_kernel<<<grid8, 256, 0, stream>>>(static_cast<const unsigned char *>(masks), k, hw, words, pixbits);
+    } else if (mask_kind == XM3D_MASK_U8) {
+        pixel_bits_kernel<unsigned char><<<grid, 256, 0, stream>>>(static_cast<const unsigned char *>(masks), thr_mode,
+                                                                    k, hw, words, vec_ok, pixbits);
+    } else {
+        pixel_bits_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float *>(masks), thr_mode, k, hw, words,
+                                                           vec_ok, pixbits);
+    }
+    count_launches(1);
+    return XM3D_OK;
+}
+
+extern "C" int xm3d_pixel_bits_batch(const void *masks, int32_t mask_kind, int32_t thr_mode, int32_t n_seg, int32_t k,
+                                     int32_t h, int32_t w, uint32_t *pixbits, xm3d_stream_t stream_) {
+    XM3D_REQUIRE(n_seg > 0 && k > 0 && h > 0 && w > 0, "bad sizes");
+    XM3D_REQUIRE(k <= 32 * MAX_WORDS, "at most 256 masks per segment");
+    XM3D_REQUIRE(masks && pixbits, "null pointer");
+    XM3D_REQUIRE(mask_kind == XM3D_MASK_U8 || mask_kind == XM3D_MASK_F32, "bad mask_kind");
+    XM3D_REQUIRE(thr_mode >= 0 && thr_mode <= 2, "bad thr_mode");
+    launch_pixel_bits(masks, mask_kind, thr_mode, n_seg, k, h, w, pixbits, static_cast<cudaStream_t>(stream_));
+    return check_launch("xm3d_pixel_bits_batch");
+}
+
 extern "C" int xm3d_gather_masks_batch(const void *masks, int32_t mask_kind, int32_t thr_mode, int32_t n_seg,
                                        int32_t k, int32_t h, int32_t w, const int32_t *rowcol,
                                        const int64_t *seg_off, int64_t cap, uint32_t *member, int32_t *counts,
@@ -254,22 +287,9 @@ extern "C" int xm3d_gather_masks_batch(const void *masks, int32_t mask_kind, int
         set_error("xm3d_gather_masks_batch: workspace too small");
         return XM3D_ERR_WORKSPACE;
     }
-    const int words = words_for(k), hw = h * w;
+    const int words = words_for(k);
     uint32_t *pixbits = static_cast<uint32_t *>(ws);
-    const int esz = mask_kind == XM3D_MASK_U8 ? 1 : 4;
-    const int pix = 16 / esz;
-    const int vec_ok = (hw % pix == 0) && (reinterpret_cast<uintptr_t>(masks) % 16 == 0);
-    dim3 grid(((hw + pix - 1) / pix + 255) / 256, n_seg);
-    if (mask_kind == XM3D_MASK_U8 && thr_mode == XM3D_THR_GE_HALF && vec_ok) {
-        dim3 grid8(grid.x, n_seg, words);
-        pixel_bits_u8_kernel<<<grid8, 256, 0, stream>>>(static_cast<const unsigned char *>(masks), k, hw, words, pixbits);
-        count_launches(1);
-    } else if (mask_kind == XM3D_MASK_U8) {
-        pixel_bits_kernel<unsigned char><<<grid, 256, 0, stream>>>(static_cast<const unsigned char *>(masks), thr_mode,
-                                                                    k, hw, words, vec_ok, pixbits); count_launches(1); }
-    else {
-        pixel_bits_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float *>(masks), thr_mode, k, hw, words,
-                                                           vec_ok, pixbits); count_launches(1); }
+    launch_pixel_bits(masks, mask_kind, thr_mode, n_seg, k, h, w, pixbits, stream);
     if (counts) cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)n_seg * k, stream);
     if (cap > 0) {
         point_bits_kernel<<<(unsigned)((cap + 255) / 256), 256, 0, stream>>>(pixbits, rowcol, seg_off, n_seg, cap, k, h,

@@ -270,6 +270,28 @@ def gather_masks(masks: torch.Tensor, rowcol: torch.Tensor, seg_off: torch.Tenso
     return member, counts
 
 
+def pixel_bits(masks: torch.Tensor, mode: str = "ge0.5", ws: Optional[torch.Tensor] = None) -> "PreparedMasks":
+    """masks [n_seg,k,h,w] bool/uint8/float32 -> per-pixel membership words (first half of gather_masks; it
+    does not depend on the projection).  Feed the result to point_bits."""
+    _require_cuda()
+    assert masks.dim() == 4
+    n_seg, k, h, w = masks.shape
+    if masks.dtype == torch.bool:
+        masks = masks.view(torch.uint8)
+    if masks.dtype == torch.uint8:
+        kind = L.MASK_U8
+    else:
+        masks, kind = masks.to(torch.float32), L.MASK_F32
+    masks = masks.contiguous()
+    words = mask_words(k)
+    need = n_seg * words * h * w * 4
+    if ws is None or ws.numel() < need:
+        ws = _ws(need, masks.device)
+    L.check(L.lib().xm3d_pixel_bits_batch(_ptr(masks), kind, THR[mode], n_seg, k, h, w, _ptr(ws), _stream()))
+    pix = ws[:need].view(torch.int32).view(n_seg, words, h * w)
+    return PreparedMasks(pix, None, None, None, k, h, w)
+
+
 def _popcount32(x: torch.Tensor) -> torch.Tensor:
     x = x.to(torch.int64) & 0xFFFFFFFF
     x = x - ((x >> 1) & 0x55555555)

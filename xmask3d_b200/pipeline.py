@@ -121,18 +121,23 @@ class CorrespondencePipeline:
         overlap = self.overlap and times is None
         if times is not None:
             times.mark("start")
-        pr = self.project()
-        if times is not None:
-            times.mark("project")
         if overlap:
-            # fork: masks-at-points + pooling (HBM-bandwidth bound) run on a side stream while the
-            # voxelization (latency bound, little bandwidth) runs on the caller's stream
+            # fork 1: the masks -> per-pixel membership words pass (HBM bound, independent of the
+            # projection) runs on the side stream NEXT TO the projection (instruction bound)
             main = torch.cuda.current_stream()
             side = self._side
             side.wait_stream(main)
             with torch.cuda.stream(side):
-                member, _ = ops.gather_masks(masks, pr.rowcol, pr.vis_off, mode=mode, cap=self.cap_vis,
-                                             ws=self.ws_gather)
+                prep = ops.pixel_bits(masks, mode=mode, ws=self.ws_gather)
+        pr = self.project()
+        if times is not None:
+            times.mark("project")
+        if overlap:
+            # fork 2: masks-at-points + pooling (HBM-bandwidth bound) stay on the side stream while the
+            # voxelization (shared-memory units, little bandwidth) runs on the caller's stream
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                member, _ = ops.point_bits(prep, pr.rowcol, pr.vis_off, cap=self.cap_vis)
                 s, cnt, mean = ops.pool(feat, pr.vis_off, self.k, member=member, cap=self.cap_vis,
                                         cap_pairs=self.cap_pairs,
                                         row_index=(pr.vis_idx if feat_per_point else None), ws=self.ws_pool,
