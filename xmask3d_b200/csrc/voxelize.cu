@@ -60,6 +60,7 @@ constexpr int FV_MU = 8704;               // unique keys per unit, at most (load
 constexpr int FV_UNIT_PTS = 7000;         // points per unit the plan aims at (24 % headroom to FV_MU)
 constexpr int FV_UNIT_PTS_MIN = 64;       // smallest value xm3d_set_voxel_path accepts (sizes the unit tables)
 constexpr int FV_PMAX = 32;               // units per segment, at most (224 k points)
+constexpr int FV_OUT_BATCH = 6;             // gathers of voxel coordinates in flight per thread (one round for M <= 6144)
 constexpr int FV_PROBE_MAX = 2048;        // a longer probe sequence means the table is (nearly) full: give up
 constexpr int FV_BATCH = 4;               // loads a thread keeps in flight in the point passes
 constexpr int FV_NS = 1024;               // sample keys for the key-range split / rank buckets
@@ -990,17 +991,17 @@ vox_fast_kernel(int4 *pgrid, const unsigned long long *__restrict__ keys_in,
     }
     __syncthreads();
     FV_T(7);
-    for (int r0 = tid; r0 < M; r0 += FV_BATCH * FV_THREADS) {
-        int f[FV_BATCH];
-        int4 g[FV_BATCH];
+    for (int r0 = tid; r0 < M; r0 += FV_OUT_BATCH * FV_THREADS) {
+        int f[FV_OUT_BATCH];
+        int4 g[FV_OUT_BATCH];
 #pragma unroll
-        for (int k = 0; k < FV_BATCH; ++k) {
+        for (int k = 0; k < FV_OUT_BATCH; ++k) {
             const int r = r0 + k * FV_THREADS;
             f[k] = r < M ? s_first[r] : 0;
             if (KEY_SRC == 0 && voxel_xyz && r < M) g[k] = pgrid[a + f[k]];     // four gathers in flight
         }
 #pragma unroll
-        for (int k = 0; k < FV_BATCH; ++k) {
+        for (int k = 0; k < FV_OUT_BATCH; ++k) {
             const int r = r0 + k * FV_THREADS;
             if (r < M) {
                 const int64_t o = uo + rbase + r;
