@@ -3,8 +3,10 @@
 //  * nearest seen neighbour of every point no view has seen — the reference builds
 //    sklearn.neighbors.KDTree(scene_coords[counter != 0]) and queries the unseen points with k = 1
 //    (run/infer.py:651-656, 684-694), then copies the neighbour's prediction.  Here: a uniform grid
-//    over the seen points of every scene (counting sort by cell), and a ring search per unseen point
-//    that stops as soon as the best distance is inside the searched cube.  Distances are float64
+//    over the seen points of every scene (counting sort by cell; cells are numbered block-major, 4 x 4 x 4
+//    cells per block, so the points of a block are contiguous) and a two-level ring search per unseen
+//    point: rings of cells up to radius 3, then rings of blocks (empty blocks cost two loads), each
+//    stopping as soon as the best distance is inside the searched cube.  Distances are float64
 //    sums of squared float64 differences in x, y, z order (what the KD tree computes on the float32
 //    coordinates promoted to float64); equal distances resolve to the lowest point index.
 //  * per-scene maximum of the sparse bottleneck features (models/xmask3d.py:154-159:
@@ -28,10 +30,20 @@ constexpr int NN_THREADS = 256;
 // cells of segment s live at cells[4 seg_off[s] + 64 s ...): at most 4 n + 64 of them
 __device__ __forceinline__ int64_t nn_cell_base(const int64_t *seg_off, int s) { return 4 * seg_off[s] + 64 * (int64_t)s; }
 
-__device__ __forceinline__ int nn_cell_of(const NnSeg &S, float x, float y, float z) {
-    int cx = (int)floorf((x - S.mn[0]) * S.inv_h), cy = (int)floorf((y - S.mn[1]) * S.inv_h), cz = (int)floorf((z - S.mn[2]) * S.inv_h);
+// cell (cx, cy, cz) -> index: blocks of 4 x 4 x 4 cells, block-major (g[] are multiples of 4)
+__device__ __forceinline__ int nn_cell_index(const NnSeg &S, int cx, int cy, int cz) {
+    const int bx = S.g[0] >> 2, by = S.g[1] >> 2;
+    const int blk = ((cz >> 2) * by + (cy >> 2)) * bx + (cx >> 2);
+    return blk * 64 + ((cz & 3) << 4) + ((cy & 3) << 2) + (cx & 3);
+}
+__device__ __forceinline__ void nn_cell_coords(const NnSeg &S, float x, float y, float z, int &cx, int &cy, int &cz) {
+    cx = (int)floorf((x - S.mn[0]) * S.inv_h); cy = (int)floorf((y - S.mn[1]) * S.inv_h); cz = (int)floorf((z - S.mn[2]) * S.inv_h);
     cx = min(max(cx, 0), S.g[0] - 1); cy = min(max(cy, 0), S.g[1] - 1); cz = min(max(cz, 0), S.g[2] - 1);
-    return (cz * S.g[1] + cy) * S.g[0] + cx;
+}
+__device__ __forceinline__ int nn_cell_of(const NnSeg &S, float x, float y, float z) {
+    int cx, cy, cz;
+    nn_cell_coords(S, x, y, z, cx, cy, cz);
+    return nn_cell_index(S, cx, cy, cz);
 }
 
 // one CTA per scene: bounding box and count of the seen points -> grid geometry
@@ -86,7 +98,10 @@ nn_plan_kernel(const float *__restrict__ xyz, const int32_t *__restrict__ counte
         h = fmaxf(h, 1e-6f);
         for (;;) {                                 // grow the cell until the grid fits the budget
             int64_t cells = 1;
-            for (int d = 0; d < 3; ++d) { S.g[d] = (int)fminf(floorf(ext[d] / h) + 1.f, 2048.f); cells *= S.g[d]; }
+            for (int d = 0; d < 3; ++d) {
+                S.g[d] = ((int)fminf(floorf(ext[d] / h) + 1.f, 2048.f) + 3) & ~3;      // whole 4 x 4 x 4 blocks
+                cells *= S.g[d];
+            }
             if (cells <= budget) break;
             h *= 1.26f;
         }
@@ -167,38 +182,84 @@ nn_query_kernel(const float *__restrict__ xyz, const int32_t *__restrict__ count
     if (S.n_seen == 0) { match[i] = -1; return; }
     const float fx = xyz[i * 3], fy = xyz[i * 3 + 1], fz = xyz[i * 3 + 2];
     const double px = fx, py = fy, pz = fz;
-    int cx = (int)floorf((fx - S.mn[0]) * S.inv_h), cy = (int)floorf((fy - S.mn[1]) * S.inv_h), cz = (int)floorf((fz - S.mn[2]) * S.inv_h);
-    cx = min(max(cx, 0), S.g[0] - 1); cy = min(max(cy, 0), S.g[1] - 1); cz = min(max(cz, 0), S.g[2] - 1);
+    int cx, cy, cz;
+    nn_cell_coords(S, fx, fy, fz, cx, cy, cz);
     const int *cs = cells + nn_cell_base(seg_off, s), *ce = cursor + nn_cell_base(seg_off, s);
     const int *srt = sorted + a;
     const float *base = xyz + a * 3;
     double best = CUDART_INF;
     int best_i = -1;
-    const int rmax = max(S.g[0], max(S.g[1], S.g[2]));
-    for (int r = 0; r <= rmax; ++r) {
-        // every unvisited point differs by more than (r - 1) h along some axis once ring r - 1 is done;
-        // the cell size carries float32 rounding, hence the 0.999
+    auto scan = [&](int q0, int q1) {
+        for (int q = q0; q < q1; ++q) {
+            const int j = srt[q];
+            const double dx = px - (double)base[j * 3], dy = py - (double)base[j * 3 + 1], dz = pz - (double)base[j * 3 + 2];
+            const double d = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+            if (d < best || (d == best && j < best_i)) { best = d; best_i = j; }
+        }
+    };
+    // Once every cell (block) within Chebyshev distance R of the query's own cell (block) has been scanned,
+    // any other seen point differs by more than R cell (block) sizes along some axis — also when the query
+    // lies outside the grid and its cell was clamped.  The cell size carries float32 rounding: 0.999.
+    bool done = false;
+    constexpr int NN_FINE_RINGS = 3;
+    for (int r = 0; r <= NN_FINE_RINGS && !done; ++r) {
         if (r > 0) {
             const double reach = 0.999 * (double)(r - 1) * (double)S.h;
-            if (best <= reach * reach) break;
+            if (best <= reach * reach) { done = true; break; }
         }
         const int z0 = max(cz - r, 0), z1 = min(cz + r, S.g[2] - 1);
         const int y0 = max(cy - r, 0), y1 = min(cy + r, S.g[1] - 1);
         for (int z = z0; z <= z1; ++z)
             for (int y = y0; y <= y1; ++y) {
                 const bool face = (z == cz - r) || (z == cz + r) || (y == cy - r) || (y == cy + r);
-                const int xs = face ? 1 : 2 * r;            // interior rows: only the two end cells
-                for (int x = cx - r; x <= cx + r; x += (xs > 0 ? xs : 1)) {
+                const int xs = (face || r == 0) ? 1 : 2 * r;     // interior rows: only the two end cells
+                for (int x = cx - r; x <= cx + r; x += xs) {
                     if (x < 0 || x >= S.g[0]) continue;
-                    const int c = (z * S.g[1] + y) * S.g[0] + x;
-                    for (int q = cs[c]; q < ce[c]; ++q) {
-                        const int j = srt[q];
-                        const double dx = px - (double)base[j * 3], dy = py - (double)base[j * 3 + 1], dz = pz - (double)base[j * 3 + 2];
-                        const double d = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-                        if (d < best || (d == best && j < best_i)) { best = d; best_i = j; }
-                    }
+                    const int c = nn_cell_index(S, x, y, z);
+                    scan(cs[c], ce[c]);
                 }
             }
+    }
+    if (!done) {
+        {   // rings 0..3 of cells are complete
+            const double reach = 0.999 * (double)NN_FINE_RINGS * (double)S.h;
+            done = best <= reach * reach;
+        }
+        const int bxn = S.g[0] >> 2, byn = S.g[1] >> 2, bzn = S.g[2] >> 2;
+        const int bx = cx >> 2, by = cy >> 2, bz = cz >> 2;
+        const double bh = 4.0 * (double)S.h;
+        const int rmax = max(bxn, max(byn, bzn));
+        for (int r = 0; r <= rmax && !done; ++r) {
+            if (r > 0) {
+                const double reach = 0.999 * (double)(r - 1) * bh;
+                if (best <= reach * reach) break;
+            }
+            const int z0 = max(bz - r, 0), z1 = min(bz + r, bzn - 1);
+            const int y0 = max(by - r, 0), y1 = min(by + r, byn - 1);
+            for (int z = z0; z <= z1; ++z)
+                for (int y = y0; y <= y1; ++y) {
+                    const bool face = (z == bz - r) || (z == bz + r) || (y == by - r) || (y == by + r);
+                    const int xs = (face || r == 0) ? 1 : 2 * r;
+                    for (int x = bx - r; x <= bx + r; x += xs) {
+                        if (x < 0 || x >= bxn) continue;
+                        // skip a block that cannot hold anything closer than the best so far (distance from
+                        // the query to the block's box, shrunk by 0.1 % of a block for the float32 cell maths)
+                        const double lo[3] = {(double)S.mn[0] + x * bh, (double)S.mn[1] + y * bh, (double)S.mn[2] + z * bh};
+                        const double q3[3] = {px, py, pz};
+                        double gap2 = 0.0;
+                        const bool last[3] = {x == bxn - 1, y == byn - 1, z == bzn - 1};   // clamped coordinates end up here
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) {
+                            const double above = last[d] ? 0.0 : q3[d] - (lo[d] + bh);
+                            const double g = fmax(fmax(lo[d] - q3[d], above), 0.0) - 0.001 * bh;
+                            if (g > 0.0) gap2 += g * g;
+                        }
+                        if (gap2 >= best) continue;
+                        const int blk = ((z * byn + y) * bxn + x) * 64;
+                        scan(cs[blk], ce[blk + 63]);            // the 64 cells of a block are contiguous
+                    }
+                }
+        }
     }
     match[i] = best_i;
 }
