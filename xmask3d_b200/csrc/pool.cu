@@ -22,6 +22,10 @@
 // A first version kept all k accumulator rows of a persistent CTA in shared memory and streamed
 // points in storage order; it reached only 16 % of the HBM roofline on B200 (one CTA per SM, and
 // register-ring prefetch deeper than the six scoreboard slots does not overlap) — see DESIGN.md.
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 #include "vec.cuh"
 
@@ -417,12 +421,174 @@ pool_combine_kernel(const float *__restrict__ partial, const int32_t *__restrict
     if (cnt && ch == 0) cnt[u] = n;
 }
 
+
+// ---- point-major variant for overlapping masks ------------------------------------------------
+// With overlapping masks the pair lists above read every feature row once PER MEMBERSHIP (7.7 x 3 KB per
+// point in the reference's raw thresholded predictions).  Here every row is read from HBM exactly once:
+// a work item is (segment, 128-channel slice); a persistent CTA streams the item's rows through two
+// 80 KB shared-memory buffers (one 512-byte bulk copy per row, mbarrier-tracked, the next tile in
+// flight while the current one is consumed — row_index indirection included), transposes the tile's
+// membership words into per-mask bit rows with warp ballots, and every warp sums the member rows of
+// its masks out of shared memory in point order (one float4 per lane), adding the tile's partial to the
+// mask's accumulator row in shared memory.  No pair list, no partial rows in HBM, no combine pass;
+// the order of every sum is fixed (tiles ascending, points ascending), so the result is deterministic.
+bool make_row_tile_map(CUtensorMap *m, const float *base, int64_t rows, int c, int box_cols, int box_rows);   // logits.cu
+
+constexpr int PR_THREADS = 512;
+constexpr int PR_WARPS = PR_THREADS / 32;
+constexpr int PR_SLICE = 128;                 // channels per work item
+constexpr int PR_TP = 160;                    // points per tile
+constexpr int PR_GROUPS = PR_TP / 32;
+constexpr int PR_KMAX = 96;                   // accumulator rows that fit next to the two buffers
+static size_t pool_rows_smem(int k) {
+    return 2 * (size_t)PR_TP * PR_SLICE * 4 + (size_t)PR_TP * 4 * 4 + (size_t)k * PR_SLICE * 4 + (size_t)k * 4 + 128;
+}
+
+template <int W>
+__global__ void __launch_bounds__(PR_THREADS, 1)
+pool_rows_kernel(const __grid_constant__ CUtensorMap map, const int use_map, const PoolIdx P,
+                 const float *__restrict__ feat, int c, float *__restrict__ sum,
+                 float *__restrict__ mean, int32_t *__restrict__ cnt, int *__restrict__ work) {
+    extern __shared__ __align__(128) unsigned char pr_smem[];
+    float *buf0 = reinterpret_cast<float *>(pr_smem);
+    float *buf1 = buf0 + PR_TP * PR_SLICE;
+    uint32_t *bits = reinterpret_cast<uint32_t *>(buf1 + PR_TP * PR_SLICE);          // [PR_TP][W] membership words of the tile
+    float *acc = reinterpret_cast<float *>(bits + PR_TP * W);                        // [k][PR_SLICE], 16-byte aligned
+    int *cntm = reinterpret_cast<int *>(acc + P.k * PR_SLICE);                       // [k]
+    __shared__ uint64_t s_full[2];
+    __shared__ int s_item, s_next;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nsl = c / PR_SLICE;
+    const int n_items = P.n_seg * nsl;
+    if (tid == 0) { mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1); mbar_fence_init(); }
+    __syncthreads();
+    uint32_t ph0 = 0, ph1 = 0;
+    const int64_t total_rows = P.seg_off[P.n_seg];
+    const bool over = total_rows > P.cap;
+    for (;;) {
+        if (tid == 0) s_item = atomicAdd(work, 1);
+        __syncthreads();
+        const int item = s_item;
+        if (item >= n_items) break;
+        const int s = item / nsl, sl = item - s * nsl;
+        const int64_t a = P.seg_off[s];
+        const int n = over ? 0 : (int)(P.seg_off[s + 1] - a);
+        for (int j = tid; j < P.k * PR_SLICE; j += PR_THREADS) acc[j] = 0.f;
+        for (int j = tid; j < P.k; j += PR_THREADS) cntm[j] = 0;
+        const int ntile = (n + PR_TP - 1) / PR_TP;
+        const float *fsl = feat + (size_t)sl * PR_SLICE;
+        auto issue = [&](int t) {                         // warp 0: the rows of tile t -> buffer t & 1
+            const int rows = min(PR_TP, n - t * PR_TP);
+            uint64_t *bar = &s_full[t & 1];
+            float *dst = (t & 1) ? buf1 : buf0;
+            if (use_map && a + (int64_t)(t + 1) * PR_TP <= total_rows) {
+                // contiguous rows: ONE tensor copy per tile (160 bulk copies of 512 bytes cost ~10 us per tile);
+                // rows past the segment (they belong to the next one) are loaded but never referenced; a tile that
+                // would reach past the last point of the batch takes the row-by-row path below
+                if (lane == 0) {
+                    mbar_expect_tx(bar, (uint32_t)PR_TP * PR_SLICE * 4);
+                    asm volatile(
+                        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                        ::"r"(smem_u32(dst)), "l"(&map), "r"(smem_u32(bar)), "r"(sl * PR_SLICE), "r"((int)(a + (int64_t)t * PR_TP))
+                        : "memory");
+                }
+                return;
+            }
+            if (lane == 0) mbar_expect_tx(bar, (uint32_t)rows * PR_SLICE * 4);
+            __syncwarp();
+            for (int r = lane; r < rows; r += 32) {
+                const int64_t i = a + (int64_t)t * PR_TP + r;
+                const int64_t row = P.row_index ? (int64_t)__ldg(P.row_index + i) : i;
+                bulk_g2s(dst + r * PR_SLICE, fsl + (size_t)row * c, PR_SLICE * 4, bar);
+            }
+        };
+        if (warp == 0 && ntile > 0) issue(0);
+        for (int t = 0; t < ntile; ++t) {
+            // the other buffer is free: everybody passed the barrier that ends iteration t - 1
+            if (warp == 0 && t + 1 < ntile) issue(t + 1);
+            if (warp < PR_GROUPS) {                       // membership words of this tile -> shared memory
+                const int pnt = t * PR_TP + warp * 32 + lane;
+                uint32_t b[W];
+                load_bits<W>(P, a + pnt, pnt < n, b);
+#pragma unroll
+                for (int w = 0; w < W; ++w) bits[(warp * 32 + lane) * W + w] = b[w];
+            }
+            if (tid == PR_THREADS - 1) s_next = 0;
+            __syncthreads();
+            if (t & 1) { mbar_wait(&s_full[1], ph1); ph1 ^= 1; } else { mbar_wait(&s_full[0], ph0); ph0 ^= 1; }
+            const float4 *rows4 = reinterpret_cast<const float4 *>((t & 1) ? buf1 : buf0);
+            for (;;) {
+                // masks are handed out dynamically: their sizes differ by an order of magnitude (every mask is
+                // still summed by ONE warp per tile, in point order, so the result does not depend on who takes it)
+                int m = 0;
+                if (lane == 0) m = atomicAdd(&s_next, 1);
+                m = __shfl_sync(0xffffffffu, m, 0);
+                if (m >= P.k) break;
+                // bit rows of mask m (one ballot per group of 32 points), kept in registers
+                uint32_t v[PR_GROUPS];
+                int members = 0;
+#pragma unroll
+                for (int g = 0; g < PR_GROUPS; ++g) {
+                    v[g] = __ballot_sync(0xffffffffu, (bits[(g * 32 + lane) * W + (m >> 5)] >> (m & 31)) & 1u);
+                    members += __popc(v[g]);
+                }
+                if (!members) continue;
+                float4 part = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int g = 0; g < PR_GROUPS; ++g) {
+                    uint32_t vv = v[g];
+                    const float4 *rg = rows4 + (g * 32) * (PR_SLICE / 4) + lane;
+                    while (vv) {                          // up to four rows in flight, added in point order
+                        float4 x[4];
+                        int cntx = 0;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (vv) {
+                                const int r = __ffs(vv) - 1;
+                                vv &= vv - 1;
+                                x[q] = rg[r * (PR_SLICE / 4)];
+                                cntx = q + 1;
+                            }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (q < cntx) vadd(part, x[q]);
+                    }
+                }
+                float4 *A = reinterpret_cast<float4 *>(acc + m * PR_SLICE) + lane;
+                float4 cur = *A;
+                vadd(cur, part);
+                *A = cur;
+                if (lane == 0) cntm[m] += members;
+            }
+            __syncthreads();
+        }
+        if (ntile == 0) __syncthreads();                  // the zeroing above before the read below
+        for (int m = warp; m < P.k; m += PR_WARPS) {
+            const float4 v = *(reinterpret_cast<const float4 *>(acc + m * PR_SLICE) + lane);
+            const int nm = cntm[m];
+            const size_t o = ((size_t)s * P.k + m) * c + (size_t)sl * PR_SLICE + lane * 4;
+            *reinterpret_cast<float4 *>(sum + o) = v;
+            if (mean) {
+                float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (nm > 0) {
+                    const float d = (float)nm;
+                    q = make_float4(__fdiv_rn(v.x, d), __fdiv_rn(v.y, d), __fdiv_rn(v.z, d), __fdiv_rn(v.w, d));
+                }
+                *reinterpret_cast<float4 *>(mean + o) = q;
+            }
+            if (cnt && sl == 0 && lane == 0) cnt[s * P.k + m] = nm;
+        }
+        __syncthreads();
+    }
+}
+
 struct PoolWs {
     int32_t *cnt, *chunk_off, *perm, *tile_off, *tile_cnt;
     int64_t max_tiles;
     int64_t *pair_off;
     float *partial;
     int64_t max_chunks;
+    int *work;                 // work-item counter of the point-major kernel
 };
 
 static PoolWs carve_pool(void *ws, int n_seg, int k, int c, int64_t cap, int64_t cap_pairs, size_t *bytes) {
@@ -438,6 +604,7 @@ static PoolWs carve_pool(void *ws, int n_seg, int k, int c, int64_t cap, int64_t
     w.max_tiles = cap / FILL_THREADS + n_seg + 1;
     w.tile_off = cv.take<int32_t>((size_t)n_seg + 1);
     w.tile_cnt = cv.take<int32_t>((size_t)w.max_tiles * k);
+    w.work = cv.take<int>(64);
     *bytes = cv.off + 256;
     return w;
 }
@@ -474,6 +641,34 @@ extern "C" int xm3d_pool_batch(const float *feat, int32_t c, const int32_t *row_
     I.member = member; I.label = label; I.row_index = row_index; I.seg_off = seg_off; I.n_seg = n_seg; I.k = k;
     I.words = words_for(k); I.cap = cap;
     const int n_units = n_seg * k;
+    // Overlapping masks (the caller's bound allows more memberships than points): point-major kernel, every
+    // row read once.  cap_pairs is not a limit on this path (there is no pair list to overrun).
+    const bool out16 = reinterpret_cast<uintptr_t>(sum) % 16 == 0 && (!mean || reinterpret_cast<uintptr_t>(mean) % 16 == 0);
+    if (member && cap_pairs > cap + 1 && vec == 4 && c % PR_SLICE == 0 && k <= PR_KMAX && out16 && !getenv("XM3D_POOL_PAIR_LISTS")) {
+        const size_t smem = pool_rows_smem(k);
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(pool_rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+            cudaFuncSetAttribute(pool_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+            cudaFuncSetAttribute(pool_rows_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+            attr_set = true;
+        }
+        cudaMemsetAsync(w.work, 0, sizeof(int), stream);
+        const int n_items = n_seg * (c / PR_SLICE);
+        const unsigned grid = (unsigned)(n_items < sm_count() ? n_items : sm_count());
+        CUtensorMap map;
+        memset(&map, 0, sizeof(map));
+        // (the map's row count only bounds the coordinates: the kernel never asks for rows past the last point)
+        const int use_map = (!row_index && cap > 0 && cap < ((int64_t)1 << 31) - PR_TP &&
+                             make_row_tile_map(&map, feat, cap, c, PR_SLICE, PR_TP)) ? 1 : 0;
+        if (g_pool_ev[0]) cudaEventRecord(g_pool_ev[0], stream);
+        if (I.words <= 1) pool_rows_kernel<1><<<grid, PR_THREADS, smem, stream>>>(map, use_map, I, feat, c, sum, mean, cnt, w.work);
+        else if (I.words <= 2) pool_rows_kernel<2><<<grid, PR_THREADS, smem, stream>>>(map, use_map, I, feat, c, sum, mean, cnt, w.work);
+        else pool_rows_kernel<4><<<grid, PR_THREADS, smem, stream>>>(map, use_map, I, feat, c, sum, mean, cnt, w.work);
+        if (g_pool_ev[1]) cudaEventRecord(g_pool_ev[1], stream);
+        count_launches(1);
+        return check_launch("xm3d_pool_batch");
+    }
     pool_tileplan_kernel<<<1, 1024, 0, stream>>>(seg_off, n_seg, cap, w.tile_off); count_launches(1);
     const int wt = I.words <= 1 ? 1 : (I.words <= 2 ? 2 : (I.words <= 4 ? 4 : 8));
     const unsigned tgrid = (unsigned)w.max_tiles;
