@@ -441,7 +441,7 @@ constexpr int PR_TP = 160;                    // points per tile
 constexpr int PR_GROUPS = PR_TP / 32;
 constexpr int PR_KMAX = 96;                   // accumulator rows that fit next to the two buffers
 static size_t pool_rows_smem(int k) {
-    return 2 * (size_t)PR_TP * PR_SLICE * 4 + (size_t)PR_TP * 4 * 4 + (size_t)k * PR_SLICE * 4 + (size_t)k * 4 + 128;
+    return 2 * (size_t)PR_TP * PR_SLICE * 4 + 2 * (size_t)PR_TP * 4 * 4 + (size_t)k * PR_SLICE * 4 + (size_t)k * 4 + 128;
 }
 
 template <int W>
@@ -452,8 +452,8 @@ pool_rows_kernel(const __grid_constant__ CUtensorMap map, const int use_map, con
     extern __shared__ __align__(128) unsigned char pr_smem[];
     float *buf0 = reinterpret_cast<float *>(pr_smem);
     float *buf1 = buf0 + PR_TP * PR_SLICE;
-    uint32_t *bits = reinterpret_cast<uint32_t *>(buf1 + PR_TP * PR_SLICE);          // [PR_TP][W] membership words of the tile
-    float *acc = reinterpret_cast<float *>(bits + PR_TP * W);                        // [k][PR_SLICE], 16-byte aligned
+    uint32_t *bits_all = reinterpret_cast<uint32_t *>(buf1 + PR_TP * PR_SLICE);      // [2][PR_TP][W] membership words of two tiles
+    float *acc = reinterpret_cast<float *>(bits_all + 2 * PR_TP * W);                // [k][PR_SLICE], 16-byte aligned
     int *cntm = reinterpret_cast<int *>(acc + P.k * PR_SLICE);                       // [k]
     __shared__ uint64_t s_full[2];
     __shared__ int s_item, s_next;
@@ -503,18 +503,25 @@ pool_rows_kernel(const __grid_constant__ CUtensorMap map, const int use_map, con
             }
         };
         if (warp == 0 && ntile > 0) issue(0);
+        if (warp < PR_GROUPS && ntile > 0) {              // membership words of tile 0
+            const int pnt = warp * 32 + lane;
+            uint32_t b0[W];
+            load_bits<W>(P, a + pnt, pnt < n, b0);
+#pragma unroll
+            for (int w = 0; w < W; ++w) bits_all[(warp * 32 + lane) * W + w] = b0[w];
+        }
         for (int t = 0; t < ntile; ++t) {
             // the other buffer is free: everybody passed the barrier that ends iteration t - 1
             if (warp == 0 && t + 1 < ntile) issue(t + 1);
-            if (warp < PR_GROUPS) {                       // membership words of this tile -> shared memory
-                const int pnt = t * PR_TP + warp * 32 + lane;
-                uint32_t b[W];
-                load_bits<W>(P, a + pnt, pnt < n, b);
-#pragma unroll
-                for (int w = 0; w < W; ++w) bits[(warp * 32 + lane) * W + w] = b[w];
-            }
             if (tid == PR_THREADS - 1) s_next = 0;
-            __syncthreads();
+            __syncthreads();                              // the words of tile t are in wbuf (stored one iteration ago)
+            const uint32_t *bits = bits_all + (t & 1) * (PR_TP * W);
+            uint32_t nb[W];
+            const bool pre = warp < PR_GROUPS && t + 1 < ntile;
+            if (pre) {                                    // membership words of the NEXT tile: in flight during the sums
+                const int pnt = (t + 1) * PR_TP + warp * 32 + lane;
+                load_bits<W>(P, a + pnt, pnt < n, nb);
+            }
             if (t & 1) { mbar_wait(&s_full[1], ph1); ph1 ^= 1; } else { mbar_wait(&s_full[0], ph0); ph0 ^= 1; }
             const float4 *rows4 = reinterpret_cast<const float4 *>((t & 1) ? buf1 : buf0);
             for (;;) {
@@ -559,6 +566,10 @@ pool_rows_kernel(const __grid_constant__ CUtensorMap map, const int use_map, con
                 vadd(cur, part);
                 *A = cur;
                 if (lane == 0) cntm[m] += members;
+            }
+            if (pre) {
+#pragma unroll
+                for (int w = 0; w < W; ++w) bits_all[((t + 1) & 1) * (PR_TP * W) + (warp * 32 + lane) * W + w] = nb[w];
             }
             __syncthreads();
         }
