@@ -190,7 +190,9 @@ XM3D_API int xm3d_pixel_bits_batch(const void *masks, int32_t mask_kind, int32_t
  *   member    as produced by xm3d_gather_masks_batch (general, overlapping masks) OR
  *   label     int32 [cap], values outside [0,k) = in no mask (partition masks); exactly one of the two
  *   cap_pairs bounds the total number of (point, mask) memberships (= cap for labels / partition
- *   masks); beyond it XM3D_FLAG_PAIR_OVERFLOW is raised and the sums are zero.
+ *   masks); beyond it XM3D_FLAG_PAIR_OVERFLOW is raised and the sums are zero.  cap_pairs > cap + 1 also
+ *   tells the library that masks may overlap: with member words, c % 128 == 0 and k <= 96 it then runs the
+ *   point-major kernel, which reads every row once and has no pair list (cap_pairs is not a limit there).
  *   sum [n_seg,k,c] float32, cnt [n_seg,k] int32 (optional), mean (optional) [n_seg,k,c] = sum/cnt
  *   (0 where cnt = 0).  Deterministic: every summation order is fixed by the point order. */
 XM3D_API size_t xm3d_pool_ws_bytes(int32_t n_seg, int32_t k, int32_t c, int64_t cap, int64_t cap_pairs);
