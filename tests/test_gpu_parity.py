@@ -370,12 +370,12 @@ def test_gather_pool_scatter_golden(golden, cport, dev):
     np.testing.assert_allclose(sp[0].cpu().numpy(), g["score_pool"], rtol=1e-5, atol=1e-7)
 
 
-@pytest.mark.parametrize("k,c", [(50, 768), (100, 768), (7, 64), (130, 256), (3, 1)])
+@pytest.mark.parametrize("k,c", [(50, 768), (100, 768), (7, 64), (130, 256), (3, 1), (96, 128), (33, 256)])
 def test_pool_scatter_vs_oracle(cport, dev, k, c):
     """Ragged batch (incl. an empty segment), overlapping members and partition labels."""
     from xmask3d_b200 import ops
     rng = np.random.default_rng(k * 1000 + c)
-    n = [3000, 0, 1777, 1, 5200]
+    n = [3000, 0, 1777, 1, 5200, 320]          # 320 = two full tiles of the point-major kernel
     off = np.concatenate([[0], np.cumsum(n)]).astype(np.int64)
     total = int(off[-1])
     feat = rng.standard_normal((total, c), dtype=np.float32)

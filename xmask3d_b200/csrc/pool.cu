@@ -655,7 +655,7 @@ extern "C" int xm3d_pool_batch(const float *feat, int32_t c, const int32_t *row_
     // Overlapping masks (the caller's bound allows more memberships than points): point-major kernel, every
     // row read once.  cap_pairs is not a limit on this path (there is no pair list to overrun).
     const bool out16 = reinterpret_cast<uintptr_t>(sum) % 16 == 0 && (!mean || reinterpret_cast<uintptr_t>(mean) % 16 == 0);
-    if (member && cap_pairs > cap + 1 && vec == 4 && c % PR_SLICE == 0 && k <= PR_KMAX && out16 && !getenv("XM3D_POOL_PAIR_LISTS")) {
+    if (member && (cap_pairs > cap + 1 || getenv("XM3D_POOL_ROWS")) && vec == 4 && c % PR_SLICE == 0 && k <= PR_KMAX && out16 && !getenv("XM3D_POOL_PAIR_LISTS")) {
         const size_t smem = pool_rows_smem(k);
         static bool attr_set = false;
         if (!attr_set) {
