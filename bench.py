@@ -601,7 +601,8 @@ def run_native(args, rank: int, world: int, local_rank: int):
     default_wl = (args.scenes, args.views, args.points, args.k, args.c, args.masks, rank) == (8, 20, 150_000, 50, 768, "partition", 0)
     if default_wl and os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("_summary", {}).get("traffic_bytes_per_launch")
-    roof = {"bound": "hbm", "kernel": "pool_sum_kernel<4> (events recorded around this launch alone)",
+    roof = {"bound": "hbm", "kernel": ("pool_rows_kernel (point-major, overlapping masks" if args.masks == "overlap"
+                                     else "pool_sum_kernel<4> (pair lists") + "; events recorded around this launch alone)",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
             "bytes_per_launch": pool_bytes, "ms_per_launch": pool_ms, "peak_source": peak_src}
     pipe_gbs = alg["total"] / (step_ms * 1e-3) / 1e9
