@@ -846,3 +846,18 @@ def test_nn_fill_and_segment_max(golden, dev):
     soff = np.concatenate([[0], np.cumsum(np.bincount(idx))]).astype(np.int64)
     sm = ops.segment_max(torch.from_numpy(g["feat"]).to(dev), torch.from_numpy(soff).to(dev)).cpu().numpy()
     assert np.array_equal(sm, g["segmax"])
+
+
+def test_voxelize_with_clip_bound_golden(golden, dev):
+    """voxelize() with a clip_bound (dataset/voxelizer.py:87-102): the translation-augmentation draws come
+    before the matrix draws, the cloud is cropped, then voxelized — same np.random state, same outputs."""
+    from tests.golden.make_golden_params import vox_kwargs
+    from xmask3d_b200.voxelizer import Voxelizer
+    g = golden("clip")
+    kw = vox_kwargs(0.05)
+    kw["clip_bound"] = tuple(map(tuple, g["clip"]))
+    np.random.seed(991)
+    grid, feats, lab, inv, inds = Voxelizer(**kw).voxelize(g["xyz"], g["colors"].copy(), g["labels"].copy(),
+                                                           return_ind=True)
+    assert np.array_equal(grid, g["grid"]) and np.array_equal(inv, g["inv"]) and np.array_equal(inds, g["inds"])
+    assert np.array_equal(feats, g["feats"]) and np.array_equal(lab, g["lab"])

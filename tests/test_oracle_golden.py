@@ -168,3 +168,17 @@ def test_nn_fill_and_segment_max_oracle_vs_reference_statements(golden):
     seen = np.nonzero(g["counter"] != 0)[0]
     assert np.array_equal(match[seen], seen)
     assert np.array_equal(ref_port.segment_max(g["feat"], g["idx"]), g["segmax"])
+
+
+def test_voxelizer_clip_matches_reference(golden):
+    """Voxelizer.clip (dataset/voxelizer.py:60-79; dead at every shipped config but part of the API):
+    the host shim returns the reference's crop predicate, with and without an explicit centre."""
+    from tests.golden.make_golden_params import vox_kwargs
+    from xmask3d_b200.voxelizer import Voxelizer
+    g = golden("clip")
+    kw = vox_kwargs(0.05)
+    kw["clip_bound"] = tuple(map(tuple, g["clip"]))
+    vox = Voxelizer(**kw)
+    assert np.array_equal(vox.clip(g["xyz"]), g["inside_default"])
+    got = vox.clip(g["xyz"], center=g["centre"].copy(), trans_aug_ratio=np.array([0.1, -0.05, 0.0]))
+    assert np.array_equal(got, g["inside_centre"])
