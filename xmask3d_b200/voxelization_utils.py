@@ -36,54 +36,53 @@ def ravel_hash_vec(arr):
     return _keys_to_numpy(ops.ravel_hash(t))
 
 
+def _validate(coords, feats, labels, hash_type):
+    """Same failure behaviour as the reference (:53-66): AssertionError on a bad hash type or bad shapes."""
+    if hash_type not in ("ravel", "fnv"):
+        raise AssertionError(f"hash_type must be 'ravel' or 'fnv', got {hash_type!r}")
+    if coords.ndim != 2:
+        raise AssertionError(f"coords must be a 2-D [n, dim] array, got shape {coords.shape}")
+    if feats is not None and (feats.ndim != 2 or feats.shape[0] != coords.shape[0]):
+        raise AssertionError("feats must be a 2-D array with one row per coordinate")
+    if labels is not None and len(labels) != coords.shape[0]:
+        raise AssertionError("labels must hold one entry per coordinate")
+
+
+def _cell_size(quantization_size, dim):
+    """Per-axis cell size (:68-77): a scalar is broadcast, a sequence must have `dim` entries."""
+    if np.isscalar(quantization_size):
+        return np.full(dim, quantization_size)
+    if isinstance(quantization_size, (list, tuple, np.ndarray, torch.Tensor)):
+        if len(quantization_size) != dim:
+            raise AssertionError("quantization_size needs one entry per coordinate axis")
+        return np.array([q for q in quantization_size])
+    raise ValueError("Not supported type for quantization_size.")
+
+
 def sparse_quantize(coords, feats=None, labels=None, ignore_label=255,
                     set_ignore_label_when_collision=False, return_index=False,
                     hash_type="fnv", quantization_size=1):
-    """Reference :38-102.  Returns exactly what the reference returns for every flag combination."""
-    use_label = labels is not None
-    use_feat = feats is not None
-    if not use_label and not use_feat:
-        return_index = True
-    assert hash_type in ["ravel", "fnv"], \
-        "Invalid hash_type. Either ravel, or fnv allowed. You put hash_type=" + hash_type
-    assert coords.ndim == 2, \
-        "The coordinates must be a 2D matrix. The shape of the input is " + str(coords.shape)
-    if use_feat:
-        assert feats.ndim == 2
-        assert coords.shape[0] == feats.shape[0]
-    if use_label:
-        assert coords.shape[0] == len(labels)
-    dimension = coords.shape[1]
-    if isinstance(quantization_size, (list, tuple, np.ndarray)) or \
-            (hasattr(quantization_size, "__len__") and not np.isscalar(quantization_size)):
-        assert len(quantization_size) == dimension, "Quantization size and coordinates size mismatch."
-        quantization_size = [i for i in quantization_size]
-    elif np.isscalar(quantization_size):
-        quantization_size = [quantization_size for _ in range(dimension)]
-    else:
-        raise ValueError("Not supported type for quantization_size.")
-    # host side, exactly the reference's arithmetic (float64 divide + floor); the hashing and the
-    # unique / inverse maps run on the GPU
-    discrete = np.floor(coords / np.array(quantization_size))
+    """Reference :38-102.  Returns exactly what the reference returns for every flag combination:
+    with labels (inds, labels') or (cells, feats, labels'); without labels (inds, inverse), (cells, feats)
+    or cells — where inds / inverse are np.unique's first-occurrence and inverse maps of the cell keys."""
+    _validate(coords, feats, labels, hash_type)
+    with_labels, with_feats = labels is not None, feats is not None
+    want_index = return_index or not (with_labels or with_feats)
+    # host side, the reference's arithmetic (float64 divide + floor, :78); hashing and the unique /
+    # first-index / inverse / count maps run on the GPU
+    cells = np.floor(coords / _cell_size(quantization_size, coords.shape[1]))
     dev = _dev()
-    d = torch.from_numpy(np.ascontiguousarray(discrete, dtype=np.float64)).to(dev)
+    d = torch.from_numpy(np.ascontiguousarray(cells, dtype=np.float64)).to(dev)
     keys = ops.ravel_hash(d) if hash_type == "ravel" else ops.fnv_hash(d)
-    n = discrete.shape[0]
-    seg = torch.tensor([0, n], dtype=torch.int64, device=dev)
-    u = ops.unique_batch(keys, seg, want_counts=use_label)
+    n = cells.shape[0]
+    u = ops.unique_batch(keys, torch.tensor([0, n], dtype=torch.int64, device=dev), want_counts=with_labels)
     m = int(u.m[0].item())
     inds = u.first[:m].cpu().numpy().astype(np.int64)
-    if use_label:
-        counts = u.counts[:m].cpu().numpy()
-        filtered = labels[inds]
+    if with_labels:                                             # :86-93
+        kept = labels[inds]
         if set_ignore_label_when_collision:
-            filtered[counts > 1] = ignore_label
-        if return_index:
-            return inds, filtered
-        return discrete[inds], feats[inds], filtered
-    inverse = u.inverse[:n].cpu().numpy().astype(np.int64)
-    if return_index:
-        return inds, inverse
-    if use_feat:
-        return discrete[inds], feats[inds]
-    return discrete[inds]
+            kept[u.counts[:m].cpu().numpy() > 1] = ignore_label
+        return (inds, kept) if want_index else (cells[inds], feats[inds], kept)
+    if want_index:                                              # :95-97
+        return inds, u.inverse[:n].cpu().numpy().astype(np.int64)
+    return (cells[inds], feats[inds]) if with_feats else cells[inds]
