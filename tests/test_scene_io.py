@@ -114,3 +114,43 @@ def test_files_to_device_pipeline_and_collation(tmp_path):
     assert torch.equal(ori[:n].cpu(), want_loc)
     assert torch.equal(coords[:M].cpu(), want_crd)
     assert np.array_equal(inv[:n].astype(np.int64), want_ind.numpy())
+
+
+def test_scene_cache_matches_loader_preprocessing(tmp_path):
+    """The /dev/shm scene cache (dataset/point_loader.py:123-181): same keys, same preprocessing as the
+    uncached branch (:182-188), idempotent init, attach returns private copies."""
+    import numpy as np
+    from xmask3d_b200 import scene_io
+    rng = np.random.default_rng(0)
+    paths = []
+    raw = []
+    for i in range(3):
+        n = 500 + 37 * i
+        locs = rng.uniform(-3, 3, (n, 3)).astype(np.float32)
+        feats = rng.uniform(-1, 1, (n, 3)).astype(np.float32)
+        labels = rng.integers(0, 20, n).astype(np.float64)
+        labels[rng.uniform(size=n) < 0.1] = -100
+        p = str(tmp_path / f"scene{i}.pth")
+        scene_io.write_scene_pth(p, locs, feats, labels)
+        paths.append(p)
+        raw.append((locs, feats, labels))
+    cache = scene_io.SceneCache("scannet_3d", "val", identifier=7, root=str(tmp_path))
+    assert cache.key("locs", 2) == "scannet_3d_val_000007_locs_00000002"
+    assert not cache.ready()
+    assert cache.init(paths, workers=2) == 3 and cache.ready()
+    assert cache.init(paths) == 0                                   # already there
+    for i, (locs, feats, labels) in enumerate(raw):
+        l2, f2, y2 = cache.attach(i)
+        # the uncached branch of the loader, restated (dataset/point_loader.py:182-188)
+        ref_labels = labels.copy()
+        ref_labels[ref_labels == -100] = 255
+        ref_labels = ref_labels.astype(np.uint8)
+        assert np.array_equal(l2, locs) and l2.dtype == np.float32
+        assert np.array_equal(f2, (feats + 1.0) * 127.5)
+        assert np.array_equal(y2, ref_labels) and y2.dtype == np.uint8
+        l2[0, 0] = 1e9                                              # a private copy: the cache is untouched
+        assert cache.attach(i)[0][0, 0] == locs[0, 0]
+    view = cache.attach(1, copy=False)[0]
+    assert not view.flags.writeable
+    cache.delete(3)
+    assert not cache.ready()

@@ -13,6 +13,7 @@ and by anyone who wants to export synthetic scenes).  `FrameBatchLoader` assembl
 of `pipeline.py` from files with a thread pool (np.loadtxt / cv2 / torch.load release the GIL for
 the bulk of their work) and `StagingRing` moves it to the device through pinned buffers on a copy
 stream, double-buffered, so file IO, H2D copies and the kernels of consecutive batches overlap.
+`SceneCache` is the loader's `/dev/shm` scene cache (dataset/point_loader.py:123-181).
 
 The depth image stays uint16 on the way to the GPU: the projection kernel divides by the scale
 itself (`depth_scale`, the `/ 1000` above) with the same IEEE division, see csrc/project.cu.
@@ -26,6 +27,78 @@ from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
+
+
+# ----------------------------------------------------------------------------- shared-memory scene cache
+def preprocess_scene(locs, feats, labels):
+    """What the point loader applies to a scene before it is cached or used (dataset/point_loader.py:140-147
+    and :182-188): labels -100 -> 255 and uint8; a scalar-zero colour array -> zeros; colours from
+    [-1, 1] to [0, 255] (float, `(feats + 1) * 127.5`)."""
+    labels = np.array(labels, copy=True)
+    labels[labels == -100] = 255
+    labels = labels.astype(np.uint8)
+    if np.isscalar(feats) and feats == 0:
+        feats = np.zeros_like(locs)
+    feats = (feats + 1.0) * 127.5
+    return locs, feats, labels
+
+
+class SceneCache:
+    """The loader's `/dev/shm` scene cache (dataset/point_loader.py:123-181: `sa_create("shm://<dataset>_
+    <split>_<identifier>_{locs,feats,labels}_<index>")` once, `SA.attach(...).copy()` per sample), so that the
+    DataLoader workers of every rank share ONE decoded copy of each scene.  SharedArray is not in the image;
+    the arrays are stored as `.npy` files under the same keys in `root` (default `/dev/shm`) and attached as
+    read-only memory maps — the same lifetime and sharing semantics (page cache of a tmpfs), the same key
+    scheme, the same preprocessing.  `init` is idempotent (the reference skips it when scene 0 exists)."""
+
+    def __init__(self, dataset_name: str, split: str, identifier: int = 0, root: str = "/dev/shm"):
+        self.dataset_name, self.split, self.identifier, self.root = dataset_name, split, int(identifier), root
+
+    def key(self, what: str, index: int) -> str:
+        return "%s_%s_%06d_%s_%08d" % (self.dataset_name, self.split, self.identifier, what, index)
+
+    def _path(self, what: str, index: int) -> str:
+        return os.path.join(self.root, self.key(what, index) + ".npy")
+
+    def ready(self) -> bool:
+        return os.path.exists(self._path("locs", 0))
+
+    def init(self, scene_paths: Sequence[str], workers: Optional[int] = None) -> int:
+        """Decode every scene file once (thread pool) and publish it; returns the number of scenes written
+        (0 if the cache was already there)."""
+        if self.ready():
+            return 0
+
+        def one(item):
+            i, path = item
+            locs, feats, labels = preprocess_scene(*read_scene_pth(path))
+            for what, arr in (("locs", locs), ("feats", feats), ("labels", labels)):
+                tmp = self._path(what, i) + ".tmp"
+                with open(tmp, "wb") as f:
+                    np.save(f, np.ascontiguousarray(arr))
+                os.replace(tmp, self._path(what, i))            # readers never see a half-written file
+            return 1
+
+        order = list(enumerate(scene_paths))
+        with ThreadPoolExecutor(max_workers=workers or min(16, os.cpu_count() or 1)) as ex:
+            done = sum(ex.map(one, order[1:]))
+        return done + one(order[0]) if order else 0             # scene 0 last: `ready()` means complete
+
+    def attach(self, index: int, copy: bool = True):
+        """(locs, feats, labels) of scene `index`; `copy=True` is the reference's `SA.attach(...).copy()`."""
+        out = []
+        for what in ("locs", "feats", "labels"):
+            a = np.load(self._path(what, index), mmap_mode="r")
+            out.append(np.array(a) if copy else a)
+        return tuple(out)
+
+    def delete(self, n_scenes: int) -> None:
+        for i in range(n_scenes):
+            for what in ("locs", "feats", "labels"):
+                try:
+                    os.remove(self._path(what, i))
+                except FileNotFoundError:
+                    pass
 
 
 # ----------------------------------------------------------------------------- single files
