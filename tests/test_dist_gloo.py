@@ -66,6 +66,50 @@ def test_allreduce_mask_sums_world2():
     assert np.array_equal(res[0][2], res[1][2])                       # identical on both ranks
 
 
+def _vote_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(3)
+        n, t, n_views = 300, 7, 5
+        seen = rng.random((n_views, n)) < 0.3
+        cls = rng.integers(0, t, (n_views, n))
+        votes = torch.zeros((n, t), dtype=torch.int32)
+        counter = torch.zeros(n, dtype=torch.int32)
+        for v in xd.shard_views(n_views, world, rank):            # this rank's views (numpy restatement of :642-647)
+            idx = np.nonzero(seen[v])[0]
+            votes[idx, cls[v][idx]] += 1
+            counter[idx] += 1
+        xd.allreduce_votes(votes, counter)
+        q.put((rank, votes.numpy(), counter.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_allreduce_votes_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_vote_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda x: x[0])
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(3)
+    n, t, n_views = 300, 7, 5
+    seen = rng.random((n_views, n)) < 0.3
+    cls = rng.integers(0, t, (n_views, n))
+    ref_v, ref_c = np.zeros((n, t), np.int32), np.zeros(n, np.int32)
+    for v in range(n_views):
+        idx = np.nonzero(seen[v])[0]
+        ref_v[idx, cls[v][idx]] += 1
+        ref_c[idx] += 1
+    for _, votes, counter in res:
+        assert np.array_equal(votes, ref_v) and np.array_equal(counter, ref_c)
+
+
 def test_sharding_properties():
     for n, w in ((100, 8), (7, 2), (3, 4), (0, 2), (20, 1)):
         parts = [list(xd.shard_views(n, w, r)) for r in range(w)]

@@ -68,6 +68,20 @@ def allreduce_mask_sums(sums: torch.Tensor, counts: torch.Tensor, group=None,
     return finish()
 
 
+def allreduce_votes(votes: torch.Tensor, counter: torch.Tensor, group=None):
+    """Cross-view vote histogram of run/infer.py:642-647 when one scene's views live on several ranks: every
+    rank accumulates `votes int32 [N, T]` / `counter int32 [N]` over ITS views (ops.accumulate_votes), one
+    all-reduce(SUM) of the packed int32 [N, T+1] buffer gives every rank the scene's totals (integers: exact
+    and order independent), after which ops.vote_argmax / ops.nn_fill run as on one GPU.  In place."""
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+        return votes, counter
+    packed = torch.cat([votes, counter.unsqueeze(1)], dim=1).contiguous()
+    dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+    votes.copy_(packed[:, :-1])
+    counter.copy_(packed[:, -1])
+    return votes, counter
+
+
 def finalize_mean(sums: torch.Tensor, counts: torch.Tensor) -> torch.Tensor:
     """mean[k,:] = sums[k,:] / counts[k] (zeros for empty masks), float32 like torch.mean of the
     reference's float32 features (models/utils/criterion.py:152-157)."""
