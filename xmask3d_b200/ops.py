@@ -559,3 +559,26 @@ def collate(proj: Projection, vox: Unique, cap: Optional[int] = None):
     L.check(L.lib().xm3d_collate_batch(_ptr(proj.xyz_vis), _ptr(proj.vis_off), _ptr(vox.voxel_xyz), _ptr(vox.uniq_off),
                                        n_seg, cap, _ptr(ori), _ptr(coords), _stream()))
     return ori, coords
+
+
+def accept_views(proj: Projection, scene_labels: torch.Tensor, view_pt_off: torch.Tensor,
+                 ignore_labels: Sequence[int] = (255,), min_points: int = 400, max_points: int = 65000,
+                 min_valid: int = 10) -> torch.Tensor:
+    """The loaders' view filter (dataset/data_loader.py:190-199, data_loader_infer.py: a frame is kept iff
+    `400 < sum(mask) < 65000` and more than 10 of its visible points carry a non-ignored label), for every
+    view of a batch at once and without a host round trip.  scene_labels: integer label per scene point
+    [sum N]; view_pt_off int64 [V]: first point of each view's scene in scene_labels.  Returns bool [V].
+    Plain torch ops on the projection's compaction outputs (works on CPU tensors too)."""
+    n_vis = proj.n_vis.to(torch.int64)
+    v = n_vis.numel()
+    cap = proj.vis_idx.shape[0]
+    dev = n_vis.device
+    j = torch.arange(cap, device=dev)
+    seg = torch.bucketize(j, proj.vis_off[1:].contiguous(), right=True).clamp_(max=v - 1)
+    live = j < proj.vis_off[-1]
+    lab = scene_labels[(view_pt_off[seg] + proj.vis_idx.to(torch.int64)).clamp_(0, scene_labels.numel() - 1)]
+    ok = live.clone()
+    for ig in ignore_labels:
+        ok &= lab != ig
+    valid = torch.zeros(v, dtype=torch.int64, device=dev).index_add_(0, seg, ok.to(torch.int64))
+    return (n_vis > min_points) & (n_vis < max_points) & (valid > min_valid)
