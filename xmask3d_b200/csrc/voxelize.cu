@@ -747,7 +747,7 @@ vox_fast_kernel(int4 *pgrid, const unsigned long long *__restrict__ keys_in,
     __syncthreads();
 
     FV_T(2);
-    // ---- insert: open addressing in shared memory; the winner of an empty slot appends it to the unique list
+    // ---- insert: open addressing in shared memory (the unique list is read off the table afterwards)
     volatile unsigned long long *vtab = s_tab;
     const unsigned int tag = (unsigned int)(p + 1) << 16;          // owner mark in pgrid[i].w (slot in the low half)
     for (int base = 0; base < n; base += FV_BATCH * FV_THREADS) {
