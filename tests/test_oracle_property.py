@@ -66,3 +66,30 @@ def test_voxelize_c_oracle_equals_numpy_port(cport, seed, n, span, voxel):
     g_ref, _, _, inv_ref, inds_ref = vox.voxelize(xyz, colors, labels, return_ind=True)
     g, first, inv = cport.voxelize(xyz, M_r @ M_v)
     assert np.array_equal(g, g_ref) and np.array_equal(first, inds_ref) and np.array_equal(inv, inv_ref)
+
+
+@settings(max_examples=40, deadline=None)
+@given(seed=st.integers(0, 2 ** 31 - 1), n=st.integers(1, 600), k=st.integers(1, 40), c=st.sampled_from([1, 7, 64]),
+       density=st.sampled_from([0.0, 0.05, 0.5]))
+def test_scatter_and_pool_c_oracle_equals_torch_port(cport, seed, n, k, c, density):
+    """mask -> point scatter-mean (fuser.py:22-34) bit for bit in float32, masked mean pooling
+    (criterion.py:152-157) against the float64 sums of the C oracle."""
+    import torch
+    rng = np.random.default_rng(seed)
+    member = rng.random((k, n)) < density
+    emb = rng.standard_normal((k, c)).astype(np.float32)
+    feat = rng.standard_normal((n, c)).astype(np.float32)
+    out, counter = cport.scatter_member_f32(member, emb)
+    ref_out, ref_counter = ref_port.scatter_mask_embed(torch.from_numpy(member), torch.from_numpy(emb),
+                                                       torch.zeros(n, c))
+    guard = member.copy()
+    if not member.any():
+        guard[0, 0] = True                                  # fuser.py:19-20, applied by the caller of the kernel
+        out, counter = cport.scatter_member_f32(guard, emb)
+    assert np.array_equal(out, ref_out.numpy())
+    assert np.array_equal(np.where(counter == 0, np.float32(1e-5), counter), ref_counter.numpy()[:, 0])
+    s64, cnt = cport.pool_member_f64(feat, member)
+    mean, ref_cnt = ref_port.masked_mean_pool(torch.from_numpy(feat), torch.from_numpy(member))
+    assert np.array_equal(cnt, ref_cnt.numpy())
+    ref64 = s64 / np.maximum(cnt, 1)[:, None]
+    assert np.abs(mean.numpy() - ref64).max() <= 1e-5 * max(1.0, np.abs(ref64).max())
