@@ -1,0 +1,84 @@
+"""Live cross-check of the oracle against the UNMODIFIED reference functions on random inputs.
+
+Runs only where the reference tree is mounted (the build container); it is skipped on the GPU box, where
+the committed golden fixtures (produced by the same functions) take over.  Nothing here touches the GPU."""
+import os
+import sys
+
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import refimport  # noqa: E402
+
+pytestmark = pytest.mark.skipif(not refimport.available(), reason="reference tree not mounted")
+
+from oracle import ref_port  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def R():
+    return refimport.load()
+
+
+@settings(max_examples=20, deadline=None)
+@given(seed=st.integers(0, 2 ** 31 - 1), n=st.integers(1, 3000), with_depth=st.booleans())
+def test_compute_mapping_live(R, seed, n, with_depth):
+    """models/utils/fusion_util.py:46-142 through models/utils/mapping_util.py:getMapping."""
+    rng = np.random.default_rng(seed)
+    xyz = rng.uniform(-4, 4, (n, 3)).astype(np.float32)
+    yaw = rng.uniform(0, 2 * np.pi)
+    pose = np.eye(4)
+    pose[:3, :3] = np.array([[np.cos(yaw), 0, np.sin(yaw)], [0, 1, 0], [-np.sin(yaw), 0, np.cos(yaw)]])
+    pose[:3, 3] = rng.uniform(-1, 1, 3)
+    depth = None
+    if with_depth:
+        depth = rng.integers(0, 6000, (240, 320)).astype(np.uint16) / 1000.0
+    state = np.random.get_state()                          # getMapping reseeds numpy / torch as a side effect
+    ref = R.getMapping().compute_mapping(pose, xyz, depth)
+    np.random.set_state(state)
+    got = ref_port.getMapping().compute_mapping(pose, xyz, depth)
+    assert got.dtype == ref.dtype and np.array_equal(got, ref)
+
+
+@settings(max_examples=20, deadline=None)
+@given(seed=st.integers(0, 2 ** 31 - 1), n=st.integers(1, 4000), voxel=st.sampled_from([0.02, 0.05, 0.25]))
+def test_voxelize_and_quantize_live(R, seed, n, voxel):
+    """dataset/voxelizer.py:81-132 (same np.random state) and dataset/voxelization_utils.py:6-102."""
+    from tests.golden.make_golden_params import vox_kwargs
+    rng = np.random.default_rng(seed)
+    xyz = rng.uniform(-3, 3, (n, 3)).astype(np.float32)
+    colors = rng.uniform(-1, 1, (n, 3)).astype(np.float32)
+    labels = rng.integers(0, 20, n).astype(np.float64)
+    outs = []
+    for V in (R.Voxelizer, ref_port.Voxelizer):
+        np.random.seed(seed % (2 ** 31))
+        outs.append(V(**vox_kwargs(voxel)).voxelize(xyz, colors.copy(), labels.copy(), return_ind=True))
+    for a, b in zip(*outs):
+        assert np.asarray(a).dtype == np.asarray(b).dtype and np.array_equal(a, b)
+    grid = np.floor(rng.uniform(0, 30, (n, 3)))
+    assert np.array_equal(ref_port.fnv_hash_vec(grid), R.fnv_hash_vec(grid))
+    assert np.array_equal(ref_port.ravel_hash_vec(grid.copy() - 7.0), R.ravel_hash_vec(grid.copy() - 7.0))
+    lab = rng.integers(0, 5, n)
+    for kw in (dict(return_index=True), dict(labels=lab, return_index=True, set_ignore_label_when_collision=True),
+               dict(return_index=True, hash_type="ravel"), dict(feats=colors), dict(quantization_size=0.5)):
+        a = R.sparse_quantize(grid.copy(), **{k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in kw.items()})
+        b = ref_port.sparse_quantize(grid.copy(), **{k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in kw.items()})
+        a, b = (a if isinstance(a, tuple) else (a,)), (b if isinstance(b, tuple) else (b,))
+        assert len(a) == len(b) and all(np.array_equal(x, y) for x, y in zip(a, b)), kw
+
+
+@settings(max_examples=15, deadline=None)
+@given(seed=st.integers(0, 2 ** 31 - 1), b=st.integers(1, 3), k=st.integers(1, 30), t=st.integers(2, 40))
+def test_cal_pred_logits_live(R, seed, b, k, t):
+    """models/xmask3d.py:129-143 — the reference's own method (self is unused)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    outputs = {"mask_embed": torch.randn(b, k, 48, generator=g), "text_embed": torch.randn(t - 1, 48, generator=g),
+               "null_embed": torch.randn(1, 48, generator=g), "labels": [[str(i)] for i in range(t - 1)],
+               "logit_scale": torch.tensor(1 / 0.07)}
+    ref = R.XMASK3d.cal_pred_logits(None, dict(outputs))
+    got = ref_port.cal_pred_logits(dict(outputs))
+    assert torch.equal(got, ref)
