@@ -82,3 +82,32 @@ def test_cal_pred_logits_live(R, seed, b, k, t):
     ref = R.XMASK3d.cal_pred_logits(None, dict(outputs))
     got = ref_port.cal_pred_logits(dict(outputs))
     assert torch.equal(got, ref)
+
+
+@settings(max_examples=15, deadline=None)
+@given(seed=st.integers(0, 2 ** 31 - 1), n=st.integers(1, 400), k=st.integers(1, 12), density=st.sampled_from([0.0, 0.1, 0.6]))
+def test_mask_mapper_live(R, seed, n, k, density):
+    """models/utils/fuser.py:6-53 run on CPU tensors with identity fc layers and an additive fuser: its
+    mask -> point scatter-mean (output_2d, since fc2 is the identity) equals the port's bit for bit, and the
+    fused output follows from it."""
+    import types
+
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    h, w, c = 24, 32, 8
+    masks = (torch.rand(k, h, w, generator=g) < density).float()
+    x = torch.randint(0, h, (n,), generator=g)
+    y = torch.randint(0, w, (n,), generator=g)
+    emb = torch.randn(k, c, generator=g)
+    pred = torch.randn(n, c, generator=g)
+    ident = torch.nn.Identity()
+    fuse = lambda a, b: a + b                                # noqa: E731
+    cfg = types.SimpleNamespace(caption_contra_2d_pre=True)
+    out, out2d, out3d, pre = R.mask_mapper([x], [y], [masks], [emb], [pred], fuse, ident, ident, cfg)
+    member = ref_port.gather_masks(masks, x, y, "ge0.5")
+    feat2d, counter = ref_port.scatter_mask_embed(member, emb, torch.zeros(n, c))
+    assert torch.equal(out2d[0], feat2d) and torch.equal(out3d[0], pred)
+    covered = counter[:, 0] >= 1
+    want = pred.clone()
+    want[covered] = feat2d[covered] + pred[covered]
+    assert torch.equal(out[0], want) and torch.equal(pre[0], feat2d[covered])
