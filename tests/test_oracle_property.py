@@ -19,7 +19,7 @@ def _pose(rng):
     return pose
 
 
-@settings(max_examples=60, deadline=None)
+@settings(max_examples=60, deadline=None, derandomize=True)
 @given(seed=st.integers(0, 2 ** 31 - 1), n=st.integers(1, 3000), with_depth=st.booleans(), small_depth=st.booleans())
 def test_projection_c_oracle_equals_numpy_port(cport, seed, n, with_depth, small_depth):
     rng = np.random.default_rng(seed)
@@ -41,7 +41,7 @@ def test_projection_c_oracle_equals_numpy_port(cport, seed, n, with_depth, small
         assert np.array_equal(got16, ref)
 
 
-@settings(max_examples=60, deadline=None)
+@settings(max_examples=60, deadline=None, derandomize=True)
 @given(seed=st.integers(0, 2 ** 31 - 1), n=st.integers(1, 4000), span=st.sampled_from([3, 40, 600]),
        voxel=st.sampled_from([0.02, 0.05, 0.2]))
 def test_voxelize_c_oracle_equals_numpy_port(cport, seed, n, span, voxel):
@@ -68,7 +68,7 @@ def test_voxelize_c_oracle_equals_numpy_port(cport, seed, n, span, voxel):
     assert np.array_equal(g, g_ref) and np.array_equal(first, inds_ref) and np.array_equal(inv, inv_ref)
 
 
-@settings(max_examples=40, deadline=None)
+@settings(max_examples=40, deadline=None, derandomize=True)
 @given(seed=st.integers(0, 2 ** 31 - 1), n=st.integers(1, 600), k=st.integers(1, 40), c=st.sampled_from([1, 7, 64]),
        density=st.sampled_from([0.0, 0.05, 0.5]))
 def test_scatter_and_pool_c_oracle_equals_torch_port(cport, seed, n, k, c, density):

@@ -23,7 +23,7 @@ def R():
     return refimport.load()
 
 
-@settings(max_examples=20, deadline=None)
+@settings(max_examples=20, deadline=None, derandomize=True)
 @given(seed=st.integers(0, 2 ** 31 - 1), n=st.integers(1, 3000), with_depth=st.booleans())
 def test_compute_mapping_live(R, seed, n, with_depth):
     """models/utils/fusion_util.py:46-142 through models/utils/mapping_util.py:getMapping."""
@@ -43,7 +43,7 @@ def test_compute_mapping_live(R, seed, n, with_depth):
     assert got.dtype == ref.dtype and np.array_equal(got, ref)
 
 
-@settings(max_examples=20, deadline=None)
+@settings(max_examples=20, deadline=None, derandomize=True)
 @given(seed=st.integers(0, 2 ** 31 - 1), n=st.integers(1, 4000), voxel=st.sampled_from([0.02, 0.05, 0.25]))
 def test_voxelize_and_quantize_live(R, seed, n, voxel):
     """dataset/voxelizer.py:81-132 (same np.random state) and dataset/voxelization_utils.py:6-102."""
@@ -70,7 +70,7 @@ def test_voxelize_and_quantize_live(R, seed, n, voxel):
         assert len(a) == len(b) and all(np.array_equal(x, y) for x, y in zip(a, b)), kw
 
 
-@settings(max_examples=15, deadline=None)
+@settings(max_examples=15, deadline=None, derandomize=True)
 @given(seed=st.integers(0, 2 ** 31 - 1), b=st.integers(1, 3), k=st.integers(1, 30), t=st.integers(2, 40))
 def test_cal_pred_logits_live(R, seed, b, k, t):
     """models/xmask3d.py:129-143 — the reference's own method (self is unused)."""
@@ -84,7 +84,7 @@ def test_cal_pred_logits_live(R, seed, b, k, t):
     assert torch.equal(got, ref)
 
 
-@settings(max_examples=15, deadline=None)
+@settings(max_examples=15, deadline=None, derandomize=True)
 @given(seed=st.integers(0, 2 ** 31 - 1), n=st.integers(1, 400), k=st.integers(1, 12), density=st.sampled_from([0.0, 0.1, 0.6]))
 def test_mask_mapper_live(R, seed, n, k, density):
     """models/utils/fuser.py:6-53 run on CPU tensors with identity fc layers and an additive fuser: its
