@@ -48,6 +48,7 @@ def parse():
     p.add_argument("--voxel", type=float, default=0.02)
     p.add_argument("--masks", default="partition", choices=["partition", "overlap"])
     p.add_argument("--cpu-views", type=int, default=12, help="views of scene 0 timed by the CPU baseline")
+    p.add_argument("--cpu-procs", type=int, default=0, help="processes of the reference arm (0 = one per host cpu)")
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--no-e2e-all", action="store_true")
     p.add_argument("--e2e-slots", type=int, default=3, help="staging slots of the pipelined end-to-end loop")
@@ -198,31 +199,59 @@ def cpu_masks(args, n_views: int, seed: int):
     return [syn.make_partition_masks(seed + v, args.k) for v in range(n_views)]
 
 
+_CPU_CTX = None      # (args, scene, views, masks): inherited by the forked workers of the reference arm
+
+
+def _cpu_worker_init():
+    import torch
+    torch.set_num_threads(1)             # one view per process, like the reference's DataLoader workers
+
+
+def _cpu_one_view(v):
+    args, sc, views, masks = _CPU_CTX
+    t, pv = cpu_reference_pass(args, sc, [views[v]], 5557 + v, args.k, args.c, [masks[v]], 1)
+    return pv
+
+
 def run_reference(args, rank: int, world: int):
+    """The reference's CPU implementation of the path on the host cores: the views of a step are spread over
+    a process pool (one view per process at a time, torch threads 1 — the reference parallelises this stage
+    with DataLoader workers, `workers: 4` in its yaml; here every host cpu gets one), wall clock per step."""
+    global _CPU_CTX
     if rank != 0:
         return
+    import multiprocessing as mp
+
     import torch
     from xmask3d_b200 import synthetic as syn
     sc = syn.make_scene(1000, args.points)
-    nv = max(1, min(args.cpu_views, 4))
+    procs = max(1, min(os.cpu_count() or 1, args.cpu_procs if args.cpu_procs > 0 else (os.cpu_count() or 1)))
+    nv = max(1, min(args.cpu_views, max(4, procs)))
     views = [syn.make_view(sc, v) for v in range(nv)]
     masks = cpu_masks(args, nv, 9000)
-    for _ in range(args.warmup):
-        cpu_reference_pass(args, sc, views, 5557, args.k, args.c, masks, 1)
+    # single process, library threading only (what one DataLoader worker does)
+    cpu_reference_pass(args, sc, views, 5557, args.k, args.c, masks, 1)
+    t1, pv1 = cpu_reference_pass(args, sc, views, 5557, args.k, args.c, masks, min(nv, 4))
+    single = pv1 / t1
+    _CPU_CTX = (args, sc, views, masks)
     tot_t, tot_pv = 0.0, 0
-    for _ in range(args.steps):
-        t, pv = cpu_reference_pass(args, sc, views, 5557, args.k, args.c, masks, nv)
-        tot_t += t
-        tot_pv += pv
+    with mp.get_context("fork").Pool(procs, initializer=_cpu_worker_init) as pool:
+        for _ in range(max(args.warmup, 1)):
+            pool.map(_cpu_one_view, range(nv))
+        for _ in range(args.steps):
+            t0 = time.perf_counter()
+            pvs = pool.map(_cpu_one_view, range(nv))
+            tot_t += time.perf_counter() - t0
+            tot_pv += sum(pvs)
     val = tot_pv / tot_t
-    cores = torch.get_num_threads()
     line = {"metric": METRIC, "value": val, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(args.steps, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64/f32", "data": "synthetic",
             "config": {"workload": workload_name(args), "sample": f"scene 0 x {nv} views per step"},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{args.steps} x (scene 0, {nv} views): numpy/torch-CPU port of the reference "
-                                       f"path, {os.cpu_count()} host cpus, torch threads {cores}"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": procs, "kind": "port",
+                             "sample": f"{args.steps} x (scene 0, {nv} views over {procs} processes): numpy/torch-CPU port of "
+                                       f"the reference path, {os.cpu_count()} host cpus",
+                             "single_process_value": single, "single_process_threads": torch.get_num_threads()},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
