@@ -190,16 +190,24 @@ XM3D_API int xm3d_pixel_bits_batch(const void *masks, int32_t mask_kind, int32_t
  *   member    as produced by xm3d_gather_masks_batch (general, overlapping masks) OR
  *   label     int32 [cap], values outside [0,k) = in no mask (partition masks); exactly one of the two
  *   cap_pairs bounds the total number of (point, mask) memberships (= cap for labels / partition
- *   masks); beyond it XM3D_FLAG_PAIR_OVERFLOW is raised and the sums are zero.  cap_pairs > cap + 1 also
- *   tells the library that masks may overlap: with member words, c % 128 == 0 and k <= 96 it then runs the
- *   point-major kernel, which reads every row once and has no pair list (cap_pairs is not a limit there).
+ *   masks); beyond it XM3D_FLAG_PAIR_OVERFLOW is raised and the sums are zero (pair-list path only).
+ *   path      XM3D_POOL_AUTO picks the kernel: partition masks / labels -> sorted pair lists + register
+ *             accumulation (every row read once, HBM peak); cap_pairs > cap + 1 tells the library that masks may
+ *             overlap -> every row is still read exactly once by the TENSOR-CORE kernel (tcgen05 tf32, member bits
+ *             as a 0/1 operand; needs member words, no row_index, c % 128 == 0, k <= 128, finite features), else by
+ *             the point-major CUDA-core kernel (c % 128 == 0, k <= 96), else by the pair lists (one row read per
+ *             membership).  XM3D_POOL_PAIR_LISTS / _ROWS / _MMA force one path (XM3D_ERR_UNSUPPORTED if not eligible).
  *   sum [n_seg,k,c] float32, cnt [n_seg,k] int32 (optional), mean (optional) [n_seg,k,c] = sum/cnt
  *   (0 where cnt = 0).  Deterministic: every summation order is fixed by the point order. */
+#define XM3D_POOL_AUTO 0
+#define XM3D_POOL_PAIR_LISTS 1
+#define XM3D_POOL_ROWS 2
+#define XM3D_POOL_MMA 3
 XM3D_API size_t xm3d_pool_ws_bytes(int32_t n_seg, int32_t k, int32_t c, int64_t cap, int64_t cap_pairs);
 XM3D_API int xm3d_pool_batch(const float *feat, int32_t c, const int32_t *row_index, const uint32_t *member,
                     const int32_t *label, int32_t n_seg, int32_t k, const int64_t *seg_off, int64_t cap,
-                    int64_t cap_pairs, float *sum, int32_t *cnt, float *mean, void *ws, size_t ws_bytes,
-                    int32_t *status, xm3d_stream_t stream);
+                    int64_t cap_pairs, int32_t path, float *sum, int32_t *cnt, float *mean, void *ws,
+                    size_t ws_bytes, int32_t *status, xm3d_stream_t stream);
 
 /* Mask -> point scatter-mean (mask_mapper, models/utils/fuser.py:22-34; twin
  * models/xmask3d.py:441-455): out[i,:] = (sum of emb[m,:] over masks m containing i, ascending m)

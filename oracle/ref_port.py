@@ -302,6 +302,27 @@ def scatter_mask_embed(member, mask_embed, n_rows_like):
     return acc / counter, counter
 
 
+def mask_mapper_ref(x_list, y_list, masks, mask_embeds, pred_3ds, fuser, fc1, fc2, caption_contra_2d_pre=True):
+    """models/utils/fuser.py:6-53 over the caller's per-scene lists (ragged K, bool or float masks —
+    models/utils/criterion.py:262-340 passes K' kept bool masks or K float zero masks): gather + `>= 0.5`,
+    the `[0][0] = True` guard, scatter-mean, fusion of covered rows.  CPU torch tensors."""
+    import torch
+    output, output_2d, output_3d, output_2d_pre = [], [], [], []
+    for x_label, y_label, mask, mask_embed, pred_3d in zip(x_list, y_list, masks, mask_embeds, pred_3ds):
+        member = gather_masks(mask, x_label, y_label, "ge0.5")
+        feat2d, counter = scatter_mask_embed(member, mask_embed, pred_3d)
+        covered = torch.sum(counter, dim=1) >= 1
+        final = torch.zeros_like(pred_3d)
+        final[covered] = fuser(feat2d[covered], pred_3d[covered])
+        final[~covered] = pred_3d[~covered]
+        output.append(final)
+        output_2d.append(fc2(feat2d))
+        output_3d.append(fc1(pred_3d))
+        if caption_contra_2d_pre:
+            output_2d_pre.append(feat2d[covered])
+    return output, output_2d, output_3d, output_2d_pre
+
+
 def masked_mean_pool(feat, member):
     """models/utils/criterion.py:152-157: per mask `feat[member_k].mean(0)`.
     feat torch [n,C] f32, member bool [K,n] -> (mean [K,C] f32, cnt [K] int64).

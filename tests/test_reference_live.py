@@ -111,3 +111,34 @@ def test_mask_mapper_live(R, seed, n, k, density):
     want = pred.clone()
     want[covered] = feat2d[covered] + pred[covered]
     assert torch.equal(out[0], want) and torch.equal(pre[0], feat2d[covered])
+
+
+@settings(max_examples=10, deadline=None, derandomize=True)
+@given(seed=st.integers(0, 2 ** 31 - 1), ks=st.lists(st.integers(1, 9), min_size=2, max_size=4))
+def test_mask_mapper_ragged_lists_live(R, seed, ks):
+    """The caller's real input (criterion.py:262-340): per-scene lists with DIFFERENT numbers of masks, bool
+    partition masks for some scenes and float32 zero masks for others — reference vs the port's restatement."""
+    import types
+
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    h, w, c = 24, 32, 8
+    xs, ys, masks, embs, preds = [], [], [], [], []
+    for i, k in enumerate(ks):
+        n = int(torch.randint(1, 300, (1,), generator=g))
+        xs.append(torch.randint(0, h, (n,), generator=g))
+        ys.append(torch.randint(0, w, (n,), generator=g))
+        if i % 3 == 2:
+            masks.append(torch.zeros(k, h, w))                                   # "nothing kept": float zeros
+        else:
+            lab = torch.randint(0, k + 1, (h, w), generator=g)                   # partition, label k = background
+            masks.append(lab.unsqueeze(0) == torch.arange(k).view(k, 1, 1))      # bool
+        embs.append(torch.randn(k, c, generator=g))
+        preds.append(torch.randn(n, c, generator=g))
+    ident = torch.nn.Identity()
+    fuse = lambda a, b: a * 0.5 + b                          # noqa: E731
+    cfg = types.SimpleNamespace(caption_contra_2d_pre=True)
+    ref = R.mask_mapper(xs, ys, masks, embs, preds, fuse, ident, ident, cfg)
+    got = ref_port.mask_mapper_ref(xs, ys, masks, embs, preds, fuse, ident, ident, True)
+    for a, b in zip(ref, got):
+        assert len(a) == len(b) and all(torch.equal(u, v) for u, v in zip(a, b))

@@ -19,6 +19,7 @@ FLAG_VIS_OVERFLOW, FLAG_PAIR_OVERFLOW, FLAG_GRID_RANGE, FLAG_KEY_SENTINEL = 1, 2
 DEPTH_NONE, DEPTH_U16, DEPTH_F64 = 0, 1, 2
 THR_GE_HALF, THR_SIGMOID_GE_HALF, THR_SIGMOID_GT_HALF = 0, 1, 2
 MASK_U8, MASK_F32 = 0, 1
+POOL_AUTO, POOL_PAIR_LISTS, POOL_ROWS, POOL_MMA = 0, 1, 2, 3
 
 
 class View(C.Structure):
@@ -57,7 +58,7 @@ PROTOTYPES = {
     "xm3d_gather_masks_batch": (C.c_int, [_P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _I64, _P, _P, _P, _SZ, _P]),
     "xm3d_pixel_bits_batch": (C.c_int, [_P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P]),
     "xm3d_pool_ws_bytes": (_SZ, [_I32, _I32, _I32, _I64, _I64]),
-    "xm3d_pool_batch": (C.c_int, [_P, _I32, _P, _P, _P, _I32, _I32, _P, _I64, _I64, _P, _P, _P, _P, _SZ, _P, _P]),
+    "xm3d_pool_batch": (C.c_int, [_P, _I32, _P, _P, _P, _I32, _I32, _P, _I64, _I64, _I32, _P, _P, _P, _P, _SZ, _P, _P]),
     "xm3d_scatter_batch": (C.c_int, [_P, _P, _I32, _I32, _P, _I64, _P, _I32, _P, _P, _P]),
     "xm3d_point_logits_ws_bytes": (_SZ, [_I32, _I32]),
     "xm3d_point_logits": (C.c_int, [_P, _I64, _I32, _P, _I32, _F32, _P, _P, _P, _P, _P, _SZ, _P]),

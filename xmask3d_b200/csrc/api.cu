@@ -28,17 +28,33 @@ int check_launch(const char *what) {
     return XM3D_ERR_CUDA;
 }
 
+static int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return dev;
+}
+
 int sm_count() {
-    static int cached = 0;
-    if (cached) return cached;
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+    static std::atomic<int> cached[64];
+    const int dev = current_device();
+    if (dev >= 0 && dev < 64) {
+        const int c = cached[dev].load(std::memory_order_relaxed);
+        if (c) return c;
+    }
+    int n = 0;
+    if (dev < 0 || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
         cudaGetLastError();
         return 148;          // B200; used only to size workspaces when no device is visible
     }
-    cached = n;
+    if (dev < 64) cached[dev].store(n, std::memory_order_relaxed);
     return n;
+}
+
+bool first_use_on_device(std::atomic<uint64_t> *flag) {
+    const int dev = current_device();
+    if (dev < 0 || dev >= 64) return true;                     // unknown device: redo the (idempotent) setup
+    const uint64_t bit = 1ull << dev;
+    return (flag->fetch_or(bit, std::memory_order_acq_rel) & bit) == 0;
 }
 
 }  // namespace xm3d

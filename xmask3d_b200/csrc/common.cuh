@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/xm3d.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -15,7 +17,11 @@ namespace xm3d {
 void set_error(const char *fmt, ...);
 int check_launch(const char *what);  // cudaGetLastError -> XM3D_OK / XM3D_ERR_CUDA
 void count_launches(int n);          // bookkeeping for xm3d_launch_count()
-int sm_count();
+int sm_count();                      // of the CURRENT device (cached per device)
+// One-time per-device setup (cudaFuncSetAttribute and the like): true exactly once per (flag, current device),
+// thread-safe.  Kernel attributes are per device, so a process-wide `static bool` would be wrong for a process
+// that drives two GPUs.
+bool first_use_on_device(std::atomic<uint64_t> *flag);
 extern thread_local cudaEvent_t g_pool_ev[2];   // optional timing hook (xm3d_set_pool_events)
 
 #define XM3D_REQUIRE(cond, msg)                      \

@@ -19,6 +19,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "tc.cuh"
 
 namespace xm3d {
 
@@ -50,43 +51,6 @@ logits_prep_kernel(const float *__restrict__ a, const float *__restrict__ b, int
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     // F.normalize: x / max(||x||_2, 1e-12)
     if (lane == 0) inv_norm[row] = __fdiv_rn(1.0f, fmaxf(sqrtf(ss), 1e-12f));
-}
-
-// ---- tcgen05 / TMA wrappers -----------------------------------------------------------------
-__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int x, int y, uint64_t *bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
-}
-__device__ __forceinline__ uint64_t make_sw128_desc(const void *smem_ptr) {
-    // K-major, 128-byte swizzle: 8-row atoms of 128 B, stride between atoms 1024 B, version 1 (sm_100)
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_u32(smem_ptr) & 0x3ffff) >> 4);        // start address, bits [0,14)
-    d |= (uint64_t)0 << 16;                                       // leading byte offset (unused: 1 atom in K)
-    d |= (uint64_t)(1024 >> 4) << 32;                             // stride byte offset, bits [32,46)
-    d |= (uint64_t)1 << 46;                                       // descriptor version
-    d |= (uint64_t)2 << 61;                                       // SWIZZLE_128B
-    return d;
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-                 ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
 struct LogitsParams {
@@ -256,16 +220,19 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-static bool make_map(CUtensorMap *m, const float *base, int64_t rows, int c, int box_rows) {
+bool make_map_sw128(CUtensorMap *m, const float *base, int64_t rows, int c, int box_cols, int box_rows, bool atom32) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
     const cuuint64_t dims[2] = {(cuuint64_t)c, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)c * 4};
-    const cuuint32_t box[2] = {(cuuint32_t)LG_BK, (cuuint32_t)box_rows};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+              CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+static bool make_map(CUtensorMap *m, const float *base, int64_t rows, int c, int box_rows) {
+    return make_map_sw128(m, base, rows, c, LG_BK, box_rows);
 }
 
 // Plain (unswizzled) row-tile map over a row-major float32 matrix: box = box_cols x box_rows (used by the
@@ -330,10 +297,6 @@ struct PointLogitsParams {
     float *out;                  // [rows, n_text] or null
     int *argmax;                 // [rows] or null
 };
-
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 
 __global__ void __launch_bounds__(PL_THREADS, 2)
 point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b_hi,
@@ -591,10 +554,9 @@ extern "C" int xm3d_logits(const float *mask_embed, int64_t rows, int32_t c, con
         return XM3D_ERR_CUDA;
     }
     const size_t smem = stage_bytes * stages + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::atomic<uint64_t> attr_set{0};
+    if (first_use_on_device(&attr_set)) {
         cudaFuncSetAttribute(logits_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
-        attr_set = true;
     }
     logits_mma_kernel<<<(unsigned)((rows + LG_BM - 1) / LG_BM), LG_THREADS, smem, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, P); count_launches(1);
     return check_launch("xm3d_logits");
@@ -634,7 +596,7 @@ extern "C" int xm3d_point_logits(const float *feat, int64_t rows, int32_t c, con
     PointLogitsParams P;
     P.rows = rows; P.c = c; P.n_text = n_text; P.bn = (n_text + 15) / 16 * 16; P.scale = logit_scale;
     P.inv_norm_b = inv_b; P.binary = binary; P.is_base = is_base; P.out = out; P.argmax = argmax;
-    P.fused = (2 * P.bn <= 256 && !getenv("XM3D_PL_NO_FUSE")) ? 1 : 0;
+    P.fused = (2 * P.bn <= 256) ? 1 : 0;
     int tc = 32;
     while (tc < (P.fused ? 2 * P.bn : P.bn)) tc <<= 1;
     P.tmem_cols = tc;
@@ -644,10 +606,6 @@ extern "C" int xm3d_point_logits(const float *feat, int64_t rows, int32_t c, con
     int stages = (int)((108 * 1024) / stage_bytes);
     if (stages < 2) stages = (int)((220 * 1024) / stage_bytes);
     if (stages > 4) stages = 4;
-    if (const char *e = getenv("XM3D_PL_STAGES")) {          // A/B experiments: force the ring depth
-        const int f = atoi(e);
-        if (f >= 1 && f <= PL_MAX_STAGES && (size_t)f * stage_bytes + 1024 <= 224 * 1024) stages = f;
-    }
     if (stages < 1) { set_error("xm3d_point_logits: tile does not fit shared memory"); return XM3D_ERR_UNSUPPORTED; }
     P.stages = stages;
     CUtensorMap ma, mbh, mbl;
@@ -656,10 +614,9 @@ extern "C" int xm3d_point_logits(const float *feat, int64_t rows, int32_t c, con
         set_error("xm3d_point_logits: cuTensorMapEncodeTiled failed");
         return XM3D_ERR_CUDA;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::atomic<uint64_t> attr_set{0};
+    if (first_use_on_device(&attr_set)) {
         cudaFuncSetAttribute(point_logits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
-        attr_set = true;
     }
     point_logits_kernel<<<(unsigned)((rows + LG_BM - 1) / LG_BM), PL_THREADS, stage_bytes * stages + 1024, stream>>>(ma, mbh,
                                                                                                                  mbl, P);

@@ -433,6 +433,11 @@ pool_combine_kernel(const float *__restrict__ partial, const int32_t *__restrict
 // mask's accumulator row in shared memory.  No pair list, no partial rows in HBM, no combine pass;
 // the order of every sum is fixed (tiles ascending, points ascending), so the result is deterministic.
 bool make_row_tile_map(CUtensorMap *m, const float *base, int64_t rows, int c, int box_cols, int box_rows);   // logits.cu
+// tensor-core variant (pool_mma.cu)
+bool pool_mma_eligible(const float *feat, int c, const int32_t *row_index, const uint32_t *member, int k, int64_t cap,
+                       const float *sum, const float *mean);
+int launch_pool_mma(const float *feat, int c, const uint32_t *member, int words, int n_seg, int k, const int64_t *seg_off,
+                    int64_t cap, float *sum, int32_t *cnt, float *mean, int *work, cudaStream_t stream);
 
 constexpr int PR_THREADS = 512;
 constexpr int PR_WARPS = PR_THREADS / 32;
@@ -635,8 +640,8 @@ extern "C" size_t xm3d_pool_ws_bytes(int32_t n_seg, int32_t k, int32_t c, int64_
 
 extern "C" int xm3d_pool_batch(const float *feat, int32_t c, const int32_t *row_index, const uint32_t *member,
                                const int32_t *label, int32_t n_seg, int32_t k, const int64_t *seg_off, int64_t cap,
-                               int64_t cap_pairs, float *sum, int32_t *cnt, float *mean, void *ws, size_t ws_bytes,
-                               int32_t *status, xm3d_stream_t stream_) {
+                               int64_t cap_pairs, int32_t path, float *sum, int32_t *cnt, float *mean, void *ws,
+                               size_t ws_bytes, int32_t *status, xm3d_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     XM3D_REQUIRE(n_seg > 0 && k > 0 && c > 0 && cap >= 0 && cap_pairs >= 0, "bad sizes");
     XM3D_REQUIRE(k <= 32 * MAX_WORDS, "at most 256 masks per segment");
@@ -655,17 +660,29 @@ extern "C" int xm3d_pool_batch(const float *feat, int32_t c, const int32_t *row_
     I.member = member; I.label = label; I.row_index = row_index; I.seg_off = seg_off; I.n_seg = n_seg; I.k = k;
     I.words = words_for(k); I.cap = cap;
     const int n_units = n_seg * k;
-    // Overlapping masks (the caller's bound allows more memberships than points): point-major kernel, every
-    // row read once.  cap_pairs is not a limit on this path (there is no pair list to overrun).
+    // Overlapping masks (the caller's bound allows more memberships than points): every row is read once, by the
+    // tensor-core kernel (pool_mma.cu) or the point-major CUDA-core kernel.  cap_pairs is not a limit on these
+    // paths (there is no pair list to overrun).
+    XM3D_REQUIRE(path >= XM3D_POOL_AUTO && path <= XM3D_POOL_MMA, "unknown pooling path");
     const bool out16 = reinterpret_cast<uintptr_t>(sum) % 16 == 0 && (!mean || reinterpret_cast<uintptr_t>(mean) % 16 == 0);
-    if (member && (cap_pairs > cap + 1 || getenv("XM3D_POOL_ROWS")) && vec == 4 && c % PR_SLICE == 0 && k <= PR_KMAX && out16 && !getenv("XM3D_POOL_PAIR_LISTS")) {
+    const bool overlap = member && cap_pairs > cap + 1;
+    const bool mma_ok = pool_mma_eligible(feat, c, row_index, member, k, cap, sum, mean);
+    const bool rows_ok = member && vec == 4 && c % PR_SLICE == 0 && k <= PR_KMAX && out16;
+    if (path == XM3D_POOL_MMA && !mma_ok) { set_error("xm3d_pool_batch: tensor-core path not eligible"); return XM3D_ERR_UNSUPPORTED; }
+    if (path == XM3D_POOL_ROWS && !rows_ok) { set_error("xm3d_pool_batch: point-major path not eligible"); return XM3D_ERR_UNSUPPORTED; }
+    if (path == XM3D_POOL_MMA || (path == XM3D_POOL_AUTO && overlap && mma_ok)) {
+        if (g_pool_ev[0]) cudaEventRecord(g_pool_ev[0], stream);
+        const int rc = launch_pool_mma(feat, c, member, I.words, n_seg, k, seg_off, cap, sum, cnt, mean, w.work, stream);
+        if (g_pool_ev[1]) cudaEventRecord(g_pool_ev[1], stream);
+        return rc;
+    }
+    if (path == XM3D_POOL_ROWS || (path == XM3D_POOL_AUTO && overlap && rows_ok)) {
         const size_t smem = pool_rows_smem(k);
-        static bool attr_set = false;
-        if (!attr_set) {
+        static std::atomic<uint64_t> attr_set{0};
+        if (first_use_on_device(&attr_set)) {
             cudaFuncSetAttribute(pool_rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
             cudaFuncSetAttribute(pool_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
             cudaFuncSetAttribute(pool_rows_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
-            attr_set = true;
         }
         cudaMemsetAsync(w.work, 0, sizeof(int), stream);
         const int n_items = n_seg * (c / PR_SLICE);

@@ -1,0 +1,336 @@
+// Stage 3, overlapping masks — segmented pooling on the tensor cores.
+//
+// Replaces the per-mask `feature[mask_3d[k]]` -> mean(0) loop of the reference for its RAW thresholded
+// predictions (models/utils/criterion.py:83-85, 148-157), where a point belongs to several masks (7.7 on
+// average in the synthetic overlap variant).  The pooled sums are a contraction over the points,
+//
+//     sum[k, c] = sum_p member[k, p] * F[p, c]          member in {0, 1},
+//
+// and run here as tcgen05.mma kind::tf32 with the accumulator in tensor memory:
+//   D[M = 128 channels, N = masks (64 / 128)] += A[128 channels, 8 points] * B[8 points, N masks]
+//   A = the feature tile exactly as it lies in HBM (row = point, 128 bytes = 32 channels): an MN-MAJOR operand,
+//       brought in by TMA with the 128-byte swizzle of 32-byte atoms — the one layout tcgen05 accepts for MN-major
+//       32-bit operands (four 32-channel column blocks x 64 points = 32 KB per tile);
+//       the tensor core ignores the 13 low mantissa bits of a tf32 operand, so the raw tile IS its hi part;
+//       converter warps write lo = x - hi as a second tile (elementwise, same swizzled layout) -> two MMAs per
+//       k-step reproduce the float32 products to 2^-22 relative;
+//   B = the membership bits of the tile's 64 points expanded to 0.0f / 1.0f (exact in tf32), K-major, built by
+//       four builder warps straight into the swizzled layout.
+// Every 64-point tile starts a FRESH accumulator (two TMEM buffers alternate); the epilogue warps add the tile's
+// result to float32 register accumulators with round-to-nearest adds, so no long accumulation chain runs inside
+// the tensor core (whose fp32 accumulation truncates) and the result is deterministic.
+// A work item is (segment, 128-channel slice), handed to one persistent CTA per SM through an atomic counter;
+// every feature row is read from HBM exactly once, independent of the number of memberships.
+//
+// Warp roles: 0 TMA producer | 1 TMEM allocator + MMA issuer | 2-5 converters | 6-9 builders | 10.. epilogue.
+// Restriction (documented in include/xm3d.h): features must be finite — a NaN / Inf row would reach, multiplied by
+// 0, the masks of its tile it does not belong to.
+#include <cuda.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "tc.cuh"
+#include "vec.cuh"
+
+namespace xm3d {
+
+constexpr int PM_TP = 64;                            // points per tile = 8 k-steps of 8 (tf32)
+constexpr int PM_SLICE = 128;                        // channels per work item = UMMA M
+constexpr int PM_RAW = PM_TP * PM_SLICE * 4;         // bytes of a raw / lo tile (32 KB)
+constexpr int PM_CB = PM_TP * 128;                   // bytes of one 32-channel column block (8 KB)
+constexpr int PM_CONV = 128, PM_BUILD = 128;         // converter / builder threads
+constexpr int PM_MAX_STAGES = 4;
+
+struct PoolMmaParams {
+    const uint32_t *member;      // [cap, words]
+    const int64_t *seg_off;      // [n_seg + 1]
+    int words, k, n_seg, c;
+    int64_t cap;
+    float *sum, *mean;           // [n_seg, k, c]
+    int32_t *cnt;                // [n_seg, k] or null
+    int *work;                   // item counter (zeroed by the host)
+    int raw_stages, conv_stages;
+};
+
+template <int N>
+__global__ void __launch_bounds__(32 * (10 + N / 16), 1)
+pool_mma_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P) {
+    constexpr int EPI_WARPS = N / 16;                // 64 accumulator columns per epilogue warp
+    constexpr int EPI_THREADS = EPI_WARPS * 32;
+    constexpr int THREADS = 32 * (10 + EPI_WARPS);
+    constexpr int B_BYTES = N * PM_TP * 4;           // [2 k-blocks of 32 points][N rows][128 B]
+    constexpr int WPT = N / 64;                      // membership words per builder thread
+    extern __shared__ __align__(1024) unsigned char pm_smem[];
+    __shared__ uint64_t s_raw_full[PM_MAX_STAGES], s_raw_empty[PM_MAX_STAGES];
+    __shared__ uint64_t s_conv_full[PM_MAX_STAGES], s_conv_empty[PM_MAX_STAGES];
+    __shared__ uint64_t s_tile_done[2], s_tmem_free[2];
+    __shared__ uint32_t s_tmem;
+    __shared__ int s_item;
+    __shared__ int s_cnt[N];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    unsigned char *base = pm_smem + ((1024u - (smem_u32(pm_smem) & 1023u)) & 1023u);
+    unsigned char *raw_base = base;
+    unsigned char *lo_base = raw_base + (size_t)P.raw_stages * PM_RAW;
+    unsigned char *b_base = lo_base + (size_t)P.conv_stages * PM_RAW;
+
+    if (tid == 0) {
+        for (int s = 0; s < PM_MAX_STAGES; ++s) {
+            mbar_init(&s_raw_full[s], 1);
+            mbar_init(&s_raw_empty[s], 1);
+            mbar_init(&s_conv_full[s], PM_CONV + PM_BUILD);
+            mbar_init(&s_conv_empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) { mbar_init(&s_tile_done[b], 1); mbar_init(&s_tmem_free[b], EPI_THREADS); }
+        mbar_fence_init();
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map));
+    }
+    if (warp == 1) {
+        __syncwarp();
+        tmem_alloc(&s_tmem, 2 * N);                 // two accumulator buffers of N columns (128 or 256: powers of two)
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s_tmem;
+
+    const int nsl = P.c / PM_SLICE;
+    const int n_items = P.n_seg * nsl;
+    const int64_t total_rows = P.seg_off[P.n_seg];
+    const bool over = total_rows > P.cap;
+
+    // ring positions persist across work items (the mbarrier phases keep running)
+    int rs = 0, cs = 0, buf = 0;
+    uint32_t rph = 0, cph = 0, bph = 0;             // phases of the raw ring, the lo / B ring, the TMEM buffers
+    if (tid < N) s_cnt[tid] = 0;
+    __syncthreads();
+
+    for (;;) {
+        if (tid == 0) s_item = atomicAdd(P.work, 1);
+        __syncthreads();
+        const int item = s_item;
+        if (item >= n_items) break;
+        const int s = item / nsl, sl = item - s * nsl;
+        const int64_t a = P.seg_off[s];
+        const int n = over ? 0 : (int)(P.seg_off[s + 1] - a);
+        const int ntile = (n + PM_TP - 1) / PM_TP;
+
+        if (warp == 0) {
+            // ===== TMA producer: four 32-channel column blocks of 64 points per tile =====
+            if (lane == 0) {
+                for (int t = 0; t < ntile; ++t) {
+                    mbar_wait(&s_raw_empty[rs], rph ^ 1);
+                    unsigned char *dst = raw_base + (size_t)rs * PM_RAW;
+                    mbar_expect_tx(&s_raw_full[rs], PM_RAW);
+                    const int y = (int)(a + (int64_t)t * PM_TP);
+#pragma unroll
+                    for (int cb = 0; cb < 4; ++cb)
+                        tma_load_2d(dst + cb * PM_CB, &map, sl * PM_SLICE + cb * 32, y, &s_raw_full[rs]);
+                    if (++rs == P.raw_stages) { rs = 0; rph ^= 1; }
+                }
+            }
+        } else if (warp == 1) {
+            // ===== MMA issuer =====
+            if (lane == 0) {
+                const uint32_t idesc = make_idesc(PM_SLICE, N, 2, /*A MN-major*/ 1, /*B K-major*/ 0);
+                for (int t = 0; t < ntile; ++t) {
+                    mbar_wait(&s_raw_full[rs], rph);
+                    mbar_wait(&s_conv_full[cs], cph);
+                    mbar_wait(&s_tmem_free[buf], bph ^ 1);
+                    tc_fence_after();
+                    const unsigned char *hi = raw_base + (size_t)rs * PM_RAW;
+                    const unsigned char *lo = lo_base + (size_t)cs * PM_RAW;
+                    const unsigned char *bt = b_base + (size_t)cs * B_BYTES;
+                    const uint32_t d = tmem_base + (uint32_t)(buf * N);
+#pragma unroll
+                    for (int ks = 0; ks < PM_TP / 8; ++ks) {
+                        // A: 8 points = two 512-byte atoms of 4 swizzled rows per column block; blocks 8 KB apart
+                        const uint64_t a_hi = make_sw128_desc_ex(hi + ks * 1024, PM_CB, 512, 1);
+                        const uint64_t a_lo = make_sw128_desc_ex(lo + ks * 1024, PM_CB, 512, 1);
+                        // B: [N rows][32 points] per k-block, 32 bytes per k-step inside the swizzle row
+                        const uint64_t bd = make_sw128_desc_ex(bt + (ks >> 2) * (N * 128) + (ks & 3) * 32, 0, 1024);
+                        umma_tf32(d, a_hi, bd, idesc, ks ? 1u : 0u);
+                        umma_tf32(d, a_lo, bd, idesc, 1u);
+                    }
+                    umma_commit(&s_raw_empty[rs]);
+                    umma_commit(&s_conv_empty[cs]);
+                    umma_commit(&s_tile_done[buf]);
+                    if (++rs == P.raw_stages) { rs = 0; rph ^= 1; }
+                    if (++cs == P.conv_stages) { cs = 0; cph ^= 1; }
+                    if (++buf == 2) { buf = 0; bph ^= 1; }
+                }
+            }
+        } else if (warp < 6) {
+            // ===== converters: lo = x - hi (hi = the raw tile as the tensor core reads it) =====
+            const int t0 = tid - 64;
+            for (int t = 0; t < ntile; ++t) {
+                mbar_wait(&s_raw_full[rs], rph);
+                mbar_wait(&s_conv_empty[cs], cph ^ 1);
+                uint4 *raw = reinterpret_cast<uint4 *>(raw_base + (size_t)rs * PM_RAW);
+                uint4 *lo = reinterpret_cast<uint4 *>(lo_base + (size_t)cs * PM_RAW);
+                const int rows_valid = min(PM_TP, n - t * PM_TP);
+#pragma unroll 4
+                for (int j = 0; j < PM_RAW / 16 / PM_CONV; ++j) {
+                    const int q = t0 + PM_CONV * j;                 // 16-byte chunk: [column block][row][8 chunks]
+                    const int row = (q >> 3) & (PM_TP - 1);
+                    if (row < rows_valid) {
+                        const uint4 v = raw[q];
+                        uint4 l;
+                        l.x = __float_as_uint(__fsub_rn(__uint_as_float(v.x), __uint_as_float(v.x & 0xffffe000u))) & 0xffffe000u;
+                        l.y = __float_as_uint(__fsub_rn(__uint_as_float(v.y), __uint_as_float(v.y & 0xffffe000u))) & 0xffffe000u;
+                        l.z = __float_as_uint(__fsub_rn(__uint_as_float(v.z), __uint_as_float(v.z & 0xffffe000u))) & 0xffffe000u;
+                        l.w = __float_as_uint(__fsub_rn(__uint_as_float(v.w), __uint_as_float(v.w & 0xffffe000u))) & 0xffffe000u;
+                        lo[q] = l;
+                    } else {
+                        // rows past the segment belong to the next one (or lie past the tensor): never let them in
+                        raw[q] = make_uint4(0u, 0u, 0u, 0u);
+                        lo[q] = make_uint4(0u, 0u, 0u, 0u);
+                    }
+                }
+                fence_proxy_async();
+                mbar_arrive(&s_conv_full[cs]);
+                if (++rs == P.raw_stages) { rs = 0; rph ^= 1; }
+                if (++cs == P.conv_stages) { cs = 0; cph ^= 1; }
+            }
+        } else if (warp < 10) {
+            // ===== builders: membership bits of the tile's points -> 0.0f / 1.0f, K-major swizzled =====
+            const int t0 = tid - 192;
+            const int p = t0 & (PM_TP - 1), h = t0 >> 6;          // point of the tile, word group of this thread
+            const int kb = p >> 5, kk = p & 31;
+            const int tail = P.k & 31;
+            int cntreg[WPT];
+#pragma unroll
+            for (int j = 0; j < WPT; ++j) cntreg[j] = 0;
+            for (int t = 0; t < ntile; ++t) {
+                uint32_t w[WPT];
+                const int pt = t * PM_TP + p;
+#pragma unroll
+                for (int j = 0; j < WPT; ++j) {
+                    const int wi = h * WPT + j;
+                    uint32_t x = 0u;
+                    if (pt < n && wi < P.words) {
+                        x = __ldg(P.member + (size_t)(a + pt) * P.words + wi);
+                        if (wi * 32 >= P.k) x = 0u;
+                        else if (tail && wi == (P.k >> 5)) x &= (1u << tail) - 1u;
+                    }
+                    w[j] = x;
+                }
+                mbar_wait(&s_conv_empty[cs], cph ^ 1);
+                unsigned char *bt = b_base + (size_t)cs * B_BYTES + kb * (N * 128) + ((kk & 3) << 2);
+#pragma unroll
+                for (int j = 0; j < WPT; ++j) {
+#pragma unroll
+                    for (int b = 0; b < 32; ++b) {
+                        const int m = (h * WPT + j) * 32 + b;
+                        const uint32_t val = ((w[j] >> b) & 1u) ? 0x3f800000u : 0u;
+                        *reinterpret_cast<uint32_t *>(bt + m * 128 + ((((kk >> 2) ^ (m & 7))) << 4)) = val;
+                        const uint32_t bal = __ballot_sync(0xffffffffu, (w[j] >> b) & 1u);
+                        if (lane == b) cntreg[j] += __popc(bal);
+                    }
+                }
+                fence_proxy_async();
+                mbar_arrive(&s_conv_full[cs]);
+                if (++cs == P.conv_stages) { cs = 0; cph ^= 1; }
+            }
+#pragma unroll
+            for (int j = 0; j < WPT; ++j) {
+                if (cntreg[j]) atomicAdd(&s_cnt[(h * WPT + j) * 32 + lane], cntreg[j]);     // integer: order independent
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(PM_BUILD + EPI_THREADS) : "memory");        // counts -> epilogue warps
+        } else {
+            // ===== epilogue: tile results out of TMEM, added in float32 registers =====
+            const int e = warp - 10;
+            const int lg = warp & 3;                              // TMEM lane group this warp may read
+            const int half = e >> 2;                              // which 64 accumulator columns
+            float acc[64];
+#pragma unroll
+            for (int j = 0; j < 64; ++j) acc[j] = 0.f;
+            for (int t = 0; t < ntile; ++t) {
+                mbar_wait(&s_tile_done[buf], bph);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * N + half * 64);
+#pragma unroll
+                for (int c0 = 0; c0 < 64; c0 += 32) {
+                    uint32_t v0[16], v1[16];
+                    tmem_ld16_nowait(taddr + c0, v0);
+                    tmem_ld16_nowait(taddr + c0 + 16, v1);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        acc[c0 + j] = __fadd_rn(acc[c0 + j], __uint_as_float(v0[j]));
+                        acc[c0 + 16 + j] = __fadd_rn(acc[c0 + 16 + j], __uint_as_float(v1[j]));
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&s_tmem_free[buf]);
+                if (++buf == 2) { buf = 0; bph ^= 1; }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(PM_BUILD + EPI_THREADS) : "memory");        // the builders' counts
+            const int ch = sl * PM_SLICE + lg * 32 + lane;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+                const int m = half * 64 + j;
+                if (m < P.k) {
+                    const size_t o = ((size_t)s * P.k + m) * P.c + ch;
+                    const int nm = s_cnt[m];
+                    P.sum[o] = acc[j];
+                    if (P.mean) P.mean[o] = nm > 0 ? __fdiv_rn(acc[j], (float)nm) : 0.f;
+                    if (P.cnt && sl == 0 && lg == 0 && lane == 0) P.cnt[s * P.k + m] = nm;
+                }
+            }
+        }
+        __syncthreads();                                          // item done: outputs written, s_cnt consumed
+        if (tid < N) s_cnt[tid] = 0;                              // (the next item's builders start after the sync above)
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        __syncwarp();
+        tmem_dealloc(tmem_base, 2 * N);
+    }
+    (void)THREADS;
+}
+
+// Host side -----------------------------------------------------------------------------------------
+bool pool_mma_eligible(const float *feat, int c, const int32_t *row_index, const uint32_t *member, int k, int64_t cap,
+                       const float *sum, const float *mean) {
+    return member && !row_index && c % PM_SLICE == 0 && k >= 1 && k <= 128 && cap > 0 &&
+           cap < ((int64_t)1 << 31) - PM_TP && reinterpret_cast<uintptr_t>(feat) % 16 == 0 && sum &&
+           reinterpret_cast<uintptr_t>(sum) % 4 == 0 && (!mean || reinterpret_cast<uintptr_t>(mean) % 4 == 0);
+}
+
+int launch_pool_mma(const float *feat, int c, const uint32_t *member, int words, int n_seg, int k, const int64_t *seg_off,
+                    int64_t cap, float *sum, int32_t *cnt, float *mean, int *work, cudaStream_t stream) {
+    CUtensorMap map;
+    memset(&map, 0, sizeof(map));
+    // rows past `cap` are zero-filled by TMA; rows past a segment are zeroed by the converters
+    if (!make_map_sw128(&map, feat, cap, c, 32, PM_TP, /*atom32=*/true)) {
+        set_error("xm3d_pool_batch: cuTensorMapEncodeTiled failed");
+        return XM3D_ERR_CUDA;
+    }
+    PoolMmaParams P;
+    P.member = member; P.seg_off = seg_off; P.words = words; P.k = k; P.n_seg = n_seg; P.c = c; P.cap = cap;
+    P.sum = sum; P.mean = mean; P.cnt = cnt; P.work = work;
+    const int n_items = n_seg * (c / PM_SLICE);
+    const unsigned grid = (unsigned)(n_items < sm_count() ? n_items : sm_count());
+    cudaMemsetAsync(work, 0, sizeof(int), stream);
+    static std::atomic<uint64_t> attr_set{0};
+    if (first_use_on_device(&attr_set)) {
+        cudaFuncSetAttribute(pool_mma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+        cudaFuncSetAttribute(pool_mma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    }
+    if (k <= 64) {
+        P.raw_stages = 3; P.conv_stages = 2;
+        const size_t smem = (size_t)P.raw_stages * PM_RAW + (size_t)P.conv_stages * (PM_RAW + 64 * PM_TP * 4) + 1024;
+        pool_mma_kernel<64><<<grid, 32 * (10 + 4), smem, stream>>>(map, P);
+    } else {
+        P.raw_stages = 2; P.conv_stages = 2;
+        const size_t smem = (size_t)P.raw_stages * PM_RAW + (size_t)P.conv_stages * (PM_RAW + 128 * PM_TP * 4) + 1024;
+        pool_mma_kernel<128><<<grid, 32 * (10 + 8), smem, stream>>>(map, P);
+    }
+    count_launches(1);
+    return check_launch("xm3d_pool_batch (tensor-core path)");
+}
+
+}  // namespace xm3d

@@ -707,11 +707,10 @@ extern "C" int xm3d_project_batch(const float *xyz, const xm3d_view_t *views_hos
     P.f_inv_scale = (float)(1.0 / depth_scale); P.f_vt = (float)vis_thres;
     P.parts = parts; P.smem_depth_bytes = (int)stage_bytes; P.use_flag = (any_depth && !covers) ? 1 : 0;
 
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::atomic<uint64_t> attr_set{0};
+    if (first_use_on_device(&attr_set)) {
         cudaFuncSetAttribute(project_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PROJ_MAX_SMEM_DEPTH + PROJ_SMEM_EXTRA);
         cudaFuncSetAttribute(project_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PROJ_MAX_SMEM_DEPTH + PROJ_SMEM_EXTRA);
-        attr_set = true;
     }
     dim3 grid(parts, n_views);
     project_plan_kernel<<<1, 1024, 0, stream>>>(d_views, n_views, parts, item_off, part_cnt); count_launches(1);

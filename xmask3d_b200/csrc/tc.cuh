@@ -1,0 +1,92 @@
+// tcgen05 / TMEM / TMA wrappers shared by the tensor-core kernels (logits.cu, pool_mma.cu).  sm_100a only.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace xm3d {
+
+// 2-D tiled TMA load (SASS: UTMALDG.2D), completion on an mbarrier
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int x, int y, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
+}
+// Shared-memory matrix descriptor, 128-byte swizzle, descriptor version 1 (sm_100).
+//   K-major operand:  8-row atoms of 128 B (32 tf32 along K); sbo = byte stride between 8-row groups, lbo unused
+//   MN-major operand: atoms of 8 K-rows x 128 B (32 tf32 along M/N); lbo = byte stride between atoms along M/N,
+//                     sbo = byte stride between 8-row groups along K
+//   MN-major 32-bit (tf32) operand: the ONLY layout is "128-byte swizzle with 32-byte atomicity" (layout type 1,
+//                     Swizzle<2,5,2>: 32-byte chunk index ^= row & 3; TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): atoms
+//                     of 4 K-rows x 128 B; lbo = byte stride between atoms along M/N, sbo = between 4-row groups along K
+__device__ __forceinline__ uint64_t make_sw128_desc_ex(const void *smem_ptr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                       uint32_t layout_type = 2) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_u32(smem_ptr) & 0x3ffff) >> 4);        // start address, bits [0,14)
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;            // leading byte offset, bits [16,30)
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;            // stride byte offset, bits [32,46)
+    d |= (uint64_t)1 << 46;                                       // descriptor version
+    d |= (uint64_t)layout_type << 61;                             // 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
+    return d;
+}
+__device__ __forceinline__ uint64_t make_sw128_desc(const void *smem_ptr) {
+    return make_sw128_desc_ex(smem_ptr, 0, 1024);
+}
+// instruction descriptor of tcgen05.mma kind::tf32 / kind::f16: D = f32, A/B format fmt (2 = tf32, 1 = bf16, 0 = f16)
+__host__ __device__ __forceinline__ uint32_t make_idesc(int m, int n, int fmt, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(a_mn_major & 1) << 15) |
+           ((uint32_t)(b_mn_major & 1) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                 ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    tmem_ld16_nowait(taddr, v);
+    tmem_ld_wait();
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t *slot, uint32_t cols) {      // one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t base, uint32_t cols) {     // the same warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(cols) : "memory");
+}
+
+// host: float32 row-major [rows, c] matrix, box = box_cols x box_rows, 128-byte swizzle (box_cols * 4 == 128)
+// (atom32: swizzle 32-byte chunks instead of 16-byte chunks — the layout of MN-major tf32 MMA operands)
+bool make_map_sw128(CUtensorMap *m, const float *base, int64_t rows, int c, int box_cols, int box_rows, bool atom32 = false);
+// host: the same without swizzle
+bool make_row_tile_map(CUtensorMap *m, const float *base, int64_t rows, int c, int box_cols, int box_rows);
+
+}  // namespace xm3d

@@ -1146,11 +1146,10 @@ static int run_unique(const float *xyz, const unsigned long long *keys, const in
     if (units_max64 > w.units_cap) units_max64 = w.units_cap;
     const int units_max = (int)units_max64;
     const int force_slow = (g_vox_mode == 1 || counts != nullptr) ? 1 : 0;
-    static bool smem_set = false;
-    if (!smem_set) {
+    static std::atomic<uint64_t> smem_set{0};
+    if (first_use_on_device(&smem_set)) {
         cudaFuncSetAttribute(vox_fast_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FV_SMEM);
         cudaFuncSetAttribute(vox_fast_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FV_SMEM);
-        smem_set = true;
     }
     vox_plan_kernel<<<1, 1024, 0, stream>>>(seg_off, n_seg, cap, w.tbl_off, w.spl_off, w.total_eff, m,
                                             xyz ? gmin : nullptr, status, unit_pts, units_max, force_slow,

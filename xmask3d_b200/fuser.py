@@ -16,32 +16,78 @@ import torch
 from . import ops
 
 
+def _stack_ragged_masks(masks, mode: str):
+    """The reference's callers pass RAGGED per-scene lists (models/utils/criterion.py:262-340): K' bool masks
+    [K',h,w] for a scene whose argmax partition kept K' masks, or K float32 zero masks when nothing was kept.
+    Pad to the largest K with planes that never hit (0 for `m >= 0.5`, -inf for the sigmoid modes).  Mixed
+    dtypes are brought to a common one: bool/uint8 stay uint8 only if every scene is bool/uint8; for the plain
+    `>= 0.5` mode float masks are thresholded first (exactly the reference's comparison)."""
+    if torch.is_tensor(masks):
+        return masks, [int(masks.shape[1])] * int(masks.shape[0])
+    masks = list(masks)
+    ks = [int(m.shape[0]) for m in masks]
+    kmax = max(max(ks), 1)
+    all_int = all(m.dtype in (torch.bool, torch.uint8) for m in masks)
+    same = all(m.shape == masks[0].shape and m.dtype == masks[0].dtype for m in masks)
+    if same and ks[0] > 0:
+        return torch.stack(masks), ks
+    h, w = masks[0].shape[-2:]
+    dev = masks[0].device
+    if all_int or mode == "ge0.5":
+        out = torch.zeros((len(masks), kmax, h, w), dtype=torch.uint8, device=dev)
+        for i, m in enumerate(masks):
+            if ks[i]:
+                out[i, :ks[i]] = m.to(torch.uint8) if m.dtype in (torch.bool, torch.uint8) else (m >= 0.5).to(torch.uint8)
+        return out, ks
+    out = torch.full((len(masks), kmax, h, w), float("-inf"), dtype=torch.float32, device=dev)
+    for i, m in enumerate(masks):
+        if ks[i]:
+            # bool planes in a float batch: True -> +inf (sigmoid = 1), False -> -inf (sigmoid = 0)
+            out[i, :ks[i]] = m.to(torch.float32) if m.dtype.is_floating_point else \
+                torch.where(m.bool(), float("inf"), float("-inf")).to(torch.float32)
+    return out, ks
+
+
 def masks_at_points(x_list, y_list, masks, mode: str = "ge0.5"):
     """mask[:, x_label, y_label] + threshold for every scene: returns (member [sum n, words] int32,
-    counts int32 [B,k], seg_off int64 [B+1] CUDA).  masks: list / tensor of [k,h,w] per scene."""
-    dev = masks[0].device
+    counts int32 [B,k], seg_off int64 [B+1] CUDA, seg_off host).  masks: tensor [B,k,h,w] or a (possibly
+    ragged, possibly mixed bool / float) list of [k_s,h,w] per scene; k = the largest k_s."""
+    m, _ = _stack_ragged_masks(masks, mode)
+    dev = m.device
     n = [int(x.shape[0]) for x in x_list]
     seg = torch.zeros(len(n) + 1, dtype=torch.int64)
     seg[1:] = torch.cumsum(torch.tensor(n, dtype=torch.int64), 0)
     rowcol = torch.stack([torch.cat([x.reshape(-1) for x in x_list]),
                           torch.cat([y.reshape(-1) for y in y_list])], 1).to(device=dev, dtype=torch.int32)
-    m = masks if torch.is_tensor(masks) else torch.stack(list(masks))
     seg_d = seg.to(dev)
     member, counts = ops.gather_masks(m, rowcol, seg_d, mode=mode, want_counts=True)
     return member, counts, seg_d, seg
+
+
+def _stack_ragged_embeds(mask_embeds, kmax: int):
+    if torch.is_tensor(mask_embeds):
+        return mask_embeds
+    embs = list(mask_embeds)
+    if all(e.shape == embs[0].shape for e in embs) and embs[0].shape[0] == kmax:
+        return torch.stack(embs)
+    out = embs[0].new_zeros((len(embs), kmax, embs[0].shape[-1]))
+    for i, e in enumerate(embs):
+        if e.shape[0]:
+            out[i, :e.shape[0]] = e           # differentiable w.r.t. every scene's embeddings
+    return out
 
 
 def mask_mapper(x_list, y_list, masks, mask_embeds, pred_3ds, fuser, fc1, fc2, cfg):
     dev = pred_3ds[0].device
     b = len(x_list)
     member, counts, seg_d, seg = masks_at_points(x_list, y_list, masks, "ge0.5")
-    # fuser.py:19-20 — when no mask holds any point, point 0 is put into mask 0
-    empty = (counts.sum(1) == 0).cpu()
-    for s in range(b):
-        if bool(empty[s]) and seg[s + 1] > seg[s]:
-            member[int(seg[s]), 0] |= 1
-    emb = mask_embeds if torch.is_tensor(mask_embeds) else torch.stack(list(mask_embeds))
+    # fuser.py:19-20 — when no mask holds any point, point 0 is put into mask 0.  On the device, no host round
+    # trip: all bits of such a scene are 0, so OR-ing bit 0 of its first point's word 0 is an integer add.
     total = int(seg[-1])
+    if total:
+        empty = ((counts.sum(1) == 0) & (seg_d[1:] > seg_d[:-1])).to(torch.int32)
+        member[:, 0].index_add_(0, seg_d[:-1].clamp(max=total - 1), empty)
+    emb = _stack_ragged_embeds(mask_embeds, int(counts.shape[1]))
     if torch.is_grad_enabled() and emb.requires_grad:
         from .autograd import scatter_mean                  # training: gradients flow to mask_embed
         feat2d_all, counter_all = scatter_mean(emb, seg_d, member, total)

@@ -235,6 +235,9 @@ def ravel_hash(coords: torch.Tensor) -> torch.Tensor:
 THR = {"ge0.5": L.THR_GE_HALF, "sigmoid_ge0.5": L.THR_SIGMOID_GE_HALF, "sigmoid_gt0.5": L.THR_SIGMOID_GT_HALF}
 
 
+POOL_PATH = {"auto": L.POOL_AUTO, "pair_lists": L.POOL_PAIR_LISTS, "rows": L.POOL_ROWS, "mma": L.POOL_MMA}
+
+
 def mask_words(k: int) -> int:
     return (int(k) + 31) // 32
 
@@ -303,10 +306,11 @@ def _popcount32(x: torch.Tensor) -> torch.Tensor:
 def pool(feat: torch.Tensor, seg_off: torch.Tensor, k: int, member: Optional[torch.Tensor] = None,
          label: Optional[torch.Tensor] = None, row_index: Optional[torch.Tensor] = None,
          cap: Optional[int] = None, cap_pairs: Optional[int] = None, want_mean: bool = True,
-         ws: Optional[torch.Tensor] = None, status: Optional[torch.Tensor] = None):
+         ws: Optional[torch.Tensor] = None, status: Optional[torch.Tensor] = None, path: str = "auto"):
     """Segmented mean pooling.  feat float32 [rows,c]; member int32 [cap,words] or label int32 [cap].
     cap_pairs: bound on the number of (point, mask) memberships (None: labels -> cap, members ->
     counted on the device, which costs one host sync).
+    path: "auto" | "pair_lists" | "rows" | "mma" (include/xm3d.h: XM3D_POOL_*).
     Returns (sum [n_seg,k,c], cnt int32 [n_seg,k], mean [n_seg,k,c] or None)."""
     _require_cuda()
     dev = feat.device
@@ -334,8 +338,8 @@ def pool(feat: torch.Tensor, seg_off: torch.Tensor, k: int, member: Optional[tor
     if ws is None or ws.numel() < need:
         ws = _ws(need, dev)
     L.check(L.lib().xm3d_pool_batch(_ptr(feat), c, _ptr(row_index), _ptr(member), _ptr(label), n_seg, int(k),
-                                    _ptr(seg_off), cap, cap_pairs, _ptr(s), _ptr(cnt), _ptr(mean), _ptr(ws),
-                                    ws.numel(), _ptr(status), _stream()))
+                                    _ptr(seg_off), cap, cap_pairs, POOL_PATH[path], _ptr(s), _ptr(cnt), _ptr(mean),
+                                    _ptr(ws), ws.numel(), _ptr(status), _stream()))
     return s, cnt, mean
 
 
