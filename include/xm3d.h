@@ -130,9 +130,15 @@ XM3D_API int xm3d_project_batch(const float *xyz, const xm3d_view_t *views_host,
  *   inverse[seg_off[s]+i]     rank of element i (+ uniq_off[s] if collate != 0, the
  *                             cumulative offset collation_fn adds, dataset/data_loader.py:341-342) */
 XM3D_API size_t xm3d_unique_ws_bytes(int32_t n_seg, int64_t cap);
+/* `path` (per call, re-entrant — both paths are bit-identical; tests and A/B timings use it): low byte
+ * XM3D_VOX_AUTO = shared-memory units whenever every segment fits (<= 224 k points), the multi-kernel
+ * global-memory path otherwise; XM3D_VOX_MULTI_KERNEL = multi-kernel path only.  Bits 8.. = points per unit the
+ * plan aims at (0 = default 7000; smaller values force several key-range units per segment). */
+#define XM3D_VOX_AUTO 0
+#define XM3D_VOX_MULTI_KERNEL 1
 XM3D_API int xm3d_unique_batch(const uint64_t *keys, const int64_t *seg_off, int32_t n_seg, int64_t cap,
                       int32_t *m, int64_t *uniq_off, int32_t *first, int32_t *counts,
-                      int32_t *inverse, int32_t collate, void *ws, size_t ws_bytes,
+                      int32_t *inverse, int32_t collate, int32_t path, void *ws, size_t ws_bytes,
                       int32_t *status, xm3d_stream_t stream);
 
 /* FNV-1 over whole 64-bit words per row (fnv_hash_vec, dataset/voxelization_utils.py:6-18)
@@ -144,26 +150,23 @@ XM3D_API size_t xm3d_ravel_ws_bytes(int32_t dim);
 
 /* Voxelizer.voxelize after the matrix is drawn (dataset/voxelizer.py:110-122) fused with
  * sparse_quantize: grid = floor([x y z 1] @ RT.T[:, :3]); grid -= min; FNV key; unique.
- *   xyz           [cap,3] float32, segments as above (e.g. xyz_vis / vis_off of the projection)
+ *   xyz           [cap,3] float32 (xyz_f64 = 0) or float64 (xyz_f64 = 1: what ElasticDistortion hands the
+ *                 voxelizer on the augmented training path, dataset/augmentation.py:171), segments as above
+ *                 (e.g. xyz_vis / vis_off of the projection)
  *   rt            [n_seg,12] float64: rows 0..2 of rigid_transformation per segment
  *   grid_min      [n_seg,3] int32   column minima that were subtracted (optional)
  *   voxel_xyz     [uniq_off[s]+r, 3] int32 voxel coordinates in unique order (grid[inds])
  * other outputs as xm3d_unique_batch. */
 XM3D_API size_t xm3d_voxelize_ws_bytes(int32_t n_seg, int64_t cap);
-/* Path selection of xm3d_unique_batch / xm3d_voxelize_batch (both paths are bit-identical; tests and
- * A/B timings use it).  mode 0 (default): shared-memory units whenever every segment fits, the
- * multi-kernel global-memory path otherwise; mode 1: multi-kernel path only.  unit_pts: points per
- * unit the plan aims at (0 = default 7000; smaller values force several key-range units per segment). */
-XM3D_API void xm3d_set_voxel_path(int32_t mode, int32_t unit_pts);
 /* Which path the last call on this workspace took (synchronises the stream; diagnostics / tests):
  * ctl_host[0] = 1 if the batch was not eligible for the shared-memory path, ctl_host[1] = 1 if a
  * unit overflowed and the batch was recomputed by the multi-kernel path. */
 XM3D_API int xm3d_voxel_path_info(const void *ws, int32_t n_seg, int64_t cap, int32_t *ctl_host,
                          xm3d_stream_t stream);
-XM3D_API int xm3d_voxelize_batch(const float *xyz, const int64_t *seg_off, int32_t n_seg, int64_t cap,
+XM3D_API int xm3d_voxelize_batch(const void *xyz, int32_t xyz_f64, const int64_t *seg_off, int32_t n_seg, int64_t cap,
                         const double *rt, int32_t *m, int64_t *uniq_off, int32_t *first,
                         int32_t *inverse, int32_t collate, int32_t *voxel_xyz, int32_t *grid_min,
-                        void *ws, size_t ws_bytes, int32_t *status, xm3d_stream_t stream);
+                        int32_t path, void *ws, size_t ws_bytes, int32_t *status, xm3d_stream_t stream);
 
 /* ------------------------------------------------------------------ stage 3: masks at points
  * Mask-at-point gather + threshold (models/utils/fuser.py:16-17, models/utils/criterion.py:83-85,

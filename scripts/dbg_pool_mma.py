@@ -97,21 +97,25 @@ w1 = (bits[:, 32:].long() << torch.arange(32, device=dev)).sum(1)
 member = torch.stack([w0, w1], 1)
 member = torch.where(member >= 2 ** 31, member - 2 ** 32, member).to(torch.int32)
 pairs = int(bits.sum().item())
-for path in ("mma", "rows"):
+def timeit(path, tune=0):
     for _ in range(2):
-        out = ops.pool(feat, seg, k, member=member, cap=total, cap_pairs=pairs + 2, path=path)
+        out = ops.pool(feat, seg, k, member=member, cap=total, cap_pairs=pairs + 2, path=path, _tune=tune)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(5):
-        out = ops.pool(feat, seg, k, member=member, cap=total, cap_pairs=pairs + 2, path=path)
+        out = ops.pool(feat, seg, k, member=member, cap=total, cap_pairs=pairs + 2, path=path, _tune=tune)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 5
-    print(f"bench-size pooling path={path}: {ms:.3f} ms  = {total * c * 4 / ms / 1e6:.0f} GB/s of feature reads ({pairs / total:.2f} memberships/point)", flush=True)
-    if path == "mma":
-        ref_s = out[0]
-    else:
-        d = (out[0] - ref_s).abs().amax(-1) / out[0].abs().amax(-1).clamp_min(1e-30)
-        print(f"   mma vs rows: worst vector-rel diff {d.max().item():.3e}")
+    print(f"bench-size pooling path={path} tune(rs,cs)=({tune & 15},{tune >> 4}): {ms:.3f} ms = {total * c * 4 / ms / 1e6:.0f} GB/s of feature reads ({pairs / total:.2f} memberships/point)", flush=True)
+    return out[0]
+
+
+ref_s = timeit("mma")
+for rs_, cs_ in ((2, 2), (2, 3), (3, 2), (4, 1), (1, 3)):
+    timeit("mma", rs_ | (cs_ << 4))
+o = timeit("rows")
+d = (o - ref_s).abs().amax(-1) / o.abs().amax(-1).clamp_min(1e-30)
+print(f"   mma vs rows: worst vector-rel diff {d.max().item():.3e}")
 print("dbg_pool_mma done")

@@ -224,10 +224,10 @@ def test_voxelize_paths_vs_oracle(cport, dev, mode, unit_pts):
     off = np.concatenate([[0], np.cumsum(n)]).astype(np.int64)
     xyz = torch.from_numpy(np.concatenate([s for s, _ in segs])).to(dev)
     rt = torch.from_numpy(np.stack([r[:3, :4] for _, r in segs])).to(dev)
-    ops.set_voxel_path(mode, unit_pts)
-    try:
+    if True:                                     # the path is a per-call argument (re-entrant, no process-global switch)
         for collate in (False, True):
-            u = ops.voxelize_batch(xyz, torch.from_numpy(off).to(dev), rt, collate=collate, cap=xyz.shape[0] + 777)
+            u = ops.voxelize_batch(xyz, torch.from_numpy(off).to(dev), rt, collate=collate, cap=xyz.shape[0] + 777,
+                                   mode=mode, unit_pts=unit_pts)
             assert int(u.status.item()) == 0
             assert ops.voxel_path_info(u) == ((1, 0) if mode == 1 else (0, 0))
             m, uoff = u.m.cpu().numpy(), u.uniq_off.cpu().numpy()
@@ -244,8 +244,6 @@ def test_voxelize_paths_vs_oracle(cport, dev, mode, unit_pts):
                 shift = a if collate else 0
                 assert np.array_equal(inv[off[i]:off[i + 1]] - shift, rinv), f"segment {i}"
             assert uoff[-1] == m.sum()
-    finally:
-        ops.set_voxel_path(0, 0)
 
 
 def test_voxelize_unit_overflow_falls_back(cport, dev):
@@ -280,13 +278,9 @@ def test_voxelize_unit_overflow_falls_back(cport, dev):
     koff = np.concatenate([[0], np.cumsum([len(s) for s in ksegs])]).astype(np.int64)
     keys = torch.from_numpy(np.concatenate(ksegs).view(np.int64)).to(dev)
     for unit_pts in (0, 300):
-        ops.set_voxel_path(0, unit_pts)
-        try:
-            ku = ops.unique_batch(keys, torch.from_numpy(koff).to(dev), collate=True)
-            if unit_pts == 0:
-                assert ops.voxel_path_info(ku) == (0, 0)
-        finally:
-            ops.set_voxel_path(0, 0)
+        ku = ops.unique_batch(keys, torch.from_numpy(koff).to(dev), collate=True, unit_pts=unit_pts)
+        if unit_pts == 0:
+            assert ops.voxel_path_info(ku) == (0, 0)
         km, kuoff = ku.m.cpu().numpy(), ku.uniq_off.cpu().numpy()
         for i, ks in enumerate(ksegs):
             rf, ri_, rc = cport.unique_u64(ks) if len(ks) else (np.zeros(0, np.int64),) * 3
@@ -370,6 +364,71 @@ def test_gather_pool_scatter_golden(golden, cport, dev):
     np.testing.assert_allclose(sp[0].cpu().numpy(), g["score_pool"], rtol=1e-5, atol=1e-7)
 
 
+def test_mask_mapper_ragged_lists(dev):
+    """The caller's real input (models/utils/criterion.py:262-340): per-scene lists with DIFFERENT numbers of masks,
+    bool partition masks for some scenes, float32 zero masks ("nothing kept") for others, one scene whose masks
+    hit no point at all (fuser.py:19-20 guard) — bit-exact against the restatement of fuser.py:6-53 that
+    tests/test_reference_live.py pins to the reference on exactly such lists."""
+    from oracle import ref_port
+    from xmask3d_b200.fuser import mask_mapper
+    g = torch.Generator().manual_seed(11)
+    h, w, c = 240, 320, 64
+    xs, ys, masks, embs, preds = [], [], [], [], []
+    for i, k in enumerate([7, 3, 12, 5, 4]):
+        n = [900, 1, 2500, 333, 50][i]
+        xs.append(torch.randint(0, h, (n,), generator=g))
+        ys.append(torch.randint(0, w, (n,), generator=g))
+        if i == 2:
+            masks.append(torch.zeros(k, h, w))                                   # float zeros: nothing kept
+        elif i == 4:
+            m = torch.zeros(k, h, w, dtype=torch.bool)
+            m[:, 0, 0] = True                                                    # bool masks that miss every point
+            xs[-1].clamp_(min=1)
+            masks.append(m)
+        else:
+            lab = torch.randint(0, k + 2, (h, w), generator=g)                   # partition; labels >= k = background
+            masks.append(lab.unsqueeze(0) == torch.arange(k).view(k, 1, 1))
+        embs.append(torch.randn(k, c, generator=g))
+        preds.append(torch.randn(n, c, generator=g))
+    ident = torch.nn.Identity()
+    fuse = lambda a, b: a * 0.5 + b                          # noqa: E731
+
+    class Cfg:
+        caption_contra_2d_pre = True
+    ref = ref_port.mask_mapper_ref(xs, ys, masks, embs, preds, fuse, ident, ident, True)
+    got = mask_mapper(xs, ys, [m.to(dev) for m in masks], [e.to(dev) for e in embs], [p.to(dev) for p in preds],
+                      fuse, ident, ident, Cfg)
+    for a, b in zip(ref, got):
+        assert len(a) == len(b)
+        for u, v in zip(a, b):
+            assert torch.equal(u, v.cpu())
+
+
+def test_voxelize_float64_coords(dev):
+    """The augmented training path hands the voxelizer FLOAT64 coordinates (ElasticDistortion returns
+    coords + interp(coords) * magnitude, dataset/augmentation.py:171; data_loader.py:252-256): homo_coords then stays
+    float64 and the matmul sees the unrounded values.  Device result vs the numpy restatement of voxelizer.py:81-132
+    on the same float64 input — and it must differ from what rounding the input to float32 first would give."""
+    from oracle import ref_port
+    from tests.golden.make_golden_params import vox_kwargs
+    from xmask3d_b200.voxelizer import Voxelizer
+    rng = np.random.default_rng(3)
+    sc = syn.make_scene(9, 60_000)
+    coords64 = sc.xyz.astype(np.float64) + rng.normal(0, 0.01, sc.xyz.shape)     # not representable in float32
+    kw = vox_kwargs(0.02)
+    for seed in (1, 2):
+        np.random.seed(seed)
+        ref = ref_port.Voxelizer(**kw).voxelize(coords64.copy(), sc.colors.copy(), sc.labels.copy(), return_ind=True)
+        np.random.seed(seed)
+        got = Voxelizer(**kw).voxelize(coords64.copy(), sc.colors.copy(), sc.labels.copy(), return_ind=True)
+        for a, b in zip(ref, got):
+            assert np.asarray(a).dtype == np.asarray(b).dtype and np.array_equal(a, b)
+    np.random.seed(2)
+    lossy = Voxelizer(**kw).voxelize(coords64.astype(np.float32), sc.colors.copy(), sc.labels.copy(), return_ind=True)
+    assert lossy[0].shape != got[0].shape or not np.array_equal(lossy[3], got[3]), \
+        "rounding the coordinates to float32 first must change some voxel assignment at 60k points"
+
+
 @pytest.mark.parametrize("k,c", [(50, 768), (100, 768), (7, 64), (130, 256), (3, 1), (96, 128), (33, 256)])
 def test_pool_scatter_vs_oracle(cport, dev, k, c):
     """Ragged batch (incl. an empty segment), overlapping members and partition labels."""
@@ -421,8 +480,73 @@ def test_pool_scatter_vs_oracle(cport, dev, k, c):
     perm = torch.randperm(total, device=dev).to(torch.int32)
     inv = torch.empty_like(perm)
     inv[perm.long()] = torch.arange(total, device=dev, dtype=torch.int32)
-    s3, _, _ = ops.pool(f[perm.long()], seg, k, member=mem, row_index=inv)
-    assert torch.equal(s3, s_sum)
+    path = "rows" if (c % 128 == 0 and k <= 96) else "pair_lists"      # kernels that take row_index
+    s3, _, _ = ops.pool(f[perm.long()], seg, k, member=mem, row_index=inv, path=path)
+    s4, _, _ = ops.pool(f, seg, k, member=mem, path=path)
+    assert torch.equal(s3, s4)
+    assert float(((s4 - s_sum).abs().amax(-1) / s_sum.abs().amax(-1).clamp_min(1e-30)).max()) < 1e-5
+
+
+@pytest.mark.parametrize("path", ["pair_lists", "rows", "mma"])
+@pytest.mark.parametrize("ns,k,c,dens", [([3000, 0, 1777, 1, 5200, 320], 50, 768, 0.12), ([3000, 64, 65, 63], 96, 128, 0.3),
+                                         ([2500, 700], 33, 256, 0.5), ([70_000], 50, 256, 0.3),
+                                         ([5000, 4000], 100, 384, 0.1), ([1000], 1, 128, 1.0), ([129], 64, 128, 0.0)])
+def test_pool_paths_vs_oracle(cport, dev, path, ns, k, c, dens):
+    """Every pooling kernel — sorted pair lists, point-major CUDA cores, tensor cores (tcgen05 tf32 hi/lo with the
+    membership bits as a 0/1 operand, csrc/pool_mma.cu) — against the float64 oracle of
+    models/utils/criterion.py:148-157 on overlapping masks: counts exact, sums / means <= 1e-5 vector-wise,
+    deterministic, rows of a following segment (here 1e30) never leak into a segment's last tile."""
+    from xmask3d_b200 import ops
+    if path == "rows" and k > 96:
+        pytest.skip("point-major kernel holds at most 96 accumulator rows")
+    rng = np.random.default_rng(k * 7 + c)
+    off = np.concatenate([[0], np.cumsum(ns)]).astype(np.int64)
+    total = int(off[-1])
+    feat = rng.standard_normal((total + 64, c), dtype=np.float32)
+    feat[total:] = 1e30                                   # rows past the last segment
+    if len(ns) > 1 and ns[1] > 0:
+        feat[off[1]:off[1] + 8] *= 1e6                    # a loud neighbour right after segment 0
+    member_b = [rng.random((k, n)) < dens for n in ns]
+    packed = np.zeros((total + 64, (k + 31) // 32), np.uint32)
+    packed[total:] = 0xFFFFFFFF                           # bits past the last segment must be ignored
+    for s_, mb in enumerate(member_b):
+        for m in range(k):
+            packed[off[s_]:off[s_ + 1], m // 32] |= (mb[m].astype(np.uint32) << np.uint32(m % 32))
+    seg = torch.from_numpy(off).to(dev)
+    f = torch.from_numpy(feat).to(dev)
+    mem = torch.from_numpy(packed.view(np.int32)).to(dev)
+    pairs = int(sum(mb.sum() for mb in member_b))
+    s_sum, cnt, mean = ops.pool(f, seg, k, member=mem, cap=total, cap_pairs=max(pairs, total + 2), path=path)
+    for s_, mb in enumerate(member_b):
+        a, b = off[s_], off[s_ + 1]
+        r_sum, r_cnt = cport.pool_member_f64(feat[a:b], mb) if ns[s_] else (np.zeros((k, c)), np.zeros(k, np.int64))
+        assert np.array_equal(cnt[s_].cpu().numpy(), r_cnt), f"segment {s_}"
+        scale = np.maximum(np.abs(r_sum).max(1), 1e-30)
+        assert (np.abs(s_sum[s_].cpu().numpy() - r_sum).max(1) / scale).max() < 1e-5, f"segment {s_}"
+        r_mean = r_sum / np.maximum(r_cnt, 1)[:, None]
+        assert (np.abs(mean[s_].cpu().numpy() - r_mean).max(1) / np.maximum(np.abs(r_mean).max(1), 1e-30)).max() < 1e-5
+    s2, c2, m2 = ops.pool(f, seg, k, member=mem, cap=total, cap_pairs=max(pairs, total + 2), path=path)
+    assert torch.equal(s2, s_sum) and torch.equal(c2, cnt) and torch.equal(m2, mean)
+
+
+def test_pool_path_selection(dev):
+    """XM3D_POOL_AUTO: overlapping memberships (cap_pairs > cap + 1) go to the tensor-core kernel when it is eligible;
+    forcing a path that is not eligible fails loudly (no silent fallback)."""
+    from xmask3d_b200 import _lib as L, ops
+    f = torch.randn(300, 96, device=dev)
+    seg = torch.tensor([0, 300], device=dev)
+    mem = torch.randint(0, 2 ** 20, (300, 1), device=dev, dtype=torch.int32)
+    with pytest.raises(L.Xm3dError):
+        ops.pool(f, seg, 20, member=mem, path="mma")              # c % 128 != 0
+    with pytest.raises(L.Xm3dError):
+        ops.pool(f, seg, 20, member=mem, path="rows")
+    a, _, _ = ops.pool(f, seg, 20, member=mem)                    # auto -> pair lists
+    b, _, _ = ops.pool(f, seg, 20, member=mem, path="pair_lists")
+    assert torch.equal(a, b)
+    f = torch.randn(300, 128, device=dev)
+    a, _, _ = ops.pool(f, seg, 20, member=mem)                    # auto -> tensor cores (overlap, eligible)
+    b, _, _ = ops.pool(f, seg, 20, member=mem, path="mma")
+    assert torch.equal(a, b)
 
 
 # ----------------------------------------------------------------------------- stage 4

@@ -31,3 +31,27 @@ def test_accept_views_matches_the_loaders_rule():
         ref.append(bool(vis[v].sum() > 400 and (lab != 255).sum() > 10 and vis[v].sum() < 4000))
     assert got.tolist() == ref
     assert ref == [True, False, True, False, False, False]   # ok, too few, ok, none, all ignored, too many
+
+
+def test_ragged_mask_lists_pad_to_never_hitting_planes():
+    """mask_mapper's caller passes per-scene lists with different numbers of masks and mixed bool / float dtypes
+    (models/utils/criterion.py:262-340); the padding must never hit under the call site's threshold."""
+    import torch
+    from xmask3d_b200.fuser import _stack_ragged_embeds, _stack_ragged_masks
+    g = torch.Generator().manual_seed(0)
+    a = torch.rand(3, 4, 5, generator=g) > 0.5                   # bool, K' = 3
+    b = torch.zeros(5, 4, 5)                                     # float zeros, K = 5
+    c = torch.rand(2, 4, 5, generator=g)                         # float probabilities, K' = 2
+    m, ks = _stack_ragged_masks([a, b, c], "ge0.5")
+    assert ks == [3, 5, 2] and m.shape == (3, 5, 4, 5) and m.dtype == torch.uint8
+    assert torch.equal(m[0, :3].bool(), a) and not m[0, 3:].any()
+    assert not m[1].any()
+    assert torch.equal(m[2, :2].bool(), c >= 0.5) and not m[2, 2:].any()
+    lg = [torch.randn(2, 4, 5, generator=g), torch.randn(4, 4, 5, generator=g)]
+    m, ks = _stack_ragged_masks(lg, "sigmoid_ge0.5")
+    assert m.dtype == torch.float32 and torch.equal(m[0, :2], lg[0]) and bool((m[0, 2:].sigmoid() < 0.5).all())
+    same = [torch.rand(3, 4, 5, generator=g) for _ in range(2)]
+    m, ks = _stack_ragged_masks(same, "ge0.5")
+    assert torch.equal(m, torch.stack(same)) and ks == [3, 3]
+    e = _stack_ragged_embeds([torch.ones(3, 6), torch.ones(5, 6), torch.ones(2, 6)], 5)
+    assert e.shape == (3, 5, 6) and float(e.sum()) == (3 + 5 + 2) * 6

@@ -58,6 +58,14 @@ def test_voxelize_and_quantize_live(R, seed, n, voxel):
         outs.append(V(**vox_kwargs(voxel)).voxelize(xyz, colors.copy(), labels.copy(), return_ind=True))
     for a, b in zip(*outs):
         assert np.asarray(a).dtype == np.asarray(b).dtype and np.array_equal(a, b)
+    # float64 coordinates (what ElasticDistortion hands the voxelizer on the augmented path, augmentation.py:171)
+    xyz64 = xyz.astype(np.float64) + rng.normal(0, 0.01, xyz.shape)
+    outs = []
+    for V in (R.Voxelizer, ref_port.Voxelizer):
+        np.random.seed(seed % (2 ** 31))
+        outs.append(V(**vox_kwargs(voxel)).voxelize(xyz64.copy(), colors.copy(), labels.copy(), return_ind=True))
+    for a, b in zip(*outs):
+        assert np.asarray(a).dtype == np.asarray(b).dtype and np.array_equal(a, b)
     grid = np.floor(rng.uniform(0, 30, (n, 3)))
     assert np.array_equal(ref_port.fnv_hash_vec(grid), R.fnv_hash_vec(grid))
     assert np.array_equal(ref_port.ravel_hash_vec(grid.copy() - 7.0), R.ravel_hash_vec(grid.copy() - 7.0))

@@ -154,3 +154,20 @@ def test_scene_cache_matches_loader_preprocessing(tmp_path):
     assert not view.flags.writeable
     cache.delete(3)
     assert not cache.ready()
+
+
+def test_scene_without_colours(tmp_path):
+    """dataset/point_loader.py:143-145: a scalar 0 colour entry means "no colours" -> zeros -> 127.5 per point,
+    through read_scene_pth and the cache's preprocessing alike."""
+    import torch
+    from xmask3d_b200 import scene_io
+    locs = np.random.default_rng(0).standard_normal((50, 3)).astype(np.float32)
+    labels = np.arange(50) % 7
+    p = str(tmp_path / "scene.pth")
+    torch.save((locs, 0, labels), p)
+    l2, f2, lab2 = scene_io.read_scene_pth(p)
+    assert np.ndim(f2) == 0 and f2 == 0
+    out_l, out_f, out_lab = scene_io.preprocess_scene(l2, f2, lab2)
+    assert out_f.shape == locs.shape and np.all(out_f == 127.5)
+    out_l, out_f, out_lab = scene_io.preprocess_scene(l2, np.asarray(0), lab2)        # 0-d array form
+    assert out_f.shape == locs.shape and np.all(out_f == 127.5)

@@ -19,6 +19,7 @@ FLAG_VIS_OVERFLOW, FLAG_PAIR_OVERFLOW, FLAG_GRID_RANGE, FLAG_KEY_SENTINEL = 1, 2
 DEPTH_NONE, DEPTH_U16, DEPTH_F64 = 0, 1, 2
 THR_GE_HALF, THR_SIGMOID_GE_HALF, THR_SIGMOID_GT_HALF = 0, 1, 2
 MASK_U8, MASK_F32 = 0, 1
+VOX_AUTO, VOX_MULTI_KERNEL = 0, 1
 POOL_AUTO, POOL_PAIR_LISTS, POOL_ROWS, POOL_MMA = 0, 1, 2, 3
 
 
@@ -45,14 +46,13 @@ PROTOTYPES = {
     "xm3d_project_batch": (C.c_int, [_P, _P, _P, _I32, _I64, _P, _I32, _F64, _I32, _I32, _I32, _F64,
                                      _P, _P, _P, _P, _I64, _P, _P, _P, _P, _SZ, _P, _P]),
     "xm3d_unique_ws_bytes": (_SZ, [_I32, _I64]),
-    "xm3d_unique_batch": (C.c_int, [_P, _P, _I32, _I64, _P, _P, _P, _P, _P, _I32, _P, _SZ, _P, _P]),
+    "xm3d_unique_batch": (C.c_int, [_P, _P, _I32, _I64, _P, _P, _P, _P, _P, _I32, _I32, _P, _SZ, _P, _P]),
     "xm3d_fnv_hash_f64": (C.c_int, [_P, _I64, _I32, _P, _P]),
     "xm3d_ravel_hash_f64": (C.c_int, [_P, _I64, _I32, _P, _P, _SZ, _P]),
     "xm3d_ravel_ws_bytes": (_SZ, [_I32]),
     "xm3d_voxelize_ws_bytes": (_SZ, [_I32, _I64]),
-    "xm3d_set_voxel_path": (None, [_I32, _I32]),
     "xm3d_voxel_path_info": (C.c_int, [_P, _I32, _I64, _P, _P]),
-    "xm3d_voxelize_batch": (C.c_int, [_P, _P, _I32, _I64, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _SZ, _P, _P]),
+    "xm3d_voxelize_batch": (C.c_int, [_P, _I32, _P, _I32, _I64, _P, _P, _P, _P, _P, _I32, _P, _P, _I32, _P, _SZ, _P, _P]),
     "xm3d_mask_words": (_I32, [_I32]),
     "xm3d_gather_ws_bytes": (_SZ, [_I32, _I32, _I32, _I32]),
     "xm3d_gather_masks_batch": (C.c_int, [_P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _I64, _P, _P, _P, _SZ, _P]),

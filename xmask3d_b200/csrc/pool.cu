@@ -437,7 +437,7 @@ bool make_row_tile_map(CUtensorMap *m, const float *base, int64_t rows, int c, i
 bool pool_mma_eligible(const float *feat, int c, const int32_t *row_index, const uint32_t *member, int k, int64_t cap,
                        const float *sum, const float *mean);
 int launch_pool_mma(const float *feat, int c, const uint32_t *member, int words, int n_seg, int k, const int64_t *seg_off,
-                    int64_t cap, float *sum, int32_t *cnt, float *mean, int *work, cudaStream_t stream);
+                    int64_t cap, float *sum, int32_t *cnt, float *mean, int *work, int tune, cudaStream_t stream);
 
 constexpr int PR_THREADS = 512;
 constexpr int PR_WARPS = PR_THREADS / 32;
@@ -663,6 +663,8 @@ extern "C" int xm3d_pool_batch(const float *feat, int32_t c, const int32_t *row_
     // Overlapping masks (the caller's bound allows more memberships than points): every row is read once, by the
     // tensor-core kernel (pool_mma.cu) or the point-major CUDA-core kernel.  cap_pairs is not a limit on these
     // paths (there is no pair list to overrun).
+    const int tune = path >> 8;          // experiments: ring depths of the tensor-core kernel (0 = defaults)
+    path &= 0xff;
     XM3D_REQUIRE(path >= XM3D_POOL_AUTO && path <= XM3D_POOL_MMA, "unknown pooling path");
     const bool out16 = reinterpret_cast<uintptr_t>(sum) % 16 == 0 && (!mean || reinterpret_cast<uintptr_t>(mean) % 16 == 0);
     const bool overlap = member && cap_pairs > cap + 1;
@@ -672,7 +674,7 @@ extern "C" int xm3d_pool_batch(const float *feat, int32_t c, const int32_t *row_
     if (path == XM3D_POOL_ROWS && !rows_ok) { set_error("xm3d_pool_batch: point-major path not eligible"); return XM3D_ERR_UNSUPPORTED; }
     if (path == XM3D_POOL_MMA || (path == XM3D_POOL_AUTO && overlap && mma_ok)) {
         if (g_pool_ev[0]) cudaEventRecord(g_pool_ev[0], stream);
-        const int rc = launch_pool_mma(feat, c, member, I.words, n_seg, k, seg_off, cap, sum, cnt, mean, w.work, stream);
+        const int rc = launch_pool_mma(feat, c, member, I.words, n_seg, k, seg_off, cap, sum, cnt, mean, w.work, tune, stream);
         if (g_pool_ev[1]) cudaEventRecord(g_pool_ev[1], stream);
         return rc;
     }

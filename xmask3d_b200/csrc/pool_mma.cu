@@ -52,6 +52,19 @@ struct PoolMmaParams {
     int raw_stages, conv_stages;
 };
 
+// Instrumented build (-DXM3D_PM_TIMING, scripts/exp_pool_mma.py): per-role wait / work cycles of every CTA
+#ifdef XM3D_PM_TIMING
+__device__ long long *g_pm_dbg = nullptr;
+#define PM_CLK() clock64()
+#define PM_ACC(var, t0) do { var += clock64() - (t0); } while (0)
+#define PM_OUT(role, a, b, c, d) do { if (g_pm_dbg) { long long *o_ = g_pm_dbg + ((size_t)blockIdx.x * 8 + (role)) * 4; \
+    o_[0] += (a); o_[1] += (b); o_[2] += (c); o_[3] += (d); } } while (0)
+#else
+#define PM_CLK() 0ll
+#define PM_ACC(var, t0) do { (void)(t0); } while (0)
+#define PM_OUT(role, a, b, c, d) do { } while (0)
+#endif
+
 template <int N>
 __global__ void __launch_bounds__(32 * (10 + N / 16), 1)
 pool_mma_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P) {
@@ -118,8 +131,11 @@ pool_mma_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P) 
         if (warp == 0) {
             // ===== TMA producer: four 32-channel column blocks of 64 points per tile =====
             if (lane == 0) {
+                long long tw0 = 0, tall = PM_CLK();
                 for (int t = 0; t < ntile; ++t) {
+                    long long c0_ = PM_CLK();
                     mbar_wait(&s_raw_empty[rs], rph ^ 1);
+                    PM_ACC(tw0, c0_);
                     unsigned char *dst = raw_base + (size_t)rs * PM_RAW;
                     mbar_expect_tx(&s_raw_full[rs], PM_RAW);
                     const int y = (int)(a + (int64_t)t * PM_TP);
@@ -128,29 +144,45 @@ pool_mma_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P) 
                         tma_load_2d(dst + cb * PM_CB, &map, sl * PM_SLICE + cb * 32, y, &s_raw_full[rs]);
                     if (++rs == P.raw_stages) { rs = 0; rph ^= 1; }
                 }
+                PM_OUT(0, tw0, 0, PM_CLK() - tall, ntile);
             }
         } else if (warp == 1) {
             // ===== MMA issuer =====
             if (lane == 0) {
                 const uint32_t idesc = make_idesc(PM_SLICE, N, 2, /*A MN-major*/ 1, /*B K-major*/ 0);
+                // descriptors of every stage once (a single thread issues the MMAs: per k-step only the start-address
+                // field moves).  A: two 512-byte atoms of 4 swizzled rows per k-step and column block, blocks 8 KB
+                // apart; B: [N rows][32 points] per k-block, 32 bytes per k-step inside the swizzle row.
+                uint64_t d_hi[PM_MAX_STAGES], d_lo[PM_MAX_STAGES], d_b[PM_MAX_STAGES];
+#pragma unroll
+                for (int q = 0; q < PM_MAX_STAGES; ++q) {
+                    d_hi[q] = make_sw128_desc_ex(raw_base + (size_t)q * PM_RAW, PM_CB, 512, 1);
+                    d_lo[q] = make_sw128_desc_ex(lo_base + (size_t)q * PM_RAW, PM_CB, 512, 1);
+                    d_b[q] = make_sw128_desc_ex(b_base + (size_t)q * B_BYTES, 0, 1024);
+                }
+                long long tw0 = 0, tw1 = 0, tw2 = 0, tall = PM_CLK();
                 for (int t = 0; t < ntile; ++t) {
+                    long long c0_ = PM_CLK();
                     mbar_wait(&s_raw_full[rs], rph);
+                    PM_ACC(tw0, c0_); c0_ = PM_CLK();
                     mbar_wait(&s_conv_full[cs], cph);
+                    PM_ACC(tw1, c0_); c0_ = PM_CLK();
                     mbar_wait(&s_tmem_free[buf], bph ^ 1);
+                    PM_ACC(tw2, c0_);
                     tc_fence_after();
-                    const unsigned char *hi = raw_base + (size_t)rs * PM_RAW;
-                    const unsigned char *lo = lo_base + (size_t)cs * PM_RAW;
-                    const unsigned char *bt = b_base + (size_t)cs * B_BYTES;
+                    uint64_t a_hi = d_hi[0], a_lo = d_lo[0], bd = d_b[0];
+#pragma unroll
+                    for (int q = 1; q < PM_MAX_STAGES; ++q) {
+                        if (rs == q) a_hi = d_hi[q];
+                        if (cs == q) { a_lo = d_lo[q]; bd = d_b[q]; }
+                    }
                     const uint32_t d = tmem_base + (uint32_t)(buf * N);
 #pragma unroll
                     for (int ks = 0; ks < PM_TP / 8; ++ks) {
-                        // A: 8 points = two 512-byte atoms of 4 swizzled rows per column block; blocks 8 KB apart
-                        const uint64_t a_hi = make_sw128_desc_ex(hi + ks * 1024, PM_CB, 512, 1);
-                        const uint64_t a_lo = make_sw128_desc_ex(lo + ks * 1024, PM_CB, 512, 1);
-                        // B: [N rows][32 points] per k-block, 32 bytes per k-step inside the swizzle row
-                        const uint64_t bd = make_sw128_desc_ex(bt + (ks >> 2) * (N * 128) + (ks & 3) * 32, 0, 1024);
-                        umma_tf32(d, a_hi, bd, idesc, ks ? 1u : 0u);
-                        umma_tf32(d, a_lo, bd, idesc, 1u);
+                        const uint64_t ka = (uint64_t)((ks * 1024) >> 4);
+                        const uint64_t kb2 = (uint64_t)(((ks >> 2) * (N * 128) + (ks & 3) * 32) >> 4);
+                        umma_tf32(d, a_hi + ka, bd + kb2, idesc, ks ? 1u : 0u);
+                        umma_tf32(d, a_lo + ka, bd + kb2, idesc, 1u);
                     }
                     umma_commit(&s_raw_empty[rs]);
                     umma_commit(&s_conv_empty[cs]);
@@ -159,13 +191,18 @@ pool_mma_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P) 
                     if (++cs == P.conv_stages) { cs = 0; cph ^= 1; }
                     if (++buf == 2) { buf = 0; bph ^= 1; }
                 }
+                PM_OUT(1, tw0, tw1, tw2, PM_CLK() - tall);
             }
         } else if (warp < 6) {
             // ===== converters: lo = x - hi (hi = the raw tile as the tensor core reads it) =====
             const int t0 = tid - 64;
+            long long tw0 = 0, tw1 = 0, tall = PM_CLK();
             for (int t = 0; t < ntile; ++t) {
+                long long c0_ = PM_CLK();
                 mbar_wait(&s_raw_full[rs], rph);
+                PM_ACC(tw0, c0_); c0_ = PM_CLK();
                 mbar_wait(&s_conv_empty[cs], cph ^ 1);
+                PM_ACC(tw1, c0_);
                 uint4 *raw = reinterpret_cast<uint4 *>(raw_base + (size_t)rs * PM_RAW);
                 uint4 *lo = reinterpret_cast<uint4 *>(lo_base + (size_t)cs * PM_RAW);
                 const int rows_valid = min(PM_TP, n - t * PM_TP);
@@ -192,6 +229,7 @@ pool_mma_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P) 
                 if (++rs == P.raw_stages) { rs = 0; rph ^= 1; }
                 if (++cs == P.conv_stages) { cs = 0; cph ^= 1; }
             }
+            if (t0 == 0) PM_OUT(2, tw0, tw1, PM_CLK() - tall, 0);
         } else if (warp < 10) {
             // ===== builders: membership bits of the tile's points -> 0.0f / 1.0f, K-major swizzled =====
             const int t0 = tid - 192;
@@ -201,8 +239,9 @@ pool_mma_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P) 
             int cntreg[WPT];
 #pragma unroll
             for (int j = 0; j < WPT; ++j) cntreg[j] = 0;
-            for (int t = 0; t < ntile; ++t) {
-                uint32_t w[WPT];
+            // membership words are fetched two tiles ahead: a tile's budget (~1400 cycles at the HBM rate) is shorter
+            // than one loaded global-memory latency
+            auto load_words = [&](int t, uint32_t (&w)[WPT]) {
                 const int pt = t * PM_TP + p;
 #pragma unroll
                 for (int j = 0; j < WPT; ++j) {
@@ -215,7 +254,16 @@ pool_mma_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P) 
                     }
                     w[j] = x;
                 }
+            };
+            uint32_t w[WPT], w1[WPT], w2[WPT];
+            long long tw0 = 0, tall = PM_CLK();
+            load_words(0, w);
+            load_words(1, w1);
+            for (int t = 0; t < ntile; ++t) {
+                load_words(t + 2, w2);
+                long long c0_ = PM_CLK();
                 mbar_wait(&s_conv_empty[cs], cph ^ 1);
+                PM_ACC(tw0, c0_);
                 unsigned char *bt = b_base + (size_t)cs * B_BYTES + kb * (N * 128) + ((kk & 3) << 2);
 #pragma unroll
                 for (int j = 0; j < WPT; ++j) {
@@ -231,11 +279,14 @@ pool_mma_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P) 
                 fence_proxy_async();
                 mbar_arrive(&s_conv_full[cs]);
                 if (++cs == P.conv_stages) { cs = 0; cph ^= 1; }
+#pragma unroll
+                for (int j = 0; j < WPT; ++j) { w[j] = w1[j]; w1[j] = w2[j]; }
             }
 #pragma unroll
             for (int j = 0; j < WPT; ++j) {
                 if (cntreg[j]) atomicAdd(&s_cnt[(h * WPT + j) * 32 + lane], cntreg[j]);     // integer: order independent
             }
+            if (t0 == 0) PM_OUT(3, tw0, 0, PM_CLK() - tall, 0);
             asm volatile("bar.sync 1, %0;" ::"n"(PM_BUILD + EPI_THREADS) : "memory");        // counts -> epilogue warps
         } else {
             // ===== epilogue: tile results out of TMEM, added in float32 registers =====
@@ -245,8 +296,11 @@ pool_mma_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P) 
             float acc[64];
 #pragma unroll
             for (int j = 0; j < 64; ++j) acc[j] = 0.f;
+            long long tw0 = 0, tall = PM_CLK();
             for (int t = 0; t < ntile; ++t) {
+                long long c0_ = PM_CLK();
                 mbar_wait(&s_tile_done[buf], bph);
+                PM_ACC(tw0, c0_);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * N + half * 64);
 #pragma unroll
@@ -265,6 +319,7 @@ pool_mma_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P) 
                 mbar_arrive(&s_tmem_free[buf]);
                 if (++buf == 2) { buf = 0; bph ^= 1; }
             }
+            if (tid == 320) PM_OUT(4, tw0, 0, PM_CLK() - tall, 0);
             asm volatile("bar.sync 1, %0;" ::"n"(PM_BUILD + EPI_THREADS) : "memory");        // the builders' counts
             const int ch = sl * PM_SLICE + lg * 32 + lane;
 #pragma unroll
@@ -292,6 +347,12 @@ pool_mma_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P) 
     (void)THREADS;
 }
 
+#ifdef XM3D_PM_TIMING
+extern "C" __attribute__((visibility("default"))) int xm3d_pool_mma_debug(void *dev_buf) {
+    return (int)cudaMemcpyToSymbol(g_pm_dbg, &dev_buf, sizeof(void *));
+}
+#endif
+
 // Host side -----------------------------------------------------------------------------------------
 bool pool_mma_eligible(const float *feat, int c, const int32_t *row_index, const uint32_t *member, int k, int64_t cap,
                        const float *sum, const float *mean) {
@@ -301,7 +362,7 @@ bool pool_mma_eligible(const float *feat, int c, const int32_t *row_index, const
 }
 
 int launch_pool_mma(const float *feat, int c, const uint32_t *member, int words, int n_seg, int k, const int64_t *seg_off,
-                    int64_t cap, float *sum, int32_t *cnt, float *mean, int *work, cudaStream_t stream) {
+                    int64_t cap, float *sum, int32_t *cnt, float *mean, int *work, int tune, cudaStream_t stream) {
     CUtensorMap map;
     memset(&map, 0, sizeof(map));
     // rows past `cap` are zero-filled by TMA; rows past a segment are zeroed by the converters
@@ -320,12 +381,16 @@ int launch_pool_mma(const float *feat, int c, const uint32_t *member, int words,
         cudaFuncSetAttribute(pool_mma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
         cudaFuncSetAttribute(pool_mma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     }
+    const int t_rs = tune & 15, t_cs = (tune >> 4) & 15;
+    const int bb = (k <= 64 ? 64 : 128) * PM_TP * 4;
+    const bool tuned = t_rs >= 1 && t_rs <= PM_MAX_STAGES && t_cs >= 1 && t_cs <= PM_MAX_STAGES &&
+                       (size_t)t_rs * PM_RAW + (size_t)t_cs * (PM_RAW + bb) + 1024 <= 226 * 1024;
     if (k <= 64) {
-        P.raw_stages = 3; P.conv_stages = 2;
+        P.raw_stages = tuned ? t_rs : 3; P.conv_stages = tuned ? t_cs : 2;
         const size_t smem = (size_t)P.raw_stages * PM_RAW + (size_t)P.conv_stages * (PM_RAW + 64 * PM_TP * 4) + 1024;
         pool_mma_kernel<64><<<grid, 32 * (10 + 4), smem, stream>>>(map, P);
     } else {
-        P.raw_stages = 2; P.conv_stages = 2;
+        P.raw_stages = tuned ? t_rs : 2; P.conv_stages = tuned ? t_cs : 2;
         const size_t smem = (size_t)P.raw_stages * PM_RAW + (size_t)P.conv_stages * (PM_RAW + 128 * PM_TP * 4) + 1024;
         pool_mma_kernel<128><<<grid, 32 * (10 + 8), smem, stream>>>(map, P);
     }

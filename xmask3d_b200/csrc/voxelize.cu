@@ -58,7 +58,7 @@ constexpr int FV_THREADS = XM3D_FV_THREADS;
 constexpr int FV_TABLE = 16384;           // 64-bit key slots per unit (128 KB)
 constexpr int FV_MU = 8704;               // unique keys per unit, at most (load factor <= 0.53)
 constexpr int FV_UNIT_PTS = 7000;         // points per unit the plan aims at (24 % headroom to FV_MU)
-constexpr int FV_UNIT_PTS_MIN = 64;       // smallest value xm3d_set_voxel_path accepts (sizes the unit tables)
+constexpr int FV_UNIT_PTS_MIN = 64;       // smallest unit size a call may ask for (sizes the unit tables)
 constexpr int FV_PMAX = 32;               // units per segment, at most (224 k points)
 constexpr int FV_OUT_BATCH = 6;             // gathers of voxel coordinates in flight per thread (one round for M <= 6144)
 constexpr int FV_PROBE_MAX = 2048;        // a longer probe sequence means the table is (nearly) full: give up
@@ -67,8 +67,6 @@ constexpr int FV_NS = 1024;               // sample keys for the key-range split
 constexpr size_t FV_SMEM = (size_t)FV_TABLE * 8 + (size_t)FV_MU * 4 + (size_t)FV_MU * 2 + (size_t)FV_MU * 4 +
                            (size_t)FV_NS * 8 + (size_t)(FV_NS + 32) * 4;
 
-static int g_vox_mode = 0;                // 0: fast path when eligible, 1: multi-kernel path only
-static int g_vox_unit_pts = FV_UNIT_PTS;
 
 struct __align__(16) Slot {
     unsigned long long key;
@@ -107,10 +105,19 @@ __device__ __forceinline__ unsigned long long f64_to_u64_numpy(double d) {
     return (unsigned long long)d;
 }
 
+// Point coordinates as the caller holds them: float32 (ScanNet .pth) or float64 (what the reference's
+// ElasticDistortion returns, dataset/augmentation.py:171 — `homo_coords` then stays float64, voxelizer.py:110-112).
+struct Xyz {
+    const float *f;
+    const double *d;
+    __host__ __device__ explicit operator bool() const { return f != nullptr || d != nullptr; }
+};
+
 // floor([x y z 1] @ RT.T[:, :3]) for one point: voxelizer.py:110-113
-__device__ __forceinline__ void grid_of(const float *__restrict__ p, const double *__restrict__ rt,
-                                        double out[3]) {
-    const double x = (double)p[0], y = (double)p[1], z = (double)p[2];
+__device__ __forceinline__ void grid_of(const Xyz src, int64_t i, const double *__restrict__ rt, double out[3]) {
+    double x, y, z;
+    if (src.d) { x = src.d[i * 3]; y = src.d[i * 3 + 1]; z = src.d[i * 3 + 2]; }
+    else { x = (double)src.f[i * 3]; y = (double)src.f[i * 3 + 1]; z = (double)src.f[i * 3 + 2]; }
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
         const double *r = rt + 4 * j;
@@ -123,11 +130,11 @@ __device__ __forceinline__ void grid_of(const float *__restrict__ p, const doubl
 }
 
 // FNV key of point i of segment s (voxelizer.py:115-121: floor(grid - min) -> uint64 -> FNV-1)
-__device__ __forceinline__ unsigned long long point_key(const float *__restrict__ xyz, int64_t i, int s,
+__device__ __forceinline__ unsigned long long point_key(const Xyz xyz, int64_t i, int s,
                                                         const double *__restrict__ rt,
                                                         const int *__restrict__ grid_min) {
     double f[3];
-    grid_of(xyz + i * 3, rt + 12 * s, f);
+    grid_of(xyz, i, rt + 12 * s, f);
     unsigned long long w[3];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
@@ -252,6 +259,7 @@ vox_plan_kernel(const int64_t *__restrict__ seg_off, int n_seg, int64_t cap, int
         tbl_off[n_seg] = s_carry[0]; spl_off[n_seg] = s_carry[1]; unit_off[n_seg] = (int)s_carry[2];
         ctl[0] = (s_slow || s_carry[2] > units_max) ? 1 : 0;
         ctl[1] = 0;
+        ctl[2] = 0;                               // unit ticket counter of vox_fast_kernel
     }
 }
 
@@ -274,7 +282,7 @@ vox_clear_kernel(Slot *__restrict__ tbl, const int64_t *__restrict__ tbl_off, in
 // ---- min pass -----------------------------------------------------------------------------
 // (a 4-points-per-thread variant of this kernel was measured 2x slower: 97 vs 47 us)
 __global__ void __launch_bounds__(VOX_THREADS)
-vox_min_kernel(const float *__restrict__ xyz, const int64_t *__restrict__ seg_off, int n_seg,
+vox_min_kernel(const Xyz xyz, const int64_t *__restrict__ seg_off, int n_seg,
                const int64_t *__restrict__ total_eff, const double *__restrict__ rt, int *__restrict__ grid_min,
                int4 *__restrict__ pgrid, int *status) {
     __shared__ int s_min[VOX_THREADS / 32][3];
@@ -289,7 +297,7 @@ vox_min_kernel(const float *__restrict__ xyz, const int64_t *__restrict__ seg_of
     int g[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff};
     if (valid) {
         double f[3];
-        grid_of(xyz + i * 3, rt + 12 * s, f);
+        grid_of(xyz, i, rt + 12 * s, f);
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
             if (!(f[j] > -(double)GRID_LIMIT && f[j] < (double)GRID_LIMIT)) {
@@ -364,7 +372,7 @@ __device__ __forceinline__ void bitonic_smem(K *k, int n /*pow2*/) {
 // KEY_SRC 0: keys from xyz through the transform (voxelize); 1: keys given (unique_batch)
 template <int KEY_SRC>
 __global__ void __launch_bounds__(1024)
-vox_sample_kernel(const float *__restrict__ xyz, const unsigned long long *__restrict__ keys_in,
+vox_sample_kernel(const Xyz xyz, const unsigned long long *__restrict__ keys_in,
                   const int64_t *__restrict__ seg_off, const int64_t *__restrict__ total_eff,
                   const double *__restrict__ rt, const int *__restrict__ grid_min,
                   const int64_t *__restrict__ spl_off, unsigned long long *__restrict__ spl, int *__restrict__ hist, const int *__restrict__ ctl) {
@@ -392,7 +400,7 @@ vox_sample_kernel(const float *__restrict__ xyz, const unsigned long long *__res
 // ---- insert pass --------------------------------------------------------------------------
 template <int KEY_SRC>
 __global__ void __launch_bounds__(VOX_THREADS)
-vox_insert_kernel(const float *__restrict__ xyz, const unsigned long long *__restrict__ keys_in,
+vox_insert_kernel(const Xyz xyz, const unsigned long long *__restrict__ keys_in,
                   const int64_t *__restrict__ seg_off, int n_seg, const int64_t *__restrict__ total_eff,
                   const double *__restrict__ rt, const int *__restrict__ grid_min, Slot *__restrict__ tbl,
                   const int64_t *__restrict__ tbl_off, const int64_t *__restrict__ spl_off,
@@ -630,7 +638,7 @@ vox_inverse_kernel(const int64_t *__restrict__ seg_off, int n_seg, const int64_t
 // ---- voxel coordinates in unique order: grid(first occurrence) - min ------------------------
 __global__ void __launch_bounds__(VOX_THREADS)
 vox_coords_kernel(const int64_t *__restrict__ seg_off, int n_seg, const int64_t *__restrict__ uniq_off,
-                  const int *__restrict__ first, const float *__restrict__ xyz, const double *__restrict__ rt,
+                  const int *__restrict__ first, const Xyz xyz, const double *__restrict__ rt,
                   const int *__restrict__ grid_min, int *__restrict__ voxel_xyz, const int *__restrict__ ctl) {
     if (!(ctl[0] | ctl[1])) return;              // the fast path produced the result
     __shared__ int s_pair[2];
@@ -641,7 +649,7 @@ vox_coords_kernel(const int64_t *__restrict__ seg_off, int n_seg, const int64_t 
     const int s = block_segment(uniq_off, n_seg, total, o, valid, s_pair).s;
     if (!valid) return;
     double g[3];
-    grid_of(xyz + (seg_off[s] + first[o]) * 3, rt + 12 * s, g);
+    grid_of(xyz, seg_off[s] + first[o], rt + 12 * s, g);
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
         if (!(g[j] > -(double)GRID_LIMIT && g[j] < (double)GRID_LIMIT)) g[j] = 0.0;
@@ -714,7 +722,13 @@ vox_fast_kernel(int4 *pgrid, const unsigned long long *__restrict__ keys_in,
     __shared__ int s_wsum[32];
 
     if (ctl[0]) return;                           // not eligible: the multi-kernel path runs
-    const int u = blockIdx.x;
+    // The unit id is a TICKET, not blockIdx.x: the look-back below waits for the units t < u, and CUDA does not
+    // promise to dispatch blocks in index order.  With a ticket a waiting CTA only ever depends on CTAs that
+    // have already started (CUB's dynamic tile id).
+    __shared__ int s_unit;
+    if (threadIdx.x == 0) s_unit = atomicAdd(&ctl[2], 1);
+    __syncthreads();
+    const int u = s_unit;
     const int U = unit_off[n_seg];
     if (u >= U) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1128,10 +1142,10 @@ static VoxWs carve_vox(void *ws, int n_seg, int64_t cap, size_t *bytes) {
     return w;
 }
 
-static int run_unique(const float *xyz, const unsigned long long *keys, const int64_t *seg_off, int n_seg,
+static int run_unique(const Xyz xyz, const unsigned long long *keys, const int64_t *seg_off, int n_seg,
                       int64_t cap, const double *rt, int *m, int64_t *uniq_off, int *first, int *counts,
                       int *inverse, int collate, int *voxel_xyz, int *grid_min_out, void *ws, size_t ws_bytes,
-                      int *status, cudaStream_t stream, const char *who) {
+                      int *status, int path, cudaStream_t stream, const char *who) {
     size_t need = 0;
     VoxWs w = carve_vox(ws, n_seg, cap, &need);
     if (ws_bytes < need) {
@@ -1141,11 +1155,14 @@ static int run_unique(const float *xyz, const unsigned long long *keys, const in
     int *gmin = grid_min_out ? grid_min_out : w.grid_min;
     const unsigned blocks = (unsigned)((cap + VOX_THREADS - 1) / VOX_THREADS);
     // fast path: one shared-memory CTA per unit; the multi-kernel path below is gated on w.ctl
-    const int unit_pts = g_vox_unit_pts;
+    // path: bits 0-7 = XM3D_VOX_AUTO / XM3D_VOX_MULTI_KERNEL, bits 8.. = points per key-range unit (0 = default)
+    const int req_pts = path >> 8;
+    const int unit_pts = req_pts <= 0 ? FV_UNIT_PTS : (req_pts < FV_UNIT_PTS_MIN ? FV_UNIT_PTS_MIN
+                                                      : (req_pts > FV_UNIT_PTS ? FV_UNIT_PTS : req_pts));
     int64_t units_max64 = cap / unit_pts + n_seg;
     if (units_max64 > w.units_cap) units_max64 = w.units_cap;
     const int units_max = (int)units_max64;
-    const int force_slow = (g_vox_mode == 1 || counts != nullptr) ? 1 : 0;
+    const int force_slow = ((path & 0xff) == XM3D_VOX_MULTI_KERNEL || counts != nullptr) ? 1 : 0;
     static std::atomic<uint64_t> smem_set{0};
     if (first_use_on_device(&smem_set)) {
         cudaFuncSetAttribute(vox_fast_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FV_SMEM);
@@ -1184,11 +1201,11 @@ static int run_unique(const float *xyz, const unsigned long long *keys, const in
             count_launches(1);
         }
     } else {
-        vox_sample_kernel<1><<<n_seg, 1024, 0, stream>>>(nullptr, keys, seg_off, w.total_eff, nullptr, nullptr, w.spl_off,
+        vox_sample_kernel<1><<<n_seg, 1024, 0, stream>>>(Xyz{nullptr, nullptr}, keys, seg_off, w.total_eff, nullptr, nullptr, w.spl_off,
                                                         w.spl, w.hist, w.ctl);
         count_launches(1);
         if (blocks) {
-            vox_insert_kernel<1><<<blocks, VOX_THREADS, 0, stream>>>(nullptr, keys, seg_off, n_seg, w.total_eff, nullptr,
+            vox_insert_kernel<1><<<blocks, VOX_THREADS, 0, stream>>>(Xyz{nullptr, nullptr}, keys, seg_off, n_seg, w.total_eff, nullptr,
                                                                      nullptr, w.tbl, w.tbl_off, w.spl_off, w.spl, w.hist,
                                                                      w.pslot, w.uniq, w.ukey, w.ubkt, w.upos, m, status, w.ctl);
             count_launches(1);
@@ -1219,12 +1236,6 @@ static int run_unique(const float *xyz, const unsigned long long *keys, const in
 
 using namespace xm3d;
 
-extern "C" void xm3d_set_voxel_path(int32_t mode, int32_t unit_pts) {
-    g_vox_mode = mode == 1 ? 1 : 0;
-    g_vox_unit_pts = unit_pts <= 0 ? FV_UNIT_PTS : (unit_pts < FV_UNIT_PTS_MIN ? FV_UNIT_PTS_MIN
-                                                    : (unit_pts > FV_UNIT_PTS ? FV_UNIT_PTS : unit_pts));
-}
-
 extern "C" int xm3d_voxel_path_info(const void *ws, int32_t n_seg, int64_t cap, int32_t *ctl_host,
                                     xm3d_stream_t stream_) {
     XM3D_REQUIRE(ws && ctl_host && n_seg > 0 && cap >= 0, "bad arguments");
@@ -1252,25 +1263,26 @@ extern "C" size_t xm3d_voxelize_ws_bytes(int32_t n_seg, int64_t cap) { return xm
 
 extern "C" int xm3d_unique_batch(const uint64_t *keys, const int64_t *seg_off, int32_t n_seg, int64_t cap,
                                  int32_t *m, int64_t *uniq_off, int32_t *first, int32_t *counts,
-                                 int32_t *inverse, int32_t collate, void *ws, size_t ws_bytes, int32_t *status,
-                                 xm3d_stream_t stream) {
+                                 int32_t *inverse, int32_t collate, int32_t path, void *ws, size_t ws_bytes,
+                                 int32_t *status, xm3d_stream_t stream) {
     XM3D_REQUIRE(n_seg > 0 && cap >= 0, "bad sizes");
     XM3D_REQUIRE(keys && seg_off && m && uniq_off && first && ws, "null pointer");
     XM3D_REQUIRE(cap < (int64_t)1 << 31, "cap must fit int32");
-    return run_unique(nullptr, reinterpret_cast<const unsigned long long *>(keys), seg_off, n_seg, cap, nullptr, m,
-                      uniq_off, first, counts, inverse, collate, nullptr, nullptr, ws, ws_bytes, status,
+    return run_unique(Xyz{nullptr, nullptr}, reinterpret_cast<const unsigned long long *>(keys), seg_off, n_seg, cap,
+                      nullptr, m, uniq_off, first, counts, inverse, collate, nullptr, nullptr, ws, ws_bytes, status, path,
                       static_cast<cudaStream_t>(stream), "xm3d_unique_batch");
 }
 
-extern "C" int xm3d_voxelize_batch(const float *xyz, const int64_t *seg_off, int32_t n_seg, int64_t cap,
+extern "C" int xm3d_voxelize_batch(const void *xyz, int32_t xyz_f64, const int64_t *seg_off, int32_t n_seg, int64_t cap,
                                    const double *rt, int32_t *m, int64_t *uniq_off, int32_t *first,
                                    int32_t *inverse, int32_t collate, int32_t *voxel_xyz, int32_t *grid_min,
-                                   void *ws, size_t ws_bytes, int32_t *status, xm3d_stream_t stream) {
+                                   int32_t path, void *ws, size_t ws_bytes, int32_t *status, xm3d_stream_t stream) {
     XM3D_REQUIRE(n_seg > 0 && cap >= 0, "bad sizes");
     XM3D_REQUIRE(xyz && seg_off && rt && m && uniq_off && first && ws, "null pointer");
     XM3D_REQUIRE(cap < (int64_t)1 << 31, "cap must fit int32");
-    return run_unique(xyz, nullptr, seg_off, n_seg, cap, rt, m, uniq_off, first, nullptr, inverse, collate,
-                      voxel_xyz, grid_min, ws, ws_bytes, status, static_cast<cudaStream_t>(stream),
+    const Xyz src = xyz_f64 ? Xyz{nullptr, static_cast<const double *>(xyz)} : Xyz{static_cast<const float *>(xyz), nullptr};
+    return run_unique(src, nullptr, seg_off, n_seg, cap, rt, m, uniq_off, first, nullptr, inverse, collate,
+                      voxel_xyz, grid_min, ws, ws_bytes, status, path, static_cast<cudaStream_t>(stream),
                       "xm3d_voxelize_batch");
 }
 

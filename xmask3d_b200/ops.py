@@ -144,10 +144,11 @@ class Unique:
     cap: Optional[int] = None
 
 
-def set_voxel_path(mode: int = 0, unit_pts: int = 0) -> None:
-    """0: shared-memory units when every segment fits (default), 1: multi-kernel path only;
-    unit_pts < 7000 forces several key-range units per segment (tests)."""
-    L.lib().xm3d_set_voxel_path(int(mode), int(unit_pts))
+def _vox_path(mode: int = 0, unit_pts: int = 0) -> int:
+    """Per-call path word of xm3d_unique_batch / xm3d_voxelize_batch: mode 0 = shared-memory units when every
+    segment fits (default), 1 = multi-kernel path only; unit_pts < 7000 forces several key-range units per
+    segment (tests)."""
+    return (int(mode) & 0xff) | (max(int(unit_pts), 0) << 8)
 
 
 def voxel_path_info(u: "Unique"):
@@ -160,7 +161,7 @@ def voxel_path_info(u: "Unique"):
 
 
 def unique_batch(keys: torch.Tensor, seg_off: torch.Tensor, cap: Optional[int] = None, collate: bool = False,
-                 want_counts: bool = False) -> Unique:
+                 want_counts: bool = False, mode: int = 0, unit_pts: int = 0) -> Unique:
     """np.unique(keys, return_index, return_inverse[, return_counts]) per segment.
     keys: int64/uint64-viewed CUDA tensor; seg_off int64 [n_seg+1] CUDA."""
     _require_cuda()
@@ -178,18 +179,19 @@ def unique_batch(keys: torch.Tensor, seg_off: torch.Tensor, cap: Optional[int] =
     status = torch.zeros(1, dtype=torch.int32, device=dev)
     ws = _ws(L.lib().xm3d_unique_ws_bytes(n_seg, cap), dev)
     L.check(L.lib().xm3d_unique_batch(_ptr(keys), _ptr(seg_off), n_seg, cap, _ptr(m), _ptr(uniq_off), _ptr(first),
-                                      _ptr(counts), _ptr(inverse), int(collate), _ptr(ws), ws.numel(),
-                                      _ptr(status), _stream()))
+                                      _ptr(counts), _ptr(inverse), int(collate), _vox_path(mode, unit_pts), _ptr(ws),
+                                      ws.numel(), _ptr(status), _stream()))
     return Unique(m, uniq_off, first, inverse, counts, status, ws=ws, cap=cap)
 
 
 def voxelize_batch(xyz: torch.Tensor, seg_off: torch.Tensor, rt: torch.Tensor, cap: Optional[int] = None,
-                   collate: bool = False, ws: Optional[torch.Tensor] = None) -> Unique:
-    """xyz float32 [cap,3] CUDA (segments concatenated); rt float64 [n_seg,3,4] (rows 0..2 of the
+                   collate: bool = False, ws: Optional[torch.Tensor] = None, mode: int = 0, unit_pts: int = 0) -> Unique:
+    """xyz float32 or float64 [cap,3] CUDA (segments concatenated; float64 = the augmented training path, where
+    ElasticDistortion hands the voxelizer float64 coordinates); rt float64 [n_seg,3,4] (rows 0..2 of the
     rigid transformation, reference dataset/voxelizer.py:104-108)."""
     _require_cuda()
     dev = xyz.device
-    xyz = _dev_contig(xyz, torch.float32)
+    xyz = _dev_contig(xyz, torch.float64 if xyz.dtype == torch.float64 else torch.float32)
     seg_off = _dev_contig(seg_off, torch.int64)
     rt = _dev_contig(rt, torch.float64)
     n_seg = seg_off.numel() - 1
@@ -205,9 +207,10 @@ def voxelize_batch(xyz: torch.Tensor, seg_off: torch.Tensor, rt: torch.Tensor, c
     need = L.lib().xm3d_voxelize_ws_bytes(n_seg, cap)
     if ws is None or ws.numel() < need:
         ws = _ws(need, dev)
-    L.check(L.lib().xm3d_voxelize_batch(_ptr(xyz), _ptr(seg_off), n_seg, cap, _ptr(rt), _ptr(m), _ptr(uniq_off),
-                                        _ptr(first), _ptr(inverse), int(collate), _ptr(voxel), _ptr(gmin),
-                                        _ptr(ws), ws.numel(), _ptr(status), _stream()))
+    L.check(L.lib().xm3d_voxelize_batch(_ptr(xyz), int(xyz.dtype == torch.float64), _ptr(seg_off), n_seg, cap, _ptr(rt),
+                                        _ptr(m), _ptr(uniq_off), _ptr(first), _ptr(inverse), int(collate), _ptr(voxel),
+                                        _ptr(gmin), _vox_path(mode, unit_pts), _ptr(ws), ws.numel(), _ptr(status),
+                                        _stream()))
     return Unique(m, uniq_off, first, inverse, None, status, voxel, gmin, ws=ws, cap=cap)
 
 
@@ -306,7 +309,7 @@ def _popcount32(x: torch.Tensor) -> torch.Tensor:
 def pool(feat: torch.Tensor, seg_off: torch.Tensor, k: int, member: Optional[torch.Tensor] = None,
          label: Optional[torch.Tensor] = None, row_index: Optional[torch.Tensor] = None,
          cap: Optional[int] = None, cap_pairs: Optional[int] = None, want_mean: bool = True,
-         ws: Optional[torch.Tensor] = None, status: Optional[torch.Tensor] = None, path: str = "auto"):
+         ws: Optional[torch.Tensor] = None, status: Optional[torch.Tensor] = None, path: str = "auto", _tune: int = 0):
     """Segmented mean pooling.  feat float32 [rows,c]; member int32 [cap,words] or label int32 [cap].
     cap_pairs: bound on the number of (point, mask) memberships (None: labels -> cap, members ->
     counted on the device, which costs one host sync).
@@ -338,7 +341,7 @@ def pool(feat: torch.Tensor, seg_off: torch.Tensor, k: int, member: Optional[tor
     if ws is None or ws.numel() < need:
         ws = _ws(need, dev)
     L.check(L.lib().xm3d_pool_batch(_ptr(feat), c, _ptr(row_index), _ptr(member), _ptr(label), n_seg, int(k),
-                                    _ptr(seg_off), cap, cap_pairs, POOL_PATH[path], _ptr(s), _ptr(cnt), _ptr(mean),
+                                    _ptr(seg_off), cap, cap_pairs, POOL_PATH[path] | (int(_tune) << 8), _ptr(s), _ptr(cnt), _ptr(mean),
                                     _ptr(ws), ws.numel(), _ptr(status), _stream()))
     return s, cnt, mean
 

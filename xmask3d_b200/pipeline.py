@@ -119,6 +119,7 @@ class CorrespondencePipeline:
         the visible-point indices (the pred_3d[inds_reconstruct] pattern of models/xmask3d.py:152).
         Returns a dict of device tensors."""
         overlap = self.overlap and times is None
+        self._side_status.zero_()                    # the pair-overflow flag describes THIS pass, not an earlier one
         if times is not None:
             times.mark("start")
         if overlap:

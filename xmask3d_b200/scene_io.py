@@ -37,7 +37,7 @@ def preprocess_scene(locs, feats, labels):
     labels = np.array(labels, copy=True)
     labels[labels == -100] = 255
     labels = labels.astype(np.uint8)
-    if np.isscalar(feats) and feats == 0:
+    if np.ndim(feats) == 0 and feats == 0:         # scalar (or 0-d array) 0: the scene has no colours
         feats = np.zeros_like(locs)
     feats = (feats + 1.0) * 127.5
     return locs, feats, labels
@@ -105,7 +105,13 @@ class SceneCache:
 def read_scene_pth(path: str) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
     """(locs_in, feats_in, labels_in) of dataset/data_loader.py:92, as numpy arrays."""
     locs, feats, labels = torch.load(path, weights_only=False)
-    return np.asarray(locs), np.asarray(feats), np.asarray(labels)
+    # a scalar 0 colour entry ("no colours", dataset/point_loader.py:143-145) must stay a Python / numpy scalar so
+    # that preprocess_scene's np.isscalar test still fires; np.asarray would turn it into a 0-d array
+    if np.ndim(feats) == 0:
+        feats = feats.item() if hasattr(feats, "item") else feats
+    else:
+        feats = np.asarray(feats)
+    return np.asarray(locs), feats, np.asarray(labels)
 
 
 def write_scene_pth(path: str, locs: np.ndarray, feats: np.ndarray, labels: np.ndarray) -> None:

@@ -104,16 +104,17 @@ class Voxelizer:
 
 def voxelize_views(coords_list, rigid_transformations, device=None):
     """Batched core of Voxelizer.voxelize: for every (points [n_i,3] float32, 4x4 float64 matrix)
-    returns (coords_aug float64 [M_i,3], inds int64 [M_i], inds_reconstruct int64 [n_i]) —
+    (float64 coordinates are accepted as well) returns (coords_aug float64 [M_i,3], inds int64 [M_i], inds_reconstruct int64 [n_i]) —
     the values the reference computes at dataset/voxelizer.py:110-122."""
     ops._require_cuda()
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
     n = [int(c.shape[0]) for c in coords_list]
     off = np.concatenate([[0], np.cumsum(n)]).astype(np.int64)
-    for c in coords_list:
-        if c.dtype != np.float32:
-            raise TypeError("voxelize_views expects float32 coordinates (ScanNet .pth coords are float32; "
-                            "the reference widens them to float64 inside the matmul)")
+    # float32 (ScanNet .pth) stays float32 — the kernel widens it exactly like numpy's matmul promotion; anything else
+    # (float64 after ElasticDistortion, dataset/augmentation.py:171; integer coordinates) goes through float64, the
+    # dtype numpy computes `homo_coords @ rigid_transformation.T` in for those inputs (voxelizer.py:110-113)
+    if not all(c.dtype == np.float32 for c in coords_list):
+        coords_list = [np.asarray(c, np.float64) for c in coords_list]
     xyz = torch.from_numpy(np.ascontiguousarray(np.concatenate(coords_list, 0))).to(dev)
     rt = torch.from_numpy(np.ascontiguousarray(np.stack([np.asarray(r, np.float64)[:3, :4]
                                                          for r in rigid_transformations]))).to(dev)
