@@ -220,6 +220,24 @@ XM3D_API int xm3d_scatter_batch(const uint32_t *member, const int32_t *label, in
                        const int64_t *seg_off, int64_t cap, const float *emb, int32_t c, float *out,
                        float *counter, xm3d_stream_t stream);
 
+/* loss_contra mask selection (models/utils/criterion.py:80-146) for every scene of a batch, no host round trip:
+ *   member      [cap, words] = sigmoid(mask[:, x_label, y_label]) >= 0.5 (xm3d_gather_masks_batch with
+ *               XM3D_THR_SIGMOID_GE_HALF); binary_gt [cap] float32 (0 = novel, 1 = base, anything else ignored)
+ *   mask_logits [n_seg, k, h, w] float32, already up-sampled to cfg.mask_shape (:53-55)
+ * The ">= 10 points, else row 0 all True" guard (:87-88) and keep (:90) are applied on the device.  Outputs:
+ *   counts [n_seg,k,3] int32   (points, of which binary_gt == 0, of which == 1) per mask AFTER the guard
+ *   kind   [n_seg,k]   int8    0 = not pooled, 1 = novel candidate (:109-112), 2 = base candidate (:114-117)
+ *   score  [n_seg,k]   float32 mean of sigmoid(mask) over the pixels with sigmoid > 0.5 (candidates; NaN elsewhere)
+ *   sel    [n_seg,5]   int32   masks to pool: up to 4 novel by descending score (stable), then up to 1 base; -1 padded
+ *   n_sel  [n_seg]     int32
+ *   sel_member [cap]   uint32  bit j set iff the point lies in sel[.,j] -> xm3d_pool_batch(member = sel_member, k = 5)
+ *               gives feature[mask_3d[fidx]].mean(0) of :148-157 for all selected masks of the batch. */
+XM3D_API size_t xm3d_contra_ws_bytes(int32_t n_seg, int32_t k);
+XM3D_API int xm3d_contra_select_batch(const uint32_t *member, int32_t k, const float *binary_gt, const int64_t *seg_off,
+                             int32_t n_seg, int64_t cap, const float *mask_logits, int32_t h, int32_t w,
+                             int32_t *counts, int8_t *kind, float *score, int32_t *sel, int32_t *n_sel,
+                             uint32_t *sel_member, void *ws, size_t ws_bytes, xm3d_stream_t stream);
+
 /* ------------------------------------------------------------------ stage 4: text logits
  * XMASK3d.cal_pred_logits (models/xmask3d.py:129-143) + ensemble_logits_with_labels
  * (models/modeling/meta_arch/helper.py:72-97, "max" or "mean"):

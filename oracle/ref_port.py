@@ -350,6 +350,84 @@ def masked_sum_f64(feat: np.ndarray, member: np.ndarray):
     return m @ feat.astype(np.float64), member.sum(1).astype(np.int64)
 
 
+def contra_select_ref(x_label, y_label, mask, binary_gt):
+    """models/utils/criterion.py:80-136 for ONE scene: which masks `loss_contra` pools.
+    mask: torch [K,H,W] float32 logits, already up-sampled to cfg.mask_shape (:53-55); binary_gt torch [n]
+    (0 = novel, 1 = base, anything else = ignored).  Returns a dict:
+      member   bool [K,n]  sigmoid(mask[:, x, y]) >= 0.5, after the "row 0 all True if no mask has >= 10 points" guard
+      keep     bool [K]    masks with >= 10 points (:90)
+      kind     int  [K]    0 = neither, 1 = novel candidate (:109-112), 2 = base candidate (:114-117)   (original index)
+      score    float [K]   torch.mean(sigmoid(mask)[sigmoid(mask) > 0.5]) of the candidates, NaN elsewhere
+      sel      list        ORIGINAL mask indices pooled: up to 4 novel by descending score, then up to 1 base (:124-139)
+      sel_kept list        the same as indices into the kept arrays (the reference's final_list_idx)"""
+    import torch
+    mask_3d = mask[:, x_label, y_label].clone().sigmoid() >= 0.5
+    if len(mask_3d[torch.sum(mask_3d, dim=1) >= 10]) == 0:
+        mask_3d[0, :] = True
+    keep = torch.sum(mask_3d, dim=1) >= 10
+    kept = torch.nonzero(keep).flatten().tolist()
+    k = mask.shape[0]
+    kind = torch.zeros(k, dtype=torch.int64)
+    score = torch.full((k,), float("nan"))
+    novel, base = [], []
+    for j, m in enumerate(kept):
+        sig = mask[m].clone().sigmoid()
+        gt = binary_gt[mask_3d[m]]
+        novel_num = gt.eq(0).sum().item()
+        base_num = len(gt) - novel_num
+        base_num_ = gt.eq(1).sum().item()
+        novel_num_ = len(gt) - base_num_
+        if novel_num > 1.8 * base_num and novel_num > 10:
+            kind[m] = 1
+            score[m] = torch.mean(sig[sig > 0.5])
+            novel.append((j, score[m]))
+        elif base_num_ > 20 * novel_num_ and base_num_ > 150:
+            kind[m] = 2
+            score[m] = torch.mean(sig[sig > 0.5])
+            base.append((j, score[m]))
+    novel = [i for i, _ in sorted(novel, key=lambda t: t[1], reverse=True)][:4]
+    base = [i for i, _ in sorted(base, key=lambda t: t[1], reverse=True)][:1]
+    sel_kept = novel + base
+    return {"member": mask_3d, "keep": keep, "kind": kind, "score": score, "sel": [kept[j] for j in sel_kept],
+            "sel_kept": sel_kept}
+
+
+def loss_contra_ref(x_list, y_list, pred_masks, mask_embeds, clip_mask_embeddings, features_fused, features_3d,
+                    binary_gts, mask_shape):
+    """models/utils/criterion.py:39-182 (`Criterion.loss_contra`): up-sample, select per scene
+    (contra_select_ref), pool the fused / 3D features under the selected masks (`feature[mask].mean(0)`,
+    :148-157), cosine loss against the selected MaskCLIP embeddings.  Returns (loss_3d_contra, final_2d_mask,
+    embedding_fused, embedding_3d) — the last two are what the reference pools and then only uses inside the loss."""
+    import torch
+    import torch.nn.functional as F
+    masks = F.interpolate(pred_masks, size=tuple(mask_shape), mode="bilinear", align_corners=False)
+    cos = torch.nn.CosineSimilarity()
+    e_fused, e_3d, e_gt, final_2d_mask = [], [], [], []
+    for b, (x, y, mask, ff, f3, clip_e, gt) in enumerate(zip(x_list, y_list, masks, features_fused, features_3d,
+                                                             clip_mask_embeddings, binary_gts)):
+        r = contra_select_ref(x, y, mask, gt)
+        if not r["sel"]:
+            continue
+        e_gt.append(torch.stack([clip_e[m] for m in r["sel"]]))
+        e_fused.append(torch.stack([torch.mean(ff[r["member"][m]], dim=0) for m in r["sel"]]))
+        e_3d.append(torch.stack([torch.mean(f3[r["member"][m]], dim=0) for m in r["sel"]]))
+        final_2d_mask.append((b, torch.stack([mask[m] for m in r["sel"]])))
+    if e_fused:
+        e_fused, e_3d, e_gt = torch.cat(e_fused), torch.cat(e_3d), torch.cat(e_gt).detach()
+        loss = (1 - cos(e_3d, e_gt)).mean()
+    else:
+        inv = torch.stack([mask_embeds[-1][0]])
+        loss = (1 - cos(inv, inv)).mean()
+        e_fused = e_3d = None
+    return loss, final_2d_mask, e_fused, e_3d
+
+
+def scene_mean_ref(features):
+    """models/xmask3d.py:239-258: `feature.mean(0)` per scene, stacked (the K = 1 all-ones pooling)."""
+    import torch
+    return torch.stack([f.mean(0, keepdim=False) for f in features])
+
+
 # --------------------------------------------------------------------------- stage 4
 def ensemble_logits_with_labels(logits, labels: List[List[str]], ensemble_method: str = "max"):
     """models/modeling/meta_arch/helper.py:72-97."""

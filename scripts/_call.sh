@@ -1,3 +1,3 @@
 set -x
-XM3D_SO=xmask3d_b200/libxm3d_dbg.so timeout 600 python scripts/exp_pool_mma.py 0 0x22 > gpurun_out/exp_pool_mma.log 2>&1; echo "rc=$?" >> gpurun_out/exp_pool_mma.log
+timeout 900 python -m pytest tests/test_contra.py tests/test_gpu_parity.py -m gpu -x -q -k "contra or scene_mean or abi" > gpurun_out/gpu_tests2.log 2>&1; echo "rc=$?" >> gpurun_out/gpu_tests2.log
 echo done

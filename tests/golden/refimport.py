@@ -88,6 +88,8 @@ def load():
     from models.modeling.meta_arch.helper import ensemble_logits_with_labels
     from models.xmask3d import XMASK3d
     from dataset.point_loader import Point3DLoader
+    from models.utils.criterion import Criterion
+    ns.Criterion = Criterion
     ns.Voxelizer, ns.sparse_quantize, ns.fnv_hash_vec, ns.ravel_hash_vec = \
         Voxelizer, sparse_quantize, fnv_hash_vec, ravel_hash_vec
     ns.getMapping, ns.PointCloudToImageMapper, ns.mask_mapper = getMapping, PointCloudToImageMapper, mask_mapper

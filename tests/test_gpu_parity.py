@@ -758,7 +758,7 @@ def test_abi_error_reporting(dev):
     lib = L.lib()
     sm, major = C.c_int32(0), C.c_int32(0)
     assert lib.xm3d_device_info(C.byref(sm), C.byref(major), None) == 0 and sm.value >= 100 and major.value == 10
-    assert lib.xm3d_pool_batch(None, 768, None, None, None, 1, 50, None, 0, 0, None, None, None, None, 0, None, None) == -1
+    assert lib.xm3d_pool_batch(None, 768, None, None, None, 1, 50, None, 0, 0, 0, None, None, None, None, 0, None, None) == -1
     assert b"xm3d_pool_batch" in lib.xm3d_last_error()
     with pytest.raises(L.Xm3dError):                      # workspace too small
         feat = torch.zeros(8, 4, device=dev)
@@ -766,7 +766,7 @@ def test_abi_error_reporting(dev):
         lab = torch.zeros(8, dtype=torch.int32, device=dev)
         out = torch.zeros(1, 2, 4, device=dev)
         L.check(lib.xm3d_pool_batch(C.c_void_p(feat.data_ptr()), 4, None, None, C.c_void_p(lab.data_ptr()), 1, 2,
-                                    C.c_void_p(seg.data_ptr()), 8, 8, C.c_void_p(out.data_ptr()), None, None,
+                                    C.c_void_p(seg.data_ptr()), 8, 8, 0, C.c_void_p(out.data_ptr()), None, None,
                                     C.c_void_p(out.data_ptr()), 16, None, None))
     with pytest.raises(L.Xm3dError):                      # more than 256 masks per segment
         ops.pool(torch.zeros(8, 4, device=dev), torch.tensor([0, 8], device=dev), 300,

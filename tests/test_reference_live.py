@@ -150,3 +150,42 @@ def test_mask_mapper_ragged_lists_live(R, seed, ks):
     got = ref_port.mask_mapper_ref(xs, ys, masks, embs, preds, fuse, ident, ident, True)
     for a, b in zip(ref, got):
         assert len(a) == len(b) and all(torch.equal(u, v) for u, v in zip(a, b))
+
+
+def _contra_inputs(seed, b, k, h, w, c, n_lo=60, n_hi=900, frac_ignored=0.1):
+    """Synthetic loss_contra inputs: low-resolution mask logits whose up-sampled masks cover 5-60 % of the image,
+    binary_gt spatially coherent (left part novel, right part base) so that both candidate classes occur."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    pm = torch.randn(b, k, h // 2, w // 2, generator=g)
+    pm = torch.nn.functional.avg_pool2d(pm, 5, stride=1, padding=2) * 6 - torch.rand(b, k, 1, 1, generator=g) * 2
+    xs, ys, gts, ff, f3 = [], [], [], [], []
+    for _ in range(b):
+        n = int(torch.randint(n_lo, n_hi, (1,), generator=g))
+        x, y = torch.randint(0, h, (n,), generator=g), torch.randint(0, w, (n,), generator=g)
+        split = int(torch.randint(w // 4, 3 * w // 4, (1,), generator=g))
+        gt = (y >= split).float()
+        gt[torch.rand(n, generator=g) < frac_ignored] = 2.0
+        xs.append(x); ys.append(y); gts.append(gt)
+        ff.append(torch.randn(n, c, generator=g)); f3.append(torch.randn(n, c, generator=g))
+    return pm, xs, ys, gts, ff, f3, torch.randn(b, k, c, generator=g), torch.randn(b, k, c, generator=g)
+
+
+@settings(max_examples=12, deadline=None, derandomize=True)
+@given(seed=st.integers(0, 2 ** 31 - 1), b=st.integers(1, 3), k=st.integers(1, 14), sparse=st.booleans())
+def test_loss_contra_live(R, seed, b, k, sparse):
+    """models/utils/criterion.py:39-182 — the reference's own `Criterion.loss_contra` (self only supplies
+    cfg.mask_shape) against the port: same loss, same selected mask planes in the same order."""
+    import types
+
+    import torch
+    h, w, c = 24, 32, 8
+    pm, xs, ys, gts, ff, f3, me, ce = _contra_inputs(seed, b, k, h, w, c, n_lo=(3 if sparse else 200), n_hi=(40 if sparse else 900))
+    self = types.SimpleNamespace(cfg=types.SimpleNamespace(mask_shape=[h, w]))
+    outputs = {"pred_masks": pm, "mask_embed": me, "mask_embed_clip": ce, "fused_pred_feature": ff, "pure3d_pred_feature": f3}
+    ref_loss, ref_masks = R.Criterion.loss_contra(self, xs, ys, None, None, gts, outputs)
+    loss, fm, _, _ = ref_port.loss_contra_ref(xs, ys, pm, me, ce, ff, f3, gts, [h, w])
+    assert torch.equal(ref_loss["loss_3d_contra"], loss)
+    assert len(ref_masks) == len(fm)
+    for (rb, rm), (pb, pmk) in zip(ref_masks, fm):
+        assert rb == pb and torch.equal(rm, pmk)

@@ -59,6 +59,8 @@ PROTOTYPES = {
     "xm3d_pixel_bits_batch": (C.c_int, [_P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P]),
     "xm3d_pool_ws_bytes": (_SZ, [_I32, _I32, _I32, _I64, _I64]),
     "xm3d_pool_batch": (C.c_int, [_P, _I32, _P, _P, _P, _I32, _I32, _P, _I64, _I64, _I32, _P, _P, _P, _P, _SZ, _P, _P]),
+    "xm3d_contra_ws_bytes": (_SZ, [_I32, _I32]),
+    "xm3d_contra_select_batch": (C.c_int, [_P, _I32, _P, _P, _I32, _I64, _P, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "xm3d_scatter_batch": (C.c_int, [_P, _P, _I32, _I32, _P, _I64, _P, _I32, _P, _P, _P]),
     "xm3d_point_logits_ws_bytes": (_SZ, [_I32, _I32]),
     "xm3d_point_logits": (C.c_int, [_P, _I64, _I32, _P, _I32, _F32, _P, _P, _P, _P, _P, _SZ, _P]),

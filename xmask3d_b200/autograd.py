@@ -41,6 +41,34 @@ def scatter_mean(emb: torch.Tensor, seg_off: torch.Tensor, member: torch.Tensor,
     return _ScatterMean.apply(emb, seg_off, member, int(n_pts))
 
 
+class _PoolMean(torch.autograd.Function):
+    """mean[s,m] = sum of feat[i] over the points i of segment s inside mask m / cnt[s,m]  (0 where cnt = 0) —
+    `feature[mask].mean(0)` of models/utils/criterion.py:148-157 and `feature.mean(0)` of models/xmask3d.py:239-258."""
+
+    @staticmethod
+    def forward(ctx, feat, seg_off, member, k, cap_pairs):
+        _, cnt, mean = ops.pool(feat.detach(), seg_off, k, member=member, cap_pairs=cap_pairs)
+        ctx.save_for_backward(seg_off, member, cnt)
+        ctx.n = feat.shape[0]
+        ctx.mark_non_differentiable(cnt)
+        return mean, cnt
+
+    @staticmethod
+    def backward(ctx, grad_mean, _grad_cnt):
+        seg_off, member, cnt = ctx.saved_tensors
+        # d feat[i] = sum over masks m containing i of grad_mean[s,m] / cnt[s,m]: the scatter kernel returns that sum
+        # divided by the number of masks containing i (its `counter`, 1e-5 where none does and the sum is 0)
+        g = (grad_mean / cnt.clamp(min=1).unsqueeze(-1).to(grad_mean.dtype)).contiguous()
+        out, counter = ops.scatter(g, seg_off, ctx.n, member=member)
+        return out * counter.unsqueeze(1), None, None, None, None
+
+
+def pool_mean(feat: torch.Tensor, seg_off: torch.Tensor, member: torch.Tensor, k: int, cap_pairs=None):
+    """Differentiable (w.r.t. feat) masked mean pooling.  Returns (mean [n_seg,k,c], cnt int32 [n_seg,k]).
+    cap_pairs: host-known bound on the memberships (None: counted on the device, one host sync)."""
+    return _PoolMean.apply(feat, seg_off, member, int(k), cap_pairs)
+
+
 class _PredLogits(torch.autograd.Function):
     """cal_pred_logits with max / mean ensembling; backward in torch from the saved operands."""
 

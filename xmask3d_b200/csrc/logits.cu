@@ -294,6 +294,12 @@ struct PointLogitsParams {
     const float *inv_norm_b;     // [n_text]
     const float *binary;         // [rows] or null
     const unsigned char *is_base;// [n_text] or null (required with binary)
+    // fused-stream ensemble (run/infer.py:568-600): softmax over the classes, then for a point inside final mask
+    // `mask_label` the geometric mean with that mask's MaskCLIP class probabilities, base / novel ratios per class
+    const int *mask_label;       // [rows] (-1 = in no mask) or null: no ensemble
+    const float *mask_probs;     // [n_masks, n_text] softmax(final_pred_open_logits)
+    int n_masks;
+    float base_ratio, novel_ratio;
     float *out;                  // [rows, n_text] or null
     int *argmax;                 // [rows] or null
 };
@@ -459,18 +465,57 @@ point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const float inv_a = __fdiv_rn(1.0f, fmaxf(sqrtf(s_ss[rloc]), 1e-12f));      // F.normalize
         const float b = (row_ok && P.binary) ? P.binary[r] : 0.f;
         const bool blend = P.binary != nullptr;
+        const uint32_t trow = tmem_base + ((uint32_t)(lg * 32) << 16);
+        // scaled cosine logit of column `col` out of the accumulator chunk(s)
+        auto logit_of = [&](const uint32_t (&v)[16], const uint32_t (&v2)[16], int j, int col) {
+            const float dot = P.fused ? __uint_as_float(v[j]) + __uint_as_float(v2[j]) : __uint_as_float(v[j]);
+            return P.scale * ((dot * inv_a) * s_invb[col]);
+        };
+        float smax = -INFINITY, ssum = 0.f;
+        int label = -1;
+        if (P.mask_label) {
+            // logits_pred.softmax(-1): two more passes over the accumulator row (TMEM reads are cheap)
+            label = row_ok ? P.mask_label[r] : -1;
+            if (label >= P.n_masks) label = -1;
+            for (int c0 = 0; c0 < P.bn; c0 += 16) {
+                uint32_t v[16], v2[16];
+                tmem_ld16(trow + (uint32_t)c0, v);
+                if (P.fused) tmem_ld16(trow + (uint32_t)(P.bn + c0), v2);
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (c0 + j < P.n_text) smax = fmaxf(smax, logit_of(v, v2, j, c0 + j));
+            }
+            for (int c0 = 0; c0 < P.bn; c0 += 16) {
+                uint32_t v[16], v2[16];
+                tmem_ld16(trow + (uint32_t)c0, v);
+                if (P.fused) tmem_ld16(trow + (uint32_t)(P.bn + c0), v2);
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (c0 + j < P.n_text) ssum += expf(logit_of(v, v2, j, c0 + j) - smax);
+            }
+        }
         float best = -INFINITY;
         int best_i = 0;
         for (int c0 = 0; c0 < P.bn; c0 += 16) {
             uint32_t v[16], v2[16];
-            tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0, v);
-            if (P.fused) tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(P.bn + c0), v2);
+            tmem_ld16(trow + (uint32_t)c0, v);
+            if (P.fused) tmem_ld16(trow + (uint32_t)(P.bn + c0), v2);
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const int col = c0 + j;
                 if (col < P.n_text) {
-                    const float dot = P.fused ? __uint_as_float(v[j]) + __uint_as_float(v2[j]) : __uint_as_float(v[j]);
-                    float val = P.scale * ((dot * inv_a) * s_invb[col]);
+                    float val = logit_of(v, v2, j, col);
+                    if (P.mask_label) {
+                        val = __fdiv_rn(expf(val - smax), ssum);                       // class probability
+                        if (label >= 0) {
+                            // (p ** ratio * q ** (1 - ratio)).log() * overlap, base and novel halves added (:577-590)
+                            const float q = __ldg(P.mask_probs + (size_t)label * P.n_text + col);
+                            const float ov = s_base[col] ? 1.f : 0.f;
+                            const float tb = __fmul_rn(logf(__fmul_rn(powf(val, P.base_ratio), powf(q, 1.f - P.base_ratio))), ov);
+                            const float tn = __fmul_rn(logf(__fmul_rn(powf(val, P.novel_ratio), powf(q, 1.f - P.novel_ratio))), 1.f - ov);
+                            val = __fadd_rn(tb, tn);
+                        }
+                    }
                     if (blend) {
                         // binary * logits_base + (1 - binary) * logits_novel, masked entries = -1e10
                         const float lb = s_base[col] ? val : -1e10f, ln = s_base[col] ? -1e10f : val;
@@ -571,14 +616,17 @@ extern "C" size_t xm3d_point_logits_ws_bytes(int32_t n_text, int32_t c) {
 }
 
 extern "C" int xm3d_point_logits(const float *feat, int64_t rows, int32_t c, const float *text_embed, int32_t n_text,
-                                 float logit_scale, const float *binary, const uint8_t *is_base, float *out,
-                                 int32_t *argmax, void *ws, size_t ws_bytes, xm3d_stream_t stream_) {
+                                 float logit_scale, const float *binary, const uint8_t *is_base,
+                                 const int32_t *mask_label, const float *mask_probs, int32_t n_masks, float base_ratio,
+                                 float novel_ratio, float *out, int32_t *argmax, void *ws, size_t ws_bytes,
+                                 xm3d_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     XM3D_REQUIRE(rows >= 0 && c > 0 && n_text > 0, "bad sizes");
     XM3D_REQUIRE(c % 4 == 0, "feature width must be a multiple of 4");
     XM3D_REQUIRE(n_text <= LG_MAX_N, "at most 256 classes");
     XM3D_REQUIRE(feat && text_embed && ws && (out || argmax), "null pointer");
     XM3D_REQUIRE(!binary || is_base, "is_base is required with binary");
+    XM3D_REQUIRE(!mask_label || (mask_probs && is_base && n_masks >= 0), "the ensemble needs mask_probs and is_base");
     XM3D_REQUIRE(rows < ((int64_t)1 << 31) - LG_BM, "rows exceed int32 tile coordinates");
     XM3D_REQUIRE(reinterpret_cast<uintptr_t>(feat) % 16 == 0, "feat must be 16-byte aligned");
     if (rows == 0) return XM3D_OK;
@@ -596,6 +644,7 @@ extern "C" int xm3d_point_logits(const float *feat, int64_t rows, int32_t c, con
     PointLogitsParams P;
     P.rows = rows; P.c = c; P.n_text = n_text; P.bn = (n_text + 15) / 16 * 16; P.scale = logit_scale;
     P.inv_norm_b = inv_b; P.binary = binary; P.is_base = is_base; P.out = out; P.argmax = argmax;
+    P.mask_label = mask_label; P.mask_probs = mask_probs; P.n_masks = n_masks; P.base_ratio = base_ratio; P.novel_ratio = novel_ratio;
     P.fused = (2 * P.bn <= 256) ? 1 : 0;
     int tc = 32;
     while (tc < (P.fused ? 2 * P.bn : P.bn)) tc <<= 1;

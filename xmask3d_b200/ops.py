@@ -365,6 +365,44 @@ def scatter(emb: torch.Tensor, seg_off: torch.Tensor, n_pts: int, member: Option
     return out[:n_pts], (counter[:n_pts] if counter is not None else None)
 
 
+@dataclass
+class ContraSelection:
+    counts: torch.Tensor      # int32 [n_seg,k,3]  (points, binary_gt == 0, binary_gt == 1) per mask, after the guard
+    kind: torch.Tensor        # int8  [n_seg,k]    0 none, 1 novel candidate, 2 base candidate
+    score: torch.Tensor       # float32 [n_seg,k]  mean sigmoid over pixels > 0.5 (candidates; NaN elsewhere)
+    sel: torch.Tensor         # int32 [n_seg,5]    masks to pool (original indices), -1 padded
+    n_sel: torch.Tensor       # int32 [n_seg]
+    sel_member: torch.Tensor  # int32 [cap,1]      bit j: the point lies in sel[., j]  (pool(..., k=5, member=sel_member))
+
+
+def contra_select(member: torch.Tensor, k: int, binary_gt: torch.Tensor, seg_off: torch.Tensor,
+                  mask_logits: torch.Tensor, cap: Optional[int] = None) -> ContraSelection:
+    """loss_contra's mask selection (models/utils/criterion.py:80-146) for all scenes of a batch on the device.
+    member int32 [cap,words] (sigmoid(mask[:, x, y]) >= 0.5), binary_gt float32 [cap], mask_logits float32
+    [n_seg,k,h,w] already up-sampled to cfg.mask_shape."""
+    _require_cuda()
+    dev = member.device
+    member = _dev_contig(member, torch.int32)
+    binary_gt = _dev_contig(binary_gt.reshape(-1), torch.float32)
+    seg_off = _dev_contig(seg_off, torch.int64)
+    mask_logits = _dev_contig(mask_logits, torch.float32)
+    n_seg, kk, h, w = mask_logits.shape
+    assert kk == k and seg_off.numel() == n_seg + 1
+    cap = int(member.shape[0]) if cap is None else int(cap)
+    assert binary_gt.numel() >= cap
+    counts = torch.empty((n_seg, k, 3), dtype=torch.int32, device=dev)
+    kind = torch.empty((n_seg, k), dtype=torch.int8, device=dev)
+    score = torch.empty((n_seg, k), dtype=torch.float32, device=dev)
+    sel = torch.empty((n_seg, 5), dtype=torch.int32, device=dev)
+    n_sel = torch.empty(n_seg, dtype=torch.int32, device=dev)
+    sel_member = torch.zeros((max(cap, 1), 1), dtype=torch.int32, device=dev)
+    ws = _ws(L.lib().xm3d_contra_ws_bytes(n_seg, k), dev)
+    L.check(L.lib().xm3d_contra_select_batch(_ptr(member), int(k), _ptr(binary_gt), _ptr(seg_off), n_seg, cap,
+                                             _ptr(mask_logits), h, w, _ptr(counts), _ptr(kind), _ptr(score), _ptr(sel),
+                                             _ptr(n_sel), _ptr(sel_member), _ptr(ws), ws.numel(), _stream()))
+    return ContraSelection(counts, kind, score, sel, n_sel, sel_member)
+
+
 # ----------------------------------------------------------------------------- stage 4
 def logits(mask_embed: torch.Tensor, text_embed: torch.Tensor, null_embed: torch.Tensor,
            group_sizes: Sequence[int], logit_scale: float, ensemble: str = "max", want_argmax: bool = False,
