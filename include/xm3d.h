@@ -50,6 +50,7 @@ typedef enum {
 #define XM3D_FLAG_PAIR_OVERFLOW 2  /* more (point,mask) pairs than cap_pairs    */
 #define XM3D_FLAG_GRID_RANGE 4     /* voxel coordinate outside +-2^30           */
 #define XM3D_FLAG_KEY_SENTINEL 8   /* a key equal to 2^64-1 was remapped        */
+#define XM3D_FLAG_I16_RANGE 16     /* xm3d_pack_i16: a value did not fit int16  */
 
 /* depth image element type */
 #define XM3D_DEPTH_NONE 0
@@ -258,13 +259,20 @@ XM3D_API int xm3d_logits(const float *mask_embed, int64_t rows, int32_t c, const
  * blending with the binary head and argmax (run/infer.py:557, 606-640; models/utils/criterion.py:184-207):
  *   val[i,t] = scale * <feat_i/|feat_i|, text_t/|text_t|>
  *   binary given:  val[i,t] = b_i * (is_base[t] ? val : -1e10) + (1 - b_i) * (is_base[t] ? -1e10 : val)
+ *   mask_label given (the FUSED stream, run/infer.py:568-600): p_i = softmax_t(val[i,:]); for a point inside final
+ *     mask m = mask_label[i] (>= 0; the final masks are an argmax partition, models/xmask3d.py:418-435) with
+ *     q = mask_probs[m,:] = softmax(logit_scale * normalize(final_pred_open_embedding) @ text.T):
+ *       val[i,t] = log(p^base_ratio * q^(1-base_ratio)) * ov[t] + log(p^novel_ratio * q^(1-novel_ratio)) * (1 - ov[t]),
+ *     ov = is_base; points in no mask keep val = p.  The binary blend above then applies to these values.
  *   out [rows, n_text] float32 (optional), argmax int32 [rows] (optional, first maximum)
  * feat [rows, c] float32 is read from HBM once (TMA -> in-place TF32 hi/lo split in shared memory ->
  * tcgen05 3xTF32); n_text <= 256, c % 4 == 0, feat 16-byte aligned. */
 XM3D_API size_t xm3d_point_logits_ws_bytes(int32_t n_text, int32_t c);
 XM3D_API int xm3d_point_logits(const float *feat, int64_t rows, int32_t c, const float *text_embed, int32_t n_text,
-                      float logit_scale, const float *binary, const uint8_t *is_base, float *out,
-                      int32_t *argmax, void *ws, size_t ws_bytes, xm3d_stream_t stream);
+                      float logit_scale, const float *binary, const uint8_t *is_base,
+                      const int32_t *mask_label, const float *mask_probs, int32_t n_masks, float base_ratio,
+                      float novel_ratio, float *out, int32_t *argmax, void *ws, size_t ws_bytes,
+                      xm3d_stream_t stream);
 
 /* ------------------------------------------------------------------ after the path: votes
  * Cross-view vote accumulation of the inference loop (run/infer.py:642-647, :658), batched:
@@ -336,6 +344,12 @@ XM3D_API int xm3d_gather_labels_batch(const int16_t *label_img, int32_t n_seg, i
 XM3D_API int xm3d_collate_batch(const float *xyz_vis, const int64_t *vis_off, const int32_t *voxel_xyz,
                        const int64_t *uniq_off, int32_t n_seg, int64_t cap, float *ori_coords,
                        int32_t *coords, xm3d_stream_t stream);
+/* int32 [rows, width] -> int16 for the host-bound copies of x_label / y_label (rowcol, values < 320) and voxel
+ * coordinates (dataset/data_loader.py:319-357 hands them to the host loop as int64 / int32; the end-to-end path is
+ * PCIe bound, so bytes matter).  rows_dev: optional DEVICE row count (vis_off[n_seg] / uniq_off[n_seg]), capped by
+ * cap_rows.  Out-of-range values are clamped and flagged (XM3D_FLAG_I16_RANGE). */
+XM3D_API int xm3d_pack_i16(const int32_t *src, const int64_t *rows_dev, int64_t cap_rows, int32_t width, int16_t *dst,
+                  int32_t *status, xm3d_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -459,6 +459,37 @@ def cal_pred_logits(outputs: dict):
 
 
 # --------------------------------------------------------------------------- after the path
+def fused_stream_ref(fused_feature, text_features, logit_scale, final_pred_open_embedding, final_mask_3d,
+                     base_category, novel_category, all_category_count, base_ratio, novel_ratio, binary_pred):
+    """run/infer.py:516-608, the FUSED stream of the inference loop, statement for statement (torch CPU):
+    normalise, logits, softmax; per final mask the geometric-mean ensemble with the mask's MaskCLIP class
+    probabilities, `.log()`, base / novel halves through category_overlapping_mask (:577-590); -1e10 masking of the
+    other category group, blend with the binary head's prediction (:592-604), argmax (:606).
+    fused_feature [n,C], text_features [T,C], final_pred_open_embedding [Kf,C], final_mask_3d bool [Kf,n] (an
+    argmax partition: every point in at most one mask), binary_pred [n,1] in {0,1}.
+    Returns (logits_pred [n,T] before the argmax, argmax int64 [n])."""
+    import torch
+    import torch.nn.functional as F
+    fused_feature = F.normalize(fused_feature, dim=-1)
+    text_features = F.normalize(text_features, dim=-1)
+    logits_pred = logit_scale * (fused_feature @ text_features.t())
+    final_pred_open_embedding = F.normalize(final_pred_open_embedding, dim=-1)
+    final_pred_open_logits = logit_scale * (final_pred_open_embedding @ text_features.t())
+    logits_pred = logits_pred.softmax(dim=-1)
+    final_pred_open_logits = final_pred_open_logits.softmax(dim=-1)
+    overlap = torch.tensor([int(t in base_category) for t in range(all_category_count)], dtype=torch.long)
+    for single_mask, open_logit in zip(final_mask_3d, final_pred_open_logits):
+        base = (logits_pred[single_mask] ** base_ratio * open_logit ** (1 - base_ratio)).log() * overlap
+        novel = (logits_pred[single_mask] ** novel_ratio * open_logit ** (1 - novel_ratio)).log() * (1 - overlap)
+        logits_pred[single_mask] = base + novel
+    logits_pred_novel = logits_pred.clone()
+    logits_pred_base = logits_pred.clone()
+    logits_pred_novel[:, base_category] = -1e10
+    logits_pred_base[:, novel_category] = -1e10
+    logits_pred = binary_pred * logits_pred_base + (1 - binary_pred) * logits_pred_novel
+    return logits_pred, torch.max(logits_pred, 1)[1]
+
+
 def accumulate_votes(scene_pred, counter, mask_2d, logits_pred):
     """run/infer.py:642-647 — one view's votes (numpy, in place)."""
     idx = np.nonzero(mask_2d)[0]

@@ -1,3 +1,3 @@
 set -x
-timeout 900 python -m pytest tests/test_contra.py tests/test_gpu_parity.py -m gpu -x -q -k "contra or scene_mean or abi" > gpurun_out/gpu_tests2.log 2>&1; echo "rc=$?" >> gpurun_out/gpu_tests2.log
+( time timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_r02_a.json 2> gpurun_out/bench_r02_a.err ) 2> gpurun_out/bench_r02_a.time; echo "rc=$?" >> gpurun_out/bench_r02_a.err
 echo done

@@ -87,7 +87,7 @@ def test_configs1_full_batch_bit_exact(cport, dev):
     from xmask3d_b200 import ops
     from xmask3d_b200.pipeline import CorrespondencePipeline
     import bench
-    args = argparse.Namespace(scenes=8, views=20, points=150_000, voxel=0.02, distinct_scenes=False, scene_seeds=None)
+    args = argparse.Namespace(scenes=8, views=20, points=150_000, voxel=0.02, replicas=False)
     batch, scenes = bench.build_batch(args, 0)
     assert batch.point_views == 24_000_000
     pipe = CorrespondencePipeline(batch, 50, 768, dev)
@@ -96,7 +96,7 @@ def test_configs1_full_batch_bit_exact(cport, dev):
     pr = ops.project_batch(pipe.xyz, pipe.views, pipe.out_off, pipe.depth, want_mapping=True, ws=pipe.ws_proj,
                            views_dev=pipe.views_dev)
     assert int(pr.status.item()) == 0
-    views_np = [(scenes[int(s)].xyz, batch.w2c[v], batch.depth_mm[v]) for v, s in enumerate(batch.view_scene)]
+    views_np = [(scenes[int(s)]["xyz"], batch.w2c[v], batch.depth_mm[v]) for v, s in enumerate(batch.view_scene)]
     n_checked, n_visible = _check_projection(cport, pr, pipe.out_off, views_np, batch.intr)
     assert n_checked == 24_000_000 and n_visible > 2_000_000
     del pr.mapping

@@ -924,6 +924,51 @@ def test_point_logits_vs_torch(dev):
         assert none is None and torch.equal(amax2, amax)
 
 
+@pytest.mark.parametrize("n,t,kf,c", [(30_000, 19, 23, 768), (5000, 200, 60, 768), (257, 7, 1, 128)])
+def test_point_logits_fused_stream_ensemble(dev, n, t, kf, c):
+    """The FUSED stream of the inference loop (run/infer.py:516-608): softmax over the classes, geometric-mean
+    ensemble with the per-mask MaskCLIP probabilities in the log domain (base / novel ratios through
+    category_overlapping_mask), -1e10 masking, blend with the binary head, argmax — in the epilogue of the
+    tcgen05 kernel, against the statement-for-statement torch-CPU restatement (oracle/ref_port.py).
+    Bars: identical argmax wherever the reference's own top-2 gap exceeds 1e-4; values within 1e-4 absolute
+    (log-domain values of size ~10; the float32 pow / log / exp of the two implementations differ in the last bits)."""
+    from oracle import ref_port
+    from xmask3d_b200 import ops
+    g = torch.Generator().manual_seed(n + t)
+    feat = torch.randn(n, c, generator=g) * 2
+    te = torch.randn(t, c, generator=g)
+    open_emb = torch.randn(kf, c, generator=g)
+    label = torch.randint(-1, kf, (n,), generator=g)                       # -1: the point is in no final mask
+    final_mask_3d = label.unsqueeze(0) == torch.arange(kf).view(kf, 1)     # partition
+    base_cat = sorted(torch.randperm(t, generator=g)[: max(1, (3 * t) // 4)].tolist())
+    novel_cat = [i for i in range(t) if i not in base_cat]
+    binary = (torch.rand(n, 1, generator=g) > 0.5).float()
+    scale, rb, rn = 1 / 0.07, 0.65, 0.35
+    ref_val, ref_arg = ref_port.fused_stream_ref(feat, te, scale, open_emb, final_mask_3d, base_cat, novel_cat, t, rb, rn,
+                                                 binary)
+    import torch.nn.functional as F
+    probs = (scale * (F.normalize(open_emb, dim=-1) @ F.normalize(te, dim=-1).t())).softmax(-1)
+    is_base = torch.zeros(t, dtype=torch.bool)
+    is_base[base_cat] = True
+    out, amax = ops.point_logits(feat.to(dev), te.to(dev), scale, binary=binary.to(dev), is_base=is_base.to(dev),
+                                 mask_label=label.to(torch.int32).to(dev), mask_probs=probs.to(dev), base_ratio=rb,
+                                 novel_ratio=rn)
+    out, amax = out.cpu(), amax.cpu().long()
+    live = ref_val > -1e9
+    assert bool(((out < -1e9) == ~live).all())
+    finite = live & torch.isfinite(ref_val)
+    assert float((out - ref_val)[finite].abs().max()) < 1e-4
+    top2 = torch.where(torch.isfinite(ref_val), ref_val, torch.full_like(ref_val, -1e10)).topk(min(2, t), -1).values
+    clear = torch.isfinite(ref_val).all(1) & ((top2[:, 0] - top2[:, -1]) > 1e-4 if t > 1 else torch.ones(n, dtype=torch.bool))
+    assert float(clear.float().mean()) > 0.98
+    assert torch.equal(amax[clear], ref_arg[clear])
+    # argmax-only call gives the same classes
+    _, amax2 = ops.point_logits(feat.to(dev), te.to(dev), scale, binary=binary.to(dev), is_base=is_base.to(dev),
+                                mask_label=label.to(torch.int32).to(dev), mask_probs=probs.to(dev), base_ratio=rb,
+                                novel_ratio=rn, want_logits=False)
+    assert torch.equal(amax2.cpu().long(), amax)
+
+
 def test_nn_fill_and_segment_max(golden, dev):
     """Nearest-seen-neighbour fill (run/infer.py:651-656, 684-694) against the golden KDTree result and the
     exhaustive oracle on a ragged multi-scene batch (a scene without seen points, one without unseen

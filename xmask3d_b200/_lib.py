@@ -15,7 +15,7 @@ SO_PATH = os.environ.get("XM3D_SO") or os.path.join(_HERE, "libxm3d.so")   # XM3
 CSRC = os.path.join(_HERE, "csrc")
 
 XM3D_OK = 0
-FLAG_VIS_OVERFLOW, FLAG_PAIR_OVERFLOW, FLAG_GRID_RANGE, FLAG_KEY_SENTINEL = 1, 2, 4, 8
+FLAG_VIS_OVERFLOW, FLAG_PAIR_OVERFLOW, FLAG_GRID_RANGE, FLAG_KEY_SENTINEL, FLAG_I16_RANGE = 1, 2, 4, 8, 16
 DEPTH_NONE, DEPTH_U16, DEPTH_F64 = 0, 1, 2
 THR_GE_HALF, THR_SIGMOID_GE_HALF, THR_SIGMOID_GT_HALF = 0, 1, 2
 MASK_U8, MASK_F32 = 0, 1
@@ -63,7 +63,7 @@ PROTOTYPES = {
     "xm3d_contra_select_batch": (C.c_int, [_P, _I32, _P, _P, _I32, _I64, _P, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "xm3d_scatter_batch": (C.c_int, [_P, _P, _I32, _I32, _P, _I64, _P, _I32, _P, _P, _P]),
     "xm3d_point_logits_ws_bytes": (_SZ, [_I32, _I32]),
-    "xm3d_point_logits": (C.c_int, [_P, _I64, _I32, _P, _I32, _F32, _P, _P, _P, _P, _P, _SZ, _P]),
+    "xm3d_point_logits": (C.c_int, [_P, _I64, _I32, _P, _I32, _F32, _P, _P, _P, _P, _I32, _F32, _F32, _P, _P, _P, _SZ, _P]),
     "xm3d_vote_batch": (C.c_int, [_P, _P, _I32, _I64, _P, _P, _I32, _P, _P, _P]),
     "xm3d_vote_argmax": (C.c_int, [_P, _P, _I64, _I32, _P, _P]),
     "xm3d_nn_fill_ws_bytes": (_SZ, [_I32, _I64]),
@@ -73,6 +73,7 @@ PROTOTYPES = {
     "xm3d_point_bits_batch": (C.c_int, [_P, _I32, _I32, _I32, _I32, _P, _P, _I64, _P, _P, _P]),
     "xm3d_gather_labels_batch": (C.c_int, [_P, _I32, _I32, _I32, _P, _P, _I64, _P, _P]),
     "xm3d_collate_batch": (C.c_int, [_P, _P, _P, _P, _I32, _I64, _P, _P, _P]),
+    "xm3d_pack_i16": (C.c_int, [_P, _P, _I64, _I32, _P, _P, _P]),
     "xm3d_logits_ws_bytes": (_SZ, [_I64, _I32, _I32, _I32]),
     "xm3d_logits": (C.c_int, [_P, _I64, _I32, _P, _I32, _P, _P, _I32, _I32, _F32, _P, _P, _P, _SZ, _P]),
 }

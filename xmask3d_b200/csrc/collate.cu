@@ -31,9 +31,42 @@ collate_voxels_kernel(const int32_t *__restrict__ voxel, const int64_t *__restri
     out[i] = make_int4(s, voxel[3 * i], voxel[3 * i + 1], voxel[3 * i + 2]);
 }
 
+// Compact host-bound copies of the index maps: pixel rows / columns (< 32768) and voxel coordinates fit int16, which
+// halves the device -> host bytes of x_label / y_label / coords (the end-to-end loop is PCIe bound).  `rows` is the
+// device-side row count (vis_off[n_seg] / uniq_off[n_seg]); rows beyond it are not touched.  A value outside
+// int16 raises XM3D_FLAG_I16_RANGE (and is clamped).
+__global__ void __launch_bounds__(256)
+pack_i16_kernel(const int32_t *__restrict__ src, const int64_t *__restrict__ rows, int64_t cap_rows, int width,
+                int16_t *__restrict__ dst, int *status) {
+    int64_t n = rows ? *rows : cap_rows;
+    if (n > cap_rows) n = cap_rows;
+    n *= width;
+    bool bad = false;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int v = src[i];
+        if (v < -32768 || v > 32767) { bad = true; v = v < 0 ? -32768 : 32767; }
+        dst[i] = (int16_t)v;
+    }
+    if (bad && status) atomicOr(status, XM3D_FLAG_I16_RANGE);
+}
+
 }  // namespace xm3d
 
 using namespace xm3d;
+
+extern "C" int xm3d_pack_i16(const int32_t *src, const int64_t *rows_dev, int64_t cap_rows, int32_t width, int16_t *dst,
+                             int32_t *status, xm3d_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    XM3D_REQUIRE(cap_rows >= 0 && width > 0, "bad sizes");
+    if (cap_rows == 0) return XM3D_OK;
+    XM3D_REQUIRE(src && dst, "null pointer");
+    int64_t blocks = (cap_rows * width + 255) / 256;
+    const int64_t maxb = (int64_t)sm_count() * 16;
+    if (blocks > maxb) blocks = maxb;
+    pack_i16_kernel<<<(unsigned)blocks, 256, 0, stream>>>(src, rows_dev, cap_rows, width, dst, status);
+    count_launches(1);
+    return check_launch("xm3d_pack_i16");
+}
 
 extern "C" int xm3d_collate_batch(const float *xyz_vis, const int64_t *vis_off, const int32_t *voxel_xyz,
                                   const int64_t *uniq_off, int32_t n_seg, int64_t cap, float *ori_coords,

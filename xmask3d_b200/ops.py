@@ -436,24 +436,37 @@ def logits(mask_embed: torch.Tensor, text_embed: torch.Tensor, null_embed: torch
 # ----------------------------------------------------------------------------- after the path
 def point_logits(feat: torch.Tensor, text_embed: torch.Tensor, logit_scale: float,
                  binary: Optional[torch.Tensor] = None, is_base: Optional[torch.Tensor] = None,
-                 want_logits: bool = True, want_argmax: bool = True):
+                 want_logits: bool = True, want_argmax: bool = True, mask_label: Optional[torch.Tensor] = None,
+                 mask_probs: Optional[torch.Tensor] = None, base_ratio: float = 0.0, novel_ratio: float = 0.0):
     """Per-point logits / argmax (run/infer.py:557, 606-640).  feat [n,c] float32 CUDA, text_embed
     [T,c]; binary [n] float32 (the binary head's 0/1 prediction) with is_base [T] bool selects the
-    base / novel blending.  Returns (logits [n,T] or None, argmax int32 [n] or None)."""
+    base / novel blending.  mask_label int32 [n] (-1 = in no final mask) with mask_probs [n_masks,T]
+    (softmax of the masks' MaskCLIP logits) turns the values into the fused stream's softmax + geometric-mean
+    ensemble of run/infer.py:568-600 (needs is_base).
+    Returns (logits [n,T] or None, argmax int32 [n] or None)."""
     _require_cuda()
     dev = feat.device
     feat = _dev_contig(feat, torch.float32)
     te = _dev_contig(text_embed, torch.float32)
     n, c = feat.shape
     t = te.shape[0]
+    if is_base is not None:
+        is_base = _dev_contig(is_base.reshape(-1).to(torch.uint8), torch.uint8)
+        assert is_base.numel() == t
     if binary is not None:
         binary = _dev_contig(binary.reshape(-1), torch.float32)
-        is_base = _dev_contig(is_base.reshape(-1).to(torch.uint8), torch.uint8)
-        assert binary.numel() == n and is_base.numel() == t
+        assert binary.numel() == n and is_base is not None
+    n_masks = 0
+    if mask_label is not None:
+        mask_label = _dev_contig(mask_label.reshape(-1), torch.int32)
+        mask_probs = _dev_contig(mask_probs, torch.float32)
+        n_masks = int(mask_probs.shape[0])
+        assert mask_label.numel() == n and mask_probs.shape[1] == t and is_base is not None
     out = torch.empty((n, t), dtype=torch.float32, device=dev) if want_logits else None
     amax = torch.empty(max(n, 1), dtype=torch.int32, device=dev) if want_argmax else None
     ws = _ws(L.lib().xm3d_point_logits_ws_bytes(t, c), dev)
     L.check(L.lib().xm3d_point_logits(_ptr(feat), n, c, _ptr(te), t, float(logit_scale), _ptr(binary), _ptr(is_base),
+                                      _ptr(mask_label), _ptr(mask_probs), n_masks, float(base_ratio), float(novel_ratio),
                                       _ptr(out), _ptr(amax), _ptr(ws), ws.numel(), _stream()))
     return out, (amax[:n] if amax is not None else None)
 
@@ -604,6 +617,20 @@ def collate(proj: Projection, vox: Unique, cap: Optional[int] = None):
     L.check(L.lib().xm3d_collate_batch(_ptr(proj.xyz_vis), _ptr(proj.vis_off), _ptr(vox.voxel_xyz), _ptr(vox.uniq_off),
                                        n_seg, cap, _ptr(ori), _ptr(coords), _stream()))
     return ori, coords
+
+
+def pack_i16(src: torch.Tensor, rows_dev: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+             status: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """int32 [rows, width] -> int16 (host-bound copies of rowcol / voxel coordinates).  rows_dev: int64 device
+    scalar (e.g. vis_off[-1:]) bounding the rows actually converted."""
+    _require_cuda()
+    src = _dev_contig(src, torch.int32)
+    rows = int(src.shape[0])
+    width = int(src.numel() // max(rows, 1))
+    if out is None:
+        out = torch.empty(src.shape, dtype=torch.int16, device=src.device)
+    L.check(L.lib().xm3d_pack_i16(_ptr(src), _ptr(rows_dev), rows, width, _ptr(out), _ptr(status), _stream()))
+    return out
 
 
 def accept_views(proj: Projection, scene_labels: torch.Tensor, view_pt_off: torch.Tensor,

@@ -66,7 +66,7 @@ class CorrespondencePipeline:
 
     def __init__(self, batch: Batch, k: int, c: int, device, cap_vis: Optional[int] = None,
                  cut_bound: int = 10, vis_thres: float = 0.25, depth_scale: float = 1000.0,
-                 pairs_per_point: float = 1.0, overlap: bool = True):
+                 pairs_per_point: float = 1.0, overlap: bool = True, pool_path: str = "auto"):
         ops._require_cuda()
         self.batch, self.k, self.c, self.dev = batch, int(k), int(c), device
         self.cut_bound, self.vis_thres, self.depth_scale = cut_bound, vis_thres, depth_scale
@@ -78,6 +78,7 @@ class CorrespondencePipeline:
         self.graph = None
         self._graph_out = None
         self.overlap = bool(overlap)                       # voxelize || (gather + pool) on two streams
+        self.pool_path = pool_path                         # "auto" | "pair_lists" | "rows" | "mma" (ops.pool)
         self._side = torch.cuda.Stream(device=device)
         self._side_status = torch.zeros(1, dtype=torch.int32, device=device)
         self.total_pv = int(self.out_off[-1])
@@ -157,7 +158,7 @@ class CorrespondencePipeline:
             times.mark("gather")
         s, cnt, mean = ops.pool(feat, pr.vis_off, self.k, member=member, cap=self.cap_vis, cap_pairs=self.cap_pairs,
                                 row_index=(pr.vis_idx if feat_per_point else None), ws=self.ws_pool,
-                                status=self._side_status)
+                                status=self._side_status, path=self.pool_path)
         if times is not None:
             times.mark("pool")
         return {"proj": pr, "vox": vox, "member": member, "sum": s, "cnt": cnt, "mean": mean,
