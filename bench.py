@@ -354,6 +354,29 @@ def run_reference(args, rank: int, world: int):
 
 
 # ----------------------------------------------------------------------------- native arm helpers
+class StdoutToStderr:
+    """NCCL prints its version banner on stdout while the communicator is created; stdout carries exactly one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
+def init_nccl(dev):
+    import torch
+    import torch.distributed as dist
+    with StdoutToStderr():
+        dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()                                  # creates the communicator (and prints the banner) now
+        torch.cuda.synchronize()
+
+
 class Timer:
     """CUDA-event timing on the current stream with the max over ranks."""
 
@@ -455,7 +478,7 @@ def run_native(args, rank: int, world: int, local_rank: int):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        init_nccl(dev)
     T = Timer(dev, world)
     pipe, masks, mode, mask_bytes, feat, xyz_h, depth_h, n_vis, total_vis, total_pairs = prepare_pipeline(
         batch, args.k, args.c, dev, args.masks, 4242 + rank, overlap=not args.no_overlap, pool_path=args.pool_path)
@@ -1046,7 +1069,7 @@ def run_split_scene(args, rank: int, world: int, local_rank: int):
     dev = torch.device("cuda", local_rank)
     gen = make_pool(4)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        init_nccl(dev)
     T = Timer(dev, world)
     r = split_scene_leg(args, rank, world, dev, gen, T, steps=args.steps)
     gen.close()

@@ -26,6 +26,13 @@ FILES = [
     "models/utils/fuser.py",              # S1     mask_mapper
     "models/modeling/meta_arch/helper.py",  # L2   ensemble_logits_with_labels
 ]
+# The reference's own CALLERS of the path (test-only): tests/test_dropin_integration.py runs ScannetLoaderFull.__getitem__
+# unmodified, once with the reference's modules and once with xmask3d_b200's drop-ins injected through sys.modules.
+FILES += [
+    "dataset/data_loader_infer.py",       # ScannetLoaderFull.__getitem__: the per-view loop around compute_mapping / voxelize
+    "dataset/point_loader.py",            # Point3DLoader (base class: builds the Voxelizer)
+    "dataset/augmentation.py",            # imported by point_loader
+]
 
 
 def vendor() -> bool:

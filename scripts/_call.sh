@@ -1,3 +1,3 @@
 set -x
-( time timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_r02_a.json 2> gpurun_out/bench_r02_a.err ) 2> gpurun_out/bench_r02_a.time; echo "rc=$?" >> gpurun_out/bench_r02_a.err
+timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/gpu_tests3.log 2>&1; echo "rc=$?" >> gpurun_out/gpu_tests3.log
 echo done

@@ -55,3 +55,29 @@ def test_ragged_mask_lists_pad_to_never_hitting_planes():
     assert torch.equal(m, torch.stack(same)) and ks == [3, 3]
     e = _stack_ragged_embeds([torch.ones(3, 6), torch.ones(5, 6), torch.ones(2, 6)], 5)
     assert e.shape == (3, 5, 6) and float(e.sum()) == (3 + 5 + 2) * 6
+
+
+def test_bench_scene_sharding_is_a_balanced_partition():
+    """bench.py's rank_scene_ids: the 8 x N distinct scenes of a job are assigned to ranks exactly once, every rank
+    gets work, and the visible-pair load (xmask3d_b200/scene_costs.json) is balanced to a few per cent; the 312-scene
+    sweep (configs[4]) likewise over 1 / 2 / 4 / 8 ranks."""
+    import argparse
+
+    import numpy as np
+
+    import bench
+    from xmask3d_b200 import dist as xd
+    for world in (1, 2, 4, 8):
+        args = argparse.Namespace(scenes=8, views=20, points=150_000, replicas=False)
+        shards = [bench.rank_scene_ids(args, r, world) for r in range(world)]
+        assert sorted(sum(shards, [])) == list(range(8 * world))
+        loads = [sum(bench.scene_cost(1000 + g, 150_000, 20) for g in s) for s in shards]
+        assert max(loads) / np.mean(loads) < 1.03
+        sizes = bench.sweep_sizes(312)
+        assert sizes.min() >= 30_000 and sizes.max() <= 500_000
+        costs = [bench.scene_cost(1000 + s, int(n), 20) for s, n in enumerate(sizes)]
+        sh = xd.shard_scenes(costs, world)
+        assert sorted(sum(sh, [])) == list(range(312))
+        ld = [sum(costs[i] for i in s) for s in sh]
+        assert max(ld) / np.mean(ld) < 1.01
+    assert bench.rank_scene_ids(argparse.Namespace(scenes=8, views=20, points=150_000, replicas=True), 3, 8) == list(range(8))
