@@ -702,7 +702,7 @@ def run_native(args, rank: int, world: int, local_rank: int):
     pool_bytes = int((4 * args.c + 4) * total_vis + V * 4 * args.k * args.c)
     pool_ms = stage_ms.get("pool_main_kernel", float("nan"))
     achieved = pool_bytes / (pool_ms * 1e-3) / 1e9
-    kernel = ("pool_mma_kernel<64> (tcgen05 tf32 hi/lo, membership bits as 0/1 operand)" if overlap_masks and args.pool_path in ("auto", "mma")
+    kernel = ("pool_mma2_kernel (tcgen05: 0/1 membership operand in TMEM, tf32 hi + bf16 lo feature tiles via TMA)" if overlap_masks and args.pool_path in ("auto", "mma")
               else "pool_rows_kernel (point-major)" if overlap_masks and args.pool_path == "rows"
               else "pool_sum_kernel<4> (pair lists)")
     # dram__bytes_read+write of this kernel from THIS ROUND's `ncu --set full` capture of the same default workload

@@ -103,6 +103,40 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
     for (uint32_t spin = 0; !mbar_try_wait(bar, phase); ++spin)
         if (spin > (1u << 26)) __trap();
 }
+// The same with a suspend-time hint: the waiting thread is parked by the hardware until the phase completes (or the
+// hint expires) instead of polling — in warp-specialised kernels the polling loops of the idle roles otherwise take
+// issue slots from the working warps (ncu on pool_mma2_kernel: 1.3 G warp instructions, half of them polls).
+__device__ __forceinline__ void mbar_wait_parked(uint64_t *bar, uint32_t phase) {
+    for (uint32_t spin = 0;; ++spin) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase), "r"(20000u) : "memory");     // up to 20 us per try
+        if (ok) return;
+        if (spin > (1u << 18)) __trap();                     // ~5 s: a wrong transaction count must trap, never hang
+    }
+}
+// Wait of a role with slack (epilogue, TMA producer): sleep between polls so that the polling loop does not take
+// issue slots from the working warps of the same SM sub-partition.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t phase, uint32_t ns) {
+    for (uint32_t spin = 0; !mbar_try_wait(bar, phase); ++spin) {
+        __nanosleep(ns);
+        if (spin > (1u << 24)) __trap();
+    }
+}
+// 32 x 32 bit-matrix transpose across the lanes of a warp: afterwards bit p of lane i = bit i of lane p before.
+__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int j = 16; j >= 1; j >>= 1) {
+        const uint32_t m = j == 16 ? 0x0000ffffu : j == 8 ? 0x00ff00ffu : j == 4 ? 0x0f0f0f0fu : j == 2 ? 0x33333333u : 0x55555555u;
+        const uint32_t y = __shfl_xor_sync(0xffffffffu, x, j);
+        x = (lane & j) ? (((y >> j) & m) | (x & ~m)) : ((x & m) | ((y & m) << j));
+    }
+    return x;
+}
 // global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned.
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

@@ -50,6 +50,7 @@ struct PoolMmaParams {
     int32_t *cnt;                // [n_seg, k] or null
     int *work;                   // item counter (zeroed by the host)
     int raw_stages, conv_stages;
+    int dbg;                     // experiments only: 1 = skip the lo MMAs, 2 = skip the hi MMAs (results are then wrong)
 };
 
 // Instrumented build (-DXM3D_PM_TIMING, scripts/exp_pool_mma.py): per-role wait / work cycles of every CTA
@@ -134,7 +135,7 @@ pool_mma_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P) 
                 long long tw0 = 0, tall = PM_CLK();
                 for (int t = 0; t < ntile; ++t) {
                     long long c0_ = PM_CLK();
-                    mbar_wait(&s_raw_empty[rs], rph ^ 1);
+                    mbar_wait_parked(&s_raw_empty[rs], rph ^ 1);
                     PM_ACC(tw0, c0_);
                     unsigned char *dst = raw_base + (size_t)rs * PM_RAW;
                     mbar_expect_tx(&s_raw_full[rs], PM_RAW);
@@ -163,11 +164,11 @@ pool_mma_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P) 
                 long long tw0 = 0, tw1 = 0, tw2 = 0, tall = PM_CLK();
                 for (int t = 0; t < ntile; ++t) {
                     long long c0_ = PM_CLK();
-                    mbar_wait(&s_raw_full[rs], rph);
+                    mbar_wait_parked(&s_raw_full[rs], rph);
                     PM_ACC(tw0, c0_); c0_ = PM_CLK();
-                    mbar_wait(&s_conv_full[cs], cph);
+                    mbar_wait_parked(&s_conv_full[cs], cph);
                     PM_ACC(tw1, c0_); c0_ = PM_CLK();
-                    mbar_wait(&s_tmem_free[buf], bph ^ 1);
+                    mbar_wait_parked(&s_tmem_free[buf], bph ^ 1);
                     PM_ACC(tw2, c0_);
                     tc_fence_after();
                     uint64_t a_hi = d_hi[0], a_lo = d_lo[0], bd = d_b[0];
@@ -199,9 +200,9 @@ pool_mma_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P) 
             long long tw0 = 0, tw1 = 0, tall = PM_CLK();
             for (int t = 0; t < ntile; ++t) {
                 long long c0_ = PM_CLK();
-                mbar_wait(&s_raw_full[rs], rph);
+                mbar_wait_parked(&s_raw_full[rs], rph);
                 PM_ACC(tw0, c0_); c0_ = PM_CLK();
-                mbar_wait(&s_conv_empty[cs], cph ^ 1);
+                mbar_wait_parked(&s_conv_empty[cs], cph ^ 1);
                 PM_ACC(tw1, c0_);
                 uint4 *raw = reinterpret_cast<uint4 *>(raw_base + (size_t)rs * PM_RAW);
                 uint4 *lo = reinterpret_cast<uint4 *>(lo_base + (size_t)cs * PM_RAW);
@@ -262,7 +263,7 @@ pool_mma_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P) 
             for (int t = 0; t < ntile; ++t) {
                 load_words(t + 2, w2);
                 long long c0_ = PM_CLK();
-                mbar_wait(&s_conv_empty[cs], cph ^ 1);
+                mbar_wait_parked(&s_conv_empty[cs], cph ^ 1);
                 PM_ACC(tw0, c0_);
                 unsigned char *bt = b_base + (size_t)cs * B_BYTES + kb * (N * 128) + ((kk & 3) << 2);
 #pragma unroll
@@ -299,7 +300,7 @@ pool_mma_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P) 
             long long tw0 = 0, tall = PM_CLK();
             for (int t = 0; t < ntile; ++t) {
                 long long c0_ = PM_CLK();
-                mbar_wait(&s_tile_done[buf], bph);
+                mbar_wait_parked(&s_tile_done[buf], bph);
                 PM_ACC(tw0, c0_);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * N + half * 64);
@@ -347,6 +348,324 @@ pool_mma_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P) 
     (void)THREADS;
 }
 
+
+// =====================================================================================================================
+// Version 2 — the membership operand lives in TENSOR MEMORY and the lo tile is bf16.
+//
+// ncu / clock64 on version 1: the kernel is bound by shared-memory bandwidth (208 KB of shared-memory traffic per
+// 32 KB feature tile: TMA write, converter read + lo write, builder write, three operand reads of the MMAs), not by
+// HBM or the tensor pipe.  Here the roles of the operands are swapped,
+//     D[M = 128 masks, N = 128 channels] += A[128 masks, K points] * B[K points, 128 channels],
+// so that the 0/1 membership matrix is the A operand and can be read from tensor memory (tcgen05.mma with A in TMEM):
+// the builder warps transpose the tile's membership words with warp ballots (lane = mask), expand them in registers
+// and store them with tcgen05.st — no shared-memory write, no shared-memory operand read.  B = the feature tile as
+// it lies in HBM (N-major): hi = the raw TMA tile (tf32, 8 points per MMA), lo = x - hi as a bf16 tile written by the
+// converters (kind::f16, 16 points per MMA; its error 2^-19 |x| is far inside the 1e-5 bar).  Shared-memory traffic
+// per tile: 32 (TMA) + 32 + 16 (converter) + 32 + 16 (MMA reads) = 128 KB.
+// TMEM map (512 columns): [0,256) two accumulator buffers of 128 channels; [256,384) two membership stages of
+// 64 points as tf32; [384,448) the same as bf16 pairs.
+constexpr int P2_LO = PM_TP * PM_SLICE * 2;          // bytes of a bf16 lo tile (16 KB)
+constexpr int P2_D = 0, P2_A32 = 256, P2_A16 = 384;  // TMEM column bases
+constexpr int P2_GROUP = 8;                                // tiles (of 64 points) per accumulator flush
+constexpr int P2_EPI_WARPS = 8, P2_THREADS = 32 * (10 + P2_EPI_WARPS);
+
+template <int UNR>                                    // converter loads in flight per thread (shared-memory latency under load)
+__global__ void __launch_bounds__(P2_THREADS, 1)
+pool_mma2_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P) {
+    constexpr int EPI_THREADS = P2_EPI_WARPS * 32;
+    extern __shared__ __align__(1024) unsigned char pm_smem[];
+    __shared__ uint64_t s_raw_full[PM_MAX_STAGES], s_raw_empty[PM_MAX_STAGES];
+    __shared__ uint64_t s_conv_full[2], s_conv_empty[2];
+    __shared__ uint64_t s_tile_done[2], s_tmem_free[2];
+    __shared__ uint32_t s_tmem;
+    __shared__ int s_item;
+    __shared__ int s_cnt[128];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    unsigned char *base = pm_smem + ((1024u - (smem_u32(pm_smem) & 1023u)) & 1023u);
+    unsigned char *raw_base = base;
+    unsigned char *lo_base = raw_base + (size_t)P.raw_stages * PM_RAW;
+
+    if (tid == 0) {
+        for (int s = 0; s < PM_MAX_STAGES; ++s) { mbar_init(&s_raw_full[s], 1); mbar_init(&s_raw_empty[s], 1); }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&s_conv_full[b], PM_CONV + PM_BUILD);
+            mbar_init(&s_conv_empty[b], 1);
+            mbar_init(&s_tile_done[b], 1);
+            mbar_init(&s_tmem_free[b], EPI_THREADS);
+        }
+        mbar_fence_init();
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map));
+    }
+    if (warp == 1) {
+        __syncwarp();
+        tmem_alloc(&s_tmem, 512);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s_tmem;
+
+    const int nsl = P.c / PM_SLICE;
+    const int n_items = P.n_seg * nsl;
+    const int64_t total_rows = P.seg_off[P.n_seg];
+    const bool over = total_rows > P.cap;
+    int rs = 0, cs = 0, buf = 0;
+    uint32_t rph = 0, cph = 0, bph = 0;
+    if (tid < 128) s_cnt[tid] = 0;
+    __syncthreads();
+
+    for (;;) {
+        if (tid == 0) s_item = atomicAdd(P.work, 1);
+        __syncthreads();
+        const int item = s_item;
+        if (item >= n_items) break;
+        const int s = item / nsl, sl = item - s * nsl;
+        const int64_t a = P.seg_off[s];
+        const int n = over ? 0 : (int)(P.seg_off[s + 1] - a);
+        const int ntile = (n + PM_TP - 1) / PM_TP;
+
+        if (warp == 0) {
+            // ===== TMA producer =====
+            if (lane == 0) {
+                long long tw0 = 0, tall = PM_CLK();
+                for (int t = 0; t < ntile; ++t) {
+                    long long c0_ = PM_CLK();
+                    mbar_wait_sleep(&s_raw_empty[rs], rph ^ 1, 200);
+                    PM_ACC(tw0, c0_);
+                    unsigned char *dst = raw_base + (size_t)rs * PM_RAW;
+                    mbar_expect_tx(&s_raw_full[rs], PM_RAW);
+                    const int y = (int)(a + (int64_t)t * PM_TP);
+#pragma unroll
+                    for (int cb = 0; cb < 4; ++cb)
+                        tma_load_2d(dst + cb * PM_CB, &map, sl * PM_SLICE + cb * 32, y, &s_raw_full[rs]);
+                    if (++rs == P.raw_stages) { rs = 0; rph ^= 1; }
+                }
+                PM_OUT(0, tw0, 0, PM_CLK() - tall, ntile);
+            }
+        } else if (warp == 1) {
+            // ===== MMA issuer: 8 tf32 MMAs (hi, 8 points each) + 4 bf16 MMAs (lo, 16 points each) per tile =====
+            if (lane == 0) {
+                const uint32_t id32 = make_idesc(128, PM_SLICE, 2, /*A: TMEM*/ 0, /*B N-major*/ 1);
+                const uint32_t id16 = make_idesc(128, PM_SLICE, 1, 0, 1);
+                uint64_t d_hi[PM_MAX_STAGES], d_lo[2];
+#pragma unroll
+                for (int q = 0; q < PM_MAX_STAGES; ++q)     // tf32 N-major: 32-byte-atom swizzle, 4 column blocks 8 KB apart
+                    d_hi[q] = make_sw128_desc_ex(raw_base + (size_t)q * PM_RAW, PM_CB, 512, 1);
+#pragma unroll
+                for (int q = 0; q < 2; ++q)                 // bf16 N-major: 128-byte swizzle, 2 blocks of 64 channels 8 KB apart
+                    d_lo[q] = make_sw128_desc_ex(lo_base + (size_t)q * P2_LO, PM_TP * 128, 1024, 2);
+                long long tw0 = 0, tw1 = 0, tw2 = 0, tall = PM_CLK();
+                for (int t = 0; t < ntile; ++t) {
+                    const bool first = t % P2_GROUP == 0, last = (t % P2_GROUP == P2_GROUP - 1) || t == ntile - 1;
+                    long long c0_ = PM_CLK();
+                    mbar_wait(&s_raw_full[rs], rph);
+                    PM_ACC(tw0, c0_); c0_ = PM_CLK();
+                    mbar_wait(&s_conv_full[cs], cph);
+                    PM_ACC(tw1, c0_); c0_ = PM_CLK();
+                    if (first) mbar_wait(&s_tmem_free[buf], bph ^ 1);      // a fresh accumulator every P2_GROUP tiles
+                    PM_ACC(tw2, c0_);
+                    tc_fence_after();
+                    uint64_t b_hi = d_hi[0];
+#pragma unroll
+                    for (int q = 1; q < PM_MAX_STAGES; ++q)
+                        if (rs == q) b_hi = d_hi[q];
+                    const uint64_t b_lo = cs ? d_lo[1] : d_lo[0];
+                    const uint32_t d = tmem_base + (uint32_t)(P2_D + buf * PM_SLICE);
+                    const uint32_t a32 = tmem_base + (uint32_t)(P2_A32 + cs * 64), a16 = tmem_base + (uint32_t)(P2_A16 + cs * 32);
+                    if (P.dbg != 2) {
+#pragma unroll
+                        for (int ks = 0; ks < PM_TP / 8; ++ks)
+                            umma_tf32_ts(d, a32 + ks * 8, b_hi + (uint64_t)((ks * 1024) >> 4), id32, (ks || !first) ? 1u : 0u);
+                    }
+                    if (P.dbg != 1) {
+#pragma unroll
+                        for (int ks = 0; ks < PM_TP / 16; ++ks)
+                            umma_f16_ts(d, a16 + ks * 8, b_lo + (uint64_t)((ks * 2048) >> 4), id16, (P.dbg == 2 && ks == 0 && first) ? 0u : 1u);
+                    }
+                    umma_commit(&s_raw_empty[rs]);
+                    umma_commit(&s_conv_empty[cs]);
+                    if (++rs == P.raw_stages) { rs = 0; rph ^= 1; }
+                    if (++cs == 2) { cs = 0; cph ^= 1; }
+                    if (last) {
+                        umma_commit(&s_tile_done[buf]);
+                        if (++buf == 2) { buf = 0; bph ^= 1; }
+                    }
+                }
+                PM_OUT(1, tw0, tw1, tw2, PM_CLK() - tall);
+            }
+        } else if (warp < 6) {
+            // ===== converters: lo = bf16(x - hi) into a 128-byte-swizzled N-major tile =====
+            const int t0 = tid - 64;
+            const int r0 = t0 >> 3, p8 = t0 & 7;
+            // logical 32-byte chunk of this thread's physical chunk (32-byte-atom swizzle of the raw tile), its 16-byte
+            // chunk inside the 64-channel block of the lo tile for even / odd 32-channel column blocks, swizzled by the row
+            const int l32 = (p8 >> 1) ^ (r0 & 3);
+            const int lo_even = r0 * 128 + ((l32 ^ (r0 & 7)) << 4) + (p8 & 1) * 8;
+            const int lo_odd = r0 * 128 + (((4 + l32) ^ (r0 & 7)) << 4) + (p8 & 1) * 8;
+            long long tw0 = 0, tw1 = 0, tw2 = 0, tall = PM_CLK();
+            for (int t = 0; t < ntile; ++t) {
+                long long c0_ = PM_CLK();
+                mbar_wait(&s_raw_full[rs], rph);
+                PM_ACC(tw0, c0_); c0_ = PM_CLK();
+                mbar_wait(&s_conv_empty[cs], cph ^ 1);
+                PM_ACC(tw1, c0_);
+                uint4 *raw = reinterpret_cast<uint4 *>(raw_base + (size_t)rs * PM_RAW);
+                unsigned char *lo = lo_base + (size_t)cs * P2_LO;
+                const int rows_valid = min(PM_TP, n - t * PM_TP);
+                // Chunk j of this thread is physical chunk q = t0 + 128 j of the raw tile ([column block][row][8 chunks]):
+                // row = r0 + 16 (j & 3), column block = j >> 2, chunk-in-row p8 — so every address below is a per-thread
+                // base plus a compile-time offset (the loop is fully unrolled).  UNR loads are issued back to back before
+                // the first one is used (the shared-memory pipe is shared with the TMA writes and the MMA operand reads).
+                for (int j0 = 0; j0 < PM_RAW / 16 / PM_CONV; j0 += UNR) {
+                    uint4 v[UNR];
+#pragma unroll
+                    for (int u = 0; u < UNR; ++u) v[u] = raw[t0 + PM_CONV * (j0 + u)];
+#pragma unroll
+                    for (int u = 0; u < UNR; ++u) {
+                        const int j = j0 + u;
+                        uint2 l = make_uint2(0u, 0u);
+                        if (r0 + 16 * (j & 3) < rows_valid) {
+                            const float l0 = __fsub_rn(__uint_as_float(v[u].x), __uint_as_float(v[u].x & 0xffffe000u));
+                            const float l1 = __fsub_rn(__uint_as_float(v[u].y), __uint_as_float(v[u].y & 0xffffe000u));
+                            const float l2 = __fsub_rn(__uint_as_float(v[u].z), __uint_as_float(v[u].z & 0xffffe000u));
+                            const float l3 = __fsub_rn(__uint_as_float(v[u].w), __uint_as_float(v[u].w & 0xffffe000u));
+                            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l.x) : "f"(l1), "f"(l0));
+                            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l.y) : "f"(l3), "f"(l2));
+                        } else {
+                            raw[t0 + PM_CONV * j] = make_uint4(0u, 0u, 0u, 0u);   // rows past the segment never reach the tensor core
+                        }
+                        // lo tile: [64-channel block j >> 3][row][16-byte chunk ^ (row & 7)][8-byte half]
+                        *reinterpret_cast<uint2 *>(lo + (((j >> 2) & 1) ? lo_odd : lo_even) + (j >> 3) * (PM_TP * 128) +
+                                                   (j & 3) * 2048) = l;
+                    }
+                }
+                c0_ = PM_CLK();
+                fence_proxy_async();
+                PM_ACC(tw2, c0_);
+                mbar_arrive(&s_conv_full[cs]);
+                if (++rs == P.raw_stages) { rs = 0; rph ^= 1; }
+                if (++cs == 2) { cs = 0; cph ^= 1; }
+            }
+            if (t0 == 0) PM_OUT(2, tw0, tw1, PM_CLK() - tall, tw2);
+        } else if (warp < 10) {
+            // ===== builders: lane = mask.  32 x 32 bit transposes (ballots) of the tile's membership words, expanded in
+            // registers to 0.0f / 1.0f (tf32) and to bf16 pairs, stored into tensor memory =====
+            const int lg = warp & 3;                              // TMEM lane group = membership word of this warp
+            const int tail = P.k & 31;
+            const bool word_ok = lg < P.words && lg * 32 < P.k;
+            auto load_word = [&](int pt) -> uint32_t {
+                uint32_t x = 0u;
+                if (word_ok && pt < n) {
+                    x = __ldg(P.member + (size_t)(a + pt) * P.words + lg);
+                    if (tail && lg == (P.k >> 5)) x &= (1u << tail) - 1u;
+                }
+                return x;
+            };
+            uint32_t wa[3], wb[3];                               // two tiles ahead (global latency > tile budget)
+            wa[0] = load_word(lane); wb[0] = load_word(32 + lane);
+            wa[1] = load_word(PM_TP + lane); wb[1] = load_word(PM_TP + 32 + lane);
+            int cnt = 0;
+            long long tw0 = 0, tw1 = 0, tall = PM_CLK();
+            for (int t = 0; t < ntile; ++t) {
+                wa[2] = load_word((t + 2) * PM_TP + lane); wb[2] = load_word((t + 2) * PM_TP + 32 + lane);
+                // points 0..31 / 32..63 of the tile inside MY mask: two 32 x 32 bit transposes (5 shuffle rounds each)
+                const uint32_t m0 = warp_transpose32(wa[0]), m1 = warp_transpose32(wb[0]);
+                cnt += __popc(m0) + __popc(m1);
+                long long c0_ = PM_CLK();
+                mbar_wait(&s_conv_empty[cs], cph ^ 1);
+                PM_ACC(tw0, c0_);
+                c0_ = PM_CLK();
+                tc_fence_after();
+                const uint32_t lane_addr = (uint32_t)(lg * 32) << 16;
+                const uint32_t a32 = tmem_base + lane_addr + (uint32_t)(P2_A32 + cs * 64);
+                const uint32_t a16 = tmem_base + lane_addr + (uint32_t)(P2_A16 + cs * 32);
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    const uint32_t bits = (h < 2 ? m0 : m1) >> ((h & 1) * 16);
+                    uint32_t v[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = ((bits >> j) & 1u) ? 0x3f800000u : 0u;
+                    tmem_st16(a32 + h * 16, v);
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t bits = h ? m1 : m0;
+                    uint32_t v[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        v[j] = (((bits >> (2 * j)) & 1u) ? 0x3f80u : 0u) | (((bits >> (2 * j + 1)) & 1u) ? 0x3f800000u : 0u);
+                    tmem_st16(a16 + h * 16, v);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                PM_ACC(tw1, c0_);
+                mbar_arrive(&s_conv_full[cs]);
+                if (++cs == 2) { cs = 0; cph ^= 1; }
+                wa[0] = wa[1]; wb[0] = wb[1]; wa[1] = wa[2]; wb[1] = wb[2];
+            }
+            s_cnt[lg * 32 + lane] = cnt;                          // exactly one thread per mask
+            if (tid == 192) PM_OUT(3, tw0, tw1, PM_CLK() - tall, 0);
+            asm volatile("bar.sync 1, %0;" ::"n"(PM_BUILD + EPI_THREADS) : "memory");
+        } else {
+            // ===== epilogue: lane = mask, 64 channels per warp =====
+            const int lg = warp & 3, half = (warp - 10) >> 2;
+            float acc[64];
+#pragma unroll
+            for (int j = 0; j < 64; ++j) acc[j] = 0.f;
+            long long tw0 = 0, tall = PM_CLK();
+            for (int g = 0; g < (ntile + P2_GROUP - 1) / P2_GROUP; ++g) {
+                long long c0_ = PM_CLK();
+                mbar_wait_sleep(&s_tile_done[buf], bph, 100);
+                PM_ACC(tw0, c0_);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(P2_D + buf * PM_SLICE + half * 64);
+#pragma unroll
+                for (int c0 = 0; c0 < 64; c0 += 32) {
+                    uint32_t v0[16], v1[16];
+                    tmem_ld16_nowait(taddr + c0, v0);
+                    tmem_ld16_nowait(taddr + c0 + 16, v1);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        acc[c0 + j] = __fadd_rn(acc[c0 + j], __uint_as_float(v0[j]));
+                        acc[c0 + 16 + j] = __fadd_rn(acc[c0 + 16 + j], __uint_as_float(v1[j]));
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&s_tmem_free[buf]);
+                if (++buf == 2) { buf = 0; bph ^= 1; }
+            }
+            if (tid == 320) PM_OUT(4, tw0, 0, PM_CLK() - tall, 0);
+            asm volatile("bar.sync 1, %0;" ::"n"(PM_BUILD + EPI_THREADS) : "memory");
+            const int m = lg * 32 + lane;
+            if (m < P.k) {
+                const int nm = s_cnt[m];
+                const size_t o = ((size_t)s * P.k + m) * P.c + (size_t)sl * PM_SLICE + half * 64;
+                float4 *so = reinterpret_cast<float4 *>(P.sum + o);
+                float4 *mo = P.mean ? reinterpret_cast<float4 *>(P.mean + o) : nullptr;
+                const float d = (float)nm;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float4 v = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+                    so[j] = v;
+                    if (mo) mo[j] = nm > 0 ? make_float4(__fdiv_rn(v.x, d), __fdiv_rn(v.y, d), __fdiv_rn(v.z, d), __fdiv_rn(v.w, d))
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                if (P.cnt && sl == 0 && half == 0) P.cnt[s * P.k + m] = nm;
+            }
+        }
+        __syncthreads();                                          // item done: outputs written, s_cnt consumed
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        __syncwarp();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
 #ifdef XM3D_PM_TIMING
 extern "C" __attribute__((visibility("default"))) int xm3d_pool_mma_debug(void *dev_buf) {
     return (int)cudaMemcpyToSymbol(g_pm_dbg, &dev_buf, sizeof(void *));
@@ -372,7 +691,7 @@ int launch_pool_mma(const float *feat, int c, const uint32_t *member, int words,
     }
     PoolMmaParams P;
     P.member = member; P.seg_off = seg_off; P.words = words; P.k = k; P.n_seg = n_seg; P.c = c; P.cap = cap;
-    P.sum = sum; P.mean = mean; P.cnt = cnt; P.work = work;
+    P.sum = sum; P.mean = mean; P.cnt = cnt; P.work = work; P.dbg = (tune >> 14) & 3;
     const int n_items = n_seg * (c / PM_SLICE);
     const unsigned grid = (unsigned)(n_items < sm_count() ? n_items : sm_count());
     cudaMemsetAsync(work, 0, sizeof(int), stream);
@@ -382,6 +701,25 @@ int launch_pool_mma(const float *feat, int c, const uint32_t *member, int words,
         cudaFuncSetAttribute(pool_mma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     }
     const int t_rs = tune & 15, t_cs = (tune >> 4) & 15;
+    const bool v1 = (tune >> 8) & 1;                      // experiments: the first version (membership operand in shared memory)
+    const bool out16 = reinterpret_cast<uintptr_t>(sum) % 16 == 0 && (!mean || reinterpret_cast<uintptr_t>(mean) % 16 == 0);
+    if (!v1 && out16) {
+        static std::atomic<uint64_t> attr2{0};
+        if (first_use_on_device(&attr2)) {
+            cudaFuncSetAttribute(pool_mma2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+            cudaFuncSetAttribute(pool_mma2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+            cudaFuncSetAttribute(pool_mma2_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+        }
+        P.raw_stages = (t_rs >= 1 && t_rs <= PM_MAX_STAGES) ? t_rs : 4;
+        P.conv_stages = 2;
+        const size_t smem2 = (size_t)P.raw_stages * PM_RAW + 2 * (size_t)P2_LO + 1024;
+        const int unr = (tune >> 12) & 3;                  // experiments: 0 = default
+        if (unr == 1) pool_mma2_kernel<4><<<grid, P2_THREADS, smem2, stream>>>(map, P);
+        else if (unr == 2) pool_mma2_kernel<8><<<grid, P2_THREADS, smem2, stream>>>(map, P);
+        else pool_mma2_kernel<16><<<grid, P2_THREADS, smem2, stream>>>(map, P);      // measured: 2.16 ms (8: 2.50, 4: 2.18)
+        count_launches(1);
+        return check_launch("xm3d_pool_batch (tensor-core path)");
+    }
     const int bb = (k <= 64 ? 64 : 128) * PM_TP * 4;
     const bool tuned = t_rs >= 1 && t_rs <= PM_MAX_STAGES && t_cs >= 1 && t_cs <= PM_MAX_STAGES &&
                        (size_t)t_rs * PM_RAW + (size_t)t_cs * (PM_RAW + bb) + 1024 <= 226 * 1024;
