@@ -707,7 +707,7 @@ def run_native(args, rank: int, world: int, local_rank: int):
               else "pool_sum_kernel<4> (pair lists)")
     # dram__bytes_read+write of this kernel from THIS ROUND's `ncu --set full` capture of the same default workload
     traffic, traffic_src = None, None
-    tname = "r02_pool_mma_kernel_ncu_full.json" if overlap_masks else "r02_pool_sum_kernel_ncu_full.json"
+    tname = "r02_pool_mma2_kernel_ncu_full.json" if overlap_masks else "r02_pool_sum_kernel_ncu_full.json"
     default_wl = (args.scenes, args.views, args.points, args.k, args.c, world) == (8, 20, 150_000, 50, 768, 1)
     tpath = os.path.join(ROOT, "profiles", tname)
     if default_wl and os.path.exists(tpath):
