@@ -1,7 +1,5 @@
 set -x
-B="python bench.py --profile-steps 2 --no-cpu --extras none"
-$B > gpurun_out/p_plain1.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_launches.csv $B > gpurun_out/p_ncu1.log 2>&1
-$B > gpurun_out/p_plain1.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:pool_sum_kernel -s 1 -c 1 -o gpurun_out/prof_r02_pool_sum $B > gpurun_out/p_ncu2.log 2>&1
-python scripts/prof_pool_mma.py 0 > gpurun_out/p_plain3.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:pool_mma2 -s 2 -c 1 -o gpurun_out/prof_r02_pool_mma2 python scripts/prof_pool_mma.py 0 > gpurun_out/p_ncu3.log 2>&1
-python scripts/prof_kernels.py > gpurun_out/p_plain4.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:point_logits_kernel -c 4 -o gpurun_out/prof_r02_point_logits python scripts/prof_kernels.py > gpurun_out/p_ncu4.log 2>&1
+( time timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/bench_r02_n8.json 2> gpurun_out/bench_r02_n8.err ) 2> gpurun_out/bench_r02_n8.time; echo "rc=$?" >> gpurun_out/bench_r02_n8.err
+nvidia-smi topo -m > gpurun_out/topo_n8.txt 2>&1
+lscpu | head -25 > gpurun_out/lscpu_n8.txt 2>&1
 echo done
