@@ -1,5 +1,4 @@
 set -x
-( time timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/bench_r02_n8.json 2> gpurun_out/bench_r02_n8.err ) 2> gpurun_out/bench_r02_n8.time; echo "rc=$?" >> gpurun_out/bench_r02_n8.err
-nvidia-smi topo -m > gpurun_out/topo_n8.txt 2>&1
-lscpu | head -25 > gpurun_out/lscpu_n8.txt 2>&1
+timeout 600 python scripts/dbg_pool_mma.py > gpurun_out/dbg_pool_mma2.log 2>&1; echo "rc=$?" >> gpurun_out/dbg_pool_mma2.log
+XM3D_SO=xmask3d_b200/libxm3d_dbg.so timeout 600 python scripts/exp_pool_mma.py 0 > gpurun_out/exp_pool_mma2.log 2>&1; echo "rc=$?" >> gpurun_out/exp_pool_mma2.log
 echo done
