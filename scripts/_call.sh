@@ -1,4 +1,5 @@
 set -x
-timeout 600 python scripts/dbg_pool_mma.py > gpurun_out/dbg_pool_mma2.log 2>&1; echo "rc=$?" >> gpurun_out/dbg_pool_mma2.log
-XM3D_SO=xmask3d_b200/libxm3d_dbg.so timeout 600 python scripts/exp_pool_mma.py 0 > gpurun_out/exp_pool_mma2.log 2>&1; echo "rc=$?" >> gpurun_out/exp_pool_mma2.log
+timeout 900 python -m pytest tests -m gpu -q -k "logits or autograd or abi" > gpurun_out/gpu_tests5.log 2>&1; echo "rc=$?" >> gpurun_out/gpu_tests5.log
+timeout 300 python scripts/time_logits.py > gpurun_out/time_logits.log 2>&1
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "rc=$?" >> gpurun_out/smoke.log
 echo done

@@ -6,17 +6,17 @@
 //   out[r, g]        = reduce_{t in group g} scale * <me_r/|me_r|, te_t/|te_t|>
 //   out[r, n_groups] = scale * <me_r/|me_r|, null/|null|>
 //
-// The (rows x C) . (C x T) contraction is the only tensor-core work on the path.  fp32 inputs
-// are split into two TF32-exact planes (hi = top 19 bits, lo = tf32(x - hi)) by a prep kernel
-// that also produces the inverse L2 norms; the GEMM kernel then issues three tcgen05.mma
-// kind::tf32 products per k-step (hi*hi + hi*lo + lo*hi, "3xTF32") into one fp32 accumulator in
-// tensor memory, which reproduces fp32 dot products to ~1e-6 relative so that argmax matches the
-// reference's fp32 matmul.  Operands are staged by TMA (cp.async.bulk.tensor, 128-byte swizzle)
-// through an mbarrier ring: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA
-// issuer, warps 2-5 = epilogue (tcgen05.ld -> normalise, scale, synonym-group max/mean, argmax).
+// The (rows x C) . (C x T) contraction runs on the tensor cores as 3xTF32 (hi*hi + lo*hi + hi*lo with the operands
+// split into TF32-exact hi / lo parts and fp32 accumulation in tensor memory), which reproduces fp32 dot products to
+// ~1e-6 relative so that argmax matches the reference's fp32 matmul.  ONE kernel serves the mask-level logits
+// (xm3d_logits: rows = B*K mask embeddings, synonym-group reduction + null column in the epilogue) and the per-point
+// logits (xm3d_point_logits): the rows are read from HBM exactly once as raw fp32 tiles by TMA and split in shared
+// memory; only the (small) text side goes through a prep kernel.  Round 1 ran the mask-level logits as prep (2 launches
+// writing hi / lo planes of the mask embeddings to HBM) + GEMM; that kernel is gone.
 #include <cuda.h>
 
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "tc.cuh"
@@ -51,157 +51,6 @@ logits_prep_kernel(const float *__restrict__ a, const float *__restrict__ b, int
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     // F.normalize: x / max(||x||_2, 1e-12)
     if (lane == 0) inv_norm[row] = __fdiv_rn(1.0f, fmaxf(sqrtf(ss), 1e-12f));
-}
-
-struct LogitsParams {
-    int64_t rows;
-    int c, n_cols, n_text, n_groups, bn, stages, tmem_cols;
-    int ensemble_mean;
-    float scale;
-    const float *inv_norm;      // [rows + n_cols]
-    const int *group_off;       // device [n_groups + 1]
-    float *out;                 // [rows, n_groups + 1]
-    int *argmax;                // [rows] or null
-};
-
-__global__ void __launch_bounds__(LG_THREADS, 1)
-logits_mma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-                  const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-                  const LogitsParams P) {
-    extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ uint64_t s_full[4], s_empty[4], s_done;
-    __shared__ uint32_t s_tmem;
-    __shared__ float s_invb[LG_MAX_N];
-    __shared__ short s_gid[LG_MAX_N];           // output column of each GEMM column
-    __shared__ short s_glen[LG_MAX_N];          // >0 on the last column of a group: the group's length
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int m0 = blockIdx.x * LG_BM;
-    const int nkb = (P.c + LG_BK - 1) / LG_BK;
-    const uint32_t a_bytes = LG_BM * LG_BK * 4, b_bytes = (uint32_t)P.bn * LG_BK * 4;
-    const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
-    // 128-byte swizzle atoms need 1024-byte aligned tiles: re-align defensively (the launch adds
-    // 1 KB of slack); every tile size is a multiple of 1024 B
-    unsigned char *tiles = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
-
-    for (int j = tid; j < LG_MAX_N; j += LG_THREADS) {
-        s_invb[j] = j < P.n_cols ? P.inv_norm[P.rows + j] : 0.f;
-        s_gid[j] = 0;
-        s_glen[j] = 0;
-    }
-    if (warp == 0 && lane == 0) {
-        for (int s = 0; s < P.stages; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 1); }
-        mbar_init(&s_done, 1);
-        mbar_fence_init();
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_hi));
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_lo));
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_hi));
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_lo));
-    }
-    if (warp == 1) {
-        __syncwarp();
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                     ::"r"(smem_u32(&s_tmem)), "r"((uint32_t)P.tmem_cols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    __syncthreads();
-    // group bookkeeping (after the zero fill above)
-    for (int g = tid; g <= P.n_groups; g += LG_THREADS) {
-        const int lo = g < P.n_groups ? P.group_off[g] : P.n_text;
-        const int hi = g < P.n_groups ? P.group_off[g + 1] : P.n_text + 1;
-        for (int j = lo; j < hi && j < LG_MAX_N; ++j) s_gid[j] = (short)g;
-        if (hi - 1 < LG_MAX_N && hi > lo) s_glen[hi - 1] = (short)(hi - lo);
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = s_tmem;
-
-    if (warp == 0) {
-        // ===== TMA producer (one lane) =====
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int kb = 0; kb < nkb; ++kb) {
-                mbar_wait(&s_empty[stage], phase ^ 1);
-                unsigned char *st = tiles + (size_t)stage * stage_bytes;
-                mbar_expect_tx(&s_full[stage], stage_bytes);
-                tma_load_2d(st, &map_a_hi, kb * LG_BK, m0, &s_full[stage]);
-                tma_load_2d(st + a_bytes, &map_a_lo, kb * LG_BK, m0, &s_full[stage]);
-                tma_load_2d(st + 2 * a_bytes, &map_b_hi, kb * LG_BK, 0, &s_full[stage]);
-                tma_load_2d(st + 2 * a_bytes + b_bytes, &map_b_lo, kb * LG_BK, 0, &s_full[stage]);
-                if (++stage == P.stages) { stage = 0; phase ^= 1; }
-            }
-        }
-    } else if (warp == 1) {
-        // ===== MMA issuer (one lane) =====
-        if (lane == 0) {
-            // instruction descriptor: D=f32, A=B=tf32, K-major both, N = bn, M = 128
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(P.bn >> 3) << 17) |
-                                   ((uint32_t)(LG_BM >> 4) << 24);
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int kb = 0; kb < nkb; ++kb) {
-                mbar_wait(&s_full[stage], phase);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                unsigned char *st = tiles + (size_t)stage * stage_bytes;
-                const uint64_t a_hi = make_sw128_desc(st), a_lo = make_sw128_desc(st + a_bytes);
-                const uint64_t b_hi = make_sw128_desc(st + 2 * a_bytes), b_lo = make_sw128_desc(st + 2 * a_bytes + b_bytes);
-#pragma unroll
-                for (int k = 0; k < LG_BK / LG_UMMA_K; ++k) {
-                    const uint64_t adv = (uint64_t)((k * LG_UMMA_K * 4) >> 4);   // bytes >> 4 inside the swizzle row
-                    umma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, (kb | k) ? 1u : 0u);
-                    umma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
-                    umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, 1u);
-                }
-                umma_commit(&s_empty[stage]);          // frees the smem slot when these MMAs retire
-                if (++stage == P.stages) { stage = 0; phase ^= 1; }
-            }
-            umma_commit(&s_done);                       // accumulator complete
-        }
-    } else {
-        // ===== epilogue: warps 2..5 own TMEM lane groups (warp % 4) =====
-        mbar_wait(&s_done, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int lg = warp & 3;
-        const int64_t r = (int64_t)m0 + lg * 32 + lane;
-        const bool row_ok = r < P.rows;
-        const float inv_a = row_ok ? P.inv_norm[r] : 0.f;
-        const int out_w = P.n_groups + 1;
-        float gacc = P.ensemble_mean ? 0.f : -INFINITY;
-        float best = -INFINITY;
-        int best_i = 0;
-        for (int c0 = 0; c0 < P.bn; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0, v);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int col = c0 + j;
-                if (col < P.n_cols) {
-                    // (me/|me|).(te/|te|) * scale, normalisation applied to the fp32 dot product
-                    const float val = P.scale * ((__uint_as_float(v[j]) * inv_a) * s_invb[col]);
-                    gacc = P.ensemble_mean ? gacc + val : fmaxf(gacc, val);
-                    const int glen = s_glen[col];
-                    if (glen > 0) {
-                        const float o = P.ensemble_mean ? __fdiv_rn(gacc, (float)glen) : gacc;
-                        const int g = s_gid[col];
-                        if (row_ok) P.out[r * out_w + g] = o;
-                        if (o > best) { best = o; best_i = g; }
-                        gacc = P.ensemble_mean ? 0.f : -INFINITY;
-                    }
-                }
-            }
-        }
-        if (row_ok && P.argmax) P.argmax[r] = best_i;
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 1) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        __syncwarp();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)P.tmem_cols)
-                     : "memory");
-    }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -249,21 +98,6 @@ bool make_row_tile_map(CUtensorMap *m, const float *base, int64_t rows, int c, i
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-struct LogitsWs {
-    float *hi, *lo, *inv_norm;
-    int *group_off;
-};
-static LogitsWs carve_logits(void *ws, int64_t rows, int n_cols, int c, int n_groups, size_t *bytes) {
-    Carver cv(ws);
-    LogitsWs w;
-    w.hi = cv.take<float>((size_t)(rows + n_cols) * c);
-    w.lo = cv.take<float>((size_t)(rows + n_cols) * c);
-    w.inv_norm = cv.take<float>((size_t)(rows + n_cols));
-    w.group_off = cv.take<int>((size_t)n_groups + 1);
-    *bytes = cv.off + 256;
-    return w;
-}
-
 // ============================================================================================
 // Per-point logits: logit_scale * (normalize(feature) @ normalize(text).T) for
 // every visible point, base / novel blending with the binary head and argmax — the pattern of
@@ -300,8 +134,12 @@ struct PointLogitsParams {
     const float *mask_probs;     // [n_masks, n_text] softmax(final_pred_open_logits)
     int n_masks;
     float base_ratio, novel_ratio;
-    float *out;                  // [rows, n_text] or null
+    float *out;                  // [rows, n_text] (or [rows, n_groups] when grouped) or null
     int *argmax;                 // [rows] or null
+    // synonym-group reduction of cal_pred_logits (helper.py:72-97): column groups [group_off[g], group_off[g+1]) are
+    // reduced (max / mean) to one output column; null: one output column per text row
+    const int *group_off;        // device [n_groups + 1] or null
+    int n_groups, ensemble_mean;
 };
 
 __global__ void __launch_bounds__(PL_THREADS, 2)
@@ -313,6 +151,8 @@ point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     __shared__ float s_invb[LG_MAX_N];
     __shared__ unsigned char s_base[LG_MAX_N];
     __shared__ float s_ss[LG_BM];
+    __shared__ short s_gid[LG_MAX_N];           // output column of each GEMM column (grouped mode)
+    __shared__ short s_glen[LG_MAX_N];          // > 0 on the last column of a group: the group's length
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t m0 = (int64_t)blockIdx.x * LG_BM;
@@ -324,6 +164,16 @@ point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     for (int j = tid; j < LG_MAX_N; j += PL_THREADS) {
         s_invb[j] = j < P.n_text ? P.inv_norm_b[j] : 0.f;
         s_base[j] = (j < P.n_text && P.is_base) ? P.is_base[j] : 0;
+        s_gid[j] = 0;
+        s_glen[j] = 0;
+    }
+    if (P.group_off) {
+        __syncthreads();
+        for (int g = tid; g < P.n_groups; g += PL_THREADS) {
+            const int lo = P.group_off[g], hi = P.group_off[g + 1];
+            for (int j = lo; j < hi && j < LG_MAX_N; ++j) s_gid[j] = (short)g;
+            if (hi > lo && hi - 1 < LG_MAX_N) s_glen[hi - 1] = (short)(hi - lo);
+        }
     }
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < P.stages; ++s) {
@@ -495,6 +345,7 @@ point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
         }
         float best = -INFINITY;
+        float gacc = P.ensemble_mean ? 0.f : -INFINITY;
         int best_i = 0;
         for (int c0 = 0; c0 < P.bn; c0 += 16) {
             uint32_t v[16], v2[16];
@@ -521,8 +372,20 @@ point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         const float lb = s_base[col] ? val : -1e10f, ln = s_base[col] ? -1e10f : val;
                         val = __fadd_rn(__fmul_rn(b, lb), __fmul_rn(__fsub_rn(1.0f, b), ln));
                     }
-                    if (row_ok && P.out) P.out[r * P.n_text + col] = val;
-                    if (val > best) { best = val; best_i = col; }
+                    if (P.group_off) {
+                        gacc = P.ensemble_mean ? gacc + val : fmaxf(gacc, val);
+                        const int glen = s_glen[col];
+                        if (glen > 0) {
+                            const float o = P.ensemble_mean ? __fdiv_rn(gacc, (float)glen) : gacc;
+                            const int g = s_gid[col];
+                            if (row_ok && P.out) P.out[r * P.n_groups + g] = o;
+                            if (o > best) { best = o; best_i = g; }
+                            gacc = P.ensemble_mean ? 0.f : -INFINITY;
+                        }
+                    } else {
+                        if (row_ok && P.out) P.out[r * P.n_text + col] = val;
+                        if (val > best) { best = val; best_i = col; }
+                    }
                 }
             }
         }
@@ -543,10 +406,17 @@ point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 
 using namespace xm3d;
 
+static int launch_point_logits(const float *feat, int64_t rows, int c, const float *b_hi, const float *b_lo,
+                               const float *inv_b, int n_cols, PointLogitsParams P, cudaStream_t stream, const char *who);
+
 extern "C" size_t xm3d_logits_ws_bytes(int64_t rows, int32_t n_text, int32_t c, int32_t n_groups) {
-    size_t b = 0;
-    carve_logits(nullptr, rows, n_text + 1, c, n_groups, &b);
-    return b;
+    (void)rows;
+    Carver cv(nullptr);
+    cv.take<float>((size_t)(n_text + 1) * c);
+    cv.take<float>((size_t)(n_text + 1) * c);
+    cv.take<float>((size_t)(n_text + 1));
+    cv.take<int>((size_t)n_groups + 2);
+    return cv.off + 256;
 }
 
 extern "C" int xm3d_logits(const float *mask_embed, int64_t rows, int32_t c, const float *text_embed,
@@ -556,55 +426,36 @@ extern "C" int xm3d_logits(const float *mask_embed, int64_t rows, int32_t c, con
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     XM3D_REQUIRE(rows >= 0 && c > 0 && n_text > 0 && n_groups > 0, "bad sizes");
     XM3D_REQUIRE(c % 4 == 0, "embedding width must be a multiple of 4");
-    XM3D_REQUIRE(n_text + 1 <= LG_MAX_N, "at most 255 text embeddings");
+    XM3D_REQUIRE(n_text + 1 <= LG_MAX_N && n_groups + 2 <= 512, "at most 255 text embeddings");
     XM3D_REQUIRE(mask_embed && text_embed && null_embed && group_off_host && out && ws, "null pointer");
     XM3D_REQUIRE(group_off_host[0] == 0 && group_off_host[n_groups] == n_text, "group offsets must span [0, n_text]");
+    XM3D_REQUIRE(reinterpret_cast<uintptr_t>(mask_embed) % 16 == 0, "mask_embed must be 16-byte aligned");
+    XM3D_REQUIRE(rows < ((int64_t)1 << 31) - LG_BM, "rows exceed int32 tile coordinates");
     for (int g = 0; g < n_groups; ++g)
         XM3D_REQUIRE(group_off_host[g + 1] > group_off_host[g], "empty label group");
     if (rows == 0) return XM3D_OK;
-    const int n_cols = n_text + 1;
-    size_t need = 0;
-    LogitsWs w = carve_logits(ws, rows, n_cols, c, n_groups, &need);
-    if (ws_bytes < need) {
+    if (ws_bytes < xm3d_logits_ws_bytes(rows, n_text, c, n_groups)) {
         set_error("xm3d_logits: workspace too small");
         return XM3D_ERR_WORKSPACE;
     }
-    cudaMemcpyAsync(w.group_off, group_off_host, sizeof(int) * (n_groups + 1), cudaMemcpyHostToDevice, stream);
-    // rows of A first, then text rows, then the null row (two launches keep the kernel simple)
-    const int wpb = 8;
-    logits_prep_kernel<<<(unsigned)((rows + wpb - 1) / wpb), 256, 0, stream>>>(mask_embed, nullptr, rows, 0, c, w.hi,
-                                                                               w.lo, w.inv_norm); count_launches(1);
-    logits_prep_kernel<<<(unsigned)((n_cols + wpb - 1) / wpb), 256, 0, stream>>>(
-        text_embed, null_embed, n_text, 1, c, w.hi + (size_t)rows * c, w.lo + (size_t)rows * c, w.inv_norm + rows); count_launches(1);
-
-    LogitsParams P;
-    P.rows = rows; P.c = c; P.n_cols = n_cols; P.n_text = n_text; P.n_groups = n_groups;
-    P.bn = (n_cols + 15) / 16 * 16;
-    P.ensemble_mean = ensemble_mean; P.scale = logit_scale; P.inv_norm = w.inv_norm; P.group_off = w.group_off;
-    P.out = out; P.argmax = argmax;
-    int tc = 32;
-    while (tc < P.bn) tc <<= 1;
-    P.tmem_cols = tc;
-    const size_t stage_bytes = 2 * (size_t)LG_BM * LG_BK * 4 + 2 * (size_t)P.bn * LG_BK * 4;
-    int stages = (int)((220 * 1024) / stage_bytes);
-    if (stages > 4) stages = 4;
-    if (stages < 1) { set_error("xm3d_logits: tile does not fit shared memory"); return XM3D_ERR_UNSUPPORTED; }
-    P.stages = stages;
-
-    CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-    if (!make_map(&ma_hi, w.hi, rows, c, LG_BM) || !make_map(&ma_lo, w.lo, rows, c, LG_BM) ||
-        !make_map(&mb_hi, w.hi + (size_t)rows * c, n_cols, c, P.bn) ||
-        !make_map(&mb_lo, w.lo + (size_t)rows * c, n_cols, c, P.bn)) {
-        set_error("xm3d_logits: cuTensorMapEncodeTiled failed");
-        return XM3D_ERR_CUDA;
-    }
-    const size_t smem = stage_bytes * stages + 1024;
-    static std::atomic<uint64_t> attr_set{0};
-    if (first_use_on_device(&attr_set)) {
-        cudaFuncSetAttribute(logits_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
-    }
-    logits_mma_kernel<<<(unsigned)((rows + LG_BM - 1) / LG_BM), LG_THREADS, smem, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, P); count_launches(1);
-    return check_launch("xm3d_logits");
+    const int n_cols = n_text + 1;                        // the null embedding is one more column, its own group
+    Carver cv(ws);
+    float *b_hi = cv.take<float>((size_t)n_cols * c);
+    float *b_lo = cv.take<float>((size_t)n_cols * c);
+    float *inv_b = cv.take<float>((size_t)n_cols);
+    int *goff = cv.take<int>((size_t)n_groups + 2);
+    int host_off[512];
+    for (int g = 0; g <= n_groups; ++g) host_off[g] = group_off_host[g];
+    host_off[n_groups + 1] = n_cols;
+    // (pageable source: the copy is staged by the driver before the call returns)
+    cudaMemcpyAsync(goff, host_off, sizeof(int) * (n_groups + 2), cudaMemcpyHostToDevice, stream);
+    logits_prep_kernel<<<(unsigned)((n_cols + 7) / 8), 256, 0, stream>>>(text_embed, null_embed, n_text, 1, c, b_hi, b_lo, inv_b);
+    count_launches(1);
+    PointLogitsParams P;
+    memset(&P, 0, sizeof(P));
+    P.scale = logit_scale; P.out = out; P.argmax = argmax;
+    P.group_off = goff; P.n_groups = n_groups + 1; P.ensemble_mean = ensemble_mean;
+    return launch_point_logits(mask_embed, rows, c, b_hi, b_lo, inv_b, n_cols, P, stream, "xm3d_logits");
 }
 
 extern "C" size_t xm3d_point_logits_ws_bytes(int32_t n_text, int32_t c) {
@@ -642,9 +493,15 @@ extern "C" int xm3d_point_logits(const float *feat, int64_t rows, int32_t c, con
     count_launches(1);
 
     PointLogitsParams P;
-    P.rows = rows; P.c = c; P.n_text = n_text; P.bn = (n_text + 15) / 16 * 16; P.scale = logit_scale;
-    P.inv_norm_b = inv_b; P.binary = binary; P.is_base = is_base; P.out = out; P.argmax = argmax;
+    memset(&P, 0, sizeof(P));
+    P.scale = logit_scale; P.binary = binary; P.is_base = is_base; P.out = out; P.argmax = argmax;
     P.mask_label = mask_label; P.mask_probs = mask_probs; P.n_masks = n_masks; P.base_ratio = base_ratio; P.novel_ratio = novel_ratio;
+    return launch_point_logits(feat, rows, c, b_hi, b_lo, inv_b, n_text, P, stream, "xm3d_point_logits");
+}
+
+static int launch_point_logits(const float *feat, int64_t rows, int c, const float *b_hi, const float *b_lo,
+                               const float *inv_b, int n_text, PointLogitsParams P, cudaStream_t stream, const char *who) {
+    P.rows = rows; P.c = c; P.n_text = n_text; P.bn = (n_text + 15) / 16 * 16; P.inv_norm_b = inv_b;
     P.fused = (2 * P.bn <= 256) ? 1 : 0;
     int tc = 32;
     while (tc < (P.fused ? 2 * P.bn : P.bn)) tc <<= 1;
@@ -655,12 +512,12 @@ extern "C" int xm3d_point_logits(const float *feat, int64_t rows, int32_t c, con
     int stages = (int)((108 * 1024) / stage_bytes);
     if (stages < 2) stages = (int)((220 * 1024) / stage_bytes);
     if (stages > 4) stages = 4;
-    if (stages < 1) { set_error("xm3d_point_logits: tile does not fit shared memory"); return XM3D_ERR_UNSUPPORTED; }
+    if (stages < 1) { set_error("%s: tile does not fit shared memory", who); return XM3D_ERR_UNSUPPORTED; }
     P.stages = stages;
     CUtensorMap ma, mbh, mbl;
     if (!make_map(&ma, feat, rows, c, LG_BM) || !make_map(&mbh, b_hi, n_text, c, P.bn) ||
         !make_map(&mbl, b_lo, n_text, c, P.bn)) {
-        set_error("xm3d_point_logits: cuTensorMapEncodeTiled failed");
+        set_error("%s: cuTensorMapEncodeTiled failed", who);
         return XM3D_ERR_CUDA;
     }
     static std::atomic<uint64_t> attr_set{0};
@@ -670,5 +527,6 @@ extern "C" int xm3d_point_logits(const float *feat, int64_t rows, int32_t c, con
     point_logits_kernel<<<(unsigned)((rows + LG_BM - 1) / LG_BM), PL_THREADS, stage_bytes * stages + 1024, stream>>>(ma, mbh,
                                                                                                                  mbl, P);
     count_launches(1);
-    return check_launch("xm3d_point_logits");
+    return check_launch(who);
 }
+
