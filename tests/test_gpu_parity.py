@@ -791,6 +791,23 @@ def test_abi_error_reporting(dev):
     assert int(u.status.item()) & L.FLAG_VIS_OVERFLOW and int(u.m.sum().item()) == 0
 
 
+def test_pack_i16(dev):
+    """Host-bound int16 copies of x/y labels and voxel coordinates: exact below 32768, device row count honoured,
+    out-of-range values clamped and flagged."""
+    from xmask3d_b200 import _lib as L, ops
+    g = torch.Generator(device=dev).manual_seed(1)
+    src = torch.randint(-3000, 32767, (100_003, 3), device=dev, generator=g, dtype=torch.int32)
+    rows = torch.tensor([77_777], dtype=torch.int64, device=dev)
+    out = torch.full((100_003, 3), -7, dtype=torch.int16, device=dev)
+    st = torch.zeros(1, dtype=torch.int32, device=dev)
+    ops.pack_i16(src, rows, out=out, status=st)
+    assert torch.equal(out[:77_777].to(torch.int32), src[:77_777]) and bool((out[77_777:] == -7).all()) and int(st.item()) == 0
+    src[5, 1] = 40_000
+    src[9, 0] = -50_000
+    o2 = ops.pack_i16(src, status=st)
+    assert int(st.item()) == L.FLAG_I16_RANGE and int(o2[5, 1]) == 32767 and int(o2[9, 0]) == -32768
+
+
 def test_vote_accumulation(cport, dev):
     """Cross-view votes (run/infer.py:642-647, :658) on the projection's compaction outputs."""
     from oracle import ref_port as P

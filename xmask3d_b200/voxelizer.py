@@ -119,17 +119,38 @@ def voxelize_views(coords_list, rigid_transformations, device=None):
     rt = torch.from_numpy(np.ascontiguousarray(np.stack([np.asarray(r, np.float64)[:3, :4]
                                                          for r in rigid_transformations]))).to(dev)
     u = ops.voxelize_batch(xyz, torch.from_numpy(off).to(dev), rt)
-    status = int(u.status.item())
+    # ONE host synchronisation: all results are copied asynchronously into cached pinned buffers first
+    total = int(off[-1])
+    host = _to_host({"status": u.status, "m": u.m, "uoff": u.uniq_off, "first": u.first[:total], "inverse": u.inverse[:total],
+                     "voxel": u.voxel_xyz[:total]})
+    status = int(host["status"][0])
     if status:
         raise RuntimeError(f"voxelize: device status flags {status:#x} (grid range / sentinel / capacity)")
-    m = u.m.cpu().numpy()
-    uoff = u.uniq_off.cpu().numpy()
-    first = u.first.cpu().numpy()
-    inverse = u.inverse.cpu().numpy()
-    voxel = u.voxel_xyz.cpu().numpy()
+    m, uoff, first, inverse, voxel = host["m"], host["uoff"], host["first"], host["inverse"], host["voxel"]
     out = []
     for i in range(len(n)):
         a, b = int(uoff[i]), int(uoff[i]) + int(m[i])
         out.append((voxel[a:b].astype(np.float64), first[a:b].astype(np.int64),
                     inverse[off[i]:off[i + 1]].astype(np.int64)))
     return out
+
+
+_PINNED = {}
+
+
+def _to_host(tensors):
+    """Device tensors -> numpy arrays with one stream synchronisation (pinned staging buffers are cached and grow
+    only; the returned arrays are views of them, valid until the next call)."""
+    out = {}
+    for name, t in tensors.items():
+        t = t.contiguous()
+        nbytes = t.numel() * t.element_size()
+        buf = _PINNED.get(name)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8).pin_memory()
+            _PINNED[name] = buf
+        dst = buf[:nbytes].view(t.dtype).view(t.shape)
+        dst.copy_(t, non_blocking=True)
+        out[name] = dst
+    torch.cuda.current_stream().synchronize()
+    return {k: v.numpy() for k, v in out.items()}
