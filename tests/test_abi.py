@@ -50,7 +50,8 @@ def test_workspace_queries_need_no_gpu(lib):
     assert l.xm3d_voxelize_ws_bytes(160, 6_400_000) > 6_400_000 * (24 + 20)
     assert l.xm3d_gather_ws_bytes(2, 50, 240, 320) >= 2 * 240 * 320 * 2 * 4
     assert l.xm3d_pool_ws_bytes(160, 50, 768, 6_400_000, 6_400_000) > 6_400_000 * 4 + 160 * 50 * 768 * 4
-    assert l.xm3d_logits_ws_bytes(8000, 19, 768, 19) > 2 * 8020 * 768 * 4
+    # (round 2: only the text side is staged — the mask embeddings are split in shared memory)
+    assert 2 * 20 * 768 * 4 < l.xm3d_logits_ws_bytes(8000, 19, 768, 19) < 2 * 8020 * 768 * 4
 
 
 def test_compute_calls_fail_loudly_without_gpu(lib):
