@@ -437,7 +437,7 @@ bool make_row_tile_map(CUtensorMap *m, const float *base, int64_t rows, int c, i
 bool pool_mma_eligible(const float *feat, int c, const int32_t *row_index, const uint32_t *member, int k, int64_t cap,
                        const float *sum, const float *mean);
 int launch_pool_mma(const float *feat, int c, const uint32_t *member, int words, int n_seg, int k, const int64_t *seg_off,
-                    int64_t cap, float *sum, int32_t *cnt, float *mean, int *work, int tune, cudaStream_t stream);
+                    int64_t cap, float *sum, int32_t *cnt, float *mean, int *work, int *order, int tune, cudaStream_t stream);
 
 constexpr int PR_THREADS = 512;
 constexpr int PR_WARPS = PR_THREADS / 32;
@@ -607,7 +607,8 @@ struct PoolWs {
     int64_t *pair_off;
     float *partial;
     int64_t max_chunks;
-    int *work;                 // work-item counter of the point-major kernel
+    int *work;                 // work-item counter of the point-major / tensor-core kernels
+    int *order;                // [n_seg] segments by descending size (longest-processing-time hand-out)
 };
 
 static PoolWs carve_pool(void *ws, int n_seg, int k, int c, int64_t cap, int64_t cap_pairs, size_t *bytes) {
@@ -624,6 +625,7 @@ static PoolWs carve_pool(void *ws, int n_seg, int k, int c, int64_t cap, int64_t
     w.tile_off = cv.take<int32_t>((size_t)n_seg + 1);
     w.tile_cnt = cv.take<int32_t>((size_t)w.max_tiles * k);
     w.work = cv.take<int>(64);
+    w.order = cv.take<int>((size_t)n_seg);
     *bytes = cv.off + 256;
     return w;
 }
@@ -674,7 +676,7 @@ extern "C" int xm3d_pool_batch(const float *feat, int32_t c, const int32_t *row_
     if (path == XM3D_POOL_ROWS && !rows_ok) { set_error("xm3d_pool_batch: point-major path not eligible"); return XM3D_ERR_UNSUPPORTED; }
     if (path == XM3D_POOL_MMA || (path == XM3D_POOL_AUTO && overlap && mma_ok)) {
         if (g_pool_ev[0]) cudaEventRecord(g_pool_ev[0], stream);
-        const int rc = launch_pool_mma(feat, c, member, I.words, n_seg, k, seg_off, cap, sum, cnt, mean, w.work, tune, stream);
+        const int rc = launch_pool_mma(feat, c, member, I.words, n_seg, k, seg_off, cap, sum, cnt, mean, w.work, w.order, tune, stream);
         if (g_pool_ev[1]) cudaEventRecord(g_pool_ev[1], stream);
         return rc;
     }

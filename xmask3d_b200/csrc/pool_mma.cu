@@ -49,9 +49,26 @@ struct PoolMmaParams {
     float *sum, *mean;           // [n_seg, k, c]
     int32_t *cnt;                // [n_seg, k] or null
     int *work;                   // item counter (zeroed by the host)
+    const int *order;            // [n_seg] segments by descending size, or null (identity)
     int raw_stages, conv_stages;
     int dbg;                     // experiments only: 1 = skip the lo MMAs, 2 = skip the hi MMAs (results are then wrong)
 };
+
+// Work items are handed out through an atomic counter; with segments of very different sizes (0 .. 60 k points per
+// view) the CTA that draws a large item last finishes late: measured 1 990 tiles on the busiest CTA against a mean of
+// 1 485.  Handing the segments out by DESCENDING size (longest-processing-time first) removes that tail.
+__global__ void __launch_bounds__(256)
+pool_order_kernel(const int64_t *__restrict__ seg_off, int n_seg, int *__restrict__ order) {
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n_seg; s += gridDim.x * blockDim.x) {
+        const int64_t ns = seg_off[s + 1] - seg_off[s];
+        int rank = 0;
+        for (int t = 0; t < n_seg; ++t) {
+            const int64_t nt = seg_off[t + 1] - seg_off[t];
+            rank += (nt > ns) || (nt == ns && t < s);
+        }
+        order[rank] = s;
+    }
+}
 
 // Instrumented build (-DXM3D_PM_TIMING, scripts/exp_pool_mma.py): per-role wait / work cycles of every CTA
 #ifdef XM3D_PM_TIMING
@@ -124,7 +141,7 @@ pool_mma_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P) 
         __syncthreads();
         const int item = s_item;
         if (item >= n_items) break;
-        const int s = item / nsl, sl = item - s * nsl;
+        const int s = P.order ? P.order[item / nsl] : item / nsl, sl = item % nsl;
         const int64_t a = P.seg_off[s];
         const int n = over ? 0 : (int)(P.seg_off[s + 1] - a);
         const int ntile = (n + PM_TP - 1) / PM_TP;
@@ -420,7 +437,7 @@ pool_mma2_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P)
         __syncthreads();
         const int item = s_item;
         if (item >= n_items) break;
-        const int s = item / nsl, sl = item - s * nsl;
+        const int s = P.order ? P.order[item / nsl] : item / nsl, sl = item % nsl;
         const int64_t a = P.seg_off[s];
         const int n = over ? 0 : (int)(P.seg_off[s + 1] - a);
         const int ntile = (n + PM_TP - 1) / PM_TP;
@@ -681,7 +698,7 @@ bool pool_mma_eligible(const float *feat, int c, const int32_t *row_index, const
 }
 
 int launch_pool_mma(const float *feat, int c, const uint32_t *member, int words, int n_seg, int k, const int64_t *seg_off,
-                    int64_t cap, float *sum, int32_t *cnt, float *mean, int *work, int tune, cudaStream_t stream) {
+                    int64_t cap, float *sum, int32_t *cnt, float *mean, int *work, int *order, int tune, cudaStream_t stream) {
     CUtensorMap map;
     memset(&map, 0, sizeof(map));
     // rows past `cap` are zero-filled by TMA; rows past a segment are zeroed by the converters
@@ -695,6 +712,12 @@ int launch_pool_mma(const float *feat, int c, const uint32_t *member, int words,
     const int n_items = n_seg * (c / PM_SLICE);
     const unsigned grid = (unsigned)(n_items < sm_count() ? n_items : sm_count());
     cudaMemsetAsync(work, 0, sizeof(int), stream);
+    P.order = nullptr;
+    if (order && n_seg > 1 && n_seg <= 4096 && !((tune >> 9) & 1)) {      // (bit 9: experiments without the ordering)
+        pool_order_kernel<<<(unsigned)((n_seg + 255) / 256), 256, 0, stream>>>(seg_off, n_seg, order);
+        count_launches(1);
+        P.order = order;
+    }
     static std::atomic<uint64_t> attr_set{0};
     if (first_use_on_device(&attr_set)) {
         cudaFuncSetAttribute(pool_mma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);

@@ -143,7 +143,7 @@ class CorrespondencePipeline:
                 s, cnt, mean = ops.pool(feat, pr.vis_off, self.k, member=member, cap=self.cap_vis,
                                         cap_pairs=self.cap_pairs,
                                         row_index=(pr.vis_idx if feat_per_point else None), ws=self.ws_pool,
-                                        status=self._side_status)
+                                        status=self._side_status, path=self.pool_path)
             vox = ops.voxelize_batch(pr.xyz_vis, pr.vis_off, self.rt, cap=self.cap_vis, collate=True, ws=self.ws_vox)
             main.wait_stream(side)                      # join
             for t in (member, s, cnt, mean):
