@@ -261,16 +261,17 @@ XM3D_API int xm3d_logits(const float *mask_embed, int64_t rows, int32_t c, const
  *   binary given:  val[i,t] = b_i * (is_base[t] ? val : -1e10) + (1 - b_i) * (is_base[t] ? -1e10 : val)
  *   mask_label given (the FUSED stream, run/infer.py:568-600): p_i = softmax_t(val[i,:]); for a point inside final
  *     mask m = mask_label[i] (>= 0; the final masks are an argmax partition, models/xmask3d.py:418-435) with
- *     q = mask_probs[m,:] = softmax(logit_scale * normalize(final_pred_open_embedding) @ text.T):
+ *     q = softmax(logit_scale * normalize(final_pred_open_embedding) @ text.T)[m,:], passed as mask_log_probs = log q:
  *       val[i,t] = log(p^base_ratio * q^(1-base_ratio)) * ov[t] + log(p^novel_ratio * q^(1-novel_ratio)) * (1 - ov[t]),
- *     ov = is_base; points in no mask keep val = p.  The binary blend above then applies to these values.
+ *     ov = is_base, evaluated in the log domain (ratio * log p + (1 - ratio) * log q; equal up to float32 rounding, finite
+ *     where the reference's p underflows); points in no mask keep val = p.  The binary blend above then applies.
  *   out [rows, n_text] float32 (optional), argmax int32 [rows] (optional, first maximum)
  * feat [rows, c] float32 is read from HBM once (TMA -> in-place TF32 hi/lo split in shared memory ->
  * tcgen05 3xTF32); n_text <= 256, c % 4 == 0, feat 16-byte aligned. */
 XM3D_API size_t xm3d_point_logits_ws_bytes(int32_t n_text, int32_t c);
 XM3D_API int xm3d_point_logits(const float *feat, int64_t rows, int32_t c, const float *text_embed, int32_t n_text,
                       float logit_scale, const float *binary, const uint8_t *is_base,
-                      const int32_t *mask_label, const float *mask_probs, int32_t n_masks, float base_ratio,
+                      const int32_t *mask_label, const float *mask_log_probs, int32_t n_masks, float base_ratio,
                       float novel_ratio, float *out, int32_t *argmax, void *ws, size_t ws_bytes,
                       xm3d_stream_t stream);
 

@@ -131,7 +131,7 @@ struct PointLogitsParams {
     // fused-stream ensemble (run/infer.py:568-600): softmax over the classes, then for a point inside final mask
     // `mask_label` the geometric mean with that mask's MaskCLIP class probabilities, base / novel ratios per class
     const int *mask_label;       // [rows] (-1 = in no mask) or null: no ensemble
-    const float *mask_probs;     // [n_masks, n_text] softmax(final_pred_open_logits)
+    const float *mask_probs;     // [n_masks, n_text] LOG of softmax(final_pred_open_logits)
     int n_masks;
     float base_ratio, novel_ratio;
     float *out;                  // [rows, n_text] (or [rows, n_groups] when grouped) or null
@@ -344,6 +344,7 @@ point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     if (c0 + j < P.n_text) ssum += expf(logit_of(v, v2, j, c0 + j) - smax);
             }
         }
+        const float lsum = P.mask_label ? logf(ssum) : 0.f;
         float best = -INFINITY;
         float gacc = P.ensemble_mean ? 0.f : -INFINITY;
         int best_i = 0;
@@ -357,14 +358,18 @@ point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 if (col < P.n_text) {
                     float val = logit_of(v, v2, j, col);
                     if (P.mask_label) {
-                        val = __fdiv_rn(expf(val - smax), ssum);                       // class probability
                         if (label >= 0) {
-                            // (p ** ratio * q ** (1 - ratio)).log() * overlap, base and novel halves added (:577-590)
-                            const float q = __ldg(P.mask_probs + (size_t)label * P.n_text + col);
-                            const float ov = s_base[col] ? 1.f : 0.f;
-                            const float tb = __fmul_rn(logf(__fmul_rn(powf(val, P.base_ratio), powf(q, 1.f - P.base_ratio))), ov);
-                            const float tn = __fmul_rn(logf(__fmul_rn(powf(val, P.novel_ratio), powf(q, 1.f - P.novel_ratio))), 1.f - ov);
-                            val = __fadd_rn(tb, tn);
+                            // (p ** ratio * q ** (1 - ratio)).log() * overlap, base and novel halves added (:577-590), in
+                            // the log domain: ratio * log p + (1 - ratio) * log q with log p = val - max - log(sum) and
+                            // log q precomputed per (mask, class) — no pow / log per element.  Equal to the reference's
+                            // float32 sequence up to rounding (~1e-6); where the reference's p underflows to 0 it yields
+                            // NaN (-inf * 0), this form stays finite.
+                            const float logp = (val - smax) - lsum;
+                            const float logq = __ldg(P.mask_probs + (size_t)label * P.n_text + col);
+                            const float ratio = s_base[col] ? P.base_ratio : P.novel_ratio;
+                            val = fmaf(ratio, logp, (1.f - ratio) * logq);
+                        } else {
+                            val = __fdiv_rn(expf(val - smax), ssum);                   // class probability
                         }
                     }
                     if (blend) {

@@ -459,7 +459,7 @@ def point_logits(feat: torch.Tensor, text_embed: torch.Tensor, logit_scale: floa
     n_masks = 0
     if mask_label is not None:
         mask_label = _dev_contig(mask_label.reshape(-1), torch.int32)
-        mask_probs = _dev_contig(mask_probs, torch.float32)
+        mask_probs = _dev_contig(mask_probs, torch.float32).log()      # the kernel works in the log domain
         n_masks = int(mask_probs.shape[0])
         assert mask_label.numel() == n and mask_probs.shape[1] == t and is_base is not None
     out = torch.empty((n, t), dtype=torch.float32, device=dev) if want_logits else None
