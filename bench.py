@@ -419,13 +419,13 @@ class Timer:
         return float(t.item())
 
 
-def prepare_pipeline(batch, k, c, dev, mask_kind, seed, overlap=True, pool_path="auto"):
+def prepare_pipeline(batch, k, c, dev, mask_kind, seed, overlap=True, pool_path="auto", vox_mode=0):
     """Pipeline + masks + features of a batch; one untimed projection fixes the visible counts (deterministic),
     which size the feature tensor."""
     import torch
     from xmask3d_b200 import ops
     from xmask3d_b200.pipeline import CorrespondencePipeline
-    pipe = CorrespondencePipeline(batch, k, c, dev, overlap=overlap, pool_path=pool_path)
+    pipe = CorrespondencePipeline(batch, k, c, dev, overlap=overlap, pool_path=pool_path, vox_mode=vox_mode)
     xyz_h = torch.from_numpy(batch.xyz).pin_memory()
     depth_h = torch.from_numpy(batch.depth_mm.view(np.int16)).pin_memory()
     pipe.upload(xyz_h, depth_h)
@@ -481,7 +481,8 @@ def run_native(args, rank: int, world: int, local_rank: int):
         init_nccl(dev)
     T = Timer(dev, world)
     pipe, masks, mode, mask_bytes, feat, xyz_h, depth_h, n_vis, total_vis, total_pairs = prepare_pipeline(
-        batch, args.k, args.c, dev, args.masks, 4242 + rank, overlap=not args.no_overlap, pool_path=args.pool_path)
+        batch, args.k, args.c, dev, args.masks, 4242 + rank, overlap=not args.no_overlap, pool_path=args.pool_path,
+        vox_mode=2)       # 150 k-point scenes: every view's visible points fit the shared-memory units (status checked)
     torch.cuda.synchronize()
     t_setup = time.perf_counter() - t_setup
 
@@ -768,6 +769,7 @@ def extra_k100(args, batch, dev, T, rank, peak, pv_job, feat_shared):
         batch, 100, args.c, dev, 5252 + rank, feat_shared)
     for _ in range(3):
         out = pipe.run(masks, feat, mode)
+    assert int(out["proj"].status.item()) == 0 and int(out["vox"].status.item()) == 0 and int(out["pool_status"].item()) == 0
     pipe.capture(masks, feat, mode)
     n = max(5, min(args.steps, 20))
     ms = T.time(lambda i: pipe.replay(), n) / n
@@ -788,7 +790,7 @@ def prepare_pipeline_shared(batch, k, c, dev, seed, feat):
     import torch
     from xmask3d_b200 import ops
     from xmask3d_b200.pipeline import CorrespondencePipeline
-    pipe = CorrespondencePipeline(batch, k, c, dev)
+    pipe = CorrespondencePipeline(batch, k, c, dev, vox_mode=2)
     pipe.upload(torch.from_numpy(batch.xyz), torch.from_numpy(batch.depth_mm.view(np.int16)))
     pr = pipe.project()
     n_vis = pr.n_vis.cpu().numpy().astype(np.int64)

@@ -51,6 +51,7 @@ typedef enum {
 #define XM3D_FLAG_GRID_RANGE 4     /* voxel coordinate outside +-2^30           */
 #define XM3D_FLAG_KEY_SENTINEL 8   /* a key equal to 2^64-1 was remapped        */
 #define XM3D_FLAG_I16_RANGE 16     /* xm3d_pack_i16: a value did not fit int16  */
+#define XM3D_FLAG_VOX_FALLBACK 32  /* XM3D_VOX_FAST_ONLY: the batch needs the multi-kernel path */
 
 /* depth image element type */
 #define XM3D_DEPTH_NONE 0
@@ -137,6 +138,9 @@ XM3D_API size_t xm3d_unique_ws_bytes(int32_t n_seg, int64_t cap);
  * plan aims at (0 = default 7000; smaller values force several key-range units per segment). */
 #define XM3D_VOX_AUTO 0
 #define XM3D_VOX_MULTI_KERNEL 1
+#define XM3D_VOX_FAST_ONLY 2   /* shared-memory units only: the fallback kernels are not launched (they cost ~5 us each just
+                                * to return); a batch that is not eligible or a unit that overflows raises
+                                * XM3D_FLAG_VOX_FALLBACK and the outputs are undefined — call again with XM3D_VOX_AUTO */
 XM3D_API int xm3d_unique_batch(const uint64_t *keys, const int64_t *seg_off, int32_t n_seg, int64_t cap,
                       int32_t *m, int64_t *uniq_off, int32_t *first, int32_t *counts,
                       int32_t *inverse, int32_t collate, int32_t path, void *ws, size_t ws_bytes,

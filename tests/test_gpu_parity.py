@@ -246,6 +246,40 @@ def test_voxelize_paths_vs_oracle(cport, dev, mode, unit_pts):
             assert uoff[-1] == m.sum()
 
 
+def test_voxelize_fast_only_path(cport, dev):
+    """XM3D_VOX_FAST_ONLY: the shared-memory units alone (the fallback kernels are not launched) give the oracle's
+    result; a batch that needs the multi-kernel path — a segment above 224 k points, a unit that overflows — is flagged
+    (FLAG_VOX_FALLBACK) instead of being recomputed."""
+    from xmask3d_b200 import _lib as L, ops
+    rng = np.random.default_rng(21)
+    sc = syn.make_scene(7, 150_000)
+    segs = [(sc.xyz[:37_000], _random_rt(rng, 0.02)), (sc.xyz[:0], _random_rt(rng, 0.02)), (sc.xyz[40_000:41_000], _random_rt(rng, 0.02))]
+    off = np.concatenate([[0], np.cumsum([len(s_) for s_, _ in segs])]).astype(np.int64)
+    xyz = torch.from_numpy(np.concatenate([s_ for s_, _ in segs])).to(dev)
+    rt = torch.from_numpy(np.stack([r[:3, :4] for _, r in segs])).to(dev)
+    u = ops.voxelize_batch(xyz, torch.from_numpy(off).to(dev), rt, collate=True, mode=2)
+    assert int(u.status.item()) == 0
+    m, uoff = u.m.cpu().numpy(), u.uniq_off.cpu().numpy()
+    for i, (p, r) in enumerate(segs):
+        if len(p) == 0:
+            continue
+        rgrid, rfirst, rinv = cport.voxelize(p, r)
+        a = int(uoff[i])
+        assert m[i] == len(rfirst) and np.array_equal(u.first.cpu().numpy()[a:a + m[i]], rfirst)
+        assert np.array_equal(u.voxel_xyz.cpu().numpy()[a:a + m[i]].astype(np.float64), rgrid)
+        assert np.array_equal(u.inverse.cpu().numpy()[off[i]:off[i + 1]] - a, rinv)
+    big = syn.make_scene(6, 300_000, room=(12.0, 10.0, 3.0))
+    u = ops.voxelize_batch(torch.from_numpy(big.xyz).to(dev), torch.tensor([0, 300_000], device=dev),
+                           torch.from_numpy(_random_rt(rng, 0.01)[None, :3, :4]).to(dev), mode=2)
+    assert int(u.status.item()) & L.FLAG_VOX_FALLBACK            # not eligible: > 224 k points in one segment
+    n = 20 * 1024
+    pts = syn.make_scene(8, 60_000).xyz[:n].copy()
+    pts[np.arange(1024) * 20] = pts[0]                              # defeats the key-range split: a unit overflows
+    u = ops.voxelize_batch(torch.from_numpy(pts).to(dev), torch.tensor([0, n], device=dev),
+                           torch.from_numpy(_random_rt(rng, 0.004)[None, :3, :4]).to(dev), mode=2)
+    assert int(u.status.item()) & L.FLAG_VOX_FALLBACK
+
+
 def test_voxelize_unit_overflow_falls_back(cport, dev):
     """A segment whose 1024 sample positions all hold the same voxel defeats the key-range split:
     one unit receives ~20 k distinct keys, overflows its 8704-key table, and the batch is recomputed by

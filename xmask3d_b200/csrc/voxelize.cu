@@ -227,7 +227,7 @@ vox_plan_kernel(const int64_t *__restrict__ seg_off, int n_seg, int64_t cap, int
     const bool over = seg_off[n_seg] > cap;
     if (tid == 0) {
         s_carry[0] = s_carry[1] = s_carry[2] = 0;
-        s_slow = force_slow;
+        s_slow = force_slow & 1;
         *total_eff = over ? 0 : seg_off[n_seg];
         if (over && status) atomicOr(status, XM3D_FLAG_VIS_OVERFLOW);
     }
@@ -260,6 +260,8 @@ vox_plan_kernel(const int64_t *__restrict__ seg_off, int n_seg, int64_t cap, int
         ctl[0] = (s_slow || s_carry[2] > units_max) ? 1 : 0;
         ctl[1] = 0;
         ctl[2] = 0;                               // unit ticket counter of vox_fast_kernel
+        ctl[3] = (force_slow >> 1) & 1;           // XM3D_VOX_FAST_ONLY: the multi-kernel path is not launched
+        if (ctl[3] && ctl[0] && status) atomicOr(status, XM3D_FLAG_VOX_FALLBACK);   // ... so "not eligible" is an error
     }
 }
 
@@ -836,7 +838,11 @@ vox_fast_kernel(int4 *pgrid, const unsigned long long *__restrict__ keys_in,
     FV_T(9);
     const int M = s_cnt;
     if (M > FV_MU || s_ovf) {                     // does not fit: publish (nobody may wait for ever) and fall back
-        if (tid == 0) { atomicExch(&ctl[1], 1); atomicExch(&unit_m[u], 0); }
+        if (tid == 0) {
+            atomicExch(&ctl[1], 1);
+            atomicExch(&unit_m[u], 0);
+            if (ctl[3] && status) atomicOr(status, XM3D_FLAG_VOX_FALLBACK);   // nobody will recompute the batch
+        }
         return;
     }
     if (tid == 0) atomicExch(&unit_m[u], M);
@@ -1162,7 +1168,9 @@ static int run_unique(const Xyz xyz, const unsigned long long *keys, const int64
     int64_t units_max64 = cap / unit_pts + n_seg;
     if (units_max64 > w.units_cap) units_max64 = w.units_cap;
     const int units_max = (int)units_max64;
-    const int force_slow = ((path & 0xff) == XM3D_VOX_MULTI_KERNEL || counts != nullptr) ? 1 : 0;
+    const bool fast_only = (path & 0xff) == XM3D_VOX_FAST_ONLY;
+    if (fast_only && counts) { set_error("%s: XM3D_VOX_FAST_ONLY cannot return counts", who); return XM3D_ERR_UNSUPPORTED; }
+    const int force_slow = (((path & 0xff) == XM3D_VOX_MULTI_KERNEL || counts != nullptr) ? 1 : 0) | (fast_only ? 2 : 0);
     static std::atomic<uint64_t> smem_set{0};
     if (first_use_on_device(&smem_set)) {
         cudaFuncSetAttribute(vox_fast_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FV_SMEM);
@@ -1176,7 +1184,7 @@ static int run_unique(const Xyz xyz, const unsigned long long *keys, const int64
         vox_min_kernel<<<blocks, VOX_THREADS, 0, stream>>>(xyz, seg_off, n_seg, w.total_eff, rt, gmin, w.pgrid, status);
         count_launches(1);
     }
-    if (!force_slow) {
+    if (!(force_slow & 1)) {
         if (xyz)
             vox_fast_kernel<0><<<units_max, FV_THREADS, FV_SMEM, stream>>>(
                 w.pgrid, nullptr, seg_off, n_seg, w.total_eff, w.unit_off, w.unit_seg, w.unit_m, w.ctl, gmin, w.pslot, m,
@@ -1187,6 +1195,7 @@ static int run_unique(const Xyz xyz, const unsigned long long *keys, const int64
                 uniq_off, first, inverse, collate, nullptr, status);
         count_launches(1);
     }
+    if (fast_only) return check_launch(who);      // the eight kernels of the multi-kernel path are not even launched
     vox_clear_kernel<<<(unsigned)(sm_count() * 8), 256, 0, stream>>>(w.tbl, w.tbl_off, n_seg, w.total_eff, first, m, w.ctl);
     count_launches(1);
     if (counts) cudaMemsetAsync(counts, 0, sizeof(int) * cap, stream);

@@ -146,8 +146,9 @@ class Unique:
 
 def _vox_path(mode: int = 0, unit_pts: int = 0) -> int:
     """Per-call path word of xm3d_unique_batch / xm3d_voxelize_batch: mode 0 = shared-memory units when every
-    segment fits (default), 1 = multi-kernel path only; unit_pts < 7000 forces several key-range units per
-    segment (tests)."""
+    segment fits (default), 1 = multi-kernel path only, 2 = shared-memory units only (the fallback kernels are not
+    launched; status flag FLAG_VOX_FALLBACK if the batch needed them); unit_pts < 7000 forces several key-range
+    units per segment (tests)."""
     return (int(mode) & 0xff) | (max(int(unit_pts), 0) << 8)
 
 

@@ -66,7 +66,7 @@ class CorrespondencePipeline:
 
     def __init__(self, batch: Batch, k: int, c: int, device, cap_vis: Optional[int] = None,
                  cut_bound: int = 10, vis_thres: float = 0.25, depth_scale: float = 1000.0,
-                 pairs_per_point: float = 1.0, overlap: bool = True, pool_path: str = "auto"):
+                 pairs_per_point: float = 1.0, overlap: bool = True, pool_path: str = "auto", vox_mode: int = 0):
         ops._require_cuda()
         self.batch, self.k, self.c, self.dev = batch, int(k), int(c), device
         self.cut_bound, self.vis_thres, self.depth_scale = cut_bound, vis_thres, depth_scale
@@ -79,6 +79,10 @@ class CorrespondencePipeline:
         self._graph_out = None
         self.overlap = bool(overlap)                       # voxelize || (gather + pool) on two streams
         self.pool_path = pool_path                         # "auto" | "pair_lists" | "rows" | "mma" (ops.pool)
+        # vox_mode 2 = XM3D_VOX_FAST_ONLY: when every segment (one view's visible points) is known to stay below 224 k
+        # points the shared-memory units always apply and the eight fallback kernels (43 us of launches that return at
+        # once) need not be launched.  A batch that needed them raises FLAG_VOX_FALLBACK in vox.status: rerun with 0.
+        self.vox_mode = int(vox_mode)
         self._side = torch.cuda.Stream(device=device)
         self._side_status = torch.zeros(1, dtype=torch.int32, device=device)
         self.total_pv = int(self.out_off[-1])
@@ -144,13 +148,15 @@ class CorrespondencePipeline:
                                         cap_pairs=self.cap_pairs,
                                         row_index=(pr.vis_idx if feat_per_point else None), ws=self.ws_pool,
                                         status=self._side_status, path=self.pool_path)
-            vox = ops.voxelize_batch(pr.xyz_vis, pr.vis_off, self.rt, cap=self.cap_vis, collate=True, ws=self.ws_vox)
+            vox = ops.voxelize_batch(pr.xyz_vis, pr.vis_off, self.rt, cap=self.cap_vis, collate=True, ws=self.ws_vox,
+                                     mode=self.vox_mode)
             main.wait_stream(side)                      # join
             for t in (member, s, cnt, mean):
                 t.record_stream(main)
             return {"proj": pr, "vox": vox, "member": member, "sum": s, "cnt": cnt, "mean": mean,
                     "pool_status": self._side_status}
-        vox = ops.voxelize_batch(pr.xyz_vis, pr.vis_off, self.rt, cap=self.cap_vis, collate=True, ws=self.ws_vox)
+        vox = ops.voxelize_batch(pr.xyz_vis, pr.vis_off, self.rt, cap=self.cap_vis, collate=True, ws=self.ws_vox,
+                                 mode=self.vox_mode)
         if times is not None:
             times.mark("voxelize")
         member, _ = ops.gather_masks(masks, pr.rowcol, pr.vis_off, mode=mode, cap=self.cap_vis, ws=self.ws_gather)
