@@ -1,5 +1,4 @@
 set -x
-for c in 25 50; do
-XM3D_CARVE=$c XM3D_SO=xmask3d_b200/libxm3d_dbg.so timeout 600 python scripts/exp_proj_overlap.py > gpurun_out/exp_proj_overlap_$c.log 2>&1; echo "rc=$?" >> gpurun_out/exp_proj_overlap_$c.log
-done
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/gpu_tests10.log 2>&1; echo "rc=$?" >> gpurun_out/gpu_tests10.log
+timeout 600 python bench.py --steps 20 --warmup 5 --masks overlap --extras none --no-cpu > gpurun_out/bench_r02_overlap.json 2> gpurun_out/bench_r02_overlap.err; echo "rc=$?" >> gpurun_out/bench_r02_overlap.err
 echo done

@@ -398,6 +398,25 @@ def test_gather_pool_scatter_golden(golden, cport, dev):
     np.testing.assert_allclose(sp[0].cpu().numpy(), g["score_pool"], rtol=1e-5, atol=1e-7)
 
 
+def test_sigmoid_threshold_near_zero(dev):
+    """`sigmoid(x) >= 0.5` / `> 0.5` (models/utils/criterion.py:83-85, models/xmask3d.py:356-357) is decided by the sign of x
+    outside |x| <= 1e-6 and by the exact float32 formula inside: identical to torch's float32 sigmoid on the CPU for
+    every |x| >= 1e-7 (below that the CPU's vectorised exp and the GPU's expf may round differently)."""
+    from xmask3d_b200 import ops
+    mags = np.array([1e-7, 1.2e-7, 2.5e-7, 5e-7, 9.9e-7, 1.0e-6, 1.01e-6, 2e-6, 1e-5, 1e-3, 0.5, 3.0, 20.0, 100.0], np.float32)
+    vals = np.concatenate([mags, -mags, [np.inf, -np.inf, np.nan]]).astype(np.float32)
+    k, h, w = len(vals), 4, 8
+    masks = torch.from_numpy(np.broadcast_to(vals[:, None, None], (k, h, w)).copy())[None]
+    rowcol = torch.tensor([[1, 2], [3, 7]], dtype=torch.int32, device=dev)
+    seg = torch.tensor([0, 2], dtype=torch.int64, device=dev)
+    for mode, ref in (("sigmoid_ge0.5", torch.from_numpy(vals).sigmoid() >= 0.5), ("sigmoid_gt0.5", torch.from_numpy(vals).sigmoid() > 0.5)):
+        member, _ = ops.gather_masks(masks.to(dev), rowcol, seg, mode=mode)
+        bits = member.cpu().numpy().view(np.uint32)
+        got = np.array([(bits[0, m // 32] >> (m % 32)) & 1 for m in range(k)], bool)
+        assert np.array_equal(got, ref.numpy()), (mode, vals[got != ref.numpy()])
+        assert np.array_equal(bits[0], bits[1])
+
+
 def test_mask_mapper_ragged_lists(dev):
     """The caller's real input (models/utils/criterion.py:262-340): per-scene lists with DIFFERENT numbers of masks,
     bool partition masks for some scenes, float32 zero masks ("nothing kept") for others, one scene whose masks

@@ -23,6 +23,9 @@ namespace xm3d {
 
 __device__ __forceinline__ bool mask_hit(float x, int thr_mode) {
     if (thr_mode == XM3D_THR_GE_HALF) return x >= 0.5f;
+    // sigmoid(x) - 0.5 has the sign of x; only within 1e-6 of zero can float32 rounding of exp / add / div decide
+    // otherwise (2 instructions instead of ~20 per (pixel, mask): the float32 pass becomes memory bound)
+    if (fabsf(x) > 1e-6f) return x > 0.f;
     const float sg = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));       // torch.sigmoid, float32
     return thr_mode == XM3D_THR_SIGMOID_GE_HALF ? (sg >= 0.5f) : (sg > 0.5f);
 }
