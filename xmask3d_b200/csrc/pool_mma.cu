@@ -52,6 +52,7 @@ struct PoolMmaParams {
     const int *order;            // [n_seg] segments by descending size, or null (identity)
     int raw_stages, conv_stages;
     int dbg;                     // experiments only: 1 = skip the lo MMAs, 2 = skip the hi MMAs (results are then wrong)
+    int m64;                     // version 2: k <= 64 -> MMAs with M = 64 (half the accumulator read-modify-write per MMA)
 };
 
 // Work items are handed out through an atomic counter; with segments of very different sizes (0 .. 60 k points per
@@ -463,8 +464,11 @@ pool_mma2_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P)
         } else if (warp == 1) {
             // ===== MMA issuer: 8 tf32 MMAs (hi, 8 points each) + 4 bf16 MMAs (lo, 16 points each) per tile =====
             if (lane == 0) {
-                const uint32_t id32 = make_idesc(128, PM_SLICE, 2, /*A: TMEM*/ 0, /*B N-major*/ 1);
-                const uint32_t id16 = make_idesc(128, PM_SLICE, 1, 0, 1);
+                // M = 64 when all masks fit 64 rows: every MMA reads and writes the whole M x 128 float32 accumulator for
+                // only 8 (tf32) or 16 (bf16) rank-1 updates, so its time is the accumulator traffic, not the MACs
+                const int mrows = P.m64 ? 64 : 128;
+                const uint32_t id32 = make_idesc(mrows, PM_SLICE, 2, /*A: TMEM*/ 0, /*B N-major*/ 1);
+                const uint32_t id16 = make_idesc(mrows, PM_SLICE, 1, 0, 1);
                 uint64_t d_hi[PM_MAX_STAGES], d_lo[2];
 #pragma unroll
                 for (int q = 0; q < PM_MAX_STAGES; ++q)     // tf32 N-major: 32-byte-atom swizzle, 4 column blocks 8 KB apart
@@ -568,14 +572,18 @@ pool_mma2_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P)
         } else if (warp < 10) {
             // ===== builders: lane = mask.  32 x 32 bit transposes (ballots) of the tile's membership words, expanded in
             // registers to 0.0f / 1.0f (tf32) and to bf16 pairs, stored into tensor memory =====
-            const int lg = warp & 3;                              // TMEM lane group = membership word of this warp
+            // M = 128: TMEM lane = mask, lane group lg holds masks 32 lg .. 32 lg + 31 = membership word lg.
+            // M = 64:  rows 16 q .. 16 q + 15 live in lanes 0..15 of lane group q: this warp's masks are 16 lg .. 16 lg + 15,
+            //          bits (lg & 1) * 16 .. of membership word lg >> 1.
+            const int lg = warp & 3;
+            const int wsel = P.m64 ? (lg >> 1) : lg;
             const int tail = P.k & 31;
-            const bool word_ok = lg < P.words && lg * 32 < P.k;
+            const bool word_ok = wsel < P.words && wsel * 32 < P.k;
             auto load_word = [&](int pt) -> uint32_t {
                 uint32_t x = 0u;
                 if (word_ok && pt < n) {
-                    x = __ldg(P.member + (size_t)(a + pt) * P.words + lg);
-                    if (tail && lg == (P.k >> 5)) x &= (1u << tail) - 1u;
+                    x = __ldg(P.member + (size_t)(a + pt) * P.words + wsel);
+                    if (tail && wsel == (P.k >> 5)) x &= (1u << tail) - 1u;
                 }
                 return x;
             };
@@ -587,7 +595,13 @@ pool_mma2_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P)
             for (int t = 0; t < ntile; ++t) {
                 wa[2] = load_word((t + 2) * PM_TP + lane); wb[2] = load_word((t + 2) * PM_TP + 32 + lane);
                 // points 0..31 / 32..63 of the tile inside MY mask: two 32 x 32 bit transposes (5 shuffle rounds each)
-                const uint32_t m0 = warp_transpose32(wa[0]), m1 = warp_transpose32(wb[0]);
+                uint32_t m0 = warp_transpose32(wa[0]), m1 = warp_transpose32(wb[0]);
+                if (P.m64) {                                      // lane L < 16 takes mask 16 lg + L = bit row (lg & 1) * 16 + L
+                    const int src = (lg & 1) * 16 + (lane & 15);
+                    m0 = __shfl_sync(0xffffffffu, m0, src);
+                    m1 = __shfl_sync(0xffffffffu, m1, src);
+                    if (lane >= 16) { m0 = 0u; m1 = 0u; }
+                }
                 cnt += __popc(m0) + __popc(m1);
                 long long c0_ = PM_CLK();
                 mbar_wait(&s_conv_empty[cs], cph ^ 1);
@@ -621,7 +635,8 @@ pool_mma2_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P)
                 if (++cs == 2) { cs = 0; cph ^= 1; }
                 wa[0] = wa[1]; wb[0] = wb[1]; wa[1] = wa[2]; wb[1] = wb[2];
             }
-            s_cnt[lg * 32 + lane] = cnt;                          // exactly one thread per mask
+            if (!P.m64) s_cnt[lg * 32 + lane] = cnt;              // exactly one thread per mask
+            else if (lane < 16) s_cnt[lg * 16 + lane] = cnt;
             if (tid == 192) PM_OUT(3, tw0, tw1, PM_CLK() - tall, 0);
             asm volatile("bar.sync 1, %0;" ::"n"(PM_BUILD + EPI_THREADS) : "memory");
         } else {
@@ -655,7 +670,7 @@ pool_mma2_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P)
             }
             if (tid == 320) PM_OUT(4, tw0, 0, PM_CLK() - tall, 0);
             asm volatile("bar.sync 1, %0;" ::"n"(PM_BUILD + EPI_THREADS) : "memory");
-            const int m = lg * 32 + lane;
+            const int m = P.m64 ? (lane < 16 ? lg * 16 + lane : P.k) : lg * 32 + lane;
             if (m < P.k) {
                 const int nm = s_cnt[m];
                 const size_t o = ((size_t)s * P.k + m) * P.c + (size_t)sl * PM_SLICE + half * 64;
@@ -709,6 +724,7 @@ int launch_pool_mma(const float *feat, int c, const uint32_t *member, int words,
     PoolMmaParams P;
     P.member = member; P.seg_off = seg_off; P.words = words; P.k = k; P.n_seg = n_seg; P.c = c; P.cap = cap;
     P.sum = sum; P.mean = mean; P.cnt = cnt; P.work = work; P.dbg = (tune >> 14) & 3;
+    P.m64 = (k <= 64 && !((tune >> 10) & 1)) ? 1 : 0;      // (bit 10: experiments with M = 128 for every k)
     const int n_items = n_seg * (c / PM_SLICE);
     const unsigned grid = (unsigned)(n_items < sm_count() ? n_items : sm_count());
     cudaMemsetAsync(work, 0, sizeof(int), stream);
