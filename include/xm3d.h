@@ -52,6 +52,7 @@ typedef enum {
 #define XM3D_FLAG_KEY_SENTINEL 8   /* a key equal to 2^64-1 was remapped        */
 #define XM3D_FLAG_I16_RANGE 16     /* xm3d_pack_i16: a value did not fit int16  */
 #define XM3D_FLAG_VOX_FALLBACK 32  /* XM3D_VOX_FAST_ONLY: the batch needs the multi-kernel path */
+#define XM3D_FLAG_NONFINITE 64     /* tensor-core pooling met a NaN / Inf feature: pool again with XM3D_POOL_ROWS */
 
 /* depth image element type */
 #define XM3D_DEPTH_NONE 0
@@ -202,7 +203,9 @@ XM3D_API int xm3d_pixel_bits_batch(const void *masks, int32_t mask_kind, int32_t
  *   path      XM3D_POOL_AUTO picks the kernel: partition masks / labels -> sorted pair lists + register
  *             accumulation (every row read once, HBM peak); cap_pairs > cap + 1 tells the library that masks may
  *             overlap -> every row is still read exactly once by the TENSOR-CORE kernel (tcgen05 tf32, member bits
- *             as a 0/1 operand; needs member words, no row_index, c % 128 == 0, k <= 128, finite features), else by
+ *             as a 0/1 operand; needs member words, no row_index, c % 128 == 0, k <= 128; a NaN / Inf feature would leak
+ *             into the other masks of its 64-point tile (0 x Inf), so the kernel raises XM3D_FLAG_NONFINITE when it
+ *             meets one and the caller pools that batch again with XM3D_POOL_ROWS), else by
  *             the point-major CUDA-core kernel (c % 128 == 0, k <= 96), else by the pair lists (one row read per
  *             membership).  XM3D_POOL_PAIR_LISTS / _ROWS / _MMA force one path (XM3D_ERR_UNSUPPORTED if not eligible).
  *   sum [n_seg,k,c] float32, cnt [n_seg,k] int32 (optional), mean (optional) [n_seg,k,c] = sum/cnt

@@ -602,6 +602,41 @@ def test_pool_path_selection(dev):
     assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("bad", [float("nan"), float("inf"), float("-inf"), "-nan"])
+@pytest.mark.parametrize("k", [20, 100])
+def test_pool_mma_flags_nonfinite_features(dev, bad, k):
+    """A NaN / Inf feature multiplied by a 0 membership would reach masks it does not belong to inside the tensor core:
+    the kernel raises XM3D_FLAG_NONFINITE (and only then), and the CUDA-core path gives the reference's result (NaN only
+    in the masks that hold the point)."""
+    from xmask3d_b200 import _lib as L, ops
+    g = torch.Generator(device="cpu").manual_seed(5)
+    n, c = 1000, 256
+    f = torch.randn(n, c, generator=g).to(dev)
+    seg = torch.tensor([0, 400, n], device=dev)
+    words = (k + 31) // 32
+    bits = (torch.rand(n, k, generator=g) < 0.2)
+    bits[777] = False
+    bits[777, 3] = True                                           # the bad point belongs to mask 3 of segment 1 only
+    mem = np.zeros((n, words), dtype=np.uint32)
+    for m in range(k):
+        mem[:, m // 32] |= bits[:, m].numpy().astype(np.uint32) << np.uint32(m % 32)
+    mem = torch.from_numpy(mem.view(np.int32)).to(dev)
+    st = torch.zeros(1, dtype=torch.int32, device=dev)
+    ops.pool(f, seg, k, member=mem, path="mma", status=st, cap_pairs=n * k)
+    assert int(st.item()) == 0                                    # finite features: no flag
+    if bad == "-nan":
+        f[777, 130:131] = torch.from_numpy(np.array([0xffc00001], dtype=np.uint32).view(np.float32)).to(dev)
+    else:
+        f[777, 130] = bad
+    ops.pool(f, seg, k, member=mem, path="mma", status=st, cap_pairs=n * k)
+    assert int(st.item()) & L.FLAG_NONFINITE
+    st.zero_()
+    s, cnt, _ = ops.pool(f, seg, k, member=mem, path="rows" if k <= 96 else "pair_lists", status=st, cap_pairs=n * k)
+    assert int(st.item()) == 0
+    nonfin = ~torch.isfinite(s)
+    assert int(nonfin.sum()) == 1 and bool(nonfin[1, 3, 130])
+
+
 # ----------------------------------------------------------------------------- stage 4
 def test_logits_golden(golden, dev):
     from xmask3d_b200.logits import cal_pred_logits, ensemble_logits_with_labels

@@ -16,6 +16,7 @@ CSRC = os.path.join(_HERE, "csrc")
 
 XM3D_OK = 0
 FLAG_VIS_OVERFLOW, FLAG_PAIR_OVERFLOW, FLAG_GRID_RANGE, FLAG_KEY_SENTINEL, FLAG_I16_RANGE, FLAG_VOX_FALLBACK = 1, 2, 4, 8, 16, 32
+FLAG_NONFINITE = 64
 DEPTH_NONE, DEPTH_U16, DEPTH_F64 = 0, 1, 2
 THR_GE_HALF, THR_SIGMOID_GE_HALF, THR_SIGMOID_GT_HALF = 0, 1, 2
 MASK_U8, MASK_F32 = 0, 1

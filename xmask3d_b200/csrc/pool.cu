@@ -437,7 +437,8 @@ bool make_row_tile_map(CUtensorMap *m, const float *base, int64_t rows, int c, i
 bool pool_mma_eligible(const float *feat, int c, const int32_t *row_index, const uint32_t *member, int k, int64_t cap,
                        const float *sum, const float *mean);
 int launch_pool_mma(const float *feat, int c, const uint32_t *member, int words, int n_seg, int k, const int64_t *seg_off,
-                    int64_t cap, float *sum, int32_t *cnt, float *mean, int *work, int *order, int tune, cudaStream_t stream);
+                    int64_t cap, float *sum, int32_t *cnt, float *mean, int *work, int *order, int tune, int32_t *status,
+                    cudaStream_t stream);
 
 constexpr int PR_THREADS = 512;
 constexpr int PR_WARPS = PR_THREADS / 32;
@@ -676,7 +677,7 @@ extern "C" int xm3d_pool_batch(const float *feat, int32_t c, const int32_t *row_
     if (path == XM3D_POOL_ROWS && !rows_ok) { set_error("xm3d_pool_batch: point-major path not eligible"); return XM3D_ERR_UNSUPPORTED; }
     if (path == XM3D_POOL_MMA || (path == XM3D_POOL_AUTO && overlap && mma_ok)) {
         if (g_pool_ev[0]) cudaEventRecord(g_pool_ev[0], stream);
-        const int rc = launch_pool_mma(feat, c, member, I.words, n_seg, k, seg_off, cap, sum, cnt, mean, w.work, w.order, tune, stream);
+        const int rc = launch_pool_mma(feat, c, member, I.words, n_seg, k, seg_off, cap, sum, cnt, mean, w.work, w.order, tune, status, stream);
         if (g_pool_ev[1]) cudaEventRecord(g_pool_ev[1], stream);
         return rc;
     }

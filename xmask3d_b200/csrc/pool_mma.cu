@@ -53,6 +53,7 @@ struct PoolMmaParams {
     int raw_stages, conv_stages;
     int dbg;                     // experiments only: 1 = skip the lo MMAs, 2 = skip the hi MMAs (results are then wrong)
     int m64;                     // version 2: k <= 64 -> MMAs with M = 64 (half the accumulator read-modify-write per MMA)
+    int32_t *status;             // XM3D_FLAG_NONFINITE is raised here (may be null)
 };
 
 // Work items are handed out through an atomic counter; with segments of very different sizes (0 .. 60 k points per
@@ -216,6 +217,7 @@ pool_mma_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P) 
             // ===== converters: lo = x - hi (hi = the raw tile as the tensor core reads it) =====
             const int t0 = tid - 64;
             long long tw0 = 0, tw1 = 0, tall = PM_CLK();
+            float nf0 = 0.f, nf1 = 0.f, nf2 = 0.f, nf3 = 0.f;      // NaN / Inf detector (see version 2)
             for (int t = 0; t < ntile; ++t) {
                 long long c0_ = PM_CLK();
                 mbar_wait_parked(&s_raw_full[rs], rph);
@@ -237,6 +239,8 @@ pool_mma_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P) 
                         l.z = __float_as_uint(__fsub_rn(__uint_as_float(v.z), __uint_as_float(v.z & 0xffffe000u))) & 0xffffe000u;
                         l.w = __float_as_uint(__fsub_rn(__uint_as_float(v.w), __uint_as_float(v.w & 0xffffe000u))) & 0xffffe000u;
                         lo[q] = l;
+                        nf0 = __fmaf_rn(__uint_as_float(l.x), 0.f, nf0); nf1 = __fmaf_rn(__uint_as_float(l.y), 0.f, nf1);
+                        nf2 = __fmaf_rn(__uint_as_float(l.z), 0.f, nf2); nf3 = __fmaf_rn(__uint_as_float(l.w), 0.f, nf3);
                     } else {
                         // rows past the segment belong to the next one (or lie past the tensor): never let them in
                         raw[q] = make_uint4(0u, 0u, 0u, 0u);
@@ -248,6 +252,7 @@ pool_mma_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P) 
                 if (++rs == P.raw_stages) { rs = 0; rph ^= 1; }
                 if (++cs == P.conv_stages) { cs = 0; cph ^= 1; }
             }
+            if (!((nf0 + nf1) + (nf2 + nf3) == 0.f) && P.status) atomicOr(P.status, XM3D_FLAG_NONFINITE);
             if (t0 == 0) PM_OUT(2, tw0, tw1, PM_CLK() - tall, 0);
         } else if (warp < 10) {
             // ===== builders: membership bits of the tile's points -> 0.0f / 1.0f, K-major swizzled =====
@@ -525,6 +530,9 @@ pool_mma2_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P)
             const int lo_even = r0 * 128 + ((l32 ^ (r0 & 7)) << 4) + (p8 & 1) * 8;
             const int lo_odd = r0 * 128 + (((4 + l32) ^ (r0 & 7)) << 4) + (p8 & 1) * 8;
             long long tw0 = 0, tw1 = 0, tw2 = 0, tall = PM_CLK();
+            // A NaN / Inf feature would reach, multiplied by a 0 membership, masks it does not belong to: lo of such an
+            // element is NaN (Inf - Inf), and NaN * 0 stays NaN in these four chains -> XM3D_FLAG_NONFINITE.
+            float nf0 = 0.f, nf1 = 0.f, nf2 = 0.f, nf3 = 0.f;
             for (int t = 0; t < ntile; ++t) {
                 long long c0_ = PM_CLK();
                 mbar_wait(&s_raw_full[rs], rph);
@@ -553,6 +561,8 @@ pool_mma2_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P)
                             const float l3 = __fsub_rn(__uint_as_float(v[u].w), __uint_as_float(v[u].w & 0xffffe000u));
                             asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l.x) : "f"(l1), "f"(l0));
                             asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l.y) : "f"(l3), "f"(l2));
+                            nf0 = __fmaf_rn(l0, 0.f, nf0); nf1 = __fmaf_rn(l1, 0.f, nf1);
+                            nf2 = __fmaf_rn(l2, 0.f, nf2); nf3 = __fmaf_rn(l3, 0.f, nf3);
                         } else {
                             raw[t0 + PM_CONV * j] = make_uint4(0u, 0u, 0u, 0u);   // rows past the segment never reach the tensor core
                         }
@@ -568,6 +578,7 @@ pool_mma2_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P)
                 if (++rs == P.raw_stages) { rs = 0; rph ^= 1; }
                 if (++cs == 2) { cs = 0; cph ^= 1; }
             }
+            if (!((nf0 + nf1) + (nf2 + nf3) == 0.f) && P.status) atomicOr(P.status, XM3D_FLAG_NONFINITE);
             if (t0 == 0) PM_OUT(2, tw0, tw1, PM_CLK() - tall, tw2);
         } else if (warp < 10) {
             // ===== builders: lane = mask.  32 x 32 bit transposes (ballots) of the tile's membership words, expanded in
@@ -713,7 +724,8 @@ bool pool_mma_eligible(const float *feat, int c, const int32_t *row_index, const
 }
 
 int launch_pool_mma(const float *feat, int c, const uint32_t *member, int words, int n_seg, int k, const int64_t *seg_off,
-                    int64_t cap, float *sum, int32_t *cnt, float *mean, int *work, int *order, int tune, cudaStream_t stream) {
+                    int64_t cap, float *sum, int32_t *cnt, float *mean, int *work, int *order, int tune, int32_t *status,
+                    cudaStream_t stream) {
     CUtensorMap map;
     memset(&map, 0, sizeof(map));
     // rows past `cap` are zero-filled by TMA; rows past a segment are zeroed by the converters
@@ -723,7 +735,7 @@ int launch_pool_mma(const float *feat, int c, const uint32_t *member, int words,
     }
     PoolMmaParams P;
     P.member = member; P.seg_off = seg_off; P.words = words; P.k = k; P.n_seg = n_seg; P.c = c; P.cap = cap;
-    P.sum = sum; P.mean = mean; P.cnt = cnt; P.work = work; P.dbg = (tune >> 14) & 3;
+    P.sum = sum; P.mean = mean; P.cnt = cnt; P.work = work; P.dbg = (tune >> 14) & 3; P.status = status;
     P.m64 = (k <= 64 && !((tune >> 10) & 1)) ? 1 : 0;      // (bit 10: experiments with M = 128 for every k)
     const int n_items = n_seg * (c / PM_SLICE);
     const unsigned grid = (unsigned)(n_items < sm_count() ? n_items : sm_count());
