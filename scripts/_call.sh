@@ -1,6 +1,4 @@
 set -x
-timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/gpu_tests13.log 2>&1; echo "rc=$?" >> gpurun_out/gpu_tests13.log
-timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/smoke13.log 2>&1; echo "rc=$?" >> gpurun_out/smoke13.log
-timeout 900 python bench.py > gpurun_out/bench13.json 2> gpurun_out/bench13.err; echo "rc=$?" >> gpurun_out/bench13.err
-timeout 900 python bench.py --impl reference > gpurun_out/bench13_ref.json 2> gpurun_out/bench13_ref.err; echo "rc=$?" >> gpurun_out/bench13_ref.err
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit,temperature.gpu --format=csv > gpurun_out/time_pm18.log
+timeout 600 python scripts/time_pool_mma.py rows 0 0x30000 0 rows >> gpurun_out/time_pm18.log 2>&1
 echo done

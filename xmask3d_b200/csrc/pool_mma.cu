@@ -52,6 +52,7 @@ struct PoolMmaParams {
     const int *order;            // [n_seg] segments by descending size, or null (identity)
     int raw_stages, conv_stages;
     int dbg;                     // experiments only: 1 = skip the lo MMAs, 2 = skip the hi MMAs (results are then wrong)
+    int dbg2;                    // experiments only: bit 0 = no TMA loads, bit 1 = converters idle (results are then wrong)
     int m64;                     // version 2: k <= 64 -> MMAs with M = 64 (half the accumulator read-modify-write per MMA)
     int32_t *status;             // XM3D_FLAG_NONFINITE is raised here (may be null)
 };
@@ -389,6 +390,8 @@ pool_mma_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P) 
 // 64 points as tf32; [384,448) the same as bf16 pairs.
 constexpr int P2_LO = PM_TP * PM_SLICE * 2;          // bytes of a bf16 lo tile (16 KB)
 constexpr int P2_D = 0, P2_A32 = 256, P2_A16 = 384;  // TMEM column bases
+constexpr int P2_MAX_DYN_SMEM = PM_MAX_STAGES * PM_RAW + 2 * PM_TP * PM_SLICE * 2 + 1024;   // + ~10 KB static < 227 KB
+constexpr int P2_MW = 8;                                   // tiles of membership words in flight (asynchronous copies)
 constexpr int P2_GROUP = 8;                                // tiles (of 64 points) per accumulator flush
 constexpr int P2_EPI_WARPS = 8, P2_THREADS = 32 * (10 + P2_EPI_WARPS);
 
@@ -403,6 +406,7 @@ pool_mma2_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P)
     __shared__ uint32_t s_tmem;
     __shared__ int s_item;
     __shared__ int s_cnt[128];
+    __shared__ uint32_t s_mw[P2_MW][4][PM_TP];       // membership words of the next P2_MW tiles (builder warps)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     unsigned char *base = pm_smem + ((1024u - (smem_u32(pm_smem) & 1023u)) & 1023u);
@@ -457,11 +461,15 @@ pool_mma2_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P)
                     mbar_wait_sleep(&s_raw_empty[rs], rph ^ 1, 200);
                     PM_ACC(tw0, c0_);
                     unsigned char *dst = raw_base + (size_t)rs * PM_RAW;
-                    mbar_expect_tx(&s_raw_full[rs], PM_RAW);
-                    const int y = (int)(a + (int64_t)t * PM_TP);
+                    if (P.dbg2 & 1) {
+                        mbar_arrive(&s_raw_full[rs]);
+                    } else {
+                        mbar_expect_tx(&s_raw_full[rs], PM_RAW);
+                        const int y = (int)(a + (int64_t)t * PM_TP);
 #pragma unroll
-                    for (int cb = 0; cb < 4; ++cb)
-                        tma_load_2d(dst + cb * PM_CB, &map, sl * PM_SLICE + cb * 32, y, &s_raw_full[rs]);
+                        for (int cb = 0; cb < 4; ++cb)
+                            tma_load_2d(dst + cb * PM_CB, &map, sl * PM_SLICE + cb * 32, y, &s_raw_full[rs]);
+                    }
                     if (++rs == P.raw_stages) { rs = 0; rph ^= 1; }
                 }
                 PM_OUT(0, tw0, 0, PM_CLK() - tall, ntile);
@@ -546,7 +554,7 @@ pool_mma2_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P)
                 // row = r0 + 16 (j & 3), column block = j >> 2, chunk-in-row p8 — so every address below is a per-thread
                 // base plus a compile-time offset (the loop is fully unrolled).  UNR loads are issued back to back before
                 // the first one is used (the shared-memory pipe is shared with the TMA writes and the MMA operand reads).
-                for (int j0 = 0; j0 < PM_RAW / 16 / PM_CONV; j0 += UNR) {
+                for (int j0 = 0; j0 < ((P.dbg2 & 2) ? 0 : PM_RAW / 16 / PM_CONV); j0 += UNR) {
                     uint4 v[UNR];
 #pragma unroll
                     for (int u = 0; u < UNR; ++u) v[u] = raw[t0 + PM_CONV * (j0 + u)];
@@ -590,23 +598,33 @@ pool_mma2_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P)
             const int wsel = P.m64 ? (lg >> 1) : lg;
             const int tail = P.k & 31;
             const bool word_ok = wsel < P.words && wsel * 32 < P.k;
-            auto load_word = [&](int pt) -> uint32_t {
-                uint32_t x = 0u;
-                if (word_ok && pt < n) {
-                    x = __ldg(P.member + (size_t)(a + pt) * P.words + wsel);
-                    if (tail && wsel == (P.k >> 5)) x &= (1u << tail) - 1u;
+            // The membership words of a tile reach this thread through an asynchronous copy ring, P2_MW tiles ahead: a
+            // register prefetch "two tiles ahead" that is rotated at the end of the iteration makes the rotation wait for
+            // the load, and the whole pipeline then runs at one loaded global-memory latency (~1 400 cycles) per tile.
+            auto issue_words = [&](int t) {
+                uint32_t *dst = &s_mw[t & (P2_MW - 1)][lg][lane];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int pt = t * PM_TP + 32 * h + lane;
+                    const bool ok = word_ok && t < ntile && pt < n;
+                    const uint32_t *src = ok ? P.member + (size_t)(a + pt) * P.words + wsel : P.member;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst + 32 * h)), "l"(src),
+                                 "r"(ok ? 4 : 0) : "memory");
                 }
-                return x;
+                asm volatile("cp.async.commit_group;" ::: "memory");
             };
-            uint32_t wa[3], wb[3];                               // two tiles ahead (global latency > tile budget)
-            wa[0] = load_word(lane); wb[0] = load_word(32 + lane);
-            wa[1] = load_word(PM_TP + lane); wb[1] = load_word(PM_TP + 32 + lane);
+#pragma unroll
+            for (int u = 0; u < P2_MW; ++u) issue_words(u);
+            const uint32_t tail_mask = (tail && wsel == (P.k >> 5)) ? (1u << tail) - 1u : 0xffffffffu;
             int cnt = 0;
             long long tw0 = 0, tw1 = 0, tall = PM_CLK();
             for (int t = 0; t < ntile; ++t) {
-                wa[2] = load_word((t + 2) * PM_TP + lane); wb[2] = load_word((t + 2) * PM_TP + 32 + lane);
+                asm volatile("cp.async.wait_group %0;" ::"n"(P2_MW - 1) : "memory");
+                const uint32_t x0 = s_mw[t & (P2_MW - 1)][lg][lane] & tail_mask;
+                const uint32_t x1 = s_mw[t & (P2_MW - 1)][lg][32 + lane] & tail_mask;
                 // points 0..31 / 32..63 of the tile inside MY mask: two 32 x 32 bit transposes (5 shuffle rounds each)
-                uint32_t m0 = warp_transpose32(wa[0]), m1 = warp_transpose32(wb[0]);
+                uint32_t m0 = warp_transpose32(x0), m1 = warp_transpose32(x1);
+                issue_words(t + P2_MW);                           // the slot is free: its words are in m0 / m1
                 if (P.m64) {                                      // lane L < 16 takes mask 16 lg + L = bit row (lg & 1) * 16 + L
                     const int src = (lg & 1) * 16 + (lane & 15);
                     m0 = __shfl_sync(0xffffffffu, m0, src);
@@ -644,8 +662,8 @@ pool_mma2_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P)
                 PM_ACC(tw1, c0_);
                 mbar_arrive(&s_conv_full[cs]);
                 if (++cs == 2) { cs = 0; cph ^= 1; }
-                wa[0] = wa[1]; wb[0] = wb[1]; wa[1] = wa[2]; wb[1] = wb[2];
             }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");   // the ring is reused by the next item
             if (!P.m64) s_cnt[lg * 32 + lane] = cnt;              // exactly one thread per mask
             else if (lane < 16) s_cnt[lg * 16 + lane] = cnt;
             if (tid == 192) PM_OUT(3, tw0, tw1, PM_CLK() - tall, 0);
@@ -735,7 +753,7 @@ int launch_pool_mma(const float *feat, int c, const uint32_t *member, int words,
     }
     PoolMmaParams P;
     P.member = member; P.seg_off = seg_off; P.words = words; P.k = k; P.n_seg = n_seg; P.c = c; P.cap = cap;
-    P.sum = sum; P.mean = mean; P.cnt = cnt; P.work = work; P.dbg = (tune >> 14) & 3; P.status = status;
+    P.sum = sum; P.mean = mean; P.cnt = cnt; P.work = work; P.dbg = (tune >> 14) & 3; P.dbg2 = (tune >> 16) & 3; P.status = status;
     P.m64 = (k <= 64 && !((tune >> 10) & 1)) ? 1 : 0;      // (bit 10: experiments with M = 128 for every k)
     const int n_items = n_seg * (c / PM_SLICE);
     const unsigned grid = (unsigned)(n_items < sm_count() ? n_items : sm_count());
@@ -757,9 +775,9 @@ int launch_pool_mma(const float *feat, int c, const uint32_t *member, int words,
     if (!v1 && out16) {
         static std::atomic<uint64_t> attr2{0};
         if (first_use_on_device(&attr2)) {
-            cudaFuncSetAttribute(pool_mma2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
-            cudaFuncSetAttribute(pool_mma2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
-            cudaFuncSetAttribute(pool_mma2_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+            cudaFuncSetAttribute(pool_mma2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_MAX_DYN_SMEM);
+            cudaFuncSetAttribute(pool_mma2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_MAX_DYN_SMEM);
+            cudaFuncSetAttribute(pool_mma2_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_MAX_DYN_SMEM);
         }
         P.raw_stages = (t_rs >= 1 && t_rs <= PM_MAX_STAGES) ? t_rs : 4;
         P.conv_stages = 2;
