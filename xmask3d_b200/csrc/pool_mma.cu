@@ -27,6 +27,7 @@
 // 0, the masks of its tile it does not belong to.
 #include <cuda.h>
 #include <string.h>
+#include <type_traits>
 
 #include "common.cuh"
 #include "tc.cuh"
@@ -391,9 +392,58 @@ pool_mma_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P) 
 constexpr int P2_LO = PM_TP * PM_SLICE * 2;          // bytes of a bf16 lo tile (16 KB)
 constexpr int P2_D = 0, P2_A32 = 256, P2_A16 = 384;  // TMEM column bases
 constexpr int P2_MAX_DYN_SMEM = PM_MAX_STAGES * PM_RAW + 2 * PM_TP * PM_SLICE * 2 + 1024;   // + ~10 KB static < 227 KB
+constexpr int P2_IQ = 4;                                   // work items published ahead of their consumers
 constexpr int P2_MW = 8;                                   // tiles of membership words in flight (asynchronous copies)
 constexpr int P2_GROUP = 8;                                // tiles (of 64 points) per accumulator flush
 constexpr int P2_EPI_WARPS = 8, P2_THREADS = 32 * (10 + P2_EPI_WARPS);
+
+struct P2Item { int s, sl, n; int64_t a; };
+
+// Producer side of the item ring (whole warp calls, lane 0 works): draw the next item from the global counter, publish it.
+__device__ __forceinline__ P2Item p2_publish_item(const PoolMmaParams &P, int4 *s_iq, long long *s_iq_a, uint64_t *s_full,
+                                                  uint64_t *s_free, int &iq, uint32_t &iqph, int &next_item, int n_items, int nsl,
+                                                  bool over, int lane) {
+    P2Item it{0, 0, 0, 0};
+    if (lane == 0) {
+        mbar_wait(&s_free[iq], iqph ^ 1);
+        // drawn only now (all loads of the previous item are issued): drawing one item ahead takes the last items away
+        // from the CTAs that would be free for them (measured: 1 638 instead of 1 517 tiles on the busiest CTA)
+        const int item = next_item ? n_items : atomicAdd(P.work, 1);
+        if (item < n_items) {
+            it.s = P.order ? P.order[item / nsl] : item / nsl;
+            it.sl = item % nsl;
+            it.a = P.seg_off[it.s];
+            it.n = over ? 0 : (int)(P.seg_off[it.s + 1] - it.a);
+        } else {
+            it.n = -1;
+            next_item = 1;                             // the counter ran out: do not touch it again
+        }
+        s_iq[iq] = make_int4(it.s, it.sl, it.n, 0);
+        s_iq_a[iq] = it.a;
+        mbar_arrive(&s_full[iq]);
+    }
+    it.s = __shfl_sync(0xffffffffu, it.s, 0); it.sl = __shfl_sync(0xffffffffu, it.sl, 0);
+    it.n = __shfl_sync(0xffffffffu, it.n, 0); it.a = __shfl_sync(0xffffffffu, it.a, 0);
+    if (++iq == P2_IQ) { iq = 0; iqph ^= 1; }
+    return it;
+}
+
+// Consumer side (whole warp calls): lane 0 reads the record and frees the slot for this warp.
+__device__ __forceinline__ P2Item p2_take_item(const int4 *s_iq, const long long *s_iq_a, uint64_t *s_full, uint64_t *s_free,
+                                               int &iq, uint32_t &iqph, int lane) {
+    P2Item it{0, 0, 0, 0};
+    if (lane == 0) {
+        mbar_wait(&s_full[iq], iqph);
+        const int4 r = s_iq[iq];
+        it.a = s_iq_a[iq];
+        mbar_arrive(&s_free[iq]);
+        it.s = r.x; it.sl = r.y; it.n = r.z;
+    }
+    it.s = __shfl_sync(0xffffffffu, it.s, 0); it.sl = __shfl_sync(0xffffffffu, it.sl, 0);
+    it.n = __shfl_sync(0xffffffffu, it.n, 0); it.a = __shfl_sync(0xffffffffu, it.a, 0);
+    if (++iq == P2_IQ) { iq = 0; iqph ^= 1; }
+    return it;
+}
 
 template <int UNR>                                    // converter loads in flight per thread (shared-memory latency under load)
 __global__ void __launch_bounds__(P2_THREADS, 1)
@@ -404,8 +454,14 @@ pool_mma2_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P)
     __shared__ uint64_t s_conv_full[2], s_conv_empty[2];
     __shared__ uint64_t s_tile_done[2], s_tmem_free[2];
     __shared__ uint32_t s_tmem;
-    __shared__ int s_item;
-    __shared__ int s_cnt[128];
+    // Work items flow through the roles WITHOUT a CTA-wide barrier (draining and refilling the TMA -> converter -> MMA ->
+    // epilogue pipeline at every item cost ~7 % of the kernel): the producer thread draws the item from the global counter
+    // and publishes (segment, slice, first row, rows) in a ring; lane 0 of every other warp reads it in order.
+    __shared__ uint64_t s_iq_full[P2_IQ], s_iq_free[P2_IQ];
+    __shared__ int4 s_iq[P2_IQ];                     // x = segment, y = slice, z = rows (< 0: no more items), w = unused
+    __shared__ long long s_iq_a[P2_IQ];              // first row of the segment
+    __shared__ uint64_t s_cnt_full[2], s_cnt_free[2];
+    __shared__ int s_cnt[2][128];                    // per-mask counts of the builders' item -> epilogue (two items in flight)
     __shared__ uint32_t s_mw[P2_MW][4][PM_TP];       // membership words of the next P2_MW tiles (builder warps)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -421,6 +477,8 @@ pool_mma2_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P)
             mbar_init(&s_tile_done[b], 1);
             mbar_init(&s_tmem_free[b], EPI_THREADS);
         }
+        for (int q = 0; q < P2_IQ; ++q) { mbar_init(&s_iq_full[q], 1); mbar_init(&s_iq_free[q], P2_THREADS / 32 - 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&s_cnt_full[b], PM_BUILD); mbar_init(&s_cnt_free[b], EPI_THREADS); }
         mbar_fence_init();
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map));
     }
@@ -439,284 +497,322 @@ pool_mma2_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P)
     const bool over = total_rows > P.cap;
     int rs = 0, cs = 0, buf = 0;
     uint32_t rph = 0, cph = 0, bph = 0;
-    if (tid < 128) s_cnt[tid] = 0;
-    __syncthreads();
-
-    for (;;) {
-        if (tid == 0) s_item = atomicAdd(P.work, 1);
-        __syncthreads();
-        const int item = s_item;
-        if (item >= n_items) break;
-        const int s = P.order ? P.order[item / nsl] : item / nsl, sl = item % nsl;
-        const int64_t a = P.seg_off[s];
-        const int n = over ? 0 : (int)(P.seg_off[s + 1] - a);
-        const int ntile = (n + PM_TP - 1) / PM_TP;
-
+    {
         if (warp == 0) {
-            // ===== TMA producer =====
-            if (lane == 0) {
-                long long tw0 = 0, tall = PM_CLK();
-                for (int t = 0; t < ntile; ++t) {
-                    long long c0_ = PM_CLK();
-                    mbar_wait_sleep(&s_raw_empty[rs], rph ^ 1, 200);
-                    PM_ACC(tw0, c0_);
-                    unsigned char *dst = raw_base + (size_t)rs * PM_RAW;
-                    if (P.dbg2 & 1) {
-                        mbar_arrive(&s_raw_full[rs]);
-                    } else {
-                        mbar_expect_tx(&s_raw_full[rs], PM_RAW);
-                        const int y = (int)(a + (int64_t)t * PM_TP);
+            int next_item = 0;                             // becomes 1 when the counter ran out
+            int iq = 0; uint32_t iqph = 0;
+            for (;;) {
+                const P2Item it = p2_publish_item(P, s_iq, s_iq_a, s_iq_full, s_iq_free, iq, iqph, next_item, n_items, nsl, over, lane);
+                if (it.n < 0) break;
+                const int s = it.s, sl = it.sl, n = it.n; const int64_t a = it.a;
+                const int ntile = (n + PM_TP - 1) / PM_TP;
+                (void)s; (void)sl; (void)a;
+                // ===== TMA producer =====
+                if (lane == 0) {
+                    long long tw0 = 0, tall = PM_CLK();
+                    for (int t = 0; t < ntile; ++t) {
+                        long long c0_ = PM_CLK();
+                        mbar_wait_sleep(&s_raw_empty[rs], rph ^ 1, 200);
+                        PM_ACC(tw0, c0_);
+                        unsigned char *dst = raw_base + (size_t)rs * PM_RAW;
+                        if (P.dbg2 & 1) {
+                            mbar_arrive(&s_raw_full[rs]);
+                        } else {
+                            mbar_expect_tx(&s_raw_full[rs], PM_RAW);
+                            const int y = (int)(a + (int64_t)t * PM_TP);
 #pragma unroll
-                        for (int cb = 0; cb < 4; ++cb)
-                            tma_load_2d(dst + cb * PM_CB, &map, sl * PM_SLICE + cb * 32, y, &s_raw_full[rs]);
+                            for (int cb = 0; cb < 4; ++cb)
+                                tma_load_2d(dst + cb * PM_CB, &map, sl * PM_SLICE + cb * 32, y, &s_raw_full[rs]);
+                        }
+                        if (++rs == P.raw_stages) { rs = 0; rph ^= 1; }
                     }
-                    if (++rs == P.raw_stages) { rs = 0; rph ^= 1; }
+                    PM_OUT(0, tw0, 0, PM_CLK() - tall, ntile);
                 }
-                PM_OUT(0, tw0, 0, PM_CLK() - tall, ntile);
             }
         } else if (warp == 1) {
-            // ===== MMA issuer: 8 tf32 MMAs (hi, 8 points each) + 4 bf16 MMAs (lo, 16 points each) per tile =====
-            if (lane == 0) {
-                // M = 64 when all masks fit 64 rows: every MMA reads and writes the whole M x 128 float32 accumulator for
-                // only 8 (tf32) or 16 (bf16) rank-1 updates, so its time is the accumulator traffic, not the MACs
-                const int mrows = P.m64 ? 64 : 128;
-                const uint32_t id32 = make_idesc(mrows, PM_SLICE, 2, /*A: TMEM*/ 0, /*B N-major*/ 1);
-                const uint32_t id16 = make_idesc(mrows, PM_SLICE, 1, 0, 1);
-                uint64_t d_hi[PM_MAX_STAGES], d_lo[2];
+            int iq = 0; uint32_t iqph = 0;
+            for (;;) {
+                const P2Item it = p2_take_item(s_iq, s_iq_a, s_iq_full, s_iq_free, iq, iqph, lane);
+                if (it.n < 0) break;
+                const int s = it.s, sl = it.sl, n = it.n; const int64_t a = it.a;
+                const int ntile = (n + PM_TP - 1) / PM_TP;
+                (void)s; (void)sl; (void)a;
+                // ===== MMA issuer: 8 tf32 MMAs (hi, 8 points each) + 4 bf16 MMAs (lo, 16 points each) per tile =====
+                if (lane == 0) {
+                    // M = 64 when all masks fit 64 rows: every MMA reads and writes the whole M x 128 float32 accumulator for
+                    // only 8 (tf32) or 16 (bf16) rank-1 updates, so its time is the accumulator traffic, not the MACs
+                    const int mrows = P.m64 ? 64 : 128;
+                    const uint32_t id32 = make_idesc(mrows, PM_SLICE, 2, /*A: TMEM*/ 0, /*B N-major*/ 1);
+                    const uint32_t id16 = make_idesc(mrows, PM_SLICE, 1, 0, 1);
+                    uint64_t d_hi[PM_MAX_STAGES], d_lo[2];
 #pragma unroll
-                for (int q = 0; q < PM_MAX_STAGES; ++q)     // tf32 N-major: 32-byte-atom swizzle, 4 column blocks 8 KB apart
-                    d_hi[q] = make_sw128_desc_ex(raw_base + (size_t)q * PM_RAW, PM_CB, 512, 1);
+                    for (int q = 0; q < PM_MAX_STAGES; ++q)     // tf32 N-major: 32-byte-atom swizzle, 4 column blocks 8 KB apart
+                        d_hi[q] = make_sw128_desc_ex(raw_base + (size_t)q * PM_RAW, PM_CB, 512, 1);
 #pragma unroll
-                for (int q = 0; q < 2; ++q)                 // bf16 N-major: 128-byte swizzle, 2 blocks of 64 channels 8 KB apart
-                    d_lo[q] = make_sw128_desc_ex(lo_base + (size_t)q * P2_LO, PM_TP * 128, 1024, 2);
+                    for (int q = 0; q < 2; ++q)                 // bf16 N-major: 128-byte swizzle, 2 blocks of 64 channels 8 KB apart
+                        d_lo[q] = make_sw128_desc_ex(lo_base + (size_t)q * P2_LO, PM_TP * 128, 1024, 2);
+                    long long tw0 = 0, tw1 = 0, tw2 = 0, tall = PM_CLK();
+                    for (int t = 0; t < ntile; ++t) {
+                        const bool first = t % P2_GROUP == 0, last = (t % P2_GROUP == P2_GROUP - 1) || t == ntile - 1;
+                        long long c0_ = PM_CLK();
+                        // conv_full implies raw_full: every converter thread has seen the tile's TMA barrier complete before it
+                        // arrives here (mbarrier operations are cumulative), so the issuer waits for ONE barrier per tile
+                        PM_ACC(tw0, c0_); c0_ = PM_CLK();
+                        mbar_wait(&s_conv_full[cs], cph);
+                        PM_ACC(tw1, c0_); c0_ = PM_CLK();
+                        if (first) mbar_wait(&s_tmem_free[buf], bph ^ 1);      // a fresh accumulator every P2_GROUP tiles
+                        PM_ACC(tw2, c0_);
+                        tc_fence_after();
+                        uint64_t b_hi = d_hi[0];
+#pragma unroll
+                        for (int q = 1; q < PM_MAX_STAGES; ++q)
+                            if (rs == q) b_hi = d_hi[q];
+                        const uint64_t b_lo = cs ? d_lo[1] : d_lo[0];
+                        const uint32_t d = tmem_base + (uint32_t)(P2_D + buf * PM_SLICE);
+                        const uint32_t a32 = tmem_base + (uint32_t)(P2_A32 + cs * 64), a16 = tmem_base + (uint32_t)(P2_A16 + cs * 32);
+                        if (P.dbg != 2) {
+#pragma unroll
+                            for (int ks = 0; ks < PM_TP / 8; ++ks)
+                                umma_tf32_ts(d, a32 + ks * 8, b_hi + (uint64_t)((ks * 1024) >> 4), id32, (ks || !first) ? 1u : 0u);
+                        }
+                        if (P.dbg != 1) {
+#pragma unroll
+                            for (int ks = 0; ks < PM_TP / 16; ++ks)
+                                umma_f16_ts(d, a16 + ks * 8, b_lo + (uint64_t)((ks * 2048) >> 4), id16, (P.dbg == 2 && ks == 0 && first) ? 0u : 1u);
+                        }
+                        umma_commit(&s_raw_empty[rs]);
+                        umma_commit(&s_conv_empty[cs]);
+                        if (++rs == P.raw_stages) { rs = 0; rph ^= 1; }
+                        if (++cs == 2) { cs = 0; cph ^= 1; }
+                        if (last) {
+                            umma_commit(&s_tile_done[buf]);
+                            if (++buf == 2) { buf = 0; bph ^= 1; }
+                        }
+                    }
+                    PM_OUT(1, tw0, tw1, tw2, PM_CLK() - tall);
+                }
+            }
+        } else if (warp < 6) {
+            int iq = 0; uint32_t iqph = 0;
+            for (;;) {
+                const P2Item it = p2_take_item(s_iq, s_iq_a, s_iq_full, s_iq_free, iq, iqph, lane);
+                if (it.n < 0) break;
+                const int s = it.s, sl = it.sl, n = it.n; const int64_t a = it.a;
+                const int ntile = (n + PM_TP - 1) / PM_TP;
+                (void)s; (void)sl; (void)a;
+                // ===== converters: lo = bf16(x - hi) into a 128-byte-swizzled N-major tile =====
+                const int t0 = tid - 64;
+                const int r0 = t0 >> 3, p8 = t0 & 7;
+                // logical 32-byte chunk of this thread's physical chunk (32-byte-atom swizzle of the raw tile), its 16-byte
+                // chunk inside the 64-channel block of the lo tile for even / odd 32-channel column blocks, swizzled by the row
+                const int l32 = (p8 >> 1) ^ (r0 & 3);
+                const int lo_even = r0 * 128 + ((l32 ^ (r0 & 7)) << 4) + (p8 & 1) * 8;
+                const int lo_odd = r0 * 128 + (((4 + l32) ^ (r0 & 7)) << 4) + (p8 & 1) * 8;
                 long long tw0 = 0, tw1 = 0, tw2 = 0, tall = PM_CLK();
+                // A NaN / Inf feature would reach, multiplied by a 0 membership, masks it does not belong to: lo of such an
+                // element is NaN (Inf - Inf), and NaN * 0 stays NaN in these four chains -> XM3D_FLAG_NONFINITE.
+                float nf0 = 0.f, nf1 = 0.f, nf2 = 0.f, nf3 = 0.f;
                 for (int t = 0; t < ntile; ++t) {
-                    const bool first = t % P2_GROUP == 0, last = (t % P2_GROUP == P2_GROUP - 1) || t == ntile - 1;
                     long long c0_ = PM_CLK();
                     mbar_wait(&s_raw_full[rs], rph);
                     PM_ACC(tw0, c0_); c0_ = PM_CLK();
-                    mbar_wait(&s_conv_full[cs], cph);
-                    PM_ACC(tw1, c0_); c0_ = PM_CLK();
-                    if (first) mbar_wait(&s_tmem_free[buf], bph ^ 1);      // a fresh accumulator every P2_GROUP tiles
+                    mbar_wait(&s_conv_empty[cs], cph ^ 1);
+                    PM_ACC(tw1, c0_);
+                    uint4 *raw = reinterpret_cast<uint4 *>(raw_base + (size_t)rs * PM_RAW);
+                    unsigned char *lo = lo_base + (size_t)cs * P2_LO;
+                    const int rows_valid = min(PM_TP, n - t * PM_TP);
+                    // Chunk j of this thread is physical chunk q = t0 + 128 j of the raw tile ([column block][row][8 chunks]):
+                    // row = r0 + 16 (j & 3), column block = j >> 2, chunk-in-row p8 — so every address below is a per-thread
+                    // base plus a compile-time offset (the loop is fully unrolled).  UNR loads are issued back to back before
+                    // the first one is used (the shared-memory pipe is shared with the TMA writes and the MMA operand reads).
+                    // full tiles (all but the last of a segment) take the branch-free copy of the loop
+                    auto convert = [&](auto full_tag) {
+                        constexpr bool FULL = decltype(full_tag)::value;
+                        for (int j0 = 0; j0 < ((P.dbg2 & 2) ? 0 : PM_RAW / 16 / PM_CONV); j0 += UNR) {
+                            uint4 v[UNR];
+#pragma unroll
+                            for (int u = 0; u < UNR; ++u) v[u] = raw[t0 + PM_CONV * (j0 + u)];
+#pragma unroll
+                            for (int u = 0; u < UNR; ++u) {
+                                const int j = j0 + u;
+                                uint2 l = make_uint2(0u, 0u);
+                                if (FULL || r0 + 16 * (j & 3) < rows_valid) {
+                                    const float l0 = __fsub_rn(__uint_as_float(v[u].x), __uint_as_float(v[u].x & 0xffffe000u));
+                                    const float l1 = __fsub_rn(__uint_as_float(v[u].y), __uint_as_float(v[u].y & 0xffffe000u));
+                                    const float l2 = __fsub_rn(__uint_as_float(v[u].z), __uint_as_float(v[u].z & 0xffffe000u));
+                                    const float l3 = __fsub_rn(__uint_as_float(v[u].w), __uint_as_float(v[u].w & 0xffffe000u));
+                                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l.x) : "f"(l1), "f"(l0));
+                                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l.y) : "f"(l3), "f"(l2));
+                                    nf0 = __fmaf_rn(l0, 0.f, nf0); nf1 = __fmaf_rn(l1, 0.f, nf1);
+                                    nf2 = __fmaf_rn(l2, 0.f, nf2); nf3 = __fmaf_rn(l3, 0.f, nf3);
+                                } else {
+                                    raw[t0 + PM_CONV * j] = make_uint4(0u, 0u, 0u, 0u);   // rows past the segment never reach the tensor core
+                                }
+                                // lo tile: [64-channel block j >> 3][row][16-byte chunk ^ (row & 7)][8-byte half]
+                                *reinterpret_cast<uint2 *>(lo + (((j >> 2) & 1) ? lo_odd : lo_even) + (j >> 3) * (PM_TP * 128) +
+                                                           (j & 3) * 2048) = l;
+                            }
+                        }
+                    };
+                    if (rows_valid == PM_TP) convert(std::true_type{}); else convert(std::false_type{});
+                    c0_ = PM_CLK();
+                    fence_proxy_async();
                     PM_ACC(tw2, c0_);
-                    tc_fence_after();
-                    uint64_t b_hi = d_hi[0];
-#pragma unroll
-                    for (int q = 1; q < PM_MAX_STAGES; ++q)
-                        if (rs == q) b_hi = d_hi[q];
-                    const uint64_t b_lo = cs ? d_lo[1] : d_lo[0];
-                    const uint32_t d = tmem_base + (uint32_t)(P2_D + buf * PM_SLICE);
-                    const uint32_t a32 = tmem_base + (uint32_t)(P2_A32 + cs * 64), a16 = tmem_base + (uint32_t)(P2_A16 + cs * 32);
-                    if (P.dbg != 2) {
-#pragma unroll
-                        for (int ks = 0; ks < PM_TP / 8; ++ks)
-                            umma_tf32_ts(d, a32 + ks * 8, b_hi + (uint64_t)((ks * 1024) >> 4), id32, (ks || !first) ? 1u : 0u);
-                    }
-                    if (P.dbg != 1) {
-#pragma unroll
-                        for (int ks = 0; ks < PM_TP / 16; ++ks)
-                            umma_f16_ts(d, a16 + ks * 8, b_lo + (uint64_t)((ks * 2048) >> 4), id16, (P.dbg == 2 && ks == 0 && first) ? 0u : 1u);
-                    }
-                    umma_commit(&s_raw_empty[rs]);
-                    umma_commit(&s_conv_empty[cs]);
+                    mbar_arrive(&s_conv_full[cs]);
                     if (++rs == P.raw_stages) { rs = 0; rph ^= 1; }
                     if (++cs == 2) { cs = 0; cph ^= 1; }
-                    if (last) {
-                        umma_commit(&s_tile_done[buf]);
-                        if (++buf == 2) { buf = 0; bph ^= 1; }
-                    }
                 }
-                PM_OUT(1, tw0, tw1, tw2, PM_CLK() - tall);
+                if (!((nf0 + nf1) + (nf2 + nf3) == 0.f) && P.status) atomicOr(P.status, XM3D_FLAG_NONFINITE);
+                if (t0 == 0) PM_OUT(2, tw0, tw1, PM_CLK() - tall, tw2);
             }
-        } else if (warp < 6) {
-            // ===== converters: lo = bf16(x - hi) into a 128-byte-swizzled N-major tile =====
-            const int t0 = tid - 64;
-            const int r0 = t0 >> 3, p8 = t0 & 7;
-            // logical 32-byte chunk of this thread's physical chunk (32-byte-atom swizzle of the raw tile), its 16-byte
-            // chunk inside the 64-channel block of the lo tile for even / odd 32-channel column blocks, swizzled by the row
-            const int l32 = (p8 >> 1) ^ (r0 & 3);
-            const int lo_even = r0 * 128 + ((l32 ^ (r0 & 7)) << 4) + (p8 & 1) * 8;
-            const int lo_odd = r0 * 128 + (((4 + l32) ^ (r0 & 7)) << 4) + (p8 & 1) * 8;
-            long long tw0 = 0, tw1 = 0, tw2 = 0, tall = PM_CLK();
-            // A NaN / Inf feature would reach, multiplied by a 0 membership, masks it does not belong to: lo of such an
-            // element is NaN (Inf - Inf), and NaN * 0 stays NaN in these four chains -> XM3D_FLAG_NONFINITE.
-            float nf0 = 0.f, nf1 = 0.f, nf2 = 0.f, nf3 = 0.f;
-            for (int t = 0; t < ntile; ++t) {
-                long long c0_ = PM_CLK();
-                mbar_wait(&s_raw_full[rs], rph);
-                PM_ACC(tw0, c0_); c0_ = PM_CLK();
-                mbar_wait(&s_conv_empty[cs], cph ^ 1);
-                PM_ACC(tw1, c0_);
-                uint4 *raw = reinterpret_cast<uint4 *>(raw_base + (size_t)rs * PM_RAW);
-                unsigned char *lo = lo_base + (size_t)cs * P2_LO;
-                const int rows_valid = min(PM_TP, n - t * PM_TP);
-                // Chunk j of this thread is physical chunk q = t0 + 128 j of the raw tile ([column block][row][8 chunks]):
-                // row = r0 + 16 (j & 3), column block = j >> 2, chunk-in-row p8 — so every address below is a per-thread
-                // base plus a compile-time offset (the loop is fully unrolled).  UNR loads are issued back to back before
-                // the first one is used (the shared-memory pipe is shared with the TMA writes and the MMA operand reads).
-                for (int j0 = 0; j0 < ((P.dbg2 & 2) ? 0 : PM_RAW / 16 / PM_CONV); j0 += UNR) {
-                    uint4 v[UNR];
-#pragma unroll
-                    for (int u = 0; u < UNR; ++u) v[u] = raw[t0 + PM_CONV * (j0 + u)];
-#pragma unroll
-                    for (int u = 0; u < UNR; ++u) {
-                        const int j = j0 + u;
-                        uint2 l = make_uint2(0u, 0u);
-                        if (r0 + 16 * (j & 3) < rows_valid) {
-                            const float l0 = __fsub_rn(__uint_as_float(v[u].x), __uint_as_float(v[u].x & 0xffffe000u));
-                            const float l1 = __fsub_rn(__uint_as_float(v[u].y), __uint_as_float(v[u].y & 0xffffe000u));
-                            const float l2 = __fsub_rn(__uint_as_float(v[u].z), __uint_as_float(v[u].z & 0xffffe000u));
-                            const float l3 = __fsub_rn(__uint_as_float(v[u].w), __uint_as_float(v[u].w & 0xffffe000u));
-                            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l.x) : "f"(l1), "f"(l0));
-                            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l.y) : "f"(l3), "f"(l2));
-                            nf0 = __fmaf_rn(l0, 0.f, nf0); nf1 = __fmaf_rn(l1, 0.f, nf1);
-                            nf2 = __fmaf_rn(l2, 0.f, nf2); nf3 = __fmaf_rn(l3, 0.f, nf3);
-                        } else {
-                            raw[t0 + PM_CONV * j] = make_uint4(0u, 0u, 0u, 0u);   // rows past the segment never reach the tensor core
-                        }
-                        // lo tile: [64-channel block j >> 3][row][16-byte chunk ^ (row & 7)][8-byte half]
-                        *reinterpret_cast<uint2 *>(lo + (((j >> 2) & 1) ? lo_odd : lo_even) + (j >> 3) * (PM_TP * 128) +
-                                                   (j & 3) * 2048) = l;
-                    }
-                }
-                c0_ = PM_CLK();
-                fence_proxy_async();
-                PM_ACC(tw2, c0_);
-                mbar_arrive(&s_conv_full[cs]);
-                if (++rs == P.raw_stages) { rs = 0; rph ^= 1; }
-                if (++cs == 2) { cs = 0; cph ^= 1; }
-            }
-            if (!((nf0 + nf1) + (nf2 + nf3) == 0.f) && P.status) atomicOr(P.status, XM3D_FLAG_NONFINITE);
-            if (t0 == 0) PM_OUT(2, tw0, tw1, PM_CLK() - tall, tw2);
         } else if (warp < 10) {
-            // ===== builders: lane = mask.  32 x 32 bit transposes (ballots) of the tile's membership words, expanded in
-            // registers to 0.0f / 1.0f (tf32) and to bf16 pairs, stored into tensor memory =====
-            // M = 128: TMEM lane = mask, lane group lg holds masks 32 lg .. 32 lg + 31 = membership word lg.
-            // M = 64:  rows 16 q .. 16 q + 15 live in lanes 0..15 of lane group q: this warp's masks are 16 lg .. 16 lg + 15,
-            //          bits (lg & 1) * 16 .. of membership word lg >> 1.
-            const int lg = warp & 3;
-            const int wsel = P.m64 ? (lg >> 1) : lg;
-            const int tail = P.k & 31;
-            const bool word_ok = wsel < P.words && wsel * 32 < P.k;
-            // The membership words of a tile reach this thread through an asynchronous copy ring, P2_MW tiles ahead: a
-            // register prefetch "two tiles ahead" that is rotated at the end of the iteration makes the rotation wait for
-            // the load, and the whole pipeline then runs at one loaded global-memory latency (~1 400 cycles) per tile.
-            auto issue_words = [&](int t) {
-                uint32_t *dst = &s_mw[t & (P2_MW - 1)][lg][lane];
+            int iq = 0; uint32_t iqph = 0; int ib = 0; uint32_t ibph = 0;
+            for (;;) {
+                const P2Item it = p2_take_item(s_iq, s_iq_a, s_iq_full, s_iq_free, iq, iqph, lane);
+                if (it.n < 0) break;
+                const int s = it.s, sl = it.sl, n = it.n; const int64_t a = it.a;
+                const int ntile = (n + PM_TP - 1) / PM_TP;
+                (void)s; (void)sl; (void)a;
+                // ===== builders: lane = mask.  32 x 32 bit transposes (ballots) of the tile's membership words, expanded in
+                // registers to 0.0f / 1.0f (tf32) and to bf16 pairs, stored into tensor memory =====
+                // M = 128: TMEM lane = mask, lane group lg holds masks 32 lg .. 32 lg + 31 = membership word lg.
+                // M = 64:  rows 16 q .. 16 q + 15 live in lanes 0..15 of lane group q: this warp's masks are 16 lg .. 16 lg + 15,
+                //          bits (lg & 1) * 16 .. of membership word lg >> 1.
+                const int lg = warp & 3;
+                const int wsel = P.m64 ? (lg >> 1) : lg;
+                const int tail = P.k & 31;
+                const bool word_ok = wsel < P.words && wsel * 32 < P.k;
+                // The membership words of a tile reach this thread through an asynchronous copy ring, P2_MW tiles ahead: a
+                // register prefetch "two tiles ahead" that is rotated at the end of the iteration makes the rotation wait for
+                // the load, and the whole pipeline then runs at one loaded global-memory latency (~1 400 cycles) per tile.
+                auto issue_words = [&](int t) {
+                    uint32_t *dst = &s_mw[t & (P2_MW - 1)][lg][lane];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int pt = t * PM_TP + 32 * h + lane;
-                    const bool ok = word_ok && t < ntile && pt < n;
-                    const uint32_t *src = ok ? P.member + (size_t)(a + pt) * P.words + wsel : P.member;
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst + 32 * h)), "l"(src),
-                                 "r"(ok ? 4 : 0) : "memory");
+                    for (int h = 0; h < 2; ++h) {
+                        const int pt = t * PM_TP + 32 * h + lane;
+                        const bool ok = word_ok && t < ntile && pt < n;
+                        const uint32_t *src = ok ? P.member + (size_t)(a + pt) * P.words + wsel : P.member;
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst + 32 * h)), "l"(src),
+                                     "r"(ok ? 4 : 0) : "memory");
+                    }
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                };
+#pragma unroll
+                for (int u = 0; u < P2_MW; ++u) issue_words(u);
+                const uint32_t tail_mask = (tail && wsel == (P.k >> 5)) ? (1u << tail) - 1u : 0xffffffffu;
+                int cnt = 0;
+                long long tw0 = 0, tw1 = 0, tall = PM_CLK();
+                for (int t = 0; t < ntile; ++t) {
+                    asm volatile("cp.async.wait_group %0;" ::"n"(P2_MW - 1) : "memory");
+                    const uint32_t x0 = s_mw[t & (P2_MW - 1)][lg][lane] & tail_mask;
+                    const uint32_t x1 = s_mw[t & (P2_MW - 1)][lg][32 + lane] & tail_mask;
+                    // points 0..31 / 32..63 of the tile inside MY mask: two 32 x 32 bit transposes (5 shuffle rounds each)
+                    uint32_t m0 = warp_transpose32(x0), m1 = warp_transpose32(x1);
+                    issue_words(t + P2_MW);                           // the slot is free: its words are in m0 / m1
+                    if (P.m64) {                                      // lane L < 16 takes mask 16 lg + L = bit row (lg & 1) * 16 + L
+                        const int src = (lg & 1) * 16 + (lane & 15);
+                        m0 = __shfl_sync(0xffffffffu, m0, src);
+                        m1 = __shfl_sync(0xffffffffu, m1, src);
+                        if (lane >= 16) { m0 = 0u; m1 = 0u; }
+                    }
+                    cnt += __popc(m0) + __popc(m1);
+                    long long c0_ = PM_CLK();
+                    mbar_wait(&s_conv_empty[cs], cph ^ 1);
+                    PM_ACC(tw0, c0_);
+                    c0_ = PM_CLK();
+                    tc_fence_after();
+                    const uint32_t lane_addr = (uint32_t)(lg * 32) << 16;
+                    const uint32_t a32 = tmem_base + lane_addr + (uint32_t)(P2_A32 + cs * 64);
+                    const uint32_t a16 = tmem_base + lane_addr + (uint32_t)(P2_A16 + cs * 32);
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+                        const uint32_t bits = (h < 2 ? m0 : m1) >> ((h & 1) * 16);
+                        uint32_t v[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = ((bits >> j) & 1u) ? 0x3f800000u : 0u;
+                        tmem_st16(a32 + h * 16, v);
+                    }
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const uint32_t bits = h ? m1 : m0;
+                        uint32_t v[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            v[j] = (((bits >> (2 * j)) & 1u) ? 0x3f80u : 0u) | (((bits >> (2 * j + 1)) & 1u) ? 0x3f800000u : 0u);
+                        tmem_st16(a16 + h * 16, v);
+                    }
+                    tmem_st_wait();
+                    tc_fence_before();
+                    PM_ACC(tw1, c0_);
+                    mbar_arrive(&s_conv_full[cs]);
+                    if (++cs == 2) { cs = 0; cph ^= 1; }
                 }
-                asm volatile("cp.async.commit_group;" ::: "memory");
-            };
-#pragma unroll
-            for (int u = 0; u < P2_MW; ++u) issue_words(u);
-            const uint32_t tail_mask = (tail && wsel == (P.k >> 5)) ? (1u << tail) - 1u : 0xffffffffu;
-            int cnt = 0;
-            long long tw0 = 0, tw1 = 0, tall = PM_CLK();
-            for (int t = 0; t < ntile; ++t) {
-                asm volatile("cp.async.wait_group %0;" ::"n"(P2_MW - 1) : "memory");
-                const uint32_t x0 = s_mw[t & (P2_MW - 1)][lg][lane] & tail_mask;
-                const uint32_t x1 = s_mw[t & (P2_MW - 1)][lg][32 + lane] & tail_mask;
-                // points 0..31 / 32..63 of the tile inside MY mask: two 32 x 32 bit transposes (5 shuffle rounds each)
-                uint32_t m0 = warp_transpose32(x0), m1 = warp_transpose32(x1);
-                issue_words(t + P2_MW);                           // the slot is free: its words are in m0 / m1
-                if (P.m64) {                                      // lane L < 16 takes mask 16 lg + L = bit row (lg & 1) * 16 + L
-                    const int src = (lg & 1) * 16 + (lane & 15);
-                    m0 = __shfl_sync(0xffffffffu, m0, src);
-                    m1 = __shfl_sync(0xffffffffu, m1, src);
-                    if (lane >= 16) { m0 = 0u; m1 = 0u; }
-                }
-                cnt += __popc(m0) + __popc(m1);
-                long long c0_ = PM_CLK();
-                mbar_wait(&s_conv_empty[cs], cph ^ 1);
-                PM_ACC(tw0, c0_);
-                c0_ = PM_CLK();
-                tc_fence_after();
-                const uint32_t lane_addr = (uint32_t)(lg * 32) << 16;
-                const uint32_t a32 = tmem_base + lane_addr + (uint32_t)(P2_A32 + cs * 64);
-                const uint32_t a16 = tmem_base + lane_addr + (uint32_t)(P2_A16 + cs * 32);
-#pragma unroll
-                for (int h = 0; h < 4; ++h) {
-                    const uint32_t bits = (h < 2 ? m0 : m1) >> ((h & 1) * 16);
-                    uint32_t v[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = ((bits >> j) & 1u) ? 0x3f800000u : 0u;
-                    tmem_st16(a32 + h * 16, v);
-                }
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const uint32_t bits = h ? m1 : m0;
-                    uint32_t v[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        v[j] = (((bits >> (2 * j)) & 1u) ? 0x3f80u : 0u) | (((bits >> (2 * j + 1)) & 1u) ? 0x3f800000u : 0u);
-                    tmem_st16(a16 + h * 16, v);
-                }
-                tmem_st_wait();
-                tc_fence_before();
-                PM_ACC(tw1, c0_);
-                mbar_arrive(&s_conv_full[cs]);
-                if (++cs == 2) { cs = 0; cph ^= 1; }
+                asm volatile("cp.async.wait_group 0;" ::: "memory");   // the ring is reused by the next item
+                mbar_wait(&s_cnt_free[ib], ibph ^ 1);                  // the epilogue has read the counts of two items ago
+                if (!P.m64) s_cnt[ib][lg * 32 + lane] = cnt;          // exactly one thread per mask
+                else if (lane < 16) s_cnt[ib][lg * 16 + lane] = cnt;
+                mbar_arrive(&s_cnt_full[ib]);
+                if (tid == 192) PM_OUT(3, tw0, tw1, PM_CLK() - tall, 0);
+                if (++ib == 2) { ib = 0; ibph ^= 1; }
             }
-            asm volatile("cp.async.wait_group 0;" ::: "memory");   // the ring is reused by the next item
-            if (!P.m64) s_cnt[lg * 32 + lane] = cnt;              // exactly one thread per mask
-            else if (lane < 16) s_cnt[lg * 16 + lane] = cnt;
-            if (tid == 192) PM_OUT(3, tw0, tw1, PM_CLK() - tall, 0);
-            asm volatile("bar.sync 1, %0;" ::"n"(PM_BUILD + EPI_THREADS) : "memory");
         } else {
-            // ===== epilogue: lane = mask, 64 channels per warp =====
-            const int lg = warp & 3, half = (warp - 10) >> 2;
-            float acc[64];
+            int iq = 0; uint32_t iqph = 0; int ib = 0; uint32_t ibph = 0;
+            for (;;) {
+                const P2Item it = p2_take_item(s_iq, s_iq_a, s_iq_full, s_iq_free, iq, iqph, lane);
+                if (it.n < 0) break;
+                const int s = it.s, sl = it.sl, n = it.n; const int64_t a = it.a;
+                const int ntile = (n + PM_TP - 1) / PM_TP;
+                (void)s; (void)sl; (void)a;
+                // ===== epilogue: lane = mask, 64 channels per warp =====
+                const int lg = warp & 3, half = (warp - 10) >> 2;
+                float acc[64];
 #pragma unroll
-            for (int j = 0; j < 64; ++j) acc[j] = 0.f;
-            long long tw0 = 0, tall = PM_CLK();
-            for (int g = 0; g < (ntile + P2_GROUP - 1) / P2_GROUP; ++g) {
-                long long c0_ = PM_CLK();
-                mbar_wait_sleep(&s_tile_done[buf], bph, 100);
-                PM_ACC(tw0, c0_);
-                tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(P2_D + buf * PM_SLICE + half * 64);
+                for (int j = 0; j < 64; ++j) acc[j] = 0.f;
+                long long tw0 = 0, tall = PM_CLK();
+                for (int g = 0; g < (ntile + P2_GROUP - 1) / P2_GROUP; ++g) {
+                    long long c0_ = PM_CLK();
+                    mbar_wait_sleep(&s_tile_done[buf], bph, 100);
+                    PM_ACC(tw0, c0_);
+                    tc_fence_after();
+                    const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(P2_D + buf * PM_SLICE + half * 64);
 #pragma unroll
-                for (int c0 = 0; c0 < 64; c0 += 32) {
-                    uint32_t v0[16], v1[16];
-                    tmem_ld16_nowait(taddr + c0, v0);
-                    tmem_ld16_nowait(taddr + c0 + 16, v1);
-                    tmem_ld_wait();
+                    for (int c0 = 0; c0 < 64; c0 += 32) {
+                        uint32_t v0[16], v1[16];
+                        tmem_ld16_nowait(taddr + c0, v0);
+                        tmem_ld16_nowait(taddr + c0 + 16, v1);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            acc[c0 + j] = __fadd_rn(acc[c0 + j], __uint_as_float(v0[j]));
+                            acc[c0 + 16 + j] = __fadd_rn(acc[c0 + 16 + j], __uint_as_float(v1[j]));
+                        }
+                    }
+                    tc_fence_before();
+                    mbar_arrive(&s_tmem_free[buf]);
+                    if (++buf == 2) { buf = 0; bph ^= 1; }
+                }
+                if (tid == 320) PM_OUT(4, tw0, 0, PM_CLK() - tall, 0);
+                mbar_wait(&s_cnt_full[ib], ibph);                      // the builders' counts of this item
+                const int m = P.m64 ? (lane < 16 ? lg * 16 + lane : P.k) : lg * 32 + lane;
+                const int nm = m < P.k ? s_cnt[ib][m] : 0;
+                mbar_arrive(&s_cnt_free[ib]);
+                if (m < P.k) {
+                    const size_t o = ((size_t)s * P.k + m) * P.c + (size_t)sl * PM_SLICE + half * 64;
+                    float4 *so = reinterpret_cast<float4 *>(P.sum + o);
+                    float4 *mo = P.mean ? reinterpret_cast<float4 *>(P.mean + o) : nullptr;
+                    const float d = (float)nm;
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        acc[c0 + j] = __fadd_rn(acc[c0 + j], __uint_as_float(v0[j]));
-                        acc[c0 + 16 + j] = __fadd_rn(acc[c0 + 16 + j], __uint_as_float(v1[j]));
+                        const float4 v = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+                        so[j] = v;
+                        if (mo) mo[j] = nm > 0 ? make_float4(__fdiv_rn(v.x, d), __fdiv_rn(v.y, d), __fdiv_rn(v.z, d), __fdiv_rn(v.w, d))
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
+                    if (P.cnt && sl == 0 && half == 0) P.cnt[s * P.k + m] = nm;
                 }
-                tc_fence_before();
-                mbar_arrive(&s_tmem_free[buf]);
-                if (++buf == 2) { buf = 0; bph ^= 1; }
-            }
-            if (tid == 320) PM_OUT(4, tw0, 0, PM_CLK() - tall, 0);
-            asm volatile("bar.sync 1, %0;" ::"n"(PM_BUILD + EPI_THREADS) : "memory");
-            const int m = P.m64 ? (lane < 16 ? lg * 16 + lane : P.k) : lg * 32 + lane;
-            if (m < P.k) {
-                const int nm = s_cnt[m];
-                const size_t o = ((size_t)s * P.k + m) * P.c + (size_t)sl * PM_SLICE + half * 64;
-                float4 *so = reinterpret_cast<float4 *>(P.sum + o);
-                float4 *mo = P.mean ? reinterpret_cast<float4 *>(P.mean + o) : nullptr;
-                const float d = (float)nm;
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float4 v = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
-                    so[j] = v;
-                    if (mo) mo[j] = nm > 0 ? make_float4(__fdiv_rn(v.x, d), __fdiv_rn(v.y, d), __fdiv_rn(v.z, d), __fdiv_rn(v.w, d))
-                                           : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                if (P.cnt && sl == 0 && half == 0) P.cnt[s * P.k + m] = nm;
+                if (++ib == 2) { ib = 0; ibph ^= 1; }
             }
         }
-        __syncthreads();                                          // item done: outputs written, s_cnt consumed
     }
     tc_fence_before();
     __syncthreads();
