@@ -40,7 +40,7 @@ for tune in tunes:
     names = {0: ("TMA producer", ["wait raw_empty", "-", "loop total", "tiles"]),
              1: ("MMA issuer", ["wait raw_full", "wait conv_full", "wait tmem_free", "loop total"]),
              2: ("converter", ["wait raw_full", "wait conv_empty", "loop total", "fence.proxy.async"]),
-             3: ("builder", ["wait conv_empty", "expand + tcgen05.st + wait", "loop total", "-"]),
+             3: ("builder", ["wait conv_empty", "expand + tcgen05.st", "loop total", "tcgen05.wait::st"]),
              4: ("epilogue", ["wait tile_done", "-", "loop total", "-"])}
     for r, (nm, cols) in names.items():
         per_tile = d[:, r, :].sum(0) / tiles.sum()

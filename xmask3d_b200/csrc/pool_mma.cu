@@ -570,6 +570,7 @@ pool_mma2_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P)
                         const uint64_t b_lo = cs ? d_lo[1] : d_lo[0];
                         const uint32_t d = tmem_base + (uint32_t)(P2_D + buf * PM_SLICE);
                         const uint32_t a32 = tmem_base + (uint32_t)(P2_A32 + cs * 64), a16 = tmem_base + (uint32_t)(P2_A16 + cs * 32);
+                        for (int rep = 0; rep < ((P.dbg2 & 4) ? 4 : 1); ++rep) {   // (experiments: 4 x the MMAs per tile)
                         if (P.dbg != 2) {
 #pragma unroll
                             for (int ks = 0; ks < PM_TP / 8; ++ks)
@@ -579,6 +580,7 @@ pool_mma2_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P)
 #pragma unroll
                             for (int ks = 0; ks < PM_TP / 16; ++ks)
                                 umma_f16_ts(d, a16 + ks * 8, b_lo + (uint64_t)((ks * 2048) >> 4), id16, (P.dbg == 2 && ks == 0 && first) ? 0u : 1u);
+                        }
                         }
                         umma_commit(&s_raw_empty[rs]);
                         umma_commit(&s_conv_empty[cs]);
@@ -700,8 +702,8 @@ pool_mma2_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P)
 #pragma unroll
                 for (int u = 0; u < P2_MW; ++u) issue_words(u);
                 const uint32_t tail_mask = (tail && wsel == (P.k >> 5)) ? (1u << tail) - 1u : 0xffffffffu;
-                int cnt = 0;
-                long long tw0 = 0, tw1 = 0, tall = PM_CLK();
+                int cnt = 0, cnt_b = 0;                                // (M = 64: rows t/4 and t/4 + 8 of this warp)
+                long long tw0 = 0, tw1 = 0, tw2 = 0, tall = PM_CLK();
                 for (int t = 0; t < ntile; ++t) {
                     asm volatile("cp.async.wait_group %0;" ::"n"(P2_MW - 1) : "memory");
                     const uint32_t x0 = s_mw[t & (P2_MW - 1)][lg][lane] & tail_mask;
@@ -709,13 +711,19 @@ pool_mma2_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P)
                     // points 0..31 / 32..63 of the tile inside MY mask: two 32 x 32 bit transposes (5 shuffle rounds each)
                     uint32_t m0 = warp_transpose32(x0), m1 = warp_transpose32(x1);
                     issue_words(t + P2_MW);                           // the slot is free: its words are in m0 / m1
-                    if (P.m64) {                                      // lane L < 16 takes mask 16 lg + L = bit row (lg & 1) * 16 + L
-                        const int src = (lg & 1) * 16 + (lane & 15);
-                        m0 = __shfl_sync(0xffffffffu, m0, src);
-                        m1 = __shfl_sync(0xffffffffu, m1, src);
-                        if (lane >= 16) { m0 = 0u; m1 = 0u; }
+                    // M = 64: the 16 mask rows of this warp go to lanes 0..15 of its lane group with the 16-lane store shape
+                    // (thread t: rows t/4 and t/4 + 8, columns 8 i + 2 (t % 4) + {0, 1}) — half the tensor-memory stores and
+                    // half the expansion work of the 32-lane shape, which would write 16 unused lanes.
+                    uint32_t ra0 = 0u, ra1 = 0u, rb0 = 0u, rb1 = 0u;
+                    if (P.m64) {
+                        const int src = (lg & 1) * 16 + (lane >> 2);
+                        ra0 = __shfl_sync(0xffffffffu, m0, src); rb0 = __shfl_sync(0xffffffffu, m0, src + 8);
+                        ra1 = __shfl_sync(0xffffffffu, m1, src); rb1 = __shfl_sync(0xffffffffu, m1, src + 8);
+                        cnt += __popc(ra0) + __popc(ra1);
+                        cnt_b += __popc(rb0) + __popc(rb1);
+                    } else {
+                        cnt += __popc(m0) + __popc(m1);
                     }
-                    cnt += __popc(m0) + __popc(m1);
                     long long c0_ = PM_CLK();
                     mbar_wait(&s_conv_empty[cs], cph ^ 1);
                     PM_ACC(tw0, c0_);
@@ -724,35 +732,72 @@ pool_mma2_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P)
                     const uint32_t lane_addr = (uint32_t)(lg * 32) << 16;
                     const uint32_t a32 = tmem_base + lane_addr + (uint32_t)(P2_A32 + cs * 64);
                     const uint32_t a16 = tmem_base + lane_addr + (uint32_t)(P2_A16 + cs * 32);
+                    if (P.m64) {
+                        {   // tf32 0.0f / 1.0f: column = point
+                            const int sh = 2 * (lane & 3);
+                            const uint32_t a_lo = ra0 >> sh, a_hi = ra1 >> sh, b_lo = rb0 >> sh, b_hi = rb1 >> sh;
+                            uint32_t v[32];
 #pragma unroll
-                    for (int h = 0; h < 4; ++h) {
-                        const uint32_t bits = (h < 2 ? m0 : m1) >> ((h & 1) * 16);
-                        uint32_t v[16];
+                            for (int i = 0; i < 8; ++i) {
+                                const uint32_t wa = i < 4 ? a_lo : a_hi, wb = i < 4 ? b_lo : b_hi;
+                                const int bit = 8 * (i & 3);
+                                v[4 * i + 0] = ((wa >> bit) & 1u) ? 0x3f800000u : 0u;
+                                v[4 * i + 1] = ((wa >> (bit + 1)) & 1u) ? 0x3f800000u : 0u;
+                                v[4 * i + 2] = ((wb >> bit) & 1u) ? 0x3f800000u : 0u;
+                                v[4 * i + 3] = ((wb >> (bit + 1)) & 1u) ? 0x3f800000u : 0u;
+                            }
+                            tmem_st_16x256b_x8(a32, v);
+                        }
+                        {   // bf16 pairs: column c = points 2 c (low half), 2 c + 1
+                            const int sh = 4 * (lane & 3);
+                            const uint32_t a_lo = ra0 >> sh, a_hi = ra1 >> sh, b_lo = rb0 >> sh, b_hi = rb1 >> sh;
+                            uint32_t v[16];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = ((bits >> j) & 1u) ? 0x3f800000u : 0u;
-                        tmem_st16(a32 + h * 16, v);
+                            for (int i = 0; i < 4; ++i) {
+                                const uint32_t wa = i < 2 ? a_lo : a_hi, wb = i < 2 ? b_lo : b_hi;
+                                const int bit = 16 * (i & 1);
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) {
+                                    v[4 * i + e] = (((wa >> (bit + 2 * e)) & 1u) ? 0x3f80u : 0u) |
+                                                   (((wa >> (bit + 2 * e + 1)) & 1u) ? 0x3f800000u : 0u);
+                                    v[4 * i + 2 + e] = (((wb >> (bit + 2 * e)) & 1u) ? 0x3f80u : 0u) |
+                                                       (((wb >> (bit + 2 * e + 1)) & 1u) ? 0x3f800000u : 0u);
+                                }
+                            }
+                            tmem_st_16x256b_x4(a16, v);
+                        }
+                    } else {
+#pragma unroll
+                        for (int h = 0; h < 4; ++h) {
+                            const uint32_t bits = (h < 2 ? m0 : m1) >> ((h & 1) * 16);
+                            uint32_t v[16];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) v[j] = ((bits >> j) & 1u) ? 0x3f800000u : 0u;
+                            tmem_st16(a32 + h * 16, v);
+                        }
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const uint32_t bits = h ? m1 : m0;
+                            uint32_t v[16];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                v[j] = (((bits >> (2 * j)) & 1u) ? 0x3f80u : 0u) | (((bits >> (2 * j + 1)) & 1u) ? 0x3f800000u : 0u);
+                            tmem_st16(a16 + h * 16, v);
+                        }
                     }
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const uint32_t bits = h ? m1 : m0;
-                        uint32_t v[16];
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            v[j] = (((bits >> (2 * j)) & 1u) ? 0x3f80u : 0u) | (((bits >> (2 * j + 1)) & 1u) ? 0x3f800000u : 0u);
-                        tmem_st16(a16 + h * 16, v);
-                    }
+                    PM_ACC(tw1, c0_); c0_ = PM_CLK();
                     tmem_st_wait();
                     tc_fence_before();
-                    PM_ACC(tw1, c0_);
+                    PM_ACC(tw2, c0_);
                     mbar_arrive(&s_conv_full[cs]);
                     if (++cs == 2) { cs = 0; cph ^= 1; }
                 }
                 asm volatile("cp.async.wait_group 0;" ::: "memory");   // the ring is reused by the next item
                 mbar_wait(&s_cnt_free[ib], ibph ^ 1);                  // the epilogue has read the counts of two items ago
                 if (!P.m64) s_cnt[ib][lg * 32 + lane] = cnt;          // exactly one thread per mask
-                else if (lane < 16) s_cnt[ib][lg * 16 + lane] = cnt;
+                else if ((lane & 3) == 0) { s_cnt[ib][lg * 16 + (lane >> 2)] = cnt; s_cnt[ib][lg * 16 + (lane >> 2) + 8] = cnt_b; }
                 mbar_arrive(&s_cnt_full[ib]);
-                if (tid == 192) PM_OUT(3, tw0, tw1, PM_CLK() - tall, 0);
+                if (tid == 192) PM_OUT(3, tw0, tw1, PM_CLK() - tall, tw2);
                 if (++ib == 2) { ib = 0; ibph ^= 1; }
             }
         } else {
@@ -849,7 +894,7 @@ int launch_pool_mma(const float *feat, int c, const uint32_t *member, int words,
     }
     PoolMmaParams P;
     P.member = member; P.seg_off = seg_off; P.words = words; P.k = k; P.n_seg = n_seg; P.c = c; P.cap = cap;
-    P.sum = sum; P.mean = mean; P.cnt = cnt; P.work = work; P.dbg = (tune >> 14) & 3; P.dbg2 = (tune >> 16) & 3; P.status = status;
+    P.sum = sum; P.mean = mean; P.cnt = cnt; P.work = work; P.dbg = (tune >> 14) & 3; P.dbg2 = (tune >> 16) & 7; P.status = status;
     P.m64 = (k <= 64 && !((tune >> 10) & 1)) ? 1 : 0;      // (bit 10: experiments with M = 128 for every k)
     const int n_items = n_seg * (c / PM_SLICE);
     const unsigned grid = (unsigned)(n_items < sm_count() ? n_items : sm_count());
