@@ -41,6 +41,7 @@ for tune in tunes:
              1: ("MMA issuer", ["wait raw_full", "wait conv_full", "wait tmem_free", "loop total"]),
              2: ("converter", ["wait raw_full", "wait conv_empty", "loop total", "fence.proxy.async"]),
              3: ("builder", ["wait conv_empty", "expand + tcgen05.st", "loop total", "tcgen05.wait::st"]),
+             5: ("builder (2)", ["wait transposed words", "-", "-", "-"]),
              4: ("epilogue", ["wait tile_done", "-", "loop total", "-"])}
     for r, (nm, cols) in names.items():
         per_tile = d[:, r, :].sum(0) / tiles.sum()

@@ -390,12 +390,16 @@ pool_mma_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P) 
 // TMEM map (512 columns): [0,256) two accumulator buffers of 128 channels; [256,384) two membership stages of
 // 64 points as tf32; [384,448) the same as bf16 pairs.
 constexpr int P2_LO = PM_TP * PM_SLICE * 2;          // bytes of a bf16 lo tile (16 KB)
-constexpr int P2_D = 0, P2_A32 = 256, P2_A16 = 384;  // TMEM column bases
-constexpr int P2_MAX_DYN_SMEM = PM_MAX_STAGES * PM_RAW + 2 * PM_TP * PM_SLICE * 2 + 1024;   // + ~10 KB static < 227 KB
+constexpr int P2_CS = 3;                             // membership (tensor memory) / lo-tile (shared memory) stages
+constexpr int P2_DB = 1;                             // accumulator buffers
+constexpr int P2_D = 0, P2_A32 = P2_DB * PM_SLICE, P2_A16 = P2_A32 + P2_CS * 64;   // TMEM column bases
+static_assert(P2_A16 + P2_CS * 32 <= 512, "tensor memory columns");
+constexpr int P2_MAX_DYN_SMEM = PM_MAX_STAGES * PM_RAW + P2_CS * PM_TP * PM_SLICE * 2 + 1024;   // + ~10 KB static < 227 KB
 constexpr int P2_IQ = 4;                                   // work items published ahead of their consumers
 constexpr int P2_MW = 8;                                   // tiles of membership words in flight (asynchronous copies)
-constexpr int P2_GROUP = 8;                                // tiles (of 64 points) per accumulator flush
-constexpr int P2_EPI_WARPS = 8, P2_THREADS = 32 * (10 + P2_EPI_WARPS);
+constexpr int P2_GROUP = 16;                               // tiles (of 64 points) per accumulator flush
+constexpr int P2_TW = 4;                                   // transposed-word stages between the preparation warps and the builders
+constexpr int P2_EPI_WARPS = 8, P2_THREADS = 32 * (10 + P2_EPI_WARPS + 2);   // + 2 preparation warps
 
 struct P2Item { int s, sl, n; int64_t a; };
 
@@ -446,13 +450,13 @@ __device__ __forceinline__ P2Item p2_take_item(const int4 *s_iq, const long long
 }
 
 template <int UNR>                                    // converter loads in flight per thread (shared-memory latency under load)
-__global__ void __launch_bounds__(P2_THREADS, 1)
+__global__ void __launch_bounds__(P2_THREADS, 1)   // 18 warps = 5 on one scheduler: 96 registers per thread (112 do not fit its 16 K)
 pool_mma2_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P) {
     constexpr int EPI_THREADS = P2_EPI_WARPS * 32;
     extern __shared__ __align__(1024) unsigned char pm_smem[];
     __shared__ uint64_t s_raw_full[PM_MAX_STAGES], s_raw_empty[PM_MAX_STAGES];
-    __shared__ uint64_t s_conv_full[2], s_conv_empty[2];
-    __shared__ uint64_t s_tile_done[2], s_tmem_free[2];
+    __shared__ uint64_t s_conv_full[P2_CS], s_conv_empty[P2_CS];
+    __shared__ uint64_t s_tile_done[P2_DB], s_tmem_free[P2_DB];
     __shared__ uint32_t s_tmem;
     // Work items flow through the roles WITHOUT a CTA-wide barrier (draining and refilling the TMA -> converter -> MMA ->
     // epilogue pipeline at every item cost ~7 % of the kernel): the producer thread draws the item from the global counter
@@ -462,7 +466,9 @@ pool_mma2_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P)
     __shared__ long long s_iq_a[P2_IQ];              // first row of the segment
     __shared__ uint64_t s_cnt_full[2], s_cnt_free[2];
     __shared__ int s_cnt[2][128];                    // per-mask counts of the builders' item -> epilogue (two items in flight)
-    __shared__ uint32_t s_mw[P2_MW][4][PM_TP];       // membership words of the next P2_MW tiles (builder warps)
+    __shared__ uint32_t s_mw[P2_MW][4][PM_TP];       // membership words of the next P2_MW tiles (preparation warps)
+    __shared__ uint32_t s_tw[P2_TW][4][2][32];       // transposed words [stage][word][points 0..31 / 32..63][mask row]
+    __shared__ uint64_t s_tw_full[P2_TW], s_tw_empty[P2_TW];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     unsigned char *base = pm_smem + ((1024u - (smem_u32(pm_smem) & 1023u)) & 1023u);
@@ -471,12 +477,15 @@ pool_mma2_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P)
 
     if (tid == 0) {
         for (int s = 0; s < PM_MAX_STAGES; ++s) { mbar_init(&s_raw_full[s], 1); mbar_init(&s_raw_empty[s], 1); }
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < P2_CS; ++b) {
             mbar_init(&s_conv_full[b], PM_CONV + PM_BUILD);
             mbar_init(&s_conv_empty[b], 1);
+        }
+        for (int b = 0; b < P2_DB; ++b) {
             mbar_init(&s_tile_done[b], 1);
             mbar_init(&s_tmem_free[b], EPI_THREADS);
         }
+        for (int q = 0; q < P2_TW; ++q) { mbar_init(&s_tw_full[q], 64); mbar_init(&s_tw_empty[q], PM_BUILD); }
         for (int q = 0; q < P2_IQ; ++q) { mbar_init(&s_iq_full[q], 1); mbar_init(&s_iq_free[q], P2_THREADS / 32 - 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&s_cnt_full[b], PM_BUILD); mbar_init(&s_cnt_free[b], EPI_THREADS); }
         mbar_fence_init();
@@ -544,12 +553,12 @@ pool_mma2_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P)
                     const int mrows = P.m64 ? 64 : 128;
                     const uint32_t id32 = make_idesc(mrows, PM_SLICE, 2, /*A: TMEM*/ 0, /*B N-major*/ 1);
                     const uint32_t id16 = make_idesc(mrows, PM_SLICE, 1, 0, 1);
-                    uint64_t d_hi[PM_MAX_STAGES], d_lo[2];
+                    uint64_t d_hi[PM_MAX_STAGES], d_lo[P2_CS];
 #pragma unroll
                     for (int q = 0; q < PM_MAX_STAGES; ++q)     // tf32 N-major: 32-byte-atom swizzle, 4 column blocks 8 KB apart
                         d_hi[q] = make_sw128_desc_ex(raw_base + (size_t)q * PM_RAW, PM_CB, 512, 1);
 #pragma unroll
-                    for (int q = 0; q < 2; ++q)                 // bf16 N-major: 128-byte swizzle, 2 blocks of 64 channels 8 KB apart
+                    for (int q = 0; q < P2_CS; ++q)             // bf16 N-major: 128-byte swizzle, 2 blocks of 64 channels 8 KB apart
                         d_lo[q] = make_sw128_desc_ex(lo_base + (size_t)q * P2_LO, PM_TP * 128, 1024, 2);
                     long long tw0 = 0, tw1 = 0, tw2 = 0, tall = PM_CLK();
                     for (int t = 0; t < ntile; ++t) {
@@ -567,7 +576,10 @@ pool_mma2_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P)
 #pragma unroll
                         for (int q = 1; q < PM_MAX_STAGES; ++q)
                             if (rs == q) b_hi = d_hi[q];
-                        const uint64_t b_lo = cs ? d_lo[1] : d_lo[0];
+                        uint64_t b_lo = d_lo[0];
+#pragma unroll
+                        for (int q = 1; q < P2_CS; ++q)
+                            if (cs == q) b_lo = d_lo[q];
                         const uint32_t d = tmem_base + (uint32_t)(P2_D + buf * PM_SLICE);
                         const uint32_t a32 = tmem_base + (uint32_t)(P2_A32 + cs * 64), a16 = tmem_base + (uint32_t)(P2_A16 + cs * 32);
                         for (int rep = 0; rep < ((P.dbg2 & 4) ? 4 : 1); ++rep) {   // (experiments: 4 x the MMAs per tile)
@@ -585,10 +597,10 @@ pool_mma2_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P)
                         umma_commit(&s_raw_empty[rs]);
                         umma_commit(&s_conv_empty[cs]);
                         if (++rs == P.raw_stages) { rs = 0; rph ^= 1; }
-                        if (++cs == 2) { cs = 0; cph ^= 1; }
+                        if (++cs == P2_CS) { cs = 0; cph ^= 1; }
                         if (last) {
                             umma_commit(&s_tile_done[buf]);
-                            if (++buf == 2) { buf = 0; bph ^= 1; }
+                            if (++buf == P2_DB) { buf = 0; bph ^= 1; }
                         }
                     }
                     PM_OUT(1, tw0, tw1, tw2, PM_CLK() - tall);
@@ -662,13 +674,13 @@ pool_mma2_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P)
                     PM_ACC(tw2, c0_);
                     mbar_arrive(&s_conv_full[cs]);
                     if (++rs == P.raw_stages) { rs = 0; rph ^= 1; }
-                    if (++cs == 2) { cs = 0; cph ^= 1; }
+                    if (++cs == P2_CS) { cs = 0; cph ^= 1; }
                 }
                 if (!((nf0 + nf1) + (nf2 + nf3) == 0.f) && P.status) atomicOr(P.status, XM3D_FLAG_NONFINITE);
                 if (t0 == 0) PM_OUT(2, tw0, tw1, PM_CLK() - tall, tw2);
             }
         } else if (warp < 10) {
-            int iq = 0; uint32_t iqph = 0; int ib = 0; uint32_t ibph = 0;
+            int iq = 0; uint32_t iqph = 0; int ib = 0; uint32_t ibph = 0; int ts = 0; uint32_t tph = 0;
             for (;;) {
                 const P2Item it = p2_take_item(s_iq, s_iq_a, s_iq_full, s_iq_free, iq, iqph, lane);
                 if (it.n < 0) break;
@@ -684,46 +696,33 @@ pool_mma2_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P)
                 const int wsel = P.m64 ? (lg >> 1) : lg;
                 const int tail = P.k & 31;
                 const bool word_ok = wsel < P.words && wsel * 32 < P.k;
-                // The membership words of a tile reach this thread through an asynchronous copy ring, P2_MW tiles ahead: a
-                // register prefetch "two tiles ahead" that is rotated at the end of the iteration makes the rotation wait for
-                // the load, and the whole pipeline then runs at one loaded global-memory latency (~1 400 cycles) per tile.
-                auto issue_words = [&](int t) {
-                    uint32_t *dst = &s_mw[t & (P2_MW - 1)][lg][lane];
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int pt = t * PM_TP + 32 * h + lane;
-                        const bool ok = word_ok && t < ntile && pt < n;
-                        const uint32_t *src = ok ? P.member + (size_t)(a + pt) * P.words + wsel : P.member;
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst + 32 * h)), "l"(src),
-                                     "r"(ok ? 4 : 0) : "memory");
-                    }
-                    asm volatile("cp.async.commit_group;" ::: "memory");
-                };
-#pragma unroll
-                for (int u = 0; u < P2_MW; ++u) issue_words(u);
-                const uint32_t tail_mask = (tail && wsel == (P.k >> 5)) ? (1u << tail) - 1u : 0xffffffffu;
                 int cnt = 0, cnt_b = 0;                                // (M = 64: rows t/4 and t/4 + 8 of this warp)
-                long long tw0 = 0, tw1 = 0, tw2 = 0, tall = PM_CLK();
+                long long tw0 = 0, tw1 = 0, tw2 = 0, tw3 = 0, tall = PM_CLK();
                 for (int t = 0; t < ntile; ++t) {
-                    asm volatile("cp.async.wait_group %0;" ::"n"(P2_MW - 1) : "memory");
-                    const uint32_t x0 = s_mw[t & (P2_MW - 1)][lg][lane] & tail_mask;
-                    const uint32_t x1 = s_mw[t & (P2_MW - 1)][lg][32 + lane] & tail_mask;
-                    // points 0..31 / 32..63 of the tile inside MY mask: two 32 x 32 bit transposes (5 shuffle rounds each)
-                    uint32_t m0 = warp_transpose32(x0), m1 = warp_transpose32(x1);
-                    issue_words(t + P2_MW);                           // the slot is free: its words are in m0 / m1
-                    // M = 64: the 16 mask rows of this warp go to lanes 0..15 of its lane group with the 16-lane store shape
-                    // (thread t: rows t/4 and t/4 + 8, columns 8 i + 2 (t % 4) + {0, 1}) — half the tensor-memory stores and
-                    // half the expansion work of the 32-lane shape, which would write 16 unused lanes.
-                    uint32_t ra0 = 0u, ra1 = 0u, rb0 = 0u, rb1 = 0u;
+                    // The transposed membership words (row = mask, bit = point) come from the two preparation warps through a
+                    // shared-memory ring: loading and transposing them here cost 600 of this warp's serial ~1 500 cycles per
+                    // tile, and this warp's chain (rows -> expansion -> tensor-memory stores) paces the MMAs.
+                    long long c1_ = PM_CLK();
+                    mbar_wait(&s_tw_full[ts], tph);
+                    PM_ACC(tw3, c1_);
+                    uint32_t m0 = 0u, m1 = 0u, ra0 = 0u, ra1 = 0u, rb0 = 0u, rb1 = 0u;
                     if (P.m64) {
-                        const int src = (lg & 1) * 16 + (lane >> 2);
-                        ra0 = __shfl_sync(0xffffffffu, m0, src); rb0 = __shfl_sync(0xffffffffu, m0, src + 8);
-                        ra1 = __shfl_sync(0xffffffffu, m1, src); rb1 = __shfl_sync(0xffffffffu, m1, src + 8);
+                        // M = 64: the 16 mask rows of this warp go to lanes 0..15 of its lane group with the 16-lane store
+                        // shape (thread t: rows t/4 and t/4 + 8, columns 8 i + 2 (t % 4) + {0, 1}) — half the tensor-memory
+                        // stores and expansion work of the 32-lane shape, which would write 16 unused lanes.
+                        if (word_ok) {
+                            const int row = (lg & 1) * 16 + (lane >> 2);
+                            ra0 = s_tw[ts][wsel][0][row]; rb0 = s_tw[ts][wsel][0][row + 8];
+                            ra1 = s_tw[ts][wsel][1][row]; rb1 = s_tw[ts][wsel][1][row + 8];
+                        }
                         cnt += __popc(ra0) + __popc(ra1);
                         cnt_b += __popc(rb0) + __popc(rb1);
                     } else {
+                        if (word_ok) { m0 = s_tw[ts][wsel][0][lane]; m1 = s_tw[ts][wsel][1][lane]; }
                         cnt += __popc(m0) + __popc(m1);
                     }
+                    mbar_arrive(&s_tw_empty[ts]);                     // (release: the reads above are ordered before it)
+                    if (++ts == P2_TW) { ts = 0; tph ^= 1; }
                     long long c0_ = PM_CLK();
                     mbar_wait(&s_conv_empty[cs], cph ^ 1);
                     PM_ACC(tw0, c0_);
@@ -790,17 +789,16 @@ pool_mma2_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P)
                     tc_fence_before();
                     PM_ACC(tw2, c0_);
                     mbar_arrive(&s_conv_full[cs]);
-                    if (++cs == 2) { cs = 0; cph ^= 1; }
+                    if (++cs == P2_CS) { cs = 0; cph ^= 1; }
                 }
-                asm volatile("cp.async.wait_group 0;" ::: "memory");   // the ring is reused by the next item
                 mbar_wait(&s_cnt_free[ib], ibph ^ 1);                  // the epilogue has read the counts of two items ago
                 if (!P.m64) s_cnt[ib][lg * 32 + lane] = cnt;          // exactly one thread per mask
                 else if ((lane & 3) == 0) { s_cnt[ib][lg * 16 + (lane >> 2)] = cnt; s_cnt[ib][lg * 16 + (lane >> 2) + 8] = cnt_b; }
                 mbar_arrive(&s_cnt_full[ib]);
-                if (tid == 192) PM_OUT(3, tw0, tw1, PM_CLK() - tall, tw2);
+                if (tid == 192) { PM_OUT(3, tw0, tw1, PM_CLK() - tall, tw2); PM_OUT(5, tw3, 0, 0, 0); }
                 if (++ib == 2) { ib = 0; ibph ^= 1; }
             }
-        } else {
+        } else if (warp < 10 + P2_EPI_WARPS) {
             int iq = 0; uint32_t iqph = 0; int ib = 0; uint32_t ibph = 0;
             for (;;) {
                 const P2Item it = p2_take_item(s_iq, s_iq_a, s_iq_full, s_iq_free, iq, iqph, lane);
@@ -816,7 +814,7 @@ pool_mma2_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P)
                 long long tw0 = 0, tall = PM_CLK();
                 for (int g = 0; g < (ntile + P2_GROUP - 1) / P2_GROUP; ++g) {
                     long long c0_ = PM_CLK();
-                    mbar_wait_sleep(&s_tile_done[buf], bph, 100);
+                    mbar_wait_sleep(&s_tile_done[buf], bph, 20);
                     PM_ACC(tw0, c0_);
                     tc_fence_after();
                     const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(P2_D + buf * PM_SLICE + half * 64);
@@ -834,7 +832,7 @@ pool_mma2_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P)
                     }
                     tc_fence_before();
                     mbar_arrive(&s_tmem_free[buf]);
-                    if (++buf == 2) { buf = 0; bph ^= 1; }
+                    if (++buf == P2_DB) { buf = 0; bph ^= 1; }
                 }
                 if (tid == 320) PM_OUT(4, tw0, 0, PM_CLK() - tall, 0);
                 mbar_wait(&s_cnt_full[ib], ibph);                      // the builders' counts of this item
@@ -856,6 +854,65 @@ pool_mma2_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P)
                     if (P.cnt && sl == 0 && half == 0) P.cnt[s * P.k + m] = nm;
                 }
                 if (++ib == 2) { ib = 0; ibph ^= 1; }
+            }
+        } else {
+            // ===== preparation warps: membership words -> transposed rows (row = mask, bit = point) in shared memory =====
+            // Warp w handles membership words w and w + 2.  The words of a tile arrive through an asynchronous copy ring P2_MW
+            // tiles ahead (a register prefetch that is rotated at the end of the iteration makes the rotation wait for the
+            // load: the pipeline then runs at one loaded global-memory latency per tile).
+            const int pw = warp - (10 + P2_EPI_WARPS);
+            const int tail = P.k & 31;
+            int iq = 0; uint32_t iqph = 0; int ts = 0; uint32_t tph = 0;
+            for (;;) {
+                const P2Item it = p2_take_item(s_iq, s_iq_a, s_iq_full, s_iq_free, iq, iqph, lane);
+                if (it.n < 0) break;
+                const int n = it.n; const int64_t a = it.a;
+                const int ntile = (n + PM_TP - 1) / PM_TP;
+                auto issue_words = [&](int t) {
+#pragma unroll
+                    for (int wq = 0; wq < 2; ++wq) {
+                        const int w = pw + 2 * wq;
+                        const bool word_ok = w < P.words && w * 32 < P.k;
+                        uint32_t *dst = &s_mw[t & (P2_MW - 1)][w][lane];
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int pt = t * PM_TP + 32 * h + lane;
+                            const bool ok = word_ok && t < ntile && pt < n;
+                            const uint32_t *src = ok ? P.member + (size_t)(a + pt) * P.words + w : P.member;
+                            if (word_ok)
+                                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst + 32 * h)), "l"(src),
+                                             "r"(ok ? 4 : 0) : "memory");
+                        }
+                    }
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                };
+#pragma unroll
+                for (int u = 0; u < P2_MW; ++u) issue_words(u);
+                for (int t = 0; t < ntile; ++t) {
+                    asm volatile("cp.async.wait_group %0;" ::"n"(P2_MW - 1) : "memory");
+                    uint32_t tr[2][2];
+#pragma unroll
+                    for (int wq = 0; wq < 2; ++wq) {
+                        const int w = pw + 2 * wq;
+                        const bool word_ok = w < P.words && w * 32 < P.k;
+                        const uint32_t tail_mask = (tail && w == (P.k >> 5)) ? (1u << tail) - 1u : 0xffffffffu;
+                        tr[wq][0] = tr[wq][1] = 0u;
+                        if (word_ok) {                                // two 32 x 32 bit transposes (5 shuffle rounds each)
+                            tr[wq][0] = warp_transpose32(s_mw[t & (P2_MW - 1)][w][lane] & tail_mask);
+                            tr[wq][1] = warp_transpose32(s_mw[t & (P2_MW - 1)][w][32 + lane] & tail_mask);
+                        }
+                    }
+                    issue_words(t + P2_MW);                           // the slot is free: its words are in registers
+                    mbar_wait(&s_tw_empty[ts], tph ^ 1);
+#pragma unroll
+                    for (int wq = 0; wq < 2; ++wq) {
+                        s_tw[ts][pw + 2 * wq][0][lane] = tr[wq][0];
+                        s_tw[ts][pw + 2 * wq][1][lane] = tr[wq][1];
+                    }
+                    mbar_arrive(&s_tw_full[ts]);
+                    if (++ts == P2_TW) { ts = 0; tph ^= 1; }
+                }
+                asm volatile("cp.async.wait_group 0;" ::: "memory");   // the copy ring is reused by the next item
             }
         }
     }
@@ -922,7 +979,7 @@ int launch_pool_mma(const float *feat, int c, const uint32_t *member, int words,
         }
         P.raw_stages = (t_rs >= 1 && t_rs <= PM_MAX_STAGES) ? t_rs : 4;
         P.conv_stages = 2;
-        const size_t smem2 = (size_t)P.raw_stages * PM_RAW + 2 * (size_t)P2_LO + 1024;
+        const size_t smem2 = (size_t)P.raw_stages * PM_RAW + P2_CS * (size_t)P2_LO + 1024;
         const int unr = (tune >> 12) & 3;                  // experiments: 0 = default
         if (unr == 1) pool_mma2_kernel<4><<<grid, P2_THREADS, smem2, stream>>>(map, P);
         else if (unr == 2) pool_mma2_kernel<8><<<grid, P2_THREADS, smem2, stream>>>(map, P);
