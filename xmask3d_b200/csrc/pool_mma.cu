@@ -547,19 +547,19 @@ pool_mma2_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P)
                 const int ntile = (n + PM_TP - 1) / PM_TP;
                 (void)s; (void)sl; (void)a;
                 // ===== MMA issuer: 8 tf32 MMAs (hi, 8 points each) + 4 bf16 MMAs (lo, 16 points each) per tile =====
-                if (lane == 0) {
-                    // M = 64 when all masks fit 64 rows: every MMA reads and writes the whole M x 128 float32 accumulator for
-                    // only 8 (tf32) or 16 (bf16) rank-1 updates, so its time is the accumulator traffic, not the MACs
+                // The WHOLE warp runs this loop and one elected lane issues: every operand is then warp-uniform for the compiler
+                // and lives in uniform registers.  Issued from inside `if (lane == 0)` each MMA was wrapped in an
+                // ELECT / 3 x R2UR.BROADCAST / BRA.U.ANY loop — ~55 cycles of serial issue per MMA, 650 per tile, with the
+                // tensor pipe idle in between (the pipe itself needs ~72 cycles per MMA).
+                {
+                    // M = 64 when all masks fit 64 rows (same MMA time, half the tensor work)
                     const int mrows = P.m64 ? 64 : 128;
                     const uint32_t id32 = make_idesc(mrows, PM_SLICE, 2, /*A: TMEM*/ 0, /*B N-major*/ 1);
                     const uint32_t id16 = make_idesc(mrows, PM_SLICE, 1, 0, 1);
-                    uint64_t d_hi[PM_MAX_STAGES], d_lo[P2_CS];
-#pragma unroll
-                    for (int q = 0; q < PM_MAX_STAGES; ++q)     // tf32 N-major: 32-byte-atom swizzle, 4 column blocks 8 KB apart
-                        d_hi[q] = make_sw128_desc_ex(raw_base + (size_t)q * PM_RAW, PM_CB, 512, 1);
-#pragma unroll
-                    for (int q = 0; q < P2_CS; ++q)             // bf16 N-major: 128-byte swizzle, 2 blocks of 64 channels 8 KB apart
-                        d_lo[q] = make_sw128_desc_ex(lo_base + (size_t)q * P2_LO, PM_TP * 128, 1024, 2);
+                    // tf32 N-major: 32-byte-atom swizzle, 4 column blocks 8 KB apart; bf16 N-major: 128-byte swizzle, 2 blocks of
+                    // 64 channels 8 KB apart
+                    const uint64_t d_hi0 = make_sw128_desc_ex(raw_base, PM_CB, 512, 1);
+                    const uint64_t d_lo0 = make_sw128_desc_ex(lo_base, PM_TP * 128, 1024, 2);
                     long long tw0 = 0, tw1 = 0, tw2 = 0, tall = PM_CLK();
                     for (int t = 0; t < ntile; ++t) {
                         const bool first = t % P2_GROUP == 0, last = (t % P2_GROUP == P2_GROUP - 1) || t == ntile - 1;
@@ -572,38 +572,32 @@ pool_mma2_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P)
                         if (first) mbar_wait(&s_tmem_free[buf], bph ^ 1);      // a fresh accumulator every P2_GROUP tiles
                         PM_ACC(tw2, c0_);
                         tc_fence_after();
-                        uint64_t b_hi = d_hi[0];
-#pragma unroll
-                        for (int q = 1; q < PM_MAX_STAGES; ++q)
-                            if (rs == q) b_hi = d_hi[q];
-                        uint64_t b_lo = d_lo[0];
-#pragma unroll
-                        for (int q = 1; q < P2_CS; ++q)
-                            if (cs == q) b_lo = d_lo[q];
+                        const uint64_t b_hi = d_hi0 + (uint64_t)((rs * PM_RAW) >> 4);      // (start address field: bytes >> 4)
+                        const uint64_t b_lo = d_lo0 + (uint64_t)((cs * P2_LO) >> 4);
                         const uint32_t d = tmem_base + (uint32_t)(P2_D + buf * PM_SLICE);
                         const uint32_t a32 = tmem_base + (uint32_t)(P2_A32 + cs * 64), a16 = tmem_base + (uint32_t)(P2_A16 + cs * 32);
-                        for (int rep = 0; rep < ((P.dbg2 & 4) ? 4 : 1); ++rep) {   // (experiments: 4 x the MMAs per tile)
-                        if (P.dbg != 2) {
+                        if (elect_one_sync()) {
+                            if (P.dbg != 2) {
 #pragma unroll
-                            for (int ks = 0; ks < PM_TP / 8; ++ks)
-                                umma_tf32_ts(d, a32 + ks * 8, b_hi + (uint64_t)((ks * 1024) >> 4), id32, (ks || !first) ? 1u : 0u);
-                        }
-                        if (P.dbg != 1) {
+                                for (int ks = 0; ks < PM_TP / 8; ++ks)
+                                    umma_tf32_ts(d, a32 + ks * 8, b_hi + (uint64_t)((ks * 1024) >> 4), id32, (ks || !first) ? 1u : 0u);
+                            }
+                            if (P.dbg != 1) {
 #pragma unroll
-                            for (int ks = 0; ks < PM_TP / 16; ++ks)
-                                umma_f16_ts(d, a16 + ks * 8, b_lo + (uint64_t)((ks * 2048) >> 4), id16, (P.dbg == 2 && ks == 0 && first) ? 0u : 1u);
+                                for (int ks = 0; ks < PM_TP / 16; ++ks)
+                                    umma_f16_ts(d, a16 + ks * 8, b_lo + (uint64_t)((ks * 2048) >> 4), id16,
+                                                (P.dbg == 2 && ks == 0 && first) ? 0u : 1u);
+                            }
+                            umma_commit(&s_raw_empty[rs]);
+                            umma_commit(&s_conv_empty[cs]);
+                            if (last) umma_commit(&s_tile_done[buf]);
                         }
-                        }
-                        umma_commit(&s_raw_empty[rs]);
-                        umma_commit(&s_conv_empty[cs]);
+                        __syncwarp();
                         if (++rs == P.raw_stages) { rs = 0; rph ^= 1; }
                         if (++cs == P2_CS) { cs = 0; cph ^= 1; }
-                        if (last) {
-                            umma_commit(&s_tile_done[buf]);
-                            if (++buf == P2_DB) { buf = 0; bph ^= 1; }
-                        }
+                        if (last && ++buf == P2_DB) { buf = 0; bph ^= 1; }
                     }
-                    PM_OUT(1, tw0, tw1, tw2, PM_CLK() - tall);
+                    if (lane == 0) PM_OUT(1, tw0, tw1, tw2, PM_CLK() - tall);
                 }
             }
         } else if (warp < 6) {
