@@ -1,5 +1,4 @@
 set -x
-timeout 300 python scripts/time_pool_mma.py rows 0 0x30000 0 > gpurun_out/time_pm32.log 2>&1
-timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_canaries.py -m gpu -q -x -k "pool or canar" > gpurun_out/gpu_tests32.log 2>&1
-XM3D_SO=xmask3d_b200/libxm3d_dbg.so timeout 600 python scripts/exp_pool_mma.py 0 0x30000 > gpurun_out/exp_pm32.log 2>&1
+timeout 300 python scripts/prof_pool_mma.py 0 > gpurun_out/prof36_plain.log 2>&1 || exit 1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:pool_mma2_kernel -c 1 -s 2 -f -o gpurun_out/prof_r02_pool_mma2_v2 python scripts/prof_pool_mma.py 0 > gpurun_out/prof36_ncu.log 2>&1
 echo done
