@@ -61,7 +61,7 @@ def parse(argv=None):
                    help="every rank processes a copy of scenes 0..7 (round-1 behaviour) instead of distinct, balanced scenes")
     p.add_argument("--no-overlap", action="store_true", help="run the stages back to back on one stream")
     p.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")
-    p.add_argument("--extras", default="c0,c2,c3,c4", help="comma list of extra BASELINE configs to run (none = skip)")
+    p.add_argument("--extras", default="c0,c2,ov,c3,c4", help="comma list of extra BASELINE configs to run (none = skip)")
     p.add_argument("--sweep-scenes", type=int, default=312)
     p.add_argument("--workload", default="batch", choices=["batch", "split_scene"],
                    help="batch = configs[1] (default, weak scaling); split_scene = configs[3] alone (strong scaling)")
@@ -665,6 +665,11 @@ def run_native(args, rank: int, world: int, local_rank: int):
     peak, peak_tf, peak_src = peaks()
     if "c2" in extras:
         cfgs["configs[2]"] = extra_k100(args, batch, dev, T, rank, peak, pv_job, feat_shared=feat)
+    if "ov" in extras and args.masks == "partition":
+        del masks
+        masks = None
+        torch.cuda.empty_cache()
+        cfgs["overlapping_masks"] = extra_overlap(args, batch, dev, T, rank, peak, pv_job, feat_shared=feat)
     del masks
     torch.cuda.empty_cache()
     if "c3" in extras:
@@ -780,6 +785,58 @@ def extra_k100(args, batch, dev, T, rank, peak, pv_job, feat_shared):
                        "logits contraction is under `logits`",
            "ms_per_step": ms, "value": pv_job / (ms * 1e-3), "unit": UNIT,
            "pipeline_roofline_frac": alg["total"] / (ms * 1e-3) / 1e9 / peak}
+    del pipe, masks
+    torch.cuda.empty_cache()
+    return res
+
+
+def extra_overlap(args, batch, dev, T, rank, peak, pv_job, feat_shared):
+    """The criterion path's masks (models/utils/criterion.py:83-85): raw thresholded float32 predictions that OVERLAP
+    (about 7.7 memberships per visible point) — pooled by the tensor-core kernel, every feature row read once."""
+    import ctypes
+    import torch
+    from xmask3d_b200 import _lib as L, ops
+    from xmask3d_b200.pipeline import CorrespondencePipeline, StageTimes, algorithmic_bytes
+    pipe = CorrespondencePipeline(batch, args.k, args.c, dev, vox_mode=2)
+    pipe.upload(torch.from_numpy(batch.xyz), torch.from_numpy(batch.depth_mm.view(np.int16)))
+    pr = pipe.project()
+    n_vis = pr.n_vis.cpu().numpy().astype(np.int64)
+    total_vis = int(n_vis.sum())
+    pipe.set_cap(total_vis)
+    masks, mode, mask_bytes = make_masks(args.k, "overlap", batch.n_views, dev, 7171 + rank)
+    member0, _ = ops.gather_masks(masks, pr.rowcol, pr.vis_off, mode=mode, cap=total_vis)
+    total_pairs = int(ops._popcount32(member0[:total_vis]).sum().item())
+    del member0
+    pipe.pairs_per_point = total_pairs / max(total_vis, 1)
+    pipe._size_pool_ws()
+    feat = feat_shared
+    for _ in range(3):
+        out = pipe.run(masks, feat, mode)
+    assert int(out["proj"].status.item()) == 0 and int(out["vox"].status.item()) == 0 and int(out["pool_status"].item()) == 0
+    ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev_a.record(); ev_b.record()
+    torch.cuda.synchronize()
+    L.lib().xm3d_set_pool_events(ctypes.c_void_p(ev_a.cuda_event), ctypes.c_void_p(ev_b.cuda_event))
+    kms = []
+    for _ in range(5):
+        pipe.run(masks, feat, mode, times=StageTimes())
+        torch.cuda.synchronize()
+        kms.append(ev_a.elapsed_time(ev_b))
+    L.lib().xm3d_set_pool_events(None, None)
+    pipe.capture(masks, feat, mode)
+    n = max(5, min(args.steps, 20))
+    ms = T.time(lambda i: pipe.replay(), n) / n
+    m_vox = out["vox"].m.cpu().numpy().astype(np.int64)
+    n_pts_view = np.diff(batch.scene_off)[batch.view_scene]
+    alg = algorithmic_bytes(n_pts_view, n_vis, m_vox, args.k, args.c, mask_bytes)
+    feat_bytes = 4 * args.c * total_vis
+    k_ms = float(np.mean(kms))
+    res = {"workload": f"the headline batch with OVERLAPPING float32 mask logits (sigmoid >= 0.5; {total_pairs / max(total_vis, 1):.1f} "
+                       "memberships per visible point, the criterion path): pooling on the tensor cores (pool_mma2_kernel)",
+           "ms_per_step": ms, "value": pv_job / (ms * 1e-3), "unit": UNIT,
+           "pipeline_roofline_frac": alg["total"] / (ms * 1e-3) / 1e9 / peak,
+           "pool_kernel_ms": k_ms, "pool_kernel_frac_of_hbm_peak": feat_bytes / (k_ms * 1e-3) / 1e9 / peak,
+           "memberships": total_pairs}
     del pipe, masks
     torch.cuda.empty_cache()
     return res
