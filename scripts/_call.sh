@@ -1,3 +1,3 @@
 set -x
-timeout 900 python bench.py > gpurun_out/bench37.json 2> gpurun_out/bench37.err; echo "rc=$?" >> gpurun_out/bench37.err
+timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 > gpurun_out/bench38_n2.json 2> gpurun_out/bench38_n2.err; echo "rc=$?" >> gpurun_out/bench38_n2.err
 echo done
