@@ -580,9 +580,40 @@ def run_native(args, rank: int, world: int, local_rank: int):
         ost["status"][1:2].copy_(o["vox"].status, non_blocking=True)
         ost["status"][2:3].copy_(o["pool_status"], non_blocking=True)
 
+    # One CUDA graph PER SLOT: it reads the slot's input buffers (the copy-in stream writes them) and leaves every output,
+    # the int16-packed maps included, in the slot's own tensors (the copy-out stream reads them) — no staging copies on the
+    # compute stream.  Without graphs (--no-graph) the step runs eagerly and stages through out_st.
+    slot_graphs = None
+    if use_graph:
+        slot_graphs = []
+        keep_xyz, keep_depth = pipe.xyz, pipe.depth
+        for b in range(NSLOT):
+            xyz_st[b].copy_(keep_xyz)
+            dep_st[b].copy_(keep_depth)
+            pipe.xyz, pipe.depth = xyz_st[b], dep_st[b]
+            torch.cuda.synchronize()
+            g_b = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_b):
+                o = pipe.run(masks, feat, mode)
+                st = torch.zeros(4, dtype=torch.int32, device=dev)
+                r16 = ops.pack_i16(o["proj"].rowcol[:total_vis], o["proj"].vis_off[-1:], status=st[3:])
+                v16 = ops.pack_i16(o["vox"].voxel_xyz[:m_bound], o["vox"].uniq_off[-1:], status=st[3:])
+                st[0:1].copy_(o["proj"].status)
+                st[1:2].copy_(o["vox"].status)
+                st[2:3].copy_(o["pool_status"])
+            slot_graphs.append((g_b, {"rowcol16": r16, "voxel16": v16, "inverse": o["vox"].inverse[:total_vis],
+                                      "first": o["vox"].first[:m_bound], "mean": o["mean"], "cnt": o["cnt"],
+                                      "vis_off": o["proj"].vis_off, "uniq_off": o["vox"].uniq_off, "status": st}))
+        pipe.xyz, pipe.depth = keep_xyz, keep_depth
+        for b in range(NSLOT):
+            for k2, (sh, dt) in shapes.items():
+                t_ = slot_graphs[b][1][k2]
+                assert tuple(t_.shape) == tuple(sh) and t_.dtype == dt, (k2, t_.shape, t_.dtype)
+
     def e2e_pipelined(i, keys, compute=True, copy_in=True):
-        """Step i of the pipelined loop: copy-in stream -> staging slot -> compute stream (graph replay + packing)
-        -> output staging slot -> copy-out stream -> pinned host; the host waits for the oldest step in flight."""
+        """Step i of the pipelined loop: copy-in stream -> the slot's input buffers -> compute stream (the slot's graph:
+        the whole step + int16 packing) -> the slot's outputs -> copy-out stream -> pinned host; the host waits for the
+        oldest step in flight."""
         b = i % NSLOT
         if copy_in:
             with torch.cuda.stream(s_in):
@@ -591,18 +622,26 @@ def run_native(args, rank: int, world: int, local_rank: int):
                 dep_st[b].copy_(depth_h, non_blocking=True)
                 ev["in_ready"][b].record(s_in)
             comp.wait_event(ev["in_ready"][b])
-        if compute:
-            pipe.xyz.copy_(xyz_st[b], non_blocking=True)
-            pipe.depth.copy_(dep_st[b], non_blocking=True)
-        ev["consumed"][b].record(comp)
-        comp.wait_event(ev["out_free"][b])
-        if compute:
-            stage_outputs(do_step(), out_st[b], keys)
+        src = out_st[b]
+        if slot_graphs is not None:
+            src = slot_graphs[b][1]
+            comp.wait_event(ev["out_free"][b])
+            if compute:
+                slot_graphs[b][0].replay()
+            ev["consumed"][b].record(comp)
+        else:
+            if compute:
+                pipe.xyz.copy_(xyz_st[b], non_blocking=True)
+                pipe.depth.copy_(dep_st[b], non_blocking=True)
+            ev["consumed"][b].record(comp)
+            comp.wait_event(ev["out_free"][b])
+            if compute:
+                stage_outputs(do_step(), out_st[b], keys)
         ev["out_ready"][b].record(comp)
         with torch.cuda.stream(s_out):
             s_out.wait_event(ev["out_ready"][b])
             for k2 in keys:
-                res_h[b][k2].copy_(out_st[b][k2], non_blocking=True)
+                res_h[b][k2].copy_(src[k2], non_blocking=True)
             ev["out_free"][b].record(s_out)
             ev["done"][b].record(s_out)
         if i >= NSLOT - 1:
@@ -643,7 +682,8 @@ def run_native(args, rank: int, world: int, local_rank: int):
     gbs = lambda nbytes, ms_: world * nbytes / (ms_ * 1e-3) / 1e9              # noqa: E731
     e2e = {"value": rate(e2e_ms), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_full,
            "ms_per_step": e2e_ms, "unpipelined_value": rate(serial_ms), "frac_of_pcie_ceiling": ceil_ms / e2e_ms,
-           "note": f"{NSLOT}-slot pipeline: copy-in / compute / copy-out streams overlap across steps.  host->device per step "
+           "note": f"{NSLOT}-slot pipeline: copy-in / compute / copy-out streams overlap across steps, one CUDA graph per slot "
+                   "(it reads the slot's input buffers and writes the slot's outputs).  host->device per step "
                    "and rank: scene xyz, depth images, view records (the loader's numpy inputs); device->host: x/y labels "
                    "(int16), inds_reconstruct (int32), first-occurrence indices (int32) and voxel coordinates (int16) of the "
                    "M voxels, offsets, pooled means (float32) and counts.  Per-point features and 2D masks are consumed on "
