@@ -1,3 +1,3 @@
 set -x
-timeout 900 python bench.py --extras none > gpurun_out/bench39.json 2> gpurun_out/bench39.err; echo "rc=$?" >> gpurun_out/bench39.err
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "many_small" > gpurun_out/gpu_tests40.log 2>&1
 echo done

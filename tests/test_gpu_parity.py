@@ -582,6 +582,34 @@ def test_pool_paths_vs_oracle(cport, dev, path, ns, k, c, dens):
     assert torch.equal(s2, s_sum) and torch.equal(c2, cnt) and torch.equal(m2, mean)
 
 
+@pytest.mark.parametrize("n_seg,k,c,max_n", [(2000, 50, 256, 300), (5000, 128, 128, 150), (300, 64, 1024, 2000)])
+def test_pool_mma_many_small_segments(dev, n_seg, k, c, max_n):
+    """Work-item ring of the tensor-core kernel under stress: thousands of segments of 0 .. max_n points (most items
+    shorter than a few 64-point tiles, many empty, more segments than the size-ordered hand-out covers in the second
+    case), K = 128 with all four membership words, eight 128-channel slices — against the pair-list kernel (itself
+    pinned to the float64 oracle above): counts exact, sums / means <= 1e-5 vector-wise, deterministic."""
+    from xmask3d_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(n_seg + k)
+    n = torch.randint(0, max_n + 1, (n_seg,), generator=g)
+    n[torch.rand(n_seg, generator=g) < 0.1] = 0
+    off = torch.cat([torch.zeros(1, dtype=torch.int64), n.cumsum(0)]).to(dev)
+    total = int(off[-1])
+    f = torch.randn(total, c, generator=g).to(dev)
+    words = (k + 31) // 32
+    mem = torch.randint(-2 ** 31, 2 ** 31 - 1, (total, words), generator=g, dtype=torch.int64).to(torch.int32)
+    mem &= torch.randint(-2 ** 31, 2 ** 31 - 1, (total, words), generator=g, dtype=torch.int64).to(torch.int32)   # density 1/4
+    mem = mem.to(dev)
+    cap_pairs = total * k
+    a_sum, a_cnt, a_mean = ops.pool(f, off, k, member=mem, cap_pairs=cap_pairs, path="mma")
+    b_sum, b_cnt, b_mean = ops.pool(f, off, k, member=mem, cap_pairs=cap_pairs, path="pair_lists")
+    assert torch.equal(a_cnt, b_cnt)
+    for x, y in ((a_sum, b_sum), (a_mean, b_mean)):
+        err = (x - y).abs().amax(-1) / y.abs().amax(-1).clamp_min(1e-30)
+        assert float(err.max()) < 1e-5
+    a2, c2, m2 = ops.pool(f, off, k, member=mem, cap_pairs=cap_pairs, path="mma")
+    assert torch.equal(a2, a_sum) and torch.equal(c2, a_cnt) and torch.equal(m2, a_mean)
+
+
 def test_pool_path_selection(dev):
     """XM3D_POOL_AUTO: overlapping memberships (cap_pairs > cap + 1) go to the tensor-core kernel when it is eligible;
     forcing a path that is not eligible fails loudly (no silent fallback)."""
