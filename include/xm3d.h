@@ -203,7 +203,8 @@ XM3D_API int xm3d_pixel_bits_batch(const void *masks, int32_t mask_kind, int32_t
  *   path      XM3D_POOL_AUTO picks the kernel: partition masks / labels -> sorted pair lists + register
  *             accumulation (every row read once, HBM peak); cap_pairs > cap + 1 tells the library that masks may
  *             overlap -> every row is still read exactly once by the TENSOR-CORE kernel (tcgen05 tf32, member bits
- *             as a 0/1 operand; needs member words, no row_index, c % 128 == 0, k <= 128; a NaN / Inf feature would leak
+ *             as a 0/1 operand; needs member words, no row_index, c % 128 == 0, k <= 128, 16-byte aligned sum / mean; a NaN / Inf
+ *             feature would leak
  *             into the other masks of its 64-point tile (0 x Inf), so the kernel raises XM3D_FLAG_NONFINITE when it
  *             meets one and the caller pools that batch again with XM3D_POOL_ROWS), else by
  *             the point-major CUDA-core kernel (c % 128 == 0, k <= 96), else by the pair lists (one row read per

@@ -6,25 +6,27 @@
 //
 //     sum[k, c] = sum_p member[k, p] * F[p, c]          member in {0, 1},
 //
-// and run here as tcgen05.mma kind::tf32 with the accumulator in tensor memory:
-//   D[M = 128 channels, N = masks (64 / 128)] += A[128 channels, 8 points] * B[8 points, N masks]
-//   A = the feature tile exactly as it lies in HBM (row = point, 128 bytes = 32 channels): an MN-MAJOR operand,
-//       brought in by TMA with the 128-byte swizzle of 32-byte atoms — the one layout tcgen05 accepts for MN-major
-//       32-bit operands (four 32-channel column blocks x 64 points = 32 KB per tile);
-//       the tensor core ignores the 13 low mantissa bits of a tf32 operand, so the raw tile IS its hi part;
-//       converter warps write lo = x - hi as a second tile (elementwise, same swizzled layout) -> two MMAs per
-//       k-step reproduce the float32 products to 2^-22 relative;
-//   B = the membership bits of the tile's 64 points expanded to 0.0f / 1.0f (exact in tf32), K-major, built by
-//       four builder warps straight into the swizzled layout.
-// Every 64-point tile starts a FRESH accumulator (two TMEM buffers alternate); the epilogue warps add the tile's
-// result to float32 register accumulators with round-to-nearest adds, so no long accumulation chain runs inside
-// the tensor core (whose fp32 accumulation truncates) and the result is deterministic.
-// A work item is (segment, 128-channel slice), handed to one persistent CTA per SM through an atomic counter;
-// every feature row is read from HBM exactly once, independent of the number of memberships.
+// and run here as tcgen05.mma with the accumulator in tensor memory:
+//   D[M = masks (64 / 128), N = 128 channels] += A[masks, K points] * B[K points, 128 channels]
+//   B = the feature tile exactly as it lies in HBM (row = point, 128 bytes = 32 channels): an N-MAJOR operand, brought in
+//       by TMA with the 128-byte swizzle of 32-byte atoms — the one layout tcgen05 accepts for N-major 32-bit operands
+//       (four 32-channel column blocks x 64 points = 32 KB per tile).  The tensor core ignores the 13 low mantissa bits of
+//       a tf32 operand, so the raw tile IS its hi part (kind::tf32, 8 points per MMA); converter warps write
+//       lo = x - hi as a bf16 N-major tile (kind::f16, 16 points per MMA; its error 2^-19 |x| is far inside the 1e-5 bar).
+//   A = the membership bits of the tile's 64 points as 0.0f / 1.0f (tf32) and bf16 pairs IN TENSOR MEMORY (tcgen05.mma
+//       with A from TMEM): no shared-memory write and no operand read for the 0/1 matrix.
+// The accumulator is flushed every P2_GROUP tiles into float32 registers of the epilogue warps with round-to-nearest
+// adds: a whole segment accumulated inside the tensor core loses precision (its fp32 accumulation truncates; measured
+// 1.1e-4 at 70 k points), and the result stays deterministic.
+// A work item is (segment, 128-channel slice), handed out by DESCENDING segment size through an atomic counter to one
+// persistent CTA per SM; every feature row is read from HBM exactly once, independent of the number of memberships.
+// A NaN / Inf feature would reach, multiplied by a 0 membership, masks of its tile it does not belong to: the converters
+// detect it (XM3D_FLAG_NONFINITE) and the caller pools that batch with the CUDA-core kernel.
 //
-// Warp roles: 0 TMA producer | 1 TMEM allocator + MMA issuer | 2-5 converters | 6-9 builders | 10.. epilogue.
-// Restriction (documented in include/xm3d.h): features must be finite — a NaN / Inf row would reach, multiplied by
-// 0, the masks of its tile it does not belong to.
+// Warp roles (640 threads): 0 TMA producer + work-item ring | 1 MMA issue | 2-5 converters | 6-9 builders (one per TMEM
+// lane group) | 10-17 epilogue | 18-19 preparation (membership words -> transposed rows in shared memory).
+// History, measurements and what was rejected: DESIGN.md section 4.4.  (The first version — membership operand as a K-major
+// B tile in shared memory, 208 KB of shared-memory traffic per 32 KB tile, 2.08 ms — was removed in round 2.)
 #include <cuda.h>
 #include <string.h>
 #include <type_traits>
@@ -77,318 +79,25 @@ pool_order_kernel(const int64_t *__restrict__ seg_off, int n_seg, int *__restric
 // Instrumented build (-DXM3D_PM_TIMING, scripts/exp_pool_mma.py): per-role wait / work cycles of every CTA
 #ifdef XM3D_PM_TIMING
 __device__ long long *g_pm_dbg = nullptr;
+// experiment switches (results are then wrong, the timing is what is measured): dbg 1 / 2 = skip the lo / hi MMAs;
+// dbg2 bit 0 = no TMA loads, bit 1 = idle converters
+#define PM_DBG(P) ((P).dbg)
+#define PM_DBG2(P) ((P).dbg2)
 #define PM_CLK() clock64()
 #define PM_ACC(var, t0) do { var += clock64() - (t0); } while (0)
 #define PM_OUT(role, a, b, c, d) do { if (g_pm_dbg) { long long *o_ = g_pm_dbg + ((size_t)blockIdx.x * 8 + (role)) * 4; \
     o_[0] += (a); o_[1] += (b); o_[2] += (c); o_[3] += (d); } } while (0)
 #else
+#define PM_DBG(P) 0
+#define PM_DBG2(P) 0
 #define PM_CLK() 0ll
 #define PM_ACC(var, t0) do { (void)(t0); } while (0)
 #define PM_OUT(role, a, b, c, d) do { } while (0)
 #endif
 
-template <int N>
-__global__ void __launch_bounds__(32 * (10 + N / 16), 1)
-pool_mma_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P) {
-    constexpr int EPI_WARPS = N / 16;                // 64 accumulator columns per epilogue warp
-    constexpr int EPI_THREADS = EPI_WARPS * 32;
-    constexpr int THREADS = 32 * (10 + EPI_WARPS);
-    constexpr int B_BYTES = N * PM_TP * 4;           // [2 k-blocks of 32 points][N rows][128 B]
-    constexpr int WPT = N / 64;                      // membership words per builder thread
-    extern __shared__ __align__(1024) unsigned char pm_smem[];
-    __shared__ uint64_t s_raw_full[PM_MAX_STAGES], s_raw_empty[PM_MAX_STAGES];
-    __shared__ uint64_t s_conv_full[PM_MAX_STAGES], s_conv_empty[PM_MAX_STAGES];
-    __shared__ uint64_t s_tile_done[2], s_tmem_free[2];
-    __shared__ uint32_t s_tmem;
-    __shared__ int s_item;
-    __shared__ int s_cnt[N];
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    unsigned char *base = pm_smem + ((1024u - (smem_u32(pm_smem) & 1023u)) & 1023u);
-    unsigned char *raw_base = base;
-    unsigned char *lo_base = raw_base + (size_t)P.raw_stages * PM_RAW;
-    unsigned char *b_base = lo_base + (size_t)P.conv_stages * PM_RAW;
-
-    if (tid == 0) {
-        for (int s = 0; s < PM_MAX_STAGES; ++s) {
-            mbar_init(&s_raw_full[s], 1);
-            mbar_init(&s_raw_empty[s], 1);
-            mbar_init(&s_conv_full[s], PM_CONV + PM_BUILD);
-            mbar_init(&s_conv_empty[s], 1);
-        }
-        for (int b = 0; b < 2; ++b) { mbar_init(&s_tile_done[b], 1); mbar_init(&s_tmem_free[b], EPI_THREADS); }
-        mbar_fence_init();
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map));
-    }
-    if (warp == 1) {
-        __syncwarp();
-        tmem_alloc(&s_tmem, 2 * N);                 // two accumulator buffers of N columns (128 or 256: powers of two)
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = s_tmem;
-
-    const int nsl = P.c / PM_SLICE;
-    const int n_items = P.n_seg * nsl;
-    const int64_t total_rows = P.seg_off[P.n_seg];
-    const bool over = total_rows > P.cap;
-
-    // ring positions persist across work items (the mbarrier phases keep running)
-    int rs = 0, cs = 0, buf = 0;
-    uint32_t rph = 0, cph = 0, bph = 0;             // phases of the raw ring, the lo / B ring, the TMEM buffers
-    if (tid < N) s_cnt[tid] = 0;
-    __syncthreads();
-
-    for (;;) {
-        if (tid == 0) s_item = atomicAdd(P.work, 1);
-        __syncthreads();
-        const int item = s_item;
-        if (item >= n_items) break;
-        const int s = P.order ? P.order[item / nsl] : item / nsl, sl = item % nsl;
-        const int64_t a = P.seg_off[s];
-        const int n = over ? 0 : (int)(P.seg_off[s + 1] - a);
-        const int ntile = (n + PM_TP - 1) / PM_TP;
-
-        if (warp == 0) {
-            // ===== TMA producer: four 32-channel column blocks of 64 points per tile =====
-            if (lane == 0) {
-                long long tw0 = 0, tall = PM_CLK();
-                for (int t = 0; t < ntile; ++t) {
-                    long long c0_ = PM_CLK();
-                    mbar_wait_parked(&s_raw_empty[rs], rph ^ 1);
-                    PM_ACC(tw0, c0_);
-                    unsigned char *dst = raw_base + (size_t)rs * PM_RAW;
-                    mbar_expect_tx(&s_raw_full[rs], PM_RAW);
-                    const int y = (int)(a + (int64_t)t * PM_TP);
-#pragma unroll
-                    for (int cb = 0; cb < 4; ++cb)
-                        tma_load_2d(dst + cb * PM_CB, &map, sl * PM_SLICE + cb * 32, y, &s_raw_full[rs]);
-                    if (++rs == P.raw_stages) { rs = 0; rph ^= 1; }
-                }
-                PM_OUT(0, tw0, 0, PM_CLK() - tall, ntile);
-            }
-        } else if (warp == 1) {
-            // ===== MMA issuer =====
-            if (lane == 0) {
-                const uint32_t idesc = make_idesc(PM_SLICE, N, 2, /*A MN-major*/ 1, /*B K-major*/ 0);
-                // descriptors of every stage once (a single thread issues the MMAs: per k-step only the start-address
-                // field moves).  A: two 512-byte atoms of 4 swizzled rows per k-step and column block, blocks 8 KB
-                // apart; B: [N rows][32 points] per k-block, 32 bytes per k-step inside the swizzle row.
-                uint64_t d_hi[PM_MAX_STAGES], d_lo[PM_MAX_STAGES], d_b[PM_MAX_STAGES];
-#pragma unroll
-                for (int q = 0; q < PM_MAX_STAGES; ++q) {
-                    d_hi[q] = make_sw128_desc_ex(raw_base + (size_t)q * PM_RAW, PM_CB, 512, 1);
-                    d_lo[q] = make_sw128_desc_ex(lo_base + (size_t)q * PM_RAW, PM_CB, 512, 1);
-                    d_b[q] = make_sw128_desc_ex(b_base + (size_t)q * B_BYTES, 0, 1024);
-                }
-                long long tw0 = 0, tw1 = 0, tw2 = 0, tall = PM_CLK();
-                for (int t = 0; t < ntile; ++t) {
-                    long long c0_ = PM_CLK();
-                    mbar_wait_parked(&s_raw_full[rs], rph);
-                    PM_ACC(tw0, c0_); c0_ = PM_CLK();
-                    mbar_wait_parked(&s_conv_full[cs], cph);
-                    PM_ACC(tw1, c0_); c0_ = PM_CLK();
-                    mbar_wait_parked(&s_tmem_free[buf], bph ^ 1);
-                    PM_ACC(tw2, c0_);
-                    tc_fence_after();
-                    uint64_t a_hi = d_hi[0], a_lo = d_lo[0], bd = d_b[0];
-#pragma unroll
-                    for (int q = 1; q < PM_MAX_STAGES; ++q) {
-                        if (rs == q) a_hi = d_hi[q];
-                        if (cs == q) { a_lo = d_lo[q]; bd = d_b[q]; }
-                    }
-                    const uint32_t d = tmem_base + (uint32_t)(buf * N);
-#pragma unroll
-                    for (int ks = 0; ks < PM_TP / 8; ++ks) {
-                        const uint64_t ka = (uint64_t)((ks * 1024) >> 4);
-                        const uint64_t kb2 = (uint64_t)(((ks >> 2) * (N * 128) + (ks & 3) * 32) >> 4);
-                        umma_tf32(d, a_hi + ka, bd + kb2, idesc, ks ? 1u : 0u);
-                        umma_tf32(d, a_lo + ka, bd + kb2, idesc, 1u);
-                    }
-                    umma_commit(&s_raw_empty[rs]);
-                    umma_commit(&s_conv_empty[cs]);
-                    umma_commit(&s_tile_done[buf]);
-                    if (++rs == P.raw_stages) { rs = 0; rph ^= 1; }
-                    if (++cs == P.conv_stages) { cs = 0; cph ^= 1; }
-                    if (++buf == 2) { buf = 0; bph ^= 1; }
-                }
-                PM_OUT(1, tw0, tw1, tw2, PM_CLK() - tall);
-            }
-        } else if (warp < 6) {
-            // ===== converters: lo = x - hi (hi = the raw tile as the tensor core reads it) =====
-            const int t0 = tid - 64;
-            long long tw0 = 0, tw1 = 0, tall = PM_CLK();
-            float nf0 = 0.f, nf1 = 0.f, nf2 = 0.f, nf3 = 0.f;      // NaN / Inf detector (see version 2)
-            for (int t = 0; t < ntile; ++t) {
-                long long c0_ = PM_CLK();
-                mbar_wait_parked(&s_raw_full[rs], rph);
-                PM_ACC(tw0, c0_); c0_ = PM_CLK();
-                mbar_wait_parked(&s_conv_empty[cs], cph ^ 1);
-                PM_ACC(tw1, c0_);
-                uint4 *raw = reinterpret_cast<uint4 *>(raw_base + (size_t)rs * PM_RAW);
-                uint4 *lo = reinterpret_cast<uint4 *>(lo_base + (size_t)cs * PM_RAW);
-                const int rows_valid = min(PM_TP, n - t * PM_TP);
-#pragma unroll 4
-                for (int j = 0; j < PM_RAW / 16 / PM_CONV; ++j) {
-                    const int q = t0 + PM_CONV * j;                 // 16-byte chunk: [column block][row][8 chunks]
-                    const int row = (q >> 3) & (PM_TP - 1);
-                    if (row < rows_valid) {
-                        const uint4 v = raw[q];
-                        uint4 l;
-                        l.x = __float_as_uint(__fsub_rn(__uint_as_float(v.x), __uint_as_float(v.x & 0xffffe000u))) & 0xffffe000u;
-                        l.y = __float_as_uint(__fsub_rn(__uint_as_float(v.y), __uint_as_float(v.y & 0xffffe000u))) & 0xffffe000u;
-                        l.z = __float_as_uint(__fsub_rn(__uint_as_float(v.z), __uint_as_float(v.z & 0xffffe000u))) & 0xffffe000u;
-                        l.w = __float_as_uint(__fsub_rn(__uint_as_float(v.w), __uint_as_float(v.w & 0xffffe000u))) & 0xffffe000u;
-                        lo[q] = l;
-                        nf0 = __fmaf_rn(__uint_as_float(l.x), 0.f, nf0); nf1 = __fmaf_rn(__uint_as_float(l.y), 0.f, nf1);
-                        nf2 = __fmaf_rn(__uint_as_float(l.z), 0.f, nf2); nf3 = __fmaf_rn(__uint_as_float(l.w), 0.f, nf3);
-                    } else {
-                        // rows past the segment belong to the next one (or lie past the tensor): never let them in
-                        raw[q] = make_uint4(0u, 0u, 0u, 0u);
-                        lo[q] = make_uint4(0u, 0u, 0u, 0u);
-                    }
-                }
-                fence_proxy_async();
-                mbar_arrive(&s_conv_full[cs]);
-                if (++rs == P.raw_stages) { rs = 0; rph ^= 1; }
-                if (++cs == P.conv_stages) { cs = 0; cph ^= 1; }
-            }
-            if (!((nf0 + nf1) + (nf2 + nf3) == 0.f) && P.status) atomicOr(P.status, XM3D_FLAG_NONFINITE);
-            if (t0 == 0) PM_OUT(2, tw0, tw1, PM_CLK() - tall, 0);
-        } else if (warp < 10) {
-            // ===== builders: membership bits of the tile's points -> 0.0f / 1.0f, K-major swizzled =====
-            const int t0 = tid - 192;
-            const int p = t0 & (PM_TP - 1), h = t0 >> 6;          // point of the tile, word group of this thread
-            const int kb = p >> 5, kk = p & 31;
-            const int tail = P.k & 31;
-            int cntreg[WPT];
-#pragma unroll
-            for (int j = 0; j < WPT; ++j) cntreg[j] = 0;
-            // membership words are fetched two tiles ahead: a tile's budget (~1400 cycles at the HBM rate) is shorter
-            // than one loaded global-memory latency
-            auto load_words = [&](int t, uint32_t (&w)[WPT]) {
-                const int pt = t * PM_TP + p;
-#pragma unroll
-                for (int j = 0; j < WPT; ++j) {
-                    const int wi = h * WPT + j;
-                    uint32_t x = 0u;
-                    if (pt < n && wi < P.words) {
-                        x = __ldg(P.member + (size_t)(a + pt) * P.words + wi);
-                        if (wi * 32 >= P.k) x = 0u;
-                        else if (tail && wi == (P.k >> 5)) x &= (1u << tail) - 1u;
-                    }
-                    w[j] = x;
-                }
-            };
-            uint32_t w[WPT], w1[WPT], w2[WPT];
-            long long tw0 = 0, tall = PM_CLK();
-            load_words(0, w);
-            load_words(1, w1);
-            for (int t = 0; t < ntile; ++t) {
-                load_words(t + 2, w2);
-                long long c0_ = PM_CLK();
-                mbar_wait_parked(&s_conv_empty[cs], cph ^ 1);
-                PM_ACC(tw0, c0_);
-                unsigned char *bt = b_base + (size_t)cs * B_BYTES + kb * (N * 128) + ((kk & 3) << 2);
-#pragma unroll
-                for (int j = 0; j < WPT; ++j) {
-#pragma unroll
-                    for (int b = 0; b < 32; ++b) {
-                        const int m = (h * WPT + j) * 32 + b;
-                        const uint32_t val = ((w[j] >> b) & 1u) ? 0x3f800000u : 0u;
-                        *reinterpret_cast<uint32_t *>(bt + m * 128 + ((((kk >> 2) ^ (m & 7))) << 4)) = val;
-                        const uint32_t bal = __ballot_sync(0xffffffffu, (w[j] >> b) & 1u);
-                        if (lane == b) cntreg[j] += __popc(bal);
-                    }
-                }
-                fence_proxy_async();
-                mbar_arrive(&s_conv_full[cs]);
-                if (++cs == P.conv_stages) { cs = 0; cph ^= 1; }
-#pragma unroll
-                for (int j = 0; j < WPT; ++j) { w[j] = w1[j]; w1[j] = w2[j]; }
-            }
-#pragma unroll
-            for (int j = 0; j < WPT; ++j) {
-                if (cntreg[j]) atomicAdd(&s_cnt[(h * WPT + j) * 32 + lane], cntreg[j]);     // integer: order independent
-            }
-            if (t0 == 0) PM_OUT(3, tw0, 0, PM_CLK() - tall, 0);
-            asm volatile("bar.sync 1, %0;" ::"n"(PM_BUILD + EPI_THREADS) : "memory");        // counts -> epilogue warps
-        } else {
-            // ===== epilogue: tile results out of TMEM, added in float32 registers =====
-            const int e = warp - 10;
-            const int lg = warp & 3;                              // TMEM lane group this warp may read
-            const int half = e >> 2;                              // which 64 accumulator columns
-            float acc[64];
-#pragma unroll
-            for (int j = 0; j < 64; ++j) acc[j] = 0.f;
-            long long tw0 = 0, tall = PM_CLK();
-            for (int t = 0; t < ntile; ++t) {
-                long long c0_ = PM_CLK();
-                mbar_wait_parked(&s_tile_done[buf], bph);
-                PM_ACC(tw0, c0_);
-                tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * N + half * 64);
-#pragma unroll
-                for (int c0 = 0; c0 < 64; c0 += 32) {
-                    uint32_t v0[16], v1[16];
-                    tmem_ld16_nowait(taddr + c0, v0);
-                    tmem_ld16_nowait(taddr + c0 + 16, v1);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        acc[c0 + j] = __fadd_rn(acc[c0 + j], __uint_as_float(v0[j]));
-                        acc[c0 + 16 + j] = __fadd_rn(acc[c0 + 16 + j], __uint_as_float(v1[j]));
-                    }
-                }
-                tc_fence_before();
-                mbar_arrive(&s_tmem_free[buf]);
-                if (++buf == 2) { buf = 0; bph ^= 1; }
-            }
-            if (tid == 320) PM_OUT(4, tw0, 0, PM_CLK() - tall, 0);
-            asm volatile("bar.sync 1, %0;" ::"n"(PM_BUILD + EPI_THREADS) : "memory");        // the builders' counts
-            const int ch = sl * PM_SLICE + lg * 32 + lane;
-#pragma unroll
-            for (int j = 0; j < 64; ++j) {
-                const int m = half * 64 + j;
-                if (m < P.k) {
-                    const size_t o = ((size_t)s * P.k + m) * P.c + ch;
-                    const int nm = s_cnt[m];
-                    P.sum[o] = acc[j];
-                    if (P.mean) P.mean[o] = nm > 0 ? __fdiv_rn(acc[j], (float)nm) : 0.f;
-                    if (P.cnt && sl == 0 && lg == 0 && lane == 0) P.cnt[s * P.k + m] = nm;
-                }
-            }
-        }
-        __syncthreads();                                          // item done: outputs written, s_cnt consumed
-        if (tid < N) s_cnt[tid] = 0;                              // (the next item's builders start after the sync above)
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        __syncwarp();
-        tmem_dealloc(tmem_base, 2 * N);
-    }
-    (void)THREADS;
-}
-
-
-// =====================================================================================================================
-// Version 2 — the membership operand lives in TENSOR MEMORY and the lo tile is bf16.
-//
-// ncu / clock64 on version 1: the kernel is bound by shared-memory bandwidth (208 KB of shared-memory traffic per
-// 32 KB feature tile: TMA write, converter read + lo write, builder write, three operand reads of the MMAs), not by
-// HBM or the tensor pipe.  Here the roles of the operands are swapped,
-//     D[M = 128 masks, N = 128 channels] += A[128 masks, K points] * B[K points, 128 channels],
-// so that the 0/1 membership matrix is the A operand and can be read from tensor memory (tcgen05.mma with A in TMEM):
-// the builder warps transpose the tile's membership words with warp ballots (lane = mask), expand them in registers
-// and store them with tcgen05.st — no shared-memory write, no shared-memory operand read.  B = the feature tile as
-// it lies in HBM (N-major): hi = the raw TMA tile (tf32, 8 points per MMA), lo = x - hi as a bf16 tile written by the
-// converters (kind::f16, 16 points per MMA; its error 2^-19 |x| is far inside the 1e-5 bar).  Shared-memory traffic
-// per tile: 32 (TMA) + 32 + 16 (converter) + 32 + 16 (MMA reads) = 128 KB.
-// TMEM map (512 columns): [0,256) two accumulator buffers of 128 channels; [256,384) two membership stages of
-// 64 points as tf32; [384,448) the same as bf16 pairs.
+// TMEM map (512 columns): [0, 128) the accumulator; then P2_CS membership stages of 64 points as tf32 (64 columns each) and the
+// same as bf16 pairs (32 columns each).  Shared-memory traffic per 32 KB tile: 32 (TMA) + 32 + 16 (converter) + 32 + 16 (MMA
+// operand reads) = 128 KB.
 constexpr int P2_LO = PM_TP * PM_SLICE * 2;          // bytes of a bf16 lo tile (16 KB)
 constexpr int P2_CS = 3;                             // membership (tensor memory) / lo-tile (shared memory) stages
 constexpr int P2_DB = 1;                             // accumulator buffers
@@ -524,7 +233,7 @@ pool_mma2_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P)
                         mbar_wait_sleep(&s_raw_empty[rs], rph ^ 1, 200);
                         PM_ACC(tw0, c0_);
                         unsigned char *dst = raw_base + (size_t)rs * PM_RAW;
-                        if (P.dbg2 & 1) {
+                        if (PM_DBG2(P) & 1) {
                             mbar_arrive(&s_raw_full[rs]);
                         } else {
                             mbar_expect_tx(&s_raw_full[rs], PM_RAW);
@@ -577,16 +286,16 @@ pool_mma2_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P)
                         const uint32_t d = tmem_base + (uint32_t)(P2_D + buf * PM_SLICE);
                         const uint32_t a32 = tmem_base + (uint32_t)(P2_A32 + cs * 64), a16 = tmem_base + (uint32_t)(P2_A16 + cs * 32);
                         if (elect_one_sync()) {
-                            if (P.dbg != 2) {
+                            if (PM_DBG(P) != 2) {
 #pragma unroll
                                 for (int ks = 0; ks < PM_TP / 8; ++ks)
                                     umma_tf32_ts(d, a32 + ks * 8, b_hi + (uint64_t)((ks * 1024) >> 4), id32, (ks || !first) ? 1u : 0u);
                             }
-                            if (P.dbg != 1) {
+                            if (PM_DBG(P) != 1) {
 #pragma unroll
                                 for (int ks = 0; ks < PM_TP / 16; ++ks)
                                     umma_f16_ts(d, a16 + ks * 8, b_lo + (uint64_t)((ks * 2048) >> 4), id16,
-                                                (P.dbg == 2 && ks == 0 && first) ? 0u : 1u);
+                                                (PM_DBG(P) == 2 && ks == 0 && first) ? 0u : 1u);
                             }
                             umma_commit(&s_raw_empty[rs]);
                             umma_commit(&s_conv_empty[cs]);
@@ -636,7 +345,7 @@ pool_mma2_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P)
                     // full tiles (all but the last of a segment) take the branch-free copy of the loop
                     auto convert = [&](auto full_tag) {
                         constexpr bool FULL = decltype(full_tag)::value;
-                        for (int j0 = 0; j0 < ((P.dbg2 & 2) ? 0 : PM_RAW / 16 / PM_CONV); j0 += UNR) {
+                        for (int j0 = 0; j0 < ((PM_DBG2(P) & 2) ? 0 : PM_RAW / 16 / PM_CONV); j0 += UNR) {
                             uint4 v[UNR];
 #pragma unroll
                             for (int u = 0; u < UNR; ++u) v[u] = raw[t0 + PM_CONV * (j0 + u)];
@@ -930,7 +639,7 @@ bool pool_mma_eligible(const float *feat, int c, const int32_t *row_index, const
                        const float *sum, const float *mean) {
     return member && !row_index && c % PM_SLICE == 0 && k >= 1 && k <= 128 && cap > 0 &&
            cap < ((int64_t)1 << 31) - PM_TP && reinterpret_cast<uintptr_t>(feat) % 16 == 0 && sum &&
-           reinterpret_cast<uintptr_t>(sum) % 4 == 0 && (!mean || reinterpret_cast<uintptr_t>(mean) % 4 == 0);
+           reinterpret_cast<uintptr_t>(sum) % 16 == 0 && (!mean || reinterpret_cast<uintptr_t>(mean) % 16 == 0);
 }
 
 int launch_pool_mma(const float *feat, int c, const uint32_t *member, int words, int n_seg, int k, const int64_t *seg_off,
@@ -957,42 +666,13 @@ int launch_pool_mma(const float *feat, int c, const uint32_t *member, int words,
         P.order = order;
     }
     static std::atomic<uint64_t> attr_set{0};
-    if (first_use_on_device(&attr_set)) {
-        cudaFuncSetAttribute(pool_mma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
-        cudaFuncSetAttribute(pool_mma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
-    }
-    const int t_rs = tune & 15, t_cs = (tune >> 4) & 15;
-    const bool v1 = (tune >> 8) & 1;                      // experiments: the first version (membership operand in shared memory)
-    const bool out16 = reinterpret_cast<uintptr_t>(sum) % 16 == 0 && (!mean || reinterpret_cast<uintptr_t>(mean) % 16 == 0);
-    if (!v1 && out16) {
-        static std::atomic<uint64_t> attr2{0};
-        if (first_use_on_device(&attr2)) {
-            cudaFuncSetAttribute(pool_mma2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_MAX_DYN_SMEM);
-            cudaFuncSetAttribute(pool_mma2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_MAX_DYN_SMEM);
-            cudaFuncSetAttribute(pool_mma2_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_MAX_DYN_SMEM);
-        }
-        P.raw_stages = (t_rs >= 1 && t_rs <= PM_MAX_STAGES) ? t_rs : 4;
-        P.conv_stages = 2;
-        const size_t smem2 = (size_t)P.raw_stages * PM_RAW + P2_CS * (size_t)P2_LO + 1024;
-        const int unr = (tune >> 12) & 3;                  // experiments: 0 = default
-        if (unr == 1) pool_mma2_kernel<4><<<grid, P2_THREADS, smem2, stream>>>(map, P);
-        else if (unr == 2) pool_mma2_kernel<8><<<grid, P2_THREADS, smem2, stream>>>(map, P);
-        else pool_mma2_kernel<16><<<grid, P2_THREADS, smem2, stream>>>(map, P);      // measured: 2.16 ms (8: 2.50, 4: 2.18)
-        count_launches(1);
-        return check_launch("xm3d_pool_batch (tensor-core path)");
-    }
-    const int bb = (k <= 64 ? 64 : 128) * PM_TP * 4;
-    const bool tuned = t_rs >= 1 && t_rs <= PM_MAX_STAGES && t_cs >= 1 && t_cs <= PM_MAX_STAGES &&
-                       (size_t)t_rs * PM_RAW + (size_t)t_cs * (PM_RAW + bb) + 1024 <= 226 * 1024;
-    if (k <= 64) {
-        P.raw_stages = tuned ? t_rs : 3; P.conv_stages = tuned ? t_cs : 2;
-        const size_t smem = (size_t)P.raw_stages * PM_RAW + (size_t)P.conv_stages * (PM_RAW + 64 * PM_TP * 4) + 1024;
-        pool_mma_kernel<64><<<grid, 32 * (10 + 4), smem, stream>>>(map, P);
-    } else {
-        P.raw_stages = tuned ? t_rs : 2; P.conv_stages = tuned ? t_cs : 2;
-        const size_t smem = (size_t)P.raw_stages * PM_RAW + (size_t)P.conv_stages * (PM_RAW + 128 * PM_TP * 4) + 1024;
-        pool_mma_kernel<128><<<grid, 32 * (10 + 8), smem, stream>>>(map, P);
-    }
+    if (first_use_on_device(&attr_set))
+        cudaFuncSetAttribute(pool_mma2_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_MAX_DYN_SMEM);
+    const int t_rs = tune & 15;                            // experiments: depth of the raw ring (default 4)
+    P.raw_stages = (t_rs >= 1 && t_rs <= PM_MAX_STAGES) ? t_rs : 4;
+    P.conv_stages = P2_CS;
+    const size_t smem2 = (size_t)P.raw_stages * PM_RAW + P2_CS * (size_t)P2_LO + 1024;
+    pool_mma2_kernel<16><<<grid, P2_THREADS, smem2, stream>>>(map, P);      // 16 converter loads in flight (8: +2 %, 4: +7 %)
     count_launches(1);
     return check_launch("xm3d_pool_batch (tensor-core path)");
 }
