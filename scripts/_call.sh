@@ -1,6 +1,3 @@
 set -x
-XM3D_SO=xmask3d_b200/libxm3d_head.so timeout 300 python scripts/time_pool_mma.py 0 0 > gpurun_out/time_pm43h.log 2>&1
-timeout 300 python scripts/time_pool_mma.py 0 0 > gpurun_out/time_pm43c.log 2>&1
-XM3D_SO=xmask3d_b200/libxm3d_head.so timeout 300 python scripts/time_pool_mma.py 0 0 >> gpurun_out/time_pm43h.log 2>&1
-timeout 300 python scripts/time_pool_mma.py 0 0 >> gpurun_out/time_pm43c.log 2>&1
+timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 > gpurun_out/bench45_n8.json 2> gpurun_out/bench45_n8.err; echo "rc=$?" >> gpurun_out/bench45_n8.err
 echo done
