@@ -435,35 +435,40 @@ pool_mma2_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P)
                     const uint32_t a32 = tmem_base + lane_addr + (uint32_t)(P2_A32 + cs * 64);
                     const uint32_t a16 = tmem_base + lane_addr + (uint32_t)(P2_A16 + cs * 32);
                     if (P.m64) {
+                        // one AND + one multiply per value: (w & (1 << b)) * (ONE >> b) is ONE or 0 exactly (b <= 23 for
+                        // 0x3f800000 = 0x7f << 23, b <= 7 for 0x3f80 = 0x7f << 7; higher bits come from a shifted copy)
                         {   // tf32 0.0f / 1.0f: column = point
                             const int sh = 2 * (lane & 3);
                             const uint32_t a_lo = ra0 >> sh, a_hi = ra1 >> sh, b_lo = rb0 >> sh, b_hi = rb1 >> sh;
+                            const uint32_t a_lo8 = a_lo >> 8, a_hi8 = a_hi >> 8, b_lo8 = b_lo >> 8, b_hi8 = b_hi >> 8;
                             uint32_t v[32];
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
-                                const uint32_t wa = i < 4 ? a_lo : a_hi, wb = i < 4 ? b_lo : b_hi;
-                                const int bit = 8 * (i & 3);
-                                v[4 * i + 0] = ((wa >> bit) & 1u) ? 0x3f800000u : 0u;
-                                v[4 * i + 1] = ((wa >> (bit + 1)) & 1u) ? 0x3f800000u : 0u;
-                                v[4 * i + 2] = ((wb >> bit) & 1u) ? 0x3f800000u : 0u;
-                                v[4 * i + 3] = ((wb >> (bit + 1)) & 1u) ? 0x3f800000u : 0u;
+                                const bool up = (i & 3) == 3;                       // bits 24, 25 -> bits 16, 17 of the >> 8 copy
+                                const uint32_t wa = i < 4 ? (up ? a_lo8 : a_lo) : (up ? a_hi8 : a_hi);
+                                const uint32_t wb = i < 4 ? (up ? b_lo8 : b_lo) : (up ? b_hi8 : b_hi);
+                                const int bit = up ? 16 : 8 * (i & 3);
+                                v[4 * i + 0] = (wa & (1u << bit)) * (0x3f800000u >> bit);
+                                v[4 * i + 1] = (wa & (2u << bit)) * (0x3f800000u >> (bit + 1));
+                                v[4 * i + 2] = (wb & (1u << bit)) * (0x3f800000u >> bit);
+                                v[4 * i + 3] = (wb & (2u << bit)) * (0x3f800000u >> (bit + 1));
                             }
                             tmem_st_16x256b_x8(a32, v);
                         }
                         {   // bf16 pairs: column c = points 2 c (low half), 2 c + 1
                             const int sh = 4 * (lane & 3);
                             const uint32_t a_lo = ra0 >> sh, a_hi = ra1 >> sh, b_lo = rb0 >> sh, b_hi = rb1 >> sh;
+                            const uint32_t a_lo16 = a_lo >> 16, a_hi16 = a_hi >> 16, b_lo16 = b_lo >> 16, b_hi16 = b_hi >> 16;
                             uint32_t v[16];
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
-                                const uint32_t wa = i < 2 ? a_lo : a_hi, wb = i < 2 ? b_lo : b_hi;
-                                const int bit = 16 * (i & 1);
+                                const uint32_t wa = i < 2 ? ((i & 1) ? a_lo16 : a_lo) : ((i & 1) ? a_hi16 : a_hi);
+                                const uint32_t wb = i < 2 ? ((i & 1) ? b_lo16 : b_lo) : ((i & 1) ? b_hi16 : b_hi);
 #pragma unroll
                                 for (int e = 0; e < 2; ++e) {
-                                    v[4 * i + e] = (((wa >> (bit + 2 * e)) & 1u) ? 0x3f80u : 0u) |
-                                                   (((wa >> (bit + 2 * e + 1)) & 1u) ? 0x3f800000u : 0u);
-                                    v[4 * i + 2 + e] = (((wb >> (bit + 2 * e)) & 1u) ? 0x3f80u : 0u) |
-                                                       (((wb >> (bit + 2 * e + 1)) & 1u) ? 0x3f800000u : 0u);
+                                    const int bit = 2 * e;
+                                    v[4 * i + e] = (wa & (1u << bit)) * (0x3f80u >> bit) + (wa & (2u << bit)) * (0x3f800000u >> (bit + 1));
+                                    v[4 * i + 2 + e] = (wb & (1u << bit)) * (0x3f80u >> bit) + (wb & (2u << bit)) * (0x3f800000u >> (bit + 1));
                                 }
                             }
                             tmem_st_16x256b_x4(a16, v);
