@@ -142,6 +142,9 @@ struct PointLogitsParams {
     int n_groups, ensemble_mean;
 };
 
+// MODE bit 0: fused-stream ensemble (mask_label), bit 1: synonym-group reduction (group_off).  Compile-time so that the plain
+// blend / argmax epilogue carries none of the other two (T = 200 runs one CTA per SM: nothing hides its epilogue).
+template <int MODE>
 __global__ void __launch_bounds__(PL_THREADS, 2)
 point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b_hi,
                     const __grid_constant__ CUtensorMap map_b_lo, const PointLogitsParams P) {
@@ -306,6 +309,7 @@ point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         }
         asm volatile("bar.sync 1, %0;" ::"n"(PL_CONV) : "memory");   // converter warps only
       if (warp < 6) {                                              // four epilogue warps: TMEM lane groups 2,3,0,1
+        constexpr bool ENS = (MODE & 1) != 0, GRP = (MODE & 2) != 0;
         mbar_wait(&s_done, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int lg = warp & 3;                                   // TMEM lane group of this warp
@@ -323,7 +327,7 @@ point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         };
         float smax = -INFINITY, ssum = 0.f;
         int label = -1;
-        if (P.mask_label) {
+        if (ENS) {
             // logits_pred.softmax(-1): two more passes over the accumulator row (TMEM reads are cheap)
             label = row_ok ? P.mask_label[r] : -1;
             if (label >= P.n_masks) label = -1;
@@ -344,7 +348,7 @@ point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     if (c0 + j < P.n_text) ssum += expf(logit_of(v, v2, j, c0 + j) - smax);
             }
         }
-        const float lsum = P.mask_label ? logf(ssum) : 0.f;
+        const float lsum = ENS ? logf(ssum) : 0.f;
         float best = -INFINITY;
         float gacc = P.ensemble_mean ? 0.f : -INFINITY;
         int best_i = 0;
@@ -357,7 +361,7 @@ point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 const int col = c0 + j;
                 if (col < P.n_text) {
                     float val = logit_of(v, v2, j, col);
-                    if (P.mask_label) {
+                    if (ENS) {
                         if (label >= 0) {
                             // (p ** ratio * q ** (1 - ratio)).log() * overlap, base and novel halves added (:577-590), in
                             // the log domain: ratio * log p + (1 - ratio) * log q with log p = val - max - log(sum) and
@@ -377,7 +381,7 @@ point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         const float lb = s_base[col] ? val : -1e10f, ln = s_base[col] ? -1e10f : val;
                         val = __fadd_rn(__fmul_rn(b, lb), __fmul_rn(__fsub_rn(1.0f, b), ln));
                     }
-                    if (P.group_off) {
+                    if (GRP) {
                         gacc = P.ensemble_mean ? gacc + val : fmaxf(gacc, val);
                         const int glen = s_glen[col];
                         if (glen > 0) {
@@ -527,10 +531,19 @@ static int launch_point_logits(const float *feat, int64_t rows, int c, const flo
     }
     static std::atomic<uint64_t> attr_set{0};
     if (first_use_on_device(&attr_set)) {
-        cudaFuncSetAttribute(point_logits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+        cudaFuncSetAttribute(point_logits_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+        cudaFuncSetAttribute(point_logits_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+        cudaFuncSetAttribute(point_logits_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+        cudaFuncSetAttribute(point_logits_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     }
-    point_logits_kernel<<<(unsigned)((rows + LG_BM - 1) / LG_BM), PL_THREADS, stage_bytes * stages + 1024, stream>>>(ma, mbh,
-                                                                                                                 mbl, P);
+    const unsigned grid = (unsigned)((rows + LG_BM - 1) / LG_BM);
+    const size_t smem = stage_bytes * stages + 1024;
+    switch ((P.mask_label ? 1 : 0) | (P.group_off ? 2 : 0)) {
+        case 0: point_logits_kernel<0><<<grid, PL_THREADS, smem, stream>>>(ma, mbh, mbl, P); break;
+        case 1: point_logits_kernel<1><<<grid, PL_THREADS, smem, stream>>>(ma, mbh, mbl, P); break;
+        case 2: point_logits_kernel<2><<<grid, PL_THREADS, smem, stream>>>(ma, mbh, mbl, P); break;
+        default: point_logits_kernel<3><<<grid, PL_THREADS, smem, stream>>>(ma, mbh, mbl, P); break;
+    }
     count_launches(1);
     return check_launch(who);
 }
