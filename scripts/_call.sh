@@ -1,5 +1,7 @@
 set -x
-timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/gpu_tests49.log 2>&1; echo "rc=$?" >> gpurun_out/gpu_tests49.log
-timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/smoke49.log 2>&1; echo "rc=$?" >> gpurun_out/smoke49.log
-timeout 900 python bench.py > gpurun_out/bench49.json 2> gpurun_out/bench49.err; echo "rc=$?" >> gpurun_out/bench49.err
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_canaries.py -m gpu -q -x -k "logits or canar or ensemble or fused" > gpurun_out/gpu_tests50.log 2>&1
+XM3D_SO=xmask3d_b200/libxm3d_prev.so timeout 300 python scripts/time_point_logits.py > gpurun_out/time_pl50p.log 2>&1
+timeout 300 python scripts/time_point_logits.py > gpurun_out/time_pl50n.log 2>&1
+XM3D_SO=xmask3d_b200/libxm3d_prev.so timeout 300 python scripts/time_logits.py >> gpurun_out/time_pl50p.log 2>&1
+timeout 300 python scripts/time_logits.py >> gpurun_out/time_pl50n.log 2>&1
 echo done

@@ -107,7 +107,10 @@ bool make_row_tile_map(CUtensorMap *m, const float *base, int64_t rows, int c, i
 // shared memory, four converter warps split every tile in place into its TF32-exact hi / lo tiles
 // (the split is elementwise, so the 128-byte swizzle written by TMA carries over unchanged) and
 // accumulate the row norms on the way; one thread issues the 3xTF32 tcgen05.mma chain into TMEM;
-// the converter warps then run the epilogue (normalise, scale, blend, argmax).
+// four epilogue warps normalise, scale, blend and take the argmax.  The CTAs are PERSISTENT (two per SM
+// when two fit) and the accumulator is double-buffered in tensor memory when there is room: the epilogue
+// of a tile runs while the next tile is loaded, split and multiplied (19 classes: 1.60 -> 1.46 ms,
+// 200 classes: 4.42 -> 3.29 ms, fused-stream ensemble with 19 classes: 1.96 -> 1.49 ms).
 #ifndef XM3D_PL_RAW_HI
 #define XM3D_PL_RAW_HI 1
 #endif
@@ -117,12 +120,14 @@ bool make_row_tile_map(CUtensorMap *m, const float *base, int64_t rows, int c, i
 constexpr int PL_CONV_WARPS = XM3D_PL_CONV_WARPS;                 // converter warps (the first four also run the epilogue)
 constexpr int PL_CONV = PL_CONV_WARPS * 32;
 constexpr int PL_CHUNKS = LG_BM * LG_BK * 4 / 16 / PL_CONV;    // 16-byte chunks per converter thread and k-block
-constexpr int PL_THREADS = 64 + PL_CONV;
+constexpr int PL_EPI = 128;                                        // four epilogue warps (one per TMEM lane group)
+constexpr int PL_THREADS = 64 + PL_CONV + PL_EPI;
 constexpr int PL_MAX_STAGES = 8;
 
 struct PointLogitsParams {
     int64_t rows;
     int c, n_text, bn, stages, tmem_cols;
+    int nbuf, acc_cols;          // accumulator buffers in tensor memory (1 or 2) and the columns of one
     int fused;                   // 1: [B_hi; B_lo] is one N = 2 bn operand (A_hi is read once), needs 2 bn <= 256
     float scale;
     const float *inv_norm_b;     // [n_text]
@@ -149,16 +154,18 @@ __global__ void __launch_bounds__(PL_THREADS, 2)
 point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b_hi,
                     const __grid_constant__ CUtensorMap map_b_lo, const PointLogitsParams P) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ uint64_t s_raw[PL_MAX_STAGES], s_conv[PL_MAX_STAGES], s_empty[PL_MAX_STAGES], s_done;
+    __shared__ uint64_t s_raw[PL_MAX_STAGES], s_conv[PL_MAX_STAGES], s_empty[PL_MAX_STAGES];
+    __shared__ uint64_t s_done[2], s_accfree[2];       // accumulator buffer: MMAs of a tile complete / epilogue has read it
+    __shared__ uint64_t s_ssfull[2], s_ssfree[2];      // row norms of a tile: converters -> epilogue
     __shared__ uint32_t s_tmem;
     __shared__ float s_invb[LG_MAX_N];
     __shared__ unsigned char s_base[LG_MAX_N];
-    __shared__ float s_ss[LG_BM];
+    __shared__ float s_ss[2][LG_BM];
     __shared__ short s_gid[LG_MAX_N];           // output column of each GEMM column (grouped mode)
     __shared__ short s_glen[LG_MAX_N];          // > 0 on the last column of a group: the group's length
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t m0 = (int64_t)blockIdx.x * LG_BM;
+    const int n_tiles = (int)((P.rows + LG_BM - 1) / LG_BM);       // persistent: tiles blockIdx.x, + gridDim.x, ...
     const int nkb = (P.c + LG_BK - 1) / LG_BK;
     const uint32_t a_bytes = LG_BM * LG_BK * 4, b_bytes = (uint32_t)P.bn * LG_BK * 4;
     const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;       // A raw -> hi (in place), A lo, B hi, B lo
@@ -184,7 +191,12 @@ point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             mbar_init(&s_conv[s], PL_CONV);
             mbar_init(&s_empty[s], 1);
         }
-        mbar_init(&s_done, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&s_done[b], 1);
+            mbar_init(&s_accfree[b], PL_EPI);
+            mbar_init(&s_ssfull[b], PL_CONV);
+            mbar_init(&s_ssfree[b], PL_EPI);
+        }
         mbar_fence_init();
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a));
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_hi));
@@ -206,11 +218,12 @@ point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
             for (int kb = 0; kb < nkb; ++kb) {
                 mbar_wait(&s_empty[stage], phase ^ 1);
                 unsigned char *st = tiles + (size_t)stage * stage_bytes;
                 mbar_expect_tx(&s_raw[stage], a_bytes + 2 * b_bytes);
-                tma_load_2d(st, &map_a, kb * LG_BK, (int)m0, &s_raw[stage]);
+                tma_load_2d(st, &map_a, kb * LG_BK, tile * LG_BM, &s_raw[stage]);
                 tma_load_2d(st + 2 * a_bytes, &map_b_hi, kb * LG_BK, 0, &s_raw[stage]);
                 tma_load_2d(st + 2 * a_bytes + b_bytes, &map_b_lo, kb * LG_BK, 0, &s_raw[stage]);
                 if (++stage == P.stages) { stage = 0; phase ^= 1; }
@@ -223,8 +236,11 @@ point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                                    ((uint32_t)(LG_BM >> 4) << 24);
             const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * P.bn) >> 3) << 17) |
                                     ((uint32_t)(LG_BM >> 4) << 24);
-            int stage = 0;
-            uint32_t phase = 0;
+            int stage = 0, buf = 0;
+            uint32_t phase = 0, bph = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            mbar_wait(&s_accfree[buf], bph ^ 1);                 // the epilogue has read this accumulator buffer
+            const uint32_t tmem_acc = tmem_base + (uint32_t)(buf * P.acc_cols);
             for (int kb = 0; kb < nkb; ++kb) {
                 mbar_wait(&s_raw[stage], phase);                 // B tiles landed (async proxy)
                 mbar_wait(&s_conv[stage], phase);                // hi / lo tiles written and fenced
@@ -238,31 +254,35 @@ point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
                     for (int k = 0; k < LG_BK / LG_UMMA_K; ++k) {
                         const uint64_t adv = (uint64_t)((k * LG_UMMA_K * 4) >> 4);
-                        umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc2, (kb | k) ? 1u : 0u);
-                        umma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, 1u);
+                        umma_tf32(tmem_acc, a_hi + adv, b_hi + adv, idesc2, (kb | k) ? 1u : 0u);
+                        umma_tf32(tmem_acc, a_lo + adv, b_hi + adv, idesc, 1u);
                     }
                 } else {
 #pragma unroll
                     for (int k = 0; k < LG_BK / LG_UMMA_K; ++k) {
                         const uint64_t adv = (uint64_t)((k * LG_UMMA_K * 4) >> 4);
-                        umma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, (kb | k) ? 1u : 0u);
-                        umma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
-                        umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, 1u);
+                        umma_tf32(tmem_acc, a_lo + adv, b_hi + adv, idesc, (kb | k) ? 1u : 0u);
+                        umma_tf32(tmem_acc, a_hi + adv, b_lo + adv, idesc, 1u);
+                        umma_tf32(tmem_acc, a_hi + adv, b_hi + adv, idesc, 1u);
                     }
                 }
                 umma_commit(&s_empty[stage]);
                 if (++stage == P.stages) { stage = 0; phase ^= 1; }
             }
-            umma_commit(&s_done);
+            umma_commit(&s_done[buf]);
+            if (++buf == P.nbuf) { buf = 0; bph ^= 1; }
+            }
         }
     } else {
-        // ===== converter warps (then epilogue): thread t owns the 16-byte chunks t + PL_CONV * j =====
+      if (warp < 2 + PL_CONV_WARPS) {
+        // ===== converter warps: thread t owns the 16-byte chunks t + PL_CONV * j =====
         const int t = tid - 64;
+        int stage = 0, sb = 0;
+        uint32_t phase = 0, sph = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         float ss[PL_CHUNKS];
 #pragma unroll
         for (int j = 0; j < PL_CHUNKS; ++j) ss[j] = 0.f;
-        int stage = 0;
-        uint32_t phase = 0;
         for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait(&s_raw[stage], phase);
             unsigned char *st = tiles + (size_t)stage * stage_bytes;
@@ -299,27 +319,37 @@ point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             if (++stage == P.stages) { stage = 0; phase ^= 1; }
         }
         // row sums of squares: the 8 chunks of a row sit in 8 consecutive threads
+        mbar_wait(&s_ssfree[sb], sph ^ 1);
 #pragma unroll
         for (int j = 0; j < PL_CHUNKS; ++j) {
             float v = ss[j];
             v += __shfl_xor_sync(0xffffffffu, v, 1);
             v += __shfl_xor_sync(0xffffffffu, v, 2);
             v += __shfl_xor_sync(0xffffffffu, v, 4);
-            if ((t & 7) == 0) s_ss[(t >> 3) + (PL_CONV / 8) * j] = v;
+            if ((t & 7) == 0) s_ss[sb][(t >> 3) + (PL_CONV / 8) * j] = v;
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(PL_CONV) : "memory");   // converter warps only
-      if (warp < 6) {                                              // four epilogue warps: TMEM lane groups 2,3,0,1
+        mbar_arrive(&s_ssfull[sb]);
+        if (++sb == P.nbuf) { sb = 0; sph ^= 1; }
+        }
+      } else {
+        // ===== four epilogue warps (one per TMEM lane group): while they work on a tile, the producer / converters / MMAs
+        // run the next one into the other accumulator buffer =====
         constexpr bool ENS = (MODE & 1) != 0, GRP = (MODE & 2) != 0;
-        mbar_wait(&s_done, 0);
+        int buf = 0;
+        uint32_t bph = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t m0 = (int64_t)tile * LG_BM;
+        mbar_wait(&s_ssfull[buf], bph);
+        mbar_wait(&s_done[buf], bph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int lg = warp & 3;                                   // TMEM lane group of this warp
         const int rloc = lg * 32 + lane;
         const int64_t r = m0 + rloc;
         const bool row_ok = r < P.rows;
-        const float inv_a = __fdiv_rn(1.0f, fmaxf(sqrtf(s_ss[rloc]), 1e-12f));      // F.normalize
+        const float inv_a = __fdiv_rn(1.0f, fmaxf(sqrtf(s_ss[buf][rloc]), 1e-12f));      // F.normalize
         const float b = (row_ok && P.binary) ? P.binary[r] : 0.f;
         const bool blend = P.binary != nullptr;
-        const uint32_t trow = tmem_base + ((uint32_t)(lg * 32) << 16);
+        const uint32_t trow = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * P.acc_cols);
         // scaled cosine logit of column `col` out of the accumulator chunk(s)
         auto logit_of = [&](const uint32_t (&v)[16], const uint32_t (&v2)[16], int j, int col) {
             const float dot = P.fused ? __uint_as_float(v[j]) + __uint_as_float(v2[j]) : __uint_as_float(v[j]);
@@ -399,6 +429,11 @@ point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
         }
         if (row_ok && P.argmax) P.argmax[r] = best_i;
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(&s_accfree[buf]);
+        mbar_arrive(&s_ssfree[buf]);
+        if (++buf == P.nbuf) { buf = 0; bph ^= 1; }
+        }
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -514,7 +549,7 @@ static int launch_point_logits(const float *feat, int64_t rows, int c, const flo
     P.fused = (2 * P.bn <= 256) ? 1 : 0;
     int tc = 32;
     while (tc < (P.fused ? 2 * P.bn : P.bn)) tc <<= 1;
-    P.tmem_cols = tc;
+    P.acc_cols = tc;
     const size_t stage_bytes = 2 * (size_t)LG_BM * LG_BK * 4 + 2 * (size_t)P.bn * LG_BK * 4;
     // two CTAs per SM when two stages of each fit (the second CTA's TMA / MMA hides the first one's
     // conversion pass), else one CTA with as many stages as fit
@@ -523,6 +558,11 @@ static int launch_point_logits(const float *feat, int64_t rows, int c, const flo
     if (stages > 4) stages = 4;
     if (stages < 1) { set_error("%s: tile does not fit shared memory", who); return XM3D_ERR_UNSUPPORTED; }
     P.stages = stages;
+    // persistent CTAs (two per SM when two fit): the epilogue of a tile overlaps the next tile's loads and MMAs through a
+    // second accumulator buffer when tensor memory has room for it (512 columns per SM, shared by the co-resident CTAs)
+    const int ctas_per_sm = (stage_bytes * (size_t)stages + 1024 <= 110 * 1024) ? 2 : 1;
+    P.nbuf = (ctas_per_sm * 2 * tc <= 512) ? 2 : 1;
+    P.tmem_cols = P.nbuf * tc;
     CUtensorMap ma, mbh, mbl;
     if (!make_map(&ma, feat, rows, c, LG_BM) || !make_map(&mbh, b_hi, n_text, c, P.bn) ||
         !make_map(&mbl, b_lo, n_text, c, P.bn)) {
@@ -531,12 +571,14 @@ static int launch_point_logits(const float *feat, int64_t rows, int c, const flo
     }
     static std::atomic<uint64_t> attr_set{0};
     if (first_use_on_device(&attr_set)) {
-        cudaFuncSetAttribute(point_logits_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
-        cudaFuncSetAttribute(point_logits_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
-        cudaFuncSetAttribute(point_logits_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
-        cudaFuncSetAttribute(point_logits_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+        cudaFuncSetAttribute(point_logits_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024);   // + 4 KB static + 1 KB reserved <= 227 KB
+        cudaFuncSetAttribute(point_logits_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024);   // + 4 KB static + 1 KB reserved <= 227 KB
+        cudaFuncSetAttribute(point_logits_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024);   // + 4 KB static + 1 KB reserved <= 227 KB
+        cudaFuncSetAttribute(point_logits_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024);   // + 4 KB static + 1 KB reserved <= 227 KB
     }
-    const unsigned grid = (unsigned)((rows + LG_BM - 1) / LG_BM);
+    const int64_t n_tiles = (rows + LG_BM - 1) / LG_BM;
+    const int64_t slots = (int64_t)sm_count() * ctas_per_sm;
+    const unsigned grid = (unsigned)(n_tiles < slots ? n_tiles : slots);
     const size_t smem = stage_bytes * stages + 1024;
     switch ((P.mask_label ? 1 : 0) | (P.group_off ? 2 : 0)) {
         case 0: point_logits_kernel<0><<<grid, PL_THREADS, smem, stream>>>(ma, mbh, mbl, P); break;
