@@ -379,6 +379,7 @@ point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
         }
         const float lsum = ENS ? logf(ssum) : 0.f;
+        const bool any_unlabelled = ENS && __any_sync(0xffffffffu, label < 0);
         float best = -INFINITY;
         float gacc = P.ensemble_mean ? 0.f : -INFINITY;
         int best_i = 0;
@@ -392,18 +393,22 @@ point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 if (col < P.n_text) {
                     float val = logit_of(v, v2, j, col);
                     if (ENS) {
-                        if (label >= 0) {
-                            // (p ** ratio * q ** (1 - ratio)).log() * overlap, base and novel halves added (:577-590), in
-                            // the log domain: ratio * log p + (1 - ratio) * log q with log p = val - max - log(sum) and
-                            // log q precomputed per (mask, class) — no pow / log per element.  Equal to the reference's
-                            // float32 sequence up to rounding (~1e-6); where the reference's p underflows to 0 it yields
-                            // NaN (-inf * 0), this form stays finite.
-                            const float logp = (val - smax) - lsum;
-                            const float logq = __ldg(P.mask_probs + (size_t)label * P.n_text + col);
-                            const float ratio = s_base[col] ? P.base_ratio : P.novel_ratio;
-                            val = fmaf(ratio, logp, (1.f - ratio) * logq);
+                        // (p ** ratio * q ** (1 - ratio)).log() * overlap, base and novel halves added (:577-590), in the log
+                        // domain: ratio * log p + (1 - ratio) * log q with log p = val - max - log(sum) and log q precomputed
+                        // per (mask, class) — no pow / log per element.  Equal to the reference's float32 sequence up to
+                        // rounding (~1e-6); where the reference's p underflows to 0 it yields NaN (-inf * 0), this form stays
+                        // finite.  Branch-free per lane (rows outside every mask read mask 0's row and discard it; the class
+                        // probability they need is computed only by warps that hold such a row): the 16 loads of a chunk
+                        // issue back to back instead of one per divergent branch.
+                        const float logp = (val - smax) - lsum;
+                        const float logq = __ldg(P.mask_probs + (size_t)(label >= 0 ? label : 0) * P.n_text + col);
+                        const float ratio = s_base[col] ? P.base_ratio : P.novel_ratio;
+                        const float ens = fmaf(ratio, logp, (1.f - ratio) * logq);
+                        if (any_unlabelled) {
+                            const float prob = __fdiv_rn(expf(val - smax), ssum);            // class probability
+                            val = label >= 0 ? ens : prob;
                         } else {
-                            val = __fdiv_rn(expf(val - smax), ssum);                   // class probability
+                            val = ens;
                         }
                     }
                     if (blend) {
