@@ -1,4 +1,8 @@
-"""Time the pooling kernels on bench-sized inputs for a list of tune words (experiments)."""
+"""Time the pooling kernels on bench-sized inputs: argv = "rows" | "pair_lists" | a tune word for the tensor-core kernel
+(0 = default; low nibble = depth of the raw ring, bit 9 = no size ordering, bit 10 = M = 128 for every K; the "switch a role
+off" bits 14-17 only act in the instrumented build: make -C xmask3d_b200/csrc BUILD=build_dbg OUT=../libxm3d_dbg.so
+EXTRA=-DXM3D_PM_TIMING, XM3D_SO=xmask3d_b200/libxm3d_dbg.so).  Timed-alone numbers differ by ~4 % from box to box: compare
+two libraries in ONE gpurun call."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
