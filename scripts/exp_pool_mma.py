@@ -9,18 +9,19 @@ dev = torch.device("cuda", 0)
 lib = ops.L.lib()
 lib.xm3d_pool_mma_debug.restype = C.c_int
 lib.xm3d_pool_mma_debug.argtypes = [C.c_void_p]
-total, c, k, nseg = 2_339_470, 768, 50, 160
+total, c, k, nseg = 2_339_470, 768, int(os.environ.get("PM_K", "50")), 160
 feat = torch.randn(total, c, device=dev)
 bounds = np.sort(np.random.default_rng(0).choice(np.arange(1, total), nseg - 1, replace=False))
 off = np.concatenate([[0], bounds, [total]]).astype(np.int64)
 seg = torch.from_numpy(off).to(dev)
-bits = (torch.rand(total, 64, device=dev) < 7.7 / 50)
-bits[:, 50:] = False
-w0 = (bits[:, :32].long() << torch.arange(32, device=dev)).sum(1)
-w1 = (bits[:, 32:].long() << torch.arange(32, device=dev)).sum(1)
-member = torch.stack([w0, w1], 1)
-member = torch.where(member >= 2 ** 31, member - 2 ** 32, member).to(torch.int32)
-pairs = int(bits.sum().item())
+words = (k + 31) // 32
+member = torch.zeros(total, words, dtype=torch.int32, device=dev)
+for w in range(words):
+    nb = min(32, k - 32 * w)
+    bits = (torch.rand(total, nb, device=dev) < 0.154)
+    val = (bits.long() << torch.arange(nb, device=dev)).sum(1)
+    member[:, w] = torch.where(val >= 2 ** 31, val - 2 ** 32, val).to(torch.int32)
+pairs = int(ops._popcount32(member).sum().item())
 tunes = [int(x, 0) for x in sys.argv[1:]] or [0]
 for tune in tunes:
     for _ in range(2):
@@ -42,6 +43,7 @@ for tune in tunes:
              2: ("converter", ["wait raw_full", "wait conv_empty", "loop total", "fence.proxy.async"]),
              3: ("builder", ["wait conv_empty", "expand + tcgen05.st", "loop total", "tcgen05.wait::st"]),
              5: ("builder (2)", ["wait transposed words", "-", "-", "-"]),
+             6: ("preparation", ["cp.async.wait_group", "LDS + transposes", "issue cp.async", "wait free slot"]),
              4: ("epilogue", ["wait tile_done", "-", "loop total", "-"])}
     for r, (nm, cols) in names.items():
         per_tile = d[:, r, :].sum(0) / tiles.sum()

@@ -137,6 +137,21 @@ __device__ __forceinline__ uint32_t warp_transpose32(uint32_t x) {
     }
     return x;
 }
+// N independent transposes, round by round: the N shuffles of a round issue back to back, so the dependent chain of
+// one transpose (5 x (shuffle latency + 6 ALU) ~ 300 cycles) is shared by all of them.
+template <int N>
+__device__ __forceinline__ void warp_transpose32_n(uint32_t (&x)[N]) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int j = 16; j >= 1; j >>= 1) {
+        const uint32_t m = j == 16 ? 0x0000ffffu : j == 8 ? 0x00ff00ffu : j == 4 ? 0x0f0f0f0fu : j == 2 ? 0x33333333u : 0x55555555u;
+        uint32_t y[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) y[i] = __shfl_xor_sync(0xffffffffu, x[i], j);
+#pragma unroll
+        for (int i = 0; i < N; ++i) x[i] = (lane & j) ? (((y[i] >> j) & m) | (x[i] & ~m)) : ((x[i] & m) | ((y[i] & m) << j));
+    }
+}
 // global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned.
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

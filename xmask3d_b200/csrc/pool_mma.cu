@@ -474,12 +474,18 @@ pool_mma2_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P)
                             tmem_st_16x256b_x4(a16, v);
                         }
                     } else {
+                        // M = 128: lane = mask row, 32-lane store shape; same AND + multiply expansion
+                        const uint32_t m0_8 = m0 >> 8, m1_8 = m1 >> 8;
 #pragma unroll
                         for (int h = 0; h < 4; ++h) {
-                            const uint32_t bits = (h < 2 ? m0 : m1) >> ((h & 1) * 16);
                             uint32_t v[16];
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) v[j] = ((bits >> j) & 1u) ? 0x3f800000u : 0u;
+                            for (int j = 0; j < 16; ++j) {
+                                const int b = (h & 1) * 16 + j;                      // bit of m0 / m1
+                                const uint32_t w = b < 24 ? (h < 2 ? m0 : m1) : (h < 2 ? m0_8 : m1_8);
+                                const int bb = b < 24 ? b : b - 8;
+                                v[j] = (w & (1u << bb)) * (0x3f800000u >> bb);
+                            }
                             tmem_st16(a32 + h * 16, v);
                         }
 #pragma unroll
@@ -487,8 +493,11 @@ pool_mma2_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P)
                             const uint32_t bits = h ? m1 : m0;
                             uint32_t v[16];
 #pragma unroll
-                            for (int j = 0; j < 16; ++j)
-                                v[j] = (((bits >> (2 * j)) & 1u) ? 0x3f80u : 0u) | (((bits >> (2 * j + 1)) & 1u) ? 0x3f800000u : 0u);
+                            for (int j = 0; j < 16; ++j) {
+                                const uint32_t w = bits >> (8 * (j >> 2));           // points 2 j, 2 j + 1 = bits r, r + 1 of this copy
+                                const int r = 2 * (j & 3);
+                                v[j] = (w & (1u << r)) * (0x3f80u >> r) + (w & (2u << r)) * (0x3f800000u >> (r + 1));
+                            }
                             tmem_st16(a16 + h * 16, v);
                         }
                     }
@@ -569,6 +578,7 @@ pool_mma2_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P)
             // tiles ahead (a register prefetch that is rotated at the end of the iteration makes the rotation wait for the
             // load: the pipeline then runs at one loaded global-memory latency per tile).
             const int pw = warp - (10 + P2_EPI_WARPS);
+            const bool second_word = pw + 2 < P.words && (pw + 2) * 32 < P.k;      // K > 64: this warp transposes two words
             const int tail = P.k & 31;
             int iq = 0; uint32_t iqph = 0; int ts = 0; uint32_t tph = 0;
             for (;;) {
@@ -596,30 +606,42 @@ pool_mma2_kernel(const __grid_constant__ CUtensorMap map, const PoolMmaParams P)
                 };
 #pragma unroll
                 for (int u = 0; u < P2_MW; ++u) issue_words(u);
+                long long pw0 = 0, pw1 = 0, pw2 = 0, pw3 = 0;
                 for (int t = 0; t < ntile; ++t) {
+                    long long c0_ = PM_CLK();
                     asm volatile("cp.async.wait_group %0;" ::"n"(P2_MW - 1) : "memory");
-                    uint32_t tr[2][2];
+                    PM_ACC(pw0, c0_); c0_ = PM_CLK();
+                    // the (up to) four 32 x 32 bit transposes of this warp's two words run round by round together
+                    uint32_t tr[4];
 #pragma unroll
                     for (int wq = 0; wq < 2; ++wq) {
                         const int w = pw + 2 * wq;
                         const bool word_ok = w < P.words && w * 32 < P.k;
                         const uint32_t tail_mask = (tail && w == (P.k >> 5)) ? (1u << tail) - 1u : 0xffffffffu;
-                        tr[wq][0] = tr[wq][1] = 0u;
-                        if (word_ok) {                                // two 32 x 32 bit transposes (5 shuffle rounds each)
-                            tr[wq][0] = warp_transpose32(s_mw[t & (P2_MW - 1)][w][lane] & tail_mask);
-                            tr[wq][1] = warp_transpose32(s_mw[t & (P2_MW - 1)][w][32 + lane] & tail_mask);
-                        }
+                        tr[2 * wq] = word_ok ? s_mw[t & (P2_MW - 1)][w][lane] & tail_mask : 0u;
+                        tr[2 * wq + 1] = word_ok ? s_mw[t & (P2_MW - 1)][w][32 + lane] & tail_mask : 0u;
                     }
+                    if (second_word) {
+                        warp_transpose32_n<4>(tr);
+                    } else {
+                        uint32_t t2[2] = {tr[0], tr[1]};
+                        warp_transpose32_n<2>(t2);
+                        tr[0] = t2[0]; tr[1] = t2[1];
+                    }
+                    PM_ACC(pw1, c0_); c0_ = PM_CLK();
                     issue_words(t + P2_MW);                           // the slot is free: its words are in registers
+                    PM_ACC(pw2, c0_); c0_ = PM_CLK();
                     mbar_wait(&s_tw_empty[ts], tph ^ 1);
+                    PM_ACC(pw3, c0_);
 #pragma unroll
                     for (int wq = 0; wq < 2; ++wq) {
-                        s_tw[ts][pw + 2 * wq][0][lane] = tr[wq][0];
-                        s_tw[ts][pw + 2 * wq][1][lane] = tr[wq][1];
+                        s_tw[ts][pw + 2 * wq][0][lane] = tr[2 * wq];
+                        s_tw[ts][pw + 2 * wq][1][lane] = tr[2 * wq + 1];
                     }
                     mbar_arrive(&s_tw_full[ts]);
                     if (++ts == P2_TW) { ts = 0; tph ^= 1; }
                 }
+                if (tid == 576) PM_OUT(6, pw0, pw1, pw2, pw3);
                 asm volatile("cp.async.wait_group 0;" ::: "memory");   // the copy ring is reused by the next item
             }
         }
