@@ -14,6 +14,7 @@
 // memory; only the (small) text side goes through a prep kernel.  Round 1 ran the mask-level logits as prep (2 launches
 // writing hi / lo planes of the mask embeddings to HBM) + GEMM; that kernel is gone.
 #include <cuda.h>
+#include <cuda_bf16.h>
 
 #include <stdlib.h>
 #include <string.h>
@@ -32,7 +33,8 @@ constexpr int LG_THREADS = 192;
 // ---- prep: inverse norms + hi/lo TF32 planes ------------------------------------------------
 __global__ void __launch_bounds__(256)
 logits_prep_kernel(const float *__restrict__ a, const float *__restrict__ b, int64_t rows_a, int64_t rows_b,
-                   int c, float *__restrict__ hi, float *__restrict__ lo, float *__restrict__ inv_norm) {
+                   int c, float *__restrict__ hi, float *__restrict__ lo, unsigned short *__restrict__ bf, int ld_bf,
+                   float *__restrict__ inv_norm) {
     // one warp per row; rows [0, rows_a) come from a, [rows_a, rows_a + rows_b) from b
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows_a + rows_b) return;
@@ -46,7 +48,9 @@ logits_prep_kernel(const float *__restrict__ a, const float *__restrict__ b, int
         const float l = __uint_as_float(__float_as_uint(__fsub_rn(x, h)) & 0xffffe000u);
         hi[row * c + j] = h;
         lo[row * c + j] = l;
+        bf[row * ld_bf + j] = __bfloat16_as_ushort(__float2bfloat16_rn(x));     // partner of the rows' bf16 lo tile
     }
+    for (int j = c + lane; j < ld_bf; j += 32) bf[row * ld_bf + j] = 0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     // F.normalize: x / max(||x||_2, 1e-12)
@@ -80,6 +84,18 @@ bool make_map_sw128(CUtensorMap *m, const float *base, int64_t rows, int c, int 
               CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
+// bf16 plane [rows, ld] with 64-byte rows per k-block: 64-byte swizzle
+static bool make_map_bf16_sw64(CUtensorMap *m, const unsigned short *base, int64_t rows, int ld, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)LG_BK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<unsigned short *>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 static bool make_map(CUtensorMap *m, const float *base, int64_t rows, int c, int box_rows) {
     return make_map_sw128(m, base, rows, c, LG_BK, box_rows);
 }
@@ -104,16 +120,14 @@ bool make_row_tile_map(CUtensorMap *m, const float *base, int64_t rows, int c, i
 // run/infer.py:557, 606-640 (and loss_exact, models/utils/criterion.py:184-207).
 //
 // The [n, C] float32 features are read from HBM exactly once: TMA brings raw 128 x 32 tiles into
-// shared memory, four converter warps split every tile in place into its TF32-exact hi / lo tiles
-// (the split is elementwise, so the 128-byte swizzle written by TMA carries over unchanged) and
-// accumulate the row norms on the way; one thread issues the 3xTF32 tcgen05.mma chain into TMEM;
+// shared memory; the raw tile IS the tf32 hi operand (the tensor core ignores the 13 low mantissa bits),
+// four converter warps write lo = x - hi as a bf16 tile (64-byte rows, 64-byte swizzle; error 2^-20 |x|)
+// and accumulate the row norms on the way; one thread issues hi x (text hi + text lo) as kind::tf32 MMAs
+// and lo x text as kind::f16 MMAs into TMEM;
 // four epilogue warps normalise, scale, blend and take the argmax.  The CTAs are PERSISTENT (two per SM
 // when two fit) and the accumulator is double-buffered in tensor memory when there is room: the epilogue
 // of a tile runs while the next tile is loaded, split and multiplied (19 classes: 1.60 -> 1.46 ms,
 // 200 classes: 4.42 -> 3.29 ms, fused-stream ensemble with 19 classes: 1.96 -> 1.49 ms).
-#ifndef XM3D_PL_RAW_HI
-#define XM3D_PL_RAW_HI 1
-#endif
 #ifndef XM3D_PL_CONV_WARPS
 #define XM3D_PL_CONV_WARPS 4
 #endif
@@ -152,7 +166,8 @@ struct PointLogitsParams {
 template <int MODE>
 __global__ void __launch_bounds__(PL_THREADS, 2)
 point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b_hi,
-                    const __grid_constant__ CUtensorMap map_b_lo, const PointLogitsParams P) {
+                    const __grid_constant__ CUtensorMap map_b_lo, const __grid_constant__ CUtensorMap map_b_bf,
+                    const PointLogitsParams P) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ uint64_t s_raw[PL_MAX_STAGES], s_conv[PL_MAX_STAGES], s_empty[PL_MAX_STAGES];
     __shared__ uint64_t s_done[2], s_accfree[2];       // accumulator buffer: MMAs of a tile complete / epilogue has read it
@@ -168,7 +183,9 @@ point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const int n_tiles = (int)((P.rows + LG_BM - 1) / LG_BM);       // persistent: tiles blockIdx.x, + gridDim.x, ...
     const int nkb = (P.c + LG_BK - 1) / LG_BK;
     const uint32_t a_bytes = LG_BM * LG_BK * 4, b_bytes = (uint32_t)P.bn * LG_BK * 4;
-    const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;       // A raw -> hi (in place), A lo, B hi, B lo
+    // stage: A raw (= its tf32 hi part) | A lo as bf16 (64-byte rows, 64-byte swizzle) | B hi | B lo (tf32) | B as bf16
+    const uint32_t alo_bytes = LG_BM * LG_BK * 2, bf_bytes = (uint32_t)P.bn * LG_BK * 2;
+    const uint32_t stage_bytes = a_bytes + alo_bytes + 2 * b_bytes + bf_bytes;
     unsigned char *tiles = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
 
     for (int j = tid; j < LG_MAX_N; j += PL_THREADS) {
@@ -201,6 +218,7 @@ point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a));
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_hi));
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_lo));
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_bf));
     }
     if (warp == 1) {
         __syncwarp();
@@ -222,10 +240,11 @@ point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             for (int kb = 0; kb < nkb; ++kb) {
                 mbar_wait(&s_empty[stage], phase ^ 1);
                 unsigned char *st = tiles + (size_t)stage * stage_bytes;
-                mbar_expect_tx(&s_raw[stage], a_bytes + 2 * b_bytes);
+                mbar_expect_tx(&s_raw[stage], a_bytes + 2 * b_bytes + bf_bytes);
                 tma_load_2d(st, &map_a, kb * LG_BK, tile * LG_BM, &s_raw[stage]);
-                tma_load_2d(st + 2 * a_bytes, &map_b_hi, kb * LG_BK, 0, &s_raw[stage]);
-                tma_load_2d(st + 2 * a_bytes + b_bytes, &map_b_lo, kb * LG_BK, 0, &s_raw[stage]);
+                tma_load_2d(st + a_bytes + alo_bytes, &map_b_hi, kb * LG_BK, 0, &s_raw[stage]);
+                tma_load_2d(st + a_bytes + alo_bytes + b_bytes, &map_b_lo, kb * LG_BK, 0, &s_raw[stage]);
+                tma_load_2d(st + a_bytes + alo_bytes + 2 * b_bytes, &map_b_bf, kb * LG_BK, 0, &s_raw[stage]);
                 if (++stage == P.stages) { stage = 0; phase ^= 1; }
             }
         }
@@ -236,6 +255,7 @@ point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                                    ((uint32_t)(LG_BM >> 4) << 24);
             const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * P.bn) >> 3) << 17) |
                                     ((uint32_t)(LG_BM >> 4) << 24);
+            const uint32_t idesc_bf = make_idesc(LG_BM, P.bn, 1, 0, 0);       // bf16 x bf16 -> f32, both K-major
             int stage = 0, buf = 0;
             uint32_t phase = 0, bph = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -246,25 +266,34 @@ point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 mbar_wait(&s_conv[stage], phase);                // hi / lo tiles written and fenced
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 unsigned char *st = tiles + (size_t)stage * stage_bytes;
-                const uint64_t a_hi = make_sw128_desc(st), a_lo = make_sw128_desc(st + a_bytes);
-                const uint64_t b_hi = make_sw128_desc(st + 2 * a_bytes), b_lo = make_sw128_desc(st + 2 * a_bytes + b_bytes);
+                // A hi / B hi / B lo: tf32, 128-byte rows, 128-byte swizzle; A lo / B bf: bf16, 64-byte rows, 64-byte swizzle
+                // (8-row groups 512 bytes apart)
+                const uint64_t a_hi = make_sw128_desc(st);
+                const uint64_t a_lo = make_sw128_desc_ex(st + a_bytes, 0, 512, 4);
+                const uint64_t b_hi = make_sw128_desc(st + a_bytes + alo_bytes);
+                const uint64_t b_lo = make_sw128_desc(st + a_bytes + alo_bytes + b_bytes);
+                const uint64_t b_bf = make_sw128_desc_ex(st + a_bytes + alo_bytes + 2 * b_bytes, 0, 512, 4);
                 if (P.fused) {
                     // B_hi and B_lo are adjacent 8-row-group aligned tiles: one N = 2 bn operand.  Columns
-                    // [0, bn) accumulate hi*hi + lo*hi, columns [bn, 2 bn) hi*lo; the epilogue adds them.
+                    // [0, bn) accumulate hi*hi (+ lo*b below), columns [bn, 2 bn) hi*lo; the epilogue adds them.
 #pragma unroll
                     for (int k = 0; k < LG_BK / LG_UMMA_K; ++k) {
                         const uint64_t adv = (uint64_t)((k * LG_UMMA_K * 4) >> 4);
                         umma_tf32(tmem_acc, a_hi + adv, b_hi + adv, idesc2, (kb | k) ? 1u : 0u);
-                        umma_tf32(tmem_acc, a_lo + adv, b_hi + adv, idesc, 1u);
                     }
                 } else {
 #pragma unroll
                     for (int k = 0; k < LG_BK / LG_UMMA_K; ++k) {
                         const uint64_t adv = (uint64_t)((k * LG_UMMA_K * 4) >> 4);
-                        umma_tf32(tmem_acc, a_lo + adv, b_hi + adv, idesc, (kb | k) ? 1u : 0u);
+                        umma_tf32(tmem_acc, a_hi + adv, b_hi + adv, idesc, (kb | k) ? 1u : 0u);
                         umma_tf32(tmem_acc, a_hi + adv, b_lo + adv, idesc, 1u);
-                        umma_tf32(tmem_acc, a_hi + adv, b_hi + adv, idesc, 1u);
                     }
+                }
+                // lo (bf16, error 2^-20 |x|) x text (bf16): kind::f16, 16 channels per MMA
+#pragma unroll
+                for (int k = 0; k < LG_BK / 16; ++k) {
+                    const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);
+                    umma_f16(tmem_acc, a_lo + adv, b_bf + adv, idesc_bf, 1u);
                 }
                 umma_commit(&s_empty[stage]);
                 if (++stage == P.stages) { stage = 0; phase ^= 1; }
@@ -286,32 +315,27 @@ point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait(&s_raw[stage], phase);
             unsigned char *st = tiles + (size_t)stage * stage_bytes;
-            uint4 *raw = reinterpret_cast<uint4 *>(st);             // overwritten in place by its hi part
-            uint4 *hi = raw, *lo = reinterpret_cast<uint4 *>(st + a_bytes);
+            const uint4 *raw = reinterpret_cast<const uint4 *>(st);  // the raw tile IS the tf32 hi operand (13 low bits ignored)
+            unsigned char *lo = st + a_bytes;                       // bf16 [128 rows][32 channels], 64-byte swizzle
 #pragma unroll
             for (int j = 0; j < PL_CHUNKS; ++j) {
-                const int q = t + PL_CONV * j;                    // chunk q lies in row q >> 3 (any swizzle)
+                const int q = t + PL_CONV * j;                    // physical 16-byte chunk q of the raw tile: row q >> 3
                 const uint4 v = raw[q];
-                uint4 h, l;
                 const uint32_t in[4] = {v.x, v.y, v.z, v.w};
-                uint32_t ho[4], lw[4];
+                float l[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const float x = __uint_as_float(in[e]);
-                    ho[e] = in[e] & 0xffffe000u;
-                    lw[e] = __float_as_uint(__fsub_rn(x, __uint_as_float(ho[e]))) & 0xffffe000u;
+                    l[e] = __fsub_rn(x, __uint_as_float(in[e] & 0xffffe000u));
                     ss[j] = fmaf(x, x, ss[j]);
                 }
-                h = make_uint4(ho[0], ho[1], ho[2], ho[3]);
-                l = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-#if XM3D_PL_RAW_HI
-                // the tensor core ignores the 13 low mantissa bits of a tf32 operand: the raw tile IS its hi
-                // part, and not writing it back saves a third of the converter's shared-memory traffic
-                (void)h; (void)hi;
-#else
-                hi[q] = h;
-#endif
-                lo[q] = l;
+                uint2 pk;
+                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk.x) : "f"(l[1]), "f"(l[0]));
+                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk.y) : "f"(l[3]), "f"(l[2]));
+                // logical chunk (channels 4 lc .. 4 lc + 3) behind the 128-byte swizzle of the raw tile, then its place in
+                // the 64-byte-swizzled bf16 row: 16-byte chunk lc >> 1 (xor (row >> 1) & 3), 8-byte half lc & 1
+                const int row = q >> 3, lc = (q & 7) ^ (row & 7);
+                *reinterpret_cast<uint2 *>(lo + row * 64 + ((((lc >> 1) ^ ((row >> 1) & 3))) << 4) + (lc & 1) * 8) = pk;
             }
             // generic-proxy writes -> visible to the tensor core's async proxy, then signal
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -456,13 +480,15 @@ point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 using namespace xm3d;
 
 static int launch_point_logits(const float *feat, int64_t rows, int c, const float *b_hi, const float *b_lo,
-                               const float *inv_b, int n_cols, PointLogitsParams P, cudaStream_t stream, const char *who);
+                               const unsigned short *b_bf, const float *inv_b, int n_cols, PointLogitsParams P,
+                               cudaStream_t stream, const char *who);
 
 extern "C" size_t xm3d_logits_ws_bytes(int64_t rows, int32_t n_text, int32_t c, int32_t n_groups) {
     (void)rows;
     Carver cv(nullptr);
     cv.take<float>((size_t)(n_text + 1) * c);
     cv.take<float>((size_t)(n_text + 1) * c);
+    cv.take<unsigned short>((size_t)(n_text + 1) * ((c + 7) / 8 * 8));
     cv.take<float>((size_t)(n_text + 1));
     cv.take<int>((size_t)n_groups + 2);
     return cv.off + 256;
@@ -489,8 +515,10 @@ extern "C" int xm3d_logits(const float *mask_embed, int64_t rows, int32_t c, con
     }
     const int n_cols = n_text + 1;                        // the null embedding is one more column, its own group
     Carver cv(ws);
+    const int ld_bf = (c + 7) / 8 * 8;
     float *b_hi = cv.take<float>((size_t)n_cols * c);
     float *b_lo = cv.take<float>((size_t)n_cols * c);
+    unsigned short *b_bf = cv.take<unsigned short>((size_t)n_cols * ld_bf);
     float *inv_b = cv.take<float>((size_t)n_cols);
     int *goff = cv.take<int>((size_t)n_groups + 2);
     int host_off[512];
@@ -498,19 +526,20 @@ extern "C" int xm3d_logits(const float *mask_embed, int64_t rows, int32_t c, con
     host_off[n_groups + 1] = n_cols;
     // (pageable source: the copy is staged by the driver before the call returns)
     cudaMemcpyAsync(goff, host_off, sizeof(int) * (n_groups + 2), cudaMemcpyHostToDevice, stream);
-    logits_prep_kernel<<<(unsigned)((n_cols + 7) / 8), 256, 0, stream>>>(text_embed, null_embed, n_text, 1, c, b_hi, b_lo, inv_b);
+    logits_prep_kernel<<<(unsigned)((n_cols + 7) / 8), 256, 0, stream>>>(text_embed, null_embed, n_text, 1, c, b_hi, b_lo, b_bf, ld_bf, inv_b);
     count_launches(1);
     PointLogitsParams P;
     memset(&P, 0, sizeof(P));
     P.scale = logit_scale; P.out = out; P.argmax = argmax;
     P.group_off = goff; P.n_groups = n_groups + 1; P.ensemble_mean = ensemble_mean;
-    return launch_point_logits(mask_embed, rows, c, b_hi, b_lo, inv_b, n_cols, P, stream, "xm3d_logits");
+    return launch_point_logits(mask_embed, rows, c, b_hi, b_lo, b_bf, inv_b, n_cols, P, stream, "xm3d_logits");
 }
 
 extern "C" size_t xm3d_point_logits_ws_bytes(int32_t n_text, int32_t c) {
     Carver cv(nullptr);
     cv.take<float>((size_t)n_text * c);
     cv.take<float>((size_t)n_text * c);
+    cv.take<unsigned short>((size_t)n_text * ((c + 7) / 8 * 8));
     cv.take<float>((size_t)n_text);
     return cv.off + 256;
 }
@@ -535,27 +564,31 @@ extern "C" int xm3d_point_logits(const float *feat, int64_t rows, int32_t c, con
         return XM3D_ERR_WORKSPACE;
     }
     Carver cv(ws);
+    const int ld_bf = (c + 7) / 8 * 8;
     float *b_hi = cv.take<float>((size_t)n_text * c);
     float *b_lo = cv.take<float>((size_t)n_text * c);
+    unsigned short *b_bf = cv.take<unsigned short>((size_t)n_text * ld_bf);
     float *inv_b = cv.take<float>((size_t)n_text);
-    logits_prep_kernel<<<(unsigned)((n_text + 7) / 8), 256, 0, stream>>>(text_embed, nullptr, n_text, 0, c, b_hi, b_lo, inv_b);
+    logits_prep_kernel<<<(unsigned)((n_text + 7) / 8), 256, 0, stream>>>(text_embed, nullptr, n_text, 0, c, b_hi, b_lo, b_bf, ld_bf, inv_b);
     count_launches(1);
 
     PointLogitsParams P;
     memset(&P, 0, sizeof(P));
     P.scale = logit_scale; P.binary = binary; P.is_base = is_base; P.out = out; P.argmax = argmax;
     P.mask_label = mask_label; P.mask_probs = mask_probs; P.n_masks = n_masks; P.base_ratio = base_ratio; P.novel_ratio = novel_ratio;
-    return launch_point_logits(feat, rows, c, b_hi, b_lo, inv_b, n_text, P, stream, "xm3d_point_logits");
+    return launch_point_logits(feat, rows, c, b_hi, b_lo, b_bf, inv_b, n_text, P, stream, "xm3d_point_logits");
 }
 
 static int launch_point_logits(const float *feat, int64_t rows, int c, const float *b_hi, const float *b_lo,
-                               const float *inv_b, int n_text, PointLogitsParams P, cudaStream_t stream, const char *who) {
+                               const unsigned short *b_bf, const float *inv_b, int n_text, PointLogitsParams P,
+                               cudaStream_t stream, const char *who) {
     P.rows = rows; P.c = c; P.n_text = n_text; P.bn = (n_text + 15) / 16 * 16; P.inv_norm_b = inv_b;
     P.fused = (2 * P.bn <= 256) ? 1 : 0;
     int tc = 32;
     while (tc < (P.fused ? 2 * P.bn : P.bn)) tc <<= 1;
     P.acc_cols = tc;
-    const size_t stage_bytes = 2 * (size_t)LG_BM * LG_BK * 4 + 2 * (size_t)P.bn * LG_BK * 4;
+    // A raw + A lo (bf16) + B hi + B lo (tf32) + B (bf16)
+    const size_t stage_bytes = (size_t)LG_BM * LG_BK * 6 + (size_t)P.bn * LG_BK * 10;
     // two CTAs per SM when two stages of each fit (the second CTA's TMA / MMA hides the first one's
     // conversion pass), else one CTA with as many stages as fit
     int stages = (int)((108 * 1024) / stage_bytes);
@@ -568,9 +601,9 @@ static int launch_point_logits(const float *feat, int64_t rows, int c, const flo
     const int ctas_per_sm = (stage_bytes * (size_t)stages + 1024 <= 110 * 1024) ? 2 : 1;
     P.nbuf = (ctas_per_sm * 2 * tc <= 512) ? 2 : 1;
     P.tmem_cols = P.nbuf * tc;
-    CUtensorMap ma, mbh, mbl;
+    CUtensorMap ma, mbh, mbl, mbf;
     if (!make_map(&ma, feat, rows, c, LG_BM) || !make_map(&mbh, b_hi, n_text, c, P.bn) ||
-        !make_map(&mbl, b_lo, n_text, c, P.bn)) {
+        !make_map(&mbl, b_lo, n_text, c, P.bn) || !make_map_bf16_sw64(&mbf, b_bf, n_text, (c + 7) / 8 * 8, P.bn)) {
         set_error("%s: cuTensorMapEncodeTiled failed", who);
         return XM3D_ERR_CUDA;
     }
@@ -586,10 +619,10 @@ static int launch_point_logits(const float *feat, int64_t rows, int c, const flo
     const unsigned grid = (unsigned)(n_tiles < slots ? n_tiles : slots);
     const size_t smem = stage_bytes * stages + 1024;
     switch ((P.mask_label ? 1 : 0) | (P.group_off ? 2 : 0)) {
-        case 0: point_logits_kernel<0><<<grid, PL_THREADS, smem, stream>>>(ma, mbh, mbl, P); break;
-        case 1: point_logits_kernel<1><<<grid, PL_THREADS, smem, stream>>>(ma, mbh, mbl, P); break;
-        case 2: point_logits_kernel<2><<<grid, PL_THREADS, smem, stream>>>(ma, mbh, mbl, P); break;
-        default: point_logits_kernel<3><<<grid, PL_THREADS, smem, stream>>>(ma, mbh, mbl, P); break;
+        case 0: point_logits_kernel<0><<<grid, PL_THREADS, smem, stream>>>(ma, mbh, mbl, mbf, P); break;
+        case 1: point_logits_kernel<1><<<grid, PL_THREADS, smem, stream>>>(ma, mbh, mbl, mbf, P); break;
+        case 2: point_logits_kernel<2><<<grid, PL_THREADS, smem, stream>>>(ma, mbh, mbl, mbf, P); break;
+        default: point_logits_kernel<3><<<grid, PL_THREADS, smem, stream>>>(ma, mbh, mbl, mbf, P); break;
     }
     count_launches(1);
     return check_launch(who);
