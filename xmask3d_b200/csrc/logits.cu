@@ -399,11 +399,12 @@ point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 if (P.fused) tmem_ld16(trow + (uint32_t)(P.bn + c0), v2);
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
-                    if (c0 + j < P.n_text) ssum += expf(logit_of(v, v2, j, c0 + j) - smax);
+                    if (c0 + j < P.n_text) ssum += __expf(logit_of(v, v2, j, c0 + j) - smax);   // ex2.approx: ~1e-6 relative
             }
         }
         const float lsum = ENS ? logf(ssum) : 0.f;
         const bool any_unlabelled = ENS && __any_sync(0xffffffffu, label < 0);
+        const float inv_ssum = ENS ? __fdiv_rn(1.0f, ssum) : 0.f;
         float best = -INFINITY;
         float gacc = P.ensemble_mean ? 0.f : -INFINITY;
         int best_i = 0;
@@ -429,7 +430,7 @@ point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         const float ratio = s_base[col] ? P.base_ratio : P.novel_ratio;
                         const float ens = fmaf(ratio, logp, (1.f - ratio) * logq);
                         if (any_unlabelled) {
-                            const float prob = __fdiv_rn(expf(val - smax), ssum);            // class probability
+                            const float prob = __expf(val - smax) * inv_ssum;                // class probability
                             val = label >= 0 ? ens : prob;
                         } else {
                             val = ens;
