@@ -249,8 +249,9 @@ point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
+        // ===== MMA issuer: the whole warp runs the loop (warp-uniform operands stay in uniform registers), one elected lane
+        // issues; from inside `if (lane == 0)` every MMA sits in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop =====
+        {
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(P.bn >> 3) << 17) |
                                    ((uint32_t)(LG_BM >> 4) << 24);
             const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * P.bn) >> 3) << 17) |
@@ -273,6 +274,7 @@ point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 const uint64_t b_hi = make_sw128_desc(st + a_bytes + alo_bytes);
                 const uint64_t b_lo = make_sw128_desc(st + a_bytes + alo_bytes + b_bytes);
                 const uint64_t b_bf = make_sw128_desc_ex(st + a_bytes + alo_bytes + 2 * b_bytes, 0, 512, 4);
+                if (elect_one_sync()) {
                 if (P.fused) {
                     // B_hi and B_lo are adjacent 8-row-group aligned tiles: one N = 2 bn operand.  Columns
                     // [0, bn) accumulate hi*hi (+ lo*b below), columns [bn, 2 bn) hi*lo; the epilogue adds them.
@@ -296,9 +298,11 @@ point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     umma_f16(tmem_acc, a_lo + adv, b_bf + adv, idesc_bf, 1u);
                 }
                 umma_commit(&s_empty[stage]);
+                if (kb == nkb - 1) umma_commit(&s_done[buf]);
+                }
+                __syncwarp();
                 if (++stage == P.stages) { stage = 0; phase ^= 1; }
             }
-            umma_commit(&s_done[buf]);
             if (++buf == P.nbuf) { buf = 0; bph ^= 1; }
             }
         }
