@@ -157,7 +157,8 @@ struct PointLogitsParams {
     int *argmax;                 // [rows] or null
     // synonym-group reduction of cal_pred_logits (helper.py:72-97): column groups [group_off[g], group_off[g+1]) are
     // reduced (max / mean) to one output column; null: one output column per text row
-    const int *group_off;        // device [n_groups + 1] or null
+    int grouped;                 // 1: goff holds the group offsets
+    unsigned short goff[LG_MAX_N + 2];   // [n_groups + 1] column offsets, in the kernel parameters (no copy, no workspace)
     int n_groups, ensemble_mean;
 };
 
@@ -194,10 +195,10 @@ point_logits_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         s_gid[j] = 0;
         s_glen[j] = 0;
     }
-    if (P.group_off) {
+    if (P.grouped) {
         __syncthreads();
         for (int g = tid; g < P.n_groups; g += PL_THREADS) {
-            const int lo = P.group_off[g], hi = P.group_off[g + 1];
+            const int lo = P.goff[g], hi = P.goff[g + 1];
             for (int j = lo; j < hi && j < LG_MAX_N; ++j) s_gid[j] = (short)g;
             if (hi > lo && hi - 1 < LG_MAX_N) s_glen[hi - 1] = (short)(hi - lo);
         }
@@ -525,18 +526,15 @@ extern "C" int xm3d_logits(const float *mask_embed, int64_t rows, int32_t c, con
     float *b_lo = cv.take<float>((size_t)n_cols * c);
     unsigned short *b_bf = cv.take<unsigned short>((size_t)n_cols * ld_bf);
     float *inv_b = cv.take<float>((size_t)n_cols);
-    int *goff = cv.take<int>((size_t)n_groups + 2);
-    int host_off[512];
-    for (int g = 0; g <= n_groups; ++g) host_off[g] = group_off_host[g];
-    host_off[n_groups + 1] = n_cols;
-    // (pageable source: the copy is staged by the driver before the call returns)
-    cudaMemcpyAsync(goff, host_off, sizeof(int) * (n_groups + 2), cudaMemcpyHostToDevice, stream);
+    cv.take<int>((size_t)n_groups + 2);                   // (kept in the workspace layout; the offsets travel as kernel parameters)
     logits_prep_kernel<<<(unsigned)((n_cols + 7) / 8), 256, 0, stream>>>(text_embed, null_embed, n_text, 1, c, b_hi, b_lo, b_bf, ld_bf, inv_b);
     count_launches(1);
     PointLogitsParams P;
     memset(&P, 0, sizeof(P));
     P.scale = logit_scale; P.out = out; P.argmax = argmax;
-    P.group_off = goff; P.n_groups = n_groups + 1; P.ensemble_mean = ensemble_mean;
+    P.grouped = 1; P.n_groups = n_groups + 1; P.ensemble_mean = ensemble_mean;
+    for (int g = 0; g <= n_groups; ++g) P.goff[g] = (unsigned short)group_off_host[g];
+    P.goff[n_groups + 1] = (unsigned short)n_cols;         // the null embedding: one more column, its own group
     return launch_point_logits(mask_embed, rows, c, b_hi, b_lo, b_bf, inv_b, n_cols, P, stream, "xm3d_logits");
 }
 
@@ -623,7 +621,7 @@ static int launch_point_logits(const float *feat, int64_t rows, int c, const flo
     const int64_t slots = (int64_t)sm_count() * ctas_per_sm;
     const unsigned grid = (unsigned)(n_tiles < slots ? n_tiles : slots);
     const size_t smem = stage_bytes * stages + 1024;
-    switch ((P.mask_label ? 1 : 0) | (P.group_off ? 2 : 0)) {
+    switch ((P.mask_label ? 1 : 0) | (P.grouped ? 2 : 0)) {
         case 0: point_logits_kernel<0><<<grid, PL_THREADS, smem, stream>>>(ma, mbh, mbl, mbf, P); break;
         case 1: point_logits_kernel<1><<<grid, PL_THREADS, smem, stream>>>(ma, mbh, mbl, mbf, P); break;
         case 2: point_logits_kernel<2><<<grid, PL_THREADS, smem, stream>>>(ma, mbh, mbl, mbf, P); break;
